@@ -1,0 +1,242 @@
+/*
+ * vtmgpu.h -- C ABI of libvtmgpu: the B200-native (sm_100a CUDA) implementation of the VVC
+ * decoder in-loop filter chain  deblocking -> SAO -> ALF / CC-ALF.
+ *
+ * This is the drop-in boundary of SURVEY.md section 8(b): plain pointers and sizes, no C++/VTM/torch
+ * types.  The reference interfaces each entry point stands behind (paths relative to the reference
+ * tree, VTM 7.3+ snapshot):
+ *
+ *   vtmgpu_create / vtmgpu_destroy      LoopFilter::create/destroy            CommonLib/LoopFilter.cpp:111,130
+ *                                        SampleAdaptiveOffset::create/destroy  CommonLib/SampleAdaptiveOffset.cpp:127,143
+ *                                        AdaptiveLoopFilter::create/destroy    CommonLib/AdaptiveLoopFilter.cpp:715,816
+ *   vtmgpu_upload / vtmgpu_download     Picture::getRecoBuf() planes          CommonLib/Picture.cpp:317  (PelStorage, int16 Pel)
+ *   vtmgpu_set_deblock + vtmgpu_deblock LoopFilter::loopFilterPic             CommonLib/LoopFilter.cpp:145
+ *                                        (edge filtering xEdgeFilterLuma :844, xEdgeFilterChroma :1087; the per-4x4
+ *                                        bS / tc / beta / filter-length DERIVATION :261-812 stays on the host and arrives
+ *                                        here as packed segment records)
+ *   vtmgpu_sao_reconstruct              SampleAdaptiveOffset::xReconstructBlkSAOParams   SampleAdaptiveOffset.cpp:266
+ *   vtmgpu_set_sao + vtmgpu_sao         SampleAdaptiveOffset::SAOProcess      CommonLib/SampleAdaptiveOffset.cpp:618
+ *   vtmgpu_set_alf + vtmgpu_alf         AdaptiveLoopFilter::ALFProcess        CommonLib/AdaptiveLoopFilter.cpp:393
+ *                                        (incl. reconstructCoeffAPSs :620, deriveClassificationBlk :873, filterBlk :1084,
+ *                                        filterBlkCcAlf :1327)
+ *   vtmgpu_filter                       DecLib::executeLoopFilters            DecoderLib/DecLib.cpp:560  (whole chain, batched)
+ *
+ * Error convention: every call returns 0 on success, non-zero on failure; vtmgpu_last_error() gives the text
+ * (the reference throws Exception via THROW/CHECK, TypeDef.h:1152 -- the C++ shim converts non-zero to THROW).
+ * There is NO CPU fallback: without a CUDA device vtmgpu_create fails.
+ *
+ * Threading: one ctx per decoder (DecLib owns one filter object of each kind, DecLib.h:97-99); a ctx is not
+ * thread-safe; calls are synchronous unless the name ends in _async.
+ *
+ * Pictures live in "slots" (0 .. capacity-1) so that a batch of independent pictures can be filtered by one
+ * launch sequence (picture-parallel replay); the decoder drop-in uses slot 0.
+ */
+#ifndef VTMGPU_H
+#define VTMGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VTMGPU_ABI_VERSION 1
+
+/* chroma_format values follow ChromaFormat (TypeDef.h): 0 = 4:0:0, 1 = 4:2:0, 2 = 4:2:2, 3 = 4:4:4 */
+typedef struct vtmgpu_seq_params
+{
+  int32_t width;             /* luma samples, multiple of 8 */
+  int32_t height;            /* luma samples, multiple of 8 */
+  int32_t chroma_format;
+  int32_t bit_depth_luma;    /* 8..12 */
+  int32_t bit_depth_chroma;  /* 8..12 */
+  int32_t ctu_size;          /* 32, 64 or 128 (sps CTUSize) */
+  int32_t capacity;          /* number of picture slots (>= 1) */
+  int32_t device;            /* CUDA device ordinal */
+} vtmgpu_seq_params;
+
+/* ---------------------------------------------------------------------------------------------
+ * Deblocking segment records.  One record describes one 4-luma-sample long
+ * piece of one edge.  A record of 0 means "do not filter".
+ *
+ * luma  (uint32), one per 4x4 luma unit and direction; the record at unit (ux,uy) describes the edge on
+ *        the LEFT side (dir 0 = EDGE_VER) or TOP side (dir 1 = EDGE_HOR) of that unit:
+ *   bits  0-10  tc      (LoopFilter.cpp:974, already scaled to the bit depth; 0 = edge not filtered)
+ *   bits 11-21  beta    (:975)
+ *   bits 22-24  maxFilterLengthP (:948, after the cuP.affine clamp :953-960)   1,2,3,5,7
+ *   bits 25-27  maxFilterLengthQ (:949)
+ *   bit  28     bPartPNoFilter  (P side is palette coded, :1017)
+ *   bit  29     bPartQNoFilter
+ *   bit  30     horizontal edge on a CTU-row boundary: sidePisLarge forced false (:967-970)
+ *   array: dbf_luma[dir][(y/4) * (width/4) + x/4]
+ *
+ * chroma (uint64), only for edges on the 8x8 chroma-sample grid (:1118-1126); one record covers the
+ *        chroma samples belonging to one 4-luma-sample unit along the edge, both Cb and Cr:
+ *   bits  0-10  tc  Cb   (0 = Cb not filtered)      bits 11-21  tc  Cr
+ *   bits 22-32  beta Cb                              bits 33-43  beta Cr
+ *   bit  44     largeBoundary (both filter lengths >= 3, :1202)
+ *   bit  45     isChromaHorCTBBoundary (:1207)
+ *   bit  46     bPartPNoFilter     bit 47  bPartQNoFilter
+ *   dir 0 array: [(y/4) * cols0 + x/(8<<sx)],  cols0 = ceil(width  / (8<<sx))
+ *   dir 1 array: [(y/(8<<sy)) * (width/4) + x/4], rows1 = ceil(height / (8<<sy))
+ *   (x,y in luma samples; sx,sy = chroma subsampling shifts)
+ * --------------------------------------------------------------------------------------------- */
+#define VTMGPU_DBF_TC_BITS      11
+#define VTMGPU_DBF_L_BETA_SHIFT 11
+#define VTMGPU_DBF_L_LENP_SHIFT 22
+#define VTMGPU_DBF_L_LENQ_SHIFT 25
+#define VTMGPU_DBF_L_PNOFILT    (1u << 28)
+#define VTMGPU_DBF_L_QNOFILT    (1u << 29)
+#define VTMGPU_DBF_L_CTUROW     (1u << 30)
+#define VTMGPU_DBF_C_TCCR_SHIFT   11
+#define VTMGPU_DBF_C_BETACB_SHIFT 22
+#define VTMGPU_DBF_C_BETACR_SHIFT 33
+#define VTMGPU_DBF_C_LARGE      (1ull << 44)
+#define VTMGPU_DBF_C_CTB        (1ull << 45)
+#define VTMGPU_DBF_C_PNOFILT    (1ull << 46)
+#define VTMGPU_DBF_C_QNOFILT    (1ull << 47)
+
+typedef struct vtmgpu_deblock_params
+{
+  const uint32_t* luma[2];     /* [dir] width/4 * height/4 records                         */
+  const uint64_t* chroma[2];   /* [dir] see above; NULL for 4:0:0                            */
+} vtmgpu_deblock_params;
+
+/* ---------------------------------------------------------------------------------------------
+ * SAO (SAOOffset / SAOBlkParam, TypeDef.h:938-963; enums :706-748)
+ * --------------------------------------------------------------------------------------------- */
+enum { VTMGPU_SAO_MODE_OFF = 0, VTMGPU_SAO_MODE_NEW = 1, VTMGPU_SAO_MODE_MERGE = 2 };
+enum { VTMGPU_SAO_EO_0 = 0, VTMGPU_SAO_EO_90 = 1, VTMGPU_SAO_EO_135 = 2, VTMGPU_SAO_EO_45 = 3, VTMGPU_SAO_BO = 4 };
+enum { VTMGPU_SAO_MERGE_LEFT = 0, VTMGPU_SAO_MERGE_ABOVE = 1 };
+
+typedef struct vtmgpu_sao_offset
+{
+  int8_t  mode;         /* VTMGPU_SAO_MODE_*                                            */
+  int8_t  type;         /* NEW: VTMGPU_SAO_EO_* / BO;  MERGE: VTMGPU_SAO_MERGE_*         */
+  int8_t  aux;          /* BO: first band (typeAuxInfo)                                   */
+  int8_t  reserved;
+  int16_t offset[32];   /* as parsed (CABACReader.cpp:318); after reconstruct: scaled    */
+} vtmgpu_sao_offset;
+
+/* neighbour-CTU availability bits for the EO classes (deriveLoopFilterBoundaryAvailibility, :668) */
+#define VTMGPU_AVAIL_LEFT        0x01
+#define VTMGPU_AVAIL_RIGHT       0x02
+#define VTMGPU_AVAIL_ABOVE       0x04
+#define VTMGPU_AVAIL_BELOW       0x08
+#define VTMGPU_AVAIL_ABOVE_LEFT  0x10
+#define VTMGPU_AVAIL_ABOVE_RIGHT 0x20
+#define VTMGPU_AVAIL_BELOW_LEFT  0x40
+#define VTMGPU_AVAIL_BELOW_RIGHT 0x80
+
+typedef struct vtmgpu_sao_ctu
+{
+  vtmgpu_sao_offset comp[3];
+  uint8_t avail;             /* VTMGPU_AVAIL_* of the 8 neighbouring CTUs                               */
+  uint8_t merge_left_ok;     /* left  CTU usable as merge candidate (getMergeList, :173: same slice+tile) */
+  uint8_t merge_above_ok;
+  uint8_t reserved;
+} vtmgpu_sao_ctu;
+
+typedef struct vtmgpu_sao_params
+{
+  const vtmgpu_sao_ctu* ctu;   /* [ctus], raster; ALREADY reconstructed (vtmgpu_sao_reconstruct)    */
+  int32_t num_ctus;
+} vtmgpu_sao_params;
+
+/* ---------------------------------------------------------------------------------------------
+ * ALF / CC-ALF (AlfParam / CcAlfFilterParam, AlfParameters.h:133-287)
+ * --------------------------------------------------------------------------------------------- */
+#define VTMGPU_ALF_CLASSES        25
+#define VTMGPU_ALF_LUMA_COEFF     13
+#define VTMGPU_ALF_CHROMA_COEFF   7
+#define VTMGPU_ALF_MAX_APS        8
+#define VTMGPU_ALF_MAX_ALTS       8
+#define VTMGPU_ALF_FIXED_SETS     16
+#define VTMGPU_CCALF_MAX_FILTERS  4
+#define VTMGPU_CCALF_COEFF        8
+
+typedef struct vtmgpu_alf_luma_aps   /* the luma part of one ALF APS as parsed (VLCReader.cpp:837) */
+{
+  int32_t num_filters;                                                  /* numLumaFilters          */
+  int32_t nonlinear;                                                    /* nonLinearFlag[LUMA]     */
+  int16_t delta_idx[VTMGPU_ALF_CLASSES];                                /* filterCoeffDeltaIdx     */
+  int16_t coeff[VTMGPU_ALF_CLASSES][VTMGPU_ALF_LUMA_COEFF];             /* lumaCoeff               */
+  int16_t clip_idx[VTMGPU_ALF_CLASSES][VTMGPU_ALF_LUMA_COEFF];          /* lumaClipp (index 0..3)  */
+} vtmgpu_alf_luma_aps;
+
+typedef struct vtmgpu_alf_chroma_aps
+{
+  int32_t num_alts;                                                     /* numAlternativesChroma   */
+  int32_t nonlinear;                                                    /* nonLinearFlag[CHROMA]   */
+  int16_t coeff[VTMGPU_ALF_MAX_ALTS][VTMGPU_ALF_CHROMA_COEFF];
+  int16_t clip_idx[VTMGPU_ALF_MAX_ALTS][VTMGPU_ALF_CHROMA_COEFF];
+} vtmgpu_alf_chroma_aps;
+
+typedef struct vtmgpu_alf_params
+{
+  int32_t enabled[3];                   /* slice getTileGroupAlfEnabledFlag(Y/Cb/Cr) (AdaptiveLoopFilter.cpp:429) */
+  int32_t num_luma_aps;                 /* slice getTileGroupNumAps()                                          */
+  const vtmgpu_alf_luma_aps*   luma_aps;     /* [num_luma_aps], in getTileGroupApsIdLuma() order               */
+  const vtmgpu_alf_chroma_aps* chroma_aps;   /* APS getTileGroupApsIdChroma(), or NULL                         */
+  const uint8_t* ctu_enable[3];         /* Picture::getAlfCtuEnableFlag(comp)  [ctus]                          */
+  const int16_t* ctu_filter_idx;        /* Picture::getAlfCtbFilterIndex()     [ctus] (<16 fixed, else APS)    */
+  const uint8_t* ctu_alt[2];            /* Picture::getAlfCtuAlternativeData(Cb/Cr) [ctus]                     */
+  int32_t ccalf_enabled[2];             /* CcAlfFilterParam::ccAlfFilterEnabled                                */
+  int16_t ccalf_coeff[2][VTMGPU_CCALF_MAX_FILTERS][VTMGPU_CCALF_COEFF];
+  const uint8_t* ccalf_idc[2];          /* m_ccAlfFilterControl[comp-1] [ctus]; 0 = off, k = filter k-1        */
+  int32_t num_ctus;
+} vtmgpu_alf_params;
+
+/* ---------------------------------------------------------------------------------------------
+ * entry points
+ * --------------------------------------------------------------------------------------------- */
+typedef struct vtmgpu_ctx vtmgpu_ctx;
+
+int          vtmgpu_abi_version(void);
+const char*  vtmgpu_last_error(const vtmgpu_ctx* ctx);   /* ctx may be NULL: error of the last failed create */
+
+int  vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out);
+void vtmgpu_destroy(vtmgpu_ctx* ctx);
+
+/* host planes (int16 samples, stride in samples) <-> device slot; plane[1], plane[2] ignored for 4:0:0 */
+int vtmgpu_upload  (vtmgpu_ctx* ctx, int slot, const int16_t* const plane[3], const ptrdiff_t stride[3]);
+int vtmgpu_download(vtmgpu_ctx* ctx, int slot, int16_t* const plane[3], const ptrdiff_t stride[3]);
+
+/* per-picture side information (host pointers; copied before return, never retained) */
+int vtmgpu_set_deblock(vtmgpu_ctx* ctx, int slot, const vtmgpu_deblock_params* p);   /* NULL = stage off */
+int vtmgpu_set_sao    (vtmgpu_ctx* ctx, int slot, const vtmgpu_sao_params* p);       /* NULL = stage off */
+int vtmgpu_set_alf    (vtmgpu_ctx* ctx, int slot, const vtmgpu_alf_params* p);       /* NULL = stage off */
+
+/* host-only helper: resolves MERGE / scales NEW offsets in place, raster order
+ * (xReconstructBlkSAOParams, SampleAdaptiveOffset.cpp:266-290).  Returns <0 on error, else a 3-bit mask
+ * of the components that have any CTU with SAO on (m_picSAOEnabled). */
+int vtmgpu_sao_reconstruct(vtmgpu_sao_ctu* ctu, int num_ctus, int width_in_ctus, int num_comps,
+                           int log2_offset_scale_luma, int log2_offset_scale_chroma);
+
+/* stages on slots [first, first+count): synchronous, in place from the caller's point of view */
+int vtmgpu_deblock(vtmgpu_ctx* ctx, int first, int count);   /* loopFilterPic                              */
+int vtmgpu_sao    (vtmgpu_ctx* ctx, int first, int count);   /* SAOProcess (no-op where SAO is off)        */
+int vtmgpu_alf    (vtmgpu_ctx* ctx, int first, int count);   /* ALFProcess                                 */
+int vtmgpu_sao_alf(vtmgpu_ctx* ctx, int first, int count);   /* SAOProcess + ALFProcess in one fused pass  */
+/* whole chain DBF -> SAO -> ALF with SAO fused into the ALF pass; same result as the three calls above */
+int vtmgpu_filter (vtmgpu_ctx* ctx, int first, int count);
+
+/* replay/benchmark support: enqueue the whole chain on the ctx stream without synchronising; timing by
+ * CUDA events recorded on that same stream */
+int vtmgpu_filter_async(vtmgpu_ctx* ctx, int first, int count);
+int vtmgpu_sync(vtmgpu_ctx* ctx);
+int vtmgpu_timer_start(vtmgpu_ctx* ctx);                 /* records an event on the ctx stream          */
+int vtmgpu_timer_stop (vtmgpu_ctx* ctx, float* ms);      /* records + synchronises, elapsed ms          */
+/* restores slot's working planes from its pristine uploaded copy (device-to-device) so a replay can repeat */
+int vtmgpu_rewind(vtmgpu_ctx* ctx, int first, int count);
+/* number of kernel launches issued by this ctx so far (bench.py "gpu_launches") */
+int64_t vtmgpu_launch_count(const vtmgpu_ctx* ctx);
+/* per-stage device time of the last vtmgpu_filter* call when profiling was enabled (ms; 0 = dbf,1 = sao+alf) */
+int vtmgpu_set_profiling(vtmgpu_ctx* ctx, int on);
+int vtmgpu_stage_ms(vtmgpu_ctx* ctx, float ms[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VTMGPU_H */

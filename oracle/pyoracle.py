@@ -1,0 +1,107 @@
+"""oracle/pyoracle.py -- TEST INFRASTRUCTURE: ctypes front end of oracle/_build/libvvcoracle.so, the plain-C
+restatement of the reference filter arithmetic (oracle/vvc_filters_oracle.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import this module --
+as the checker or the CPU baseline, never on the product path.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from vvc_b200 import abi  # noqa: E402
+
+LIB_PATH = os.path.join(HERE, "_build", "libvvcoracle.so")
+
+
+def build(force=False):
+    src = os.path.join(HERE, "vvc_filters_oracle.c")
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+        os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+        subprocess.run(["gcc", "-std=c11", "-O2", "-fPIC", "-shared", "-Wall", "-I", os.path.join(HERE, "..", "include"),
+                        "-o", LIB_PATH, src], check=True)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        common = [abi.PlanePtrs, abi.Strides, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        _lib.vvco_deblock.argtypes = common + [C.POINTER(abi.DeblockParams)]
+        _lib.vvco_sao.argtypes = common + [C.c_int, C.POINTER(abi.SaoParams)]
+        _lib.vvco_alf.argtypes = common + [C.c_int, C.POINTER(abi.AlfParams)]
+        _lib.vvco_sao_reconstruct.argtypes = [C.POINTER(abi.SaoCtu), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        _lib.vvco_filter_picture.argtypes = common + [C.c_int, C.POINTER(abi.DeblockParams), C.POINTER(abi.SaoParams), C.POINTER(abi.AlfParams)]
+    return _lib
+
+
+def _planes(planes):
+    ptrs, strides = abi.PlanePtrs(), abi.Strides()
+    for c, p in enumerate(planes):
+        assert p.dtype == np.int16 and p.flags["C_CONTIGUOUS"]
+        ptrs[c] = p.ctypes.data_as(C.POINTER(C.c_int16))
+        strides[c] = p.shape[1]
+    return ptrs, strides
+
+
+def _seq(seq):
+    return [seq["width"], seq["height"], seq["chroma_format"], seq["bit_depth_luma"], seq["bit_depth_chroma"]]
+
+
+def deblock(seq, planes, dbf_params):
+    """In place on the list of int16 planes."""
+    ptrs, strides = _planes(planes)
+    rc = lib().vvco_deblock(ptrs, strides, *_seq(seq), C.byref(dbf_params))
+    if rc:
+        raise RuntimeError("vvco_deblock rc=%d" % rc)
+
+
+def sao_reconstruct(ctus, width_in_ctus, ncomp, scale_luma, scale_chroma):
+    rc = lib().vvco_sao_reconstruct(ctus, len(ctus), width_in_ctus, ncomp, scale_luma, scale_chroma)
+    if rc < 0:
+        raise RuntimeError("vvco_sao_reconstruct rc=%d" % rc)
+    return rc
+
+
+def sao(seq, planes, ctus):
+    """ctus: RECONSTRUCTED (abi.SaoCtu * n)."""
+    ptrs, strides = _planes(planes)
+    p = abi.SaoParams(C.cast(ctus, C.POINTER(abi.SaoCtu)), len(ctus))
+    rc = lib().vvco_sao(ptrs, strides, *_seq(seq), seq["ctu_size"], C.byref(p))
+    if rc:
+        raise RuntimeError("vvco_sao rc=%d" % rc)
+
+
+def alf(seq, planes, alf_params):
+    ptrs, strides = _planes(planes)
+    rc = lib().vvco_alf(ptrs, strides, *_seq(seq), seq["ctu_size"], C.byref(alf_params))
+    if rc:
+        raise RuntimeError("vvco_alf rc=%d" % rc)
+
+
+def filter_capture(cap, stages=("dbf", "sao", "alf")):
+    """Runs the chain of the oracle on a vvc_b200.capture.Capture; returns {stage: [planes]} after each stage."""
+    planes = [p.copy() for p in cap.pre]
+    out = {}
+    if "dbf" in stages:
+        deblock(cap.seq, planes, cap.deblock_params())
+        out["dbf"] = [p.copy() for p in planes]
+    ctus = cap.sao_ctus()
+    if "sao" in stages and ctus is not None:
+        sao_reconstruct(ctus, cap.width_in_ctus, cap.ncomp, cap.sao_scale[0], cap.sao_scale[1])
+        sao(cap.seq, planes, ctus)
+        out["sao"] = [p.copy() for p in planes]
+    ap = cap.alf_params()
+    if "alf" in stages and ap is not None:
+        alf(cap.seq, planes, ap)
+        out["alf"] = [p.copy() for p in planes]
+    out["final"] = planes
+    return out

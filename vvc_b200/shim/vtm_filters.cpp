@@ -1,0 +1,375 @@
+// vtm_filters.cpp -- the drop-in: OUR definitions of the entry points DecLib::executeLoopFilters needs from
+// LoopFilter / SampleAdaptiveOffset / AdaptiveLoopFilter (the 17 symbols of SURVEY.md 8b), compiled against the
+// reference's unmodified headers (class layouts stay identical, DecLib embeds the objects by value) and linked
+// INSTEAD of the reference's LoopFilter.cpp / SampleAdaptiveOffset.cpp / AdaptiveLoopFilter.cpp (+ the ALF SIMD stubs).
+//
+//   loopFilterPic : derive segment records on the host -> upload planes -> device deblocking
+//   SAOProcess    : reconstruct SAO params -> (deferred, fused into the ALF pass when the SPS enables ALF)
+//   ALFProcess    : flatten slice/APS/CTU data -> device SAO+ALF+CC-ALF -> download planes
+//
+// No sample is filtered on the CPU here.  If libvtmgpu cannot be loaded or any call fails the shim THROWs
+// (reference error convention, TypeDef.h:1152) -- there is no fallback.
+//
+// environment:
+//   VTMGPU_LIB=<path>           libvtmgpu.so to dlopen (default: libvtmgpu.so via rpath / LD_LIBRARY_PATH)
+//   VTMGPU_DEVICE=<n>           CUDA device ordinal (default 0)
+//   VTMGPU_STAGED=1             run and download stage by stage (no SAO+ALF fusion)
+//   VTMGPU_CAPTURE_DIR=<dir>    write one VTMGCAP1 file per picture (capture_format.h); implies staged
+//   VTMGPU_SHIM_BACKEND=ref     test binaries only: use the linked alternative backend (shim_backend.h)
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+#include "AdaptiveLoopFilter.h"
+#include "CodingStructure.h"
+#include "LoopFilter.h"
+#include "Picture.h"
+#include "SampleAdaptiveOffset.h"
+
+#include "capture_format.h"
+#include "shim_backend.h"
+#include "vtm_flatten.h"
+#include "vtmgpu.h"
+
+namespace
+{
+
+using namespace vtmshim;
+
+struct GpuApi
+{
+  void* so = nullptr;
+  decltype(&vtmgpu_abi_version) abi_version = nullptr;
+  decltype(&vtmgpu_last_error) last_error = nullptr;
+  decltype(&vtmgpu_create) create = nullptr;
+  decltype(&vtmgpu_destroy) destroy = nullptr;
+  decltype(&vtmgpu_upload) upload = nullptr;
+  decltype(&vtmgpu_download) download = nullptr;
+  decltype(&vtmgpu_set_deblock) set_deblock = nullptr;
+  decltype(&vtmgpu_set_sao) set_sao = nullptr;
+  decltype(&vtmgpu_set_alf) set_alf = nullptr;
+  decltype(&vtmgpu_sao_reconstruct) sao_reconstruct = nullptr;
+  decltype(&vtmgpu_deblock) deblock = nullptr;
+  decltype(&vtmgpu_sao) sao = nullptr;
+  decltype(&vtmgpu_alf) alf = nullptr;
+  decltype(&vtmgpu_sao_alf) sao_alf = nullptr;
+
+  void load()
+  {
+    if (so) return;
+    const char* path = getenv("VTMGPU_LIB");
+    so = dlopen(path ? path : "libvtmgpu.so", RTLD_NOW | RTLD_LOCAL);
+    if (!so) THROW("vtmgpu shim: cannot load libvtmgpu.so (" << dlerror() << ") -- no CPU fallback");
+#define SYM(n) n = reinterpret_cast<decltype(n)>(dlsym(so, "vtmgpu_" #n)); if (!n) THROW("vtmgpu shim: missing symbol vtmgpu_" #n)
+    SYM(abi_version); SYM(last_error); SYM(create); SYM(destroy); SYM(upload); SYM(download); SYM(set_deblock); SYM(set_sao);
+    SYM(set_alf); SYM(sao_reconstruct); SYM(deblock); SYM(sao); SYM(alf); SYM(sao_alf);
+#undef SYM
+    if (abi_version() != VTMGPU_ABI_VERSION) THROW("vtmgpu shim: ABI version mismatch");
+  }
+};
+
+struct Shim
+{
+  GpuApi api;
+  vtmgpu_ctx* ctx = nullptr;
+  vtmgpu_seq_params seq{};
+  bool useRef = false, staged = false, saoPending = false;
+  std::string captureDir;
+  int picCount = 0;
+  // per-picture
+  FlatDeblock dbf;
+  FlatSao sao;
+  FlatAlf alf;
+  CaptureWriter cap;
+  int saoLog2Scale[2] = { 0, 0 };
+
+  Shim()
+  {
+    const char* b = getenv("VTMGPU_SHIM_BACKEND");
+    useRef = b && std::string(b) == "ref";
+    if (useRef && (!vtmgpu_shim_alt_backend || !vtmgpu_shim_alt_backend())) THROW("vtmgpu shim: no alternative backend linked into this binary");
+    if (const char* d = getenv("VTMGPU_CAPTURE_DIR")) captureDir = d;
+    staged = !captureDir.empty() || (getenv("VTMGPU_STAGED") && atoi(getenv("VTMGPU_STAGED")));
+  }
+  ~Shim() { if (ctx) api.destroy(ctx); }
+
+  void check(int rc, const char* what) { if (rc) THROW("vtmgpu shim: " << what << " failed: " << (api.last_error ? api.last_error(ctx) : "?")); }
+
+  void ensureCtx(const CodingStructure& cs)
+  {
+    vtmgpu_seq_params s{};
+    s.width = cs.pcv->lumaWidth;
+    s.height = cs.pcv->lumaHeight;
+    s.chroma_format = (int)cs.pcv->chrFormat;
+    s.bit_depth_luma = cs.sps->getBitDepth(CHANNEL_TYPE_LUMA);
+    s.bit_depth_chroma = cs.sps->getBitDepth(CHANNEL_TYPE_CHROMA);
+    s.ctu_size = cs.pcv->maxCUWidth;
+    s.capacity = 1;
+    s.device = getenv("VTMGPU_DEVICE") ? atoi(getenv("VTMGPU_DEVICE")) : 0;
+    const bool same = s.width == seq.width && s.height == seq.height && s.chroma_format == seq.chroma_format && s.bit_depth_luma == seq.bit_depth_luma &&
+                      s.bit_depth_chroma == seq.bit_depth_chroma && s.ctu_size == seq.ctu_size;
+    seq = s;
+    if (useRef || (ctx && same)) return;
+    api.load();
+    if (ctx) { api.destroy(ctx); ctx = nullptr; }
+    if (api.create(&seq, &ctx)) THROW("vtmgpu shim: vtmgpu_create failed: " << api.last_error(nullptr));
+  }
+
+  static void planes(CodingStructure& cs, int16_t* p[3], ptrdiff_t st[3], int w[3], int h[3])
+  {
+    PelUnitBuf rec = cs.getRecoBuf();
+    for (int c = 0; c < 3; c++)
+    {
+      p[c] = nullptr; st[c] = 0; w[c] = h[c] = 0;
+      if (c >= (int)getNumberValidComponents(cs.pcv->chrFormat)) continue;
+      PelBuf& b = rec.get(ComponentID(c));
+      p[c] = b.buf; st[c] = b.stride; w[c] = b.width; h[c] = b.height;
+    }
+  }
+  void upload(CodingStructure& cs)   { int16_t* p[3]; ptrdiff_t st[3]; int w[3], h[3]; planes(cs, p, st, w, h); check(api.upload(ctx, 0, p, st), "upload"); }
+  void download(CodingStructure& cs) { int16_t* p[3]; ptrdiff_t st[3]; int w[3], h[3]; planes(cs, p, st, w, h); check(api.download(ctx, 0, p, st), "download"); }
+
+  void capturePlanes(CodingStructure& cs, const char* stage)
+  {
+    if (captureDir.empty()) return;
+    int16_t* p[3]; ptrdiff_t st[3]; int w[3], h[3];
+    planes(cs, p, st, w, h);
+    for (int c = 0; c < 3; c++)
+      if (p[c]) cap.addPlane((std::string(stage) + "_" + std::to_string(c)).c_str(), p[c], st[c], w[c], h[c]);
+  }
+  void finishPicture(CodingStructure& cs, int stagesMask)
+  {
+    if (!captureDir.empty())
+    {
+      const int32_t hdr[8] = { seq.width, seq.height, seq.chroma_format, seq.bit_depth_luma, seq.bit_depth_chroma, seq.ctu_size, cs.slice->getPOC(), stagesMask };
+      cap.add("seq", hdr, sizeof(hdr));
+      char name[64];
+      snprintf(name, sizeof(name), "/pic%04d_poc%03d.cap", picCount, cs.slice->getPOC());
+      if (!cap.write(captureDir + name)) THROW("vtmgpu shim: cannot write capture file in " << captureDir);
+      cap.clear();
+    }
+    picCount++;
+  }
+};
+
+Shim& shim()
+{
+  static Shim s;
+  return s;
+}
+
+bool lastStage(const CodingStructure& cs, int stage)   // 0 dbf, 1 sao, 2 alf
+{
+  const bool sao = cs.sps->getSAOEnabledFlag(), alf = cs.sps->getALFEnabledFlag();
+  return stage == 2 || (stage == 1 && !alf) || (stage == 0 && !sao && !alf);
+}
+
+}   // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// SAOOffset / SAOBlkParam (declared in TypeDef.h:938-963, defined in the reference's SampleAdaptiveOffset.cpp)
+// ---------------------------------------------------------------------------------------------------------
+SAOOffset::SAOOffset() { reset(); }
+SAOOffset::~SAOOffset() {}
+void SAOOffset::reset()
+{
+  modeIdc = SAO_MODE_OFF;
+  typeIdc = typeAuxInfo = -1;
+  std::fill(offset, offset + MAX_NUM_SAO_CLASSES, 0);
+}
+const SAOOffset& SAOOffset::operator=(const SAOOffset& src)
+{
+  modeIdc = src.modeIdc;
+  typeIdc = src.typeIdc;
+  typeAuxInfo = src.typeAuxInfo;
+  std::copy(src.offset, src.offset + MAX_NUM_SAO_CLASSES, offset);
+  return *this;
+}
+SAOBlkParam::SAOBlkParam() { reset(); }
+SAOBlkParam::~SAOBlkParam() {}
+void SAOBlkParam::reset() { for (auto& o : offsetParam) o.reset(); }
+const SAOBlkParam& SAOBlkParam::operator=(const SAOBlkParam& src)
+{
+  for (int c = 0; c < MAX_NUM_COMPONENT; c++) offsetParam[c] = src.offsetParam[c];
+  return *this;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// LoopFilter
+// ---------------------------------------------------------------------------------------------------------
+LoopFilter::LoopFilter() {}
+LoopFilter::~LoopFilter() {}
+void LoopFilter::create(const unsigned uiMaxCUDepth)
+{
+  m_enc = false;
+  if (shim().useRef) vtmgpu_shim_alt_backend()->lfCreate(uiMaxCUDepth);
+}
+void LoopFilter::destroy() {}
+
+void LoopFilter::loopFilterPic(CodingStructure& cs)
+{
+  Shim& s = shim();
+  s.ensureCtx(cs);
+  s.saoPending = false;
+  deriveDeblockRecords(cs, s.dbf);
+  if (!s.captureDir.empty())
+  {
+    s.cap.clear();
+    s.capturePlanes(cs, "pre");
+    s.cap.add("dbfrec_l0", s.dbf.luma[0].data(), s.dbf.luma[0].size() * 4);
+    s.cap.add("dbfrec_l1", s.dbf.luma[1].data(), s.dbf.luma[1].size() * 4);
+    s.cap.add("dbfrec_c0", s.dbf.chroma[0].data(), s.dbf.chroma[0].size() * 8);
+    s.cap.add("dbfrec_c1", s.dbf.chroma[1].data(), s.dbf.chroma[1].size() * 8);
+  }
+  if (s.useRef)
+  {
+    vtmgpu_shim_alt_backend()->lfRun(cs);
+  }
+  else
+  {
+    const vtmgpu_deblock_params p = s.dbf.view();
+    s.upload(cs);
+    s.check(s.api.set_deblock(s.ctx, 0, &p), "set_deblock");
+    s.check(s.api.set_sao(s.ctx, 0, nullptr), "set_sao");
+    s.check(s.api.set_alf(s.ctx, 0, nullptr), "set_alf");
+    s.check(s.api.deblock(s.ctx, 0, 1), "deblock");
+    if (s.staged || lastStage(cs, 0)) s.download(cs);
+  }
+  s.capturePlanes(cs, "dbf");
+  if (lastStage(cs, 0)) s.finishPicture(cs, 1);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// SampleAdaptiveOffset
+// ---------------------------------------------------------------------------------------------------------
+SampleAdaptiveOffset::SampleAdaptiveOffset() { m_numberOfComponents = 0; m_pcReshape = nullptr; }
+SampleAdaptiveOffset::~SampleAdaptiveOffset() { destroy(); }
+void SampleAdaptiveOffset::create(int picWidth, int picHeight, ChromaFormat format, uint32_t maxCUWidth, uint32_t maxCUHeight, uint32_t maxCUDepth,
+                                  uint32_t lumaBitShift, uint32_t chromaBitShift)
+{
+  for (int c = 0; c < MAX_NUM_COMPONENT; c++) m_offsetStepLog2[c] = isLuma(ComponentID(c)) ? lumaBitShift : chromaBitShift;
+  m_numberOfComponents = getNumberValidComponents(format);
+  shim().saoLog2Scale[0] = lumaBitShift;
+  shim().saoLog2Scale[1] = chromaBitShift;
+  if (shim().useRef) vtmgpu_shim_alt_backend()->saoCreate(picWidth, picHeight, (int)format, maxCUWidth, maxCUHeight, maxCUDepth, lumaBitShift, chromaBitShift);
+}
+void SampleAdaptiveOffset::destroy() {}
+
+void SampleAdaptiveOffset::SAOProcess(CodingStructure& cs, SAOBlkParam* saoBlkParams)
+{
+  CHECK(!saoBlkParams, "No parameters present");
+  Shim& s = shim();
+  flattenSao(cs, saoBlkParams, s.saoLog2Scale[0], s.saoLog2Scale[1], s.sao);
+  if (!s.captureDir.empty())
+  {
+    s.cap.add("sao_raw", s.sao.ctu.data(), s.sao.ctu.size() * sizeof(vtmgpu_sao_ctu));
+    s.cap.add("sao_scale", s.saoLog2Scale, sizeof(s.saoLog2Scale));
+  }
+  if (s.useRef)
+  {
+    vtmgpu_shim_alt_backend()->saoRun(cs, saoBlkParams);
+  }
+  else
+  {
+    const int mask = s.api.sao_reconstruct(s.sao.ctu.data(), (int)s.sao.ctu.size(), s.sao.widthInCtus, s.sao.numComps, s.saoLog2Scale[0], s.saoLog2Scale[1]);
+    if (mask < 0) THROW("vtmgpu shim: invalid SAO parameters (" << mask << ")");
+    writeBackSao(s.sao, saoBlkParams);
+    const vtmgpu_sao_params p = s.sao.view();
+    s.check(s.api.set_sao(s.ctx, 0, &p), "set_sao");
+    if (s.staged || lastStage(cs, 1))
+    {
+      s.check(s.api.sao(s.ctx, 0, 1), "sao");
+      s.download(cs);
+    }
+    else
+    {
+      s.saoPending = true;     // fused into the ALF pass
+    }
+  }
+  s.capturePlanes(cs, "sao");
+  if (lastStage(cs, 1)) s.finishPicture(cs, 3);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// AdaptiveLoopFilter
+// ---------------------------------------------------------------------------------------------------------
+AdaptiveLoopFilter::AdaptiveLoopFilter() : m_classifier(nullptr)
+{
+  for (int c = 0; c < MAX_NUM_COMPONENT; c++) { m_ctuEnableFlag[c] = nullptr; m_ctuAlternative[c] = nullptr; }
+  m_ccAlfFilterControl[0] = m_ccAlfFilterControl[1] = nullptr;
+  m_deriveClassificationBlk = nullptr;
+  m_filterCcAlf = nullptr;
+  m_filter5x5Blk = m_filter7x7Blk = nullptr;
+}
+
+void AdaptiveLoopFilter::create(const int picWidth, const int picHeight, const ChromaFormat format, const int maxCUWidth, const int maxCUHeight,
+                                const int maxCUDepth, const int inputBitDepth[MAX_NUM_CHANNEL_TYPE])
+{
+  // called again for every picture (DecLib.cpp:1151): idempotent while the geometry is unchanged
+  const int ctus = ((picWidth + maxCUWidth - 1) / maxCUWidth) * ((picHeight + maxCUHeight - 1) / maxCUHeight);
+  if (m_created && (picWidth != m_picWidth || picHeight != m_picHeight || maxCUWidth != m_maxCUWidth || ctus != m_numCTUsInPic)) destroy();
+  m_inputBitDepth[0] = inputBitDepth[0];
+  m_inputBitDepth[1] = inputBitDepth[1];
+  m_picWidth = picWidth; m_picHeight = picHeight; m_maxCUWidth = maxCUWidth; m_maxCUHeight = maxCUHeight; m_maxCUDepth = maxCUDepth;
+  m_chromaFormat = format;
+  m_numCTUsInPic = ctus;
+  if (shim().useRef) vtmgpu_shim_alt_backend()->alfCreate(picWidth, picHeight, (int)format, maxCUWidth, maxCUHeight, maxCUDepth, inputBitDepth);
+  if (m_created) return;
+  m_ccAlfFilterControl[0] = new uint8_t[ctus]();     // CABACReader writes the per-CTU CC-ALF idc here (DecLib.cpp:1154-1155)
+  m_ccAlfFilterControl[1] = new uint8_t[ctus]();
+  m_created = true;
+}
+
+void AdaptiveLoopFilter::destroy()
+{
+  if (!m_created) return;
+  delete[] m_ccAlfFilterControl[0];
+  delete[] m_ccAlfFilterControl[1];
+  m_ccAlfFilterControl[0] = m_ccAlfFilterControl[1] = nullptr;
+  m_created = false;
+}
+
+void AdaptiveLoopFilter::ALFProcess(CodingStructure& cs)
+{
+  Shim& s = shim();
+  flattenAlf(cs, m_ccAlfFilterParam, m_ccAlfFilterControl, s.alf);
+  const vtmgpu_alf_params* p = s.alf.view();
+  if (!s.captureDir.empty())
+  {
+    const int32_t hdr[8] = { p->enabled[0], p->enabled[1], p->enabled[2], p->num_luma_aps, s.alf.hasChromaAps, p->ccalf_enabled[0], p->ccalf_enabled[1], p->num_ctus };
+    s.cap.add("alf_hdr", hdr, sizeof(hdr));
+    s.cap.add("alf_luma_aps", s.alf.lumaAps.data(), s.alf.lumaAps.size() * sizeof(vtmgpu_alf_luma_aps));
+    s.cap.add("alf_chroma_aps", &s.alf.chromaAps, sizeof(vtmgpu_alf_chroma_aps));
+    for (int c = 0; c < 3; c++) s.cap.add(("alf_en" + std::to_string(c)).c_str(), s.alf.ctuEnable[c].data(), s.alf.ctuEnable[c].size());
+    s.cap.add("alf_fidx", s.alf.filterIdx.data(), s.alf.filterIdx.size() * 2);
+    for (int c = 0; c < 2; c++) s.cap.add(("alf_alt" + std::to_string(c)).c_str(), s.alf.ctuAlt[c].data(), s.alf.ctuAlt[c].size());
+    s.cap.add("alf_cccoef", p->ccalf_coeff, sizeof(p->ccalf_coeff));
+    for (int c = 0; c < 2; c++) s.cap.add(("alf_ccidc" + std::to_string(c)).c_str(), s.alf.ccIdc[c].data(), s.alf.ccIdc[c].size());
+  }
+  if (s.useRef)
+  {
+    vtmgpu_shim_alt_backend()->alfRun(cs, m_ccAlfFilterParam, m_ccAlfFilterControl, p->num_ctus);
+  }
+  else
+  {
+    s.check(s.api.set_alf(s.ctx, 0, p), "set_alf");
+    if (s.saoPending) s.check(s.api.sao_alf(s.ctx, 0, 1), "sao_alf");
+    else              s.check(s.api.alf(s.ctx, 0, 1), "alf");
+    s.saoPending = false;
+    s.download(cs);
+  }
+  s.capturePlanes(cs, "alf");
+  s.finishPicture(cs, cs.sps->getSAOEnabledFlag() ? 7 : 5);
+}
+
+// InitX86.cpp (kept in the host build for the non-filter SIMD) still references the per-ISA ALF initialisers that
+// lived in the removed x86/*/AdaptiveLoopFilter_*.cpp stubs; they are never called (our constructor does not
+// dispatch), so empty definitions satisfy the linker.
+#ifdef TARGET_SIMD_X86
+template<X86_VEXT vext> void AdaptiveLoopFilter::_initAdaptiveLoopFilterX86() {}
+template void AdaptiveLoopFilter::_initAdaptiveLoopFilterX86<SSE41>();
+template void AdaptiveLoopFilter::_initAdaptiveLoopFilterX86<AVX>();
+template void AdaptiveLoopFilter::_initAdaptiveLoopFilterX86<AVX2>();
+#endif

@@ -1,0 +1,658 @@
+// vtm_flatten.cpp -- see vtm_flatten.h.  Host-side derivation of the per-picture side information.
+//
+// The deblocking part follows LoopFilter::xDeblockCU and its helpers (LoopFilter.cpp:261-812) decision by
+// decision, but is organised around EMITTING packed segment records (vtmgpu.h) for the device kernels instead of
+// calling the sample filters; the luma/chroma edge walks follow xEdgeFilterLuma :896-977 and
+// xEdgeFilterChroma :1114-1249 up to (not including) the sample reads.
+#include "vtm_flatten.h"
+
+#include <algorithm>
+#include <cstring>
+
+#include "CodingStructure.h"
+#include "Picture.h"
+#include "Quant.h"
+#include "Slice.h"
+#include "UnitTools.h"
+#include "AlfParameters.h"
+
+namespace vtmshim
+{
+
+vtmgpu_deblock_params FlatDeblock::view() const
+{
+  vtmgpu_deblock_params p;
+  for (int d = 0; d < 2; d++)
+  {
+    p.luma[d]   = luma[d].data();
+    p.chroma[d] = chroma[d].empty() ? nullptr : chroma[d].data();
+  }
+  return p;
+}
+
+vtmgpu_sao_params FlatSao::view() const
+{
+  vtmgpu_sao_params p;
+  p.ctu      = ctu.data();
+  p.num_ctus = (int)ctu.size();
+  return p;
+}
+
+const vtmgpu_alf_params* FlatAlf::view()
+{
+  p.luma_aps   = lumaAps.empty() ? nullptr : lumaAps.data();
+  p.chroma_aps = hasChromaAps ? &chromaAps : nullptr;
+  for (int c = 0; c < 3; c++) p.ctu_enable[c] = ctuEnable[c].data();
+  for (int c = 0; c < 2; c++) { p.ctu_alt[c] = ctuAlt[c].data(); p.ccalf_idc[c] = ccIdc[c].data(); }
+  p.ctu_filter_idx = filterIdx.data();
+  return &p;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// deblocking derivation
+// ---------------------------------------------------------------------------------------------------------
+namespace
+{
+
+// tc / beta tables of the standard (LoopFilter.cpp:66-74)
+const uint16_t kTc[66] = { 0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,3,4,4,4,4,5,5,5,5,7,7,8,9,10,10,11,13,14,15,17,19,21,24,25,29,33,36,
+                           41,45,51,57,64,71,80,89,100,112,125,141,157,177,198,222,250,280,314,352,395 };
+const uint8_t  kBeta[64] = { 0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,6,7,8,9,10,11,12,13,14,15,16,17,18,20,22,24,26,28,30,32,34,36,38,40,
+                             42,44,46,48,50,52,54,56,58,60,62,64,66,68,70,72,74,76,78,80,82,84,86,88 };
+
+constexpr int kU = 32;   // 4x4 luma units per CTU side at CTU 128
+
+enum { VER = 0, HOR = 1 };
+
+// what the reference keeps per CTU and direction in m_aapucBS / m_aapbEdgeFilter / m_maxFilterLength{P,Q} /
+// m_transformEdge; here everything is indexed in units of 4 luma samples
+struct CtuState
+{
+  uint8_t code[kU * kU];   // before the bS step: 0 none / 1 TU edge / 3 TU+PU edge; afterwards packed bS Y|Cb<<2|Cr<<4
+  bool    on[kU * kU];
+  uint8_t lenP[3][kU][kU], lenQ[3][kU][kU];   // [comp][x unit][y unit]
+  bool    tuEdge[3][kU][kU];
+  void clear() { memset(this, 0, sizeof(*this)); }
+};
+
+class Deriver
+{
+public:
+  Deriver(CodingStructure& cs, FlatDeblock& out) : m_cs(cs), m_pcv(*cs.pcv), m_out(out)
+  {
+    m_sx = getComponentScaleX(COMPONENT_Cb, m_pcv.chrFormat);
+    m_sy = getComponentScaleY(COMPONENT_Cb, m_pcv.chrFormat);
+  }
+  void run();
+
+private:
+  CodingStructure&     m_cs;
+  const PreCalcValues& m_pcv;
+  FlatDeblock&         m_out;
+  CtuState             m_st;
+  int  m_sx, m_sy, m_ctuX = 0, m_ctuY = 0, m_dir = VER;
+  bool m_left = false, m_top = false, m_internal = false;
+
+  int uidx(int x, int y) const { return ((y & (int)m_pcv.maxCUHeightMask) >> 2) * kU + ((x & (int)m_pcv.maxCUWidthMask) >> 2); }
+  // unit coordinates inside the CTU of a position given in component samples
+  int ux(int comp, int xComp) const { return ((comp ? (xComp << m_sx) : xComp) - m_ctuX) >> 2; }
+  int uy(int comp, int yComp) const { return ((comp ? (yComp << m_sy) : yComp) - m_ctuY) >> 2; }
+
+  void ctuPass(const UnitArea& ctuArea);
+  void deriveCU(CodingUnit& cu);
+  void edgeEnables(const CodingUnit& cu);
+  void mark(int dir, const Area& a, bool value, bool puInternal);
+  void lengthsFromTU(const CodingUnit& cu, const TransformUnit& tu);
+  void lengthsFromSubBlocks(const PredictionUnit& pu, bool mvSub, int sub, const Area& ap);
+  unsigned strength(const CodingUnit& cu, const Position& p) const;
+  void emitLuma(const CodingUnit& cu, int edge);
+  void emitChroma(const CodingUnit& cu, int edge);
+};
+
+bool usable(const CodingUnit& q, const CodingUnit& p, const PPS& pps)
+{
+  // isAvailableLeft / isAvailableAbove (LoopFilter.cpp:85-93)
+  return (pps.getLoopFilterAcrossSlicesEnabledFlag() || CU::isSameSlice(q, p)) &&
+         (pps.getLoopFilterAcrossTilesEnabledFlag() || CU::isSameTile(q, p));
+}
+
+void Deriver::run()
+{
+  const int W = m_pcv.lumaWidth, H = m_pcv.lumaHeight;
+  CHECK(m_pcv.maxCUWidth > 128 || m_pcv.minCUWidth != 4 || m_pcv.minCUHeight != 4, "vtmgpu shim: unsupported CTU / min CU size");
+  CHECK(m_cs.picHeader->getLoopFilterAcrossVirtualBoundariesDisabledFlag(), "vtmgpu shim: signalled virtual boundaries are not supported");
+  CHECK(m_cs.sps->getLadfEnabled(), "vtmgpu shim: LADF (sample dependent deblocking QP) is not supported");
+  m_out.width = W; m_out.height = H; m_out.sx = m_sx; m_out.sy = m_sy;
+  const bool chroma = m_pcv.chrFormat != CHROMA_400;
+  const int gx = 8 << m_sx, gy = 8 << m_sy;
+  m_out.luma[VER].assign((size_t)(W / 4) * (H / 4), 0);
+  m_out.luma[HOR].assign((size_t)(W / 4) * (H / 4), 0);
+  m_out.chroma[VER].assign(chroma ? (size_t)((W + gx - 1) / gx) * (H / 4) : 0, 0);
+  m_out.chroma[HOR].assign(chroma ? (size_t)((H + gy - 1) / gy) * (W / 4) : 0, 0);
+
+  // two passes over the picture as in loopFilterPic (LoopFilter.cpp:165-240).  No record depends on samples
+  // (LADF is rejected above), so both passes can be derived before any filtering happens.
+  for (m_dir = VER; m_dir <= HOR; m_dir++)
+    for (int y = 0; y < (int)m_pcv.heightInCtus; y++)
+      for (int x = 0; x < (int)m_pcv.widthInCtus; x++)
+      {
+        const UnitArea ctuArea(m_pcv.chrFormat, Area(x << m_pcv.maxCUWidthLog2, y << m_pcv.maxCUHeightLog2, m_pcv.maxCUWidth, m_pcv.maxCUWidth));
+        m_ctuX = x << m_pcv.maxCUWidthLog2;
+        m_ctuY = y << m_pcv.maxCUHeightLog2;
+        ctuPass(ctuArea);
+      }
+}
+
+void Deriver::ctuPass(const UnitArea& ctuArea)
+{
+  m_st.clear();
+  m_cs.slice = m_cs.getCU(ctuArea.lumaPos(), CH_L)->slice;   // side effect kept (LoopFilter.cpp:179,218)
+  for (auto& cu : m_cs.traverseCUs(CS::getArea(m_cs, ctuArea, CH_L), CH_L)) deriveCU(cu);
+  if (CS::isDualITree(m_cs))
+  {
+    m_st.clear();
+    for (auto& cu : m_cs.traverseCUs(CS::getArea(m_cs, ctuArea, CH_C), CH_C)) deriveCU(cu);
+  }
+}
+
+void Deriver::edgeEnables(const CodingUnit& cu)
+{
+  // xSetLoopfilterParam (LoopFilter.cpp:656-672)
+  m_left = m_top = m_internal = false;
+  if (cu.slice->getDeblockingFilterDisable()) return;
+  const Position& pos = cu.blocks[cu.chType].pos();
+  const PPS& pps = *cu.cs->pps;
+  m_internal = true;
+  m_left = pos.x > 0 && usable(cu, *cu.cs->getCU(pos.offset(-1, 0), cu.chType), pps);
+  m_top  = pos.y > 0 && usable(cu, *cu.cs->getCU(pos.offset(0, -1), cu.chType), pps);
+}
+
+void Deriver::mark(int dir, const Area& a, bool value, bool puInternal)
+{
+  // xSetEdgefilterMultiple (LoopFilter.cpp:627-655) for the left column (VER) / top row (HOR) of units of area a.
+  // The reference updates the arrays of both directions but only ever reads those of the pass direction.
+  if (dir != m_dir) return;
+  const int n = dir == VER ? a.height / 4 : a.width / 4;
+  for (int i = 0; i < n; i++)
+  {
+    const int id = dir == VER ? uidx(a.x, a.y + 4 * i) : uidx(a.x + 4 * i, a.y);
+    m_st.on[id] = value;
+    if (m_st.code[id] && value) m_st.code[id] = 3;            // TU edge that is also a PU edge
+    else if (!puInternal)       m_st.code[id] = value;
+  }
+}
+
+void Deriver::lengthsFromTU(const CodingUnit& cu, const TransformUnit& tu)
+{
+  // xSetMaxFilterLengthPQFromTransformSizes (LoopFilter.cpp:454-548)
+  for (int c = 0; c < MAX_NUM_COMPONENT; c++)
+  {
+    const ComponentID comp = ComponentID(c);
+    const ChannelType ch   = toChannelType(comp);
+    const CompArea&   tb   = tu.block(comp);
+    if (!tb.valid()) continue;
+    const bool atCuBorder = m_dir == HOR ? tb.y == cu.block(comp).y : tb.x == cu.block(comp).x;
+    if (!(atCuBorder ? (m_dir == HOR ? m_top : m_left) : m_internal)) continue;
+    const int step   = 4 >> (c ? (m_dir == HOR ? m_sx : m_sy) : 0);
+    const int extent = m_dir == HOR ? (int)tu.blocks[c].width : (int)tu.blocks[c].height;
+    const int sizeQ  = m_dir == HOR ? tb.height : tb.width;
+    for (int k = 0; k < extent; k += step)
+    {
+      const Position posQ = m_dir == HOR ? Position(tu.blocks[ch].x + k, tu.blocks[ch].y) : Position(tu.blocks[ch].x, tu.blocks[ch].y + k);
+      const Position posP = m_dir == HOR ? posQ.offset(0, -1) : posQ.offset(-1, 0);
+      const TransformUnit& tuP = *cu.cs->getTU(posP, ch);
+      const int sizeP = m_dir == HOR ? tuP.block(comp).height : tuP.block(comp).width;
+      const int x = m_dir == HOR ? ux(c, tb.x + k) : ux(c, tb.x);
+      const int y = m_dir == HOR ? uy(c, tb.y) : uy(c, tb.y + k);
+      m_st.tuEdge[c][x][y] = true;
+      if (c == 0)
+      {
+        const bool small = sizeP <= 4 || sizeQ <= 4;
+        m_st.lenQ[c][x][y] = small ? 1 : (sizeQ >= 32 ? 7 : 3);
+        m_st.lenP[c][x][y] = small ? 1 : (sizeP >= 32 ? 7 : 3);
+      }
+      else
+      {
+        m_st.lenQ[c][x][y] = m_st.lenP[c][x][y] = (sizeQ >= 8 && sizeP >= 8) ? 3 : 1;
+      }
+    }
+  }
+}
+
+void Deriver::lengthsFromSubBlocks(const PredictionUnit& pu, bool mvSub, int sub, const Area& ap)
+{
+  // xSetMaxFilterLengthPQForCodingSubBlocks (LoopFilter.cpp:550-625); luma only, a = along the edge, d = across
+  if (!mvSub || !pu.Y().valid()) return;
+  const int x0 = ux(0, pu.Y().x), y0 = uy(0, pu.Y().y);
+  const int across = m_dir == HOR ? ap.height : ap.width, along = m_dir == HOR ? ap.width : ap.height;
+  auto te   = [&](int d, int a) -> bool { return m_dir == HOR ? m_st.tuEdge[0][x0 + a / 4][y0 + d / 4] : m_st.tuEdge[0][x0 + d / 4][y0 + a / 4]; };
+  auto lenP = [&](int d, int a) -> uint8_t& { return m_dir == HOR ? m_st.lenP[0][x0 + a / 4][y0 + d / 4] : m_st.lenP[0][x0 + d / 4][y0 + a / 4]; };
+  auto lenQ = [&](int d, int a) -> uint8_t& { return m_dir == HOR ? m_st.lenQ[0][x0 + a / 4][y0 + d / 4] : m_st.lenQ[0][x0 + d / 4][y0 + a / 4]; };
+  for (int d = 0; d < across; d += sub)
+    for (int a = 0; a < along; a += 4)
+    {
+      if (te(d, a))
+      {
+        lenQ(d, a) = std::min<int>(lenQ(d, a), 5);
+        if (d > 0) lenP(d, a) = std::min<int>(lenP(d, a), 5);
+      }
+      else if (d > 0 && (te(d - 4, a) || d + 4 >= across || te(d + 4, a)))   lenQ(d, a) = lenP(d, a) = 1;
+      else if (d > 0 && (te(d - 8, a) || d + 8 >= across || te(d + 8, a)))   lenQ(d, a) = lenP(d, a) = 2;
+      else                                                                   lenQ(d, a) = lenP(d, a) = 3;
+    }
+}
+
+unsigned Deriver::strength(const CodingUnit& cu, const Position& lumaPos) const
+{
+  // xGetBoundaryStrengthSingle (LoopFilter.cpp:674-812); result packed Y | Cb<<2 | Cr<<4
+  const bool hasLuma = cu.Y().valid();
+  const int  sh = hasLuma ? 0 : getComponentScaleX(COMPONENT_Cb, cu.firstPU->chromaFormat);
+  const int  sv = hasLuma ? 0 : getComponentScaleY(COMPONENT_Cb, cu.firstPU->chromaFormat);
+  const Position posQ(lumaPos.x >> sh, lumaPos.y >> sv);
+  const Position posP = m_dir == VER ? posQ.offset(-1, 0) : posQ.offset(0, -1);
+  const CodingUnit& cuQ = cu;
+  const CodingUnit& cuP = *cu.cs->getCU(posP, cu.chType);
+  const bool intraP = cuP.predMode == MODE_INTRA, intraQ = cuQ.predMode == MODE_INTRA;
+  if (intraP || intraQ)
+  {
+    const unsigned y = (intraP && cuP.bdpcmMode && intraQ && cuQ.bdpcmMode) ? 0 : 2;
+    const unsigned c = (intraP && cuP.bdpcmModeChroma && intraQ && cuQ.bdpcmModeChroma) ? 0 : 2;
+    return y | (c << 2) | (c << 4);
+  }
+  const TransformUnit& tuQ = *cuQ.cs->getTU(posQ, cuQ.chType);
+  const TransformUnit& tuP = *cuP.cs->getTU(posP, cuQ.chType);
+  const uint8_t code = m_st.code[uidx(lumaPos.x, lumaPos.y)];
+  const bool ciip = cuP.firstPU->ciipFlag || cuQ.firstPU->ciipFlag;
+  if (code && ciip) return 2 | (2 << 2) | (2 << 4);
+
+  unsigned bs = 0;
+  if (code)
+  {
+    if (TU::getCbf(tuQ, COMPONENT_Y) || TU::getCbf(tuP, COMPONENT_Y)) bs |= 1;
+    if (TU::getCbf(tuQ, COMPONENT_Cb) || TU::getCbf(tuP, COMPONENT_Cb) || tuQ.jointCbCr || tuP.jointCbCr) bs |= 1 << 2;
+    if (TU::getCbf(tuQ, COMPONENT_Cr) || TU::getCbf(tuP, COMPONENT_Cr) || tuQ.jointCbCr || tuP.jointCbCr) bs |= 1 << 4;
+  }
+  if ((bs & 3) == 1) return bs;
+  if (ciip) return 1;
+  if (!hasLuma) return bs;
+  if (code != 0 && code != 3) return bs;          // pure TU edge: no motion test
+
+  // motion test, on the UNREFINED motion field (setRefinedMotionField runs after deblocking, DecLib.cpp:579-580)
+  const Position lumaPosP = m_dir == VER ? lumaPos.offset(-1, 0) : lumaPos.offset(0, -1);
+  const MotionInfo& miQ = cuQ.cs->getMotionInfo(lumaPos);
+  const MotionInfo& miP = cuP.cs->getMotionInfo(lumaPosP);
+  const Slice& sliceQ = *cuQ.slice;
+  const Slice& sliceP = *cuP.slice;
+  const int thr = (1 << MV_FRACTIONAL_BITS_INTERNAL) >> 1;
+  auto far = [thr](const Mv& a, const Mv& b) { return abs(a.getHor() - b.getHor()) >= thr || abs(a.getVer() - b.getVer()) >= thr; };
+
+  if (sliceQ.isInterB() || sliceP.isInterB())
+  {
+    const Picture* refP0 = CU::isIBC(cuP) ? sliceP.getPic() : (miP.refIdx[0] < 0 ? nullptr : sliceP.getRefPic(REF_PIC_LIST_0, miP.refIdx[0]));
+    const Picture* refP1 = CU::isIBC(cuP) ? nullptr         : (miP.refIdx[1] < 0 ? nullptr : sliceP.getRefPic(REF_PIC_LIST_1, miP.refIdx[1]));
+    const Picture* refQ0 = CU::isIBC(cuQ) ? sliceQ.getPic() : (miQ.refIdx[0] < 0 ? nullptr : sliceQ.getRefPic(REF_PIC_LIST_0, miQ.refIdx[0]));
+    const Picture* refQ1 = CU::isIBC(cuQ) ? nullptr         : (miQ.refIdx[1] < 0 ? nullptr : sliceQ.getRefPic(REF_PIC_LIST_1, miQ.refIdx[1]));
+    Mv p0, p1, q0, q1;   // zero unless the list is used
+    if (miP.refIdx[0] >= 0) p0 = miP.mv[0];
+    if (miP.refIdx[1] >= 0) p1 = miP.mv[1];
+    if (miQ.refIdx[0] >= 0) q0 = miQ.mv[0];
+    if (miQ.refIdx[1] >= 0) q1 = miQ.mv[1];
+    unsigned mvBs = 1;                         // different reference pictures
+    if ((refP0 == refQ0 && refP1 == refQ1) || (refP0 == refQ1 && refP1 == refQ0))
+    {
+      if (refP0 != refP1)                      // two distinct references
+        mvBs = refP0 == refQ0 ? (far(q0, p0) || far(q1, p1)) : (far(q1, p0) || far(q0, p1));
+      else                                     // both lists point at the same picture
+        mvBs = (far(q0, p0) || far(q1, p1)) && (far(q1, p0) || far(q0, p1));
+    }
+    return bs + mvBs;
+  }
+  // P slices
+  const Picture* refP0 = CU::isIBC(cuP) ? sliceP.getPic() : sliceP.getRefPic(REF_PIC_LIST_0, miP.refIdx[0]);
+  const Picture* refQ0 = CU::isIBC(cuQ) ? sliceQ.getPic() : sliceQ.getRefPic(REF_PIC_LIST_0, miQ.refIdx[0]);
+  if (refP0 != refQ0) return bs + 1;
+  return far(miQ.mv[0], miP.mv[0]) ? bs + 1 : bs;
+}
+
+void Deriver::emitLuma(const CodingUnit& cu, int edge)
+{
+  // xEdgeFilterLuma (LoopFilter.cpp:844-977): everything up to the sample reads
+  const CompArea& la = cu.block(COMPONENT_Y);
+  const SPS& sps = *cu.cs->sps;
+  const PPS& pps = *cu.cs->pps;
+  const Slice& slice = *cu.slice;
+  const int bd = sps.getBitDepth(CHANNEL_TYPE_LUMA);
+  const ClpRng& clp = cu.cs->slice->clpRng(COMPONENT_Y);
+  CHECK(clp.min != 0 || clp.max != (1 << bd) - 1, "vtmgpu shim: non-default luma clipping range");
+  const int n = m_dir == VER ? la.height / 4 : la.width / 4;
+  const int tcOff = slice.getDeblockingFilterTcOffsetDiv2() * 2, betaOff = slice.getDeblockingFilterBetaOffsetDiv2() * 2;
+  for (int i = 0; i < n; i++)
+  {
+    const Position pos = m_dir == VER ? Position(la.x + edge * 4, la.y + i * 4) : Position(la.x + i * 4, la.y + edge * 4);
+    const int id = uidx(pos.x, pos.y);
+    const unsigned bs = m_st.code[id] & 3;
+    if (!bs) continue;
+    const CodingUnit& cuP = *cu.cs->getCU(m_dir == VER ? pos.offset(-4, 0) : pos.offset(0, -4), cu.chType);
+    if (!usable(cu, cuP, pps))
+    {
+      m_st.code[id] = 0;      // also suppresses the chroma filtering of this unit (LoopFilter.cpp:918-933)
+      continue;
+    }
+    const int qp = (cuP.qp + cu.qp + 1) >> 1;
+    int lp = m_st.lenP[0][(pos.x - m_ctuX) >> 2][(pos.y - m_ctuY) >> 2];
+    const int lq = m_st.lenQ[0][(pos.x - m_ctuX) >> 2][(pos.y - m_ctuY) >> 2];
+    if (lp > 5 && cuP.affine) lp = 5;
+    const bool ctuRow = m_dir == HOR && pos.y % (int)slice.getSPS()->getCTUSize() == 0;
+    const int iTc = Clip3(0, MAX_QP + 2, qp + 2 * (int(bs) - 1) + tcOff);
+    const int iB  = Clip3(0, MAX_QP, qp + betaOff);
+    const unsigned tc   = bd < 10 ? (kTc[iTc] + 2) >> (10 - bd) : kTc[iTc] << (bd - 10);
+    const unsigned beta = kBeta[iB] << (bd - 8);
+    CHECK(tc > 0x7ff || beta > 0x7ff, "vtmgpu shim: tc/beta out of record range");
+    uint32_t rec = tc | (beta << VTMGPU_DBF_L_BETA_SHIFT) | (uint32_t(lp) << VTMGPU_DBF_L_LENP_SHIFT) | (uint32_t(lq) << VTMGPU_DBF_L_LENQ_SHIFT);
+    if (sps.getPLTMode())
+    {
+      if (CU::isPLT(cuP)) rec |= VTMGPU_DBF_L_PNOFILT;
+      if (CU::isPLT(cu))  rec |= VTMGPU_DBF_L_QNOFILT;
+    }
+    if (ctuRow) rec |= VTMGPU_DBF_L_CTUROW;
+    if (!tc) rec = 0;
+    m_out.luma[m_dir][(size_t)(pos.y / 4) * (m_out.width / 4) + pos.x / 4] = rec;
+  }
+}
+
+void Deriver::emitChroma(const CodingUnit& cu, int edge)
+{
+  // xEdgeFilterChroma (LoopFilter.cpp:1087-1249): everything up to the sample reads
+  const bool hasLuma = cu.Y().valid();
+  const Position lumaPos = hasLuma ? cu.Y().pos() : recalcPosition(cu.chromaFormat, cu.chType, CHANNEL_TYPE_LUMA, cu.blocks[cu.chType].pos());
+  const Size     lumaSize = hasLuma ? cu.Y().size() : recalcSize(cu.chromaFormat, cu.chType, CHANNEL_TYPE_LUMA, cu.blocks[cu.chType].size());
+  const SPS& sps = *cu.cs->sps;
+  const PPS& pps = *cu.cs->pps;
+  const Slice& slice = *cu.slice;
+  const int unitH = 4 >> m_sx, unitV = 4 >> m_sy;          // chroma samples per 4-luma unit
+  // only edges on the 8x8 chroma-sample grid, measured from the CTU origin (LoopFilter.cpp:1115-1126)
+  const int edgeInCtu = (m_dir == VER ? ((lumaPos.x & (int)m_pcv.maxCUWidthMask) >> 2) : ((lumaPos.y & (int)m_pcv.maxCUHeightMask) >> 2)) + edge;
+  if (unitH < 8 && unitV < 8 && (edgeInCtu % (8 / (m_dir == VER ? unitH : unitV))) != 0) return;
+
+  const int bd = sps.getBitDepth(CHANNEL_TYPE_CHROMA);
+  const int n = m_dir == VER ? lumaSize.height / 4 : lumaSize.width / 4;
+  const int tcOff = slice.getDeblockingFilterTcOffsetDiv2() * 2, betaOff = slice.getDeblockingFilterBetaOffsetDiv2() * 2;
+  const int gx = 8 << m_sx, gy = 8 << m_sy;
+  for (int i = 0; i < n; i++)
+  {
+    const Position pos = m_dir == VER ? Position(lumaPos.x + edge * 4, lumaPos.y + i * 4) : Position(lumaPos.x + i * 4, lumaPos.y + edge * 4);
+    const unsigned packed = m_st.code[uidx(pos.x, pos.y)];
+    const unsigned bsC[2] = { (packed >> 2) & 3, (packed >> 4) & 3 };
+    if (!bsC[0] && !bsC[1]) continue;
+    const Position lumaP = m_dir == VER ? pos.offset(-4, 0) : pos.offset(0, -4);
+    const CodingUnit& cuP1 = *cu.cs->getCU(recalcPosition(cu.chromaFormat, CHANNEL_TYPE_LUMA, cu.chType, lumaP), cu.chType);
+    const ChannelType chP  = cuP1.isSepTree() ? CHANNEL_TYPE_CHROMA : cu.chType;
+    const CodingUnit& cuP  = *cu.cs->getCU(recalcPosition(cu.chromaFormat, CHANNEL_TYPE_LUMA, chP, lumaP), chP);
+    CHECK(!usable(cu, cuP, pps), "Neighbour not available");
+
+    const int x = (pos.x - m_ctuX) >> 2, y = (pos.y - m_ctuY) >> 2;
+    const bool large = m_st.lenP[COMPONENT_Cb][x][y] >= 3 && m_st.lenQ[COMPONENT_Cb][x][y] >= 3;
+    const bool ctb   = m_dir == HOR && pos.y % (int)cuP.slice->getSPS()->getCTUSize() == 0;
+    uint64_t rec = 0;
+    for (int c = 0; c < 2; c++)
+    {
+      if (!(bsC[c] == 2 || (large && bsC[c] == 1))) continue;
+      const ComponentID comp = ComponentID(c + 1);
+      const ClpRng& clp = cu.cs->slice->clpRng(comp);
+      CHECK(clp.min != 0 || clp.max != (1 << bd) - 1, "vtmgpu shim: non-default chroma clipping range");
+      const int shP = cuP.Y().valid() ? 0 : getComponentScaleX(COMPONENT_Cb, cuP.firstPU->chromaFormat);
+      const int svP = cuP.Y().valid() ? 0 : getComponentScaleY(COMPONENT_Cb, cuP.firstPU->chromaFormat);
+      const int shQ = hasLuma ? 0 : getComponentScaleX(COMPONENT_Cb, cu.firstPU->chromaFormat);
+      const int svQ = hasLuma ? 0 : getComponentScaleY(COMPONENT_Cb, cu.firstPU->chromaFormat);
+      const Position posQ(pos.x >> shQ, pos.y >> svQ);
+      const Position posP1(pos.x >> shP, pos.y >> svP);
+      const Position posP = m_dir == VER ? posP1.offset(-1, 0) : posP1.offset(0, -1);
+      const TransformUnit& tuQ = *cu.cs->getTU(posQ, cu.chType);
+      const TransformUnit& tuP = *cuP.cs->getTU(posP, cuP.chType);
+      const QpParam qpP(tuP, comp, -MAX_INT, false);
+      const QpParam qpQ(tuQ, comp, -MAX_INT, false);
+      const int bdOff = tuP.cs->sps->getQpBDOffset(toChannelType(comp));
+      const int qp = ((qpQ.Qp(0) - bdOff) + (qpP.Qp(0) - bdOff) + 1) >> 1;
+      const int iTc = Clip3<int>(0, MAX_QP + 2, qp + 2 * (int(bsC[c]) - 1) + tcOff);
+      const uint64_t tc = bd < 10 ? (kTc[iTc] + 2) >> (10 - bd) : kTc[iTc] << (bd - 10);
+      uint64_t beta = 0;
+      if (large) beta = kBeta[Clip3<int>(0, MAX_QP, qp + betaOff)] << (bd - 8);
+      CHECK(tc > 0x7ff || beta > 0x7ff, "vtmgpu shim: tc/beta out of record range");
+      rec |= tc << (c ? VTMGPU_DBF_C_TCCR_SHIFT : 0);
+      rec |= beta << (c ? VTMGPU_DBF_C_BETACR_SHIFT : VTMGPU_DBF_C_BETACB_SHIFT);
+    }
+    if (!(rec & 0x3fffff)) continue;           // both tc zero: nothing to do
+    if (large) rec |= VTMGPU_DBF_C_LARGE;
+    if (ctb)   rec |= VTMGPU_DBF_C_CTB;
+    if (sps.getPLTMode())
+    {
+      if (CU::isPLT(cuP)) rec |= VTMGPU_DBF_C_PNOFILT;
+      if (CU::isPLT(cu))  rec |= VTMGPU_DBF_C_QNOFILT;
+    }
+    if (m_dir == VER) m_out.chroma[VER][(size_t)(pos.y / 4) * ((m_out.width + gx - 1) / gx) + pos.x / gx] = rec;
+    else              m_out.chroma[HOR][(size_t)(pos.y / gy) * (m_out.width / 4) + pos.x / 4] = rec;
+  }
+}
+
+void Deriver::deriveCU(CodingUnit& cu)
+{
+  // xDeblockCU (LoopFilter.cpp:261-408)
+  const bool hasLuma = cu.Y().valid();
+  const Area area = hasLuma ? Area(cu.Y())
+                            : Area(recalcPosition(cu.chromaFormat, cu.chType, CHANNEL_TYPE_LUMA, cu.blocks[cu.chType].pos()),
+                                   recalcSize(cu.chromaFormat, cu.chType, CHANNEL_TYPE_LUMA, cu.blocks[cu.chType].size()));
+  edgeEnables(cu);
+  std::vector<int> edges;
+  const CompArea& own = cu.blocks[cu.chType];
+  auto edgeOf = [&](const CompArea& b, int off) { return m_dir == HOR ? (b.y + off - own.y) / 4 : (b.x + off - own.x) / 4; };
+
+  for (auto& tu : CU::traverseTUs(cu))
+  {
+    const Area at = hasLuma ? Area(tu.block(COMPONENT_Y)) : area;
+    mark(VER, at, m_internal, false);
+    mark(HOR, at, m_internal, false);
+    lengthsFromTU(cu, tu);
+    edges.push_back(edgeOf(tu.blocks[cu.chType], 0));
+  }
+
+  bool mvSub = false;
+  const int sub = 8;
+  for (auto& pu : CU::traversePUs(cu))
+  {
+    const Area ap = hasLuma ? Area(pu.block(COMPONENT_Y)) : area;
+    const bool xOff = pu.blocks[cu.chType].x != own.x, yOff = pu.blocks[cu.chType].y != own.y;
+    mark(VER, ap, xOff ? m_internal : m_left, xOff);
+    mark(HOR, ap, yOff ? m_internal : m_top, yOff);
+    edges.push_back(edgeOf(pu.blocks[cu.chType], 0));
+    if ((pu.mergeFlag && pu.mergeType == MRG_TYPE_SUBPU_ATMVP) || cu.affine)
+    {
+      mvSub = true;
+      const int extent = m_dir == HOR ? ap.height : ap.width;
+      for (int off = sub; off < extent; off += sub)
+      {
+        const Area blk = m_dir == HOR ? Area(cu.Y().x, cu.Y().y + off, cu.Y().width, 4) : Area(cu.Y().x + off, cu.Y().y, 4, cu.Y().height);
+        mark(m_dir, blk, m_internal, true);
+        edges.push_back(edgeOf(pu.blocks[cu.chType], off));
+      }
+    }
+    lengthsFromSubBlocks(pu, mvSub, sub, ap);
+  }
+
+  for (int y = 0; y < (int)area.height; y += 4)
+    for (int x = 0; x < (int)area.width; x += 4)
+    {
+      const int id = uidx(area.x + x, area.y + y);
+      if (m_st.on[id]) m_st.code[id] = (uint8_t)strength(cu, Position(area.x + x, area.y + y));
+    }
+
+  std::sort(edges.begin(), edges.end());
+  edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+  for (int e : edges)
+  {
+    if (cu.blocks[COMPONENT_Y].valid()) emitLuma(cu, e);
+    if (cu.blocks[COMPONENT_Cb].valid() && m_pcv.chrFormat != CHROMA_400 && (!cu.ispMode || e == 0)) emitChroma(cu, e);
+  }
+}
+
+}   // namespace
+
+void deriveDeblockRecords(CodingStructure& cs, FlatDeblock& out)
+{
+  Deriver d(cs, out);
+  d.run();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// SAO
+// ---------------------------------------------------------------------------------------------------------
+void flattenSao(CodingStructure& cs, const SAOBlkParam* blk, int log2ScaleLuma, int log2ScaleChroma, FlatSao& out)
+{
+  const PreCalcValues& pcv = *cs.pcv;
+  CHECK(cs.picHeader->getLoopFilterAcrossVirtualBoundariesDisabledFlag(), "vtmgpu shim: signalled virtual boundaries are not supported");
+  out.widthInCtus = pcv.widthInCtus;
+  out.numComps = getNumberValidComponents(pcv.chrFormat);
+  out.log2ScaleLuma = log2ScaleLuma;
+  out.log2ScaleChroma = log2ScaleChroma;
+  out.ctu.assign(pcv.sizeInCtus, vtmgpu_sao_ctu{});
+  const bool acrossSlices = cs.pps->getLoopFilterAcrossSlicesEnabledFlag(), acrossTiles = cs.pps->getLoopFilterAcrossTilesEnabledFlag();
+  static const int nbDx[8] = { -1, 1, 0, 0, -1, 1, -1, 1 }, nbDy[8] = { 0, 0, -1, 1, -1, -1, 1, 1 };   // bit order of VTMGPU_AVAIL_*
+  for (int a = 0; a < (int)pcv.sizeInCtus; a++)
+  {
+    vtmgpu_sao_ctu& o = out.ctu[a];
+    const int cx = a % pcv.widthInCtus, cy = a / pcv.widthInCtus;
+    const Position pos(cx * pcv.maxCUWidth, cy * pcv.maxCUHeight);
+    for (int c = 0; c < out.numComps; c++)
+    {
+      const SAOOffset& s = blk[a][c];
+      o.comp[c].mode = (int8_t)s.modeIdc;
+      o.comp[c].type = (int8_t)s.typeIdc;
+      o.comp[c].aux  = (int8_t)s.typeAuxInfo;
+      for (int k = 0; k < 32; k++) o.comp[c].offset[k] = (int16_t)s.offset[k];
+    }
+    // deriveLoopFilterBoundaryAvailibility (SampleAdaptiveOffset.cpp:668-729)
+    const CodingUnit* cur = cs.getCU(pos, CH_L);
+    for (int k = 0; k < 8; k++)
+    {
+      const CodingUnit* nb = cs.getCU(pos.offset(nbDx[k] * (int)pcv.maxCUWidth, nbDy[k] * (int)pcv.maxCUHeight), CH_L);
+      bool ok = nb != nullptr;
+      if (ok && !acrossSlices) ok = CU::isSameSlice(*cur, *nb);
+      if (ok && !acrossTiles)  ok = CU::isSameTile(*cur, *nb);
+      if (ok) o.avail |= 1 << k;
+    }
+    // getMergeList (:173-227)
+    o.merge_left_ok  = cx > 0 && cs.getCURestricted(pos.offset(-(int)pcv.maxCUWidth, 0), *cur, cur->chType) != nullptr;
+    o.merge_above_ok = cy > 0 && cs.getCURestricted(pos.offset(0, -(int)pcv.maxCUHeight), *cur, cur->chType) != nullptr;
+  }
+}
+
+void writeBackSao(const FlatSao& in, SAOBlkParam* blk)
+{
+  for (size_t a = 0; a < in.ctu.size(); a++)
+    for (int c = 0; c < in.numComps; c++)
+    {
+      SAOOffset& s = blk[a][c];
+      const vtmgpu_sao_offset& o = in.ctu[a].comp[c];
+      s.modeIdc = SAOMode(o.mode);
+      s.typeIdc = o.type;
+      s.typeAuxInfo = o.aux;
+      for (int k = 0; k < 32; k++) s.offset[k] = o.offset[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ALF
+// ---------------------------------------------------------------------------------------------------------
+void flattenAlf(CodingStructure& cs, const CcAlfFilterParam& cc, uint8_t* const ccControl[2], FlatAlf& out)
+{
+  const PreCalcValues& pcv = *cs.pcv;
+  const int n = pcv.sizeInCtus;
+  out = FlatAlf();
+  out.p.num_ctus = n;
+  // single parameter set per picture: every CTU's slice must agree with the first one (ALFProcess reloads the APSs at
+  // every slice change, AdaptiveLoopFilter.cpp:436-441 -- multi-slice pictures with differing ALF data are rejected)
+  Slice* first = cs.getCU(Position(0, 0), CH_L)->slice;
+  for (int a = 0; a < n; a++)
+  {
+    const Position pos((a % pcv.widthInCtus) * pcv.maxCUWidth, (a / pcv.widthInCtus) * pcv.maxCUHeight);
+    Slice* s = cs.getCU(pos, CH_L)->slice;
+    if (s == first) continue;
+    bool same = s->getTileGroupNumAps() == first->getTileGroupNumAps() && s->getTileGroupApsIdLuma() == first->getTileGroupApsIdLuma() &&
+                s->getTileGroupApsIdChroma() == first->getTileGroupApsIdChroma();
+    for (int c = 0; c < 3; c++) same = same && s->getTileGroupAlfEnabledFlag(ComponentID(c)) == first->getTileGroupAlfEnabledFlag(ComponentID(c));
+    CHECK(!same, "vtmgpu shim: slices with different ALF parameters in one picture are not supported");
+  }
+  cs.slice = cs.getCU(Position(((n - 1) % pcv.widthInCtus) * pcv.maxCUWidth, ((n - 1) / pcv.widthInCtus) * pcv.maxCUHeight), CH_L)->slice;
+  // the clip/pad path of ALFProcess (:458-555) is entered when a CTU touches a slice/tile boundary that must not be
+  // crossed (isCrossedByVirtualBoundaries, :79-202); that path is not implemented on the device yet
+  CHECK(cs.picHeader->getLoopFilterAcrossVirtualBoundariesDisabledFlag(), "vtmgpu shim: signalled virtual boundaries are not supported");
+  const bool acrossSlices = cs.pps->getLoopFilterAcrossSlicesEnabledFlag(), acrossTiles = cs.pps->getLoopFilterAcrossTilesEnabledFlag();
+  if (!acrossSlices || !acrossTiles)
+    for (int a = 0; a < n; a++)
+    {
+      const int cx = a % pcv.widthInCtus, cy = a / pcv.widthInCtus;
+      const CodingUnit* cur = cs.getCU(Position(cx * pcv.maxCUWidth, cy * pcv.maxCUHeight), CH_L);
+      const int dx[3] = { -1, 0, -1 }, dy[3] = { 0, -1, -1 };
+      for (int k = 0; k < 3; k++)
+      {
+        if (cx + dx[k] < 0 || cy + dy[k] < 0) continue;
+        const CodingUnit* nb = cs.getCU(Position((cx + dx[k]) * pcv.maxCUWidth, (cy + dy[k]) * pcv.maxCUHeight), CH_L);
+        const bool blocked = (!acrossSlices && !CU::isSameSlice(*cur, *nb)) || (k < 2 && !acrossTiles && !CU::isSameTile(*cur, *nb));
+        CHECK(blocked, "vtmgpu shim: ALF across-slice/tile clipping is not supported");
+      }
+    }
+
+  for (int c = 0; c < 3; c++) out.p.enabled[c] = first->getTileGroupAlfEnabledFlag(ComponentID(c));
+  APS** apss = first->getAlfAPSs();
+  if (out.p.enabled[0] || out.p.enabled[1] || out.p.enabled[2])
+  {
+    const std::vector<int> ids = first->getTileGroupApsIdLuma();
+    out.p.num_luma_aps = first->getTileGroupNumAps();
+    for (int i = 0; i < out.p.num_luma_aps; i++)
+    {
+      APS* aps = apss[ids[i]];
+      CHECK(aps == nullptr, "invalid APS");
+      const AlfParam& ap = aps->getAlfAPSParam();
+      vtmgpu_alf_luma_aps f{};
+      f.num_filters = ap.numLumaFilters;
+      f.nonlinear = ap.nonLinearFlag[CHANNEL_TYPE_LUMA];
+      for (int k = 0; k < VTMGPU_ALF_CLASSES; k++)
+      {
+        f.delta_idx[k] = ap.filterCoeffDeltaIdx[k];
+        for (int j = 0; j < VTMGPU_ALF_LUMA_COEFF; j++)
+        {
+          f.coeff[k][j]    = ap.lumaCoeff[k * MAX_NUM_ALF_LUMA_COEFF + j];
+          f.clip_idx[k][j] = ap.lumaClipp[k * MAX_NUM_ALF_LUMA_COEFF + j];
+        }
+      }
+      out.lumaAps.push_back(f);
+    }
+    if (out.p.enabled[1] || out.p.enabled[2])
+    {
+      APS* aps = apss[first->getTileGroupApsIdChroma()];
+      CHECK(aps == nullptr, "invalid chroma APS");
+      const AlfParam& ap = aps->getAlfAPSParam();
+      out.hasChromaAps = true;
+      out.chromaAps.num_alts = ap.numAlternativesChroma;
+      out.chromaAps.nonlinear = ap.nonLinearFlag[CHANNEL_TYPE_CHROMA];
+      for (int k = 0; k < VTMGPU_ALF_MAX_ALTS; k++)
+        for (int j = 0; j < VTMGPU_ALF_CHROMA_COEFF; j++)
+        {
+          out.chromaAps.coeff[k][j]    = ap.chromaCoeff[k][j];
+          out.chromaAps.clip_idx[k][j] = ap.chromaClipp[k][j];
+        }
+    }
+  }
+  for (int c = 0; c < 3; c++) out.ctuEnable[c].assign(cs.picture->getAlfCtuEnableFlag(c), cs.picture->getAlfCtuEnableFlag(c) + n);
+  out.filterIdx.assign(cs.picture->getAlfCtbFilterIndex(), cs.picture->getAlfCtbFilterIndex() + n);
+  for (int c = 0; c < 2; c++)
+  {
+    out.ctuAlt[c].assign(cs.picture->getAlfCtuAlternativeData(c + 1), cs.picture->getAlfCtuAlternativeData(c + 1) + n);
+    out.p.ccalf_enabled[c] = first->m_ccAlfFilterParam.ccAlfFilterEnabled[c];
+    out.ccIdc[c].assign(n, 0);
+    if (out.p.ccalf_enabled[c] && ccControl[c]) out.ccIdc[c].assign(ccControl[c], ccControl[c] + n);
+    for (int f = 0; f < VTMGPU_CCALF_MAX_FILTERS; f++)
+      for (int j = 0; j < VTMGPU_CCALF_COEFF; j++) out.p.ccalf_coeff[c][f][j] = cc.ccAlfCoeff[c][f][j];
+  }
+}
+
+}   // namespace vtmshim

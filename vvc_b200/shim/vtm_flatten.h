@@ -1,0 +1,58 @@
+// vtm_flatten.h -- host side of the drop-in boundary: turns the decoder's block metadata
+// (CodingStructure / CodingUnit / TransformUnit / MotionInfo, Slice / APS) into the POD side information of
+// include/vtmgpu.h.  Compiled against the reference's headers; nothing here touches sample arithmetic.
+#pragma once
+
+#include <cstdint>
+#include <vector>
+
+#include "vtmgpu.h"
+
+class CodingStructure;
+struct SAOBlkParam;
+struct CcAlfFilterParam;
+
+namespace vtmshim
+{
+
+struct FlatDeblock
+{
+  int width = 0, height = 0, sx = 0, sy = 0;
+  std::vector<uint32_t> luma[2];
+  std::vector<uint64_t> chroma[2];
+  vtmgpu_deblock_params view() const;
+};
+
+struct FlatSao
+{
+  std::vector<vtmgpu_sao_ctu> ctu;   // raw (as parsed) until reconstruct() is called
+  int widthInCtus = 0, numComps = 3, log2ScaleLuma = 0, log2ScaleChroma = 0;
+  int enabledMask = 0;               // m_picSAOEnabled after reconstruct
+  vtmgpu_sao_params view() const;
+};
+
+struct FlatAlf
+{
+  vtmgpu_alf_params p{};
+  std::vector<vtmgpu_alf_luma_aps> lumaAps;
+  vtmgpu_alf_chroma_aps chromaAps{};
+  bool hasChromaAps = false;
+  std::vector<uint8_t> ctuEnable[3], ctuAlt[2], ccIdc[2];
+  std::vector<int16_t> filterIdx;
+  const vtmgpu_alf_params* view();
+};
+
+// LoopFilter::xDeblockCU (LoopFilter.cpp:261-408) and everything it calls except the sample filters,
+// re-stated to EMIT one record per edge segment instead of filtering (records: include/vtmgpu.h).
+void deriveDeblockRecords(CodingStructure& cs, FlatDeblock& out);
+
+// SAOBlkParam[] (TypeDef.h:938-963) + neighbour availability (SampleAdaptiveOffset.cpp:668-729) + merge
+// candidate availability (getMergeList, :173-227)
+void flattenSao(CodingStructure& cs, const SAOBlkParam* blk, int log2ScaleLuma, int log2ScaleChroma, FlatSao& out);
+// writes the reconstructed parameters back (SAOProcess side effect, SampleAdaptiveOffset.cpp:247,255)
+void writeBackSao(const FlatSao& in, SAOBlkParam* blk);
+
+// slice / APS / per-CTU ALF control data read by ALFProcess (AdaptiveLoopFilter.cpp:393-456, :620-649)
+void flattenAlf(CodingStructure& cs, const CcAlfFilterParam& cc, uint8_t* const ccControl[2], FlatAlf& out);
+
+}   // namespace vtmshim
