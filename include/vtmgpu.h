@@ -194,6 +194,8 @@ typedef struct vtmgpu_alf_params
 typedef struct vtmgpu_ctx vtmgpu_ctx;
 
 int          vtmgpu_abi_version(void);
+int          vtmgpu_abi_sizeof(int which);   /* sizeof of ABI struct #which (0 seq, 1 deblock, 2 sao_offset, 3 sao_ctu, 4 sao_params,
+                                                5 alf_luma_aps, 6 alf_chroma_aps, 7 alf_params) for binding self-checks */
 const char*  vtmgpu_last_error(const vtmgpu_ctx* ctx);   /* ctx may be NULL: error of the last failed create */
 
 int  vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out);
@@ -202,6 +204,10 @@ void vtmgpu_destroy(vtmgpu_ctx* ctx);
 /* host planes (int16 samples, stride in samples) <-> device slot; plane[1], plane[2] ignored for 4:0:0 */
 int vtmgpu_upload  (vtmgpu_ctx* ctx, int slot, const int16_t* const plane[3], const ptrdiff_t stride[3]);
 int vtmgpu_download(vtmgpu_ctx* ctx, int slot, int16_t* const plane[3], const ptrdiff_t stride[3]);
+/* the same, enqueued on the ctx stream without waiting (host memory must stay valid until vtmgpu_sync; truly
+ * asynchronous only from/to page-locked host memory) */
+int vtmgpu_upload_async  (vtmgpu_ctx* ctx, int slot, const int16_t* const plane[3], const ptrdiff_t stride[3]);
+int vtmgpu_download_async(vtmgpu_ctx* ctx, int slot, int16_t* const plane[3], const ptrdiff_t stride[3]);
 
 /* per-picture side information (host pointers; copied before return, never retained) */
 int vtmgpu_set_deblock(vtmgpu_ctx* ctx, int slot, const vtmgpu_deblock_params* p);   /* NULL = stage off */

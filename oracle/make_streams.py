@@ -39,15 +39,18 @@ STREAMS = {
     "ai_416x240":   (416, 240, 420, 2, 77, 14, 32, [AI], ["--TemporalSubsampleRatio=1"], 0),
     "ld444_416x240": (416, 240, 444, 4, 444, 14, 30, [LD, "444/yuv444.cfg"], [], 0),
     "ra_q22_416x240": (416, 240, 420, 5, 99, 20, 22, [RA], [], 0),
+    # chroma correlated with the luma texture (seed >= 9000 selects that content): makes the encoder pick CC-ALF
+    "ai_cc_416x240": (416, 240, 420, 2, 9001, 14, 27, [AI], ["--TemporalSubsampleRatio=1"], 0),
+    "ld444_cc_416x240": (416, 240, 444, 3, 9002, 14, 27, [LD, "444/yuv444.cfg"], [], 0),
     "ld_q37_832x480": (832, 480, 420, 3, 5, 10, 37, [LD], K, 0),
     # BASELINE.json configs 2..5 (fast flags K)
     "ra_1080p":     (1920, 1080, 420, 32, 4321, 14, 32, [RA], K, 0),
-    "ra_2160p_a":   (3840, 2160, 420, 64, 2160, 14, 32, [RA], K, 0),     # frames 0..31
-    "ra_2160p_b":   (3840, 2160, 420, 64, 2160, 14, 32, [RA], K, 32),    # frames 32..63
+    "ra_2160p_a":   (3840, 2160, 420, 64, 9160, 14, 32, [RA], K, 0),     # frames 0..31
+    "ra_2160p_b":   (3840, 2160, 420, 64, 9160, 14, 32, [RA], K, 32),    # frames 32..63
     "ai_4320p":     (7680, 4320, 420, 1, 4320, 14, 32, [AI], K + ["--TemporalSubsampleRatio=1"], 0),
     "ld444_1080p":  (1920, 1080, 444, 16, 444, 14, 32, [LD, "444/yuv444.cfg"], K, 0),
     # short 4K clip for fast turnaround (first 8 pictures of the config-3 source)
-    "ra_2160p_8":   (3840, 2160, 420, 8, 2160, 14, 32, [RA], K, 0),
+    "ra_2160p_8":   (3840, 2160, 420, 8, 9160, 14, 32, [RA], K, 0),
 }
 
 
@@ -67,6 +70,10 @@ def gen_yuv(path, W, H, chroma, frames, seed, sigma):
                  + rng.normal(0, sigma / 2, cy.shape))
             v = (512 + 200 * np.cos((cy / cs + 2 * t) / 23.0) + 60 * (((cx / cs + 4 * t) // 24) % 2)
                  + rng.normal(0, sigma / 2, cy.shape))
+            if seed >= 9000:   # CC-ALF content: chroma carries a blurred copy of the luma structure
+                yd = y[::sy, ::sx] if chroma == 420 else y
+                u = 512 + 0.45 * (yd - 512) + rng.normal(0, sigma / 2, cy.shape)
+                v = 512 - 0.35 * (yd - 512) + 40 * np.sin(cx / 17.0) + rng.normal(0, sigma / 2, cy.shape)
             for p in (y, u, v):
                 f.write(np.clip(p, 0, 1023).astype("<u2").tobytes())
 

@@ -1,0 +1,122 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against (a) the reference's stage outputs in the golden
+fixtures, (b) the SEI MD5 of the reference encoder, (c) the oracle on seeded synthetic pictures of other sizes,
+chroma formats and bit depths.  Bar: bit-exact (integer sample work)."""
+import numpy as np
+import pytest
+
+import pyoracle
+from conftest import golden_names, load_golden, plane_md5
+from vvc_b200 import gpu, synth
+
+pytestmark = pytest.mark.gpu
+NAMES = golden_names()
+
+
+def _eq(a, b, what):
+    for c in range(len(a)):
+        if not np.array_equal(a[c], b[c]):
+            bad = np.argwhere(a[c] != b[c])
+            raise AssertionError("%s: component %d differs at %d samples, first (y,x)=%s got %d want %d" %
+                                 (what, c, len(bad), tuple(bad[0]), a[c][tuple(bad[0])], b[c][tuple(bad[0])]))
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_golden_staged(name):
+    """loopFilterPic / SAOProcess / ALFProcess one by one, compared with the reference after every stage."""
+    cap = load_golden(name)
+    out = gpu.execute_loop_filters(cap, fused=False)
+    _eq(out["dbf"], cap.stage["dbf"], "deblocking")
+    if cap.stage["sao"] is not None:
+        _eq(out["sao"], cap.stage["sao"], "SAO")
+    if cap.stage["alf"] is not None:
+        _eq(out["alf"], cap.stage["alf"], "ALF")
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_golden_fused_md5(name, manifest):
+    """whole chain with SAO fused into the ALF pass == decoded picture hash of the reference encoder"""
+    cap = load_golden(name)
+    out = gpu.execute_loop_filters(cap, fused=True)["final"]
+    assert [plane_md5(p) for p in out] == manifest[name]["sei_md5"]
+
+
+SYNTH = [
+    # width, height, chroma_format, bit depth, ctu, density
+    (128, 128, 1, 10, 128, 1.0),      # a single CTU
+    (136, 72, 1, 10, 128, 0.7),       # ragged: smaller than one tile in both directions
+    (416, 240, 1, 10, 128, 0.6),
+    (456, 264, 3, 10, 128, 0.8),      # 4:4:4, partial CTUs / partial tiles
+    (448, 256, 2, 10, 128, 0.8),      # 4:2:2
+    (320, 192, 0, 10, 128, 0.8),      # 4:0:0
+    (384, 256, 1, 8, 128, 0.8),       # 8-bit
+    (384, 256, 1, 12, 128, 0.8),      # 12-bit
+    (384, 320, 1, 10, 64, 0.8),       # CTU 64
+    (1920, 1080, 1, 10, 128, 0.5),
+]
+
+
+@pytest.mark.parametrize("w,h,cf,bd,ctu,density", SYNTH)
+def test_synthetic_vs_oracle(w, h, cf, bd, ctu, density):
+    cap = synth.make_picture(w, h, chroma_format=cf, bit_depth=bd, ctu_size=ctu, seed=w + h + cf, density=density)
+    want = pyoracle.filter_capture(cap)
+    got = gpu.execute_loop_filters(cap, fused=False)
+    for st in ("dbf", "sao", "alf"):
+        _eq(got[st], want[st], st)
+    fused = gpu.execute_loop_filters(cap, fused=True)["final"]
+    _eq(fused, want["final"], "fused chain")
+
+
+def test_stage_switches():
+    """NULL side info switches a stage off: the picture must pass through unchanged."""
+    cap = synth.make_picture(256, 128, seed=5)
+    ctx = gpu.Context(cap.seq)
+    ctx.upload(0, cap.pre)
+    ctx.set_deblock(0, None)
+    ctx.set_sao(0, None)
+    ctx.set_alf(0, None)
+    ctx.filter(0, 1)
+    _eq(ctx.download(0), cap.pre, "all stages off")
+    ctx.close()
+
+
+def test_batch_of_slots_and_rewind():
+    """picture-parallel: several independent pictures in one launch sequence; rewind repeats the result"""
+    caps = [synth.make_picture(384, 256, seed=s, density=0.7) for s in range(5)]
+    want = [pyoracle.filter_capture(c)["final"] for c in caps]
+    ctx = gpu.Context(caps[0].seq, capacity=len(caps))
+    for s, c in enumerate(caps):
+        ctx.set_capture(s, c)
+    for rep in range(2):
+        ctx.filter(0, len(caps))
+        for s in range(len(caps)):
+            _eq(ctx.download(s), want[s], "slot %d rep %d" % (s, rep))
+        ctx.rewind(0, len(caps))
+    assert ctx.launch_count() == 4
+    ctx.close()
+
+
+def test_full_size_4k_properties():
+    """3840x2160 (BASELINE config 3 size): GPU == oracle on one forced-on picture, and the chain is deterministic."""
+    cap = synth.make_picture(3840, 2160, seed=2160, density=1.0)
+    ctx = gpu.Context(cap.seq)
+    ctx.set_capture(0, cap)
+    ctx.filter(0, 1)
+    a = ctx.download(0)
+    ctx.rewind(0, 1)
+    ctx.filter(0, 1)
+    b = ctx.download(0)
+    ctx.close()
+    _eq(a, b, "determinism")
+    _eq(a, pyoracle.filter_capture(cap)["final"], "4K forced-on vs oracle")
+
+
+def test_bad_arguments_fail_loudly():
+    cap = synth.make_picture(256, 128, seed=1)
+    ctx = gpu.Context(cap.seq)
+    with pytest.raises(gpu.VtmGpuError):
+        ctx.filter(0, 2)                       # capacity is 1
+    p = cap.alf_params()
+    p.num_ctus += 1
+    with pytest.raises(gpu.VtmGpuError):
+        ctx.set_alf(0, p)
+    ctx.close()

@@ -1,0 +1,372 @@
+// dbf_kernel.cuh -- deblocking filter (LoopFilter::loopFilterPic, LoopFilter.cpp:145) for sm_100a.
+//
+// One CTA filters one TW x TH tile of one plane, BOTH passes fused through shared memory:
+//   load (TW+16) x (TH+16) samples (8-sample aligned, 128-bit coalesced)  ->  all vertical edges of the tile incl.
+//   the 8-row halo (pass 1 of the reference)  ->  __syncthreads  ->  all horizontal edges (pass 2, which reads the
+//   V-filtered samples)  ->  store the TW x TH own region (128-bit coalesced) to the OUTPUT plane.
+// The two edges on the tile border are evaluated by both neighbouring tiles (each keeps only its own side), so no
+// inter-CTA ordering is needed and input/output planes are distinct.  Why the halo of 8 suffices: tile origins are
+// multiples of 64, every block side >= 32 samples starts on a multiple of 16, hence an edge 4 samples outside the
+// tile can modify at most 3 samples on the tile's side of it.
+//
+// Work items: one thread per 4-sample edge segment; the per-segment decisions follow xEdgeFilterLuma
+// (LoopFilter.cpp:971-1080) / xEdgeFilterChroma (:1246-1279) and the filters :1302-1555, driven by the packed
+// segment records of include/vtmgpu.h.  HBM traffic per plane: read (1 + halo) + write 1 samples, records 0.25 B/px.
+#pragma once
+
+#include "vtmgpu_dev.cuh"
+#include "vtmgpu.h"
+
+namespace vtmgpu
+{
+
+constexpr int DBF_TW = 128, DBF_TH = 64, DBF_HALO = 8;
+constexpr int DBF_SW = DBF_TW + 2 * DBF_HALO;           // 144
+constexpr int DBF_SH = DBF_TH + 2 * DBF_HALO;           // 80
+constexpr int DBF_PITCH = DBF_SW + 8;                   // 152 samples = 304 B: rows shift by 12 banks
+constexpr int DBF_THREADS = 256;
+
+// x points at q0 of one line in shared memory; o = step across the edge; P(k) = x[-(k+1)*o], Q(k) = x[k*o]
+#define PK(k) ((int)x[-((k) + 1) * o])
+#define QK(k) ((int)x[(k) * o])
+
+__device__ __forceinline__ bool dbfStrongShort(const pel* x, int o, int d, int beta, int tc, bool pOne)
+{
+  const int sp3 = pOne ? iabs(PK(1) - PK(0)) : iabs(PK(3) - PK(0));
+  const int sq3 = iabs(QK(3) - QK(0));
+  return (sp3 + sq3 < (beta >> 3)) && (d < (beta >> 2)) && (iabs(PK(0) - QK(0)) < ((tc * 5 + 1) >> 1));
+}
+
+__device__ __forceinline__ bool dbfStrongLong(const pel* x, int o, int d, int beta, int tc, bool largeP, bool largeQ, int lenP, int lenQ)
+{
+  int sp3 = iabs(PK(3) - PK(0));
+  int sq3 = iabs(QK(3) - QK(0));
+  if (largeP)
+  {
+    int far;
+    if (lenP == 7) { far = PK(7); sp3 += iabs(PK(4) - PK(5) - PK(6) + far); }
+    else           { far = PK(5); }
+    sp3 = (sp3 + iabs(PK(3) - far) + 1) >> 1;
+  }
+  if (largeQ)
+  {
+    int far;
+    if (lenQ == 7) { far = QK(7); sq3 += iabs(QK(4) - QK(5) - QK(6) + far); }
+    else           { far = QK(5); }
+    sq3 = (sq3 + iabs(far - QK(3)) + 1) >> 1;
+  }
+  return (sp3 + sq3 < ((beta * 3) >> 5)) && (d < (beta >> 4)) && (iabs(PK(0) - QK(0)) < ((tc * 5 + 1) >> 1));
+}
+
+// bilinear long filter of one line (xFilteringPandQ / xBilinearFilter); nP,nQ in {3,5,7}, not both 3
+__device__ void dbfLongLine(pel* x, int o, int nP, int nQ, int tc, bool wP, bool wQ)
+{
+  int p[8], q[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) { p[k] = PK(k); q[k] = QK(k); }
+  const int refP = nP == 7 ? (p[6] + p[7] + 1) >> 1 : (nP == 5 ? (p[4] + p[5] + 1) >> 1 : (p[2] + p[3] + 1) >> 1);
+  const int refQ = nQ == 7 ? (q[6] + q[7] + 1) >> 1 : (nQ == 5 ? (q[4] + q[5] + 1) >> 1 : (q[2] + q[3] + 1) >> 1);
+  int mid;
+  if (nP == nQ)
+  {
+    if (nP == 5) mid = (2 * (p[0] + q[0] + p[1] + q[1] + p[2] + q[2]) + p[3] + q[3] + p[4] + q[4] + 8) >> 4;
+    else         mid = (2 * (p[0] + q[0]) + p[1] + q[1] + p[2] + q[2] + p[3] + q[3] + p[4] + q[4] + p[5] + q[5] + p[6] + q[6] + 8) >> 4;
+  }
+  else
+  {
+    const int nL = max(nP, nQ), nS = min(nP, nQ);
+    if (nL == 7 && nS == 5)
+      mid = (2 * (p[0] + q[0] + p[1] + q[1]) + p[2] + q[2] + p[3] + q[3] + p[4] + q[4] + p[5] + q[5] + 8) >> 4;
+    else if (nL == 7 && nS == 3)
+    {
+      const bool pl = nP > nQ;
+      const int L0 = pl ? p[0] : q[0], S0 = pl ? q[0] : p[0], S1 = pl ? q[1] : p[1], S2 = pl ? q[2] : p[2];
+      int sumL = 0;
+#pragma unroll
+      for (int k = 1; k < 7; k++) sumL += pl ? p[k] : q[k];
+      mid = (2 * (L0 + S0) + S0 + 2 * (S1 + S2) + S1 + sumL + 8) >> 4;
+    }
+    else
+      mid = (p[0] + q[0] + p[1] + q[1] + p[2] + q[2] + p[3] + q[3] + 4) >> 3;
+  }
+  // dbCoeffs{7,5,3} are arithmetic progressions: 59-9k, 58-13k, 53-21k ; tc scale {6,5,4,3,2,1,1} or {6,4,2}
+  if (wP)
+  {
+    const int c0 = nP == 7 ? 59 : (nP == 5 ? 58 : 53), cd = nP == 7 ? 9 : (nP == 5 ? 13 : 21);
+#pragma unroll
+    for (int k = 0; k < 7; k++)
+      if (k < nP)
+      {
+        const int c = c0 - cd * k, t = nP == 3 ? 6 - 2 * k : max(6 - k, 1);
+        const int cv = (tc * t) >> 1;
+        x[-(k + 1) * o] = (pel)clip3(p[k] - cv, p[k] + cv, (mid * c + refP * (64 - c) + 32) >> 6);
+      }
+  }
+  if (wQ)
+  {
+    const int c0 = nQ == 7 ? 59 : (nQ == 5 ? 58 : 53), cd = nQ == 7 ? 9 : (nQ == 5 ? 13 : 21);
+#pragma unroll
+    for (int k = 0; k < 7; k++)
+      if (k < nQ)
+      {
+        const int c = c0 - cd * k, t = nQ == 3 ? 6 - 2 * k : max(6 - k, 1);
+        const int cv = (tc * t) >> 1;
+        x[k * o] = (pel)clip3(q[k] - cv, q[k] + cv, (mid * c + refQ * (64 - c) + 32) >> 6);
+      }
+  }
+}
+
+__device__ __forceinline__ void dbfLumaLine(pel* x, int o, int tc, bool strong, bool wP, bool wQ, bool secondP, bool secondQ, int maxv)
+{
+  const int p0 = PK(0), p1 = PK(1), p2 = PK(2), q0 = QK(0), q1 = QK(1), q2 = QK(2);
+  if (strong)
+  {
+    const int p3 = PK(3), q3 = QK(3);
+    if (wP)
+    {
+      x[-1 * o] = (pel)clip3(p0 - 3 * tc, p0 + 3 * tc, (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
+      x[-2 * o] = (pel)clip3(p1 - 2 * tc, p1 + 2 * tc, (p2 + p1 + p0 + q0 + 2) >> 2);
+      x[-3 * o] = (pel)clip3(p2 - tc, p2 + tc, (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
+    }
+    if (wQ)
+    {
+      x[0]     = (pel)clip3(q0 - 3 * tc, q0 + 3 * tc, (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
+      x[1 * o] = (pel)clip3(q1 - 2 * tc, q1 + 2 * tc, (p0 + q0 + q1 + q2 + 2) >> 2);
+      x[2 * o] = (pel)clip3(q2 - tc, q2 + tc, (p0 + q0 + q1 + 3 * q2 + 2 * q3 + 4) >> 3);
+    }
+    return;
+  }
+  int delta = (9 * (q0 - p0) - 3 * (q1 - p1) + 8) >> 4;
+  if (iabs(delta) >= tc * 10) return;
+  delta = clip3(-tc, tc, delta);
+  const int tc2 = tc >> 1;
+  if (wP)
+  {
+    x[-1 * o] = (pel)clip3(0, maxv, p0 + delta);
+    if (secondP) x[-2 * o] = (pel)clip3(0, maxv, p1 + clip3(-tc2, tc2, (((p2 + p0 + 1) >> 1) - p1 + delta) >> 1));
+  }
+  if (wQ)
+  {
+    x[0] = (pel)clip3(0, maxv, q0 - delta);
+    if (secondQ) x[1 * o] = (pel)clip3(0, maxv, q1 + clip3(-tc2, tc2, (((q2 + q0 + 1) >> 1) - q1 - delta) >> 1));
+  }
+}
+
+// one 4-line luma segment; x0 = q0 of line 0, o = across, s = along
+__device__ void dbfLumaSegment(pel* x0, int o, int s, uint32_t rec, int maxv)
+{
+  const int tc = rec & 0x7ff;
+  const int beta = (rec >> VTMGPU_DBF_L_BETA_SHIFT) & 0x7ff;
+  const int lenP = (rec >> VTMGPU_DBF_L_LENP_SHIFT) & 7, lenQ = (rec >> VTMGPU_DBF_L_LENQ_SHIFT) & 7;
+  const bool wP = !(rec & VTMGPU_DBF_L_PNOFILT), wQ = !(rec & VTMGPU_DBF_L_QNOFILT);
+  const bool largeP = lenP > 3 && !(rec & VTMGPU_DBF_L_CTUROW), largeQ = lenQ > 3;
+  const int sideThr = (beta + (beta >> 1)) >> 3;
+  const pel* x = x0;
+  const int dp0 = iabs(PK(2) - 2 * PK(1) + PK(0)), dq0 = iabs(QK(0) - 2 * QK(1) + QK(2));
+  x = x0 + 3 * s;
+  const int dp3 = iabs(PK(2) - 2 * PK(1) + PK(0)), dq3 = iabs(QK(0) - 2 * QK(1) + QK(2));
+
+  if (largeP || largeQ)
+  {
+    int dp0L = dp0, dq0L = dq0, dp3L = dp3, dq3L = dq3;
+    if (largeP)
+    {
+      x = x0;         dp0L = (dp0L + iabs(PK(5) - 2 * PK(4) + PK(3)) + 1) >> 1;
+      x = x0 + 3 * s; dp3L = (dp3L + iabs(PK(5) - 2 * PK(4) + PK(3)) + 1) >> 1;
+    }
+    if (largeQ)
+    {
+      x = x0;         dq0L = (dq0L + iabs(QK(3) - 2 * QK(4) + QK(5)) + 1) >> 1;
+      x = x0 + 3 * s; dq3L = (dq3L + iabs(QK(3) - 2 * QK(4) + QK(5)) + 1) >> 1;
+    }
+    const int d0L = dp0L + dq0L, d3L = dp3L + dq3L;
+    if (d0L + d3L < beta && dbfStrongLong(x0, o, 2 * d0L, beta, tc, largeP, largeQ, lenP, lenQ) &&
+        dbfStrongLong(x0 + 3 * s, o, 2 * d3L, beta, tc, largeP, largeQ, lenP, lenQ))
+    {
+      for (int i = 0; i < 4; i++) dbfLongLine(x0 + i * s, o, largeP ? lenP : 3, largeQ ? lenQ : 3, tc, wP, wQ);
+      return;
+    }
+  }
+  const int d0 = dp0 + dq0, d3 = dp3 + dq3;
+  if (d0 + d3 < beta)
+  {
+    bool secondP = false, secondQ = false, strong = false;
+    if (lenP > 1 && lenQ > 1)
+    {
+      secondP = (dp0 + dp3) < sideThr;
+      secondQ = (dq0 + dq3) < sideThr;
+    }
+    if (lenP > 2 && lenQ > 2)
+      strong = dbfStrongShort(x0, o, 2 * d0, beta, tc, false) && dbfStrongShort(x0 + 3 * s, o, 2 * d3, beta, tc, false);
+#pragma unroll
+    for (int i = 0; i < 4; i++) dbfLumaLine(x0 + i * s, o, tc, strong, wP, wQ, secondP, secondQ, maxv);
+  }
+}
+
+__device__ __forceinline__ void dbfChromaLine(pel* x, int o, int tc, bool strong, bool ctb, bool wP, bool wQ, int maxv)
+{
+  const int p0 = PK(0), p1 = PK(1), q0 = QK(0), q1 = QK(1);
+  if (strong)
+  {
+    const int p2 = PK(2), p3 = PK(3), q2 = QK(2), q3 = QK(3);
+    if (ctb)
+    {
+      if (wP) x[-1 * o] = (pel)clip3(p0 - tc, p0 + tc, (3 * p1 + 2 * p0 + q0 + q1 + q2 + 4) >> 3);
+      if (wQ) x[0]      = (pel)clip3(q0 - tc, q0 + tc, (2 * p1 + p0 + 2 * q0 + q1 + q2 + q3 + 4) >> 3);
+    }
+    else
+    {
+      if (wP)
+      {
+        x[-3 * o] = (pel)clip3(p2 - tc, p2 + tc, (3 * p3 + 2 * p2 + p1 + p0 + q0 + 4) >> 3);
+        x[-2 * o] = (pel)clip3(p1 - tc, p1 + tc, (2 * p3 + p2 + 2 * p1 + p0 + q0 + q1 + 4) >> 3);
+        x[-1 * o] = (pel)clip3(p0 - tc, p0 + tc, (p3 + p2 + p1 + 2 * p0 + q0 + q1 + q2 + 4) >> 3);
+      }
+      if (wQ) x[0] = (pel)clip3(q0 - tc, q0 + tc, (p2 + p1 + p0 + 2 * q0 + q1 + q2 + q3 + 4) >> 3);
+    }
+    if (wQ)
+    {
+      x[1 * o] = (pel)clip3(q1 - tc, q1 + tc, (p1 + p0 + q0 + 2 * q1 + q2 + 2 * q3 + 4) >> 3);
+      x[2 * o] = (pel)clip3(q2 - tc, q2 + tc, (p0 + q0 + q1 + 2 * q2 + 3 * q3 + 4) >> 3);
+    }
+    return;
+  }
+  const int delta = clip3(-tc, tc, (((q0 - p0) << 2) + p1 - q1 + 4) >> 3);
+  if (wP) x[-1 * o] = (pel)clip3(0, maxv, p0 + delta);
+  if (wQ) x[0]      = (pel)clip3(0, maxv, q0 - delta);
+}
+
+// one chroma segment of n (2 or 4) lines of one component
+__device__ void dbfChromaSegment(pel* x0, int o, int s, int n, int tc, int beta, bool large, bool ctb, bool wP, bool wQ, int maxv)
+{
+  bool strong = false;
+  if (large)
+  {
+    const int l3 = (n == 2 ? 1 : 3) * s;
+    const pel* x = x0;
+    const int dp0 = ctb ? iabs(PK(0) - PK(1)) : iabs(PK(2) - 2 * PK(1) + PK(0));
+    const int dq0 = iabs(QK(0) - 2 * QK(1) + QK(2));
+    x = x0 + l3;
+    const int dp3 = ctb ? iabs(PK(0) - PK(1)) : iabs(PK(2) - 2 * PK(1) + PK(0));
+    const int dq3 = iabs(QK(0) - 2 * QK(1) + QK(2));
+    const int d0 = dp0 + dq0, d3 = dp3 + dq3;
+    if (d0 + d3 < beta)
+      strong = dbfStrongShort(x0, o, 2 * d0, beta, tc, ctb) && dbfStrongShort(x0 + l3, o, 2 * d3, beta, tc, ctb);
+  }
+  for (int i = 0; i < n; i++) dbfChromaLine(x0 + i * s, o, tc, strong, ctb, wP, wQ, maxv);
+}
+#undef PK
+#undef QK
+
+struct DbfLaunch
+{
+  int tilesXL, tilesL;      // luma tile grid
+  int tilesXC, tilesC;      // per chroma plane
+};
+
+__global__ void __launch_bounds__(DBF_THREADS) k_deblock(const SlotDev* __restrict__ slots, int firstSlot, int srcBuf, int dstBuf, Geom g, DbfLaunch L)
+{
+  __shared__ __align__(16) pel sm[DBF_SH * DBF_PITCH];
+  const SlotDev& S = slots[firstSlot + blockIdx.y];
+  int t = blockIdx.x, comp = 0;
+  if (t >= L.tilesL) { t -= L.tilesL; comp = 1 + t / L.tilesC; t -= (comp - 1) * L.tilesC; }
+  const int tilesX = comp ? L.tilesXC : L.tilesXL;
+  const int x0 = (t % tilesX) * DBF_TW, y0 = (t / tilesX) * DBF_TH;
+  const PlaneDev src = S.buf[srcBuf][comp], dst = S.buf[dstBuf][comp];
+  const int w = src.w, h = src.h;
+  const int tid = threadIdx.x;
+
+  // ---- load tile + halo: (DBF_SW/8) groups x DBF_SH rows, 128-bit each --------------------------------
+  constexpr int GROUPS = DBF_SW / 8;
+  for (int i = tid; i < GROUPS * DBF_SH; i += DBF_THREADS)
+  {
+    const int r = i / GROUPS, gcol = i - r * GROUPS;
+    const int y = y0 - DBF_HALO + r, x = x0 - DBF_HALO + gcol * 8;
+    int4 v = make_int4(0, 0, 0, 0);
+    if (y >= 0 && y < h && x >= 0 && x < w) v = __ldg(reinterpret_cast<const int4*>(src.p + (size_t)y * src.pitch + x));
+    *reinterpret_cast<int4*>(&sm[r * DBF_PITCH + gcol * 8]) = v;
+  }
+  __syncthreads();
+
+  if (S.dbfOn)
+  {
+    const int maxv = (1 << (comp ? g.bdC : g.bdL)) - 1;
+    if (comp == 0)
+    {
+      const int uw = g.w >> 2;
+      // pass 1: vertical edges x0 .. x0+TW (step 4), all rows of tile + halo
+      constexpr int NE = DBF_TW / 4 + 1, NS = DBF_SH / 4;
+      for (int i = tid; i < NE * NS; i += DBF_THREADS)
+      {
+        const int sg = i / NE, e = i - sg * NE;
+        const int x = x0 + 4 * e, y = y0 - DBF_HALO + 4 * sg;
+        if (x <= 0 || x >= w || y < 0 || y >= h) continue;
+        const uint32_t rec = __ldg(&S.dbfL[0][(y >> 2) * uw + (x >> 2)]);
+        if (rec & 0x7ff) dbfLumaSegment(&sm[(4 * sg) * DBF_PITCH + DBF_HALO + 4 * e], 1, DBF_PITCH, rec, maxv);
+      }
+      __syncthreads();
+      // pass 2: horizontal edges y0 .. y0+TH (step 4), own columns
+      constexpr int NEH = DBF_TH / 4 + 1, NSH = DBF_TW / 4;
+      for (int i = tid; i < NEH * NSH; i += DBF_THREADS)
+      {
+        const int e = i / NSH, sg = i - e * NSH;
+        const int x = x0 + 4 * sg, y = y0 + 4 * e;
+        if (y <= 0 || y >= h || x >= w) continue;
+        const uint32_t rec = __ldg(&S.dbfL[1][(y >> 2) * uw + (x >> 2)]);
+        if (rec & 0x7ff) dbfLumaSegment(&sm[(DBF_HALO + 4 * e) * DBF_PITCH + DBF_HALO + 4 * sg], DBF_PITCH, 1, rec, maxv);
+      }
+    }
+    else
+    {
+      const int c = comp - 1;
+      const int tcShift = c ? VTMGPU_DBF_C_TCCR_SHIFT : 0, betaShift = c ? VTMGPU_DBF_C_BETACR_SHIFT : VTMGPU_DBF_C_BETACB_SHIFT;
+      // pass 1: vertical edges on the 8-sample chroma grid; one item = the chroma rows of one 4-luma-row unit
+      {
+        const int n = 4 >> g.sy, cols0 = (g.w + (8 << g.sx) - 1) / (8 << g.sx);
+        constexpr int NE = DBF_TW / 8 + 1;
+        const int NS = DBF_SH / n;
+        for (int i = tid; i < NE * NS; i += DBF_THREADS)
+        {
+          const int sg = i / NE, e = i - sg * NE;
+          const int x = x0 + 8 * e, y = y0 - DBF_HALO + n * sg;
+          if (x <= 0 || x >= w || y < 0 || y >= h) continue;
+          const uint64_t rec = __ldg(&S.dbfC[0][(y / n) * cols0 + (x >> 3)]);
+          const int tc = (int)(rec >> tcShift) & 0x7ff;
+          if (tc)
+            dbfChromaSegment(&sm[(n * sg) * DBF_PITCH + DBF_HALO + 8 * e], 1, DBF_PITCH, n, tc, (int)(rec >> betaShift) & 0x7ff,
+                             (rec & VTMGPU_DBF_C_LARGE) != 0, (rec & VTMGPU_DBF_C_CTB) != 0, !(rec & VTMGPU_DBF_C_PNOFILT), !(rec & VTMGPU_DBF_C_QNOFILT), maxv);
+        }
+      }
+      __syncthreads();
+      {
+        const int n = 4 >> g.sx, uw = g.w >> 2;
+        constexpr int NEH = DBF_TH / 8 + 1;
+        const int NSH = DBF_TW / n;
+        for (int i = tid; i < NEH * NSH; i += DBF_THREADS)
+        {
+          const int e = i / NSH, sg = i - e * NSH;
+          const int x = x0 + n * sg, y = y0 + 8 * e;
+          if (y <= 0 || y >= h || x >= w) continue;
+          const uint64_t rec = __ldg(&S.dbfC[1][(y >> 3) * uw + (x / n)]);
+          const int tc = (int)(rec >> tcShift) & 0x7ff;
+          if (tc)
+            dbfChromaSegment(&sm[(DBF_HALO + 8 * e) * DBF_PITCH + DBF_HALO + n * sg], DBF_PITCH, 1, n, tc, (int)(rec >> betaShift) & 0x7ff,
+                             (rec & VTMGPU_DBF_C_LARGE) != 0, (rec & VTMGPU_DBF_C_CTB) != 0, !(rec & VTMGPU_DBF_C_PNOFILT), !(rec & VTMGPU_DBF_C_QNOFILT), maxv);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- store own region -----------------------------------------------------------------------------------
+  constexpr int OG = DBF_TW / 8;
+  for (int i = tid; i < OG * DBF_TH; i += DBF_THREADS)
+  {
+    const int r = i / OG, gcol = i - r * OG;
+    const int y = y0 + r, x = x0 + gcol * 8;
+    if (y < h && x < w)
+      *reinterpret_cast<int4*>(dst.p + (size_t)y * dst.pitch + x) = *reinterpret_cast<const int4*>(&sm[(DBF_HALO + r) * DBF_PITCH + DBF_HALO + gcol * 8]);
+  }
+}
+
+}   // namespace vtmgpu

@@ -1,0 +1,610 @@
+// vtmgpu.cu -- libvtmgpu: host side of the C ABI (include/vtmgpu.h) + kernel launches.  sm_100a only, no CPU path.
+//
+// HBM layout per picture slot (sized for 180 GB: a 3840x2160 4:2:0 slot is 3 x 24.9 MB planes + 6.3 MB side info):
+//   buf[0]  pristine upload (kept so a replay can rewind without another H2D)
+//   buf[1]  deblocked picture            (k_deblock: buf[0] -> buf[1])
+//   buf[2]  final picture                (k_sao_alf: buf[1] -> buf[2])
+//   side    one contiguous block: luma/chroma segment records of both directions, SaoDev[ctus][3], ALF per-CTU
+//           control bytes, filter indices, AlfDev (coefficient tables) -- mirrored in pinned host memory so the
+//           set_* calls are a pack + one async H2D each.
+// All work of a ctx is enqueued on its own stream; stage calls synchronise unless named *_async.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "dbf_kernel.cuh"
+#include "saoalf_kernel.cuh"
+#include "vtmgpu.h"
+#include "vvc_alf_fixed_tables.h"
+
+using namespace vtmgpu;
+
+namespace
+{
+std::string g_createError;
+
+struct SideLayout     // byte offsets inside a slot's side-info block
+{
+  size_t dbfL[2], dbfC[2], sao, alfCtu, alfIdx, alf, total;
+  size_t nL, nC[2];
+};
+
+size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
+}   // namespace
+
+struct vtmgpu_ctx
+{
+  vtmgpu_seq_params seq{};
+  Geom g{};
+  int nCtus = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[2] = { nullptr, nullptr };
+  cudaEvent_t stageEv[3] = { nullptr, nullptr, nullptr };
+  bool profiling = false, stageValid = false;
+  std::string err;
+  SideLayout lay{};
+  std::vector<pel*> planeMem;          // one allocation per slot (3 buffers x ncomp planes)
+  std::vector<unsigned char*> sideDev; // per slot
+  unsigned char* sidePinned = nullptr; // capacity * lay.total
+  SlotDev* slotsPinned = nullptr;      // capacity entries (pinned mirror)
+  SlotDev* slotsDev = nullptr;
+  std::vector<int> cur;                // buffer index holding the current state of each slot
+  int64_t launches = 0;
+
+  int fail(const char* fmt, ...)
+  {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    err = buf;
+    return -1;
+  }
+  int cuda(cudaError_t e, const char* what)
+  {
+    if (e == cudaSuccess) return 0;
+    return fail("%s: %s", what, cudaGetErrorString(e));
+  }
+  bool slotOk(int first, int count) { return first >= 0 && count >= 1 && first + count <= seq.capacity; }
+  unsigned char* pinnedSide(int slot) { return sidePinned + (size_t)slot * lay.total; }
+  int pushSlot(int slot) { return cuda(cudaMemcpyAsync(slotsDev + slot, slotsPinned + slot, sizeof(SlotDev), cudaMemcpyHostToDevice, stream), "slot table upload"); }
+  int pushSide(int slot, size_t off, size_t bytes)
+  {
+    return cuda(cudaMemcpyAsync(sideDev[slot] + off, pinnedSide(slot) + off, bytes, cudaMemcpyHostToDevice, stream), "side info upload");
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int vtmgpu_abi_version(void) { return VTMGPU_ABI_VERSION; }
+
+extern "C" const char* vtmgpu_last_error(const vtmgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_createError.c_str(); }
+
+// sizes of the ABI structures, so that language bindings can verify their mirrors
+extern "C" int vtmgpu_abi_sizeof(int which)
+{
+  switch (which)
+  {
+  case 0: return (int)sizeof(vtmgpu_seq_params);
+  case 1: return (int)sizeof(vtmgpu_deblock_params);
+  case 2: return (int)sizeof(vtmgpu_sao_offset);
+  case 3: return (int)sizeof(vtmgpu_sao_ctu);
+  case 4: return (int)sizeof(vtmgpu_sao_params);
+  case 5: return (int)sizeof(vtmgpu_alf_luma_aps);
+  case 6: return (int)sizeof(vtmgpu_alf_chroma_aps);
+  case 7: return (int)sizeof(vtmgpu_alf_params);
+  default: return -1;
+  }
+}
+
+extern "C" void vtmgpu_destroy(vtmgpu_ctx* c)
+{
+  if (!c) return;
+  cudaSetDevice(c->seq.device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (pel* p : c->planeMem) cudaFree(p);
+  for (unsigned char* p : c->sideDev) cudaFree(p);
+  if (c->sidePinned) cudaFreeHost(c->sidePinned);
+  if (c->slotsPinned) cudaFreeHost(c->slotsPinned);
+  if (c->slotsDev) cudaFree(c->slotsDev);
+  for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : c->stageEv) if (e) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
+{
+  if (!seq || !out) { g_createError = "vtmgpu_create: null argument"; return -1; }
+  *out = nullptr;
+  const vtmgpu_seq_params& s = *seq;
+  auto bad = [](const char* m) { g_createError = std::string("vtmgpu_create: ") + m; return -1; };
+  if (s.width <= 0 || s.height <= 0 || (s.width & 7) || (s.height & 7)) return bad("width/height must be positive multiples of 8");
+  if (s.chroma_format < 0 || s.chroma_format > 3) return bad("bad chroma_format");
+  if (s.bit_depth_luma < 8 || s.bit_depth_luma > 12 || s.bit_depth_chroma < 8 || s.bit_depth_chroma > 12) return bad("bit depth must be 8..12");
+  if (s.ctu_size != 64 && s.ctu_size != 128) return bad("ctu_size must be 64 or 128");
+  if (s.capacity < 1) return bad("capacity must be >= 1");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return bad("no CUDA device available (libvtmgpu has no CPU fallback)");
+  if (s.device < 0 || s.device >= ndev) return bad("bad device ordinal");
+  if ((e = cudaSetDevice(s.device)) != cudaSuccess) return bad(cudaGetErrorString(e));
+
+  vtmgpu_ctx* c = new vtmgpu_ctx();
+  c->seq = s;
+  Geom& g = c->g;
+  g.w = s.width; g.h = s.height;
+  g.sx = (s.chroma_format == 1 || s.chroma_format == 2) ? 1 : 0;
+  g.sy = (s.chroma_format == 1) ? 1 : 0;
+  g.ncomp = s.chroma_format == 0 ? 1 : 3;
+  g.bdL = s.bit_depth_luma; g.bdC = s.bit_depth_chroma;
+  g.ctu = s.ctu_size; g.ctuLog2 = s.ctu_size == 128 ? 7 : 6;
+  g.wCtus = (g.w + g.ctu - 1) / g.ctu; g.hCtus = (g.h + g.ctu - 1) / g.ctu;
+  c->nCtus = g.wCtus * g.hCtus;
+
+  SideLayout& L = c->lay;
+  L.nL = (size_t)(g.w / 4) * (g.h / 4);
+  L.nC[0] = g.ncomp > 1 ? (size_t)((g.w + (8 << g.sx) - 1) / (8 << g.sx)) * (g.h / 4) : 0;
+  L.nC[1] = g.ncomp > 1 ? (size_t)((g.h + (8 << g.sy) - 1) / (8 << g.sy)) * (g.w / 4) : 0;
+  size_t off = 0;
+  for (int d = 0; d < 2; d++) { L.dbfL[d] = off; off = alignUp(off + L.nL * 4, 256); }
+  for (int d = 0; d < 2; d++) { L.dbfC[d] = off; off = alignUp(off + L.nC[d] * 8, 256); }
+  L.sao = off;    off = alignUp(off + (size_t)c->nCtus * 3 * sizeof(SaoDev), 256);
+  L.alfCtu = off; off = alignUp(off + (size_t)c->nCtus * 8, 256);
+  L.alfIdx = off; off = alignUp(off + (size_t)c->nCtus * 2, 256);
+  L.alf = off;    off = alignUp(off + sizeof(AlfDev), 256);
+  L.total = off;
+
+#define CK(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_createError = std::string("vtmgpu_create: ") + what + ": " + cudaGetErrorString(e_); vtmgpu_destroy(c); return -1; } } while (0)
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "stream");
+  for (auto& ev : c->ev) CK(cudaEventCreate(&ev), "event");
+  for (auto& ev : c->stageEv) CK(cudaEventCreate(&ev), "event");
+  CK(cudaHostAlloc((void**)&c->sidePinned, L.total * s.capacity, cudaHostAllocDefault), "pinned side info");
+  CK(cudaHostAlloc((void**)&c->slotsPinned, sizeof(SlotDev) * s.capacity, cudaHostAllocDefault), "pinned slot table");
+  CK(cudaMalloc((void**)&c->slotsDev, sizeof(SlotDev) * s.capacity), "slot table");
+  memset(c->sidePinned, 0, L.total * s.capacity);
+  memset(c->slotsPinned, 0, sizeof(SlotDev) * s.capacity);
+  c->cur.assign(s.capacity, 0);
+
+  // plane geometry: pitch multiple of 64 samples (128 B)
+  int pw[3], ph[3], pitch[3];
+  size_t planeElems[3], slotElems = 0;
+  for (int k = 0; k < g.ncomp; k++)
+  {
+    pw[k] = k ? g.w >> g.sx : g.w;
+    ph[k] = k ? g.h >> g.sy : g.h;
+    pitch[k] = (int)alignUp(pw[k], 64);
+    planeElems[k] = alignUp((size_t)pitch[k] * ph[k], 128);
+    slotElems += planeElems[k];
+  }
+  for (int sl = 0; sl < s.capacity; sl++)
+  {
+    pel* mem = nullptr;
+    unsigned char* side = nullptr;
+    CK(cudaMalloc((void**)&mem, slotElems * 3 * sizeof(pel)), "plane memory");
+    c->planeMem.push_back(mem);
+    CK(cudaMemsetAsync(mem, 0, slotElems * 3 * sizeof(pel), c->stream), "memset");
+    CK(cudaMalloc((void**)&side, L.total), "side info memory");
+    c->sideDev.push_back(side);
+    CK(cudaMemsetAsync(side, 0, L.total, c->stream), "memset");
+    SlotDev& sd = c->slotsPinned[sl];
+    pel* p = mem;
+    for (int b = 0; b < 3; b++)
+      for (int k = 0; k < g.ncomp; k++)
+      {
+        sd.buf[b][k] = PlaneDev{ p, pitch[k], pw[k], ph[k] };
+        p += planeElems[k];
+      }
+    for (int d = 0; d < 2; d++)
+    {
+      sd.dbfL[d] = reinterpret_cast<const uint32_t*>(side + L.dbfL[d]);
+      sd.dbfC[d] = reinterpret_cast<const uint64_t*>(side + L.dbfC[d]);
+    }
+    sd.sao = reinterpret_cast<const SaoDev*>(side + L.sao);
+    sd.alf = reinterpret_cast<const AlfDev*>(side + L.alf);
+    sd.alfCtu = side + L.alfCtu;
+    sd.alfFilterIdx = reinterpret_cast<const int16_t*>(side + L.alfIdx);
+    sd.dbfOn = sd.saoOn = sd.alfOn = 0;
+  }
+  CK(cudaMemcpyAsync(c->slotsDev, c->slotsPinned, sizeof(SlotDev) * s.capacity, cudaMemcpyHostToDevice, c->stream), "slot table upload");
+  CK(cudaFuncSetAttribute(k_sao_alf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SaoAlfSmem)), "smem attribute");
+  CK(cudaStreamSynchronize(c->stream), "sync");
+#undef CK
+  *out = c;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// planes
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int vtmgpu_upload_async(vtmgpu_ctx* c, int slot, const int16_t* const plane[3], const ptrdiff_t stride[3])
+{
+  if (!c) return -1;
+  if (!c->slotOk(slot, 1)) return c->fail("upload: bad slot %d", slot);
+  cudaSetDevice(c->seq.device);
+  const SlotDev& sd = c->slotsPinned[slot];
+  for (int k = 0; k < c->g.ncomp; k++)
+  {
+    if (!plane[k]) return c->fail("upload: plane %d is NULL", k);
+    const PlaneDev& d = sd.buf[0][k];
+    if (c->cuda(cudaMemcpy2DAsync(d.p, (size_t)d.pitch * 2, plane[k], (size_t)stride[k] * 2, (size_t)d.w * 2, d.h, cudaMemcpyHostToDevice, c->stream), "upload")) return -1;
+  }
+  c->cur[slot] = 0;
+  return 0;
+}
+
+extern "C" int vtmgpu_download_async(vtmgpu_ctx* c, int slot, int16_t* const plane[3], const ptrdiff_t stride[3])
+{
+  if (!c) return -1;
+  if (!c->slotOk(slot, 1)) return c->fail("download: bad slot %d", slot);
+  cudaSetDevice(c->seq.device);
+  const SlotDev& sd = c->slotsPinned[slot];
+  for (int k = 0; k < c->g.ncomp; k++)
+  {
+    if (!plane[k]) return c->fail("download: plane %d is NULL", k);
+    const PlaneDev& d = sd.buf[c->cur[slot]][k];
+    if (c->cuda(cudaMemcpy2DAsync(plane[k], (size_t)stride[k] * 2, d.p, (size_t)d.pitch * 2, (size_t)d.w * 2, d.h, cudaMemcpyDeviceToHost, c->stream), "download")) return -1;
+  }
+  return 0;
+}
+
+extern "C" int vtmgpu_sync(vtmgpu_ctx* c)
+{
+  if (!c) return -1;
+  cudaSetDevice(c->seq.device);
+  return c->cuda(cudaStreamSynchronize(c->stream), "sync");
+}
+
+extern "C" int vtmgpu_upload(vtmgpu_ctx* c, int slot, const int16_t* const plane[3], const ptrdiff_t stride[3])
+{
+  return vtmgpu_upload_async(c, slot, plane, stride) ? -1 : vtmgpu_sync(c);
+}
+
+extern "C" int vtmgpu_download(vtmgpu_ctx* c, int slot, int16_t* const plane[3], const ptrdiff_t stride[3])
+{
+  return vtmgpu_download_async(c, slot, plane, stride) ? -1 : vtmgpu_sync(c);
+}
+
+extern "C" int vtmgpu_rewind(vtmgpu_ctx* c, int first, int count)
+{
+  if (!c) return -1;
+  if (!c->slotOk(first, count)) return c->fail("rewind: bad slot range");
+  for (int s = first; s < first + count; s++) c->cur[s] = 0;   // buf[0] is never written by a kernel
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// side information
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int vtmgpu_set_deblock(vtmgpu_ctx* c, int slot, const vtmgpu_deblock_params* p)
+{
+  if (!c) return -1;
+  if (!c->slotOk(slot, 1)) return c->fail("set_deblock: bad slot %d", slot);
+  cudaSetDevice(c->seq.device);
+  SlotDev& sd = c->slotsPinned[slot];
+  sd.dbfOn = p != nullptr;
+  if (p)
+  {
+    const SideLayout& L = c->lay;
+    for (int d = 0; d < 2; d++)
+    {
+      if (!p->luma[d]) return c->fail("set_deblock: luma[%d] is NULL", d);
+      memcpy(c->pinnedSide(slot) + L.dbfL[d], p->luma[d], L.nL * 4);
+      if (L.nC[d])
+      {
+        if (p->chroma[d]) memcpy(c->pinnedSide(slot) + L.dbfC[d], p->chroma[d], L.nC[d] * 8);
+        else memset(c->pinnedSide(slot) + L.dbfC[d], 0, L.nC[d] * 8);
+      }
+    }
+    if (c->pushSide(slot, L.dbfL[0], L.sao - L.dbfL[0])) return -1;
+  }
+  return c->pushSlot(slot);
+}
+
+extern "C" int vtmgpu_sao_reconstruct(vtmgpu_sao_ctu* ctu, int num_ctus, int width_in_ctus, int num_comps, int log2_scale_luma, int log2_scale_chroma)
+{
+  // xReconstructBlkSAOParams (SampleAdaptiveOffset.cpp:266-290): raster order so that a MERGE candidate is already final;
+  // NEW: invertQuantOffsets (:148-171); MERGE: copy of the left / above CTU's component parameters (:250-257)
+  if (!ctu || num_ctus < 0 || width_in_ctus < 1 || num_comps < 1 || num_comps > 3) return -1;
+  int mask = 0;
+  for (int a = 0; a < num_ctus; a++)
+    for (int k = 0; k < num_comps; k++)
+    {
+      vtmgpu_sao_offset& o = ctu[a].comp[k];
+      switch (o.mode)
+      {
+      case VTMGPU_SAO_MODE_OFF: continue;
+      case VTMGPU_SAO_MODE_NEW:
+      {
+        const int mul = 1 << (k == 0 ? log2_scale_luma : log2_scale_chroma);
+        if (o.type == VTMGPU_SAO_BO)
+        {
+          int16_t keep[4];
+          for (int i = 0; i < 4; i++) keep[i] = (int16_t)(o.offset[(o.aux + i) & 31] * mul);
+          memset(o.offset, 0, sizeof(o.offset));
+          for (int i = 0; i < 4; i++) o.offset[(o.aux + i) & 31] = keep[i];
+        }
+        else if (o.type >= VTMGPU_SAO_EO_0 && o.type <= VTMGPU_SAO_EO_45)
+        {
+          for (int i = 0; i < 32; i++) o.offset[i] = i < 5 ? (int16_t)(o.offset[i] * mul) : 0;
+          if (o.offset[2] != 0) return -2;       // "EO offset is not '0'"
+        }
+        else return -3;
+        break;
+      }
+      case VTMGPU_SAO_MODE_MERGE:
+      {
+        int from;
+        if (o.type == VTMGPU_SAO_MERGE_LEFT && ctu[a].merge_left_ok && (a % width_in_ctus) > 0) from = a - 1;
+        else if (o.type == VTMGPU_SAO_MERGE_ABOVE && ctu[a].merge_above_ok && a >= width_in_ctus) from = a - width_in_ctus;
+        else return -4;                          // "Merge target does not exist"
+        o = ctu[from].comp[k];
+        break;
+      }
+      default: return -5;
+      }
+      if (o.mode != VTMGPU_SAO_MODE_OFF) mask |= 1 << k;
+    }
+  return mask;
+}
+
+extern "C" int vtmgpu_set_sao(vtmgpu_ctx* c, int slot, const vtmgpu_sao_params* p)
+{
+  if (!c) return -1;
+  if (!c->slotOk(slot, 1)) return c->fail("set_sao: bad slot %d", slot);
+  cudaSetDevice(c->seq.device);
+  SlotDev& sd = c->slotsPinned[slot];
+  sd.saoOn = 0;
+  if (p)
+  {
+    if (!p->ctu || p->num_ctus != c->nCtus) return c->fail("set_sao: expected %d CTUs, got %d", c->nCtus, p->num_ctus);
+    SaoDev* d = reinterpret_cast<SaoDev*>(c->pinnedSide(slot) + c->lay.sao);
+    int any = 0;
+    for (int a = 0; a < c->nCtus; a++)
+      for (int k = 0; k < 3; k++)
+      {
+        SaoDev z{};
+        const vtmgpu_sao_offset& o = p->ctu[a].comp[k];
+        if (k < c->g.ncomp && o.mode != VTMGPU_SAO_MODE_OFF)
+        {
+          if (o.mode != VTMGPU_SAO_MODE_NEW) return c->fail("set_sao: CTU %d comp %d is not reconstructed (mode %d)", a, k, o.mode);
+          if (o.type == VTMGPU_SAO_BO)
+          {
+            z.type = 5;
+            z.band = (uint8_t)(o.aux & 31);
+            for (int i = 0; i < 4; i++) z.off[i] = o.offset[(o.aux + i) & 31];
+          }
+          else if (o.type >= 0 && o.type <= 3)
+          {
+            z.type = (uint8_t)(1 + o.type);
+            for (int i = 0; i < 5; i++) z.off[i] = o.offset[i];
+          }
+          else return c->fail("set_sao: CTU %d comp %d bad type %d", a, k, o.type);
+          z.avail = p->ctu[a].avail;
+          any = 1;
+        }
+        d[a * 3 + k] = z;
+      }
+    sd.saoOn = any;     // SAOProcess returns early when no CTU has SAO on (SampleAdaptiveOffset.cpp:626-637)
+    if (c->pushSide(slot, c->lay.sao, (size_t)c->nCtus * 3 * sizeof(SaoDev))) return -1;
+  }
+  return c->pushSlot(slot);
+}
+
+extern "C" int vtmgpu_set_alf(vtmgpu_ctx* c, int slot, const vtmgpu_alf_params* p)
+{
+  if (!c) return -1;
+  if (!c->slotOk(slot, 1)) return c->fail("set_alf: bad slot %d", slot);
+  cudaSetDevice(c->seq.device);
+  SlotDev& sd = c->slotsPinned[slot];
+  sd.alfOn = 0;
+  if (p)
+  {
+    const int n = c->nCtus;
+    if (p->num_ctus != n) return c->fail("set_alf: expected %d CTUs, got %d", n, p->num_ctus);
+    if (p->num_luma_aps < 0 || p->num_luma_aps > VTMGPU_ALF_MAX_APS) return c->fail("set_alf: bad num_luma_aps");
+    const bool chroma = c->g.ncomp > 1;
+    AlfDev& A = *reinterpret_cast<AlfDev*>(c->pinnedSide(slot) + c->lay.alf);
+    uint8_t* ctl = c->pinnedSide(slot) + c->lay.alfCtu;
+    int16_t* idx = reinterpret_cast<int16_t*>(c->pinnedSide(slot) + c->lay.alfIdx);
+    memset(&A, 0, sizeof(A));
+    for (int k = 0; k < 3; k++) A.enabled[k] = p->enabled[k] != 0;
+    A.numSets = VTMGPU_ALF_FIXED_SETS + p->num_luma_aps;
+    // coefficient tables: reconstructCoeff (AdaptiveLoopFilter.cpp:651-713), clip values :743-762, fixed sets :792-807
+    const int bdL = c->g.bdL, bdC = c->g.bdC;
+    const int clipL[4] = { 1 << bdL, 1 << (bdL - 3), 1 << (bdL - 5), 1 << (bdL - 7) };
+    const int clipC[4] = { 1 << bdC, 1 << (bdC - 3), 1 << (bdC - 5), 1 << (bdC - 7) };
+    for (int s = 0; s < VTMGPU_ALF_FIXED_SETS; s++)
+      for (int cl = 0; cl < 25; cl++)
+        for (int k = 0; k < 12; k++) A.luma[s][cl][k] = make_short2(vvc_alf_fix_coeff[vvc_alf_class_to_filt[s * 25 + cl] * 12 + k], (short)clipL[0]);
+    for (int s = 0; s < p->num_luma_aps; s++)
+    {
+      if (!p->luma_aps) return c->fail("set_alf: luma_aps is NULL");
+      const vtmgpu_alf_luma_aps& a = p->luma_aps[s];
+      for (int cl = 0; cl < 25; cl++)
+      {
+        const int f = a.delta_idx[cl];
+        if (f < 0 || f >= a.num_filters || f >= 25) return c->fail("set_alf: bad coeff delta idx in APS %d", s);
+        for (int k = 0; k < 12; k++)
+        {
+          const int ci = a.nonlinear ? a.clip_idx[f][k] : 0;
+          if (ci < 0 || ci > 3) return c->fail("set_alf: bad clip idx in APS %d", s);
+          A.luma[VTMGPU_ALF_FIXED_SETS + s][cl][k] = make_short2(a.coeff[f][k], (short)clipL[ci]);
+        }
+      }
+    }
+    int numAlts = 0;
+    if (p->chroma_aps)
+    {
+      numAlts = p->chroma_aps->num_alts;
+      if (numAlts < 1 || numAlts > VTMGPU_ALF_MAX_ALTS) return c->fail("set_alf: bad number of chroma alternatives");
+      for (int a = 0; a < numAlts; a++)
+        for (int k = 0; k < 6; k++)
+        {
+          const int ci = p->chroma_aps->nonlinear ? p->chroma_aps->clip_idx[a][k] : 0;
+          if (ci < 0 || ci > 3) return c->fail("set_alf: bad chroma clip idx");
+          A.chroma[a][k] = make_short2(p->chroma_aps->coeff[a][k], (short)clipC[ci]);
+        }
+    }
+    for (int k = 0; k < 2; k++)
+    {
+      A.ccEnabled[k] = chroma && p->ccalf_enabled[k];
+      memcpy(A.cc[k], p->ccalf_coeff[k], sizeof(A.cc[k]));
+    }
+    // per-CTU control
+    memset(ctl, 0, (size_t)n * 8);
+    for (int a = 0; a < n; a++)
+    {
+      const bool y = p->ctu_enable[0] && p->ctu_enable[0][a];
+      ctl[0 * n + a] = y;
+      idx[a] = 0;
+      if (y)
+      {
+        if (!p->ctu_filter_idx || p->ctu_filter_idx[a] < 0 || p->ctu_filter_idx[a] >= A.numSets) return c->fail("set_alf: CTU %d: bad filter set index", a);
+        idx[a] = p->ctu_filter_idx[a];
+      }
+      for (int k = 0; k < 2 && chroma; k++)
+      {
+        const bool on = p->ctu_enable[1 + k] && p->ctu_enable[1 + k][a];
+        ctl[(1 + k) * n + a] = on;
+        if (on)
+        {
+          const int alt = p->ctu_alt[k] ? p->ctu_alt[k][a] : 0;
+          if (alt >= numAlts) return c->fail("set_alf: CTU %d: chroma alternative %d not in the APS", a, alt);
+          ctl[(3 + k) * n + a] = (uint8_t)alt;
+        }
+        if (A.ccEnabled[k])
+        {
+          const int idc = p->ccalf_idc[k] ? p->ccalf_idc[k][a] : 0;
+          if (idc > VTMGPU_CCALF_MAX_FILTERS) return c->fail("set_alf: CTU %d: bad CC-ALF idc", a);
+          ctl[(5 + k) * n + a] = (uint8_t)idc;
+        }
+      }
+    }
+    sd.alfOn = 1;
+    if (c->pushSide(slot, c->lay.alfCtu, c->lay.total - c->lay.alfCtu)) return -1;
+  }
+  return c->pushSlot(slot);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// stages
+// ------------------------------------------------------------------------------------------------------------
+namespace
+{
+
+enum Stage { ST_DBF = 1, ST_SAO = 2, ST_ALF = 4 };
+
+// runs one kernel over maximal runs of slots that share the same current buffer
+template <class F> int forRuns(vtmgpu_ctx* c, int first, int count, F f)
+{
+  int s = first;
+  while (s < first + count)
+  {
+    int e = s + 1;
+    while (e < first + count && c->cur[e] == c->cur[s]) e++;
+    if (f(s, e - s, c->cur[s])) return -1;
+    s = e;
+  }
+  return 0;
+}
+
+int launchDeblock(vtmgpu_ctx* c, int first, int count)
+{
+  bool any = false;
+  for (int s = first; s < first + count; s++) any |= c->slotsPinned[s].dbfOn != 0;
+  if (!any) return 0;
+  const Geom& g = c->g;
+  DbfLaunch L;
+  L.tilesXL = (g.w + DBF_TW - 1) / DBF_TW;
+  L.tilesL = L.tilesXL * ((g.h + DBF_TH - 1) / DBF_TH);
+  L.tilesXC = g.ncomp > 1 ? ((g.w >> g.sx) + DBF_TW - 1) / DBF_TW : 0;
+  L.tilesC = g.ncomp > 1 ? L.tilesXC * (((g.h >> g.sy) + DBF_TH - 1) / DBF_TH) : 0;
+  return forRuns(c, first, count, [&](int s, int n, int src) {
+    const int dst = src == 1 ? 2 : 1;
+    k_deblock<<<dim3(L.tilesL + 2 * L.tilesC, n), DBF_THREADS, 0, c->stream>>>(c->slotsDev, s, src, dst, g, L);
+    c->launches++;
+    for (int i = s; i < s + n; i++) c->cur[i] = dst;
+    return c->cuda(cudaGetLastError(), "k_deblock launch");
+  });
+}
+
+int launchSaoAlf(vtmgpu_ctx* c, int first, int count, int doSao, int doAlf)
+{
+  bool any = false;
+  for (int s = first; s < first + count; s++) any |= (doSao && c->slotsPinned[s].saoOn) || (doAlf && c->slotsPinned[s].alfOn);
+  if (!any) return 0;
+  const Geom& g = c->g;
+  const int tilesX = (g.w + SA_T - 1) / SA_T, tiles = tilesX * ((g.h + SA_T - 1) / SA_T);
+  return forRuns(c, first, count, [&](int s, int n, int src) {
+    const int dst = src == 1 ? 2 : 1;
+    k_sao_alf<<<dim3(tiles, n), SA_THREADS, sizeof(SaoAlfSmem), c->stream>>>(c->slotsDev, s, src, dst, g, tilesX, doSao, doAlf);
+    c->launches++;
+    for (int i = s; i < s + n; i++) c->cur[i] = dst;
+    return c->cuda(cudaGetLastError(), "k_sao_alf launch");
+  });
+}
+
+int runStages(vtmgpu_ctx* c, int first, int count, int stages, bool sync, const char* what)
+{
+  if (!c) return -1;
+  if (!c->slotOk(first, count)) return c->fail("%s: bad slot range [%d,%d)", what, first, first + count);
+  cudaSetDevice(c->seq.device);
+  c->stageValid = false;
+  if (c->profiling) cudaEventRecord(c->stageEv[0], c->stream);
+  if ((stages & ST_DBF) && launchDeblock(c, first, count)) return -1;
+  if (c->profiling) cudaEventRecord(c->stageEv[1], c->stream);
+  if ((stages & (ST_SAO | ST_ALF)) && launchSaoAlf(c, first, count, (stages & ST_SAO) != 0, (stages & ST_ALF) != 0)) return -1;
+  if (c->profiling) { cudaEventRecord(c->stageEv[2], c->stream); c->stageValid = true; }
+  if (sync && c->cuda(cudaStreamSynchronize(c->stream), what)) return -1;
+  return 0;
+}
+
+}   // namespace
+
+extern "C" int vtmgpu_deblock(vtmgpu_ctx* c, int first, int count) { return runStages(c, first, count, ST_DBF, true, "deblock"); }
+extern "C" int vtmgpu_sao(vtmgpu_ctx* c, int first, int count) { return runStages(c, first, count, ST_SAO, true, "sao"); }
+extern "C" int vtmgpu_alf(vtmgpu_ctx* c, int first, int count) { return runStages(c, first, count, ST_ALF, true, "alf"); }
+extern "C" int vtmgpu_sao_alf(vtmgpu_ctx* c, int first, int count) { return runStages(c, first, count, ST_SAO | ST_ALF, true, "sao_alf"); }
+extern "C" int vtmgpu_filter(vtmgpu_ctx* c, int first, int count) { return runStages(c, first, count, ST_DBF | ST_SAO | ST_ALF, true, "filter"); }
+extern "C" int vtmgpu_filter_async(vtmgpu_ctx* c, int first, int count) { return runStages(c, first, count, ST_DBF | ST_SAO | ST_ALF, false, "filter_async"); }
+
+extern "C" int vtmgpu_timer_start(vtmgpu_ctx* c)
+{
+  if (!c) return -1;
+  cudaSetDevice(c->seq.device);
+  return c->cuda(cudaEventRecord(c->ev[0], c->stream), "timer_start");
+}
+
+extern "C" int vtmgpu_timer_stop(vtmgpu_ctx* c, float* ms)
+{
+  if (!c || !ms) return -1;
+  cudaSetDevice(c->seq.device);
+  if (c->cuda(cudaEventRecord(c->ev[1], c->stream), "timer_stop")) return -1;
+  if (c->cuda(cudaEventSynchronize(c->ev[1]), "timer_stop")) return -1;
+  return c->cuda(cudaEventElapsedTime(ms, c->ev[0], c->ev[1]), "timer_stop");
+}
+
+extern "C" int64_t vtmgpu_launch_count(const vtmgpu_ctx* c) { return c ? c->launches : -1; }
+
+extern "C" int vtmgpu_set_profiling(vtmgpu_ctx* c, int on)
+{
+  if (!c) return -1;
+  c->profiling = on != 0;
+  c->stageValid = false;
+  return 0;
+}
+
+extern "C" int vtmgpu_stage_ms(vtmgpu_ctx* c, float ms[4])
+{
+  if (!c || !ms) return -1;
+  if (!c->stageValid) return c->fail("stage_ms: no profiled run recorded");
+  cudaSetDevice(c->seq.device);
+  if (c->cuda(cudaEventSynchronize(c->stageEv[2]), "stage_ms")) return -1;
+  ms[0] = ms[1] = ms[2] = ms[3] = 0.f;
+  cudaEventElapsedTime(&ms[0], c->stageEv[0], c->stageEv[1]);
+  cudaEventElapsedTime(&ms[1], c->stageEv[1], c->stageEv[2]);
+  return 0;
+}

@@ -1,0 +1,70 @@
+// vtmgpu_dev.cuh -- device-side data model shared by the kernels of libvtmgpu (sm_100a).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace vtmgpu
+{
+
+typedef int16_t pel;
+
+// One sample plane in HBM: planar int16, no apron; pitch (in samples) is a multiple of 64 so every row starts on a
+// 128-byte boundary and every aligned group of 8 samples (one 128-bit access) lies inside the row.
+struct PlaneDev
+{
+  pel* p;
+  int  pitch, w, h;
+};
+
+// SAO parameters of one CTU component, reconstructed and compacted (16 bytes): SampleAdaptiveOffset.cpp:528-541 keeps
+// a 32-entry band table with 4 live bands; here the 4 band offsets are stored with the first band position.
+struct SaoDev
+{
+  uint8_t type;      // 0 off, 1..4 = EO 0/90/135/45 degrees, 5 = BO
+  uint8_t band;      // BO: first band
+  uint8_t avail;     // VTMGPU_AVAIL_* bits of the 8 neighbouring CTUs
+  uint8_t pad;
+  int16_t off[5];    // EO: offsets for edgeType -2..2 ; BO: off[0..3] for bands band..band+3 (mod 32)
+  int16_t pad2;
+};
+
+#define VTMGPU_MAX_LUMA_SETS 24
+
+// ALF data of one picture
+struct AlfDev
+{
+  int32_t enabled[3];
+  int32_t ccEnabled[2];
+  int32_t numSets;                                   // 16 fixed + APS sets
+  short2  luma[VTMGPU_MAX_LUMA_SETS][25][12];        // {coeff, clip} per set, class, tap (transpose 0 order)
+  short2  chroma[8][6];                              // {coeff, clip} per alternative, tap
+  int16_t cc[2][4][8];                               // CC-ALF coefficients (7 used)
+};
+
+struct SlotDev
+{
+  PlaneDev buf[3][3];            // [buffer][component]; buffer 0 = pristine upload, 1/2 = working
+  const uint32_t* dbfL[2];
+  const uint64_t* dbfC[2];
+  const SaoDev*   sao;           // [ctus][3]                     (NULL: stage off)
+  const AlfDev*   alf;           //                               (NULL: stage off)
+  const uint8_t*  alfCtu;        // [8][ctus]: enable Y,Cb,Cr, alt Cb,Cr, cc idc Cb,Cr, (unused)
+  const int16_t*  alfFilterIdx;  // [ctus]
+  int32_t dbfOn, saoOn, alfOn;
+};
+
+struct Geom
+{
+  int w, h;             // luma
+  int sx, sy;           // chroma shifts
+  int ncomp;
+  int bdL, bdC;
+  int ctu, ctuLog2;
+  int wCtus, hCtus;
+};
+
+__device__ __forceinline__ int iabs(int v) { return v < 0 ? -v : v; }
+__device__ __forceinline__ int clip3(int lo, int hi, int v) { return min(max(v, lo), hi); }
+
+}   // namespace vtmgpu

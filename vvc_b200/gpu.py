@@ -1,0 +1,302 @@
+"""ctypes binding of libvtmgpu.so (vvc_b200/csrc, CUDA for sm_100a) and the Python mirror of the reference's
+operator interface for the in-loop filter chain.
+
+Reference interface mirrored (names and call order as in DecLib::executeLoopFilters, DecoderLib/DecLib.cpp:560-623):
+
+    LoopFilter.loopFilterPic            CommonLib/LoopFilter.cpp:145
+    SampleAdaptiveOffset.SAOProcess     CommonLib/SampleAdaptiveOffset.cpp:618
+    AdaptiveLoopFilter.ALFProcess       CommonLib/AdaptiveLoopFilter.cpp:393
+
+There is no CPU path in here: if the library is missing, cannot be loaded or finds no CUDA device, every entry
+point raises VtmGpuError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libvtmgpu.so")
+
+
+class VtmGpuError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """Loads libvtmgpu.so and declares the prototypes of include/vtmgpu.h.  Raises VtmGpuError when it is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or os.environ.get("VTMGPU_LIB") or LIB_PATH
+    if not os.path.exists(p):
+        raise VtmGpuError("libvtmgpu.so not found at %s -- build it with __graft_entry__.build() (there is no CPU fallback)" % p)
+    try:
+        lib = C.CDLL(p)
+    except OSError as e:
+        raise VtmGpuError("cannot load %s: %s (there is no CPU fallback)" % (p, e))
+    ctx = C.c_void_p
+    planes_in = [ctx, C.c_int, abi.PlanePtrs, abi.Strides]
+    proto = {
+        "vtmgpu_abi_version": (C.c_int, []),
+        "vtmgpu_abi_sizeof": (C.c_int, [C.c_int]),
+        "vtmgpu_last_error": (C.c_char_p, [ctx]),
+        "vtmgpu_create": (C.c_int, [C.POINTER(abi.SeqParams), C.POINTER(ctx)]),
+        "vtmgpu_destroy": (None, [ctx]),
+        "vtmgpu_upload": (C.c_int, planes_in), "vtmgpu_download": (C.c_int, planes_in),
+        "vtmgpu_upload_async": (C.c_int, planes_in), "vtmgpu_download_async": (C.c_int, planes_in),
+        "vtmgpu_set_deblock": (C.c_int, [ctx, C.c_int, C.POINTER(abi.DeblockParams)]),
+        "vtmgpu_set_sao": (C.c_int, [ctx, C.c_int, C.POINTER(abi.SaoParams)]),
+        "vtmgpu_set_alf": (C.c_int, [ctx, C.c_int, C.POINTER(abi.AlfParams)]),
+        "vtmgpu_sao_reconstruct": (C.c_int, [C.POINTER(abi.SaoCtu), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+        "vtmgpu_deblock": (C.c_int, [ctx, C.c_int, C.c_int]), "vtmgpu_sao": (C.c_int, [ctx, C.c_int, C.c_int]),
+        "vtmgpu_alf": (C.c_int, [ctx, C.c_int, C.c_int]), "vtmgpu_sao_alf": (C.c_int, [ctx, C.c_int, C.c_int]),
+        "vtmgpu_filter": (C.c_int, [ctx, C.c_int, C.c_int]), "vtmgpu_filter_async": (C.c_int, [ctx, C.c_int, C.c_int]),
+        "vtmgpu_sync": (C.c_int, [ctx]), "vtmgpu_timer_start": (C.c_int, [ctx]),
+        "vtmgpu_timer_stop": (C.c_int, [ctx, C.POINTER(C.c_float)]),
+        "vtmgpu_rewind": (C.c_int, [ctx, C.c_int, C.c_int]),
+        "vtmgpu_launch_count": (C.c_int64, [ctx]),
+        "vtmgpu_set_profiling": (C.c_int, [ctx, C.c_int]),
+        "vtmgpu_stage_ms": (C.c_int, [ctx, C.POINTER(C.c_float * 4)]),
+    }
+    for name, (res, args) in proto.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            raise VtmGpuError("%s does not export %s" % (p, name))
+        fn.restype, fn.argtypes = res, args
+    if lib.vtmgpu_abi_version() != abi.ABI_VERSION:
+        raise VtmGpuError("libvtmgpu ABI version %d, binding expects %d" % (lib.vtmgpu_abi_version(), abi.ABI_VERSION))
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def sao_reconstruct(ctus, width_in_ctus, ncomp, scale_luma=0, scale_chroma=0):
+    """Host-only helper of the library: xReconstructBlkSAOParams (SampleAdaptiveOffset.cpp:266) in place.
+    Returns the 3-bit mask of components with SAO on; raises on malformed parameters."""
+    rc = load_library().vtmgpu_sao_reconstruct(ctus, len(ctus), width_in_ctus, ncomp, scale_luma, scale_chroma)
+    if rc < 0:
+        raise VtmGpuError("vtmgpu_sao_reconstruct: invalid SAO parameters (rc=%d)" % rc)
+    return rc
+
+
+def _plane_args(planes):
+    ptrs, strides = abi.PlanePtrs(), abi.Strides()
+    for c, p in enumerate(planes):
+        if p.dtype != np.int16 or p.ndim != 2 or p.strides[1] != 2:
+            raise ValueError("planes must be 2-D int16 arrays with contiguous rows")
+        ptrs[c] = C.cast(p.ctypes.data, C.POINTER(C.c_int16))
+        strides[c] = p.strides[0] // 2
+    return ptrs, strides
+
+
+class Context:
+    """One libvtmgpu context: device planes + side info for `capacity` picture slots on one GPU."""
+
+    def __init__(self, seq, capacity=1, device=0):
+        self.lib = load_library()
+        self.seq = dict(seq)
+        sp = abi.SeqParams(seq["width"], seq["height"], seq["chroma_format"], seq["bit_depth_luma"], seq["bit_depth_chroma"],
+                           seq["ctu_size"], capacity, device)
+        self.h = C.c_void_p()
+        if self.lib.vtmgpu_create(C.byref(sp), C.byref(self.h)):
+            raise VtmGpuError(self.lib.vtmgpu_last_error(None).decode())
+        self.capacity = capacity
+        self.ncomp = 1 if seq["chroma_format"] == 0 else 3
+        sx, sy = abi.chroma_shifts(seq["chroma_format"])
+        w, h = seq["width"], seq["height"]
+        self.shapes = [(h, w)] + ([(h >> sy, w >> sx)] * 2 if self.ncomp == 3 else [])
+
+    def close(self):
+        if self.h:
+            self.lib.vtmgpu_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc:
+            raise VtmGpuError("%s: %s" % (what, self.lib.vtmgpu_last_error(self.h).decode()))
+
+    # ---- planes ----------------------------------------------------------------------------------------
+    def upload(self, slot, planes, sync=True):
+        ptrs, strides = _plane_args(planes)
+        self._ck((self.lib.vtmgpu_upload if sync else self.lib.vtmgpu_upload_async)(self.h, slot, ptrs, strides), "upload")
+
+    def download(self, slot, out=None, sync=True):
+        if out is None:
+            out = [np.empty(s, dtype=np.int16) for s in self.shapes]
+        ptrs, strides = _plane_args(out)
+        self._ck((self.lib.vtmgpu_download if sync else self.lib.vtmgpu_download_async)(self.h, slot, ptrs, strides), "download")
+        return out
+
+    # ---- side information --------------------------------------------------------------------------------
+    def set_deblock(self, slot, params):
+        self._ck(self.lib.vtmgpu_set_deblock(self.h, slot, C.byref(params) if params is not None else None), "set_deblock")
+
+    def set_sao(self, slot, ctus):
+        """ctus: reconstructed (abi.SaoCtu * n) array, or None to switch the stage off."""
+        if ctus is None:
+            self._ck(self.lib.vtmgpu_set_sao(self.h, slot, None), "set_sao")
+            return
+        p = abi.SaoParams(C.cast(ctus, C.POINTER(abi.SaoCtu)), len(ctus))
+        self._ck(self.lib.vtmgpu_set_sao(self.h, slot, C.byref(p)), "set_sao")
+
+    def set_alf(self, slot, params):
+        self._ck(self.lib.vtmgpu_set_alf(self.h, slot, C.byref(params) if params is not None else None), "set_alf")
+
+    def set_capture(self, slot, cap, upload=True, sync=True):
+        """Loads one captured picture (planes + all side information) into a slot."""
+        if upload:
+            self.upload(slot, cap.pre, sync=sync)
+        self.set_deblock(slot, cap.deblock_params())
+        ctus = cap.sao_ctus()
+        if ctus is not None:
+            sao_reconstruct(ctus, cap.width_in_ctus, cap.ncomp, cap.sao_scale[0], cap.sao_scale[1])
+        self.set_sao(slot, ctus)
+        self.set_alf(slot, cap.alf_params())
+
+    # ---- stages ------------------------------------------------------------------------------------------
+    def deblock(self, first=0, count=1):
+        self._ck(self.lib.vtmgpu_deblock(self.h, first, count), "deblock")
+
+    def sao(self, first=0, count=1):
+        self._ck(self.lib.vtmgpu_sao(self.h, first, count), "sao")
+
+    def alf(self, first=0, count=1):
+        self._ck(self.lib.vtmgpu_alf(self.h, first, count), "alf")
+
+    def sao_alf(self, first=0, count=1):
+        self._ck(self.lib.vtmgpu_sao_alf(self.h, first, count), "sao_alf")
+
+    def filter(self, first=0, count=1, sync=True):
+        self._ck((self.lib.vtmgpu_filter if sync else self.lib.vtmgpu_filter_async)(self.h, first, count), "filter")
+
+    def sync(self):
+        self._ck(self.lib.vtmgpu_sync(self.h), "sync")
+
+    def rewind(self, first=0, count=1):
+        self._ck(self.lib.vtmgpu_rewind(self.h, first, count), "rewind")
+
+    def timer_start(self):
+        self._ck(self.lib.vtmgpu_timer_start(self.h), "timer_start")
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._ck(self.lib.vtmgpu_timer_stop(self.h, C.byref(ms)), "timer_stop")
+        return ms.value
+
+    def launch_count(self):
+        return int(self.lib.vtmgpu_launch_count(self.h))
+
+    def set_profiling(self, on):
+        self._ck(self.lib.vtmgpu_set_profiling(self.h, int(on)), "set_profiling")
+
+    def stage_ms(self):
+        ms = (C.c_float * 4)()
+        self._ck(self.lib.vtmgpu_stage_ms(self.h, C.byref(ms)), "stage_ms")
+        return [float(v) for v in ms]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# mirror of the reference's three filter classes (same names / call order as DecLib::executeLoopFilters)
+# ---------------------------------------------------------------------------------------------------------------
+class Picture:
+    """What DecLib hands to the filters, flattened: reco planes (modified in place) + the side information."""
+
+    def __init__(self, cap):
+        self.cap = cap
+        self.seq = cap.seq
+        self.reco = [p.copy() for p in cap.pre]
+
+
+class LoopFilter:
+    """LoopFilter (CommonLib/LoopFilter.h:107-129)."""
+
+    def __init__(self):
+        self.ctx = None
+
+    def create(self, seq, device=0):
+        if self.ctx is None or self.ctx.seq != dict(seq):
+            self.ctx = Context(seq, capacity=1, device=device)
+
+    def destroy(self):
+        if self.ctx:
+            self.ctx.close()
+            self.ctx = None
+
+    def loopFilterPic(self, pic):
+        self.ctx.upload(0, pic.reco)
+        self.ctx.set_deblock(0, pic.cap.deblock_params())
+        self.ctx.deblock(0, 1)
+        self.ctx.download(0, pic.reco)
+
+
+class SampleAdaptiveOffset:
+    """SampleAdaptiveOffset (CommonLib/SampleAdaptiveOffset.h:63-73); shares the LoopFilter's device context."""
+
+    def __init__(self, loop_filter):
+        self.lf = loop_filter
+
+    def SAOProcess(self, pic, sao_ctus):
+        if sao_ctus is None:
+            raise VtmGpuError("No parameters present")           # CHECK at SampleAdaptiveOffset.cpp:621
+        sao_reconstruct(sao_ctus, pic.cap.width_in_ctus, pic.cap.ncomp, pic.cap.sao_scale[0], pic.cap.sao_scale[1])
+        self.lf.ctx.set_sao(0, sao_ctus)
+        self.lf.ctx.sao(0, 1)
+        self.lf.ctx.download(0, pic.reco)
+
+
+class AdaptiveLoopFilter:
+    """AdaptiveLoopFilter (CommonLib/AdaptiveLoopFilter.h:83-120)."""
+
+    def __init__(self, loop_filter):
+        self.lf = loop_filter
+
+    def ALFProcess(self, pic):
+        self.lf.ctx.set_alf(0, pic.cap.alf_params())
+        self.lf.ctx.alf(0, 1)
+        self.lf.ctx.download(0, pic.reco)
+
+
+def execute_loop_filters(cap, device=0, fused=True, ctx=None):
+    """DecLib::executeLoopFilters for one captured picture.  Returns {stage: planes} (fused: only 'final')."""
+    own = ctx is None
+    if own:
+        ctx = Context(cap.seq, capacity=1, device=device)
+    try:
+        out = {}
+        if fused:
+            ctx.set_capture(0, cap)
+            ctx.filter(0, 1)
+            out["final"] = ctx.download(0)
+            return out
+        pic = Picture(cap)
+        lf = LoopFilter()
+        lf.ctx = ctx
+        ctx.set_sao(0, None)
+        ctx.set_alf(0, None)
+        lf.loopFilterPic(pic)
+        out["dbf"] = [p.copy() for p in pic.reco]
+        ctus = cap.sao_ctus()
+        if ctus is not None:
+            SampleAdaptiveOffset(lf).SAOProcess(pic, ctus)
+            out["sao"] = [p.copy() for p in pic.reco]
+        if cap.alf is not None:
+            AdaptiveLoopFilter(lf).ALFProcess(pic)
+            out["alf"] = [p.copy() for p in pic.reco]
+        out["final"] = pic.reco
+        return out
+    finally:
+        if own:
+            ctx.close()

@@ -18,6 +18,8 @@
 //   VTMGPU_SHIM_BACKEND=ref     test binaries only: use the linked alternative backend (shim_backend.h)
 #include <dlfcn.h>
 
+#include <chrono>
+
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -92,8 +94,24 @@ struct Shim
     if (useRef && (!vtmgpu_shim_alt_backend || !vtmgpu_shim_alt_backend())) THROW("vtmgpu shim: no alternative backend linked into this binary");
     if (const char* d = getenv("VTMGPU_CAPTURE_DIR")) captureDir = d;
     staged = !captureDir.empty() || (getenv("VTMGPU_STAGED") && atoi(getenv("VTMGPU_STAGED")));
+    timing = getenv("VTMGPU_SHIM_TIMING") && atoi(getenv("VTMGPU_SHIM_TIMING"));
   }
-  ~Shim() { if (ctx) api.destroy(ctx); }
+  ~Shim()
+  {
+    if (timing)
+      printf("vtmgpu-shim-timing: pictures=%d luma_pixels=%lld filter_s=%.6f dbf_s=%.6f sao_s=%.6f alf_s=%.6f derive_s=%.6f backend=%s\n", picCount,
+             lumaPixels, stageSec[0] + stageSec[1] + stageSec[2], stageSec[0], stageSec[1], stageSec[2], deriveSec, useRef ? "ref" : "gpu");
+    if (ctx) api.destroy(ctx);
+  }
+
+  // VTMGPU_SHIM_TIMING=1: steady_clock around the backend's stage calls only (for the reference backend that is exactly
+  // loopFilterPic / SAOProcess / ALFProcess of the reference classes -- BASELINE.md section 4); host derivation separately
+  bool timing = false;
+  double stageSec[3] = { 0, 0, 0 }, deriveSec = 0;
+  long long lumaPixels = 0;
+  std::chrono::steady_clock::time_point t0;
+  void tic() { if (timing) t0 = std::chrono::steady_clock::now(); }
+  void toc(double& acc) { if (timing) acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
 
   void check(int rc, const char* what) { if (rc) THROW("vtmgpu shim: " << what << " failed: " << (api.last_error ? api.last_error(ctx) : "?")); }
 
@@ -213,7 +231,13 @@ void LoopFilter::loopFilterPic(CodingStructure& cs)
   Shim& s = shim();
   s.ensureCtx(cs);
   s.saoPending = false;
-  deriveDeblockRecords(cs, s.dbf);
+  s.lumaPixels += (long long)cs.pcv->lumaWidth * cs.pcv->lumaHeight;
+  if (!s.useRef || !s.captureDir.empty() || !s.timing)   // the reference backend derives its own parameters; skip ours when only timing it
+  {
+    s.tic();
+    deriveDeblockRecords(cs, s.dbf);
+    s.toc(s.deriveSec);
+  }
   if (!s.captureDir.empty())
   {
     s.cap.clear();
@@ -223,6 +247,7 @@ void LoopFilter::loopFilterPic(CodingStructure& cs)
     s.cap.add("dbfrec_c0", s.dbf.chroma[0].data(), s.dbf.chroma[0].size() * 8);
     s.cap.add("dbfrec_c1", s.dbf.chroma[1].data(), s.dbf.chroma[1].size() * 8);
   }
+  s.tic();
   if (s.useRef)
   {
     vtmgpu_shim_alt_backend()->lfRun(cs);
@@ -237,6 +262,7 @@ void LoopFilter::loopFilterPic(CodingStructure& cs)
     s.check(s.api.deblock(s.ctx, 0, 1), "deblock");
     if (s.staged || lastStage(cs, 0)) s.download(cs);
   }
+  s.toc(s.stageSec[0]);
   s.capturePlanes(cs, "dbf");
   if (lastStage(cs, 0)) s.finishPicture(cs, 1);
 }
@@ -267,6 +293,7 @@ void SampleAdaptiveOffset::SAOProcess(CodingStructure& cs, SAOBlkParam* saoBlkPa
     s.cap.add("sao_raw", s.sao.ctu.data(), s.sao.ctu.size() * sizeof(vtmgpu_sao_ctu));
     s.cap.add("sao_scale", s.saoLog2Scale, sizeof(s.saoLog2Scale));
   }
+  s.tic();
   if (s.useRef)
   {
     vtmgpu_shim_alt_backend()->saoRun(cs, saoBlkParams);
@@ -288,6 +315,7 @@ void SampleAdaptiveOffset::SAOProcess(CodingStructure& cs, SAOBlkParam* saoBlkPa
       s.saoPending = true;     // fused into the ALF pass
     }
   }
+  s.toc(s.stageSec[1]);
   s.capturePlanes(cs, "sao");
   if (lastStage(cs, 1)) s.finishPicture(cs, 3);
 }
@@ -348,6 +376,7 @@ void AdaptiveLoopFilter::ALFProcess(CodingStructure& cs)
     s.cap.add("alf_cccoef", p->ccalf_coeff, sizeof(p->ccalf_coeff));
     for (int c = 0; c < 2; c++) s.cap.add(("alf_ccidc" + std::to_string(c)).c_str(), s.alf.ccIdc[c].data(), s.alf.ccIdc[c].size());
   }
+  s.tic();
   if (s.useRef)
   {
     vtmgpu_shim_alt_backend()->alfRun(cs, m_ccAlfFilterParam, m_ccAlfFilterControl, p->num_ctus);
@@ -360,6 +389,7 @@ void AdaptiveLoopFilter::ALFProcess(CodingStructure& cs)
     s.saoPending = false;
     s.download(cs);
   }
+  s.toc(s.stageSec[2]);
   s.capturePlanes(cs, "alf");
   s.finishPicture(cs, cs.sps->getSAOEnabledFlag() ? 7 : 5);
 }
