@@ -120,3 +120,18 @@ def test_bad_arguments_fail_loudly():
     with pytest.raises(gpu.VtmGpuError):
         ctx.set_alf(0, p)
     ctx.close()
+
+
+def test_decoder_drop_in_md5():
+    """The reference decoder with OUR filter entry points linked in (vvc_b200/_bin/DecoderApp_gpu) decodes a
+    reference-encoded stream (full CTC tool set, RA) and every picture matches the encoder's MD5 SEI."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dec = os.path.join(root, "vvc_b200", "_bin", "DecoderApp_gpu")
+    if not os.path.exists(dec):
+        pytest.skip("DecoderApp_gpu not built (needs the reference sources at build time)")
+    r = subprocess.run([dec, "-b", os.path.join(root, "tests", "golden", "streams", "ra_416x240.bin"), "-d", "0"],
+                       capture_output=True, text=True, timeout=300, env=dict(os.environ, VTMGPU_SHIM_BACKEND="gpu"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("(OK)") == 8 and "ERROR" not in r.stdout, r.stdout[-2000:]
