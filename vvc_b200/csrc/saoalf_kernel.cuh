@@ -8,8 +8,17 @@
 // (SAO input, ALF input incl. 3-sample replicate border); here each plane is read ONCE from HBM into shared memory
 // (tile + halo, 8-sample aligned 128-bit loads, coordinates clamped = replicate border), SAO is applied in shared
 // memory (tile + 3), the 4x4 Laplacian classification and the diamond filters read that SAO output, CC-ALF reads the
-// SAO-output luma tile that is still resident, and each plane is written ONCE.  With saoOn=0 / alfOn=0 the same
-// kernel is the stand-alone ALF / SAO stage.
+// SAO-output luma tile that is still resident, and each plane is written ONCE.
+//
+// The chain is instruction-issue bound on B200, so all sample arithmetic runs TWO SAMPLES PER
+// 32-BIT REGISTER on the native packed 16-bit integer instructions of sm_100a:
+//   VIADD.16x2            packed add                      (__vadd2)
+//   VIADDMNMX.S16x2.RELU  max(min(a+b, c), 0) per lane    (__viaddmin_s16x2_relu): one instruction = subtract + clamp
+//   IDP.2A                s16 x s8 dot product into s32   (__dp2a_lo / __dp2a_hi): the ALF multiply-accumulate
+//   PRMT                  byte permute: 16-bit lane shuffles and the SAO offset look-up table
+// A filter tap pair costs 4 ALU-pipe + 2 FMA-pipe instructions per two pixels (scalar code: ~14 per two pixels).
+// Rows that touch an ALF virtual boundary (2 of 32 block rows per CTU) and non-4:2:0 CC-ALF use the generic scalar
+// routines at the end of this file; they follow the reference line by line.
 //
 // Per luma pixel algorithmic HBM bytes at 4:2:0: read 3, write 3 (+ CTU params, negligible).
 #pragma once
@@ -25,9 +34,9 @@ constexpr int SA_THREADS = 256;             // = (SA_T/4)^2 : one thread per 4x4
 constexpr int SA_HX = 8, SA_HY = 4;         // halo loaded around a tile (x: one aligned group of 8)
 constexpr int SA_W = SA_T + 2 * SA_HX;      // 80
 constexpr int SA_H = SA_T + 2 * SA_HY;      // 72
-constexpr int SA_P = SA_W + 8;              // smem pitch in samples (88 -> 176 B)
-constexpr int SA_LAPN = SA_T / 2 + 2;       // 34 gradient positions per dimension
-constexpr int SA_LAPP = SA_LAPN + 1;
+constexpr int SA_P = SA_W + 8;              // smem pitch in samples (88 -> 176 B: rows shift by 12 banks)
+constexpr int SA_CELLS = SA_T / 2 + 2;      // 34 Laplacian cells (2x2 samples) per dimension: tile + 2 samples each side
+constexpr int SA_CELLP = SA_CELLS + 2;      // cell row pitch (uint2 units)
 
 __constant__ int8_t c_perm7[4][12] = { { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11 }, { 9, 4, 10, 8, 1, 5, 11, 7, 3, 0, 2, 6 },
                                        { 0, 3, 2, 1, 8, 7, 6, 5, 4, 9, 10, 11 }, { 9, 8, 10, 4, 3, 7, 11, 5, 1, 0, 2, 6 } };
@@ -38,14 +47,26 @@ struct SaoAlfSmem
   pel      bl[SA_H * SA_P];                 // SAO output, luma (stays resident for CC-ALF)
   union
   {
-    uint16_t lap[4][SA_LAPN][SA_LAPP];      // V, H, D0, D1 Laplacian pair sums
+    uint2    cell[SA_CELLS][SA_CELLP];      // Laplacian sums of one 2x2 cell: .x = V | H << 16, .y = D0 | D1 << 16
     pel      bc[SA_H * SA_P];               // SAO output, chroma component
   } u;
   SaoDev   sao[3][9];                       // 3x3 CTU neighbourhood per component
-  short2   lumaSet[25][12];
   short2   chromaSet[2][6];
   int16_t  cc[2][8];
 };
+
+// ---- packed 16x2 helpers ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
+{
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(s));
+  return d;
+}
+__device__ __forceinline__ uint32_t dup16(int v) { return (uint32_t)(v & 0xffff) * 0x10001u; }
+// (hi lane of lo, lo lane of hi): the pair that starts one sample after lo
+__device__ __forceinline__ uint32_t mid16(uint32_t lo, uint32_t hi) { return __funnelshift_r(lo, hi, 16); }
+// max(min(a + b, c), 0) per signed 16-bit lane
+__device__ __forceinline__ uint32_t addClamp0(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_s16x2_relu(a, b, c); }
 
 // loads rows y0-SA_HY .. , columns x0-SA_HX .. of a plane into s (tile w x h samples + halo), replicate border
 __device__ __forceinline__ void saLoadTile(pel* s, const PlaneDev& pl, int x0, int y0, int tw, int th)
@@ -57,7 +78,16 @@ __device__ __forceinline__ void saLoadTile(pel* s, const PlaneDev& pl, int x0, i
     const int y = min(max(y0 - SA_HY + r, 0), pl.h - 1), x = x0 - SA_HX + gc * 8;
     const pel* row = pl.p + (size_t)y * pl.pitch;
     int4 v;
-    if (x >= 0 && x < pl.w) v = __ldg(reinterpret_cast<const int4*>(row + x));
+    if (x >= 0 && x < pl.w)
+    {
+      v = __ldg(reinterpret_cast<const int4*>(row + x));
+      if (x + 8 > pl.w)
+      {
+        // the picture ends inside this group (plane widths are multiples of 4): replicate the last column
+        const int e = (int)__byte_perm((uint32_t)v.y, 0u, 0x3232);
+        v.z = e; v.w = e;
+      }
+    }
     else
     {
       const uint32_t e = (uint16_t)row[x < 0 ? 0 : pl.w - 1];
@@ -68,60 +98,196 @@ __device__ __forceinline__ void saLoadTile(pel* s, const PlaneDev& pl, int x0, i
   }
 }
 
-// SAO of the sample at plane position (x,y) (inside the picture); a = smem tile, (ax,ay) its tile coordinates
-__device__ __forceinline__ int saoSample(const pel* a, int ax, int ay, int x, int y, int w, int h, int cw, int ch, int tcx, int tcy,
-                                         const SaoDev* nb, int bd)
+// ---- SAO ----------------------------------------------------------------------------------------------------
+struct SaoGeom
 {
-  const int v = a[ay * SA_P + ax];
-  const int cx = x / cw, cy = y / ch;
-  const SaoDev& P = nb[(cy - tcy + 1) * 3 + (cx - tcx + 1)];
-  if (P.type == 0) return v;
-  const int maxv = (1 << bd) - 1;
-  if (P.type == 5)
-  {
-    const int k = ((v >> (bd - 5)) - P.band) & 31;
-    return k < 4 ? clip3(0, maxv, v + P.off[k]) : v;
-  }
-  const int t = P.type - 1;                       // 0: 0deg, 1: 90deg, 2: 135deg, 3: 45deg
-  const int dx = t == 1 ? 0 : (t == 3 ? 1 : -1);  // first neighbour (dx,dy); second is (-dx,-dy)
-  const int dy = t == 0 ? 0 : -1;
-  int e = 0;
+  int bx0, by0;          // plane coordinates of smem position (0,0)
+  int w, h;              // plane size
+  int cwLog, chLog;      // log2 CTU size in this plane
+  int tcx, tcy;          // CTU of the tile
+  int bd;
+};
+
+__device__ __forceinline__ bool saoCtuAvail(uint32_t avail, int rx, int ry)
+{
+  if ((rx | ry) == 0) return true;
+  const int bit = ry == 0 ? (rx < 0 ? 0x01 : 0x02) : (ry < 0 ? (rx == 0 ? 0x04 : (rx < 0 ? 0x10 : 0x20)) : (rx == 0 ? 0x08 : (rx < 0 ? 0x40 : 0x80)));
+  return (avail & bit) != 0;
+}
+
+// lanes of the 8-sample group at (x,y) that edge-offset class (dxa,dya) must leave untouched: a neighbour outside the
+// picture or in a CTU that is not available (offsetBlock start/end and first/last line rules, SampleAdaptiveOffset.cpp
+// :311-312,:340-341,:398-399,:444-445,:476-477,:514-515 with deriveLoopFilterBoundaryAvailibility :668)
+__device__ __forceinline__ uint32_t saoSkipLanes(int x, int y, int dxa, int dya, uint32_t avail, const SaoGeom& g)
+{
+  const int cwm = (1 << g.cwLog) - 1, chm = (1 << g.chLog) - 1;
+  if ((y & chm) != 0 && ((y + 1) & chm) != 0 && y + 1 < g.h && (x & cwm) != 0 && ((x + 8) & cwm) != 0 && x + 8 < g.w) return 0;
+  const int cx = x >> g.cwLog, cy = y >> g.chLog, last = min(7, g.w - 1 - x);
+  uint32_t m = 0;
 #pragma unroll
   for (int k = 0; k < 2; k++)
   {
-    const int sx_ = k ? -dx : dx, sy_ = k ? -dy : dy;
-    const int nx = x + sx_, ny = y + sy_;
-    if (nx < 0 || ny < 0 || nx >= w || ny >= h) return v;
-    const int rx = nx / cw - cx, ry = ny / ch - cy;
-    if (rx | ry)
+    const int ddx = k ? -dxa : dxa, ddy = k ? -dya : dya;
+    const int ny = y + ddy;
+    if (ny < 0 || ny >= g.h) { m = 0xff; continue; }
+    const int ry = (ny >> g.chLog) - cy;
+    uint32_t mm = saoCtuAvail(avail, 0, ry) ? 0u : 0xffu;
+    if (ddx < 0)
     {
-      // VTMGPU_AVAIL_* bit of the neighbouring CTU at (rx,ry)
-      const int bit = ry == 0 ? (rx < 0 ? 0x01 : 0x02) : (ry < 0 ? (rx == 0 ? 0x04 : (rx < 0 ? 0x10 : 0x20)) : (rx == 0 ? 0x08 : (rx < 0 ? 0x40 : 0x80)));
-      if (!(P.avail & bit)) return v;
+      const bool av = x > 0 && saoCtuAvail(avail, ((x - 1) >> g.cwLog) - cx, ry);
+      mm = (mm & ~1u) | (av ? 0u : 1u);
     }
-    const int n = a[(ay + sy_) * SA_P + ax + sx_];
-    e += (v > n) - (v < n);
+    if (ddx > 0)
+    {
+      const int nx = x + last + 1;
+      const bool av = nx < g.w && saoCtuAvail(avail, (nx >> g.cwLog) - cx, ry);
+      mm = (mm & ~(1u << last)) | (av ? 0u : (1u << last));
+    }
+    m |= mm;
   }
-  return clip3(0, maxv, v + P.off[2 + e]);
+  return m;
 }
 
-// SAO over tile + 3 (everything the ALF stage may read); positions outside the picture take the value of the
-// clamped position (= UnitBuf::extendBorderPel of the SAO output, AdaptiveLoopFilter.cpp:411)
-__device__ __forceinline__ void saSaoTile(pel* b, const pel* a, bool on, int x0, int y0, int tw, int th, int w, int h, int cw, int ch,
-                                          int tcx, int tcy, const SaoDev* nb, int bd)
+// the 8 samples at offset (DX, DY) from the group at ap, as 4 packed registers
+template <int DX> __device__ __forceinline__ uint4 saoNeighbours(const pel* base)
 {
-  const int cols = tw + 6, rows = th + 6;
-  for (int i = threadIdx.x; i < cols * rows; i += SA_THREADS)
+  const uint4 q = *reinterpret_cast<const uint4*>(base);
+  if (DX == 0) return q;
+  if (DX < 0)
   {
-    const int r = i / cols, c = i - r * cols;
-    const int px = x0 - 3 + c, py = y0 - 3 + r;
-    const int x = min(max(px, 0), w - 1), y = min(max(py, 0), h - 1);
-    const int ax = x - (x0 - SA_HX), ay = y - (y0 - SA_HY);
-    b[(py - (y0 - SA_HY)) * SA_P + px - (x0 - SA_HX)] = (pel)(on ? saoSample(a, ax, ay, x, y, w, h, cw, ch, tcx, tcy, nb, bd) : a[ay * SA_P + ax]);
+    const uint32_t l = *reinterpret_cast<const uint32_t*>(base - 2);
+    return make_uint4(mid16(l, q.x), mid16(q.x, q.y), mid16(q.y, q.z), mid16(q.z, q.w));
+  }
+  const uint32_t r = *reinterpret_cast<const uint32_t*>(base + 8);
+  return make_uint4(mid16(q.x, q.y), mid16(q.y, q.z), mid16(q.z, q.w), mid16(q.w, r));
+}
+
+// offset look-up for two lanes: k = packed indices 0..4, lut = 5 signed bytes (lutHi holds byte 4); returns packed s16
+__device__ __forceinline__ uint32_t saoLut(uint32_t k, uint32_t lutLo, uint32_t lutHi)
+{
+  const uint32_t sel = k * 0x11u + 0x00800080u;             // per lane: low nibble k, high nibble k + 8 (= sign replicate)
+  return prmt(lutLo, lutHi, prmt(sel, 0u, 0x4420u));
+}
+
+template <int DXA, int DYA> __device__ __forceinline__ uint4 saoEdge(const pel* ap, uint4 v, uint32_t lutLo, uint32_t lutHi, uint32_t maxvP)
+{
+  const uint4 na = saoNeighbours<DXA>(ap + DYA * SA_P), nb = saoNeighbours<-DXA>(ap - DYA * SA_P);
+  const uint32_t vv[4] = { v.x, v.y, v.z, v.w }, aa[4] = { na.x, na.y, na.z, na.w }, bb[4] = { nb.x, nb.y, nb.z, nb.w };
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+  {
+    const uint32_t c1 = __vadd2(~vv[j], 0x00020002u);                           // 1 - v
+    const uint32_t k = addClamp0(aa[j], c1, 0x00020002u) + addClamp0(bb[j], c1, 0x00020002u);   // 2 + sgn(a-v) + sgn(b-v)
+    o[j] = addClamp0(vv[j], saoLut(k, lutLo, lutHi), maxvP);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+__device__ __forceinline__ uint32_t laneMask2(uint32_t bits) { return ((bits & 1u) ? 0xffffu : 0u) | ((bits & 2u) ? 0xffff0000u : 0u); }
+
+// SAO of the 8-sample group at smem row r, group gcol (inside the picture); offsetBlock, SampleAdaptiveOffset.cpp:293-547
+__device__ __forceinline__ void saoGroup(pel* b, const pel* a, int r, int gcol, const SaoDev* nb, const SaoGeom& g)
+{
+  const int x = g.bx0 + 8 * gcol, y = g.by0 + r;
+  const pel* ap = a + r * SA_P + 8 * gcol;
+  uint4 v = *reinterpret_cast<const uint4*>(ap);
+  const SaoDev& P = nb[((y >> g.chLog) - g.tcy + 1) * 3 + (x >> g.cwLog) - g.tcx + 1];
+  const int type = P.type;
+  if (type != 0)
+  {
+    const uint32_t maxvP = dup16((1 << g.bd) - 1);
+    if (type == 5)
+    {
+      // band offset: k = (band - first band) & 31 ; bands k = 0..3 carry an offset (:528-541)
+      const uint32_t lutLo = (P.off[0] & 0xff) | (P.off[1] & 0xff) << 8 | (P.off[2] & 0xff) << 16 | (uint32_t)(P.off[3] & 0xff) << 24;
+      const uint32_t nstart = dup16(-(int)P.band);
+      const int sh = g.bd - 5;
+      uint32_t vv[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+      {
+        const uint32_t band = (vv[j] >> sh) & 0x001f001fu;
+        const uint32_t k = __vminu2(__vadd2(band, nstart) & 0x001f001fu, 0x00040004u);
+        vv[j] = addClamp0(vv[j], saoLut(k, lutLo, 0u), maxvP);
+      }
+      v = make_uint4(vv[0], vv[1], vv[2], vv[3]);
+    }
+    else
+    {
+      // edge offset: index k = 2 - edgeType  ->  look-up table holds the offsets in reverse order
+      const uint32_t lutLo = (P.off[4] & 0xff) | (P.off[3] & 0xff) << 8 | (P.off[2] & 0xff) << 16 | (uint32_t)(P.off[1] & 0xff) << 24;
+      const uint32_t lutHi = P.off[0] & 0xff;
+      uint4 o;
+      int dxa, dya;
+      if (type == 1)      { o = saoEdge<-1, 0>(ap, v, lutLo, lutHi, maxvP);  dxa = -1; dya = 0; }
+      else if (type == 2) { o = saoEdge<0, -1>(ap, v, lutLo, lutHi, maxvP);  dxa = 0;  dya = -1; }
+      else if (type == 3) { o = saoEdge<-1, -1>(ap, v, lutLo, lutHi, maxvP); dxa = -1; dya = -1; }
+      else                { o = saoEdge<1, -1>(ap, v, lutLo, lutHi, maxvP);  dxa = 1;  dya = -1; }
+      const uint32_t skip = saoSkipLanes(x, y, dxa, dya, P.avail, g);
+      if (skip)
+      {
+        const uint32_t m0 = laneMask2(skip), m1 = laneMask2(skip >> 2), m2 = laneMask2(skip >> 4), m3 = laneMask2(skip >> 6);
+        o.x = (o.x & ~m0) | (v.x & m0); o.y = (o.y & ~m1) | (v.y & m1); o.z = (o.z & ~m2) | (v.z & m2); o.w = (o.w & ~m3) | (v.w & m3);
+      }
+      v = o;
+    }
+  }
+  *reinterpret_cast<uint4*>(b + r * SA_P + 8 * gcol) = v;
+}
+
+// SAO of a tile of tw x th samples (+ `halo` samples around it: 3 when an ALF stage reads the result, else 0) from smem
+// tile a into smem tile b.  Work items are 8-sample groups; the interior (one CTU => one parameter set => no
+// divergence) is issued first, then the halo strips.  Positions outside the picture are filled afterwards with the
+// value of the clamped position (= UnitBuf::extendBorderPel of the SAO output, AdaptiveLoopFilter.cpp:411).
+__device__ __forceinline__ void saSaoTile(pel* b, const pel* a, int tw, int th, bool halo, const SaoDev* nb, const SaoGeom& g)
+{
+  const int tid = threadIdx.x;
+  const int gin = tw >> 3;                                   // interior groups per row
+  // interior: rows SA_HY .. SA_HY+th-1, groups 1 .. gin ; column-major item order keeps 128-bit smem accesses conflict free
+  for (int i = tid; i < gin * th; i += SA_THREADS)
+  {
+    const int gc = 1 + i / th, r = SA_HY + (i - (gc - 1) * th);
+    if (g.by0 + r < g.h && g.bx0 + 8 * gc < g.w) saoGroup(b, a, r, gc, nb, g);
+  }
+  if (halo)
+  {
+    // left / right halo columns (rows of the tile), then top / bottom 3 rows over all groups
+    const int nside = 2 * th, ntb = 6 * (gin + 2);
+    for (int i = tid; i < nside + ntb; i += SA_THREADS)
+    {
+      int r, gc;
+      if (i < nside) { gc = i < th ? 0 : gin + 1; r = SA_HY + (i < th ? i : i - th); }
+      else
+      {
+        const int j = i - nside, k = j / (gin + 2);
+        gc = j - k * (gin + 2);
+        r = k < 3 ? SA_HY - 3 + k : SA_HY + th + (k - 3);
+      }
+      const int y = g.by0 + r, x = g.bx0 + 8 * gc;
+      if (y >= 0 && y < g.h && x >= 0 && x < g.w) saoGroup(b, a, r, gc, nb, g);
+    }
+    // replicate border of the SAO output for tiles on the picture border
+    const int xl = g.bx0 + SA_HX - 3, xr = g.bx0 + SA_HX + tw + 2, yt = g.by0 + SA_HY - 3, yb = g.by0 + SA_HY + th + 2;
+    if (xl < 0 || yt < 0 || xr >= g.w || yb >= g.h)
+    {
+      __syncthreads();
+      const int cols = tw + 6, rows = th + 6;
+      for (int i = tid; i < cols * rows; i += SA_THREADS)
+      {
+        const int rr = i / cols, cc = i - rr * cols;
+        const int px = xl + cc, py = yt + rr;
+        if (px < 0 || py < 0 || px >= g.w || py >= g.h)
+        {
+          const int sx_ = min(max(px, 0), g.w - 1), sy_ = min(max(py, 0), g.h - 1);
+          b[(py - g.by0) * SA_P + px - g.bx0] = b[(sy_ - g.by0) * SA_P + sx_ - g.bx0];
+        }
+      }
+    }
   }
 }
 
-// one output sample of filterBlk; c = centre in smem, o1..o3 = row offsets (already limited by the virtual boundary)
+// ---- ALF: generic scalar routines (virtual-boundary rows, halo cells, wide coefficients, non-4:2:0 CC-ALF) ----------
 __device__ __forceinline__ int alfTap(const pel* c, int off, int cur, short2 f)
 {
   const int cl = f.y;
@@ -135,8 +301,286 @@ __device__ __forceinline__ void vbLimit(int yv, int vbPos, int span, int& lim, b
   else if (yv >= vbPos && yv <= vbPos + span - 1) { lim = yv - vbPos; nearVb = yv == vbPos; }
 }
 
-__global__ void __launch_bounds__(SA_THREADS) k_sao_alf(const SlotDev* __restrict__ slots, int firstSlot, int srcBuf, int dstBuf, Geom g, int tilesX,
-                                                        int doSao, int doAlf)
+// Laplacian sums of the 2x2 cell whose top-left sample is p0 (picture row r): positions (r,c) and (r+1,c+1);
+// rows beyond the virtual boundary are replaced (deriveClassificationBlk :906-915)
+__device__ __forceinline__ uint2 alfCellGeneric(const pel* p0, int r, int ctuMask, int vbL)
+{
+  int up = -SA_P, dn2 = 2 * SA_P;                                             // row r-1, row r+2
+  const int rv = r & ctuMask;
+  if (r > 0 && rv == vbL - 2) dn2 = SA_P;
+  else if (r > 0 && rv == vbL) up = 0;
+  const int y0v = p0[0] << 1, y1v = p0[SA_P + 1] << 1;
+  const int v = iabs(y0v - p0[up] - p0[SA_P]) + iabs(y1v - p0[1] - p0[dn2 + 1]);
+  const int h = iabs(y0v - p0[1] - p0[-1]) + iabs(y1v - p0[SA_P + 2] - p0[SA_P]);
+  const int d0 = iabs(y0v - p0[up - 1] - p0[SA_P + 1]) + iabs(y1v - p0[0] - p0[dn2 + 2]);
+  const int d1 = iabs(y0v - p0[SA_P - 1] - p0[up + 1]) + iabs(y1v - p0[dn2] - p0[2]);
+  return make_uint2((uint32_t)v | (uint32_t)h << 16, (uint32_t)d0 | (uint32_t)d1 << 16);
+}
+
+// class index and transpose index of a 4x4 block from the four direction sums (deriveClassificationBlk :1012-1075)
+__device__ __forceinline__ void alfClassify(int sumV, int sumH, int sumD0, int sumD1, int scale, int bd, int& cls, int& tIdx)
+{
+  const int act = clip3(0, 15, ((sumV + sumH) * scale) >> (bd + 4));
+  cls = act == 0 ? 0 : (act == 1 ? 1 : (act < 7 ? 2 : (act < 15 ? 3 : 4)));      // th[] = {0,1,2,2,2,2,2,3,3,3,3,3,3,3,3,4}
+  int hv1, hv0, d1, d0, dirHV, dirD;
+  if (sumV > sumH) { hv1 = sumV; hv0 = sumH; dirHV = 1; } else { hv1 = sumH; hv0 = sumV; dirHV = 3; }
+  if (sumD0 > sumD1) { d1 = sumD0; d0 = sumD1; dirD = 0; } else { d1 = sumD1; d0 = sumD0; dirD = 2; }
+  int hvd1, hvd0, mainDir, secDir;
+  if ((uint32_t)d1 * (uint32_t)hv0 > (uint32_t)hv1 * (uint32_t)d0) { hvd1 = d1; hvd0 = d0; mainDir = dirD; secDir = dirHV; }
+  else { hvd1 = hv1; hvd0 = hv0; mainDir = dirHV; secDir = dirD; }
+  int strength = 0;
+  if (hvd1 > 2 * hvd0) strength = 1;
+  if (hvd1 * 2 > 9 * hvd0) strength = 2;
+  if (strength) cls += (((mainDir & 1) << 1) + strength) * 5;
+  tIdx = (0x31322010 >> (4 * (mainDir * 2 + (secDir >> 1)))) & 0xf;              // transposeTable = {0,1,0,2,2,3,1,3}
+}
+
+// one 4x4 luma block, any row position: classification incl. the virtual-boundary rules and the 7x7 filter with row clamping
+__device__ void alfLumaBlockGeneric(const SaoAlfSmem& sm, const pel* c0, pel* out, int pitchOut, int bi, int bj, int by, const short2* set,
+                                    int ctuMask, int vbL, int bd)
+{
+  const int yb = by & ctuMask;
+  const int i0 = (yb == vbL) ? 1 : 0, i1 = (yb == vbL - 4) ? 3 : 4;
+  int sum[4] = { 0, 0, 0, 0 };
+  for (int i = i0; i < i1; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+    {
+      const uint2 c = sm.u.cell[2 * bi + i][2 * bj + j];
+      sum[0] += c.x & 0xffff; sum[1] += c.x >> 16; sum[2] += c.y & 0xffff; sum[3] += c.y >> 16;
+    }
+  int cls, tIdx;
+  alfClassify(sum[0], sum[1], sum[2], sum[3], (yb == vbL - 4 || yb == vbL) ? 96 : 64, bd, cls, tIdx);
+  short2 f[12];
+#pragma unroll
+  for (int k = 0; k < 12; k++) f[k] = __ldg(&set[cls * 12 + c_perm7[tIdx][k]]);
+  const int maxv = (1 << bd) - 1;
+  for (int r = 0; r < 4; r++)
+  {
+    int lim; bool nearVb;
+    vbLimit((by + r) & ctuMask, vbL, 4, lim, nearVb);
+    const int o1 = min(1, lim) * SA_P, o2 = min(2, lim) * SA_P, o3 = lim * SA_P;   // lim <= 3
+    pel res[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+    {
+      const pel* c = c0 + r * SA_P + q;
+      const int cur = c[0];
+      int s = alfTap(c, o3, cur, f[0]) + alfTap(c, o2 + 1, cur, f[1]) + alfTap(c, o2, cur, f[2]) + alfTap(c, o2 - 1, cur, f[3]) +
+              alfTap(c, o1 + 2, cur, f[4]) + alfTap(c, o1 + 1, cur, f[5]) + alfTap(c, o1, cur, f[6]) + alfTap(c, o1 - 1, cur, f[7]) +
+              alfTap(c, o1 - 2, cur, f[8]) + alfTap(c, 3, cur, f[9]) + alfTap(c, 2, cur, f[10]) + alfTap(c, 1, cur, f[11]);
+      s = (s + 64) >> (nearVb ? 10 : 7);
+      res[q] = (pel)clip3(0, maxv, cur + s);
+    }
+    *reinterpret_cast<int2*>(out + (size_t)r * pitchOut) = *reinterpret_cast<const int2*>(res);
+  }
+}
+
+// ---- ALF luma: packed fast path (block rows that do not touch a virtual boundary) -------------------------------------
+// Laplacian cells of the block's own 4x4 samples (2x2 cells) from the 6x6 sample patch around it
+__device__ __forceinline__ void alfOwnCells(SaoAlfSmem& sm, const pel* c0, int bi, int bj)
+{
+  int p[6][6];                                               // p[r][c] = sample (r-1, c-1) relative to the block
+#pragma unroll
+  for (int r = 0; r < 6; r++)
+  {
+    const pel* row = c0 + (r - 1) * SA_P;
+    const uint2 q0 = *reinterpret_cast<const uint2*>(row - 4), q1 = *reinterpret_cast<const uint2*>(row);
+    const uint32_t w4 = *reinterpret_cast<const uint32_t*>(row + 4);
+    p[r][0] = q0.y >> 16; p[r][1] = q1.x & 0xffff; p[r][2] = q1.x >> 16; p[r][3] = q1.y & 0xffff; p[r][4] = q1.y >> 16; p[r][5] = w4 & 0xffff;
+  }
+#pragma unroll
+  for (int cy = 0; cy < 2; cy++)
+#pragma unroll
+    for (int cx = 0; cx < 2; cx++)
+    {
+      const int r = 1 + 2 * cy, c = 1 + 2 * cx;
+      const int a2 = 2 * p[r][c], b2 = 2 * p[r + 1][c + 1];
+      const int v = iabs(a2 - p[r - 1][c] - p[r + 1][c]) + iabs(b2 - p[r][c + 1] - p[r + 2][c + 1]);
+      const int h = iabs(a2 - p[r][c - 1] - p[r][c + 1]) + iabs(b2 - p[r + 1][c] - p[r + 1][c + 2]);
+      const int d0 = iabs(a2 - p[r - 1][c - 1] - p[r + 1][c + 1]) + iabs(b2 - p[r][c] - p[r + 2][c + 2]);
+      const int d1 = iabs(a2 - p[r + 1][c - 1] - p[r - 1][c + 1]) + iabs(b2 - p[r + 2][c] - p[r][c + 2]);
+      sm.u.cell[2 * bi + 1 + cy][2 * bj + 1 + cx] = make_uint2((uint32_t)v | (uint32_t)h << 16, (uint32_t)d0 | (uint32_t)d1 << 16);
+    }
+}
+
+// 7x7 diamond on one 4x4 block, two pixels per register.  e = pre-expanded {coefficient, clip} entry of the block's
+// (filter set, class, transpose).  clamp(n - cur, -c, c) + c  ==  max(min(n + (c - cur), 2c), 0)  is ONE instruction;
+// the excess sum(coef * 2c) is folded into e->bias together with the rounding offset 64 (filterBlk :1249-1297).
+__device__ __forceinline__ void alfLumaBlockFast(const pel* c0, pel* out, int pitchOut, const AlfLumaEntry* __restrict__ e, uint32_t maxvP)
+{
+  uint32_t coefB[12], clipP1[12], clip2[12];
+  {
+    const uint4* q = reinterpret_cast<const uint4*>(e);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+    {
+      const uint4 a = __ldg(q + i), b = __ldg(q + 3 + i), c = __ldg(q + 6 + i);
+      coefB[4 * i] = a.x; coefB[4 * i + 1] = a.y; coefB[4 * i + 2] = a.z; coefB[4 * i + 3] = a.w;
+      clipP1[4 * i] = b.x; clipP1[4 * i + 1] = b.y; clipP1[4 * i + 2] = b.z; clipP1[4 * i + 3] = b.w;
+      clip2[4 * i] = c.x; clip2[4 * i + 1] = c.y; clip2[4 * i + 2] = c.z; clip2[4 * i + 3] = c.w;
+    }
+  }
+  const int bias = __ldg(&e->bias);
+  // w[ir][j] = samples (4bj - 4 + 2j, +1) of input row ir - 3 ; o[ir][j] = the pair starting one sample later
+  uint32_t w[10][6], o[10][5];
+#pragma unroll
+  for (int ir = 0; ir < 10; ir++)
+  {
+    const uint2* rp = reinterpret_cast<const uint2*>(c0 + (ir - 3) * SA_P - 4);
+    const uint2 q0 = rp[0], q1 = rp[1], q2 = rp[2];
+    w[ir][0] = q0.x; w[ir][1] = q0.y; w[ir][2] = q1.x; w[ir][3] = q1.y; w[ir][4] = q2.x; w[ir][5] = q2.y;
+#pragma unroll
+    for (int j = 0; j < 5; j++) o[ir][j] = mid16(w[ir][j], w[ir][j + 1]);
+  }
+#define ALF_PAIR(IR, C) ((((C) & 1) != 0) ? o[IR][((C) + 3) >> 1] : w[IR][((C) + 4) >> 1])
+#define ALF_TAP(K, DX, DY)                                                                                              \
+  {                                                                                                                     \
+    const uint32_t cb = __vadd2(clipP1[K], ncur);                                                                       \
+    const uint32_t s = addClamp0(ALF_PAIR(orow + 3 + (DY), 2 * px + (DX)), cb, clip2[K]) +                              \
+                       addClamp0(ALF_PAIR(orow + 3 - (DY), 2 * px - (DX)), cb, clip2[K]);                               \
+    acc0 = __dp2a_lo((int)s, (int)coefB[K], acc0);                                                                      \
+    acc1 = __dp2a_hi((int)s, (int)coefB[K], acc1);                                                                      \
+  }
+#pragma unroll
+  for (int orow = 0; orow < 4; orow++)
+  {
+    uint32_t res[2];
+#pragma unroll
+    for (int px = 0; px < 2; px++)
+    {
+      const uint32_t cur = w[orow + 3][2 + px], ncur = ~cur;                   // clipP1 + ~cur = clip - cur per lane
+      int acc0 = bias, acc1 = bias;
+      ALF_TAP(0, 0, 3)
+      ALF_TAP(1, 1, 2) ALF_TAP(2, 0, 2) ALF_TAP(3, -1, 2)
+      ALF_TAP(4, 2, 1) ALF_TAP(5, 1, 1) ALF_TAP(6, 0, 1) ALF_TAP(7, -1, 1) ALF_TAP(8, -2, 1)
+      ALF_TAP(9, 3, 0) ALF_TAP(10, 2, 0) ALF_TAP(11, 1, 0)
+      res[px] = addClamp0(cur, prmt((uint32_t)(acc0 >> 7), (uint32_t)(acc1 >> 7), 0x5410u), maxvP);
+    }
+    *reinterpret_cast<uint2*>(out + (size_t)orow * pitchOut) = make_uint2(res[0], res[1]);
+  }
+#undef ALF_TAP
+#undef ALF_PAIR
+}
+
+// ---- chroma 5x5 + CC-ALF, packed (four horizontally adjacent chroma samples per thread) ----------------------------
+struct ChromaCoef
+{
+  uint32_t coefB[6], clipP1[6], clip2[6];
+  int bias;
+};
+
+__device__ __forceinline__ ChromaCoef chromaCoef(const short2* f)
+{
+  ChromaCoef c;
+  int b = 64;
+#pragma unroll
+  for (int k = 0; k < 6; k++)
+  {
+    const int co = f[k].x, cl = f[k].y;
+    c.coefB[k] = (uint32_t)(co & 0xff) * 0x01000001u;
+    c.clipP1[k] = dup16(cl + 1);
+    c.clip2[k] = dup16(2 * cl);
+    b -= co * 2 * cl;
+  }
+  c.bias = b;
+  return c;
+}
+
+// ALF of the 4 chroma samples at cb (smem, SAO output); o1/o2 = row offsets after virtual-boundary clamping
+__device__ __forceinline__ uint2 alfChromaQuad(const pel* cb, int o1, int o2, bool nearVb, const ChromaCoef& C, uint32_t maxvP)
+{
+  // words of a row: wm2 = samples (-2,-1), w0 = (0,1), w2 = (2,3), w4 = (4,5)
+  uint32_t res[2];
+  const uint2 c0q = *reinterpret_cast<const uint2*>(cb - 4), c0r = *reinterpret_cast<const uint2*>(cb);
+  const uint32_t c0w4 = *reinterpret_cast<const uint32_t*>(cb + 4);
+  const uint32_t r0[5] = { c0q.y, c0r.x, c0r.y, c0w4, 0 };                                   // centre row: wm2, w0, w2, w4
+  const uint32_t r0o[3] = { mid16(r0[0], r0[1]), mid16(r0[1], r0[2]), mid16(r0[2], r0[3]) };    // pairs starting at -1, 1, 3
+  uint32_t pe[2][3], po[2][3];                                                              // rows +o1 / -o1: even words wm2.., odd pairs
+#pragma unroll
+  for (int s = 0; s < 2; s++)
+  {
+    const pel* rp = cb + (s ? -o1 : o1);
+    const uint2 q = *reinterpret_cast<const uint2*>(rp - 4), r = *reinterpret_cast<const uint2*>(rp);
+    const uint32_t w4 = *reinterpret_cast<const uint32_t*>(rp + 4);
+    pe[s][0] = r.x; pe[s][1] = r.y; pe[s][2] = 0;
+    po[s][0] = mid16(q.y, r.x); po[s][1] = mid16(r.x, r.y); po[s][2] = mid16(r.y, w4);
+  }
+  const uint2 p2 = *reinterpret_cast<const uint2*>(cb + o2), m2 = *reinterpret_cast<const uint2*>(cb - o2);
+  const uint32_t p2w[2] = { p2.x, p2.y }, m2w[2] = { m2.x, m2.y };
+#pragma unroll
+  for (int px = 0; px < 2; px++)
+  {
+    const uint32_t cur = r0[1 + px], ncur = ~cur;
+    int acc0 = C.bias, acc1 = C.bias;
+#define CH_TAP(K, NP, NM)                                                                       \
+    {                                                                                           \
+      const uint32_t cbv = __vadd2(C.clipP1[K], ncur);                                          \
+      const uint32_t s = addClamp0(NP, cbv, C.clip2[K]) + addClamp0(NM, cbv, C.clip2[K]);       \
+      acc0 = __dp2a_lo((int)s, (int)C.coefB[K], acc0);                                          \
+      acc1 = __dp2a_hi((int)s, (int)C.coefB[K], acc1);                                          \
+    }
+    CH_TAP(0, p2w[px], m2w[px])                       // (0,+2) / (0,-2)
+    CH_TAP(1, po[0][px + 1], po[1][px])               // (+1,+1) / (-1,-1)
+    CH_TAP(2, pe[0][px], pe[1][px])                   // (0,+1) / (0,-1)
+    CH_TAP(3, po[0][px], po[1][px + 1])               // (-1,+1) / (+1,-1)
+    CH_TAP(4, r0[2 + px], r0[px])                     // (+2,0) / (-2,0)
+    CH_TAP(5, r0o[px + 1], r0o[px])                   // (+1,0) / (-1,0)
+#undef CH_TAP
+    const int sh = nearVb ? 10 : 7;
+    res[px] = addClamp0(cur, prmt((uint32_t)(acc0 >> sh), (uint32_t)(acc1 >> sh), 0x5410u), maxvP);
+  }
+  return make_uint2(res[0], res[1]);
+}
+
+// CC-ALF correction for 4 chroma samples in 4:2:0 / 4:2:2 (sx = 1): collocated luma column = 2 * chroma column.
+// l = luma sample collocated with the first chroma sample (smem, SAO output); l1,l2,l3 = row offsets (filterBlkCcAlf
+// :1376-1386).  Returns the packed corrections (already clipped to the chroma range around 0).
+__device__ __forceinline__ uint2 ccAlfQuad420(const pel* l, int l1, int l2, int l3, const int cc[7], uint32_t maxcP, uint32_t halfP)
+{
+  // luma words of a row relative to l: W(-2), W(0), W(2), W(4), W(6)
+  uint32_t ctr[2], up[2], lf[2][2], rt[2][2], dl[2], dm[2], dr[2], d2[2];
+  {
+    const uint2 q = *reinterpret_cast<const uint2*>(l - 4), r = *reinterpret_cast<const uint2*>(l), t = *reinterpret_cast<const uint2*>(l + 4);
+    // even samples (0,2),(4,6) ; odd samples (-1,1),(3,5) and (1,3),(5,7)
+    ctr[0] = prmt(r.x, r.y, 0x5410u); ctr[1] = prmt(t.x, t.y, 0x5410u);
+    lf[0][0] = prmt(q.y, r.x, 0x7632u); lf[0][1] = prmt(r.y, t.x, 0x7632u);
+    rt[0][0] = prmt(r.x, r.y, 0x7632u); rt[0][1] = prmt(t.x, t.y, 0x7632u);
+  }
+  {
+    const uint2 r = *reinterpret_cast<const uint2*>(l + l2), t = *reinterpret_cast<const uint2*>(l + l2 + 4);
+    up[0] = prmt(r.x, r.y, 0x5410u); up[1] = prmt(t.x, t.y, 0x5410u);
+  }
+  {
+    const uint2 q = *reinterpret_cast<const uint2*>(l + l1 - 4), r = *reinterpret_cast<const uint2*>(l + l1), t = *reinterpret_cast<const uint2*>(l + l1 + 4);
+    dm[0] = prmt(r.x, r.y, 0x5410u); dm[1] = prmt(t.x, t.y, 0x5410u);
+    dl[0] = prmt(q.y, r.x, 0x7632u); dl[1] = prmt(r.y, t.x, 0x7632u);
+    dr[0] = prmt(r.x, r.y, 0x7632u); dr[1] = prmt(t.x, t.y, 0x7632u);
+  }
+  {
+    const uint2 r = *reinterpret_cast<const uint2*>(l + l3), t = *reinterpret_cast<const uint2*>(l + l3 + 4);
+    d2[0] = prmt(r.x, r.y, 0x5410u); d2[1] = prmt(t.x, t.y, 0x5410u);
+  }
+  uint32_t cB[7];
+  int fsum = 0;
+#pragma unroll
+  for (int k = 0; k < 7; k++) { cB[k] = (uint32_t)(cc[k] & 0xff) * 0x01000001u; fsum += cc[k]; }
+  uint32_t res[2];
+#pragma unroll
+  for (int px = 0; px < 2; px++)
+  {
+    int a0 = 64 - (int)(ctr[px] & 0xffff) * fsum, a1 = 64 - (int)(ctr[px] >> 16) * fsum;
+#define CC_TAP(K, N) a0 = __dp2a_lo((int)(N), (int)cB[K], a0); a1 = __dp2a_hi((int)(N), (int)cB[K], a1);
+    CC_TAP(0, up[px]) CC_TAP(1, lf[0][px]) CC_TAP(2, rt[0][px]) CC_TAP(3, dl[px]) CC_TAP(4, dm[px]) CC_TAP(5, dr[px]) CC_TAP(6, d2[px])
+#undef CC_TAP
+    const uint32_t t = addClamp0(prmt((uint32_t)(a0 >> 7), (uint32_t)(a1 >> 7), 0x5410u), halfP, maxcP);     // ClipPel(sum + half)
+    res[px] = __vadd2(t, ~halfP + 0x00010001u);                                                                // - half
+  }
+  return make_uint2(res[0], res[1]);
+}
+
+__global__ void __launch_bounds__(SA_THREADS, 2) k_sao_alf(const SlotDev* __restrict__ slots, int firstSlot, int srcBuf, int dstBuf, Geom g, int tilesX,
+                                                           int doSao, int doAlf)
 {
   extern __shared__ __align__(16) unsigned char smraw[];
   SaoAlfSmem& sm = *reinterpret_cast<SaoAlfSmem*>(smraw);
@@ -148,11 +592,11 @@ __global__ void __launch_bounds__(SA_THREADS) k_sao_alf(const SlotDev* __restric
   const bool saoOn = doSao && S.saoOn, alfPic = doAlf && S.alfOn && (S.alf->enabled[0] | S.alf->enabled[1] | S.alf->enabled[2]);
 
   // ---- per-tile parameters ------------------------------------------------------------------------------
-  if (saoOn && tid < 27)
+  if (tid < 27)
   {
     const int c = tid / 9, k = tid - c * 9, cx = tcx + k % 3 - 1, cy = tcy + k / 3 - 1;
     SaoDev z = {};
-    if (cx >= 0 && cy >= 0 && cx < g.wCtus && cy < g.hCtus && c < g.ncomp) z = S.sao[(cy * g.wCtus + cx) * 3 + c];
+    if (saoOn && cx >= 0 && cy >= 0 && cx < g.wCtus && cy < g.hCtus && c < g.ncomp) z = S.sao[(cy * g.wCtus + cx) * 3 + c];
     sm.sao[c][k] = z;
   }
   bool alfY = false, alfC[2] = { false, false };
@@ -165,11 +609,6 @@ __global__ void __launch_bounds__(SA_THREADS) k_sao_alf(const SlotDev* __restric
       alfC[c] = g.ncomp > 1 && S.alfCtu[(1 + c) * nCtus + ctuIdx] != 0;
       ccIdc[c] = (g.ncomp > 1 && S.alf->ccEnabled[c]) ? S.alfCtu[(5 + c) * nCtus + ctuIdx] : 0;
     }
-    if (alfY)
-    {
-      const short2* set = &S.alf->luma[S.alfFilterIdx[ctuIdx]][0][0];
-      for (int i = tid; i < 25 * 12; i += SA_THREADS) (&sm.lumaSet[0][0])[i] = set[i];
-    }
     if (tid < 12 && alfC[tid / 6]) sm.chromaSet[tid / 6][tid % 6] = S.alf->chroma[S.alfCtu[(3 + tid / 6) * nCtus + ctuIdx]][tid % 6];
     if (tid < 16 && ccIdc[tid >> 3]) sm.cc[tid >> 3][tid & 7] = S.alf->cc[tid >> 3][ccIdc[tid >> 3] - 1][tid & 7];
   }
@@ -178,120 +617,110 @@ __global__ void __launch_bounds__(SA_THREADS) k_sao_alf(const SlotDev* __restric
   const PlaneDev srcY = S.buf[srcBuf][0], dstY = S.buf[dstBuf][0];
   saLoadTile(sm.a, srcY, x0, y0, SA_T, SA_T);
   __syncthreads();
-  saSaoTile(sm.bl, sm.a, saoOn, x0, y0, SA_T, SA_T, g.w, g.h, g.ctu, g.ctu, tcx, tcy, sm.sao[0], g.bdL);
-  __syncthreads();
-
-  const int vbL = g.ctu - 4;
-  if (alfY)
+  bool saoY = false;
+#pragma unroll
+  for (int k = 0; k < 9; k++) saoY |= sm.sao[0][k].type != 0;
+  const bool lumaHalo = alfY || ccIdc[0] || ccIdc[1];
+  // without SAO in reach the loaded tile (already replicate padded) IS the ALF input; chroma then stages through sm.bl
+  pel* const lumaB = saoY ? sm.bl : sm.a;
+  pel* const chromaA = saoY ? sm.a : sm.bl;
+  if (saoY)
   {
-    // Laplacian pair sums at the 2x2-subsampled positions (r,c) = (y0-2+2i, x0-2+2j)
-    for (int i = tid; i < SA_LAPN * SA_LAPN; i += SA_THREADS)
-    {
-      const int li = i / SA_LAPN, lj = i - li * SA_LAPN;
-      const int r = y0 - 2 + 2 * li;
-      const pel* p0 = &sm.bl[(2 * li + SA_HY - 2) * SA_P + 2 * lj + SA_HX - 2];   // (r, c)
-      int up = -SA_P, dn2 = 2 * SA_P;                                            // row r-1, row r+2
-      const int rv = r & (g.ctu - 1);
-      if (r > 0 && rv == vbL - 2) dn2 = SA_P;
-      else if (r > 0 && rv == vbL) up = 0;
-      const int y0v = p0[0] << 1, y1v = p0[SA_P + 1] << 1;
-      sm.u.lap[0][li][lj] = (uint16_t)(iabs(y0v - p0[up] - p0[SA_P]) + iabs(y1v - p0[1] - p0[dn2 + 1]));
-      sm.u.lap[1][li][lj] = (uint16_t)(iabs(y0v - p0[1] - p0[-1]) + iabs(y1v - p0[SA_P + 2] - p0[SA_P]));
-      sm.u.lap[2][li][lj] = (uint16_t)(iabs(y0v - p0[up - 1] - p0[SA_P + 1]) + iabs(y1v - p0[0] - p0[dn2 + 2]));
-      sm.u.lap[3][li][lj] = (uint16_t)(iabs(y0v - p0[SA_P - 1] - p0[up + 1]) + iabs(y1v - p0[dn2] - p0[2]));
-    }
+    const SaoGeom sg = { x0 - SA_HX, y0 - SA_HY, g.w, g.h, g.ctuLog2, g.ctuLog2, tcx, tcy, g.bdL };
+    saSaoTile(sm.bl, sm.a, SA_T, SA_T, lumaHalo, sm.sao[0], sg);
     __syncthreads();
   }
+
+  const int vbL = g.ctu - 4, ctuMask = g.ctu - 1;
+  const int bi = tid >> 4, bj = tid & 15;
+  const int bx = x0 + 4 * bj, by = y0 + 4 * bi;
+  const pel* c0 = &lumaB[(4 * bi + SA_HY) * SA_P + 4 * bj + SA_HX];
+  if (alfY)
   {
-    const int bi = tid >> 4, bj = tid & 15;
-    const int bx = x0 + 4 * bj, by = y0 + 4 * bi;
+    const int yb = by & ctuMask;
+    const bool vbBlk = yb == vbL - 4 || yb == vbL;             // uniform per warp (two block rows) for CTU sizes >= 32
+    const bool wide = S.alf->wide != 0;
+    // Laplacian cells: own 2x2 cells per block (registers), ring and virtual-boundary rows by the generic routine
+    if (!vbBlk) alfOwnCells(sm, c0, bi, bj);
+    else
+    {
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+      {
+        const int li = 2 * bi + 1 + (k >> 1), lj = 2 * bj + 1 + (k & 1);
+        sm.u.cell[li][lj] = alfCellGeneric(&lumaB[(2 * li + SA_HY - 2) * SA_P + 2 * lj + SA_HX - 2], y0 - 2 + 2 * li, ctuMask, vbL);
+      }
+    }
+    if (tid < 4 * (SA_CELLS - 1))
+    {
+      const int side = tid / (SA_CELLS - 1), k = tid - side * (SA_CELLS - 1);
+      const int li = side == 0 ? 0 : (side == 1 ? SA_CELLS - 1 : (side == 2 ? 1 + k : k));
+      const int lj = side == 0 ? k : (side == 1 ? 1 + k : (side == 2 ? 0 : SA_CELLS - 1));
+      sm.u.cell[li][lj] = alfCellGeneric(&lumaB[(2 * li + SA_HY - 2) * SA_P + 2 * lj + SA_HX - 2], y0 - 2 + 2 * li, ctuMask, vbL);
+    }
+    __syncthreads();
     if (bx < g.w && by < g.h)
     {
-      const pel* c0 = &sm.bl[(4 * bi + SA_HY) * SA_P + 4 * bj + SA_HX];
       pel* out = dstY.p + (size_t)by * dstY.pitch + bx;
-      if (!alfY)
-      {
-#pragma unroll
-        for (int r = 0; r < 4; r++) *reinterpret_cast<int2*>(out + (size_t)r * dstY.pitch) = *reinterpret_cast<const int2*>(c0 + r * SA_P);
-      }
+      const int setIdx = S.alfFilterIdx[ctuIdx];
+      if (vbBlk || wide) alfLumaBlockGeneric(sm, c0, out, dstY.pitch, bi, bj, by, &S.alf->luma[setIdx][0][0], ctuMask, vbL, g.bdL);
       else
       {
-        // classification of this 4x4 block (deriveClassificationBlk)
-        const int yb = by & (g.ctu - 1);
-        const int i0 = (yb == vbL) ? 1 : 0, i1 = (yb == vbL - 4) ? 3 : 4;
-        int sum[4] = { 0, 0, 0, 0 };
+        // window = cells (2bi .. 2bi+3) x (2bj .. 2bj+3); row sums stay below 2^16 per lane for any bit depth <= 12
+        int sumV = 0, sumH = 0, sumD0 = 0, sumD1 = 0;
 #pragma unroll
-        for (int d = 0; d < 4; d++)
-          for (int i = i0; i < i1; i++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) sum[d] += sm.u.lap[d][2 * bi + i][2 * bj + j];
-        const int sumV = sum[0], sumH = sum[1], sumD0 = sum[2], sumD1 = sum[3];
-        const int scale = (yb == vbL - 4 || yb == vbL) ? 96 : 64;
-        const int act = clip3(0, 15, ((sumV + sumH) * scale) >> (g.bdL + 4));
-        // th[] = {0,1,2,2,2,2,2,3,3,3,3,3,3,3,3,4}
-        int cls = act == 0 ? 0 : (act == 1 ? 1 : (act < 7 ? 2 : (act < 15 ? 3 : 4)));
-        int hv1, hv0, d1, d0, dirHV, dirD;
-        if (sumV > sumH) { hv1 = sumV; hv0 = sumH; dirHV = 1; } else { hv1 = sumH; hv0 = sumV; dirHV = 3; }
-        if (sumD0 > sumD1) { d1 = sumD0; d0 = sumD1; dirD = 0; } else { d1 = sumD1; d0 = sumD0; dirD = 2; }
-        int hvd1, hvd0, mainDir, secDir;
-        if ((uint32_t)d1 * (uint32_t)hv0 > (uint32_t)hv1 * (uint32_t)d0) { hvd1 = d1; hvd0 = d0; mainDir = dirD; secDir = dirHV; }
-        else { hvd1 = hv1; hvd0 = hv0; mainDir = dirHV; secDir = dirD; }
-        int strength = 0;
-        if (hvd1 > 2 * hvd0) strength = 1;
-        if (hvd1 * 2 > 9 * hvd0) strength = 2;
-        if (strength) cls += (((mainDir & 1) << 1) + strength) * 5;
-        // transposeTable = {0,1,0,2,2,3,1,3}[mainDir*2 + (secDir>>1)]
-        const int tIdx = (0x31322010 >> (4 * (mainDir * 2 + (secDir >> 1)))) & 0xf;
-
-        short2 f[12];
-#pragma unroll
-        for (int k = 0; k < 12; k++) f[k] = sm.lumaSet[cls][c_perm7[tIdx][k]];
-        const int maxv = (1 << g.bdL) - 1;
-#pragma unroll
-        for (int r = 0; r < 4; r++)
+        for (int i = 0; i < 4; i++)
         {
-          int lim; bool nearVb;
-          vbLimit((by + r) & (g.ctu - 1), vbL, 4, lim, nearVb);
-          const int o1 = min(1, lim) * SA_P, o2 = min(2, lim) * SA_P, o3 = lim * SA_P;   // lim <= 3
-          pel res[4];
-#pragma unroll
-          for (int q = 0; q < 4; q++)
-          {
-            const pel* c = c0 + r * SA_P + q;
-            const int cur = c[0];
-            int s = alfTap(c, o3, cur, f[0]) + alfTap(c, o2 + 1, cur, f[1]) + alfTap(c, o2, cur, f[2]) + alfTap(c, o2 - 1, cur, f[3]) +
-                    alfTap(c, o1 + 2, cur, f[4]) + alfTap(c, o1 + 1, cur, f[5]) + alfTap(c, o1, cur, f[6]) + alfTap(c, o1 - 1, cur, f[7]) +
-                    alfTap(c, o1 - 2, cur, f[8]) + alfTap(c, 3, cur, f[9]) + alfTap(c, 2, cur, f[10]) + alfTap(c, 1, cur, f[11]);
-            s = (s + 64) >> (nearVb ? 10 : 7);
-            res[q] = (pel)clip3(0, maxv, cur + s);
-          }
-          *reinterpret_cast<int2*>(out + (size_t)r * dstY.pitch) = *reinterpret_cast<const int2*>(res);
+          const uint4* rp = reinterpret_cast<const uint4*>(&sm.u.cell[2 * bi + i][2 * bj]);
+          const uint4 q0 = rp[0], q1 = rp[1];
+          const uint32_t vh = q0.x + q0.z + q1.x + q1.z, dd = q0.y + q0.w + q1.y + q1.w;
+          sumV += vh & 0xffff; sumH += vh >> 16; sumD0 += dd & 0xffff; sumD1 += dd >> 16;
         }
+        int cls, tIdx;
+        alfClassify(sumV, sumH, sumD0, sumD1, 64, g.bdL, cls, tIdx);
+        alfLumaBlockFast(c0, out, dstY.pitch, S.lumaTab + ((size_t)(setIdx * 25 + cls) * 4 + tIdx), dup16((1 << g.bdL) - 1));
       }
+    }
+  }
+  else
+  {
+    // no luma ALF in this CTU: the SAO output is the result (128-bit rows)
+    for (int i = tid; i < SA_T * (SA_T / 8); i += SA_THREADS)
+    {
+      const int r = i >> 3, gc = i & 7;
+      const int y = y0 + r, x = x0 + 8 * gc;
+      if (y < g.h && x < g.w)
+        *reinterpret_cast<int4*>(dstY.p + (size_t)y * dstY.pitch + x) = *reinterpret_cast<const int4*>(&lumaB[(r + SA_HY) * SA_P + 8 * gc + SA_HX]);
     }
   }
   if (g.ncomp == 1) return;
 
   // ---- chroma (Cb then Cr reuse the same shared buffers) ---------------------------------------------------
   const int tw = SA_T >> g.sx, th = SA_T >> g.sy, cx0 = x0 >> g.sx, cy0 = y0 >> g.sy;
-  const int cw = g.w >> g.sx, chh = g.h >> g.sy, ctuW = g.ctu >> g.sx, ctuH = g.ctu >> g.sy;
+  const int cw = g.w >> g.sx, chh = g.h >> g.sy, ctuH = g.ctu >> g.sy;
   const int vbC = ctuH - 2, maxc = (1 << g.bdC) - 1, half = (1 << g.bdC) >> 1;
+  const uint32_t maxcP = dup16(maxc), halfP = dup16(half);
   for (int c = 0; c < 2; c++)
   {
     const PlaneDev srcC = S.buf[srcBuf][1 + c], dstC = S.buf[dstBuf][1 + c];
-    __syncthreads();                                  // previous users of sm.a / sm.u are done
-    saLoadTile(sm.a, srcC, cx0, cy0, tw, th);
+    __syncthreads();                                  // previous users of chromaA / sm.u are done
+    saLoadTile(chromaA, srcC, cx0, cy0, tw, th);
     __syncthreads();
-    saSaoTile(sm.u.bc, sm.a, saoOn, cx0, cy0, tw, th, cw, chh, ctuW, ctuH, tcx, tcy, sm.sao[1 + c], g.bdC);
-    __syncthreads();
+    bool saoC = false;
+#pragma unroll
+    for (int k = 0; k < 9; k++) saoC |= sm.sao[1 + c][k].type != 0;
     const bool fOn = alfC[c];
     const int idc = ccIdc[c];
-    short2 f[6];
-    if (fOn)
+    const pel* chromaB = chromaA;
+    if (saoC)
     {
-#pragma unroll
-      for (int k = 0; k < 6; k++) f[k] = sm.chromaSet[c][k];
+      const SaoGeom sg = { cx0 - SA_HX, cy0 - SA_HY, cw, chh, g.ctuLog2 - g.sx, g.ctuLog2 - g.sy, tcx, tcy, g.bdC };
+      saSaoTile(sm.u.bc, chromaA, tw, th, fOn, sm.sao[1 + c], sg);
+      __syncthreads();
+      chromaB = sm.u.bc;
     }
+    ChromaCoef C;
+    if (fOn) C = chromaCoef(sm.chromaSet[c]);
     int cc[7];
     if (idc)
     {
@@ -305,41 +734,45 @@ __global__ void __launch_bounds__(SA_THREADS) k_sao_alf(const SlotDev* __restric
       const int r = i / (tw >> 2), qx = (i - r * (tw >> 2)) * 4;
       const int x = cx0 + qx, y = cy0 + r;
       if (x >= cw || y >= chh) continue;
-      const pel* cb = &sm.u.bc[(r + SA_HY) * SA_P + qx + SA_HX];
-      int lim; bool nearVb;
-      vbLimit(y & (ctuH - 1), vbC, 2, lim, nearVb);
-      const int o1 = min(1, lim) * SA_P, o2 = min(2, lim) * SA_P;
-      // CC-ALF row offsets in the luma tile (filterBlkCcAlf :1376-1386)
-      const int ly = (r << g.sy) + SA_HY, lpos = (y << g.sy) & (g.ctu - 1);
-      int l1 = SA_P, l2 = -SA_P, l3 = 2 * SA_P;
-      if (lpos == vbL - 2 || lpos == vbL + 1) l3 = SA_P;
-      else if (lpos == vbL - 1 || lpos == vbL) l1 = l2 = l3 = 0;
-      pel res[4];
-#pragma unroll
-      for (int q = 0; q < 4; q++)
+      const pel* cb = &chromaB[(r + SA_HY) * SA_P + qx + SA_HX];
+      uint2 v = *reinterpret_cast<const uint2*>(cb);
+      if (fOn)
       {
-        const pel* p = cb + q;
-        int v = p[0];
-        if (fOn)
-        {
-          int s = alfTap(p, o2, v, f[0]) + alfTap(p, o1 + 1, v, f[1]) + alfTap(p, o1, v, f[2]) + alfTap(p, o1 - 1, v, f[3]) +
-                  alfTap(p, 2, v, f[4]) + alfTap(p, 1, v, f[5]);
-          s = (s + 64) >> (nearVb ? 10 : 7);
-          v = clip3(0, maxc, v + s);
-        }
-        if (idc)
-        {
-          const pel* l = &sm.bl[ly * SA_P + ((qx + q) << g.sx) + SA_HX];
-          const int cur = l[0];
-          int s = cc[0] * (l[l2] - cur) + cc[1] * (l[-1] - cur) + cc[2] * (l[1] - cur) + cc[3] * (l[l1 - 1] - cur) + cc[4] * (l[l1] - cur) +
-                  cc[5] * (l[l1 + 1] - cur) + cc[6] * (l[l3] - cur);
-          s = (s + 64) >> 7;
-          s = clip3(0, maxc, s + half) - half;
-          v = clip3(0, maxc, v + s);
-        }
-        res[q] = (pel)v;
+        int lim; bool nearVb;
+        vbLimit(y & (ctuH - 1), vbC, 2, lim, nearVb);
+        v = alfChromaQuad(cb, min(1, lim) * SA_P, min(2, lim) * SA_P, nearVb, C, maxcP);
       }
-      *reinterpret_cast<int2*>(dstC.p + (size_t)y * dstC.pitch + x) = *reinterpret_cast<const int2*>(res);
+      if (idc)
+      {
+        // CC-ALF row offsets in the luma tile (filterBlkCcAlf :1376-1386)
+        const int ly = (r << g.sy) + SA_HY, lpos = (y << g.sy) & ctuMask;
+        int l1 = SA_P, l2 = -SA_P, l3 = 2 * SA_P;
+        if (lpos == vbL - 2 || lpos == vbL + 1) l3 = SA_P;
+        else if (lpos == vbL - 1 || lpos == vbL) l1 = l2 = l3 = 0;
+        if (g.sx == 1)
+        {
+          const uint2 d = ccAlfQuad420(&lumaB[ly * SA_P + (qx << 1) + SA_HX], l1, l2, l3, cc, maxcP, halfP);
+          v.x = addClamp0(v.x, d.x, maxcP);
+          v.y = addClamp0(v.y, d.y, maxcP);
+        }
+        else
+        {
+          pel res[4] = { (pel)(v.x & 0xffff), (pel)(v.x >> 16), (pel)(v.y & 0xffff), (pel)(v.y >> 16) };
+#pragma unroll
+          for (int q = 0; q < 4; q++)
+          {
+            const pel* l = &lumaB[ly * SA_P + qx + q + SA_HX];
+            const int cur = l[0];
+            int s = cc[0] * (l[l2] - cur) + cc[1] * (l[-1] - cur) + cc[2] * (l[1] - cur) + cc[3] * (l[l1 - 1] - cur) + cc[4] * (l[l1] - cur) +
+                    cc[5] * (l[l1 + 1] - cur) + cc[6] * (l[l3] - cur);
+            s = (s + 64) >> 7;
+            s = clip3(0, maxc, s + half) - half;
+            res[q] = (pel)clip3(0, maxc, res[q] + s);
+          }
+          v = *reinterpret_cast<const uint2*>(res);
+        }
+      }
+      *reinterpret_cast<uint2*>(dstC.p + (size_t)y * dstC.pitch + x) = v;
     }
   }
 }

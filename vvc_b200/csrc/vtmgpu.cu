@@ -27,11 +27,40 @@ std::string g_createError;
 
 struct SideLayout     // byte offsets inside a slot's side-info block
 {
-  size_t dbfL[2], dbfC[2], sao, alfCtu, alfIdx, alf, total;
+  size_t dbfL[2], dbfC[2], sao, alfTab, alfCtu, alfIdx, alf, total;
   size_t nL, nC[2];
 };
 
 size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// tap order of the 7x7 diamond for transposeIdx 0..3 (AdaptiveLoopFilter.cpp:1170-1189)
+const int8_t kPerm7[4][12] = { { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11 }, { 9, 4, 10, 8, 1, 5, 11, 7, 3, 0, 2, 6 },
+                               { 0, 3, 2, 1, 8, 7, 6, 5, 4, 9, 10, 11 }, { 9, 8, 10, 4, 3, 7, 11, 5, 1, 0, 2, 6 } };
+
+// expands one luma filter set ({coeff, clip} per class and tap) into the per-(class, transpose) operand table of the packed
+// kernel; returns true when a coefficient does not fit the signed 8-bit operand of IDP.2A
+bool expandLumaSet(const short2 (*set)[12], AlfLumaEntry* out)
+{
+  bool wide = false;
+  for (int cl = 0; cl < 25; cl++)
+    for (int t = 0; t < 4; t++)
+    {
+      AlfLumaEntry& e = out[cl * 4 + t];
+      int bias = 64;
+      for (int k = 0; k < 12; k++)
+      {
+        const int co = set[cl][kPerm7[t][k]].x, clp = set[cl][kPerm7[t][k]].y;
+        wide |= co < -128 || co > 127;
+        e.coefB[k] = (uint32_t)(co & 0xff) * 0x01000001u;
+        e.clipP1[k] = (uint32_t)((clp + 1) & 0xffff) * 0x10001u;
+        e.clip2[k] = (uint32_t)((2 * clp) & 0xffff) * 0x10001u;
+        bias -= co * 2 * clp;
+      }
+      e.bias = bias;
+      e.pad[0] = e.pad[1] = e.pad[2] = 0;
+    }
+  return wide;
+}
 }   // namespace
 
 struct vtmgpu_ctx
@@ -152,6 +181,7 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
   for (int d = 0; d < 2; d++) { L.dbfL[d] = off; off = alignUp(off + L.nL * 4, 256); }
   for (int d = 0; d < 2; d++) { L.dbfC[d] = off; off = alignUp(off + L.nC[d] * 8, 256); }
   L.sao = off;    off = alignUp(off + (size_t)c->nCtus * 3 * sizeof(SaoDev), 256);
+  L.alfTab = off; off = alignUp(off + sizeof(AlfLumaEntry) * VTMGPU_MAX_LUMA_SETS * 25 * 4, 256);
   L.alfCtu = off; off = alignUp(off + (size_t)c->nCtus * 8, 256);
   L.alfIdx = off; off = alignUp(off + (size_t)c->nCtus * 2, 256);
   L.alf = off;    off = alignUp(off + sizeof(AlfDev), 256);
@@ -206,7 +236,24 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
     sd.alf = reinterpret_cast<const AlfDev*>(side + L.alf);
     sd.alfCtu = side + L.alfCtu;
     sd.alfFilterIdx = reinterpret_cast<const int16_t*>(side + L.alfIdx);
+    sd.lumaTab = reinterpret_cast<const AlfLumaEntry*>(side + L.alfTab);
     sd.dbfOn = sd.saoOn = sd.alfOn = 0;
+  }
+  {
+    // the 16 fixed luma filter sets (AdaptiveLoopFilter.cpp:204-289, clip = 1 << bitDepth :500-509) never change: expand and upload once
+    std::vector<short2> fixedSet(25 * 12);
+    for (int fs = 0; fs < VTMGPU_ALF_FIXED_SETS; fs++)
+    {
+      for (int cl = 0; cl < 25; cl++)
+        for (int k = 0; k < 12; k++) fixedSet[cl * 12 + k] = make_short2(vvc_alf_fix_coeff[vvc_alf_class_to_filt[fs * 25 + cl] * 12 + k], (short)(1 << g.bdL));
+      expandLumaSet(reinterpret_cast<const short2(*)[12]>(fixedSet.data()), reinterpret_cast<AlfLumaEntry*>(c->pinnedSide(0) + L.alfTab) + fs * 100);
+    }
+    const size_t fixedBytes = sizeof(AlfLumaEntry) * VTMGPU_ALF_FIXED_SETS * 100;
+    for (int sl = 0; sl < s.capacity; sl++)
+    {
+      if (sl) memcpy(c->pinnedSide(sl) + L.alfTab, c->pinnedSide(0) + L.alfTab, fixedBytes);
+      CK(cudaMemcpyAsync(c->sideDev[sl] + L.alfTab, c->pinnedSide(sl) + L.alfTab, fixedBytes, cudaMemcpyHostToDevice, c->stream), "fixed filter table upload");
+    }
   }
   CK(cudaMemcpyAsync(c->slotsDev, c->slotsPinned, sizeof(SlotDev) * s.capacity, cudaMemcpyHostToDevice, c->stream), "slot table upload");
   CK(cudaFuncSetAttribute(k_sao_alf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SaoAlfSmem)), "smem attribute");
@@ -435,6 +482,10 @@ extern "C" int vtmgpu_set_alf(vtmgpu_ctx* c, int slot, const vtmgpu_alf_params* 
         }
       }
     }
+    AlfLumaEntry* tab = reinterpret_cast<AlfLumaEntry*>(c->pinnedSide(slot) + c->lay.alfTab);
+    bool wide = false;
+    for (int s = 0; s < p->num_luma_aps; s++) wide |= expandLumaSet(A.luma[VTMGPU_ALF_FIXED_SETS + s], tab + (VTMGPU_ALF_FIXED_SETS + s) * 100);
+    A.wide = wide;
     int numAlts = 0;
     if (p->chroma_aps)
     {
@@ -484,6 +535,7 @@ extern "C" int vtmgpu_set_alf(vtmgpu_ctx* c, int slot, const vtmgpu_alf_params* 
       }
     }
     sd.alfOn = 1;
+    if (p->num_luma_aps && c->pushSide(slot, c->lay.alfTab + sizeof(AlfLumaEntry) * VTMGPU_ALF_FIXED_SETS * 100, sizeof(AlfLumaEntry) * 100 * p->num_luma_aps)) return -1;
     if (c->pushSide(slot, c->lay.alfCtu, c->lay.total - c->lay.alfCtu)) return -1;
   }
   return c->pushSlot(slot);

@@ -37,9 +37,22 @@ struct AlfDev
   int32_t enabled[3];
   int32_t ccEnabled[2];
   int32_t numSets;                                   // 16 fixed + APS sets
+  int32_t wide;                                      // a luma coefficient does not fit the s8 operand of IDP.2A: generic path
+  int32_t pad;
   short2  luma[VTMGPU_MAX_LUMA_SETS][25][12];        // {coeff, clip} per set, class, tap (transpose 0 order)
   short2  chroma[8][6];                              // {coeff, clip} per alternative, tap
   int16_t cc[2][4][8];                               // CC-ALF coefficients (7 used)
+};
+
+// One luma filter of a (filter set, class, transpose index), expanded on the host for the packed 7x7 kernel:
+// tap k (after the transpose permutation, AdaptiveLoopFilter.cpp:1170-1189) as the three register operands it needs.
+struct AlfLumaEntry
+{
+  uint32_t coefB[12];    // coefficient as s8 in byte 0 and byte 3 (IDP.2A.LO uses bytes 0-1, .HI bytes 2-3)
+  uint32_t clipP1[12];   // (clip + 1) in both 16-bit lanes
+  uint32_t clip2[12];    // (2 * clip) in both 16-bit lanes
+  int32_t  bias;         // 64 - sum(coef * 2 * clip)
+  int32_t  pad[3];
 };
 
 struct SlotDev
@@ -51,6 +64,7 @@ struct SlotDev
   const AlfDev*   alf;           //                               (NULL: stage off)
   const uint8_t*  alfCtu;        // [8][ctus]: enable Y,Cb,Cr, alt Cb,Cr, cc idc Cb,Cr, (unused)
   const int16_t*  alfFilterIdx;  // [ctus]
+  const AlfLumaEntry* lumaTab;   // [sets][25 classes][4 transposes]
   int32_t dbfOn, saoOn, alfOn;
 };
 
