@@ -41,19 +41,53 @@ constexpr int SA_CELLP = SA_CELLS + 2;      // cell row pitch (uint2 units)
 __constant__ int8_t c_perm7[4][12] = { { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11 }, { 9, 4, 10, 8, 1, 5, 11, 7, 3, 0, 2, 6 },
                                        { 0, 3, 2, 1, 8, 7, 6, 5, 4, 9, 10, 11 }, { 9, 8, 10, 4, 3, 7, 11, 5, 1, 0, 2, 6 } };
 
-struct SaoAlfSmem
+// Shared memory of one CTA (dynamic; offsets in bytes).  Input tiles are double buffered: while a CTA filters tile i the
+// cp.async copies of tile i+1 are in flight.
+//   A[stage][comp]  input tile + halo (deblocked samples, replicate padded at the picture border)
+//   B[comp]         SAO output of the tile + 3 (stays resident: ALF input, CC-ALF luma source)
+//   cell            Laplacian sums of the 2x2 cells: .x = V | H << 16, .y = D0 | D1 << 16
+//   par[stage]      SAO parameters of the 3x3 CTU neighbourhood per component + the ALF control record of the CTU
+struct SaoGeom
 {
-  pel      a[SA_H * SA_P];                  // input tile of the current component
-  pel      bl[SA_H * SA_P];                 // SAO output, luma (stays resident for CC-ALF)
-  union
-  {
-    uint2    cell[SA_CELLS][SA_CELLP];      // Laplacian sums of one 2x2 cell: .x = V | H << 16, .y = D0 | D1 << 16
-    pel      bc[SA_H * SA_P];               // SAO output, chroma component
-  } u;
-  SaoDev   sao[3][9];                       // 3x3 CTU neighbourhood per component
-  short2   chromaSet[2][6];
-  int16_t  cc[2][8];
+  int bx0, by0;          // plane coordinates of smem position (0,0)
+  int w, h;              // plane size
+  int cwLog, chLog;      // log2 CTU size in this plane
+  int tcx, tcy;          // CTU of the tile
+  int bd;
+  int pitch;             // smem pitch (samples)
+  int tw, thLog;         // tile size of this component (th = 1 << thLog)
 };
+
+struct SaTilePar
+{
+  SaoDev    sao[3][9];
+  SaoGeom   geom[3];
+  AlfCtuDev ctl;
+  int32_t   pad[2];
+};
+
+struct SaLayout
+{
+  int pitchC, rowsC;               // chroma tile buffers: pitch in samples, rows
+  int lumaBytes, chromaBytes, offCell, offPar, total;
+  __host__ __device__ int comp(int c) const { return c ? lumaBytes + (c - 1) * chromaBytes : 0; }
+  __host__ __device__ int offA(int stage, int c) const { return stage * (lumaBytes + 2 * chromaBytes) + comp(c); }
+  __host__ __device__ int offB(int c) const { return 2 * (lumaBytes + 2 * chromaBytes) + comp(c); }
+};
+
+__host__ __device__ inline SaLayout saLayout(int sx, int sy, int ncomp)
+{
+  SaLayout L;
+  const int tw = SA_T >> sx, th = SA_T >> sy;
+  L.pitchC = tw + 2 * SA_HX + 8;
+  L.rowsC = th + 2 * SA_HY;
+  L.lumaBytes = SA_H * SA_P * 2;
+  L.chromaBytes = ncomp > 1 ? L.rowsC * L.pitchC * 2 : 0;
+  L.offCell = 3 * (L.lumaBytes + 2 * L.chromaBytes);
+  L.offPar = L.offCell + SA_CELLS * SA_CELLP * 8;
+  L.total = L.offPar + 2 * (int)sizeof(SaTilePar);
+  return L;
+}
 
 // ---- packed 16x2 helpers ----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
@@ -68,46 +102,55 @@ __device__ __forceinline__ uint32_t mid16(uint32_t lo, uint32_t hi) { return __f
 // max(min(a + b, c), 0) per signed 16-bit lane
 __device__ __forceinline__ uint32_t addClamp0(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_s16x2_relu(a, b, c); }
 
-// loads rows y0-SA_HY .. , columns x0-SA_HX .. of a plane into s (tile w x h samples + halo), replicate border
-__device__ __forceinline__ void saLoadTile(pel* s, const PlaneDev& pl, int x0, int y0, int tw, int th)
+// ---- asynchronous tile load ---------------------------------------------------------------------------------
+__device__ __forceinline__ void cpAsync16(void* smem, const void* gmem)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cpAsync8(void* smem, const void* gmem)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// copies rows y0-SA_HY .. y0+th+SA_HY-1, columns x0-SA_HX .. x0+tw+SA_HX-1 of a plane into s (pitch in samples) with
+// cp.async (no register staging); rows are clamped to the picture (= replicate border), groups that leave the picture
+// on the left / right are filled synchronously with the edge sample (picture-border tiles only).
+// rcpGroups = ceil(65536 / groups): i / groups == (i * rcpGroups) >> 16 for i < 4096.
+__device__ __forceinline__ void saLoadTileAsync(pel* s, int pitch, const PlaneDev& pl, int x0, int y0, int tw, int th)
 {
   const int groups = (tw + 2 * SA_HX) >> 3, rows = th + 2 * SA_HY;
+  const int rcpGroups = (65536 + groups - 1) / groups;
   for (int i = threadIdx.x; i < groups * rows; i += SA_THREADS)
   {
-    const int r = i / groups, gc = i - r * groups;
+    const int r = (i * rcpGroups) >> 16, gc = i - r * groups;
     const int y = min(max(y0 - SA_HY + r, 0), pl.h - 1), x = x0 - SA_HX + gc * 8;
     const pel* row = pl.p + (size_t)y * pl.pitch;
-    int4 v;
-    if (x >= 0 && x < pl.w)
+    pel* d = &s[r * pitch + gc * 8];
+    if (x >= 0 && x + 8 <= pl.w) cpAsync16(d, row + x);
+    else
     {
-      v = __ldg(reinterpret_cast<const int4*>(row + x));
-      if (x + 8 > pl.w)
+      int4 v;
+      if (x >= 0 && x < pl.w)
       {
         // the picture ends inside this group (plane widths are multiples of 4): replicate the last column
+        v = __ldg(reinterpret_cast<const int4*>(row + x));
         const int e = (int)__byte_perm((uint32_t)v.y, 0u, 0x3232);
         v.z = e; v.w = e;
       }
+      else
+      {
+        const uint32_t e = (uint16_t)row[x < 0 ? 0 : pl.w - 1];
+        const int ee = (int)(e | (e << 16));
+        v = make_int4(ee, ee, ee, ee);
+      }
+      *reinterpret_cast<int4*>(d) = v;
     }
-    else
-    {
-      const uint32_t e = (uint16_t)row[x < 0 ? 0 : pl.w - 1];
-      const int ee = (int)(e | (e << 16));
-      v = make_int4(ee, ee, ee, ee);
-    }
-    *reinterpret_cast<int4*>(&s[r * SA_P + gc * 8]) = v;
   }
 }
 
 // ---- SAO ----------------------------------------------------------------------------------------------------
-struct SaoGeom
-{
-  int bx0, by0;          // plane coordinates of smem position (0,0)
-  int w, h;              // plane size
-  int cwLog, chLog;      // log2 CTU size in this plane
-  int tcx, tcy;          // CTU of the tile
-  int bd;
-};
-
 __device__ __forceinline__ bool saoCtuAvail(uint32_t avail, int rx, int ry)
 {
   if ((rx | ry) == 0) return true;
@@ -118,29 +161,27 @@ __device__ __forceinline__ bool saoCtuAvail(uint32_t avail, int rx, int ry)
 // lanes of the 8-sample group at (x,y) that edge-offset class (dxa,dya) must leave untouched: a neighbour outside the
 // picture or in a CTU that is not available (offsetBlock start/end and first/last line rules, SampleAdaptiveOffset.cpp
 // :311-312,:340-341,:398-399,:444-445,:476-477,:514-515 with deriveLoopFilterBoundaryAvailibility :668)
-__device__ __forceinline__ uint32_t saoSkipLanes(int x, int y, int dxa, int dya, uint32_t avail, const SaoGeom& g)
+__device__ __noinline__ uint32_t saoSkipLanesSlow(int x, int y, int dxa, int dya, uint32_t avail, int w, int h, int cwLog, int chLog)
 {
-  const int cwm = (1 << g.cwLog) - 1, chm = (1 << g.chLog) - 1;
-  if ((y & chm) != 0 && ((y + 1) & chm) != 0 && y + 1 < g.h && (x & cwm) != 0 && ((x + 8) & cwm) != 0 && x + 8 < g.w) return 0;
-  const int cx = x >> g.cwLog, cy = y >> g.chLog, last = min(7, g.w - 1 - x);
+  const int cx = x >> cwLog, cy = y >> chLog, last = min(7, w - 1 - x);
   uint32_t m = 0;
 #pragma unroll
   for (int k = 0; k < 2; k++)
   {
     const int ddx = k ? -dxa : dxa, ddy = k ? -dya : dya;
     const int ny = y + ddy;
-    if (ny < 0 || ny >= g.h) { m = 0xff; continue; }
-    const int ry = (ny >> g.chLog) - cy;
+    if (ny < 0 || ny >= h) { m = 0xff; continue; }
+    const int ry = (ny >> chLog) - cy;
     uint32_t mm = saoCtuAvail(avail, 0, ry) ? 0u : 0xffu;
     if (ddx < 0)
     {
-      const bool av = x > 0 && saoCtuAvail(avail, ((x - 1) >> g.cwLog) - cx, ry);
+      const bool av = x > 0 && saoCtuAvail(avail, ((x - 1) >> cwLog) - cx, ry);
       mm = (mm & ~1u) | (av ? 0u : 1u);
     }
     if (ddx > 0)
     {
       const int nx = x + last + 1;
-      const bool av = nx < g.w && saoCtuAvail(avail, (nx >> g.cwLog) - cx, ry);
+      const bool av = nx < w && saoCtuAvail(avail, (nx >> cwLog) - cx, ry);
       mm = (mm & ~(1u << last)) | (av ? 0u : (1u << last));
     }
     m |= mm;
@@ -148,7 +189,14 @@ __device__ __forceinline__ uint32_t saoSkipLanes(int x, int y, int dxa, int dya,
   return m;
 }
 
-// the 8 samples at offset (DX, DY) from the group at ap, as 4 packed registers
+__device__ __forceinline__ uint32_t saoSkipLanes(int x, int y, int dxa, int dya, uint32_t avail, const SaoGeom& g)
+{
+  const int cwm = (1 << g.cwLog) - 1, chm = (1 << g.chLog) - 1;
+  if ((y & chm) != 0 && ((y + 1) & chm) != 0 && y + 1 < g.h && (x & cwm) != 0 && ((x + 8) & cwm) != 0 && x + 8 < g.w) return 0;
+  return saoSkipLanesSlow(x, y, dxa, dya, avail, g.w, g.h, g.cwLog, g.chLog);
+}
+
+// the 8 samples at horizontal offset DX from the group at base, as 4 packed registers
 template <int DX> __device__ __forceinline__ uint4 saoNeighbours(const pel* base)
 {
   const uint4 q = *reinterpret_cast<const uint4*>(base);
@@ -169,9 +217,9 @@ __device__ __forceinline__ uint32_t saoLut(uint32_t k, uint32_t lutLo, uint32_t 
   return prmt(lutLo, lutHi, prmt(sel, 0u, 0x4420u));
 }
 
-template <int DXA, int DYA> __device__ __forceinline__ uint4 saoEdge(const pel* ap, uint4 v, uint32_t lutLo, uint32_t lutHi, uint32_t maxvP)
+template <int DXA, int DYA> __device__ __forceinline__ uint4 saoEdge(const pel* ap, int pitch, uint4 v, uint32_t lutLo, uint32_t lutHi, uint32_t maxvP)
 {
-  const uint4 na = saoNeighbours<DXA>(ap + DYA * SA_P), nb = saoNeighbours<-DXA>(ap - DYA * SA_P);
+  const uint4 na = saoNeighbours<DXA>(ap + DYA * pitch), nb = saoNeighbours<-DXA>(ap - DYA * pitch);
   const uint32_t vv[4] = { v.x, v.y, v.z, v.w }, aa[4] = { na.x, na.y, na.z, na.w }, bb[4] = { nb.x, nb.y, nb.z, nb.w };
   uint32_t o[4];
 #pragma unroll
@@ -190,17 +238,18 @@ __device__ __forceinline__ uint32_t laneMask2(uint32_t bits) { return ((bits & 1
 __device__ __forceinline__ void saoGroup(pel* b, const pel* a, int r, int gcol, const SaoDev* nb, const SaoGeom& g)
 {
   const int x = g.bx0 + 8 * gcol, y = g.by0 + r;
-  const pel* ap = a + r * SA_P + 8 * gcol;
+  const pel* ap = a + r * g.pitch + 8 * gcol;
   uint4 v = *reinterpret_cast<const uint4*>(ap);
   const SaoDev& P = nb[((y >> g.chLog) - g.tcy + 1) * 3 + (x >> g.cwLog) - g.tcx + 1];
   const int type = P.type;
   if (type != 0)
   {
     const uint32_t maxvP = dup16((1 << g.bd) - 1);
+    const uint4 pq = *reinterpret_cast<const uint4*>(&P);                         // .y = off0 | off1 << 16, .z = off2 | off3 << 16, .w = off4
     if (type == 5)
     {
       // band offset: k = (band - first band) & 31 ; bands k = 0..3 carry an offset (:528-541)
-      const uint32_t lutLo = (P.off[0] & 0xff) | (P.off[1] & 0xff) << 8 | (P.off[2] & 0xff) << 16 | (uint32_t)(P.off[3] & 0xff) << 24;
+      const uint32_t lutLo = prmt(pq.y, pq.z, 0x6420u);
       const uint32_t nstart = dup16(-(int)P.band);
       const int sh = g.bd - 5;
       uint32_t vv[4] = { v.x, v.y, v.z, v.w };
@@ -215,15 +264,15 @@ __device__ __forceinline__ void saoGroup(pel* b, const pel* a, int r, int gcol, 
     }
     else
     {
-      // edge offset: index k = 2 - edgeType  ->  look-up table holds the offsets in reverse order
-      const uint32_t lutLo = (P.off[4] & 0xff) | (P.off[3] & 0xff) << 8 | (P.off[2] & 0xff) << 16 | (uint32_t)(P.off[1] & 0xff) << 24;
-      const uint32_t lutHi = P.off[0] & 0xff;
+      // edge offset: index k = 2 - edgeType  ->  look-up table holds the offsets in reverse order: off[4], off[3], off[2], off[1] | off[0]
+      const uint32_t lutLo = (prmt(pq.y, pq.z, 0x2460u) & 0xffffff00u) | (pq.w & 0xffu);
+      const uint32_t lutHi = pq.y & 0xffu;
       uint4 o;
       int dxa, dya;
-      if (type == 1)      { o = saoEdge<-1, 0>(ap, v, lutLo, lutHi, maxvP);  dxa = -1; dya = 0; }
-      else if (type == 2) { o = saoEdge<0, -1>(ap, v, lutLo, lutHi, maxvP);  dxa = 0;  dya = -1; }
-      else if (type == 3) { o = saoEdge<-1, -1>(ap, v, lutLo, lutHi, maxvP); dxa = -1; dya = -1; }
-      else                { o = saoEdge<1, -1>(ap, v, lutLo, lutHi, maxvP);  dxa = 1;  dya = -1; }
+      if (type == 1)      { o = saoEdge<-1, 0>(ap, g.pitch, v, lutLo, lutHi, maxvP);  dxa = -1; dya = 0; }
+      else if (type == 2) { o = saoEdge<0, -1>(ap, g.pitch, v, lutLo, lutHi, maxvP);  dxa = 0;  dya = -1; }
+      else if (type == 3) { o = saoEdge<-1, -1>(ap, g.pitch, v, lutLo, lutHi, maxvP); dxa = -1; dya = -1; }
+      else                { o = saoEdge<1, -1>(ap, g.pitch, v, lutLo, lutHi, maxvP);  dxa = 1;  dya = -1; }
       const uint32_t skip = saoSkipLanes(x, y, dxa, dya, P.avail, g);
       if (skip)
       {
@@ -233,58 +282,62 @@ __device__ __forceinline__ void saoGroup(pel* b, const pel* a, int r, int gcol, 
       v = o;
     }
   }
-  *reinterpret_cast<uint4*>(b + r * SA_P + 8 * gcol) = v;
+  *reinterpret_cast<uint4*>(b + r * g.pitch + 8 * gcol) = v;
 }
 
-// SAO of a tile of tw x th samples (+ `halo` samples around it: 3 when an ALF stage reads the result, else 0) from smem
-// tile a into smem tile b.  Work items are 8-sample groups; the interior (one CTU => one parameter set => no
-// divergence) is issued first, then the halo strips.  Positions outside the picture are filled afterwards with the
-// value of the clamped position (= UnitBuf::extendBorderPel of the SAO output, AdaptiveLoopFilter.cpp:411).
-__device__ __forceinline__ void saSaoTile(pel* b, const pel* a, int tw, int th, bool halo, const SaoDev* nb, const SaoGeom& g)
+// Work items of the SAO phase of one component: 8-sample groups.  Item classes (all sizes are powers of two or padded
+// to 16 so that the decode needs no division):
+//   interior   th x gin groups, column-major (keeps 128-bit smem accesses conflict free); one CTU => one parameter set
+//   sides      the halo group left and right of every tile row            (only when an ALF stage reads the halo)
+//   top/bottom 3 halo rows above and below, 16 group slots per row        (                "                   )
+__device__ __forceinline__ int saoItemsInterior(const SaoGeom& g) { return (g.tw >> 3) << g.thLog; }
+__device__ __forceinline__ int saoItemsHalo(const SaoGeom& g) { return (2 << g.thLog) + 6 * 16; }
+
+__device__ __forceinline__ bool saoItemInterior(int i, const SaoGeom& g, int& r, int& gc)
 {
-  const int tid = threadIdx.x;
-  const int gin = tw >> 3;                                   // interior groups per row
-  // interior: rows SA_HY .. SA_HY+th-1, groups 1 .. gin ; column-major item order keeps 128-bit smem accesses conflict free
-  for (int i = tid; i < gin * th; i += SA_THREADS)
+  gc = 1 + (i >> g.thLog);
+  r = SA_HY + (i & ((1 << g.thLog) - 1));
+  return g.by0 + r < g.h && g.bx0 + 8 * gc < g.w;
+}
+
+__device__ __forceinline__ bool saoItemHalo(int i, const SaoGeom& g, int& r, int& gc)
+{
+  const int th = 1 << g.thLog, gin = g.tw >> 3;
+  if (i < 2 * th) { gc = i < th ? 0 : gin + 1; r = SA_HY + (i & (th - 1)); }
+  else
   {
-    const int gc = 1 + i / th, r = SA_HY + (i - (gc - 1) * th);
-    if (g.by0 + r < g.h && g.bx0 + 8 * gc < g.w) saoGroup(b, a, r, gc, nb, g);
+    const int j = i - 2 * th, k = j >> 4;
+    gc = j & 15;
+    r = k < 3 ? SA_HY - 3 + k : SA_HY + th + (k - 3);
+    if (gc > gin + 1) return false;
   }
-  if (halo)
-  {
-    // left / right halo columns (rows of the tile), then top / bottom 3 rows over all groups
-    const int nside = 2 * th, ntb = 6 * (gin + 2);
-    for (int i = tid; i < nside + ntb; i += SA_THREADS)
+  const int y = g.by0 + r, x = g.bx0 + 8 * gc;
+  return y >= 0 && y < g.h && x >= 0 && x < g.w;
+}
+
+// true when the tile + 3 region of this component leaves the picture (the SAO output then needs its replicate border)
+__device__ __forceinline__ bool saoNeedsBorder(const SaoGeom& g)
+{
+  const int th = 1 << g.thLog;
+  return g.bx0 + SA_HX - 3 < 0 || g.by0 + SA_HY - 3 < 0 || g.bx0 + SA_HX + g.tw + 2 >= g.w || g.by0 + SA_HY + th + 2 >= g.h;
+}
+
+// positions of tile + 3 outside the picture take the value of the clamped position (= UnitBuf::extendBorderPel of the SAO
+// output, AdaptiveLoopFilter.cpp:411)
+__device__ __noinline__ void saoBorder(pel* b, int bx0, int by0, int w, int h, int pitch, int tw, int th)
+{
+  const int xl = bx0 + SA_HX - 3, yt = by0 + SA_HY - 3;
+  const int cols = tw + 6, rows = th + 6;
+  for (int rr = threadIdx.x >> 5; rr < rows; rr += SA_THREADS / 32)
+    for (int cc = threadIdx.x & 31; cc < cols; cc += 32)
     {
-      int r, gc;
-      if (i < nside) { gc = i < th ? 0 : gin + 1; r = SA_HY + (i < th ? i : i - th); }
-      else
+      const int px = xl + cc, py = yt + rr;
+      if (px < 0 || py < 0 || px >= w || py >= h)
       {
-        const int j = i - nside, k = j / (gin + 2);
-        gc = j - k * (gin + 2);
-        r = k < 3 ? SA_HY - 3 + k : SA_HY + th + (k - 3);
-      }
-      const int y = g.by0 + r, x = g.bx0 + 8 * gc;
-      if (y >= 0 && y < g.h && x >= 0 && x < g.w) saoGroup(b, a, r, gc, nb, g);
-    }
-    // replicate border of the SAO output for tiles on the picture border
-    const int xl = g.bx0 + SA_HX - 3, xr = g.bx0 + SA_HX + tw + 2, yt = g.by0 + SA_HY - 3, yb = g.by0 + SA_HY + th + 2;
-    if (xl < 0 || yt < 0 || xr >= g.w || yb >= g.h)
-    {
-      __syncthreads();
-      const int cols = tw + 6, rows = th + 6;
-      for (int i = tid; i < cols * rows; i += SA_THREADS)
-      {
-        const int rr = i / cols, cc = i - rr * cols;
-        const int px = xl + cc, py = yt + rr;
-        if (px < 0 || py < 0 || px >= g.w || py >= g.h)
-        {
-          const int sx_ = min(max(px, 0), g.w - 1), sy_ = min(max(py, 0), g.h - 1);
-          b[(py - g.by0) * SA_P + px - g.bx0] = b[(sy_ - g.by0) * SA_P + sx_ - g.bx0];
-        }
+        const int sx_ = min(max(px, 0), w - 1), sy_ = min(max(py, 0), h - 1);
+        b[(py - by0) * pitch + px - bx0] = b[(sy_ - by0) * pitch + sx_ - bx0];
       }
     }
-  }
 }
 
 // ---- ALF: generic scalar routines (virtual-boundary rows, halo cells, wide coefficients, non-4:2:0 CC-ALF) ----------
@@ -303,7 +356,7 @@ __device__ __forceinline__ void vbLimit(int yv, int vbPos, int span, int& lim, b
 
 // Laplacian sums of the 2x2 cell whose top-left sample is p0 (picture row r): positions (r,c) and (r+1,c+1);
 // rows beyond the virtual boundary are replaced (deriveClassificationBlk :906-915)
-__device__ __forceinline__ uint2 alfCellGeneric(const pel* p0, int r, int ctuMask, int vbL)
+__device__ __noinline__ uint2 alfCellGeneric(const pel* p0, int r, int ctuMask, int vbL)
 {
   int up = -SA_P, dn2 = 2 * SA_P;                                             // row r-1, row r+2
   const int rv = r & ctuMask;
@@ -335,9 +388,11 @@ __device__ __forceinline__ void alfClassify(int sumV, int sumH, int sumD0, int s
   tIdx = (0x31322010 >> (4 * (mainDir * 2 + (secDir >> 1)))) & 0xf;              // transposeTable = {0,1,0,2,2,3,1,3}
 }
 
+typedef uint2 (*CellRows)[SA_CELLP];
+
 // one 4x4 luma block, any row position: classification incl. the virtual-boundary rules and the 7x7 filter with row clamping
-__device__ void alfLumaBlockGeneric(const SaoAlfSmem& sm, const pel* c0, pel* out, int pitchOut, int bi, int bj, int by, const short2* set,
-                                    int ctuMask, int vbL, int bd)
+__device__ __noinline__ void alfLumaBlockGeneric(const uint2 (*cell)[SA_CELLP], const pel* c0, pel* out, int pitchOut, int bi, int bj, int by,
+                                                 const short2* set, int ctuMask, int vbL, int bd)
 {
   const int yb = by & ctuMask;
   const int i0 = (yb == vbL) ? 1 : 0, i1 = (yb == vbL - 4) ? 3 : 4;
@@ -346,7 +401,7 @@ __device__ void alfLumaBlockGeneric(const SaoAlfSmem& sm, const pel* c0, pel* ou
 #pragma unroll
     for (int j = 0; j < 4; j++)
     {
-      const uint2 c = sm.u.cell[2 * bi + i][2 * bj + j];
+      const uint2 c = cell[2 * bi + i][2 * bj + j];
       sum[0] += c.x & 0xffff; sum[1] += c.x >> 16; sum[2] += c.y & 0xffff; sum[3] += c.y >> 16;
     }
   int cls, tIdx;
@@ -360,7 +415,7 @@ __device__ void alfLumaBlockGeneric(const SaoAlfSmem& sm, const pel* c0, pel* ou
     int lim; bool nearVb;
     vbLimit((by + r) & ctuMask, vbL, 4, lim, nearVb);
     const int o1 = min(1, lim) * SA_P, o2 = min(2, lim) * SA_P, o3 = lim * SA_P;   // lim <= 3
-    pel res[4];
+    int res[4];
 #pragma unroll
     for (int q = 0; q < 4; q++)
     {
@@ -370,15 +425,15 @@ __device__ void alfLumaBlockGeneric(const SaoAlfSmem& sm, const pel* c0, pel* ou
               alfTap(c, o1 + 2, cur, f[4]) + alfTap(c, o1 + 1, cur, f[5]) + alfTap(c, o1, cur, f[6]) + alfTap(c, o1 - 1, cur, f[7]) +
               alfTap(c, o1 - 2, cur, f[8]) + alfTap(c, 3, cur, f[9]) + alfTap(c, 2, cur, f[10]) + alfTap(c, 1, cur, f[11]);
       s = (s + 64) >> (nearVb ? 10 : 7);
-      res[q] = (pel)clip3(0, maxv, cur + s);
+      res[q] = clip3(0, maxv, cur + s);
     }
-    *reinterpret_cast<int2*>(out + (size_t)r * pitchOut) = *reinterpret_cast<const int2*>(res);
+    *reinterpret_cast<uint2*>(out + (size_t)r * pitchOut) = make_uint2((uint32_t)res[0] | (uint32_t)res[1] << 16, (uint32_t)res[2] | (uint32_t)res[3] << 16);
   }
 }
 
 // ---- ALF luma: packed fast path (block rows that do not touch a virtual boundary) -------------------------------------
 // Laplacian cells of the block's own 4x4 samples (2x2 cells) from the 6x6 sample patch around it
-__device__ __forceinline__ void alfOwnCells(SaoAlfSmem& sm, const pel* c0, int bi, int bj)
+__device__ __forceinline__ void alfOwnCells(uint2 (*cell)[SA_CELLP], const pel* c0, int bi, int bj)
 {
   int p[6][6];                                               // p[r][c] = sample (r-1, c-1) relative to the block
 #pragma unroll
@@ -400,7 +455,7 @@ __device__ __forceinline__ void alfOwnCells(SaoAlfSmem& sm, const pel* c0, int b
       const int h = iabs(a2 - p[r][c - 1] - p[r][c + 1]) + iabs(b2 - p[r + 1][c] - p[r + 1][c + 2]);
       const int d0 = iabs(a2 - p[r - 1][c - 1] - p[r + 1][c + 1]) + iabs(b2 - p[r][c] - p[r + 2][c + 2]);
       const int d1 = iabs(a2 - p[r + 1][c - 1] - p[r - 1][c + 1]) + iabs(b2 - p[r + 2][c] - p[r][c + 2]);
-      sm.u.cell[2 * bi + 1 + cy][2 * bj + 1 + cx] = make_uint2((uint32_t)v | (uint32_t)h << 16, (uint32_t)d0 | (uint32_t)d1 << 16);
+      cell[2 * bi + 1 + cy][2 * bj + 1 + cx] = make_uint2((uint32_t)v | (uint32_t)h << 16, (uint32_t)d0 | (uint32_t)d1 << 16);
     }
 }
 
@@ -470,14 +525,15 @@ struct ChromaCoef
   int bias;
 };
 
-__device__ __forceinline__ ChromaCoef chromaCoef(const short2* f)
+__device__ __forceinline__ ChromaCoef chromaCoef(const short2* __restrict__ f)
 {
   ChromaCoef c;
   int b = 64;
 #pragma unroll
   for (int k = 0; k < 6; k++)
   {
-    const int co = f[k].x, cl = f[k].y;
+    const short2 e = __ldg(&f[k]);
+    const int co = e.x, cl = e.y;
     c.coefB[k] = (uint32_t)(co & 0xff) * 0x01000001u;
     c.clipP1[k] = dup16(cl + 1);
     c.clip2[k] = dup16(2 * cl);
@@ -494,16 +550,16 @@ __device__ __forceinline__ uint2 alfChromaQuad(const pel* cb, int o1, int o2, bo
   uint32_t res[2];
   const uint2 c0q = *reinterpret_cast<const uint2*>(cb - 4), c0r = *reinterpret_cast<const uint2*>(cb);
   const uint32_t c0w4 = *reinterpret_cast<const uint32_t*>(cb + 4);
-  const uint32_t r0[5] = { c0q.y, c0r.x, c0r.y, c0w4, 0 };                                   // centre row: wm2, w0, w2, w4
+  const uint32_t r0[4] = { c0q.y, c0r.x, c0r.y, c0w4 };                                     // centre row: wm2, w0, w2, w4
   const uint32_t r0o[3] = { mid16(r0[0], r0[1]), mid16(r0[1], r0[2]), mid16(r0[2], r0[3]) };    // pairs starting at -1, 1, 3
-  uint32_t pe[2][3], po[2][3];                                                              // rows +o1 / -o1: even words wm2.., odd pairs
+  uint32_t pe[2][2], po[2][3];                                                              // rows +o1 / -o1: even words w0,w2 ; odd pairs
 #pragma unroll
   for (int s = 0; s < 2; s++)
   {
     const pel* rp = cb + (s ? -o1 : o1);
     const uint2 q = *reinterpret_cast<const uint2*>(rp - 4), r = *reinterpret_cast<const uint2*>(rp);
     const uint32_t w4 = *reinterpret_cast<const uint32_t*>(rp + 4);
-    pe[s][0] = r.x; pe[s][1] = r.y; pe[s][2] = 0;
+    pe[s][0] = r.x; pe[s][1] = r.y;
     po[s][0] = mid16(q.y, r.x); po[s][1] = mid16(r.x, r.y); po[s][2] = mid16(r.y, w4);
   }
   const uint2 p2 = *reinterpret_cast<const uint2*>(cb + o2), m2 = *reinterpret_cast<const uint2*>(cb - o2);
@@ -536,16 +592,16 @@ __device__ __forceinline__ uint2 alfChromaQuad(const pel* cb, int o1, int o2, bo
 // CC-ALF correction for 4 chroma samples in 4:2:0 / 4:2:2 (sx = 1): collocated luma column = 2 * chroma column.
 // l = luma sample collocated with the first chroma sample (smem, SAO output); l1,l2,l3 = row offsets (filterBlkCcAlf
 // :1376-1386).  Returns the packed corrections (already clipped to the chroma range around 0).
-__device__ __forceinline__ uint2 ccAlfQuad420(const pel* l, int l1, int l2, int l3, const int cc[7], uint32_t maxcP, uint32_t halfP)
+__device__ __forceinline__ uint2 ccAlfQuad420(const pel* l, int l1, int l2, int l3, const int16_t* __restrict__ ccg, uint32_t maxcP, uint32_t halfP)
 {
   // luma words of a row relative to l: W(-2), W(0), W(2), W(4), W(6)
-  uint32_t ctr[2], up[2], lf[2][2], rt[2][2], dl[2], dm[2], dr[2], d2[2];
+  uint32_t ctr[2], up[2], lf[2], rt[2], dl[2], dm[2], dr[2], d2[2];
   {
     const uint2 q = *reinterpret_cast<const uint2*>(l - 4), r = *reinterpret_cast<const uint2*>(l), t = *reinterpret_cast<const uint2*>(l + 4);
     // even samples (0,2),(4,6) ; odd samples (-1,1),(3,5) and (1,3),(5,7)
     ctr[0] = prmt(r.x, r.y, 0x5410u); ctr[1] = prmt(t.x, t.y, 0x5410u);
-    lf[0][0] = prmt(q.y, r.x, 0x7632u); lf[0][1] = prmt(r.y, t.x, 0x7632u);
-    rt[0][0] = prmt(r.x, r.y, 0x7632u); rt[0][1] = prmt(t.x, t.y, 0x7632u);
+    lf[0] = prmt(q.y, r.x, 0x7632u); lf[1] = prmt(r.y, t.x, 0x7632u);
+    rt[0] = prmt(r.x, r.y, 0x7632u); rt[1] = prmt(t.x, t.y, 0x7632u);
   }
   {
     const uint2 r = *reinterpret_cast<const uint2*>(l + l2), t = *reinterpret_cast<const uint2*>(l + l2 + 4);
@@ -564,14 +620,14 @@ __device__ __forceinline__ uint2 ccAlfQuad420(const pel* l, int l1, int l2, int 
   uint32_t cB[7];
   int fsum = 0;
 #pragma unroll
-  for (int k = 0; k < 7; k++) { cB[k] = (uint32_t)(cc[k] & 0xff) * 0x01000001u; fsum += cc[k]; }
+  for (int k = 0; k < 7; k++) { const int c = __ldg(&ccg[k]); cB[k] = (uint32_t)(c & 0xff) * 0x01000001u; fsum += c; }
   uint32_t res[2];
 #pragma unroll
   for (int px = 0; px < 2; px++)
   {
     int a0 = 64 - (int)(ctr[px] & 0xffff) * fsum, a1 = 64 - (int)(ctr[px] >> 16) * fsum;
 #define CC_TAP(K, N) a0 = __dp2a_lo((int)(N), (int)cB[K], a0); a1 = __dp2a_hi((int)(N), (int)cB[K], a1);
-    CC_TAP(0, up[px]) CC_TAP(1, lf[0][px]) CC_TAP(2, rt[0][px]) CC_TAP(3, dl[px]) CC_TAP(4, dm[px]) CC_TAP(5, dr[px]) CC_TAP(6, d2[px])
+    CC_TAP(0, up[px]) CC_TAP(1, lf[px]) CC_TAP(2, rt[px]) CC_TAP(3, dl[px]) CC_TAP(4, dm[px]) CC_TAP(5, dr[px]) CC_TAP(6, d2[px])
 #undef CC_TAP
     const uint32_t t = addClamp0(prmt((uint32_t)(a0 >> 7), (uint32_t)(a1 >> 7), 0x5410u), halfP, maxcP);     // ClipPel(sum + half)
     res[px] = __vadd2(t, ~halfP + 0x00010001u);                                                                // - half
@@ -579,201 +635,277 @@ __device__ __forceinline__ uint2 ccAlfQuad420(const pel* l, int l1, int l2, int 
   return make_uint2(res[0], res[1]);
 }
 
-__global__ void __launch_bounds__(SA_THREADS, 2) k_sao_alf(const SlotDev* __restrict__ slots, int firstSlot, int srcBuf, int dstBuf, Geom g, int tilesX,
-                                                           int doSao, int doAlf)
+// ---- the kernel ---------------------------------------------------------------------------------------------------
+struct SaTile
 {
-  extern __shared__ __align__(16) unsigned char smraw[];
-  SaoAlfSmem& sm = *reinterpret_cast<SaoAlfSmem*>(smraw);
-  const SlotDev& S = slots[firstSlot + blockIdx.y];
-  const int tid = threadIdx.x;
-  const int x0 = (blockIdx.x % tilesX) * SA_T, y0 = (blockIdx.x / tilesX) * SA_T;
-  const int tcx = x0 >> g.ctuLog2, tcy = y0 >> g.ctuLog2, ctuIdx = tcy * g.wCtus + tcx;
-  const int nCtus = g.wCtus * g.hCtus;
-  const bool saoOn = doSao && S.saoOn, alfPic = doAlf && S.alfOn && (S.alf->enabled[0] | S.alf->enabled[1] | S.alf->enabled[2]);
+  int slot, x0, y0;      // luma origin
+};
 
-  // ---- per-tile parameters ------------------------------------------------------------------------------
+__device__ __forceinline__ SaTile saDecodeTile(int t, int tilesX, int tilesPerPic)
+{
+  SaTile T;
+  T.slot = t / tilesPerPic;
+  const int rem = t - T.slot * tilesPerPic, ty = rem / tilesX;
+  T.x0 = (rem - ty * tilesX) * SA_T;
+  T.y0 = ty * SA_T;
+  return T;
+}
+
+// issues the asynchronous loads of one tile (three planes + SAO / ALF parameters of its CTU neighbourhood) into `stage`
+__device__ __forceinline__ void saPrefetch(unsigned char* smraw, const SaLayout& L, int stage, const SlotDev& S, int srcBuf, const SaTile& T, const Geom& g,
+                                           bool saoOn, bool alfOn)
+{
+  saLoadTileAsync(reinterpret_cast<pel*>(smraw + L.offA(stage, 0)), SA_P, S.buf[srcBuf][0], T.x0, T.y0, SA_T, SA_T);
+  if (g.ncomp > 1)
+  {
+    const int tw = SA_T >> g.sx, th = SA_T >> g.sy;
+    saLoadTileAsync(reinterpret_cast<pel*>(smraw + L.offA(stage, 1)), L.pitchC, S.buf[srcBuf][1], T.x0 >> g.sx, T.y0 >> g.sy, tw, th);
+    saLoadTileAsync(reinterpret_cast<pel*>(smraw + L.offA(stage, 2)), L.pitchC, S.buf[srcBuf][2], T.x0 >> g.sx, T.y0 >> g.sy, tw, th);
+  }
+  SaTilePar* par = reinterpret_cast<SaTilePar*>(smraw + L.offPar) + stage;
+  const int tid = threadIdx.x, tcx = T.x0 >> g.ctuLog2, tcy = T.y0 >> g.ctuLog2;
   if (tid < 27)
   {
     const int c = tid / 9, k = tid - c * 9, cx = tcx + k % 3 - 1, cy = tcy + k / 3 - 1;
-    SaoDev z = {};
-    if (saoOn && cx >= 0 && cy >= 0 && cx < g.wCtus && cy < g.hCtus && c < g.ncomp) z = S.sao[(cy * g.wCtus + cx) * 3 + c];
-    sm.sao[c][k] = z;
+    if (saoOn && cx >= 0 && cy >= 0 && cx < g.wCtus && cy < g.hCtus && c < g.ncomp) cpAsync16(&par->sao[c][k], &S.sao[(cy * g.wCtus + cx) * 3 + c]);
+    else *reinterpret_cast<uint4*>(&par->sao[c][k]) = make_uint4(0, 0, 0, 0);
   }
-  bool alfY = false, alfC[2] = { false, false };
-  int ccIdc[2] = { 0, 0 };
-  if (alfPic)
+  else if (tid == 32)
   {
-    alfY = S.alfCtu[0 * nCtus + ctuIdx] != 0;
-    for (int c = 0; c < 2; c++)
-    {
-      alfC[c] = g.ncomp > 1 && S.alfCtu[(1 + c) * nCtus + ctuIdx] != 0;
-      ccIdc[c] = (g.ncomp > 1 && S.alf->ccEnabled[c]) ? S.alfCtu[(5 + c) * nCtus + ctuIdx] : 0;
-    }
-    if (tid < 12 && alfC[tid / 6]) sm.chromaSet[tid / 6][tid % 6] = S.alf->chroma[S.alfCtu[(3 + tid / 6) * nCtus + ctuIdx]][tid % 6];
-    if (tid < 16 && ccIdc[tid >> 3]) sm.cc[tid >> 3][tid & 7] = S.alf->cc[tid >> 3][ccIdc[tid >> 3] - 1][tid & 7];
+    if (alfOn) cpAsync8(&par->ctl, &S.alfCtu[tcy * g.wCtus + tcx]);
+    else *reinterpret_cast<uint2*>(&par->ctl) = make_uint2(0, 0);
   }
-
-  // ---- luma ----------------------------------------------------------------------------------------------
-  const PlaneDev srcY = S.buf[srcBuf][0], dstY = S.buf[dstBuf][0];
-  saLoadTile(sm.a, srcY, x0, y0, SA_T, SA_T);
-  __syncthreads();
-  bool saoY = false;
-#pragma unroll
-  for (int k = 0; k < 9; k++) saoY |= sm.sao[0][k].type != 0;
-  const bool lumaHalo = alfY || ccIdc[0] || ccIdc[1];
-  // without SAO in reach the loaded tile (already replicate padded) IS the ALF input; chroma then stages through sm.bl
-  pel* const lumaB = saoY ? sm.bl : sm.a;
-  pel* const chromaA = saoY ? sm.a : sm.bl;
-  if (saoY)
+  else if (tid >= 64 && tid < 67)
   {
-    const SaoGeom sg = { x0 - SA_HX, y0 - SA_HY, g.w, g.h, g.ctuLog2, g.ctuLog2, tcx, tcy, g.bdL };
-    saSaoTile(sm.bl, sm.a, SA_T, SA_T, lumaHalo, sm.sao[0], sg);
-    __syncthreads();
+    const int c = tid - 64, sxc = c ? g.sx : 0, syc = c ? g.sy : 0;
+    par->geom[c] = SaoGeom{ (T.x0 >> sxc) - SA_HX, (T.y0 >> syc) - SA_HY, g.w >> sxc, g.h >> syc, g.ctuLog2 - sxc, g.ctuLog2 - syc, tcx, tcy,
+                            c ? g.bdC : g.bdL, c ? L.pitchC : SA_P, SA_T >> sxc, 6 - syc };
   }
+}
 
+// Persistent kernel: gridDim.x CTAs walk the tiles of slots [firstSlot, firstSlot + numSlots) round robin.
+__global__ void __launch_bounds__(SA_THREADS, 2) k_sao_alf(const SlotDev* __restrict__ slots, int firstSlot, int numSlots, int srcBuf, int dstBuf, Geom g,
+                                                           int tilesX, int tilesY, int doSao, int doAlf)
+{
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const SaLayout L = saLayout(g.sx, g.sy, g.ncomp);
+  const int tid = threadIdx.x;
+  const int tilesPerPic = tilesX * tilesY, numTiles = tilesPerPic * numSlots;
+  uint2 (*cell)[SA_CELLP] = reinterpret_cast<uint2 (*)[SA_CELLP]>(smraw + L.offCell);
   const int vbL = g.ctu - 4, ctuMask = g.ctu - 1;
   const int bi = tid >> 4, bj = tid & 15;
-  const int bx = x0 + 4 * bj, by = y0 + 4 * bi;
-  const pel* c0 = &lumaB[(4 * bi + SA_HY) * SA_P + 4 * bj + SA_HX];
-  if (alfY)
-  {
-    const int yb = by & ctuMask;
-    const bool vbBlk = yb == vbL - 4 || yb == vbL;             // uniform per warp (two block rows) for CTU sizes >= 32
-    const bool wide = S.alf->wide != 0;
-    // Laplacian cells: own 2x2 cells per block (registers), ring and virtual-boundary rows by the generic routine
-    if (!vbBlk) alfOwnCells(sm, c0, bi, bj);
-    else
-    {
-#pragma unroll
-      for (int k = 0; k < 4; k++)
-      {
-        const int li = 2 * bi + 1 + (k >> 1), lj = 2 * bj + 1 + (k & 1);
-        sm.u.cell[li][lj] = alfCellGeneric(&lumaB[(2 * li + SA_HY - 2) * SA_P + 2 * lj + SA_HX - 2], y0 - 2 + 2 * li, ctuMask, vbL);
-      }
-    }
-    if (tid < 4 * (SA_CELLS - 1))
-    {
-      const int side = tid / (SA_CELLS - 1), k = tid - side * (SA_CELLS - 1);
-      const int li = side == 0 ? 0 : (side == 1 ? SA_CELLS - 1 : (side == 2 ? 1 + k : k));
-      const int lj = side == 0 ? k : (side == 1 ? 1 + k : (side == 2 ? 0 : SA_CELLS - 1));
-      sm.u.cell[li][lj] = alfCellGeneric(&lumaB[(2 * li + SA_HY - 2) * SA_P + 2 * lj + SA_HX - 2], y0 - 2 + 2 * li, ctuMask, vbL);
-    }
-    __syncthreads();
-    if (bx < g.w && by < g.h)
-    {
-      pel* out = dstY.p + (size_t)by * dstY.pitch + bx;
-      const int setIdx = S.alfFilterIdx[ctuIdx];
-      if (vbBlk || wide) alfLumaBlockGeneric(sm, c0, out, dstY.pitch, bi, bj, by, &S.alf->luma[setIdx][0][0], ctuMask, vbL, g.bdL);
-      else
-      {
-        // window = cells (2bi .. 2bi+3) x (2bj .. 2bj+3); row sums stay below 2^16 per lane for any bit depth <= 12
-        int sumV = 0, sumH = 0, sumD0 = 0, sumD1 = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-        {
-          const uint4* rp = reinterpret_cast<const uint4*>(&sm.u.cell[2 * bi + i][2 * bj]);
-          const uint4 q0 = rp[0], q1 = rp[1];
-          const uint32_t vh = q0.x + q0.z + q1.x + q1.z, dd = q0.y + q0.w + q1.y + q1.w;
-          sumV += vh & 0xffff; sumH += vh >> 16; sumD0 += dd & 0xffff; sumD1 += dd >> 16;
-        }
-        int cls, tIdx;
-        alfClassify(sumV, sumH, sumD0, sumD1, 64, g.bdL, cls, tIdx);
-        alfLumaBlockFast(c0, out, dstY.pitch, S.lumaTab + ((size_t)(setIdx * 25 + cls) * 4 + tIdx), dup16((1 << g.bdL) - 1));
-      }
-    }
-  }
-  else
-  {
-    // no luma ALF in this CTU: the SAO output is the result (128-bit rows)
-    for (int i = tid; i < SA_T * (SA_T / 8); i += SA_THREADS)
-    {
-      const int r = i >> 3, gc = i & 7;
-      const int y = y0 + r, x = x0 + 8 * gc;
-      if (y < g.h && x < g.w)
-        *reinterpret_cast<int4*>(dstY.p + (size_t)y * dstY.pitch + x) = *reinterpret_cast<const int4*>(&lumaB[(r + SA_HY) * SA_P + 8 * gc + SA_HX]);
-    }
-  }
-  if (g.ncomp == 1) return;
-
-  // ---- chroma (Cb then Cr reuse the same shared buffers) ---------------------------------------------------
-  const int tw = SA_T >> g.sx, th = SA_T >> g.sy, cx0 = x0 >> g.sx, cy0 = y0 >> g.sy;
+  const int tw = SA_T >> g.sx, thLogC = 6 - g.sy;
   const int cw = g.w >> g.sx, chh = g.h >> g.sy, ctuH = g.ctu >> g.sy;
   const int vbC = ctuH - 2, maxc = (1 << g.bdC) - 1, half = (1 << g.bdC) >> 1;
   const uint32_t maxcP = dup16(maxc), halfP = dup16(half);
-  for (int c = 0; c < 2; c++)
+
+  int t = blockIdx.x, stage = 0;
+  if (t >= numTiles) return;
   {
-    const PlaneDev srcC = S.buf[srcBuf][1 + c], dstC = S.buf[dstBuf][1 + c];
-    __syncthreads();                                  // previous users of chromaA / sm.u are done
-    saLoadTile(chromaA, srcC, cx0, cy0, tw, th);
-    __syncthreads();
-    bool saoC = false;
-#pragma unroll
-    for (int k = 0; k < 9; k++) saoC |= sm.sao[1 + c][k].type != 0;
-    const bool fOn = alfC[c];
-    const int idc = ccIdc[c];
-    const pel* chromaB = chromaA;
-    if (saoC)
+    const SaTile T = saDecodeTile(t, tilesX, tilesPerPic);
+    const SlotDev& S = slots[firstSlot + T.slot];
+    saPrefetch(smraw, L, 0, S, srcBuf, T, g, doSao && S.saoOn, doAlf && S.alfOn);
+    cpAsyncCommit();
+  }
+  for (; t < numTiles; t += gridDim.x, stage ^= 1)
+  {
+    const SaTile T = saDecodeTile(t, tilesX, tilesPerPic);
+    const SlotDev& S = slots[firstSlot + T.slot];
+    if (t + (int)gridDim.x < numTiles)
     {
-      const SaoGeom sg = { cx0 - SA_HX, cy0 - SA_HY, cw, chh, g.ctuLog2 - g.sx, g.ctuLog2 - g.sy, tcx, tcy, g.bdC };
-      saSaoTile(sm.u.bc, chromaA, tw, th, fOn, sm.sao[1 + c], sg);
-      __syncthreads();
-      chromaB = sm.u.bc;
+      const SaTile Tn = saDecodeTile(t + gridDim.x, tilesX, tilesPerPic);
+      const SlotDev& Sn = slots[firstSlot + Tn.slot];
+      saPrefetch(smraw, L, stage ^ 1, Sn, srcBuf, Tn, g, doSao && Sn.saoOn, doAlf && Sn.alfOn);
     }
-    ChromaCoef C;
-    if (fOn) C = chromaCoef(sm.chromaSet[c]);
-    int cc[7];
-    if (idc)
-    {
+    cpAsyncCommit();
+    cpAsyncWait<1>();
+    __syncthreads();                                         // tile t and its parameters are in shared memory
+
+    const int x0 = T.x0, y0 = T.y0;
+    const SaTilePar& par = reinterpret_cast<const SaTilePar*>(smraw + L.offPar)[stage];
+    const AlfCtuDev ctl = par.ctl;
+    const bool alfY = ctl.enY != 0, alfC[2] = { ctl.enCb != 0, ctl.enCr != 0 };
+    const int ccIdc[2] = { ctl.ccCb, ctl.ccCr };
+    pel* const A[3] = { reinterpret_cast<pel*>(smraw + L.offA(stage, 0)), reinterpret_cast<pel*>(smraw + L.offA(stage, 1)),
+                        reinterpret_cast<pel*>(smraw + L.offA(stage, 2)) };
+    pel* B[3] = { reinterpret_cast<pel*>(smraw + L.offB(0)), reinterpret_cast<pel*>(smraw + L.offB(1)), reinterpret_cast<pel*>(smraw + L.offB(2)) };
+
+    // ---- phase 1: SAO of all components (tile + 3 where an ALF stage reads the halo) ------------------------------
+    bool saoC[3];
+    int nInt[3], nHalo[3];
+    bool border = false;
 #pragma unroll
-      for (int k = 0; k < 7; k++) cc[k] = sm.cc[c][k];
-    }
-    // one thread = 4 horizontally adjacent chroma samples
-    const int quads = (tw >> 2) * th;
-    for (int i = tid; i < quads; i += SA_THREADS)
+    for (int c = 0; c < 3; c++)
     {
-      const int r = i / (tw >> 2), qx = (i - r * (tw >> 2)) * 4;
-      const int x = cx0 + qx, y = cy0 + r;
-      if (x >= cw || y >= chh) continue;
-      const pel* cb = &chromaB[(r + SA_HY) * SA_P + qx + SA_HX];
-      uint2 v = *reinterpret_cast<const uint2*>(cb);
-      if (fOn)
+      saoC[c] = false;
+      if (c < g.ncomp)
       {
-        int lim; bool nearVb;
-        vbLimit(y & (ctuH - 1), vbC, 2, lim, nearVb);
-        v = alfChromaQuad(cb, min(1, lim) * SA_P, min(2, lim) * SA_P, nearVb, C, maxcP);
+#pragma unroll
+        for (int k = 0; k < 9; k++) saoC[c] |= par.sao[c][k].type != 0;
       }
-      if (idc)
+      const bool halo = c == 0 ? (alfY || ccIdc[0] || ccIdc[1]) : alfC[c - 1];
+      nInt[c] = saoC[c] ? saoItemsInterior(par.geom[c]) : 0;
+      nHalo[c] = saoC[c] && halo ? saoItemsHalo(par.geom[c]) : 0;
+      border |= nHalo[c] && saoNeedsBorder(par.geom[c]);
+      if (!saoC[c]) B[c] = A[c];                              // no SAO in reach: the (replicate padded) input IS the ALF input
+    }
+    if (saoC[0] | saoC[1] | saoC[2])
+    {
+      const int e0 = nInt[0], e1 = e0 + nInt[1], e2 = e1 + nInt[2], e3 = e2 + nHalo[0], e4 = e3 + nHalo[1], e5 = e4 + nHalo[2];
+      for (int i = tid; i < e5; i += SA_THREADS)
       {
-        // CC-ALF row offsets in the luma tile (filterBlkCcAlf :1376-1386)
-        const int ly = (r << g.sy) + SA_HY, lpos = (y << g.sy) & ctuMask;
-        int l1 = SA_P, l2 = -SA_P, l3 = 2 * SA_P;
-        if (lpos == vbL - 2 || lpos == vbL + 1) l3 = SA_P;
-        else if (lpos == vbL - 1 || lpos == vbL) l1 = l2 = l3 = 0;
-        if (g.sx == 1)
+        const bool interior = i < e2;
+        const int c = interior ? (i < e0 ? 0 : (i < e1 ? 1 : 2)) : (i < e3 ? 0 : (i < e4 ? 1 : 2));
+        const int base = interior ? (c == 0 ? 0 : (c == 1 ? e0 : e1)) : (c == 0 ? e2 : (c == 1 ? e3 : e4));
+        const SaoGeom sg = par.geom[c];
+        pel* bq = reinterpret_cast<pel*>(smraw + L.offB(c));
+        const pel* aq = reinterpret_cast<const pel*>(smraw + L.offA(stage, c));
+        int r, gc;
+        bool ok;
+        if (interior) ok = saoItemInterior(i - base, sg, r, gc); else ok = saoItemHalo(i - base, sg, r, gc);
+        if (ok) saoGroup(bq, aq, r, gc, par.sao[c], sg);
+      }
+      if (border)
+      {
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+          if (nHalo[c] && saoNeedsBorder(par.geom[c]))
+            saoBorder(B[c], par.geom[c].bx0, par.geom[c].by0, par.geom[c].w, par.geom[c].h, par.geom[c].pitch, par.geom[c].tw, 1 << par.geom[c].thLog);
+      }
+      __syncthreads();
+    }
+
+    // ---- phase 2: Laplacian cells (luma ALF only) -------------------------------------------------------------------
+    const pel* lumaB = B[0];
+    const int bx = x0 + 4 * bj, by = y0 + 4 * bi;
+    const pel* c0 = &lumaB[(4 * bi + SA_HY) * SA_P + 4 * bj + SA_HX];
+    const int yb = by & ctuMask;
+    const bool vbBlk = yb == vbL - 4 || yb == vbL;             // uniform per warp (two block rows) for CTU sizes >= 32
+    if (alfY)
+    {
+      if (!vbBlk) alfOwnCells(cell, c0, bi, bj);
+      else
+      {
+        for (int k = 0; k < 4; k++)
         {
-          const uint2 d = ccAlfQuad420(&lumaB[ly * SA_P + (qx << 1) + SA_HX], l1, l2, l3, cc, maxcP, halfP);
-          v.x = addClamp0(v.x, d.x, maxcP);
-          v.y = addClamp0(v.y, d.y, maxcP);
+          const int li = 2 * bi + 1 + (k >> 1), lj = 2 * bj + 1 + (k & 1);
+          cell[li][lj] = alfCellGeneric(&lumaB[(2 * li + SA_HY - 2) * SA_P + 2 * lj + SA_HX - 2], y0 - 2 + 2 * li, ctuMask, vbL);
         }
+      }
+      if (tid < 4 * (SA_CELLS - 1))
+      {
+        const int side = tid / (SA_CELLS - 1), k = tid - side * (SA_CELLS - 1);
+        const int li = side == 0 ? 0 : (side == 1 ? SA_CELLS - 1 : (side == 2 ? 1 + k : k));
+        const int lj = side == 0 ? k : (side == 1 ? 1 + k : (side == 2 ? 0 : SA_CELLS - 1));
+        cell[li][lj] = alfCellGeneric(&lumaB[(2 * li + SA_HY - 2) * SA_P + 2 * lj + SA_HX - 2], y0 - 2 + 2 * li, ctuMask, vbL);
+      }
+      __syncthreads();
+    }
+
+    // ---- phase 3: filters; every plane is written once ----------------------------------------------------------------
+    const PlaneDev dstY = S.buf[dstBuf][0];
+    if (alfY)
+    {
+      if (bx < g.w && by < g.h)
+      {
+        pel* out = dstY.p + (size_t)by * dstY.pitch + bx;
+        const int setIdx = ctl.setIdx;
+        if (vbBlk || S.alfWide) alfLumaBlockGeneric(cell, c0, out, dstY.pitch, bi, bj, by, &S.alf->luma[setIdx][0][0], ctuMask, vbL, g.bdL);
         else
         {
-          pel res[4] = { (pel)(v.x & 0xffff), (pel)(v.x >> 16), (pel)(v.y & 0xffff), (pel)(v.y >> 16) };
+          // window = cells (2bi .. 2bi+3) x (2bj .. 2bj+3); row sums stay below 2^16 per lane for any bit depth <= 12
+          int sumV = 0, sumH = 0, sumD0 = 0, sumD1 = 0;
 #pragma unroll
-          for (int q = 0; q < 4; q++)
+          for (int i = 0; i < 4; i++)
           {
-            const pel* l = &lumaB[ly * SA_P + qx + q + SA_HX];
-            const int cur = l[0];
-            int s = cc[0] * (l[l2] - cur) + cc[1] * (l[-1] - cur) + cc[2] * (l[1] - cur) + cc[3] * (l[l1 - 1] - cur) + cc[4] * (l[l1] - cur) +
-                    cc[5] * (l[l1 + 1] - cur) + cc[6] * (l[l3] - cur);
-            s = (s + 64) >> 7;
-            s = clip3(0, maxc, s + half) - half;
-            res[q] = (pel)clip3(0, maxc, res[q] + s);
+            const uint4* rp = reinterpret_cast<const uint4*>(&cell[2 * bi + i][2 * bj]);
+            const uint4 q0 = rp[0], q1 = rp[1];
+            const uint32_t vh = q0.x + q0.z + q1.x + q1.z, dd = q0.y + q0.w + q1.y + q1.w;
+            sumV += vh & 0xffff; sumH += vh >> 16; sumD0 += dd & 0xffff; sumD1 += dd >> 16;
           }
-          v = *reinterpret_cast<const uint2*>(res);
+          int cls, tIdx;
+          alfClassify(sumV, sumH, sumD0, sumD1, 64, g.bdL, cls, tIdx);
+          alfLumaBlockFast(c0, out, dstY.pitch, S.lumaTab + ((size_t)(setIdx * 25 + cls) * 4 + tIdx), dup16((1 << g.bdL) - 1));
         }
       }
-      *reinterpret_cast<uint2*>(dstC.p + (size_t)y * dstC.pitch + x) = v;
     }
+    else
+    {
+      // no luma ALF in this CTU: the SAO output is the result (128-bit rows)
+      for (int i = tid; i < SA_T * (SA_T / 8); i += SA_THREADS)
+      {
+        const int r = i >> 3, gc = i & 7;
+        const int y = y0 + r, x = x0 + 8 * gc;
+        if (y < g.h && x < g.w)
+          *reinterpret_cast<int4*>(dstY.p + (size_t)y * dstY.pitch + x) = *reinterpret_cast<const int4*>(&lumaB[(r + SA_HY) * SA_P + 8 * gc + SA_HX]);
+      }
+    }
+    if (g.ncomp > 1)
+    {
+      // chroma: one item = 4 horizontally adjacent samples
+      const int cx0 = x0 >> g.sx, cy0 = y0 >> g.sy, qShift = 4 - g.sx, quads = (tw >> 2) << thLogC;       // tw / 4 = 1 << qShift
+#pragma unroll 1
+      for (int c = 0; c < 2; c++)
+      {
+        const PlaneDev dstC = S.buf[dstBuf][1 + c];
+        const pel* Bc = c ? B[2] : B[1];
+        const bool fOn = c ? alfC[1] : alfC[0];
+        const int idc = c ? ccIdc[1] : ccIdc[0];
+        ChromaCoef C;
+        if (fOn) C = chromaCoef(S.alf->chroma[c ? ctl.altCr : ctl.altCb]);
+        const int16_t* ccg = S.alf->cc[c][idc ? idc - 1 : 0];
+        for (int j = tid; j < quads; j += SA_THREADS)
+        {
+          const int r = j >> qShift, qx = (j & ((1 << qShift) - 1)) * 4;
+          const int x = cx0 + qx, y = cy0 + r;
+          if (x >= cw || y >= chh) continue;
+          const pel* cb = &Bc[(r + SA_HY) * L.pitchC + qx + SA_HX];
+          uint2 v = *reinterpret_cast<const uint2*>(cb);
+          if (fOn)
+          {
+            int lim; bool nearVb;
+            vbLimit(y & (ctuH - 1), vbC, 2, lim, nearVb);
+            v = alfChromaQuad(cb, min(1, lim) * L.pitchC, min(2, lim) * L.pitchC, nearVb, C, maxcP);
+          }
+          if (idc)
+          {
+            // CC-ALF row offsets in the luma tile (filterBlkCcAlf :1376-1386)
+            const int ly = (r << g.sy) + SA_HY, lpos = (y << g.sy) & ctuMask;
+            int l1 = SA_P, l2 = -SA_P, l3 = 2 * SA_P;
+            if (lpos == vbL - 2 || lpos == vbL + 1) l3 = SA_P;
+            else if (lpos == vbL - 1 || lpos == vbL) l1 = l2 = l3 = 0;
+            if (g.sx == 1)
+            {
+              const uint2 d = ccAlfQuad420(&lumaB[ly * SA_P + (qx << 1) + SA_HX], l1, l2, l3, ccg, maxcP, halfP);
+              v.x = addClamp0(v.x, d.x, maxcP);
+              v.y = addClamp0(v.y, d.y, maxcP);
+            }
+            else
+            {
+              int res[4] = { (int)(v.x & 0xffff), (int)(v.x >> 16), (int)(v.y & 0xffff), (int)(v.y >> 16) };
+              int cc[7];
+#pragma unroll
+              for (int k = 0; k < 7; k++) cc[k] = __ldg(&ccg[k]);
+#pragma unroll
+              for (int q = 0; q < 4; q++)
+              {
+                const pel* l = &lumaB[ly * SA_P + qx + q + SA_HX];
+                const int cur = l[0];
+                int s = cc[0] * (l[l2] - cur) + cc[1] * (l[-1] - cur) + cc[2] * (l[1] - cur) + cc[3] * (l[l1 - 1] - cur) + cc[4] * (l[l1] - cur) +
+                        cc[5] * (l[l1 + 1] - cur) + cc[6] * (l[l3] - cur);
+                s = (s + 64) >> 7;
+                s = clip3(0, maxc, s + half) - half;
+                res[q] = clip3(0, maxc, res[q] + s);
+              }
+              v = make_uint2((uint32_t)res[0] | (uint32_t)res[1] << 16, (uint32_t)res[2] | (uint32_t)res[3] << 16);
+            }
+          }
+          *reinterpret_cast<uint2*>(dstC.p + (size_t)y * dstC.pitch + x) = v;
+        }
+      }
+    }
+    __syncthreads();                                         // all reads of stage buffers / B / cells are done before they are refilled
   }
 }
 

@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -27,7 +28,7 @@ std::string g_createError;
 
 struct SideLayout     // byte offsets inside a slot's side-info block
 {
-  size_t dbfL[2], dbfC[2], sao, alfTab, alfCtu, alfIdx, alf, total;
+  size_t dbfL[2], dbfC[2], sao, alfTab, alfCtu, alf, total;
   size_t nL, nC[2];
 };
 
@@ -81,6 +82,7 @@ struct vtmgpu_ctx
   SlotDev* slotsDev = nullptr;
   std::vector<int> cur;                // buffer index holding the current state of each slot
   int64_t launches = 0;
+  int numSms = 0;
 
   int fail(const char* fmt, ...)
   {
@@ -182,8 +184,7 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
   for (int d = 0; d < 2; d++) { L.dbfC[d] = off; off = alignUp(off + L.nC[d] * 8, 256); }
   L.sao = off;    off = alignUp(off + (size_t)c->nCtus * 3 * sizeof(SaoDev), 256);
   L.alfTab = off; off = alignUp(off + sizeof(AlfLumaEntry) * VTMGPU_MAX_LUMA_SETS * 25 * 4, 256);
-  L.alfCtu = off; off = alignUp(off + (size_t)c->nCtus * 8, 256);
-  L.alfIdx = off; off = alignUp(off + (size_t)c->nCtus * 2, 256);
+  L.alfCtu = off; off = alignUp(off + (size_t)c->nCtus * sizeof(AlfCtuDev), 256);
   L.alf = off;    off = alignUp(off + sizeof(AlfDev), 256);
   L.total = off;
 
@@ -234,8 +235,7 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
     }
     sd.sao = reinterpret_cast<const SaoDev*>(side + L.sao);
     sd.alf = reinterpret_cast<const AlfDev*>(side + L.alf);
-    sd.alfCtu = side + L.alfCtu;
-    sd.alfFilterIdx = reinterpret_cast<const int16_t*>(side + L.alfIdx);
+    sd.alfCtu = reinterpret_cast<const AlfCtuDev*>(side + L.alfCtu);
     sd.lumaTab = reinterpret_cast<const AlfLumaEntry*>(side + L.alfTab);
     sd.dbfOn = sd.saoOn = sd.alfOn = 0;
   }
@@ -256,7 +256,8 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
     }
   }
   CK(cudaMemcpyAsync(c->slotsDev, c->slotsPinned, sizeof(SlotDev) * s.capacity, cudaMemcpyHostToDevice, c->stream), "slot table upload");
-  CK(cudaFuncSetAttribute(k_sao_alf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SaoAlfSmem)), "smem attribute");
+  CK(cudaFuncSetAttribute(k_sao_alf, cudaFuncAttributeMaxDynamicSharedMemorySize, saLayout(g.sx, g.sy, g.ncomp).total), "smem attribute");
+  CK(cudaDeviceGetAttribute(&c->numSms, cudaDevAttrMultiProcessorCount, s.device), "device attribute");
   CK(cudaStreamSynchronize(c->stream), "sync");
 #undef CK
   *out = c;
@@ -454,8 +455,7 @@ extern "C" int vtmgpu_set_alf(vtmgpu_ctx* c, int slot, const vtmgpu_alf_params* 
     if (p->num_luma_aps < 0 || p->num_luma_aps > VTMGPU_ALF_MAX_APS) return c->fail("set_alf: bad num_luma_aps");
     const bool chroma = c->g.ncomp > 1;
     AlfDev& A = *reinterpret_cast<AlfDev*>(c->pinnedSide(slot) + c->lay.alf);
-    uint8_t* ctl = c->pinnedSide(slot) + c->lay.alfCtu;
-    int16_t* idx = reinterpret_cast<int16_t*>(c->pinnedSide(slot) + c->lay.alfIdx);
+    AlfCtuDev* ctl = reinterpret_cast<AlfCtuDev*>(c->pinnedSide(slot) + c->lay.alfCtu);
     memset(&A, 0, sizeof(A));
     for (int k = 0; k < 3; k++) A.enabled[k] = p->enabled[k] != 0;
     A.numSets = VTMGPU_ALF_FIXED_SETS + p->num_luma_aps;
@@ -505,36 +505,36 @@ extern "C" int vtmgpu_set_alf(vtmgpu_ctx* c, int slot, const vtmgpu_alf_params* 
       memcpy(A.cc[k], p->ccalf_coeff[k], sizeof(A.cc[k]));
     }
     // per-CTU control
-    memset(ctl, 0, (size_t)n * 8);
+    memset(ctl, 0, (size_t)n * sizeof(AlfCtuDev));
     for (int a = 0; a < n; a++)
     {
-      const bool y = p->ctu_enable[0] && p->ctu_enable[0][a];
-      ctl[0 * n + a] = y;
-      idx[a] = 0;
-      if (y)
+      AlfCtuDev& r = ctl[a];
+      r.enY = p->ctu_enable[0] && p->ctu_enable[0][a];
+      if (r.enY)
       {
         if (!p->ctu_filter_idx || p->ctu_filter_idx[a] < 0 || p->ctu_filter_idx[a] >= A.numSets) return c->fail("set_alf: CTU %d: bad filter set index", a);
-        idx[a] = p->ctu_filter_idx[a];
+        r.setIdx = (uint8_t)p->ctu_filter_idx[a];
       }
       for (int k = 0; k < 2 && chroma; k++)
       {
         const bool on = p->ctu_enable[1 + k] && p->ctu_enable[1 + k][a];
-        ctl[(1 + k) * n + a] = on;
+        (k ? r.enCr : r.enCb) = on;
         if (on)
         {
           const int alt = p->ctu_alt[k] ? p->ctu_alt[k][a] : 0;
           if (alt >= numAlts) return c->fail("set_alf: CTU %d: chroma alternative %d not in the APS", a, alt);
-          ctl[(3 + k) * n + a] = (uint8_t)alt;
+          (k ? r.altCr : r.altCb) = (uint8_t)alt;
         }
         if (A.ccEnabled[k])
         {
           const int idc = p->ccalf_idc[k] ? p->ccalf_idc[k][a] : 0;
           if (idc > VTMGPU_CCALF_MAX_FILTERS) return c->fail("set_alf: CTU %d: bad CC-ALF idc", a);
-          ctl[(5 + k) * n + a] = (uint8_t)idc;
+          (k ? r.ccCr : r.ccCb) = (uint8_t)idc;
         }
       }
     }
-    sd.alfOn = 1;
+    sd.alfOn = (A.enabled[0] | A.enabled[1] | A.enabled[2]) != 0;    // ALFProcess skips the picture otherwise (AdaptiveLoopFilter.cpp:429)
+    sd.alfWide = wide;
     if (p->num_luma_aps && c->pushSide(slot, c->lay.alfTab + sizeof(AlfLumaEntry) * VTMGPU_ALF_FIXED_SETS * 100, sizeof(AlfLumaEntry) * 100 * p->num_luma_aps)) return -1;
     if (c->pushSide(slot, c->lay.alfCtu, c->lay.total - c->lay.alfCtu)) return -1;
   }
@@ -589,10 +589,13 @@ int launchSaoAlf(vtmgpu_ctx* c, int first, int count, int doSao, int doAlf)
   for (int s = first; s < first + count; s++) any |= (doSao && c->slotsPinned[s].saoOn) || (doAlf && c->slotsPinned[s].alfOn);
   if (!any) return 0;
   const Geom& g = c->g;
-  const int tilesX = (g.w + SA_T - 1) / SA_T, tiles = tilesX * ((g.h + SA_T - 1) / SA_T);
+  const int tilesX = (g.w + SA_T - 1) / SA_T, tilesY = (g.h + SA_T - 1) / SA_T;
+  const int smem = saLayout(g.sx, g.sy, g.ncomp).total;
   return forRuns(c, first, count, [&](int s, int n, int src) {
     const int dst = src == 1 ? 2 : 1;
-    k_sao_alf<<<dim3(tiles, n), SA_THREADS, sizeof(SaoAlfSmem), c->stream>>>(c->slotsDev, s, src, dst, g, tilesX, doSao, doAlf);
+    // persistent CTAs: two per SM (register limited), each walks the tiles round robin with double-buffered cp.async loads
+    const int grid = std::min(tilesX * tilesY * n, 2 * c->numSms);
+    k_sao_alf<<<grid, SA_THREADS, smem, c->stream>>>(c->slotsDev, s, n, src, dst, g, tilesX, tilesY, doSao, doAlf);
     c->launches++;
     for (int i = s; i < s + n; i++) c->cur[i] = dst;
     return c->cuda(cudaGetLastError(), "k_sao_alf launch");

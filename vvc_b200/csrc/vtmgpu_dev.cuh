@@ -55,6 +55,15 @@ struct AlfLumaEntry
   int32_t  pad[3];
 };
 
+// ALF control of one CTU (Picture::getAlfCtuEnableFlag / getAlfCtbFilterIndex / getAlfCtuAlternativeData, m_ccAlfFilterControl)
+struct AlfCtuDev
+{
+  uint8_t enY, enCb, enCr;       // CTU enable flags
+  uint8_t altCb, altCr;          // chroma filter alternative
+  uint8_t ccCb, ccCr;            // CC-ALF filter idc (0 = off)
+  uint8_t setIdx;                // luma filter set: < 16 fixed, else APS
+};
+
 struct SlotDev
 {
   PlaneDev buf[3][3];            // [buffer][component]; buffer 0 = pristine upload, 1/2 = working
@@ -62,10 +71,10 @@ struct SlotDev
   const uint64_t* dbfC[2];
   const SaoDev*   sao;           // [ctus][3]                     (NULL: stage off)
   const AlfDev*   alf;           //                               (NULL: stage off)
-  const uint8_t*  alfCtu;        // [8][ctus]: enable Y,Cb,Cr, alt Cb,Cr, cc idc Cb,Cr, (unused)
-  const int16_t*  alfFilterIdx;  // [ctus]
+  const AlfCtuDev* alfCtu;       // [ctus]
   const AlfLumaEntry* lumaTab;   // [sets][25 classes][4 transposes]
-  int32_t dbfOn, saoOn, alfOn;
+  int32_t dbfOn, saoOn, alfOn;   // alfOn: parameters set AND the slice enables ALF for at least one component
+  int32_t alfWide;               // a luma coefficient does not fit the s8 operand of IDP.2A: generic path
 };
 
 struct Geom
