@@ -23,6 +23,8 @@
 // Per luma pixel algorithmic HBM bytes at 4:2:0: read 3, write 3 (+ CTU params, negligible).
 #pragma once
 
+#include <cuda.h>
+
 #include "vtmgpu_dev.cuh"
 #include "vtmgpu.h"
 
@@ -61,20 +63,19 @@ struct SaoGeom
 struct SaTilePar
 {
   SaoDev    sao[3][9];
-  SaoGeom   geom[3];
-  AlfCtuDev ctl;
-  int32_t   pad[2];
+  CtuCtlDev ctl;
 };
 
 struct SaLayout
 {
   int pitchC, rowsC;               // chroma tile buffers: pitch in samples, rows
-  int lumaBytes, chromaBytes, offCell, offPar, total;
+  int lumaBytes, chromaBytes, offCell, offPar, offBar, total;
   __host__ __device__ int comp(int c) const { return c ? lumaBytes + (c - 1) * chromaBytes : 0; }
   __host__ __device__ int offA(int stage, int c) const { return stage * (lumaBytes + 2 * chromaBytes) + comp(c); }
   __host__ __device__ int offB(int c) const { return 2 * (lumaBytes + 2 * chromaBytes) + comp(c); }
 };
 
+// all tile buffer sizes are multiples of 128 bytes (TMA destination alignment)
 __host__ __device__ inline SaLayout saLayout(int sx, int sy, int ncomp)
 {
   SaLayout L;
@@ -85,7 +86,8 @@ __host__ __device__ inline SaLayout saLayout(int sx, int sy, int ncomp)
   L.chromaBytes = ncomp > 1 ? L.rowsC * L.pitchC * 2 : 0;
   L.offCell = 3 * (L.lumaBytes + 2 * L.chromaBytes);
   L.offPar = L.offCell + SA_CELLS * SA_CELLP * 8;
-  L.total = L.offPar + 2 * (int)sizeof(SaTilePar);
+  L.offBar = L.offPar + 2 * (int)sizeof(SaTilePar);
+  L.total = L.offBar + 16;
   return L;
 }
 
@@ -102,50 +104,53 @@ __device__ __forceinline__ uint32_t mid16(uint32_t lo, uint32_t hi) { return __f
 // max(min(a + b, c), 0) per signed 16-bit lane
 __device__ __forceinline__ uint32_t addClamp0(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_s16x2_relu(a, b, c); }
 
-// ---- asynchronous tile load ---------------------------------------------------------------------------------
+// ---- asynchronous tile load: TMA (cp.async.bulk.tensor) completing on an mbarrier ------------------------------------
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cpAsync16(void* smem, const void* gmem)
 {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cpAsync8(void* smem, const void* gmem)
-{
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smemAddr(smem)), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// copies rows y0-SA_HY .. y0+th+SA_HY-1, columns x0-SA_HX .. x0+tw+SA_HX-1 of a plane into s (pitch in samples) with
-// cp.async (no register staging); rows are clamped to the picture (= replicate border), groups that leave the picture
-// on the left / right are filled synchronously with the edge sample (picture-border tiles only).
-// rcpGroups = ceil(65536 / groups): i / groups == (i * rcpGroups) >> 16 for i < 4096.
-__device__ __forceinline__ void saLoadTileAsync(pel* s, int pitch, const PlaneDev& pl, int x0, int y0, int tw, int th)
+__device__ __forceinline__ void mbarInit(uint64_t* bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes)
 {
-  const int groups = (tw + 2 * SA_HX) >> 3, rows = th + 2 * SA_HY;
-  const int rcpGroups = (65536 + groups - 1) / groups;
-  for (int i = threadIdx.x; i < groups * rows; i += SA_THREADS)
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity)
+{
+  asm volatile(
+    "{\n"
+    ".reg .pred p;\n"
+    "MBAR_WAIT_%=:\n"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+    "@p bra MBAR_DONE_%=;\n"
+    "bra MBAR_WAIT_%=;\n"
+    "MBAR_DONE_%=:\n"
+    "}\n" ::"r"(smemAddr(bar)), "r"(parity) : "memory");
+}
+// one 2-D box of a plane (element coordinates, may start outside: those elements arrive as zeros) into shared memory
+__device__ __forceinline__ void tmaLoad2D(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar)
+{
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smemAddr(dst)), "l"(map), "r"(x), "r"(y), "r"(smemAddr(bar)) : "memory");
+}
+
+// TMA fills positions outside the picture with zeros; the filters want the border samples replicated
+// (rows / columns of tile +- 4 that lie outside take the value of the clamped position)
+__device__ __noinline__ void saReplicateBorder(pel* s, int bx0, int by0, int w, int h, int pitch, int tw, int th, int margin)
+{
+  const int xl = bx0 + SA_HX - margin, yt = by0 + SA_HY - margin;
+  const int cols = tw + 2 * margin, rows = th + 2 * margin;
+  for (int rr = threadIdx.x >> 5; rr < rows; rr += SA_THREADS / 32)
   {
-    const int r = (i * rcpGroups) >> 16, gc = i - r * groups;
-    const int y = min(max(y0 - SA_HY + r, 0), pl.h - 1), x = x0 - SA_HX + gc * 8;
-    const pel* row = pl.p + (size_t)y * pl.pitch;
-    pel* d = &s[r * pitch + gc * 8];
-    if (x >= 0 && x + 8 <= pl.w) cpAsync16(d, row + x);
-    else
+    const int py = yt + rr, sy_ = min(max(py, 0), h - 1);
+    const bool rowOut = py != sy_;
+    for (int cc = threadIdx.x & 31; cc < cols; cc += 32)
     {
-      int4 v;
-      if (x >= 0 && x < pl.w)
-      {
-        // the picture ends inside this group (plane widths are multiples of 4): replicate the last column
-        v = __ldg(reinterpret_cast<const int4*>(row + x));
-        const int e = (int)__byte_perm((uint32_t)v.y, 0u, 0x3232);
-        v.z = e; v.w = e;
-      }
-      else
-      {
-        const uint32_t e = (uint16_t)row[x < 0 ? 0 : pl.w - 1];
-        const int ee = (int)(e | (e << 16));
-        v = make_int4(ee, ee, ee, ee);
-      }
-      *reinterpret_cast<int4*>(d) = v;
+      const int px = xl + cc, sx_ = min(max(px, 0), w - 1);
+      if (rowOut || px != sx_) s[(py - by0) * pitch + px - bx0] = s[(sy_ - by0) * pitch + sx_ - bx0];
     }
   }
 }
@@ -193,6 +198,7 @@ __device__ __forceinline__ uint32_t saoSkipLanes(int x, int y, int dxa, int dya,
 {
   const int cwm = (1 << g.cwLog) - 1, chm = (1 << g.chLog) - 1;
   if ((y & chm) != 0 && ((y + 1) & chm) != 0 && y + 1 < g.h && (x & cwm) != 0 && ((x + 8) & cwm) != 0 && x + 8 < g.w) return 0;
+  if (avail == 0xffu && y > 0 && y + 1 < g.h && x > 0 && x + 8 < g.w) return 0;       // all 8 neighbour CTUs usable, not on the picture border
   return saoSkipLanesSlow(x, y, dxa, dya, avail, g.w, g.h, g.cwLog, g.chLog);
 }
 
@@ -313,31 +319,6 @@ __device__ __forceinline__ bool saoItemHalo(int i, const SaoGeom& g, int& r, int
   }
   const int y = g.by0 + r, x = g.bx0 + 8 * gc;
   return y >= 0 && y < g.h && x >= 0 && x < g.w;
-}
-
-// true when the tile + 3 region of this component leaves the picture (the SAO output then needs its replicate border)
-__device__ __forceinline__ bool saoNeedsBorder(const SaoGeom& g)
-{
-  const int th = 1 << g.thLog;
-  return g.bx0 + SA_HX - 3 < 0 || g.by0 + SA_HY - 3 < 0 || g.bx0 + SA_HX + g.tw + 2 >= g.w || g.by0 + SA_HY + th + 2 >= g.h;
-}
-
-// positions of tile + 3 outside the picture take the value of the clamped position (= UnitBuf::extendBorderPel of the SAO
-// output, AdaptiveLoopFilter.cpp:411)
-__device__ __noinline__ void saoBorder(pel* b, int bx0, int by0, int w, int h, int pitch, int tw, int th)
-{
-  const int xl = bx0 + SA_HX - 3, yt = by0 + SA_HY - 3;
-  const int cols = tw + 6, rows = th + 6;
-  for (int rr = threadIdx.x >> 5; rr < rows; rr += SA_THREADS / 32)
-    for (int cc = threadIdx.x & 31; cc < cols; cc += 32)
-    {
-      const int px = xl + cc, py = yt + rr;
-      if (px < 0 || py < 0 || px >= w || py >= h)
-      {
-        const int sx_ = min(max(px, 0), w - 1), sy_ = min(max(py, 0), h - 1);
-        b[(py - by0) * pitch + px - bx0] = b[(sy_ - by0) * pitch + sx_ - bx0];
-      }
-    }
 }
 
 // ---- ALF: generic scalar routines (virtual-boundary rows, halo cells, wide coefficients, non-4:2:0 CC-ALF) ----------
@@ -525,21 +506,15 @@ struct ChromaCoef
   int bias;
 };
 
-__device__ __forceinline__ ChromaCoef chromaCoef(const short2* __restrict__ f)
+__device__ __forceinline__ ChromaCoef chromaCoef(const AlfChromaEntry* __restrict__ e)
 {
   ChromaCoef c;
-  int b = 64;
-#pragma unroll
-  for (int k = 0; k < 6; k++)
-  {
-    const short2 e = __ldg(&f[k]);
-    const int co = e.x, cl = e.y;
-    c.coefB[k] = (uint32_t)(co & 0xff) * 0x01000001u;
-    c.clipP1[k] = dup16(cl + 1);
-    c.clip2[k] = dup16(2 * cl);
-    b -= co * 2 * cl;
-  }
-  c.bias = b;
+  const uint4* q = reinterpret_cast<const uint4*>(e);
+  const uint4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4);
+  c.coefB[0] = q0.x; c.coefB[1] = q0.y; c.coefB[2] = q0.z; c.coefB[3] = q0.w; c.coefB[4] = q1.x; c.coefB[5] = q1.y;
+  c.clipP1[0] = q1.z; c.clipP1[1] = q1.w; c.clipP1[2] = q2.x; c.clipP1[3] = q2.y; c.clipP1[4] = q2.z; c.clipP1[5] = q2.w;
+  c.clip2[0] = q3.x; c.clip2[1] = q3.y; c.clip2[2] = q3.z; c.clip2[3] = q3.w; c.clip2[4] = q4.x; c.clip2[5] = q4.y;
+  c.bias = (int)q4.z;
   return c;
 }
 
@@ -636,128 +611,150 @@ __device__ __forceinline__ uint2 ccAlfQuad420(const pel* l, int l1, int l2, int 
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------
-struct SaTile
+struct SaWalk            // position of a CTA in its round-robin walk over the tiles of a batch of picture slots
 {
-  int slot, x0, y0;      // luma origin
+  int slot, ty, tx;
 };
 
-__device__ __forceinline__ SaTile saDecodeTile(int t, int tilesX, int tilesPerPic)
+struct SaStep            // one step of the walk = gridDim.x tiles, decomposed on the host (no division in the loop)
 {
-  SaTile T;
-  T.slot = t / tilesPerPic;
-  const int rem = t - T.slot * tilesPerPic, ty = rem / tilesX;
-  T.x0 = (rem - ty * tilesX) * SA_T;
-  T.y0 = ty * SA_T;
-  return T;
+  int dx, dy, ds;
+};
+
+__device__ __forceinline__ void saAdvance(SaWalk& p, const SaStep& st, int tilesX, int tilesY)
+{
+  p.tx += st.dx; if (p.tx >= tilesX) { p.tx -= tilesX; p.ty++; }
+  p.ty += st.dy; if (p.ty >= tilesY) { p.ty -= tilesY; p.slot++; }
+  p.slot += st.ds;
 }
 
-// issues the asynchronous loads of one tile (three planes + SAO / ALF parameters of its CTU neighbourhood) into `stage`
-__device__ __forceinline__ void saPrefetch(unsigned char* smraw, const SaLayout& L, int stage, const SlotDev& S, int srcBuf, const SaTile& T, const Geom& g,
-                                           bool saoOn, bool alfOn)
+// issues the asynchronous loads of one tile into `stage`: three TMA boxes (one thread) + SAO / control parameters of the
+// CTU neighbourhood (cp.async, 28 threads)
+__device__ __forceinline__ void saPrefetch(unsigned char* smraw, const SaLayout& L, int stage, const SlotDev& S, const CUtensorMap* maps, const SaWalk& p,
+                                           const Geom& g, bool saoOn)
 {
-  saLoadTileAsync(reinterpret_cast<pel*>(smraw + L.offA(stage, 0)), SA_P, S.buf[srcBuf][0], T.x0, T.y0, SA_T, SA_T);
-  if (g.ncomp > 1)
+  const int tid = threadIdx.x, x0 = p.tx * SA_T, y0 = p.ty * SA_T;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smraw + L.offBar) + stage;
+  if (tid == 0)
   {
-    const int tw = SA_T >> g.sx, th = SA_T >> g.sy;
-    saLoadTileAsync(reinterpret_cast<pel*>(smraw + L.offA(stage, 1)), L.pitchC, S.buf[srcBuf][1], T.x0 >> g.sx, T.y0 >> g.sy, tw, th);
-    saLoadTileAsync(reinterpret_cast<pel*>(smraw + L.offA(stage, 2)), L.pitchC, S.buf[srcBuf][2], T.x0 >> g.sx, T.y0 >> g.sy, tw, th);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic-proxy accesses to the stage buffers are ordered before the TMA writes
+    mbarExpectTx(bar, (uint32_t)(L.lumaBytes + 2 * L.chromaBytes));
+    tmaLoad2D(smraw + L.offA(stage, 0), maps, x0 - SA_HX, y0 - SA_HY, bar);
+    if (g.ncomp > 1)
+    {
+      tmaLoad2D(smraw + L.offA(stage, 1), maps + 1, (x0 >> g.sx) - SA_HX, (y0 >> g.sy) - SA_HY, bar);
+      tmaLoad2D(smraw + L.offA(stage, 2), maps + 2, (x0 >> g.sx) - SA_HX, (y0 >> g.sy) - SA_HY, bar);
+    }
   }
   SaTilePar* par = reinterpret_cast<SaTilePar*>(smraw + L.offPar) + stage;
-  const int tid = threadIdx.x, tcx = T.x0 >> g.ctuLog2, tcy = T.y0 >> g.ctuLog2;
-  if (tid < 27)
+  const int tcx = x0 >> g.ctuLog2, tcy = y0 >> g.ctuLog2;
+  if (tid >= 32 && tid < 59)
   {
-    const int c = tid / 9, k = tid - c * 9, cx = tcx + k % 3 - 1, cy = tcy + k / 3 - 1;
+    const int q = tid - 32, c = q / 9, k = q - c * 9, cx = tcx + k % 3 - 1, cy = tcy + k / 3 - 1;
     if (saoOn && cx >= 0 && cy >= 0 && cx < g.wCtus && cy < g.hCtus && c < g.ncomp) cpAsync16(&par->sao[c][k], &S.sao[(cy * g.wCtus + cx) * 3 + c]);
     else *reinterpret_cast<uint4*>(&par->sao[c][k]) = make_uint4(0, 0, 0, 0);
   }
-  else if (tid == 32)
-  {
-    if (alfOn) cpAsync8(&par->ctl, &S.alfCtu[tcy * g.wCtus + tcx]);
-    else *reinterpret_cast<uint2*>(&par->ctl) = make_uint2(0, 0);
-  }
-  else if (tid >= 64 && tid < 67)
-  {
-    const int c = tid - 64, sxc = c ? g.sx : 0, syc = c ? g.sy : 0;
-    par->geom[c] = SaoGeom{ (T.x0 >> sxc) - SA_HX, (T.y0 >> syc) - SA_HY, g.w >> sxc, g.h >> syc, g.ctuLog2 - sxc, g.ctuLog2 - syc, tcx, tcy,
-                            c ? g.bdC : g.bdL, c ? L.pitchC : SA_P, SA_T >> sxc, 6 - syc };
-  }
+  else if (tid == 59) cpAsync16(&par->ctl, &S.ctuCtl[tcy * g.wCtus + tcx]);
 }
 
-// Persistent kernel: gridDim.x CTAs walk the tiles of slots [firstSlot, firstSlot + numSlots) round robin.
-__global__ void __launch_bounds__(SA_THREADS, 2) k_sao_alf(const SlotDev* __restrict__ slots, int firstSlot, int numSlots, int srcBuf, int dstBuf, Geom g,
-                                                           int tilesX, int tilesY, int doSao, int doAlf)
+// Persistent kernel: gridDim.x CTAs walk the tiles of slots [firstSlot, firstSlot + numSlots) round robin; while a CTA
+// filters tile i, the TMA loads of tile i+1 are in flight (two stages).  maps = tensor maps of the source buffer of the
+// first slot: [slot][3 buffers][3 planes].
+__global__ void __launch_bounds__(SA_THREADS, 2) k_sao_alf(const SlotDev* __restrict__ slots, const CUtensorMap* __restrict__ tmaps, int firstSlot, int numSlots,
+                                                           int srcBuf, int dstBuf, Geom g, int tilesX, int tilesY, SaStep step, int doSao, int doAlf)
 {
-  extern __shared__ __align__(16) unsigned char smraw[];
+  extern __shared__ __align__(128) unsigned char smraw[];
   const SaLayout L = saLayout(g.sx, g.sy, g.ncomp);
   const int tid = threadIdx.x;
-  const int tilesPerPic = tilesX * tilesY, numTiles = tilesPerPic * numSlots;
   uint2 (*cell)[SA_CELLP] = reinterpret_cast<uint2 (*)[SA_CELLP]>(smraw + L.offCell);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + L.offBar);
   const int vbL = g.ctu - 4, ctuMask = g.ctu - 1;
   const int bi = tid >> 4, bj = tid & 15;
-  const int tw = SA_T >> g.sx, thLogC = 6 - g.sy;
+  const int tw = SA_T >> g.sx, th = SA_T >> g.sy, thLogC = 6 - g.sy;
   const int cw = g.w >> g.sx, chh = g.h >> g.sy, ctuH = g.ctu >> g.sy;
   const int vbC = ctuH - 2, maxc = (1 << g.bdC) - 1, half = (1 << g.bdC) >> 1;
   const uint32_t maxcP = dup16(maxc), halfP = dup16(half);
 
-  int t = blockIdx.x, stage = 0;
-  if (t >= numTiles) return;
+  SaWalk cur;
   {
-    const SaTile T = saDecodeTile(t, tilesX, tilesPerPic);
-    const SlotDev& S = slots[firstSlot + T.slot];
-    saPrefetch(smraw, L, 0, S, srcBuf, T, g, doSao && S.saoOn, doAlf && S.alfOn);
+    const int tilesPerPic = tilesX * tilesY, t = blockIdx.x;
+    cur.slot = t / tilesPerPic;
+    const int rem = t - cur.slot * tilesPerPic;
+    cur.ty = rem / tilesX;
+    cur.tx = rem - cur.ty * tilesX;
+  }
+  if (cur.slot >= numSlots) return;
+  if (tid == 0)
+  {
+    mbarInit(&bars[0], 1);
+    mbarInit(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  {
+    const SlotDev& S = slots[firstSlot + cur.slot];
+    saPrefetch(smraw, L, 0, S, tmaps + ((size_t)(firstSlot + cur.slot) * 3 + srcBuf) * 3, cur, g, doSao && S.saoOn);
     cpAsyncCommit();
   }
-  for (; t < numTiles; t += gridDim.x, stage ^= 1)
+  for (uint32_t it = 0; cur.slot < numSlots; it++)
   {
-    const SaTile T = saDecodeTile(t, tilesX, tilesPerPic);
-    const SlotDev& S = slots[firstSlot + T.slot];
-    if (t + (int)gridDim.x < numTiles)
+    const int stage = it & 1;
+    const SlotDev& S = slots[firstSlot + cur.slot];
+    SaWalk nxt = cur;
+    saAdvance(nxt, step, tilesX, tilesY);
+    if (nxt.slot < numSlots)
     {
-      const SaTile Tn = saDecodeTile(t + gridDim.x, tilesX, tilesPerPic);
-      const SlotDev& Sn = slots[firstSlot + Tn.slot];
-      saPrefetch(smraw, L, stage ^ 1, Sn, srcBuf, Tn, g, doSao && Sn.saoOn, doAlf && Sn.alfOn);
+      const SlotDev& Sn = slots[firstSlot + nxt.slot];
+      saPrefetch(smraw, L, stage ^ 1, Sn, tmaps + ((size_t)(firstSlot + nxt.slot) * 3 + srcBuf) * 3, nxt, g, doSao && Sn.saoOn);
     }
     cpAsyncCommit();
     cpAsyncWait<1>();
-    __syncthreads();                                         // tile t and its parameters are in shared memory
+    mbarWait(&bars[stage], (it >> 1) & 1);
+    __syncthreads();                                         // tile and its parameters are in shared memory
 
-    const int x0 = T.x0, y0 = T.y0;
+    const int x0 = cur.tx * SA_T, y0 = cur.ty * SA_T, tcx = x0 >> g.ctuLog2, tcy = y0 >> g.ctuLog2;
     const SaTilePar& par = reinterpret_cast<const SaTilePar*>(smraw + L.offPar)[stage];
-    const AlfCtuDev ctl = par.ctl;
-    const bool alfY = ctl.enY != 0, alfC[2] = { ctl.enCb != 0, ctl.enCr != 0 };
-    const int ccIdc[2] = { ctl.ccCb, ctl.ccCr };
-    pel* const A[3] = { reinterpret_cast<pel*>(smraw + L.offA(stage, 0)), reinterpret_cast<pel*>(smraw + L.offA(stage, 1)),
-                        reinterpret_cast<pel*>(smraw + L.offA(stage, 2)) };
-    pel* B[3] = { reinterpret_cast<pel*>(smraw + L.offB(0)), reinterpret_cast<pel*>(smraw + L.offB(1)), reinterpret_cast<pel*>(smraw + L.offB(2)) };
+    const CtuCtlDev ctl = par.ctl;
+    const bool alfOn = doAlf && S.alfOn, saoOn = doSao && S.saoOn;
+    const bool alfY = alfOn && ctl.enY != 0, alfCb = alfOn && ctl.enCb != 0, alfCr = alfOn && ctl.enCr != 0;
+    const int ccCb = alfOn ? ctl.ccCb : 0, ccCr = alfOn ? ctl.ccCr : 0;
+    const int reach = saoOn ? ctl.saoReach : 0;
+    pel* const A0 = reinterpret_cast<pel*>(smraw + L.offA(stage, 0));
+    pel* const A1 = reinterpret_cast<pel*>(smraw + L.offA(stage, 1));
+    pel* const A2 = reinterpret_cast<pel*>(smraw + L.offA(stage, 2));
+    // tiles on the picture border: replicate the border samples into the zero-filled outside (all later stages rely on it)
+    const bool onBorder = x0 == 0 || y0 == 0 || x0 + SA_T + 8 > g.w || y0 + SA_T + 8 > g.h;
+    if (onBorder)
+    {
+      saReplicateBorder(A0, x0 - SA_HX, y0 - SA_HY, g.w, g.h, SA_P, SA_T, SA_T, 4);
+      if (g.ncomp > 1)
+      {
+        saReplicateBorder(A1, (x0 >> g.sx) - SA_HX, (y0 >> g.sy) - SA_HY, cw, chh, L.pitchC, tw, th, 4);
+        saReplicateBorder(A2, (x0 >> g.sx) - SA_HX, (y0 >> g.sy) - SA_HY, cw, chh, L.pitchC, tw, th, 4);
+      }
+      __syncthreads();
+    }
 
     // ---- phase 1: SAO of all components (tile + 3 where an ALF stage reads the halo) ------------------------------
-    bool saoC[3];
-    int nInt[3], nHalo[3];
-    bool border = false;
-#pragma unroll
-    for (int c = 0; c < 3; c++)
+    // without SAO in reach the (replicate padded) input IS the ALF input
+    const pel* const B0 = (reach & 1) ? reinterpret_cast<pel*>(smraw + L.offB(0)) : A0;
+    const pel* const B1 = (reach & 2) ? reinterpret_cast<pel*>(smraw + L.offB(1)) : A1;
+    const pel* const B2 = (reach & 4) ? reinterpret_cast<pel*>(smraw + L.offB(2)) : A2;
+    if (reach)
     {
-      saoC[c] = false;
-      if (c < g.ncomp)
-      {
-#pragma unroll
-        for (int k = 0; k < 9; k++) saoC[c] |= par.sao[c][k].type != 0;
-      }
-      const bool halo = c == 0 ? (alfY || ccIdc[0] || ccIdc[1]) : alfC[c - 1];
-      nInt[c] = saoC[c] ? saoItemsInterior(par.geom[c]) : 0;
-      nHalo[c] = saoC[c] && halo ? saoItemsHalo(par.geom[c]) : 0;
-      border |= nHalo[c] && saoNeedsBorder(par.geom[c]);
-      if (!saoC[c]) B[c] = A[c];                              // no SAO in reach: the (replicate padded) input IS the ALF input
-    }
-    if (saoC[0] | saoC[1] | saoC[2])
-    {
-      const int e0 = nInt[0], e1 = e0 + nInt[1], e2 = e1 + nInt[2], e3 = e2 + nHalo[0], e4 = e3 + nHalo[1], e5 = e4 + nHalo[2];
+      const bool halo0 = alfY || ccCb || ccCr;
+      const int nI0 = (reach & 1) ? (SA_T / 8) * SA_T : 0, nIC = (tw >> 3) << thLogC;
+      const int nH0 = (reach & 1) && halo0 ? 2 * SA_T + 96 : 0, nHC = 2 * th + 96;
+      const int e0 = nI0, e1 = e0 + ((reach & 2) ? nIC : 0), e2 = e1 + ((reach & 4) ? nIC : 0);
+      const int e3 = e2 + nH0, e4 = e3 + ((reach & 2) && alfCb ? nHC : 0), e5 = e4 + ((reach & 4) && alfCr ? nHC : 0);
       for (int i = tid; i < e5; i += SA_THREADS)
       {
         const bool interior = i < e2;
         const int c = interior ? (i < e0 ? 0 : (i < e1 ? 1 : 2)) : (i < e3 ? 0 : (i < e4 ? 1 : 2));
         const int base = interior ? (c == 0 ? 0 : (c == 1 ? e0 : e1)) : (c == 0 ? e2 : (c == 1 ? e3 : e4));
-        const SaoGeom sg = par.geom[c];
+        const int sxc = c ? g.sx : 0, syc = c ? g.sy : 0;
+        const SaoGeom sg = { (x0 >> sxc) - SA_HX, (y0 >> syc) - SA_HY, g.w >> sxc, g.h >> syc, g.ctuLog2 - sxc, g.ctuLog2 - syc, tcx, tcy,
+                             c ? g.bdC : g.bdL, c ? L.pitchC : SA_P, SA_T >> sxc, 6 - syc };
         pel* bq = reinterpret_cast<pel*>(smraw + L.offB(c));
         const pel* aq = reinterpret_cast<const pel*>(smraw + L.offA(stage, c));
         int r, gc;
@@ -765,19 +762,19 @@ __global__ void __launch_bounds__(SA_THREADS, 2) k_sao_alf(const SlotDev* __rest
         if (interior) ok = saoItemInterior(i - base, sg, r, gc); else ok = saoItemHalo(i - base, sg, r, gc);
         if (ok) saoGroup(bq, aq, r, gc, par.sao[c], sg);
       }
-      if (border)
+      if (onBorder)
       {
+        // replicate border of the SAO output (= UnitBuf::extendBorderPel of the ALF input, AdaptiveLoopFilter.cpp:411)
         __syncthreads();
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-          if (nHalo[c] && saoNeedsBorder(par.geom[c]))
-            saoBorder(B[c], par.geom[c].bx0, par.geom[c].by0, par.geom[c].w, par.geom[c].h, par.geom[c].pitch, par.geom[c].tw, 1 << par.geom[c].thLog);
+        if (nH0) saReplicateBorder(const_cast<pel*>(B0), x0 - SA_HX, y0 - SA_HY, g.w, g.h, SA_P, SA_T, SA_T, 3);
+        if ((reach & 2) && alfCb) saReplicateBorder(const_cast<pel*>(B1), (x0 >> g.sx) - SA_HX, (y0 >> g.sy) - SA_HY, cw, chh, L.pitchC, tw, th, 3);
+        if ((reach & 4) && alfCr) saReplicateBorder(const_cast<pel*>(B2), (x0 >> g.sx) - SA_HX, (y0 >> g.sy) - SA_HY, cw, chh, L.pitchC, tw, th, 3);
       }
       __syncthreads();
     }
 
     // ---- phase 2: Laplacian cells (luma ALF only) -------------------------------------------------------------------
-    const pel* lumaB = B[0];
+    const pel* lumaB = B0;
     const int bx = x0 + 4 * bj, by = y0 + 4 * bi;
     const pel* c0 = &lumaB[(4 * bi + SA_HY) * SA_P + 4 * bj + SA_HX];
     const int yb = by & ctuMask;
@@ -849,11 +846,11 @@ __global__ void __launch_bounds__(SA_THREADS, 2) k_sao_alf(const SlotDev* __rest
       for (int c = 0; c < 2; c++)
       {
         const PlaneDev dstC = S.buf[dstBuf][1 + c];
-        const pel* Bc = c ? B[2] : B[1];
-        const bool fOn = c ? alfC[1] : alfC[0];
-        const int idc = c ? ccIdc[1] : ccIdc[0];
+        const pel* Bc = c ? B2 : B1;
+        const bool fOn = c ? alfCr : alfCb;
+        const int idc = c ? ccCr : ccCb;
         ChromaCoef C;
-        if (fOn) C = chromaCoef(S.alf->chroma[c ? ctl.altCr : ctl.altCb]);
+        if (fOn) C = chromaCoef(&S.alf->chromaTab[c ? ctl.altCr : ctl.altCb]);
         const int16_t* ccg = S.alf->cc[c][idc ? idc - 1 : 0];
         for (int j = tid; j < quads; j += SA_THREADS)
         {
@@ -906,6 +903,7 @@ __global__ void __launch_bounds__(SA_THREADS, 2) k_sao_alf(const SlotDev* __rest
       }
     }
     __syncthreads();                                         // all reads of stage buffers / B / cells are done before they are refilled
+    cur = nxt;
   }
 }
 

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
+#include <cuda.h>
 #include <string>
 #include <vector>
 
@@ -28,7 +29,7 @@ std::string g_createError;
 
 struct SideLayout     // byte offsets inside a slot's side-info block
 {
-  size_t dbfL[2], dbfC[2], sao, alfTab, alfCtu, alf, total;
+  size_t dbfL[2], dbfC[2], sao, alfTab, ctuCtl, alf, total;
   size_t nL, nC[2];
 };
 
@@ -83,6 +84,7 @@ struct vtmgpu_ctx
   std::vector<int> cur;                // buffer index holding the current state of each slot
   int64_t launches = 0;
   int numSms = 0;
+  CUtensorMap* tmapsDev = nullptr;     // [capacity][3 buffers][3 planes]: TMA descriptors of the plane buffers (box = smem tile of k_sao_alf)
 
   int fail(const char* fmt, ...)
   {
@@ -140,6 +142,7 @@ extern "C" void vtmgpu_destroy(vtmgpu_ctx* c)
   if (c->sidePinned) cudaFreeHost(c->sidePinned);
   if (c->slotsPinned) cudaFreeHost(c->slotsPinned);
   if (c->slotsDev) cudaFree(c->slotsDev);
+  if (c->tmapsDev) cudaFree(c->tmapsDev);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   for (auto& e : c->stageEv) if (e) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -184,7 +187,7 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
   for (int d = 0; d < 2; d++) { L.dbfC[d] = off; off = alignUp(off + L.nC[d] * 8, 256); }
   L.sao = off;    off = alignUp(off + (size_t)c->nCtus * 3 * sizeof(SaoDev), 256);
   L.alfTab = off; off = alignUp(off + sizeof(AlfLumaEntry) * VTMGPU_MAX_LUMA_SETS * 25 * 4, 256);
-  L.alfCtu = off; off = alignUp(off + (size_t)c->nCtus * sizeof(AlfCtuDev), 256);
+  L.ctuCtl = off; off = alignUp(off + (size_t)c->nCtus * sizeof(CtuCtlDev), 256);
   L.alf = off;    off = alignUp(off + sizeof(AlfDev), 256);
   L.total = off;
 
@@ -235,9 +238,35 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
     }
     sd.sao = reinterpret_cast<const SaoDev*>(side + L.sao);
     sd.alf = reinterpret_cast<const AlfDev*>(side + L.alf);
-    sd.alfCtu = reinterpret_cast<const AlfCtuDev*>(side + L.alfCtu);
+    sd.ctuCtl = reinterpret_cast<const CtuCtlDev*>(side + L.ctuCtl);
     sd.lumaTab = reinterpret_cast<const AlfLumaEntry*>(side + L.alfTab);
     sd.dbfOn = sd.saoOn = sd.alfOn = 0;
+  }
+  {
+    // TMA descriptors: one per plane buffer; box = the shared-memory tile of k_sao_alf (row pitch incl. padding), zero fill outside
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                 CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres), "cuTensorMapEncodeTiled lookup");
+    if (!fn || qres != cudaDriverEntryPointSuccess) { g_createError = "vtmgpu_create: driver has no cuTensorMapEncodeTiled"; vtmgpu_destroy(c); return -1; }
+    const SaLayout SL = saLayout(g.sx, g.sy, g.ncomp);
+    std::vector<CUtensorMap> maps((size_t)s.capacity * 9);
+    memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
+    for (int sl = 0; sl < s.capacity; sl++)
+      for (int b = 0; b < 3; b++)
+        for (int k = 0; k < g.ncomp; k++)
+        {
+          const PlaneDev& pd = c->slotsPinned[sl].buf[b][k];
+          const cuuint64_t dims[2] = { (cuuint64_t)pd.w, (cuuint64_t)pd.h }, strides[1] = { (cuuint64_t)pd.pitch * 2 };
+          const cuuint32_t box[2] = { (cuuint32_t)(k ? SL.pitchC : SA_P), (cuuint32_t)(k ? SL.rowsC : SA_H) }, es[2] = { 1, 1 };
+          const CUresult r = reinterpret_cast<EncodeFn>(fn)(&maps[((size_t)sl * 3 + b) * 3 + k], CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, pd.p, dims, strides, box, es,
+                                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          if (r != CUDA_SUCCESS) { g_createError = "vtmgpu_create: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"; vtmgpu_destroy(c); return -1; }
+        }
+    CK(cudaMalloc((void**)&c->tmapsDev, maps.size() * sizeof(CUtensorMap)), "tensor maps");
+    CK(cudaMemcpy(c->tmapsDev, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice), "tensor maps upload");
   }
   {
     // the 16 fixed luma filter sets (AdaptiveLoopFilter.cpp:204-289, clip = 1 << bitDepth :500-509) never change: expand and upload once
@@ -436,7 +465,20 @@ extern "C" int vtmgpu_set_sao(vtmgpu_ctx* c, int slot, const vtmgpu_sao_params* 
         d[a * 3 + k] = z;
       }
     sd.saoOn = any;     // SAOProcess returns early when no CTU has SAO on (SampleAdaptiveOffset.cpp:626-637)
+    // reach bits: does any CTU of the 3x3 neighbourhood switch SAO on for the component (the tile kernel skips the stage otherwise)
+    CtuCtlDev* ctl = reinterpret_cast<CtuCtlDev*>(c->pinnedSide(slot) + c->lay.ctuCtl);
+    const int wc = c->g.wCtus, hc = c->g.hCtus;
+    for (int cy = 0; cy < hc; cy++)
+      for (int cx = 0; cx < wc; cx++)
+      {
+        uint8_t reach = 0;
+        for (int ny = std::max(cy - 1, 0); ny <= std::min(cy + 1, hc - 1); ny++)
+          for (int nx = std::max(cx - 1, 0); nx <= std::min(cx + 1, wc - 1); nx++)
+            for (int k = 0; k < 3; k++) reach |= (d[(ny * wc + nx) * 3 + k].type != 0) << k;
+        ctl[cy * wc + cx].saoReach = reach;
+      }
     if (c->pushSide(slot, c->lay.sao, (size_t)c->nCtus * 3 * sizeof(SaoDev))) return -1;
+    if (c->pushSide(slot, c->lay.ctuCtl, (size_t)c->nCtus * sizeof(CtuCtlDev))) return -1;
   }
   return c->pushSlot(slot);
 }
@@ -455,7 +497,7 @@ extern "C" int vtmgpu_set_alf(vtmgpu_ctx* c, int slot, const vtmgpu_alf_params* 
     if (p->num_luma_aps < 0 || p->num_luma_aps > VTMGPU_ALF_MAX_APS) return c->fail("set_alf: bad num_luma_aps");
     const bool chroma = c->g.ncomp > 1;
     AlfDev& A = *reinterpret_cast<AlfDev*>(c->pinnedSide(slot) + c->lay.alf);
-    AlfCtuDev* ctl = reinterpret_cast<AlfCtuDev*>(c->pinnedSide(slot) + c->lay.alfCtu);
+    CtuCtlDev* ctl = reinterpret_cast<CtuCtlDev*>(c->pinnedSide(slot) + c->lay.ctuCtl);
     memset(&A, 0, sizeof(A));
     for (int k = 0; k < 3; k++) A.enabled[k] = p->enabled[k] != 0;
     A.numSets = VTMGPU_ALF_FIXED_SETS + p->num_luma_aps;
@@ -498,6 +540,21 @@ extern "C" int vtmgpu_set_alf(vtmgpu_ctx* c, int slot, const vtmgpu_alf_params* 
           if (ci < 0 || ci > 3) return c->fail("set_alf: bad chroma clip idx");
           A.chroma[a][k] = make_short2(p->chroma_aps->coeff[a][k], (short)clipC[ci]);
         }
+      for (int a = 0; a < numAlts; a++)
+      {
+        AlfChromaEntry& e = A.chromaTab[a];
+        int bias = 64;
+        for (int k = 0; k < 6; k++)
+        {
+          const int co = A.chroma[a][k].x, clp = A.chroma[a][k].y;      // AlfCoeffC is restricted to -127..127 by the parser (VLCReader.cpp:3840)
+          if (co < -128 || co > 127) return c->fail("set_alf: chroma coefficient %d out of range", co);
+          e.coefB[k] = (uint32_t)(co & 0xff) * 0x01000001u;
+          e.clipP1[k] = (uint32_t)((clp + 1) & 0xffff) * 0x10001u;
+          e.clip2[k] = (uint32_t)((2 * clp) & 0xffff) * 0x10001u;
+          bias -= co * 2 * clp;
+        }
+        e.bias = bias;
+      }
     }
     for (int k = 0; k < 2; k++)
     {
@@ -505,10 +562,10 @@ extern "C" int vtmgpu_set_alf(vtmgpu_ctx* c, int slot, const vtmgpu_alf_params* 
       memcpy(A.cc[k], p->ccalf_coeff[k], sizeof(A.cc[k]));
     }
     // per-CTU control
-    memset(ctl, 0, (size_t)n * sizeof(AlfCtuDev));
     for (int a = 0; a < n; a++)
     {
-      AlfCtuDev& r = ctl[a];
+      CtuCtlDev& r = ctl[a];
+      r.enCb = r.enCr = r.altCb = r.altCr = r.ccCb = r.ccCr = r.setIdx = 0;
       r.enY = p->ctu_enable[0] && p->ctu_enable[0][a];
       if (r.enY)
       {
@@ -536,7 +593,7 @@ extern "C" int vtmgpu_set_alf(vtmgpu_ctx* c, int slot, const vtmgpu_alf_params* 
     sd.alfOn = (A.enabled[0] | A.enabled[1] | A.enabled[2]) != 0;    // ALFProcess skips the picture otherwise (AdaptiveLoopFilter.cpp:429)
     sd.alfWide = wide;
     if (p->num_luma_aps && c->pushSide(slot, c->lay.alfTab + sizeof(AlfLumaEntry) * VTMGPU_ALF_FIXED_SETS * 100, sizeof(AlfLumaEntry) * 100 * p->num_luma_aps)) return -1;
-    if (c->pushSide(slot, c->lay.alfCtu, c->lay.total - c->lay.alfCtu)) return -1;
+    if (c->pushSide(slot, c->lay.ctuCtl, c->lay.total - c->lay.ctuCtl)) return -1;
   }
   return c->pushSlot(slot);
 }
@@ -593,9 +650,13 @@ int launchSaoAlf(vtmgpu_ctx* c, int first, int count, int doSao, int doAlf)
   const int smem = saLayout(g.sx, g.sy, g.ncomp).total;
   return forRuns(c, first, count, [&](int s, int n, int src) {
     const int dst = src == 1 ? 2 : 1;
-    // persistent CTAs: two per SM (register limited), each walks the tiles round robin with double-buffered cp.async loads
+    // persistent CTAs: two per SM (register limited), each walks the tiles round robin with double-buffered TMA loads
     const int grid = std::min(tilesX * tilesY * n, 2 * c->numSms);
-    k_sao_alf<<<grid, SA_THREADS, smem, c->stream>>>(c->slotsDev, s, n, src, dst, g, tilesX, tilesY, doSao, doAlf);
+    SaStep st;
+    st.dx = grid % tilesX;
+    st.dy = (grid / tilesX) % tilesY;
+    st.ds = (grid / tilesX) / tilesY;
+    k_sao_alf<<<grid, SA_THREADS, smem, c->stream>>>(c->slotsDev, c->tmapsDev, s, n, src, dst, g, tilesX, tilesY, st, doSao, doAlf);
     c->launches++;
     for (int i = s; i < s + n; i++) c->cur[i] = dst;
     return c->cuda(cudaGetLastError(), "k_sao_alf launch");

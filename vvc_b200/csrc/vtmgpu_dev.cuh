@@ -31,6 +31,14 @@ struct SaoDev
 
 #define VTMGPU_MAX_LUMA_SETS 24
 
+// One chroma filter alternative expanded for the packed 5x5 kernel (see AlfLumaEntry below)
+struct AlfChromaEntry
+{
+  uint32_t coefB[6], clipP1[6], clip2[6];
+  int32_t  bias;
+  int32_t  pad;
+};
+
 // ALF data of one picture
 struct AlfDev
 {
@@ -41,6 +49,7 @@ struct AlfDev
   int32_t pad;
   short2  luma[VTMGPU_MAX_LUMA_SETS][25][12];        // {coeff, clip} per set, class, tap (transpose 0 order)
   short2  chroma[8][6];                              // {coeff, clip} per alternative, tap
+  AlfChromaEntry chromaTab[8];                       // the same, expanded into the operands of the packed 5x5 kernel
   int16_t cc[2][4][8];                               // CC-ALF coefficients (7 used)
 };
 
@@ -55,13 +64,17 @@ struct AlfLumaEntry
   int32_t  pad[3];
 };
 
-// ALF control of one CTU (Picture::getAlfCtuEnableFlag / getAlfCtbFilterIndex / getAlfCtuAlternativeData, m_ccAlfFilterControl)
-struct AlfCtuDev
+// Per-CTU control record (16 bytes, one 128-bit load per tile): ALF control (Picture::getAlfCtuEnableFlag /
+// getAlfCtbFilterIndex / getAlfCtuAlternativeData, m_ccAlfFilterControl) written by vtmgpu_set_alf and the SAO reach
+// bits written by vtmgpu_set_sao.
+struct CtuCtlDev
 {
-  uint8_t enY, enCb, enCr;       // CTU enable flags
+  uint8_t enY, enCb, enCr;       // ALF CTU enable flags
   uint8_t altCb, altCr;          // chroma filter alternative
   uint8_t ccCb, ccCr;            // CC-ALF filter idc (0 = off)
   uint8_t setIdx;                // luma filter set: < 16 fixed, else APS
+  uint8_t saoReach;              // bit c: a CTU of the 3x3 neighbourhood (incl. this one) has SAO on for component c
+  uint8_t pad[7];
 };
 
 struct SlotDev
@@ -71,7 +84,7 @@ struct SlotDev
   const uint64_t* dbfC[2];
   const SaoDev*   sao;           // [ctus][3]                     (NULL: stage off)
   const AlfDev*   alf;           //                               (NULL: stage off)
-  const AlfCtuDev* alfCtu;       // [ctus]
+  const CtuCtlDev* ctuCtl;       // [ctus]
   const AlfLumaEntry* lumaTab;   // [sets][25 classes][4 transposes]
   int32_t dbfOn, saoOn, alfOn;   // alfOn: parameters set AND the slice enables ALF for at least one component
   int32_t alfWide;               // a luma coefficient does not fit the s8 operand of IDP.2A: generic path
