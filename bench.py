@@ -32,8 +32,8 @@ sys.path.insert(0, ROOT)
 
 W4K, H4K = 3840, 2160
 B_ALG_CHAIN = 6.5          # algorithmic bytes per luma pixel of the whole chain at 4:2:0 (SURVEY.md 8d / BASELINE.md 3)
-B_ALG_DBF = 6.5            # k_deblock : read 3 + write 3 + 0.5 segment records
-B_ALG_SAOALF = 6.0         # k_sao_alf : read 3 + write 3 (CTU parameters negligible)
+B_ALG_DBF = 6.5            # k_dbf_sao : read 3 + write 3 + 0.5 segment records
+B_ALG_SAOALF = 6.0         # k_alf     : read 3 + write 3 (CTU parameters negligible)
 CAP_DIR = os.path.join(ROOT, "data", "captures", "ra_2160p")
 
 
@@ -264,9 +264,9 @@ def main():
     dom = 1 if k_ms[1] >= k_ms[0] else 0
     alg_bytes = (B_ALG_SAOALF if dom else B_ALG_DBF) * px_per_pic * B
     achieved = alg_bytes / (k_ms[dom] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_sao_alf" if dom else "k_deblock", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_alf" if dom else "k_dbf_sao", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
-                "kernel_ms": {"k_deblock": round(k_ms[0], 4), "k_sao_alf": round(k_ms[1], 4)},
+                "kernel_ms": {"k_dbf_sao": round(k_ms[0], 4), "k_alf": round(k_ms[1], 4)},
                 "chain_achieved": round(B_ALG_CHAIN * px_per_pic * B / (ms_total / args.steps * 1e-3) / 1e9, 1),
                 "chain_frac": round(B_ALG_CHAIN * px_per_pic * B / (ms_total / args.steps * 1e-3) / 1e9 / peak, 4)}
     tr = os.path.join(ROOT, "profiles", "traffic.json")

@@ -224,8 +224,8 @@ int vtmgpu_sao_reconstruct(vtmgpu_sao_ctu* ctu, int num_ctus, int width_in_ctus,
 int vtmgpu_deblock(vtmgpu_ctx* ctx, int first, int count);   /* loopFilterPic                              */
 int vtmgpu_sao    (vtmgpu_ctx* ctx, int first, int count);   /* SAOProcess (no-op where SAO is off)        */
 int vtmgpu_alf    (vtmgpu_ctx* ctx, int first, int count);   /* ALFProcess                                 */
-int vtmgpu_sao_alf(vtmgpu_ctx* ctx, int first, int count);   /* SAOProcess + ALFProcess in one fused pass  */
-/* whole chain DBF -> SAO -> ALF with SAO fused into the ALF pass; same result as the three calls above */
+int vtmgpu_sao_alf(vtmgpu_ctx* ctx, int first, int count);   /* SAOProcess + ALFProcess back to back, one sync */
+/* whole chain DBF -> SAO -> ALF in two kernels (deblocking + SAO, ALF + CC-ALF); same result as the three calls above */
 int vtmgpu_filter (vtmgpu_ctx* ctx, int first, int count);
 
 /* replay/benchmark support: enqueue the whole chain on the ctx stream without synchronising; timing by
@@ -238,7 +238,7 @@ int vtmgpu_timer_stop (vtmgpu_ctx* ctx, float* ms);      /* records + synchronis
 int vtmgpu_rewind(vtmgpu_ctx* ctx, int first, int count);
 /* number of kernel launches issued by this ctx so far (bench.py "gpu_launches") */
 int64_t vtmgpu_launch_count(const vtmgpu_ctx* ctx);
-/* per-stage device time of the last vtmgpu_filter* call when profiling was enabled (ms; 0 = dbf,1 = sao+alf) */
+/* per-stage device time of the last vtmgpu_filter* call when profiling was enabled (ms; 0 = deblocking + SAO kernel, 1 = ALF kernel) */
 int vtmgpu_set_profiling(vtmgpu_ctx* ctx, int on);
 int vtmgpu_stage_ms(vtmgpu_ctx* ctx, float ms[4]);
 

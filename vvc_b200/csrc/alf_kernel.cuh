@@ -1,30 +1,30 @@
-// saoalf_kernel.cuh -- SAO + ALF + CC-ALF in ONE pass over the deblocked picture (sm_100a).
+// alf_kernel.cuh -- ALF + CC-ALF over the SAO output picture (sm_100a).
 //
-//   SampleAdaptiveOffset::SAOProcess  (SampleAdaptiveOffset.cpp:618, offsetBlock :293-547)
 //   AdaptiveLoopFilter::ALFProcess    (AdaptiveLoopFilter.cpp:393; deriveClassificationBlk :873-1082,
 //                                      filterBlk :1084-1324, filterBlkCcAlf :1327-1416)
 //
-// One CTA owns a 64x64 luma tile and the collocated chroma tiles.  The reference makes two whole-picture temp copies
-// (SAO input, ALF input incl. 3-sample replicate border); here each plane is read ONCE from HBM into shared memory
-// (tile + halo, 8-sample aligned 128-bit loads, coordinates clamped = replicate border), SAO is applied in shared
-// memory (tile + 3), the 4x4 Laplacian classification and the diamond filters read that SAO output, CC-ALF reads the
-// SAO-output luma tile that is still resident, and each plane is written ONCE.
+// Persistent CTAs walk the 64x64 luma tiles (+ collocated chroma tiles) of a batch of pictures.  The reference copies the
+// whole picture and pads it by 3 samples (:408-411); here the three planes of a tile arrive by TMA (tile + halo, zero
+// filled outside the picture, border samples replicated in shared memory for picture-border tiles), double buffered so
+// that the loads of tile i+1 fly while tile i is filtered; the 4x4 Laplacian classification and the diamond filters read
+// shared memory, CC-ALF reads the luma tile that is still resident, and each plane is written ONCE.
 //
 // The chain is instruction-issue bound on B200, so all sample arithmetic runs TWO SAMPLES PER
 // 32-BIT REGISTER on the native packed 16-bit integer instructions of sm_100a:
 //   VIADD.16x2            packed add                      (__vadd2)
 //   VIADDMNMX.S16x2.RELU  max(min(a+b, c), 0) per lane    (__viaddmin_s16x2_relu): one instruction = subtract + clamp
 //   IDP.2A                s16 x s8 dot product into s32   (__dp2a_lo / __dp2a_hi): the ALF multiply-accumulate
-//   PRMT                  byte permute: 16-bit lane shuffles and the SAO offset look-up table
+//   PRMT / SHF            16-bit lane shuffles
 // A filter tap pair costs 4 ALU-pipe + 2 FMA-pipe instructions per two pixels (scalar code: ~14 per two pixels).
 // Rows that touch an ALF virtual boundary (2 of 32 block rows per CTU) and non-4:2:0 CC-ALF use the generic scalar
-// routines at the end of this file; they follow the reference line by line.
+// routines in this file; they follow the reference line by line.
 //
 // Per luma pixel algorithmic HBM bytes at 4:2:0: read 3, write 3 (+ CTU params, negligible).
 #pragma once
 
 #include <cuda.h>
 
+#include "packed16.cuh"
 #include "vtmgpu_dev.cuh"
 #include "vtmgpu.h"
 
@@ -44,35 +44,17 @@ __constant__ int8_t c_perm7[4][12] = { { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11 },
                                        { 0, 3, 2, 1, 8, 7, 6, 5, 4, 9, 10, 11 }, { 9, 8, 10, 4, 3, 7, 11, 5, 1, 0, 2, 6 } };
 
 // Shared memory of one CTA (dynamic; offsets in bytes).  Input tiles are double buffered: while a CTA filters tile i the
-// cp.async copies of tile i+1 are in flight.
-//   A[stage][comp]  input tile + halo (deblocked samples, replicate padded at the picture border)
-//   B[comp]         SAO output of the tile + 3 (stays resident: ALF input, CC-ALF luma source)
+// TMA copies of tile i+1 are in flight.
+//   A[stage][comp]  input tile + halo (SAO output samples; replicate padded at the picture border by the CTA)
 //   cell            Laplacian sums of the 2x2 cells: .x = V | H << 16, .y = D0 | D1 << 16
-//   par[stage]      SAO parameters of the 3x3 CTU neighbourhood per component + the ALF control record of the CTU
-struct SaoGeom
-{
-  int bx0, by0;          // plane coordinates of smem position (0,0)
-  int w, h;              // plane size
-  int cwLog, chLog;      // log2 CTU size in this plane
-  int tcx, tcy;          // CTU of the tile
-  int bd;
-  int pitch;             // smem pitch (samples)
-  int tw, thLog;         // tile size of this component (th = 1 << thLog)
-};
-
-struct SaTilePar
-{
-  SaoDev    sao[3][9];
-  CtuCtlDev ctl;
-};
-
+//   ctl[stage]      control record of the tile's CTU
+//   bar[stage]      mbarriers the TMA loads complete on
 struct SaLayout
 {
   int pitchC, rowsC;               // chroma tile buffers: pitch in samples, rows
   int lumaBytes, chromaBytes, offCell, offPar, offBar, total;
   __host__ __device__ int comp(int c) const { return c ? lumaBytes + (c - 1) * chromaBytes : 0; }
   __host__ __device__ int offA(int stage, int c) const { return stage * (lumaBytes + 2 * chromaBytes) + comp(c); }
-  __host__ __device__ int offB(int c) const { return 2 * (lumaBytes + 2 * chromaBytes) + comp(c); }
 };
 
 // all tile buffer sizes are multiples of 128 bytes (TMA destination alignment)
@@ -84,25 +66,12 @@ __host__ __device__ inline SaLayout saLayout(int sx, int sy, int ncomp)
   L.rowsC = th + 2 * SA_HY;
   L.lumaBytes = SA_H * SA_P * 2;
   L.chromaBytes = ncomp > 1 ? L.rowsC * L.pitchC * 2 : 0;
-  L.offCell = 3 * (L.lumaBytes + 2 * L.chromaBytes);
+  L.offCell = 2 * (L.lumaBytes + 2 * L.chromaBytes);
   L.offPar = L.offCell + SA_CELLS * SA_CELLP * 8;
-  L.offBar = L.offPar + 2 * (int)sizeof(SaTilePar);
+  L.offBar = L.offPar + 2 * (int)sizeof(CtuCtlDev);
   L.total = L.offBar + 16;
   return L;
 }
-
-// ---- packed 16x2 helpers ----------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
-{
-  uint32_t d;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(s));
-  return d;
-}
-__device__ __forceinline__ uint32_t dup16(int v) { return (uint32_t)(v & 0xffff) * 0x10001u; }
-// (hi lane of lo, lo lane of hi): the pair that starts one sample after lo
-__device__ __forceinline__ uint32_t mid16(uint32_t lo, uint32_t hi) { return __funnelshift_r(lo, hi, 16); }
-// max(min(a + b, c), 0) per signed 16-bit lane
-__device__ __forceinline__ uint32_t addClamp0(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_s16x2_relu(a, b, c); }
 
 // ---- asynchronous tile load: TMA (cp.async.bulk.tensor) completing on an mbarrier ------------------------------------
 __device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -138,187 +107,28 @@ __device__ __forceinline__ void tmaLoad2D(void* dst, const CUtensorMap* map, int
 }
 
 // TMA fills positions outside the picture with zeros; the filters want the border samples replicated
-// (rows / columns of tile +- 4 that lie outside take the value of the clamped position)
+// (rows / columns of tile +- margin that lie outside take the value of the clamped position)
 __device__ __noinline__ void saReplicateBorder(pel* s, int bx0, int by0, int w, int h, int pitch, int tw, int th, int margin)
 {
   const int xl = bx0 + SA_HX - margin, yt = by0 + SA_HY - margin;
   const int cols = tw + 2 * margin, rows = th + 2 * margin;
+  const int nl = max(0, -xl), cr = min(cols, max(0, w - xl));          // columns [0,nl) and [cr,cols) of the region are outside
   for (int rr = threadIdx.x >> 5; rr < rows; rr += SA_THREADS / 32)
   {
     const int py = yt + rr, sy_ = min(max(py, 0), h - 1);
-    const bool rowOut = py != sy_;
-    for (int cc = threadIdx.x & 31; cc < cols; cc += 32)
+    const pel* srow = s + (sy_ - by0) * pitch - bx0;
+    pel* drow = s + (py - by0) * pitch - bx0;
+    if (py != sy_)
     {
-      const int px = xl + cc, sx_ = min(max(px, 0), w - 1);
-      if (rowOut || px != sx_) s[(py - by0) * pitch + px - bx0] = s[(sy_ - by0) * pitch + sx_ - bx0];
-    }
-  }
-}
-
-// ---- SAO ----------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool saoCtuAvail(uint32_t avail, int rx, int ry)
-{
-  if ((rx | ry) == 0) return true;
-  const int bit = ry == 0 ? (rx < 0 ? 0x01 : 0x02) : (ry < 0 ? (rx == 0 ? 0x04 : (rx < 0 ? 0x10 : 0x20)) : (rx == 0 ? 0x08 : (rx < 0 ? 0x40 : 0x80)));
-  return (avail & bit) != 0;
-}
-
-// lanes of the 8-sample group at (x,y) that edge-offset class (dxa,dya) must leave untouched: a neighbour outside the
-// picture or in a CTU that is not available (offsetBlock start/end and first/last line rules, SampleAdaptiveOffset.cpp
-// :311-312,:340-341,:398-399,:444-445,:476-477,:514-515 with deriveLoopFilterBoundaryAvailibility :668)
-__device__ __noinline__ uint32_t saoSkipLanesSlow(int x, int y, int dxa, int dya, uint32_t avail, int w, int h, int cwLog, int chLog)
-{
-  const int cx = x >> cwLog, cy = y >> chLog, last = min(7, w - 1 - x);
-  uint32_t m = 0;
-#pragma unroll
-  for (int k = 0; k < 2; k++)
-  {
-    const int ddx = k ? -dxa : dxa, ddy = k ? -dya : dya;
-    const int ny = y + ddy;
-    if (ny < 0 || ny >= h) { m = 0xff; continue; }
-    const int ry = (ny >> chLog) - cy;
-    uint32_t mm = saoCtuAvail(avail, 0, ry) ? 0u : 0xffu;
-    if (ddx < 0)
-    {
-      const bool av = x > 0 && saoCtuAvail(avail, ((x - 1) >> cwLog) - cx, ry);
-      mm = (mm & ~1u) | (av ? 0u : 1u);
-    }
-    if (ddx > 0)
-    {
-      const int nx = x + last + 1;
-      const bool av = nx < w && saoCtuAvail(avail, (nx >> cwLog) - cx, ry);
-      mm = (mm & ~(1u << last)) | (av ? 0u : (1u << last));
-    }
-    m |= mm;
-  }
-  return m;
-}
-
-__device__ __forceinline__ uint32_t saoSkipLanes(int x, int y, int dxa, int dya, uint32_t avail, const SaoGeom& g)
-{
-  const int cwm = (1 << g.cwLog) - 1, chm = (1 << g.chLog) - 1;
-  if ((y & chm) != 0 && ((y + 1) & chm) != 0 && y + 1 < g.h && (x & cwm) != 0 && ((x + 8) & cwm) != 0 && x + 8 < g.w) return 0;
-  if (avail == 0xffu && y > 0 && y + 1 < g.h && x > 0 && x + 8 < g.w) return 0;       // all 8 neighbour CTUs usable, not on the picture border
-  return saoSkipLanesSlow(x, y, dxa, dya, avail, g.w, g.h, g.cwLog, g.chLog);
-}
-
-// the 8 samples at horizontal offset DX from the group at base, as 4 packed registers
-template <int DX> __device__ __forceinline__ uint4 saoNeighbours(const pel* base)
-{
-  const uint4 q = *reinterpret_cast<const uint4*>(base);
-  if (DX == 0) return q;
-  if (DX < 0)
-  {
-    const uint32_t l = *reinterpret_cast<const uint32_t*>(base - 2);
-    return make_uint4(mid16(l, q.x), mid16(q.x, q.y), mid16(q.y, q.z), mid16(q.z, q.w));
-  }
-  const uint32_t r = *reinterpret_cast<const uint32_t*>(base + 8);
-  return make_uint4(mid16(q.x, q.y), mid16(q.y, q.z), mid16(q.z, q.w), mid16(q.w, r));
-}
-
-// offset look-up for two lanes: k = packed indices 0..4, lut = 5 signed bytes (lutHi holds byte 4); returns packed s16
-__device__ __forceinline__ uint32_t saoLut(uint32_t k, uint32_t lutLo, uint32_t lutHi)
-{
-  const uint32_t sel = k * 0x11u + 0x00800080u;             // per lane: low nibble k, high nibble k + 8 (= sign replicate)
-  return prmt(lutLo, lutHi, prmt(sel, 0u, 0x4420u));
-}
-
-template <int DXA, int DYA> __device__ __forceinline__ uint4 saoEdge(const pel* ap, int pitch, uint4 v, uint32_t lutLo, uint32_t lutHi, uint32_t maxvP)
-{
-  const uint4 na = saoNeighbours<DXA>(ap + DYA * pitch), nb = saoNeighbours<-DXA>(ap - DYA * pitch);
-  const uint32_t vv[4] = { v.x, v.y, v.z, v.w }, aa[4] = { na.x, na.y, na.z, na.w }, bb[4] = { nb.x, nb.y, nb.z, nb.w };
-  uint32_t o[4];
-#pragma unroll
-  for (int j = 0; j < 4; j++)
-  {
-    const uint32_t c1 = __vadd2(~vv[j], 0x00020002u);                           // 1 - v
-    const uint32_t k = addClamp0(aa[j], c1, 0x00020002u) + addClamp0(bb[j], c1, 0x00020002u);   // 2 + sgn(a-v) + sgn(b-v)
-    o[j] = addClamp0(vv[j], saoLut(k, lutLo, lutHi), maxvP);
-  }
-  return make_uint4(o[0], o[1], o[2], o[3]);
-}
-
-__device__ __forceinline__ uint32_t laneMask2(uint32_t bits) { return ((bits & 1u) ? 0xffffu : 0u) | ((bits & 2u) ? 0xffff0000u : 0u); }
-
-// SAO of the 8-sample group at smem row r, group gcol (inside the picture); offsetBlock, SampleAdaptiveOffset.cpp:293-547
-__device__ __forceinline__ void saoGroup(pel* b, const pel* a, int r, int gcol, const SaoDev* nb, const SaoGeom& g)
-{
-  const int x = g.bx0 + 8 * gcol, y = g.by0 + r;
-  const pel* ap = a + r * g.pitch + 8 * gcol;
-  uint4 v = *reinterpret_cast<const uint4*>(ap);
-  const SaoDev& P = nb[((y >> g.chLog) - g.tcy + 1) * 3 + (x >> g.cwLog) - g.tcx + 1];
-  const int type = P.type;
-  if (type != 0)
-  {
-    const uint32_t maxvP = dup16((1 << g.bd) - 1);
-    const uint4 pq = *reinterpret_cast<const uint4*>(&P);                         // .y = off0 | off1 << 16, .z = off2 | off3 << 16, .w = off4
-    if (type == 5)
-    {
-      // band offset: k = (band - first band) & 31 ; bands k = 0..3 carry an offset (:528-541)
-      const uint32_t lutLo = prmt(pq.y, pq.z, 0x6420u);
-      const uint32_t nstart = dup16(-(int)P.band);
-      const int sh = g.bd - 5;
-      uint32_t vv[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-      for (int j = 0; j < 4; j++)
-      {
-        const uint32_t band = (vv[j] >> sh) & 0x001f001fu;
-        const uint32_t k = __vminu2(__vadd2(band, nstart) & 0x001f001fu, 0x00040004u);
-        vv[j] = addClamp0(vv[j], saoLut(k, lutLo, 0u), maxvP);
-      }
-      v = make_uint4(vv[0], vv[1], vv[2], vv[3]);
+      for (int cc = threadIdx.x & 31; cc < cols; cc += 32) { const int px = xl + cc; drow[px] = srow[min(max(px, 0), w - 1)]; }
     }
     else
     {
-      // edge offset: index k = 2 - edgeType  ->  look-up table holds the offsets in reverse order: off[4], off[3], off[2], off[1] | off[0]
-      const uint32_t lutLo = (prmt(pq.y, pq.z, 0x2460u) & 0xffffff00u) | (pq.w & 0xffu);
-      const uint32_t lutHi = pq.y & 0xffu;
-      uint4 o;
-      int dxa, dya;
-      if (type == 1)      { o = saoEdge<-1, 0>(ap, g.pitch, v, lutLo, lutHi, maxvP);  dxa = -1; dya = 0; }
-      else if (type == 2) { o = saoEdge<0, -1>(ap, g.pitch, v, lutLo, lutHi, maxvP);  dxa = 0;  dya = -1; }
-      else if (type == 3) { o = saoEdge<-1, -1>(ap, g.pitch, v, lutLo, lutHi, maxvP); dxa = -1; dya = -1; }
-      else                { o = saoEdge<1, -1>(ap, g.pitch, v, lutLo, lutHi, maxvP);  dxa = 1;  dya = -1; }
-      const uint32_t skip = saoSkipLanes(x, y, dxa, dya, P.avail, g);
-      if (skip)
-      {
-        const uint32_t m0 = laneMask2(skip), m1 = laneMask2(skip >> 2), m2 = laneMask2(skip >> 4), m3 = laneMask2(skip >> 6);
-        o.x = (o.x & ~m0) | (v.x & m0); o.y = (o.y & ~m1) | (v.y & m1); o.z = (o.z & ~m2) | (v.z & m2); o.w = (o.w & ~m3) | (v.w & m3);
-      }
-      v = o;
+      const int lane = threadIdx.x & 31;
+      if (lane < nl) drow[xl + lane] = srow[0];
+      for (int cc = cr + lane; cc < cols; cc += 32) drow[xl + cc] = srow[w - 1];
     }
   }
-  *reinterpret_cast<uint4*>(b + r * g.pitch + 8 * gcol) = v;
-}
-
-// Work items of the SAO phase of one component: 8-sample groups.  Item classes (all sizes are powers of two or padded
-// to 16 so that the decode needs no division):
-//   interior   th x gin groups, column-major (keeps 128-bit smem accesses conflict free); one CTU => one parameter set
-//   sides      the halo group left and right of every tile row            (only when an ALF stage reads the halo)
-//   top/bottom 3 halo rows above and below, 16 group slots per row        (                "                   )
-__device__ __forceinline__ int saoItemsInterior(const SaoGeom& g) { return (g.tw >> 3) << g.thLog; }
-__device__ __forceinline__ int saoItemsHalo(const SaoGeom& g) { return (2 << g.thLog) + 6 * 16; }
-
-__device__ __forceinline__ bool saoItemInterior(int i, const SaoGeom& g, int& r, int& gc)
-{
-  gc = 1 + (i >> g.thLog);
-  r = SA_HY + (i & ((1 << g.thLog) - 1));
-  return g.by0 + r < g.h && g.bx0 + 8 * gc < g.w;
-}
-
-__device__ __forceinline__ bool saoItemHalo(int i, const SaoGeom& g, int& r, int& gc)
-{
-  const int th = 1 << g.thLog, gin = g.tw >> 3;
-  if (i < 2 * th) { gc = i < th ? 0 : gin + 1; r = SA_HY + (i & (th - 1)); }
-  else
-  {
-    const int j = i - 2 * th, k = j >> 4;
-    gc = j & 15;
-    r = k < 3 ? SA_HY - 3 + k : SA_HY + th + (k - 3);
-    if (gc > gin + 1) return false;
-  }
-  const int y = g.by0 + r, x = g.bx0 + 8 * gc;
-  return y >= 0 && y < g.h && x >= 0 && x < g.w;
 }
 
 // ---- ALF: generic scalar routines (virtual-boundary rows, halo cells, wide coefficients, non-4:2:0 CC-ALF) ----------
@@ -628,10 +438,9 @@ __device__ __forceinline__ void saAdvance(SaWalk& p, const SaStep& st, int tiles
   p.slot += st.ds;
 }
 
-// issues the asynchronous loads of one tile into `stage`: three TMA boxes (one thread) + SAO / control parameters of the
-// CTU neighbourhood (cp.async, 28 threads)
+// issues the asynchronous loads of one tile into `stage`: three TMA boxes (one thread) + the control record of its CTU
 __device__ __forceinline__ void saPrefetch(unsigned char* smraw, const SaLayout& L, int stage, const SlotDev& S, const CUtensorMap* maps, const SaWalk& p,
-                                           const Geom& g, bool saoOn)
+                                           const Geom& g)
 {
   const int tid = threadIdx.x, x0 = p.tx * SA_T, y0 = p.ty * SA_T;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smraw + L.offBar) + stage;
@@ -646,22 +455,14 @@ __device__ __forceinline__ void saPrefetch(unsigned char* smraw, const SaLayout&
       tmaLoad2D(smraw + L.offA(stage, 2), maps + 2, (x0 >> g.sx) - SA_HX, (y0 >> g.sy) - SA_HY, bar);
     }
   }
-  SaTilePar* par = reinterpret_cast<SaTilePar*>(smraw + L.offPar) + stage;
-  const int tcx = x0 >> g.ctuLog2, tcy = y0 >> g.ctuLog2;
-  if (tid >= 32 && tid < 59)
-  {
-    const int q = tid - 32, c = q / 9, k = q - c * 9, cx = tcx + k % 3 - 1, cy = tcy + k / 3 - 1;
-    if (saoOn && cx >= 0 && cy >= 0 && cx < g.wCtus && cy < g.hCtus && c < g.ncomp) cpAsync16(&par->sao[c][k], &S.sao[(cy * g.wCtus + cx) * 3 + c]);
-    else *reinterpret_cast<uint4*>(&par->sao[c][k]) = make_uint4(0, 0, 0, 0);
-  }
-  else if (tid == 59) cpAsync16(&par->ctl, &S.ctuCtl[tcy * g.wCtus + tcx]);
+  if (tid == 32) cpAsync16(reinterpret_cast<CtuCtlDev*>(smraw + L.offPar) + stage, &S.ctuCtl[(y0 >> g.ctuLog2) * g.wCtus + (x0 >> g.ctuLog2)]);
 }
 
 // Persistent kernel: gridDim.x CTAs walk the tiles of slots [firstSlot, firstSlot + numSlots) round robin; while a CTA
 // filters tile i, the TMA loads of tile i+1 are in flight (two stages).  maps = tensor maps of the source buffer of the
 // first slot: [slot][3 buffers][3 planes].
-__global__ void __launch_bounds__(SA_THREADS, 2) k_sao_alf(const SlotDev* __restrict__ slots, const CUtensorMap* __restrict__ tmaps, int firstSlot, int numSlots,
-                                                           int srcBuf, int dstBuf, Geom g, int tilesX, int tilesY, SaStep step, int doSao, int doAlf)
+__global__ void __launch_bounds__(SA_THREADS, 2) k_alf(const SlotDev* __restrict__ slots, const CUtensorMap* __restrict__ tmaps, int firstSlot, int numSlots,
+                                                           int srcBuf, int dstBuf, Geom g, int tilesX, int tilesY, SaStep step, int dbg)
 {
   extern __shared__ __align__(128) unsigned char smraw[];
   const SaLayout L = saLayout(g.sx, g.sy, g.ncomp);
@@ -693,7 +494,7 @@ __global__ void __launch_bounds__(SA_THREADS, 2) k_sao_alf(const SlotDev* __rest
   __syncthreads();
   {
     const SlotDev& S = slots[firstSlot + cur.slot];
-    saPrefetch(smraw, L, 0, S, tmaps + ((size_t)(firstSlot + cur.slot) * 3 + srcBuf) * 3, cur, g, doSao && S.saoOn);
+    saPrefetch(smraw, L, 0, S, tmaps + ((size_t)(firstSlot + cur.slot) * 3 + srcBuf) * 3, cur, g);
     cpAsyncCommit();
   }
   for (uint32_t it = 0; cur.slot < numSlots; it++)
@@ -705,80 +506,41 @@ __global__ void __launch_bounds__(SA_THREADS, 2) k_sao_alf(const SlotDev* __rest
     if (nxt.slot < numSlots)
     {
       const SlotDev& Sn = slots[firstSlot + nxt.slot];
-      saPrefetch(smraw, L, stage ^ 1, Sn, tmaps + ((size_t)(firstSlot + nxt.slot) * 3 + srcBuf) * 3, nxt, g, doSao && Sn.saoOn);
+      saPrefetch(smraw, L, stage ^ 1, Sn, tmaps + ((size_t)(firstSlot + nxt.slot) * 3 + srcBuf) * 3, nxt, g);
     }
     cpAsyncCommit();
     cpAsyncWait<1>();
     mbarWait(&bars[stage], (it >> 1) & 1);
     __syncthreads();                                         // tile and its parameters are in shared memory
 
-    const int x0 = cur.tx * SA_T, y0 = cur.ty * SA_T, tcx = x0 >> g.ctuLog2, tcy = y0 >> g.ctuLog2;
-    const SaTilePar& par = reinterpret_cast<const SaTilePar*>(smraw + L.offPar)[stage];
-    const CtuCtlDev ctl = par.ctl;
-    const bool alfOn = doAlf && S.alfOn, saoOn = doSao && S.saoOn;
-    const bool alfY = alfOn && ctl.enY != 0, alfCb = alfOn && ctl.enCb != 0, alfCr = alfOn && ctl.enCr != 0;
+    const int x0 = cur.tx * SA_T, y0 = cur.ty * SA_T;
+    const CtuCtlDev ctl = reinterpret_cast<const CtuCtlDev*>(smraw + L.offPar)[stage];
+    const bool alfOn = S.alfOn != 0;
+    const bool alfY = alfOn && ctl.enY != 0 && !(dbg & 8), alfCb = alfOn && ctl.enCb != 0, alfCr = alfOn && ctl.enCr != 0;
     const int ccCb = alfOn ? ctl.ccCb : 0, ccCr = alfOn ? ctl.ccCr : 0;
-    const int reach = saoOn ? ctl.saoReach : 0;
     pel* const A0 = reinterpret_cast<pel*>(smraw + L.offA(stage, 0));
     pel* const A1 = reinterpret_cast<pel*>(smraw + L.offA(stage, 1));
     pel* const A2 = reinterpret_cast<pel*>(smraw + L.offA(stage, 2));
-    // tiles on the picture border: replicate the border samples into the zero-filled outside (all later stages rely on it)
+    // tiles on the picture border: replicate the border samples into the zero-filled outside
+    // (= UnitBuf::extendBorderPel of the ALF input, AdaptiveLoopFilter.cpp:411)
     const bool onBorder = x0 == 0 || y0 == 0 || x0 + SA_T + 8 > g.w || y0 + SA_T + 8 > g.h;
     if (onBorder)
     {
-      saReplicateBorder(A0, x0 - SA_HX, y0 - SA_HY, g.w, g.h, SA_P, SA_T, SA_T, 4);
-      if (g.ncomp > 1)
-      {
-        saReplicateBorder(A1, (x0 >> g.sx) - SA_HX, (y0 >> g.sy) - SA_HY, cw, chh, L.pitchC, tw, th, 4);
-        saReplicateBorder(A2, (x0 >> g.sx) - SA_HX, (y0 >> g.sy) - SA_HY, cw, chh, L.pitchC, tw, th, 4);
-      }
+      if (alfY || ccCb || ccCr) saReplicateBorder(A0, x0 - SA_HX, y0 - SA_HY, g.w, g.h, SA_P, SA_T, SA_T, 3);
+      if (alfCb) saReplicateBorder(A1, (x0 >> g.sx) - SA_HX, (y0 >> g.sy) - SA_HY, cw, chh, L.pitchC, tw, th, 3);
+      if (alfCr) saReplicateBorder(A2, (x0 >> g.sx) - SA_HX, (y0 >> g.sy) - SA_HY, cw, chh, L.pitchC, tw, th, 3);
       __syncthreads();
     }
+    const pel* const B0 = A0;
+    const pel* const B1 = A1;
+    const pel* const B2 = A2;
 
-    // ---- phase 1: SAO of all components (tile + 3 where an ALF stage reads the halo) ------------------------------
-    // without SAO in reach the (replicate padded) input IS the ALF input
-    const pel* const B0 = (reach & 1) ? reinterpret_cast<pel*>(smraw + L.offB(0)) : A0;
-    const pel* const B1 = (reach & 2) ? reinterpret_cast<pel*>(smraw + L.offB(1)) : A1;
-    const pel* const B2 = (reach & 4) ? reinterpret_cast<pel*>(smraw + L.offB(2)) : A2;
-    if (reach)
-    {
-      const bool halo0 = alfY || ccCb || ccCr;
-      const int nI0 = (reach & 1) ? (SA_T / 8) * SA_T : 0, nIC = (tw >> 3) << thLogC;
-      const int nH0 = (reach & 1) && halo0 ? 2 * SA_T + 96 : 0, nHC = 2 * th + 96;
-      const int e0 = nI0, e1 = e0 + ((reach & 2) ? nIC : 0), e2 = e1 + ((reach & 4) ? nIC : 0);
-      const int e3 = e2 + nH0, e4 = e3 + ((reach & 2) && alfCb ? nHC : 0), e5 = e4 + ((reach & 4) && alfCr ? nHC : 0);
-      for (int i = tid; i < e5; i += SA_THREADS)
-      {
-        const bool interior = i < e2;
-        const int c = interior ? (i < e0 ? 0 : (i < e1 ? 1 : 2)) : (i < e3 ? 0 : (i < e4 ? 1 : 2));
-        const int base = interior ? (c == 0 ? 0 : (c == 1 ? e0 : e1)) : (c == 0 ? e2 : (c == 1 ? e3 : e4));
-        const int sxc = c ? g.sx : 0, syc = c ? g.sy : 0;
-        const SaoGeom sg = { (x0 >> sxc) - SA_HX, (y0 >> syc) - SA_HY, g.w >> sxc, g.h >> syc, g.ctuLog2 - sxc, g.ctuLog2 - syc, tcx, tcy,
-                             c ? g.bdC : g.bdL, c ? L.pitchC : SA_P, SA_T >> sxc, 6 - syc };
-        pel* bq = reinterpret_cast<pel*>(smraw + L.offB(c));
-        const pel* aq = reinterpret_cast<const pel*>(smraw + L.offA(stage, c));
-        int r, gc;
-        bool ok;
-        if (interior) ok = saoItemInterior(i - base, sg, r, gc); else ok = saoItemHalo(i - base, sg, r, gc);
-        if (ok) saoGroup(bq, aq, r, gc, par.sao[c], sg);
-      }
-      if (onBorder)
-      {
-        // replicate border of the SAO output (= UnitBuf::extendBorderPel of the ALF input, AdaptiveLoopFilter.cpp:411)
-        __syncthreads();
-        if (nH0) saReplicateBorder(const_cast<pel*>(B0), x0 - SA_HX, y0 - SA_HY, g.w, g.h, SA_P, SA_T, SA_T, 3);
-        if ((reach & 2) && alfCb) saReplicateBorder(const_cast<pel*>(B1), (x0 >> g.sx) - SA_HX, (y0 >> g.sy) - SA_HY, cw, chh, L.pitchC, tw, th, 3);
-        if ((reach & 4) && alfCr) saReplicateBorder(const_cast<pel*>(B2), (x0 >> g.sx) - SA_HX, (y0 >> g.sy) - SA_HY, cw, chh, L.pitchC, tw, th, 3);
-      }
-      __syncthreads();
-    }
-
-    // ---- phase 2: Laplacian cells (luma ALF only) -------------------------------------------------------------------
+    // ---- phase 1: Laplacian cells (luma ALF only) -------------------------------------------------------------------
     const pel* lumaB = B0;
     const int bx = x0 + 4 * bj, by = y0 + 4 * bi;
     const pel* c0 = &lumaB[(4 * bi + SA_HY) * SA_P + 4 * bj + SA_HX];
     const int yb = by & ctuMask;
-    const bool vbBlk = yb == vbL - 4 || yb == vbL;             // uniform per warp (two block rows) for CTU sizes >= 32
+    const bool vbBlk = (yb == vbL - 4 || yb == vbL) && !(dbg & 1);             // uniform per warp (two block rows) for CTU sizes >= 32
     if (alfY)
     {
       if (!vbBlk) alfOwnCells(cell, c0, bi, bj);
@@ -800,7 +562,7 @@ __global__ void __launch_bounds__(SA_THREADS, 2) k_sao_alf(const SlotDev* __rest
       __syncthreads();
     }
 
-    // ---- phase 3: filters; every plane is written once ----------------------------------------------------------------
+    // ---- phase 2: filters; every plane is written once ----------------------------------------------------------------
     const PlaneDev dstY = S.buf[dstBuf][0];
     if (alfY)
     {
@@ -829,7 +591,7 @@ __global__ void __launch_bounds__(SA_THREADS, 2) k_sao_alf(const SlotDev* __rest
     }
     else
     {
-      // no luma ALF in this CTU: the SAO output is the result (128-bit rows)
+      // no luma ALF in this CTU: copy (128-bit rows)
       for (int i = tid; i < SA_T * (SA_T / 8); i += SA_THREADS)
       {
         const int r = i >> 3, gc = i & 7;
@@ -838,7 +600,7 @@ __global__ void __launch_bounds__(SA_THREADS, 2) k_sao_alf(const SlotDev* __rest
           *reinterpret_cast<int4*>(dstY.p + (size_t)y * dstY.pitch + x) = *reinterpret_cast<const int4*>(&lumaB[(r + SA_HY) * SA_P + 8 * gc + SA_HX]);
       }
     }
-    if (g.ncomp > 1)
+    if (g.ncomp > 1 && !(dbg & 4))
     {
       // chroma: one item = 4 horizontally adjacent samples
       const int cx0 = x0 >> g.sx, cy0 = y0 >> g.sy, qShift = 4 - g.sx, quads = (tw >> 2) << thLogC;       // tw / 4 = 1 << qShift

@@ -14,6 +14,7 @@
 // segment records of include/vtmgpu.h.  HBM traffic per plane: read (1 + halo) + write 1 samples, records 0.25 B/px.
 #pragma once
 
+#include "sao_device.cuh"
 #include "vtmgpu_dev.cuh"
 #include "vtmgpu.h"
 
@@ -264,7 +265,14 @@ struct DbfLaunch
   int tilesXC, tilesC;      // per chroma plane
 };
 
-__global__ void __launch_bounds__(DBF_THREADS) k_deblock(const SlotDev* __restrict__ slots, int firstSlot, int srcBuf, int dstBuf, Geom g, DbfLaunch L)
+// Deblocking (both passes) of one tile followed by SAO of the tile's own samples, written straight to the output plane.
+// SAO classifies against the deblocked neighbours one sample outside the tile, so both passes are evaluated 4 samples
+// beyond the tile on every side (luma: the vertical edges x0-4 and x0+TW+4 and the horizontal-edge segments of the
+// columns x0-4..x0-1 / x0+TW..x0+TW+3; chroma: one more horizontal-edge segment on each side).  The 8-sample halo still
+// suffices: a block side that starts 4 samples off a multiple of 16 is shorter than 32, so those edges read at most 4
+// samples on their far side.
+__global__ void __launch_bounds__(DBF_THREADS) k_dbf_sao(const SlotDev* __restrict__ slots, int firstSlot, int srcBuf, int dstBuf, Geom g, DbfLaunch L,
+                                                          int doDbf, int doSao)
 {
   __shared__ __align__(16) pel sm[DBF_SH * DBF_PITCH];
   const SlotDev& S = slots[firstSlot + blockIdx.y];
@@ -288,32 +296,32 @@ __global__ void __launch_bounds__(DBF_THREADS) k_deblock(const SlotDev* __restri
   }
   __syncthreads();
 
-  if (S.dbfOn)
+  if (doDbf && S.dbfOn)
   {
     const int maxv = (1 << (comp ? g.bdC : g.bdL)) - 1;
     if (comp == 0)
     {
       const int uw = g.w >> 2;
-      // pass 1: vertical edges x0 .. x0+TW (step 4), all rows of tile + halo
-      constexpr int NE = DBF_TW / 4 + 1, NS = DBF_SH / 4;
+      // pass 1: vertical edges x0-4 .. x0+TW+4 (step 4), all rows of tile + halo
+      constexpr int NE = DBF_TW / 4 + 3, NS = DBF_SH / 4;
       for (int i = tid; i < NE * NS; i += DBF_THREADS)
       {
         const int sg = i / NE, e = i - sg * NE;
-        const int x = x0 + 4 * e, y = y0 - DBF_HALO + 4 * sg;
+        const int x = x0 - 4 + 4 * e, y = y0 - DBF_HALO + 4 * sg;
         if (x <= 0 || x >= w || y < 0 || y >= h) continue;
         const uint32_t rec = __ldg(&S.dbfL[0][(y >> 2) * uw + (x >> 2)]);
-        if (rec & 0x7ff) dbfLumaSegment(&sm[(4 * sg) * DBF_PITCH + DBF_HALO + 4 * e], 1, DBF_PITCH, rec, maxv);
+        if (rec & 0x7ff) dbfLumaSegment(&sm[(4 * sg) * DBF_PITCH + DBF_HALO - 4 + 4 * e], 1, DBF_PITCH, rec, maxv);
       }
       __syncthreads();
-      // pass 2: horizontal edges y0 .. y0+TH (step 4), own columns
-      constexpr int NEH = DBF_TH / 4 + 1, NSH = DBF_TW / 4;
+      // pass 2: horizontal edges y0 .. y0+TH (step 4), columns x0-4 .. x0+TW+3
+      constexpr int NEH = DBF_TH / 4 + 1, NSH = DBF_TW / 4 + 2;
       for (int i = tid; i < NEH * NSH; i += DBF_THREADS)
       {
         const int e = i / NSH, sg = i - e * NSH;
-        const int x = x0 + 4 * sg, y = y0 + 4 * e;
-        if (y <= 0 || y >= h || x >= w) continue;
+        const int x = x0 - 4 + 4 * sg, y = y0 + 4 * e;
+        if (y <= 0 || y >= h || x < 0 || x >= w) continue;
         const uint32_t rec = __ldg(&S.dbfL[1][(y >> 2) * uw + (x >> 2)]);
-        if (rec & 0x7ff) dbfLumaSegment(&sm[(DBF_HALO + 4 * e) * DBF_PITCH + DBF_HALO + 4 * sg], DBF_PITCH, 1, rec, maxv);
+        if (rec & 0x7ff) dbfLumaSegment(&sm[(DBF_HALO + 4 * e) * DBF_PITCH + DBF_HALO - 4 + 4 * sg], DBF_PITCH, 1, rec, maxv);
       }
     }
     else
@@ -339,18 +347,19 @@ __global__ void __launch_bounds__(DBF_THREADS) k_deblock(const SlotDev* __restri
       }
       __syncthreads();
       {
+        // pass 2: horizontal edges, one more segment of columns on each side of the tile
         const int n = 4 >> g.sx, uw = g.w >> 2;
         constexpr int NEH = DBF_TH / 8 + 1;
-        const int NSH = DBF_TW / n;
+        const int NSH = DBF_TW / n + 2;
         for (int i = tid; i < NEH * NSH; i += DBF_THREADS)
         {
           const int e = i / NSH, sg = i - e * NSH;
-          const int x = x0 + n * sg, y = y0 + 8 * e;
-          if (y <= 0 || y >= h || x >= w) continue;
+          const int x = x0 - n + n * sg, y = y0 + 8 * e;
+          if (y <= 0 || y >= h || x < 0 || x >= w) continue;
           const uint64_t rec = __ldg(&S.dbfC[1][(y >> 3) * uw + (x / n)]);
           const int tc = (int)(rec >> tcShift) & 0x7ff;
           if (tc)
-            dbfChromaSegment(&sm[(DBF_HALO + 8 * e) * DBF_PITCH + DBF_HALO + n * sg], DBF_PITCH, 1, n, tc, (int)(rec >> betaShift) & 0x7ff,
+            dbfChromaSegment(&sm[(DBF_HALO + 8 * e) * DBF_PITCH + DBF_HALO - n + n * sg], DBF_PITCH, 1, n, tc, (int)(rec >> betaShift) & 0x7ff,
                              (rec & VTMGPU_DBF_C_LARGE) != 0, (rec & VTMGPU_DBF_C_CTB) != 0, !(rec & VTMGPU_DBF_C_PNOFILT), !(rec & VTMGPU_DBF_C_QNOFILT), maxv);
         }
       }
@@ -358,14 +367,21 @@ __global__ void __launch_bounds__(DBF_THREADS) k_deblock(const SlotDev* __restri
     __syncthreads();
   }
 
-  // ---- store own region -----------------------------------------------------------------------------------
-  constexpr int OG = DBF_TW / 8;
-  for (int i = tid; i < OG * DBF_TH; i += DBF_THREADS)
+  // ---- epilogue: SAO of the own region straight into the output plane (or a plain 128-bit copy) -------------------
+  // one thread = one 8-sample group column x 4 rows (a 4-row strip never crosses a CTU boundary)
   {
-    const int r = i / OG, gcol = i - r * OG;
-    const int y = y0 + r, x = x0 + gcol * 8;
-    if (y < h && x < w)
-      *reinterpret_cast<int4*>(dst.p + (size_t)y * dst.pitch + x) = *reinterpret_cast<const int4*>(&sm[(DBF_HALO + r) * DBF_PITCH + DBF_HALO + gcol * 8]);
+    const int gcol = tid & (DBF_TW / 8 - 1), rb = tid / (DBF_TW / 8);
+    const int x = x0 + 8 * gcol, y = y0 + 4 * rb;
+    if (x < w && y < h)
+    {
+      const int nrows = min(4, h - y);
+      const pel* a = &sm[(DBF_HALO + 4 * rb) * DBF_PITCH + DBF_HALO + 8 * gcol];
+      pel* out = dst.p + (size_t)y * dst.pitch + x;
+      uint4 pq = make_uint4(0, 0, 0, 0);
+      const int cwLog = g.ctuLog2 - (comp ? g.sx : 0), chLog = g.ctuLog2 - (comp ? g.sy : 0);
+      if (doSao && S.saoOn) pq = __ldg(reinterpret_cast<const uint4*>(&S.sao[((y >> chLog) * g.wCtus + (x >> cwLog)) * 3 + comp]));
+      saoStrip(out, dst.pitch, a, DBF_PITCH, nrows, x, y, pq, w, h, cwLog | chLog << 8 | (comp ? g.bdC : g.bdL) << 16);
+    }
   }
 }
 

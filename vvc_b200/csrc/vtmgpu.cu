@@ -17,7 +17,7 @@
 #include <vector>
 
 #include "dbf_kernel.cuh"
-#include "saoalf_kernel.cuh"
+#include "alf_kernel.cuh"
 #include "vtmgpu.h"
 #include "vvc_alf_fixed_tables.h"
 
@@ -285,7 +285,7 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
     }
   }
   CK(cudaMemcpyAsync(c->slotsDev, c->slotsPinned, sizeof(SlotDev) * s.capacity, cudaMemcpyHostToDevice, c->stream), "slot table upload");
-  CK(cudaFuncSetAttribute(k_sao_alf, cudaFuncAttributeMaxDynamicSharedMemorySize, saLayout(g.sx, g.sy, g.ncomp).total), "smem attribute");
+  CK(cudaFuncSetAttribute(k_alf, cudaFuncAttributeMaxDynamicSharedMemorySize, saLayout(g.sx, g.sy, g.ncomp).total), "smem attribute");
   CK(cudaDeviceGetAttribute(&c->numSms, cudaDevAttrMultiProcessorCount, s.device), "device attribute");
   CK(cudaStreamSynchronize(c->stream), "sync");
 #undef CK
@@ -465,20 +465,7 @@ extern "C" int vtmgpu_set_sao(vtmgpu_ctx* c, int slot, const vtmgpu_sao_params* 
         d[a * 3 + k] = z;
       }
     sd.saoOn = any;     // SAOProcess returns early when no CTU has SAO on (SampleAdaptiveOffset.cpp:626-637)
-    // reach bits: does any CTU of the 3x3 neighbourhood switch SAO on for the component (the tile kernel skips the stage otherwise)
-    CtuCtlDev* ctl = reinterpret_cast<CtuCtlDev*>(c->pinnedSide(slot) + c->lay.ctuCtl);
-    const int wc = c->g.wCtus, hc = c->g.hCtus;
-    for (int cy = 0; cy < hc; cy++)
-      for (int cx = 0; cx < wc; cx++)
-      {
-        uint8_t reach = 0;
-        for (int ny = std::max(cy - 1, 0); ny <= std::min(cy + 1, hc - 1); ny++)
-          for (int nx = std::max(cx - 1, 0); nx <= std::min(cx + 1, wc - 1); nx++)
-            for (int k = 0; k < 3; k++) reach |= (d[(ny * wc + nx) * 3 + k].type != 0) << k;
-        ctl[cy * wc + cx].saoReach = reach;
-      }
     if (c->pushSide(slot, c->lay.sao, (size_t)c->nCtus * 3 * sizeof(SaoDev))) return -1;
-    if (c->pushSide(slot, c->lay.ctuCtl, (size_t)c->nCtus * sizeof(CtuCtlDev))) return -1;
   }
   return c->pushSlot(slot);
 }
@@ -620,10 +607,11 @@ template <class F> int forRuns(vtmgpu_ctx* c, int first, int count, F f)
   return 0;
 }
 
-int launchDeblock(vtmgpu_ctx* c, int first, int count)
+// deblocking and / or SAO: one pass over the picture (k_dbf_sao); stages that are off for a slot are skipped inside the kernel
+int launchDbfSao(vtmgpu_ctx* c, int first, int count, int doDbf, int doSao)
 {
   bool any = false;
-  for (int s = first; s < first + count; s++) any |= c->slotsPinned[s].dbfOn != 0;
+  for (int s = first; s < first + count; s++) any |= (doDbf && c->slotsPinned[s].dbfOn) || (doSao && c->slotsPinned[s].saoOn);
   if (!any) return 0;
   const Geom& g = c->g;
   DbfLaunch L;
@@ -633,17 +621,18 @@ int launchDeblock(vtmgpu_ctx* c, int first, int count)
   L.tilesC = g.ncomp > 1 ? L.tilesXC * (((g.h >> g.sy) + DBF_TH - 1) / DBF_TH) : 0;
   return forRuns(c, first, count, [&](int s, int n, int src) {
     const int dst = src == 1 ? 2 : 1;
-    k_deblock<<<dim3(L.tilesL + 2 * L.tilesC, n), DBF_THREADS, 0, c->stream>>>(c->slotsDev, s, src, dst, g, L);
+    k_dbf_sao<<<dim3(L.tilesL + 2 * L.tilesC, n), DBF_THREADS, 0, c->stream>>>(c->slotsDev, s, src, dst, g, L, doDbf, doSao);
     c->launches++;
     for (int i = s; i < s + n; i++) c->cur[i] = dst;
-    return c->cuda(cudaGetLastError(), "k_deblock launch");
+    return c->cuda(cudaGetLastError(), "k_dbf_sao launch");
   });
 }
 
-int launchSaoAlf(vtmgpu_ctx* c, int first, int count, int doSao, int doAlf)
+// ALF + CC-ALF (k_alf)
+int launchAlf(vtmgpu_ctx* c, int first, int count)
 {
   bool any = false;
-  for (int s = first; s < first + count; s++) any |= (doSao && c->slotsPinned[s].saoOn) || (doAlf && c->slotsPinned[s].alfOn);
+  for (int s = first; s < first + count; s++) any |= c->slotsPinned[s].alfOn != 0;
   if (!any) return 0;
   const Geom& g = c->g;
   const int tilesX = (g.w + SA_T - 1) / SA_T, tilesY = (g.h + SA_T - 1) / SA_T;
@@ -656,10 +645,10 @@ int launchSaoAlf(vtmgpu_ctx* c, int first, int count, int doSao, int doAlf)
     st.dx = grid % tilesX;
     st.dy = (grid / tilesX) % tilesY;
     st.ds = (grid / tilesX) / tilesY;
-    k_sao_alf<<<grid, SA_THREADS, smem, c->stream>>>(c->slotsDev, c->tmapsDev, s, n, src, dst, g, tilesX, tilesY, st, doSao, doAlf);
+    k_alf<<<grid, SA_THREADS, smem, c->stream>>>(c->slotsDev, c->tmapsDev, s, n, src, dst, g, tilesX, tilesY, st, getenv("VTMGPU_DEBUG") ? atoi(getenv("VTMGPU_DEBUG")) : 0);
     c->launches++;
     for (int i = s; i < s + n; i++) c->cur[i] = dst;
-    return c->cuda(cudaGetLastError(), "k_sao_alf launch");
+    return c->cuda(cudaGetLastError(), "k_alf launch");
   });
 }
 
@@ -670,9 +659,9 @@ int runStages(vtmgpu_ctx* c, int first, int count, int stages, bool sync, const 
   cudaSetDevice(c->seq.device);
   c->stageValid = false;
   if (c->profiling) cudaEventRecord(c->stageEv[0], c->stream);
-  if ((stages & ST_DBF) && launchDeblock(c, first, count)) return -1;
+  if ((stages & (ST_DBF | ST_SAO)) && launchDbfSao(c, first, count, (stages & ST_DBF) != 0, (stages & ST_SAO) != 0)) return -1;
   if (c->profiling) cudaEventRecord(c->stageEv[1], c->stream);
-  if ((stages & (ST_SAO | ST_ALF)) && launchSaoAlf(c, first, count, (stages & ST_SAO) != 0, (stages & ST_ALF) != 0)) return -1;
+  if ((stages & ST_ALF) && launchAlf(c, first, count)) return -1;
   if (c->profiling) { cudaEventRecord(c->stageEv[2], c->stream); c->stageValid = true; }
   if (sync && c->cuda(cudaStreamSynchronize(c->stream), what)) return -1;
   return 0;

@@ -65,16 +65,14 @@ struct AlfLumaEntry
 };
 
 // Per-CTU control record (16 bytes, one 128-bit load per tile): ALF control (Picture::getAlfCtuEnableFlag /
-// getAlfCtbFilterIndex / getAlfCtuAlternativeData, m_ccAlfFilterControl) written by vtmgpu_set_alf and the SAO reach
-// bits written by vtmgpu_set_sao.
+// getAlfCtbFilterIndex / getAlfCtuAlternativeData, m_ccAlfFilterControl) written by vtmgpu_set_alf.
 struct CtuCtlDev
 {
   uint8_t enY, enCb, enCr;       // ALF CTU enable flags
   uint8_t altCb, altCr;          // chroma filter alternative
   uint8_t ccCb, ccCr;            // CC-ALF filter idc (0 = off)
   uint8_t setIdx;                // luma filter set: < 16 fixed, else APS
-  uint8_t saoReach;              // bit c: a CTU of the 3x3 neighbourhood (incl. this one) has SAO on for component c
-  uint8_t pad[7];
+  uint8_t pad[8];
 };
 
 struct SlotDev
