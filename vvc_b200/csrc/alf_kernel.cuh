@@ -24,6 +24,7 @@
 
 #include <cuda.h>
 
+#include "async_copy.cuh"
 #include "packed16.cuh"
 #include "vtmgpu_dev.cuh"
 #include "vtmgpu.h"
@@ -71,39 +72,6 @@ __host__ __device__ inline SaLayout saLayout(int sx, int sy, int ncomp)
   L.offBar = L.offPar + 2 * (int)sizeof(CtuCtlDev);
   L.total = L.offBar + 16;
   return L;
-}
-
-// ---- asynchronous tile load: TMA (cp.async.bulk.tensor) completing on an mbarrier ------------------------------------
-__device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cpAsync16(void* smem, const void* gmem)
-{
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smemAddr(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-__device__ __forceinline__ void mbarInit(uint64_t* bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory"); }
-__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes)
-{
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity)
-{
-  asm volatile(
-    "{\n"
-    ".reg .pred p;\n"
-    "MBAR_WAIT_%=:\n"
-    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-    "@p bra MBAR_DONE_%=;\n"
-    "bra MBAR_WAIT_%=;\n"
-    "MBAR_DONE_%=:\n"
-    "}\n" ::"r"(smemAddr(bar)), "r"(parity) : "memory");
-}
-// one 2-D box of a plane (element coordinates, may start outside: those elements arrive as zeros) into shared memory
-__device__ __forceinline__ void tmaLoad2D(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar)
-{
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-               ::"r"(smemAddr(dst)), "l"(map), "r"(x), "r"(y), "r"(smemAddr(bar)) : "memory");
 }
 
 // TMA fills positions outside the picture with zeros; the filters want the border samples replicated

@@ -14,6 +14,7 @@
 // segment records of include/vtmgpu.h.  HBM traffic per plane: read (1 + halo) + write 1 samples, records 0.25 B/px.
 #pragma once
 
+#include "async_copy.cuh"
 #include "sao_device.cuh"
 #include "vtmgpu_dev.cuh"
 #include "vtmgpu.h"
@@ -265,123 +266,234 @@ struct DbfLaunch
   int tilesXC, tilesC;      // per chroma plane
 };
 
+// ---- the kernel ---------------------------------------------------------------------------------------------------
 // Deblocking (both passes) of one tile followed by SAO of the tile's own samples, written straight to the output plane.
 // SAO classifies against the deblocked neighbours one sample outside the tile, so both passes are evaluated 4 samples
 // beyond the tile on every side (luma: the vertical edges x0-4 and x0+TW+4 and the horizontal-edge segments of the
 // columns x0-4..x0-1 / x0+TW..x0+TW+3; chroma: one more horizontal-edge segment on each side).  The 8-sample halo still
 // suffices: a block side that starts 4 samples off a multiple of 16 is shorter than 32, so those edges read at most 4
 // samples on their far side.
-__global__ void __launch_bounds__(DBF_THREADS) k_dbf_sao(const SlotDev* __restrict__ slots, int firstSlot, int srcBuf, int dstBuf, Geom g, DbfLaunch L,
-                                                          int doDbf, int doSao)
-{
-  __shared__ __align__(16) pel sm[DBF_SH * DBF_PITCH];
-  const SlotDev& S = slots[firstSlot + blockIdx.y];
-  int t = blockIdx.x, comp = 0;
-  if (t >= L.tilesL) { t -= L.tilesL; comp = 1 + t / L.tilesC; t -= (comp - 1) * L.tilesC; }
-  const int tilesX = comp ? L.tilesXC : L.tilesXL;
-  const int x0 = (t % tilesX) * DBF_TW, y0 = (t / tilesX) * DBF_TH;
-  const PlaneDev src = S.buf[srcBuf][comp], dst = S.buf[dstBuf][comp];
-  const int w = src.w, h = src.h;
-  const int tid = threadIdx.x;
+//
+// Persistent CTAs walk the plane tiles of a batch of picture slots round robin (per slot: luma tiles, Cb tiles, Cr tiles).
+// While tile i is filtered, tile i+1 arrives: the samples (tile + 8 halo, zero filled outside the picture) by ONE TMA box,
+// the segment records of both passes by cp.async in exactly the order the passes consume them.
+constexpr int DBF_RECA_BYTES = 5632;                    // pass-1 records of a tile: luma 35x20 u32, chroma 17x40 u64
+constexpr int DBF_RECB_BYTES = 4864;                    // pass-2 records: luma 34x17 u32, chroma 66x9 u64
+constexpr int DBF_TILE_BYTES = DBF_SH * DBF_PITCH * 2;  // 24320 (multiple of 128: TMA destination)
+constexpr int DBF_STAGE_BYTES = DBF_TILE_BYTES + DBF_RECA_BYTES + DBF_RECB_BYTES;
+constexpr int DBF_SMEM_BYTES = 2 * DBF_STAGE_BYTES + 16;
 
-  // ---- load tile + halo: (DBF_SW/8) groups x DBF_SH rows, 128-bit each --------------------------------
-  constexpr int GROUPS = DBF_SW / 8;
-  for (int i = tid; i < GROUPS * DBF_SH; i += DBF_THREADS)
+struct DbfTile
+{
+  int comp, x0, y0;
+};
+
+__device__ __forceinline__ DbfTile dbfDecodeTile(int item, const DbfLaunch& L)
+{
+  DbfTile T;
+  T.comp = 0;
+  if (item >= L.tilesL) { item -= L.tilesL; T.comp = 1; if (item >= L.tilesC) { item -= L.tilesC; T.comp = 2; } }
+  const int tilesX = T.comp ? L.tilesXC : L.tilesXL, ty = item / tilesX;
+  T.x0 = (item - ty * tilesX) * DBF_TW;
+  T.y0 = ty * DBF_TH;
+  return T;
+}
+
+// slot counts of the two passes of a tile (work items i = 0 .. n-1; the record of item i sits at rec[i])
+struct DbfPassGeom
+{
+  int ne1, ns1, n1;      // pass 1: ne1 edges per row of segments, ns1 segment rows
+  int ne2, ns2, n2;      // pass 2: ne2 edge rows, ns2 segments per edge row
+  int nv, nh;            // chroma: samples along the edge per record (vertical edges / horizontal edges)
+};
+
+__device__ __forceinline__ DbfPassGeom dbfPassGeom(int comp, const Geom& g)
+{
+  DbfPassGeom P;
+  if (comp == 0) { P.ne1 = DBF_TW / 4 + 3; P.ns1 = DBF_SH / 4; P.ne2 = DBF_TH / 4 + 1; P.ns2 = DBF_TW / 4 + 2; P.nv = P.nh = 4; }
+  else
   {
-    const int r = i / GROUPS, gcol = i - r * GROUPS;
-    const int y = y0 - DBF_HALO + r, x = x0 - DBF_HALO + gcol * 8;
-    int4 v = make_int4(0, 0, 0, 0);
-    if (y >= 0 && y < h && x >= 0 && x < w) v = __ldg(reinterpret_cast<const int4*>(src.p + (size_t)y * src.pitch + x));
-    *reinterpret_cast<int4*>(&sm[r * DBF_PITCH + gcol * 8]) = v;
+    P.nv = 4 >> g.sy; P.nh = 4 >> g.sx;
+    P.ne1 = DBF_TW / 8 + 1; P.ns1 = DBF_SH / P.nv; P.ne2 = DBF_TH / 8 + 1; P.ns2 = DBF_TW / P.nh + 2;
+  }
+  P.n1 = P.ne1 * P.ns1; P.n2 = P.ne2 * P.ns2;
+  return P;
+}
+
+// issues the asynchronous loads of one tile into a stage: the TMA box (one thread) and the records (all threads, cp.async)
+__device__ __forceinline__ void dbfPrefetch(unsigned char* stageMem, uint64_t* bar, const SlotDev& S, const CUtensorMap* map, const DbfTile& T, const Geom& g,
+                                            bool dbfOn)
+{
+  const int tid = threadIdx.x;
+  if (tid == 0)
+  {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbarExpectTx(bar, DBF_TILE_BYTES);
+    tmaLoad2D(stageMem, map, T.x0 - DBF_HALO, T.y0 - DBF_HALO, bar);
+  }
+  if (!dbfOn) return;
+  const DbfPassGeom P = dbfPassGeom(T.comp, g);
+  if (T.comp == 0)
+  {
+    const int uw = g.w >> 2, uh = g.h >> 2;
+    uint32_t* ra = reinterpret_cast<uint32_t*>(stageMem + DBF_TILE_BYTES);
+    uint32_t* rb = reinterpret_cast<uint32_t*>(stageMem + DBF_TILE_BYTES + DBF_RECA_BYTES);
+    for (int i = tid; i < P.n1; i += DBF_THREADS)
+    {
+      const int sg = i / P.ne1, e = i - sg * P.ne1;
+      const int ux = (T.x0 >> 2) - 1 + e, uy = ((T.y0 - DBF_HALO) >> 2) + sg;
+      if (ux > 0 && ux < uw && uy >= 0 && uy < uh) cpAsync4(&ra[i], &S.dbfL[0][uy * uw + ux]); else ra[i] = 0;
+    }
+    for (int i = tid; i < P.n2; i += DBF_THREADS)
+    {
+      const int e = i / P.ns2, sg = i - e * P.ns2;
+      const int ux = (T.x0 >> 2) - 1 + sg, uy = (T.y0 >> 2) + e;
+      if (uy > 0 && uy < uh && ux >= 0 && ux < uw) cpAsync4(&rb[i], &S.dbfL[1][uy * uw + ux]); else rb[i] = 0;
+    }
+  }
+  else
+  {
+    // chroma planes: x0,y0 in chroma samples; record arrays are indexed in luma units (include/vtmgpu.h)
+    const int cw = g.w >> g.sx, ch = g.h >> g.sy;
+    const int cols0 = (g.w + (8 << g.sx) - 1) / (8 << g.sx), uw = g.w >> 2;
+    uint64_t* ra = reinterpret_cast<uint64_t*>(stageMem + DBF_TILE_BYTES);
+    uint64_t* rb = reinterpret_cast<uint64_t*>(stageMem + DBF_TILE_BYTES + DBF_RECA_BYTES);
+    for (int i = tid; i < P.n1; i += DBF_THREADS)
+    {
+      const int sg = i / P.ne1, e = i - sg * P.ne1;
+      const int x = T.x0 + 8 * e, y = T.y0 - DBF_HALO + P.nv * sg;
+      if (x > 0 && x < cw && y >= 0 && y < ch) cpAsync8(&ra[i], &S.dbfC[0][(y / P.nv) * cols0 + (x >> 3)]); else ra[i] = 0;
+    }
+    for (int i = tid; i < P.n2; i += DBF_THREADS)
+    {
+      const int e = i / P.ns2, sg = i - e * P.ns2;
+      const int x = T.x0 - P.nh + P.nh * sg, y = T.y0 + 8 * e;
+      if (y > 0 && y < ch && x >= 0 && x < cw) cpAsync8(&rb[i], &S.dbfC[1][(y >> 3) * uw + (x / P.nh)]); else rb[i] = 0;
+    }
+  }
+}
+
+// maps = TMA descriptors of the plane buffers: [slot][3 buffers][3 planes], box = DBF_PITCH x DBF_SH samples
+__global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __restrict__ slots, const CUtensorMap* __restrict__ tmaps, int firstSlot, int numSlots,
+                                                             int srcBuf, int dstBuf, Geom g, DbfLaunch L, TileStep step, int doDbf, int doSao)
+{
+  extern __shared__ __align__(128) unsigned char smraw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + 2 * DBF_STAGE_BYTES);
+  const int tid = threadIdx.x;
+  const int itemsPerSlot = L.tilesL + 2 * L.tilesC;
+  int slot = blockIdx.x / itemsPerSlot, item = blockIdx.x - slot * itemsPerSlot;
+  if (slot >= numSlots) return;
+  if (tid == 0)
+  {
+    mbarInit(&bars[0], 1);
+    mbarInit(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-
-  if (doDbf && S.dbfOn)
   {
-    const int maxv = (1 << (comp ? g.bdC : g.bdL)) - 1;
-    if (comp == 0)
-    {
-      const int uw = g.w >> 2;
-      // pass 1: vertical edges x0-4 .. x0+TW+4 (step 4), all rows of tile + halo
-      constexpr int NE = DBF_TW / 4 + 3, NS = DBF_SH / 4;
-      for (int i = tid; i < NE * NS; i += DBF_THREADS)
-      {
-        const int sg = i / NE, e = i - sg * NE;
-        const int x = x0 - 4 + 4 * e, y = y0 - DBF_HALO + 4 * sg;
-        if (x <= 0 || x >= w || y < 0 || y >= h) continue;
-        const uint32_t rec = __ldg(&S.dbfL[0][(y >> 2) * uw + (x >> 2)]);
-        if (rec & 0x7ff) dbfLumaSegment(&sm[(4 * sg) * DBF_PITCH + DBF_HALO - 4 + 4 * e], 1, DBF_PITCH, rec, maxv);
-      }
-      __syncthreads();
-      // pass 2: horizontal edges y0 .. y0+TH (step 4), columns x0-4 .. x0+TW+3
-      constexpr int NEH = DBF_TH / 4 + 1, NSH = DBF_TW / 4 + 2;
-      for (int i = tid; i < NEH * NSH; i += DBF_THREADS)
-      {
-        const int e = i / NSH, sg = i - e * NSH;
-        const int x = x0 - 4 + 4 * sg, y = y0 + 4 * e;
-        if (y <= 0 || y >= h || x < 0 || x >= w) continue;
-        const uint32_t rec = __ldg(&S.dbfL[1][(y >> 2) * uw + (x >> 2)]);
-        if (rec & 0x7ff) dbfLumaSegment(&sm[(DBF_HALO + 4 * e) * DBF_PITCH + DBF_HALO - 4 + 4 * sg], DBF_PITCH, 1, rec, maxv);
-      }
-    }
-    else
-    {
-      const int c = comp - 1;
-      const int tcShift = c ? VTMGPU_DBF_C_TCCR_SHIFT : 0, betaShift = c ? VTMGPU_DBF_C_BETACR_SHIFT : VTMGPU_DBF_C_BETACB_SHIFT;
-      // pass 1: vertical edges on the 8-sample chroma grid; one item = the chroma rows of one 4-luma-row unit
-      {
-        const int n = 4 >> g.sy, cols0 = (g.w + (8 << g.sx) - 1) / (8 << g.sx);
-        constexpr int NE = DBF_TW / 8 + 1;
-        const int NS = DBF_SH / n;
-        for (int i = tid; i < NE * NS; i += DBF_THREADS)
-        {
-          const int sg = i / NE, e = i - sg * NE;
-          const int x = x0 + 8 * e, y = y0 - DBF_HALO + n * sg;
-          if (x <= 0 || x >= w || y < 0 || y >= h) continue;
-          const uint64_t rec = __ldg(&S.dbfC[0][(y / n) * cols0 + (x >> 3)]);
-          const int tc = (int)(rec >> tcShift) & 0x7ff;
-          if (tc)
-            dbfChromaSegment(&sm[(n * sg) * DBF_PITCH + DBF_HALO + 8 * e], 1, DBF_PITCH, n, tc, (int)(rec >> betaShift) & 0x7ff,
-                             (rec & VTMGPU_DBF_C_LARGE) != 0, (rec & VTMGPU_DBF_C_CTB) != 0, !(rec & VTMGPU_DBF_C_PNOFILT), !(rec & VTMGPU_DBF_C_QNOFILT), maxv);
-        }
-      }
-      __syncthreads();
-      {
-        // pass 2: horizontal edges, one more segment of columns on each side of the tile
-        const int n = 4 >> g.sx, uw = g.w >> 2;
-        constexpr int NEH = DBF_TH / 8 + 1;
-        const int NSH = DBF_TW / n + 2;
-        for (int i = tid; i < NEH * NSH; i += DBF_THREADS)
-        {
-          const int e = i / NSH, sg = i - e * NSH;
-          const int x = x0 - n + n * sg, y = y0 + 8 * e;
-          if (y <= 0 || y >= h || x < 0 || x >= w) continue;
-          const uint64_t rec = __ldg(&S.dbfC[1][(y >> 3) * uw + (x / n)]);
-          const int tc = (int)(rec >> tcShift) & 0x7ff;
-          if (tc)
-            dbfChromaSegment(&sm[(DBF_HALO + 8 * e) * DBF_PITCH + DBF_HALO - n + n * sg], DBF_PITCH, 1, n, tc, (int)(rec >> betaShift) & 0x7ff,
-                             (rec & VTMGPU_DBF_C_LARGE) != 0, (rec & VTMGPU_DBF_C_CTB) != 0, !(rec & VTMGPU_DBF_C_PNOFILT), !(rec & VTMGPU_DBF_C_QNOFILT), maxv);
-        }
-      }
-    }
-    __syncthreads();
+    const SlotDev& S = slots[firstSlot + slot];
+    const DbfTile T = dbfDecodeTile(item, L);
+    dbfPrefetch(smraw, &bars[0], S, tmaps + ((size_t)(firstSlot + slot) * 3 + srcBuf) * 3 + T.comp, T, g, doDbf && S.dbfOn);
+    cpAsyncCommit();
   }
-
-  // ---- epilogue: SAO of the own region straight into the output plane (or a plain 128-bit copy) -------------------
-  // one thread = one 8-sample group column x 4 rows (a 4-row strip never crosses a CTU boundary)
+  for (uint32_t it = 0; slot < numSlots; it++)
   {
-    const int gcol = tid & (DBF_TW / 8 - 1), rb = tid / (DBF_TW / 8);
-    const int x = x0 + 8 * gcol, y = y0 + 4 * rb;
-    if (x < w && y < h)
+    const int stage = it & 1;
+    unsigned char* stageMem = smraw + stage * DBF_STAGE_BYTES;
+    const SlotDev& S = slots[firstSlot + slot];
+    const DbfTile T = dbfDecodeTile(item, L);
+    int nslot = slot + step.dSlot, nitem = item + step.dItem;
+    if (nitem >= itemsPerSlot) { nitem -= itemsPerSlot; nslot++; }
+    if (nslot < numSlots)
     {
-      const int nrows = min(4, h - y);
-      const pel* a = &sm[(DBF_HALO + 4 * rb) * DBF_PITCH + DBF_HALO + 8 * gcol];
-      pel* out = dst.p + (size_t)y * dst.pitch + x;
-      uint4 pq = make_uint4(0, 0, 0, 0);
-      const int cwLog = g.ctuLog2 - (comp ? g.sx : 0), chLog = g.ctuLog2 - (comp ? g.sy : 0);
-      if (doSao && S.saoOn) pq = __ldg(reinterpret_cast<const uint4*>(&S.sao[((y >> chLog) * g.wCtus + (x >> cwLog)) * 3 + comp]));
-      saoStrip(out, dst.pitch, a, DBF_PITCH, nrows, x, y, pq, w, h, cwLog | chLog << 8 | (comp ? g.bdC : g.bdL) << 16);
+      const SlotDev& Sn = slots[firstSlot + nslot];
+      const DbfTile Tn = dbfDecodeTile(nitem, L);
+      dbfPrefetch(smraw + (stage ^ 1) * DBF_STAGE_BYTES, &bars[stage ^ 1], Sn, tmaps + ((size_t)(firstSlot + nslot) * 3 + srcBuf) * 3 + Tn.comp, Tn, g,
+                  doDbf && Sn.dbfOn);
     }
+    cpAsyncCommit();
+
+    const int comp = T.comp, x0 = T.x0, y0 = T.y0;
+    const PlaneDev dst = S.buf[dstBuf][comp];
+    const int w = dst.w, h = dst.h;
+    // SAO parameters of this thread's strip (one 8-sample group column x 4 rows; a 4-row strip never crosses a CTU boundary):
+    // loaded now, consumed after the deblocking passes
+    const int gcol = tid & (DBF_TW / 8 - 1), rb = tid / (DBF_TW / 8);
+    const int sx_ = x0 + 8 * gcol, sy_ = y0 + 4 * rb;
+    const int cwLog = g.ctuLog2 - (comp ? g.sx : 0), chLog = g.ctuLog2 - (comp ? g.sy : 0);
+    uint4 pq = make_uint4(0, 0, 0, 0);
+    if (doSao && S.saoOn && sx_ < w && sy_ < h) pq = __ldg(reinterpret_cast<const uint4*>(&S.sao[((sy_ >> chLog) * g.wCtus + (sx_ >> cwLog)) * 3 + comp]));
+
+    cpAsyncWait<1>();
+    mbarWait(&bars[stage], (it >> 1) & 1);
+    __syncthreads();                                         // samples and records of this tile are in shared memory
+    pel* sm = reinterpret_cast<pel*>(stageMem);
+
+    if (doDbf && S.dbfOn)
+    {
+      const int maxv = (1 << (comp ? g.bdC : g.bdL)) - 1;
+      const DbfPassGeom P = dbfPassGeom(comp, g);
+      if (comp == 0)
+      {
+        const uint32_t* ra = reinterpret_cast<const uint32_t*>(stageMem + DBF_TILE_BYTES);
+        const uint32_t* rbv = reinterpret_cast<const uint32_t*>(stageMem + DBF_TILE_BYTES + DBF_RECA_BYTES);
+        // pass 1: vertical edges x0-4 .. x0+TW+4 (step 4), all rows of tile + halo
+        constexpr int NE = DBF_TW / 4 + 3;
+        for (int i = tid; i < P.n1; i += DBF_THREADS)
+        {
+          const uint32_t rec = ra[i];
+          if (!(rec & 0x7ff)) continue;
+          const int sg = i / NE, e = i - sg * NE;
+          dbfLumaSegment(&sm[(4 * sg) * DBF_PITCH + DBF_HALO - 4 + 4 * e], 1, DBF_PITCH, rec, maxv);
+        }
+        __syncthreads();
+        // pass 2: horizontal edges y0 .. y0+TH (step 4), columns x0-4 .. x0+TW+3
+        constexpr int NSH = DBF_TW / 4 + 2;
+        for (int i = tid; i < P.n2; i += DBF_THREADS)
+        {
+          const uint32_t rec = rbv[i];
+          if (!(rec & 0x7ff)) continue;
+          const int e = i / NSH, sg = i - e * NSH;
+          dbfLumaSegment(&sm[(DBF_HALO + 4 * e) * DBF_PITCH + DBF_HALO - 4 + 4 * sg], DBF_PITCH, 1, rec, maxv);
+        }
+      }
+      else
+      {
+        const uint64_t* ra = reinterpret_cast<const uint64_t*>(stageMem + DBF_TILE_BYTES);
+        const uint64_t* rbv = reinterpret_cast<const uint64_t*>(stageMem + DBF_TILE_BYTES + DBF_RECA_BYTES);
+        const int c = comp - 1;
+        const int tcShift = c ? VTMGPU_DBF_C_TCCR_SHIFT : 0, betaShift = c ? VTMGPU_DBF_C_BETACR_SHIFT : VTMGPU_DBF_C_BETACB_SHIFT;
+        // pass 1: vertical edges on the 8-sample chroma grid; one item = the chroma rows of one 4-luma-row unit
+        for (int i = tid; i < P.n1; i += DBF_THREADS)
+        {
+          const uint64_t rec = ra[i];
+          const int tc = (int)(rec >> tcShift) & 0x7ff;
+          if (!tc) continue;
+          const int sg = i / P.ne1, e = i - sg * P.ne1;
+          dbfChromaSegment(&sm[(P.nv * sg) * DBF_PITCH + DBF_HALO + 8 * e], 1, DBF_PITCH, P.nv, tc, (int)(rec >> betaShift) & 0x7ff,
+                           (rec & VTMGPU_DBF_C_LARGE) != 0, (rec & VTMGPU_DBF_C_CTB) != 0, !(rec & VTMGPU_DBF_C_PNOFILT), !(rec & VTMGPU_DBF_C_QNOFILT), maxv);
+        }
+        __syncthreads();
+        // pass 2: horizontal edges, one more segment of columns on each side of the tile
+        for (int i = tid; i < P.n2; i += DBF_THREADS)
+        {
+          const uint64_t rec = rbv[i];
+          const int tc = (int)(rec >> tcShift) & 0x7ff;
+          if (!tc) continue;
+          const int e = i / P.ns2, sg = i - e * P.ns2;
+          dbfChromaSegment(&sm[(DBF_HALO + 8 * e) * DBF_PITCH + DBF_HALO - P.nh + P.nh * sg], DBF_PITCH, 1, P.nh, tc, (int)(rec >> betaShift) & 0x7ff,
+                           (rec & VTMGPU_DBF_C_LARGE) != 0, (rec & VTMGPU_DBF_C_CTB) != 0, !(rec & VTMGPU_DBF_C_PNOFILT), !(rec & VTMGPU_DBF_C_QNOFILT), maxv);
+        }
+      }
+      __syncthreads();
+    }
+
+    // ---- epilogue: SAO of the own region straight into the output plane (a plain 128-bit copy where SAO is off) -------
+    if (sx_ < w && sy_ < h)
+      saoStrip(dst.p + (size_t)sy_ * dst.pitch + sx_, dst.pitch, &sm[(DBF_HALO + 4 * rb) * DBF_PITCH + DBF_HALO + 8 * gcol], DBF_PITCH, min(4, h - sy_), sx_, sy_,
+               pq, w, h, cwLog | chLog << 8 | (comp ? g.bdC : g.bdL) << 16);
+    __syncthreads();                                         // the stage is free for the load after next
+    slot = nslot; item = nitem;
   }
 }
 

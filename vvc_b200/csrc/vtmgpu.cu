@@ -84,7 +84,8 @@ struct vtmgpu_ctx
   std::vector<int> cur;                // buffer index holding the current state of each slot
   int64_t launches = 0;
   int numSms = 0;
-  CUtensorMap* tmapsDev = nullptr;     // [capacity][3 buffers][3 planes]: TMA descriptors of the plane buffers (box = smem tile of k_sao_alf)
+  CUtensorMap* tmapsDev = nullptr;     // [capacity][3 buffers][3 planes]: TMA descriptors of the plane buffers, box = smem tile of k_alf
+  CUtensorMap* tmapsDbfDev = nullptr;  // the same planes, box = smem tile of k_dbf_sao
 
   int fail(const char* fmt, ...)
   {
@@ -143,6 +144,7 @@ extern "C" void vtmgpu_destroy(vtmgpu_ctx* c)
   if (c->slotsPinned) cudaFreeHost(c->slotsPinned);
   if (c->slotsDev) cudaFree(c->slotsDev);
   if (c->tmapsDev) cudaFree(c->tmapsDev);
+  if (c->tmapsDbfDev) cudaFree(c->tmapsDbfDev);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   for (auto& e : c->stageEv) if (e) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -251,22 +253,27 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
     CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres), "cuTensorMapEncodeTiled lookup");
     if (!fn || qres != cudaDriverEntryPointSuccess) { g_createError = "vtmgpu_create: driver has no cuTensorMapEncodeTiled"; vtmgpu_destroy(c); return -1; }
     const SaLayout SL = saLayout(g.sx, g.sy, g.ncomp);
-    std::vector<CUtensorMap> maps((size_t)s.capacity * 9);
-    memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
-    for (int sl = 0; sl < s.capacity; sl++)
-      for (int b = 0; b < 3; b++)
-        for (int k = 0; k < g.ncomp; k++)
-        {
-          const PlaneDev& pd = c->slotsPinned[sl].buf[b][k];
-          const cuuint64_t dims[2] = { (cuuint64_t)pd.w, (cuuint64_t)pd.h }, strides[1] = { (cuuint64_t)pd.pitch * 2 };
-          const cuuint32_t box[2] = { (cuuint32_t)(k ? SL.pitchC : SA_P), (cuuint32_t)(k ? SL.rowsC : SA_H) }, es[2] = { 1, 1 };
-          const CUresult r = reinterpret_cast<EncodeFn>(fn)(&maps[((size_t)sl * 3 + b) * 3 + k], CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, pd.p, dims, strides, box, es,
-                                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-          if (r != CUDA_SUCCESS) { g_createError = "vtmgpu_create: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"; vtmgpu_destroy(c); return -1; }
-        }
-    CK(cudaMalloc((void**)&c->tmapsDev, maps.size() * sizeof(CUtensorMap)), "tensor maps");
-    CK(cudaMemcpy(c->tmapsDev, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice), "tensor maps upload");
+    for (int which = 0; which < 2; which++)
+    {
+      std::vector<CUtensorMap> maps((size_t)s.capacity * 9);
+      memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
+      for (int sl = 0; sl < s.capacity; sl++)
+        for (int b = 0; b < 3; b++)
+          for (int k = 0; k < g.ncomp; k++)
+          {
+            const PlaneDev& pd = c->slotsPinned[sl].buf[b][k];
+            const cuuint64_t dims[2] = { (cuuint64_t)pd.w, (cuuint64_t)pd.h }, strides[1] = { (cuuint64_t)pd.pitch * 2 };
+            const cuuint32_t boxAlf[2] = { (cuuint32_t)(k ? SL.pitchC : SA_P), (cuuint32_t)(k ? SL.rowsC : SA_H) };
+            const cuuint32_t boxDbf[2] = { (cuuint32_t)DBF_PITCH, (cuuint32_t)DBF_SH }, es[2] = { 1, 1 };
+            const CUresult r = reinterpret_cast<EncodeFn>(fn)(&maps[((size_t)sl * 3 + b) * 3 + k], CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, pd.p, dims, strides,
+                                                              which ? boxDbf : boxAlf, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { g_createError = "vtmgpu_create: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"; vtmgpu_destroy(c); return -1; }
+          }
+      CUtensorMap** dev = which ? &c->tmapsDbfDev : &c->tmapsDev;
+      CK(cudaMalloc((void**)dev, maps.size() * sizeof(CUtensorMap)), "tensor maps");
+      CK(cudaMemcpy(*dev, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice), "tensor maps upload");
+    }
   }
   {
     // the 16 fixed luma filter sets (AdaptiveLoopFilter.cpp:204-289, clip = 1 << bitDepth :500-509) never change: expand and upload once
@@ -285,6 +292,7 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
     }
   }
   CK(cudaMemcpyAsync(c->slotsDev, c->slotsPinned, sizeof(SlotDev) * s.capacity, cudaMemcpyHostToDevice, c->stream), "slot table upload");
+  CK(cudaFuncSetAttribute(k_dbf_sao, cudaFuncAttributeMaxDynamicSharedMemorySize, DBF_SMEM_BYTES), "smem attribute");
   CK(cudaFuncSetAttribute(k_alf, cudaFuncAttributeMaxDynamicSharedMemorySize, saLayout(g.sx, g.sy, g.ncomp).total), "smem attribute");
   CK(cudaDeviceGetAttribute(&c->numSms, cudaDevAttrMultiProcessorCount, s.device), "device attribute");
   CK(cudaStreamSynchronize(c->stream), "sync");
@@ -621,7 +629,12 @@ int launchDbfSao(vtmgpu_ctx* c, int first, int count, int doDbf, int doSao)
   L.tilesC = g.ncomp > 1 ? L.tilesXC * (((g.h >> g.sy) + DBF_TH - 1) / DBF_TH) : 0;
   return forRuns(c, first, count, [&](int s, int n, int src) {
     const int dst = src == 1 ? 2 : 1;
-    k_dbf_sao<<<dim3(L.tilesL + 2 * L.tilesC, n), DBF_THREADS, 0, c->stream>>>(c->slotsDev, s, src, dst, g, L, doDbf, doSao);
+    // persistent CTAs: three per SM, each walks the plane tiles round robin with double-buffered TMA loads
+    const int items = L.tilesL + 2 * L.tilesC, grid = std::min(items * n, 3 * c->numSms);
+    TileStep st;
+    st.dSlot = grid / items;
+    st.dItem = grid % items;
+    k_dbf_sao<<<grid, DBF_THREADS, DBF_SMEM_BYTES, c->stream>>>(c->slotsDev, c->tmapsDbfDev, s, n, src, dst, g, L, st, doDbf, doSao);
     c->launches++;
     for (int i = s; i < s + n; i++) c->cur[i] = dst;
     return c->cuda(cudaGetLastError(), "k_dbf_sao launch");
