@@ -205,6 +205,56 @@ __device__ void dbfLumaSegment(pel* x0, int o, int s, uint32_t rec, int maxv)
   }
 }
 
+// The same decisions as dbfLumaSegment, spread over the 4 lanes of a quad: lane ln owns line ln of the segment, computes the
+// gradients / strong-filter tests of its own line, lines 0 and 3 are broadcast with shuffles (xEdgeFilterLuma evaluates the
+// first and the last line of a segment, LoopFilter.cpp:977-1043), then every lane filters its own line.  All 32 lanes of
+// the warp must call this together; `valid` = false marks a quad without work (reads stay legal, nothing is written).
+__device__ __forceinline__ void dbfLumaSegmentQuad(pel* x0, int o, int s, uint32_t rec, int maxv, int ln, bool valid)
+{
+  const int tc = rec & 0x7ff;
+  const int beta = (rec >> VTMGPU_DBF_L_BETA_SHIFT) & 0x7ff;
+  const int lenP = (rec >> VTMGPU_DBF_L_LENP_SHIFT) & 7, lenQ = (rec >> VTMGPU_DBF_L_LENQ_SHIFT) & 7;
+  const bool wP = valid && !(rec & VTMGPU_DBF_L_PNOFILT), wQ = valid && !(rec & VTMGPU_DBF_L_QNOFILT);
+  const bool largeP = lenP > 3 && !(rec & VTMGPU_DBF_L_CTUROW), largeQ = lenQ > 3;
+  const int sideThr = (beta + (beta >> 1)) >> 3;
+  pel* xl = x0 + ln * s;
+  const pel* x = xl;
+  const int dp = iabs(PK(2) - 2 * PK(1) + PK(0)), dq = iabs(QK(0) - 2 * QK(1) + QK(2));
+  int dpL = dp, dqL = dq;
+  if (largeP) dpL = (dp + iabs(PK(5) - 2 * PK(4) + PK(3)) + 1) >> 1;
+  if (largeQ) dqL = (dq + iabs(QK(3) - 2 * QK(4) + QK(5)) + 1) >> 1;
+  const bool anyLarge = largeP || largeQ;
+  const bool sL = anyLarge && dbfStrongLong(x, o, 2 * (dpL + dqL), beta, tc, largeP, largeQ, lenP, lenQ);
+  const bool sS = lenP > 2 && lenQ > 2 && dbfStrongShort(x, o, 2 * (dp + dq), beta, tc, false);
+  // broadcast lines 0 and 3: gradients packed dp | dq << 16 (each < 2^13), flags in bits 0,1
+  const unsigned lane = threadIdx.x & 31, qb = lane & ~3u;
+  const uint32_t gS = (uint32_t)dp | (uint32_t)dq << 16, gL = (uint32_t)dpL | (uint32_t)dqL << 16, fl = (sL ? 1u : 0u) | (sS ? 2u : 0u);
+  const uint32_t gS0 = __shfl_sync(0xffffffffu, gS, qb), gS3 = __shfl_sync(0xffffffffu, gS, qb + 3);
+  const uint32_t gL0 = __shfl_sync(0xffffffffu, gL, qb), gL3 = __shfl_sync(0xffffffffu, gL, qb + 3);
+  const uint32_t fl0 = __shfl_sync(0xffffffffu, fl, qb), fl3 = __shfl_sync(0xffffffffu, fl, qb + 3);
+  if (anyLarge)
+  {
+    const int dL = (int)(gL0 & 0xffff) + (int)(gL0 >> 16) + (int)(gL3 & 0xffff) + (int)(gL3 >> 16);
+    if (dL < beta && (fl0 & 1) && (fl3 & 1))
+    {
+      dbfLongLine(xl, o, largeP ? lenP : 3, largeQ ? lenQ : 3, tc, wP, wQ);
+      return;
+    }
+  }
+  const int dp0 = gS0 & 0xffff, dq0 = gS0 >> 16, dp3 = gS3 & 0xffff, dq3 = gS3 >> 16;
+  if (dp0 + dq0 + dp3 + dq3 < beta)
+  {
+    bool secondP = false, secondQ = false;
+    if (lenP > 1 && lenQ > 1)
+    {
+      secondP = (dp0 + dp3) < sideThr;
+      secondQ = (dq0 + dq3) < sideThr;
+    }
+    const bool strong = (fl0 & 2) && (fl3 & 2);
+    dbfLumaLine(xl, o, tc, strong, wP, wQ, secondP, secondQ, maxv);
+  }
+}
+
 __device__ __forceinline__ void dbfChromaLine(pel* x, int o, int tc, bool strong, bool ctb, bool wP, bool wQ, int maxv)
 {
   const int p0 = PK(0), p1 = PK(1), q0 = QK(0), q1 = QK(1);
@@ -281,7 +331,8 @@ constexpr int DBF_RECA_BYTES = 5632;                    // pass-1 records of a t
 constexpr int DBF_RECB_BYTES = 4864;                    // pass-2 records: luma 34x17 u32, chroma 66x9 u64
 constexpr int DBF_TILE_BYTES = DBF_SH * DBF_PITCH * 2;  // 24320 (multiple of 128: TMA destination)
 constexpr int DBF_STAGE_BYTES = DBF_TILE_BYTES + DBF_RECA_BYTES + DBF_RECB_BYTES;
-constexpr int DBF_SMEM_BYTES = 2 * DBF_STAGE_BYTES + 16;
+constexpr int DBF_QUEUE = 96;                          // active-segment queue entries per warp (a warp scans <= 96 slots per pass)
+constexpr int DBF_SMEM_BYTES = 2 * DBF_STAGE_BYTES + 16 + (DBF_THREADS / 32) * DBF_QUEUE * 2;
 
 struct DbfTile
 {
@@ -318,6 +369,24 @@ __device__ __forceinline__ DbfPassGeom dbfPassGeom(int comp, const Geom& g)
   }
   P.n1 = P.ne1 * P.ns1; P.n2 = P.ne2 * P.ns2;
   return P;
+}
+
+// Warp-local compaction: the warp scans its share of the n record slots (chunks of 32, interleaved over the 8 warps) and
+// queues the indices of the active ones (typically < 10 % of the slots) so that the filters run on full warps.
+template <class RecT, class Active> __device__ __forceinline__ int dbfCompact(const RecT* rec, int n, uint16_t* q, Active act)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int cnt = 0;
+  for (int i0 = warp * 32; i0 < n; i0 += DBF_THREADS)
+  {
+    const int i = i0 + lane;
+    const bool a = i < n && act(rec[i]);
+    const unsigned m = __ballot_sync(0xffffffffu, a);
+    if (a) q[cnt + __popc(m & ((1u << lane) - 1))] = (uint16_t)i;
+    cnt += __popc(m);
+  }
+  __syncwarp();
+  return cnt;
 }
 
 // issues the asynchronous loads of one tile into a stage: the TMA box (one thread) and the records (all threads, cp.async)
@@ -379,7 +448,8 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
 {
   extern __shared__ __align__(128) unsigned char smraw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + 2 * DBF_STAGE_BYTES);
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
+  uint16_t* queue = reinterpret_cast<uint16_t*>(smraw + 2 * DBF_STAGE_BYTES + 16) + (tid >> 5) * DBF_QUEUE;
   const int itemsPerSlot = L.tilesL + 2 * L.tilesC;
   int slot = blockIdx.x / itemsPerSlot, item = blockIdx.x - slot * itemsPerSlot;
   if (slot >= numSlots) return;
@@ -437,24 +507,30 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
       {
         const uint32_t* ra = reinterpret_cast<const uint32_t*>(stageMem + DBF_TILE_BYTES);
         const uint32_t* rbv = reinterpret_cast<const uint32_t*>(stageMem + DBF_TILE_BYTES + DBF_RECA_BYTES);
-        // pass 1: vertical edges x0-4 .. x0+TW+4 (step 4), all rows of tile + halo
+        // pass 1: vertical edges x0-4 .. x0+TW+4 (step 4), all rows of tile + halo; 8 segments per warp round, one line per lane
         constexpr int NE = DBF_TW / 4 + 3;
-        for (int i = tid; i < P.n1; i += DBF_THREADS)
         {
-          const uint32_t rec = ra[i];
-          if (!(rec & 0x7ff)) continue;
-          const int sg = i / NE, e = i - sg * NE;
-          dbfLumaSegment(&sm[(4 * sg) * DBF_PITCH + DBF_HALO - 4 + 4 * e], 1, DBF_PITCH, rec, maxv);
+          const int cnt = dbfCompact(ra, P.n1, queue, [](uint32_t r) { return (r & 0x7ff) != 0; });
+          for (int k0 = 0; k0 < cnt; k0 += 8)
+          {
+            const int k = k0 + (lane >> 2);
+            const bool valid = k < cnt;
+            const int i = queue[valid ? k : k0], sg = i / NE, e = i - sg * NE;
+            dbfLumaSegmentQuad(&sm[(4 * sg) * DBF_PITCH + DBF_HALO - 4 + 4 * e], 1, DBF_PITCH, ra[i], maxv, lane & 3, valid);
+          }
         }
         __syncthreads();
         // pass 2: horizontal edges y0 .. y0+TH (step 4), columns x0-4 .. x0+TW+3
         constexpr int NSH = DBF_TW / 4 + 2;
-        for (int i = tid; i < P.n2; i += DBF_THREADS)
         {
-          const uint32_t rec = rbv[i];
-          if (!(rec & 0x7ff)) continue;
-          const int e = i / NSH, sg = i - e * NSH;
-          dbfLumaSegment(&sm[(DBF_HALO + 4 * e) * DBF_PITCH + DBF_HALO - 4 + 4 * sg], DBF_PITCH, 1, rec, maxv);
+          const int cnt = dbfCompact(rbv, P.n2, queue, [](uint32_t r) { return (r & 0x7ff) != 0; });
+          for (int k0 = 0; k0 < cnt; k0 += 8)
+          {
+            const int k = k0 + (lane >> 2);
+            const bool valid = k < cnt;
+            const int i = queue[valid ? k : k0], e = i / NSH, sg = i - e * NSH;
+            dbfLumaSegmentQuad(&sm[(DBF_HALO + 4 * e) * DBF_PITCH + DBF_HALO - 4 + 4 * sg], DBF_PITCH, 1, rbv[i], maxv, lane & 3, valid);
+          }
         }
       }
       else
@@ -464,25 +540,28 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
         const int c = comp - 1;
         const int tcShift = c ? VTMGPU_DBF_C_TCCR_SHIFT : 0, betaShift = c ? VTMGPU_DBF_C_BETACR_SHIFT : VTMGPU_DBF_C_BETACB_SHIFT;
         // pass 1: vertical edges on the 8-sample chroma grid; one item = the chroma rows of one 4-luma-row unit
-        for (int i = tid; i < P.n1; i += DBF_THREADS)
         {
-          const uint64_t rec = ra[i];
-          const int tc = (int)(rec >> tcShift) & 0x7ff;
-          if (!tc) continue;
-          const int sg = i / P.ne1, e = i - sg * P.ne1;
-          dbfChromaSegment(&sm[(P.nv * sg) * DBF_PITCH + DBF_HALO + 8 * e], 1, DBF_PITCH, P.nv, tc, (int)(rec >> betaShift) & 0x7ff,
-                           (rec & VTMGPU_DBF_C_LARGE) != 0, (rec & VTMGPU_DBF_C_CTB) != 0, !(rec & VTMGPU_DBF_C_PNOFILT), !(rec & VTMGPU_DBF_C_QNOFILT), maxv);
+          const int cnt = dbfCompact(ra, P.n1, queue, [tcShift](uint64_t r) { return ((r >> tcShift) & 0x7ff) != 0; });
+          for (int k = lane; k < cnt; k += 32)
+          {
+            const int i = queue[k], sg = i / P.ne1, e = i - sg * P.ne1;
+            const uint64_t rec = ra[i];
+            dbfChromaSegment(&sm[(P.nv * sg) * DBF_PITCH + DBF_HALO + 8 * e], 1, DBF_PITCH, P.nv, (int)(rec >> tcShift) & 0x7ff, (int)(rec >> betaShift) & 0x7ff,
+                             (rec & VTMGPU_DBF_C_LARGE) != 0, (rec & VTMGPU_DBF_C_CTB) != 0, !(rec & VTMGPU_DBF_C_PNOFILT), !(rec & VTMGPU_DBF_C_QNOFILT), maxv);
+          }
         }
         __syncthreads();
         // pass 2: horizontal edges, one more segment of columns on each side of the tile
-        for (int i = tid; i < P.n2; i += DBF_THREADS)
         {
-          const uint64_t rec = rbv[i];
-          const int tc = (int)(rec >> tcShift) & 0x7ff;
-          if (!tc) continue;
-          const int e = i / P.ns2, sg = i - e * P.ns2;
-          dbfChromaSegment(&sm[(DBF_HALO + 8 * e) * DBF_PITCH + DBF_HALO - P.nh + P.nh * sg], DBF_PITCH, 1, P.nh, tc, (int)(rec >> betaShift) & 0x7ff,
-                           (rec & VTMGPU_DBF_C_LARGE) != 0, (rec & VTMGPU_DBF_C_CTB) != 0, !(rec & VTMGPU_DBF_C_PNOFILT), !(rec & VTMGPU_DBF_C_QNOFILT), maxv);
+          const int cnt = dbfCompact(rbv, P.n2, queue, [tcShift](uint64_t r) { return ((r >> tcShift) & 0x7ff) != 0; });
+          for (int k = lane; k < cnt; k += 32)
+          {
+            const int i = queue[k], e = i / P.ns2, sg = i - e * P.ns2;
+            const uint64_t rec = rbv[i];
+            dbfChromaSegment(&sm[(DBF_HALO + 8 * e) * DBF_PITCH + DBF_HALO - P.nh + P.nh * sg], DBF_PITCH, 1, P.nh, (int)(rec >> tcShift) & 0x7ff,
+                             (int)(rec >> betaShift) & 0x7ff, (rec & VTMGPU_DBF_C_LARGE) != 0, (rec & VTMGPU_DBF_C_CTB) != 0, !(rec & VTMGPU_DBF_C_PNOFILT),
+                             !(rec & VTMGPU_DBF_C_QNOFILT), maxv);
+          }
         }
       }
       __syncthreads();
