@@ -402,6 +402,8 @@ __device__ __forceinline__ void dbfPrefetch(unsigned char* stageMem, uint64_t* b
   }
   if (!dbfOn) return;
   const DbfPassGeom P = dbfPassGeom(T.comp, g);
+  // i / n == (i * ceil(65536 / n)) >> 16 for i < 4096
+  const int rcp1 = (65536 + P.ne1 - 1) / P.ne1, rcp2 = (65536 + P.ns2 - 1) / P.ns2;
   if (T.comp == 0)
   {
     const int uw = g.w >> 2, uh = g.h >> 2;
@@ -409,13 +411,13 @@ __device__ __forceinline__ void dbfPrefetch(unsigned char* stageMem, uint64_t* b
     uint32_t* rb = reinterpret_cast<uint32_t*>(stageMem + DBF_TILE_BYTES + DBF_RECA_BYTES);
     for (int i = tid; i < P.n1; i += DBF_THREADS)
     {
-      const int sg = i / P.ne1, e = i - sg * P.ne1;
+      const int sg = (i * rcp1) >> 16, e = i - sg * P.ne1;
       const int ux = (T.x0 >> 2) - 1 + e, uy = ((T.y0 - DBF_HALO) >> 2) + sg;
       if (ux > 0 && ux < uw && uy >= 0 && uy < uh) cpAsync4(&ra[i], &S.dbfL[0][uy * uw + ux]); else ra[i] = 0;
     }
     for (int i = tid; i < P.n2; i += DBF_THREADS)
     {
-      const int e = i / P.ns2, sg = i - e * P.ns2;
+      const int e = (i * rcp2) >> 16, sg = i - e * P.ns2;
       const int ux = (T.x0 >> 2) - 1 + sg, uy = (T.y0 >> 2) + e;
       if (uy > 0 && uy < uh && ux >= 0 && ux < uw) cpAsync4(&rb[i], &S.dbfL[1][uy * uw + ux]); else rb[i] = 0;
     }
@@ -429,15 +431,15 @@ __device__ __forceinline__ void dbfPrefetch(unsigned char* stageMem, uint64_t* b
     uint64_t* rb = reinterpret_cast<uint64_t*>(stageMem + DBF_TILE_BYTES + DBF_RECA_BYTES);
     for (int i = tid; i < P.n1; i += DBF_THREADS)
     {
-      const int sg = i / P.ne1, e = i - sg * P.ne1;
+      const int sg = (i * rcp1) >> 16, e = i - sg * P.ne1;
       const int x = T.x0 + 8 * e, y = T.y0 - DBF_HALO + P.nv * sg;
-      if (x > 0 && x < cw && y >= 0 && y < ch) cpAsync8(&ra[i], &S.dbfC[0][(y / P.nv) * cols0 + (x >> 3)]); else ra[i] = 0;
+      if (x > 0 && x < cw && y >= 0 && y < ch) cpAsync8(&ra[i], &S.dbfC[0][(y >> (2 - g.sy)) * cols0 + (x >> 3)]); else ra[i] = 0;
     }
     for (int i = tid; i < P.n2; i += DBF_THREADS)
     {
-      const int e = i / P.ns2, sg = i - e * P.ns2;
+      const int e = (i * rcp2) >> 16, sg = i - e * P.ns2;
       const int x = T.x0 - P.nh + P.nh * sg, y = T.y0 + 8 * e;
-      if (y > 0 && y < ch && x >= 0 && x < cw) cpAsync8(&rb[i], &S.dbfC[1][(y >> 3) * uw + (x / P.nh)]); else rb[i] = 0;
+      if (y > 0 && y < ch && x >= 0 && x < cw) cpAsync8(&rb[i], &S.dbfC[1][(y >> 3) * uw + (x >> (2 - g.sx))]); else rb[i] = 0;
     }
   }
 }
@@ -460,9 +462,9 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  DbfTile T = dbfDecodeTile(item, L), Tn = T;
   {
     const SlotDev& S = slots[firstSlot + slot];
-    const DbfTile T = dbfDecodeTile(item, L);
     dbfPrefetch(smraw, &bars[0], S, tmaps + ((size_t)(firstSlot + slot) * 3 + srcBuf) * 3 + T.comp, T, g, doDbf && S.dbfOn);
     cpAsyncCommit();
   }
@@ -471,13 +473,12 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
     const int stage = it & 1;
     unsigned char* stageMem = smraw + stage * DBF_STAGE_BYTES;
     const SlotDev& S = slots[firstSlot + slot];
-    const DbfTile T = dbfDecodeTile(item, L);
     int nslot = slot + step.dSlot, nitem = item + step.dItem;
     if (nitem >= itemsPerSlot) { nitem -= itemsPerSlot; nslot++; }
     if (nslot < numSlots)
     {
       const SlotDev& Sn = slots[firstSlot + nslot];
-      const DbfTile Tn = dbfDecodeTile(nitem, L);
+      Tn = dbfDecodeTile(nitem, L);
       dbfPrefetch(smraw + (stage ^ 1) * DBF_STAGE_BYTES, &bars[stage ^ 1], Sn, tmaps + ((size_t)(firstSlot + nslot) * 3 + srcBuf) * 3 + Tn.comp, Tn, g,
                   doDbf && Sn.dbfOn);
     }
@@ -488,7 +489,7 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
     const int w = dst.w, h = dst.h;
     // SAO parameters of this thread's strip (one 8-sample group column x 4 rows; a 4-row strip never crosses a CTU boundary):
     // loaded now, consumed after the deblocking passes
-    const int gcol = tid & (DBF_TW / 8 - 1), rb = tid / (DBF_TW / 8);
+    const int gcol = (tid & 7) | ((tid >> 4) & 8), rb = (tid >> 3) & 15;     // warp = 8 group columns x 4 row blocks: one CTU for every plane
     const int sx_ = x0 + 8 * gcol, sy_ = y0 + 4 * rb;
     const int cwLog = g.ctuLog2 - (comp ? g.sx : 0), chLog = g.ctuLog2 - (comp ? g.sy : 0);
     uint4 pq = make_uint4(0, 0, 0, 0);
@@ -572,7 +573,7 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
       saoStrip(dst.p + (size_t)sy_ * dst.pitch + sx_, dst.pitch, &sm[(DBF_HALO + 4 * rb) * DBF_PITCH + DBF_HALO + 8 * gcol], DBF_PITCH, min(4, h - sy_), sx_, sy_,
                pq, w, h, cwLog | chLog << 8 | (comp ? g.bdC : g.bdL) << 16);
     __syncthreads();                                         // the stage is free for the load after next
-    slot = nslot; item = nitem;
+    slot = nslot; item = nitem; T = Tn;
   }
 }
 
