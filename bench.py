@@ -34,7 +34,8 @@ W4K, H4K = 3840, 2160
 B_ALG_CHAIN = 6.5          # algorithmic bytes per luma pixel of the whole chain at 4:2:0 (SURVEY.md 8d / BASELINE.md 3)
 B_ALG_DBF = 6.5            # k_dbf_sao : read 3 + write 3 + 0.5 segment records
 B_ALG_SAOALF = 6.0         # k_alf     : read 3 + write 3 (CTU parameters negligible)
-CAP_DIR = os.path.join(ROOT, "data", "captures", "ra_2160p")
+STREAM_4K = os.path.join(ROOT, "tests", "golden", "streams", "ra_2160p_8.bin")
+DEC_GPU = os.path.join(ROOT, "vvc_b200", "_bin", "DecoderApp_gpu")
 
 
 def measured_peak():
@@ -82,14 +83,30 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------------------------
 # workload
 # ------------------------------------------------------------------------------------------------------------------
-def load_pictures(distinct):
-    """Returns (list of Capture, description)."""
+def load_pictures(distinct, device):
+    """Returns (list of Capture, description).
+
+    Preferred workload (BASELINE config 3): the VTM-encoded 3840x2160 RA stream of synthetic YUV (tests/golden/streams) is
+    decoded HERE by the reference decoder with our filters dropped in (vvc_b200/_bin/DecoderApp_gpu, every picture must
+    print MD5 (OK)); the shim's capture mode records what crosses the boundary per picture -- pre-filter planes and the
+    flattened side information -- and those pictures are replayed.  Fallback: seeded synthetic pictures."""
+    import shutil
+    import tempfile
     from vvc_b200 import capture, synth
-    files = sorted(glob.glob(os.path.join(CAP_DIR, "*.npz")))[:distinct]
-    if len(files) >= 1:
-        caps = [capture.load(f) for f in files]
-        if caps[0].width == W4K and caps[0].height == H4K:
-            return caps, "captured: VTM-encoded (RA, QP32, CC-ALF) synthetic YUV, %d distinct pictures" % len(caps)
+    if os.path.exists(STREAM_4K) and os.path.exists(DEC_GPU) and not os.environ.get("VTMGPU_BENCH_SYNTH"):
+        tmp = tempfile.mkdtemp(prefix="vtmgpu_cap_")
+        try:
+            env = dict(os.environ, VTMGPU_SHIM_BACKEND="gpu", VTMGPU_CAPTURE_DIR=tmp, VTMGPU_DEVICE=str(device))
+            r = subprocess.run([DEC_GPU, "-b", STREAM_4K, "-d", "0"], env=env, capture_output=True, text=True, timeout=600)
+            ok = r.stdout.count("(OK)")
+            files = sorted(glob.glob(os.path.join(tmp, "*.cap")))
+            if r.returncode == 0 and ok == len(files) and ok >= 1 and "ERROR" not in r.stdout:
+                caps = [capture.load(f) for f in files[:distinct]]
+                return caps, ("captured: VTM-encoded (RA, QP32, CC-ALF) synthetic 4K YUV decoded by DecoderApp_gpu, %d/%d pictures MD5 (OK), "
+                              "%d distinct pictures replayed" % (ok, len(files), len(caps)))
+            sys.stderr.write("bench.py: DecoderApp_gpu capture failed (rc=%d, OK=%d): %s\n" % (r.returncode, ok, (r.stdout + r.stderr)[-400:]))
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
     caps = [synth.make_picture(W4K, H4K, seed=2160 + i, density=0.6) for i in range(distinct)]
     return caps, "synthetic planes + synthetic side info (vvc_b200/synth.py density 0.6), %d distinct pictures" % distinct
 
@@ -109,7 +126,7 @@ def cpu_reference_run(max_procs=None, repeats=1):
     all started together on the 4K stream; the shim's steady_clock timers bracket ONLY those three reference calls.
     Returns (Mpixel/s aggregate, cores, kind, sample description) or None."""
     dec = os.path.join(ROOT, "oracle", "_ref", "DecoderApp_cap")
-    streams = [os.path.join(ROOT, "data", "streams", n) for n in ("ra_2160p_8.bin", "ra_1080p.bin", "ra_416x240.bin")]
+    streams = [os.path.join(ROOT, "tests", "golden", "streams", n) for n in ("ra_2160p_8.bin", "ra_1080p.bin", "ra_416x240.bin")]
     stream = next((s for s in streams if os.path.exists(s)), None)
     cores = len(os.sched_getaffinity(0))
     if max_procs:
@@ -220,7 +237,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    caps, workload = load_pictures(args.distinct)
+    caps, workload = load_pictures(args.distinct, local)
     B = args.batch
     seq = caps[0].seq
     px_per_pic = caps[0].luma_pixels()
