@@ -221,7 +221,12 @@ __device__ __forceinline__ void alfOwnCells(uint2 (*cell)[SA_CELLP], const pel* 
 // 7x7 diamond on one 4x4 block, two pixels per register.  e = pre-expanded {coefficient, clip} entry of the block's
 // (filter set, class, transpose).  clamp(n - cur, -c, c) + c  ==  max(min(n + (c - cur), 2c), 0)  is ONE instruction;
 // the excess sum(coef * 2c) is folded into e->bias together with the rounding offset 64 (filterBlk :1249-1297).
-__device__ __forceinline__ void alfLumaBlockFast(const pel* c0, pel* out, int pitchOut, const AlfLumaEntry* __restrict__ e, uint32_t maxvP)
+//
+// VB = 0: block away from the virtual boundary.  VB = 1 / 2: the block directly above / below the boundary (CTU rows
+// vbPos-4..vbPos-1 / vbPos..vbPos+3): tap rows are clamped to the rows on the block's side of the boundary
+// (filterBlk :1227-1247: row offset min(|dy|, lim) with lim = 3 - orow above, orow below) and the row adjacent to the
+// boundary is rounded with >> 10 (:1288-1295).  All of it folds into compile-time register indices.
+template <int VB> __device__ __forceinline__ void alfLumaBlockFast(const pel* c0, pel* out, int pitchOut, const AlfLumaEntry* __restrict__ e, uint32_t maxvP)
 {
   uint32_t coefB[12], clipP1[12], clip2[12];
   {
@@ -248,17 +253,20 @@ __device__ __forceinline__ void alfLumaBlockFast(const pel* c0, pel* out, int pi
     for (int j = 0; j < 5; j++) o[ir][j] = mid16(w[ir][j], w[ir][j + 1]);
   }
 #define ALF_PAIR(IR, C) ((((C) & 1) != 0) ? o[IR][((C) + 3) >> 1] : w[IR][((C) + 4) >> 1])
+#define ALF_ROW(DY) ((DY) < lim ? (DY) : lim)
 #define ALF_TAP(K, DX, DY)                                                                                              \
   {                                                                                                                     \
     const uint32_t cb = __vadd2(clipP1[K], ncur);                                                                       \
-    const uint32_t s = addClamp0(ALF_PAIR(orow + 3 + (DY), 2 * px + (DX)), cb, clip2[K]) +                              \
-                       addClamp0(ALF_PAIR(orow + 3 - (DY), 2 * px - (DX)), cb, clip2[K]);                               \
+    const uint32_t s = addClamp0(ALF_PAIR(orow + 3 + ALF_ROW(DY), 2 * px + (DX)), cb, clip2[K]) +                       \
+                       addClamp0(ALF_PAIR(orow + 3 - ALF_ROW(DY), 2 * px - (DX)), cb, clip2[K]);                        \
     acc0 = __dp2a_lo((int)s, (int)coefB[K], acc0);                                                                      \
     acc1 = __dp2a_hi((int)s, (int)coefB[K], acc1);                                                                      \
   }
 #pragma unroll
   for (int orow = 0; orow < 4; orow++)
   {
+    const int lim = VB == 0 ? 3 : (VB == 1 ? 3 - orow : orow);                 // rows available on this side of the virtual boundary
+    const int sh = (VB == 1 && orow == 3) || (VB == 2 && orow == 0) ? 10 : 7;
     uint32_t res[2];
 #pragma unroll
     for (int px = 0; px < 2; px++)
@@ -269,11 +277,12 @@ __device__ __forceinline__ void alfLumaBlockFast(const pel* c0, pel* out, int pi
       ALF_TAP(1, 1, 2) ALF_TAP(2, 0, 2) ALF_TAP(3, -1, 2)
       ALF_TAP(4, 2, 1) ALF_TAP(5, 1, 1) ALF_TAP(6, 0, 1) ALF_TAP(7, -1, 1) ALF_TAP(8, -2, 1)
       ALF_TAP(9, 3, 0) ALF_TAP(10, 2, 0) ALF_TAP(11, 1, 0)
-      res[px] = addClamp0(cur, prmt((uint32_t)(acc0 >> 7), (uint32_t)(acc1 >> 7), 0x5410u), maxvP);
+      res[px] = addClamp0(cur, prmt((uint32_t)(acc0 >> sh), (uint32_t)(acc1 >> sh), 0x5410u), maxvP);
     }
     *reinterpret_cast<uint2*>(out + (size_t)orow * pitchOut) = make_uint2(res[0], res[1]);
   }
 #undef ALF_TAP
+#undef ALF_ROW
 #undef ALF_PAIR
 }
 
@@ -538,22 +547,29 @@ __global__ void __launch_bounds__(SA_THREADS, 2) k_alf(const SlotDev* __restrict
       {
         pel* out = dstY.p + (size_t)by * dstY.pitch + bx;
         const int setIdx = ctl.setIdx;
-        if (vbBlk || S.alfWide) alfLumaBlockGeneric(cell, c0, out, dstY.pitch, bi, bj, by, &S.alf->luma[setIdx][0][0], ctuMask, vbL, g.bdL);
+        if (S.alfWide) alfLumaBlockGeneric(cell, c0, out, dstY.pitch, bi, bj, by, &S.alf->luma[setIdx][0][0], ctuMask, vbL, g.bdL);
         else
         {
-          // window = cells (2bi .. 2bi+3) x (2bj .. 2bj+3); row sums stay below 2^16 per lane for any bit depth <= 12
+          // window = cells (2bi .. 2bi+3) x (2bj .. 2bj+3); row sums stay below 2^16 per lane for any bit depth <= 12.
+          // Blocks at the virtual boundary use 3 of the 4 cell rows and the scale 96 (deriveClassificationBlk :977-1010)
+          const int vb = yb == vbL - 4 ? 1 : (yb == vbL ? 2 : 0);
           int sumV = 0, sumH = 0, sumD0 = 0, sumD1 = 0;
 #pragma unroll
           for (int i = 0; i < 4; i++)
           {
+            if ((vb == 1 && i == 3) || (vb == 2 && i == 0)) continue;
             const uint4* rp = reinterpret_cast<const uint4*>(&cell[2 * bi + i][2 * bj]);
             const uint4 q0 = rp[0], q1 = rp[1];
             const uint32_t vh = q0.x + q0.z + q1.x + q1.z, dd = q0.y + q0.w + q1.y + q1.w;
             sumV += vh & 0xffff; sumH += vh >> 16; sumD0 += dd & 0xffff; sumD1 += dd >> 16;
           }
           int cls, tIdx;
-          alfClassify(sumV, sumH, sumD0, sumD1, 64, g.bdL, cls, tIdx);
-          alfLumaBlockFast(c0, out, dstY.pitch, S.lumaTab + ((size_t)(setIdx * 25 + cls) * 4 + tIdx), dup16((1 << g.bdL) - 1));
+          alfClassify(sumV, sumH, sumD0, sumD1, vb ? 96 : 64, g.bdL, cls, tIdx);
+          const AlfLumaEntry* e = S.lumaTab + ((size_t)(setIdx * 25 + cls) * 4 + tIdx);
+          const uint32_t maxvP = dup16((1 << g.bdL) - 1);
+          if (vb == 0) alfLumaBlockFast<0>(c0, out, dstY.pitch, e, maxvP);          // vb is uniform per warp for CTU sizes >= 32
+          else if (vb == 1) alfLumaBlockFast<1>(c0, out, dstY.pitch, e, maxvP);
+          else alfLumaBlockFast<2>(c0, out, dstY.pitch, e, maxvP);
         }
       }
     }
