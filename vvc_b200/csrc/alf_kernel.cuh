@@ -32,13 +32,16 @@
 namespace vtmgpu
 {
 
-constexpr int SA_T = 64;                    // luma tile edge
-constexpr int SA_THREADS = 256;             // = (SA_T/4)^2 : one thread per 4x4 luma block
+constexpr int SA_T = 64;                    // luma tile width
+constexpr int SA_TH = 32;                   // luma tile height
+constexpr int SA_THLOG = 5;
+constexpr int SA_THREADS = (SA_T / 4) * (SA_TH / 4);   // 128: one thread per 4x4 luma block; small CTAs (4 per SM) decorrelate the phases
 constexpr int SA_HX = 8, SA_HY = 4;         // halo loaded around a tile (x: one aligned group of 8)
 constexpr int SA_W = SA_T + 2 * SA_HX;      // 80
-constexpr int SA_H = SA_T + 2 * SA_HY;      // 72
+constexpr int SA_H = SA_TH + 2 * SA_HY;     // 40
 constexpr int SA_P = SA_W + 8;              // smem pitch in samples (88 -> 176 B: rows shift by 12 banks)
-constexpr int SA_CELLS = SA_T / 2 + 2;      // 34 Laplacian cells (2x2 samples) per dimension: tile + 2 samples each side
+constexpr int SA_CELLS = SA_T / 2 + 2;      // 34 Laplacian cells (2x2 samples) per row: tile + 2 samples each side
+constexpr int SA_CELLR = SA_TH / 2 + 2;     // 18 cell rows
 constexpr int SA_CELLP = SA_CELLS + 2;      // cell row pitch (uint2 units)
 
 __constant__ int8_t c_perm7[4][12] = { { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11 }, { 9, 4, 10, 8, 1, 5, 11, 7, 3, 0, 2, 6 },
@@ -62,13 +65,13 @@ struct SaLayout
 __host__ __device__ inline SaLayout saLayout(int sx, int sy, int ncomp)
 {
   SaLayout L;
-  const int tw = SA_T >> sx, th = SA_T >> sy;
+  const int tw = SA_T >> sx, th = SA_TH >> sy;
   L.pitchC = tw + 2 * SA_HX + 8;
   L.rowsC = th + 2 * SA_HY;
   L.lumaBytes = SA_H * SA_P * 2;
   L.chromaBytes = ncomp > 1 ? L.rowsC * L.pitchC * 2 : 0;
   L.offCell = 2 * (L.lumaBytes + 2 * L.chromaBytes);
-  L.offPar = L.offCell + SA_CELLS * SA_CELLP * 8;
+  L.offPar = L.offCell + SA_CELLR * SA_CELLP * 8;
   L.offBar = L.offPar + 2 * (int)sizeof(CtuCtlDev);
   L.total = L.offBar + 16;
   return L;
@@ -419,7 +422,7 @@ __device__ __forceinline__ void saAdvance(SaWalk& p, const SaStep& st, int tiles
 __device__ __forceinline__ void saPrefetch(unsigned char* smraw, const SaLayout& L, int stage, const SlotDev& S, const CUtensorMap* maps, const SaWalk& p,
                                            const Geom& g)
 {
-  const int tid = threadIdx.x, x0 = p.tx * SA_T, y0 = p.ty * SA_T;
+  const int tid = threadIdx.x, x0 = p.tx * SA_T, y0 = p.ty * SA_TH;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smraw + L.offBar) + stage;
   if (tid == 0)
   {
@@ -438,7 +441,7 @@ __device__ __forceinline__ void saPrefetch(unsigned char* smraw, const SaLayout&
 // Persistent kernel: gridDim.x CTAs walk the tiles of slots [firstSlot, firstSlot + numSlots) round robin; while a CTA
 // filters tile i, the TMA loads of tile i+1 are in flight (two stages).  maps = tensor maps of the source buffer of the
 // first slot: [slot][3 buffers][3 planes].
-__global__ void __launch_bounds__(SA_THREADS, 2) k_alf(const SlotDev* __restrict__ slots, const CUtensorMap* __restrict__ tmaps, int firstSlot, int numSlots,
+__global__ void __launch_bounds__(SA_THREADS, 4) k_alf(const SlotDev* __restrict__ slots, const CUtensorMap* __restrict__ tmaps, int firstSlot, int numSlots,
                                                            int srcBuf, int dstBuf, Geom g, int tilesX, int tilesY, SaStep step, int dbg)
 {
   extern __shared__ __align__(128) unsigned char smraw[];
@@ -448,7 +451,7 @@ __global__ void __launch_bounds__(SA_THREADS, 2) k_alf(const SlotDev* __restrict
   uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + L.offBar);
   const int vbL = g.ctu - 4, ctuMask = g.ctu - 1;
   const int bi = tid >> 4, bj = tid & 15;
-  const int tw = SA_T >> g.sx, th = SA_T >> g.sy, thLogC = 6 - g.sy;
+  const int tw = SA_T >> g.sx, th = SA_TH >> g.sy, thLogC = SA_THLOG - g.sy;
   const int cw = g.w >> g.sx, chh = g.h >> g.sy, ctuH = g.ctu >> g.sy;
   const int vbC = ctuH - 2, maxc = (1 << g.bdC) - 1, half = (1 << g.bdC) >> 1;
   const uint32_t maxcP = dup16(maxc), halfP = dup16(half);
@@ -490,7 +493,7 @@ __global__ void __launch_bounds__(SA_THREADS, 2) k_alf(const SlotDev* __restrict
     mbarWait(&bars[stage], (it >> 1) & 1);
     __syncthreads();                                         // tile and its parameters are in shared memory
 
-    const int x0 = cur.tx * SA_T, y0 = cur.ty * SA_T;
+    const int x0 = cur.tx * SA_T, y0 = cur.ty * SA_TH;
     const CtuCtlDev ctl = reinterpret_cast<const CtuCtlDev*>(smraw + L.offPar)[stage];
     const bool alfOn = S.alfOn != 0;
     const bool alfY = alfOn && ctl.enY != 0 && !(dbg & 8), alfCb = alfOn && ctl.enCb != 0, alfCr = alfOn && ctl.enCr != 0;
@@ -500,10 +503,10 @@ __global__ void __launch_bounds__(SA_THREADS, 2) k_alf(const SlotDev* __restrict
     pel* const A2 = reinterpret_cast<pel*>(smraw + L.offA(stage, 2));
     // tiles on the picture border: replicate the border samples into the zero-filled outside
     // (= UnitBuf::extendBorderPel of the ALF input, AdaptiveLoopFilter.cpp:411)
-    const bool onBorder = x0 == 0 || y0 == 0 || x0 + SA_T + 8 > g.w || y0 + SA_T + 8 > g.h;
+    const bool onBorder = x0 == 0 || y0 == 0 || x0 + SA_T + 8 > g.w || y0 + SA_TH + 8 > g.h;
     if (onBorder)
     {
-      if (alfY || ccCb || ccCr) saReplicateBorder(A0, x0 - SA_HX, y0 - SA_HY, g.w, g.h, SA_P, SA_T, SA_T, 3);
+      if (alfY || ccCb || ccCr) saReplicateBorder(A0, x0 - SA_HX, y0 - SA_HY, g.w, g.h, SA_P, SA_T, SA_TH, 3);
       if (alfCb) saReplicateBorder(A1, (x0 >> g.sx) - SA_HX, (y0 >> g.sy) - SA_HY, cw, chh, L.pitchC, tw, th, 3);
       if (alfCr) saReplicateBorder(A2, (x0 >> g.sx) - SA_HX, (y0 >> g.sy) - SA_HY, cw, chh, L.pitchC, tw, th, 3);
       __syncthreads();
@@ -529,11 +532,12 @@ __global__ void __launch_bounds__(SA_THREADS, 2) k_alf(const SlotDev* __restrict
           cell[li][lj] = alfCellGeneric(&lumaB[(2 * li + SA_HY - 2) * SA_P + 2 * lj + SA_HX - 2], y0 - 2 + 2 * li, ctuMask, vbL);
         }
       }
-      if (tid < 4 * (SA_CELLS - 1))
+      // ring of halo cells: top and bottom cell rows, left and right cell columns
+      for (int q = tid; q < 2 * SA_CELLS + 2 * (SA_CELLR - 2); q += SA_THREADS)
       {
-        const int side = tid / (SA_CELLS - 1), k = tid - side * (SA_CELLS - 1);
-        const int li = side == 0 ? 0 : (side == 1 ? SA_CELLS - 1 : (side == 2 ? 1 + k : k));
-        const int lj = side == 0 ? k : (side == 1 ? 1 + k : (side == 2 ? 0 : SA_CELLS - 1));
+        int li, lj;
+        if (q < 2 * SA_CELLS) { li = q < SA_CELLS ? 0 : SA_CELLR - 1; lj = q < SA_CELLS ? q : q - SA_CELLS; }
+        else { const int k = q - 2 * SA_CELLS; li = 1 + (k >> 1); lj = (k & 1) ? SA_CELLS - 1 : 0; }
         cell[li][lj] = alfCellGeneric(&lumaB[(2 * li + SA_HY - 2) * SA_P + 2 * lj + SA_HX - 2], y0 - 2 + 2 * li, ctuMask, vbL);
       }
       __syncthreads();
@@ -576,7 +580,7 @@ __global__ void __launch_bounds__(SA_THREADS, 2) k_alf(const SlotDev* __restrict
     else
     {
       // no luma ALF in this CTU: copy (128-bit rows)
-      for (int i = tid; i < SA_T * (SA_T / 8); i += SA_THREADS)
+      for (int i = tid; i < SA_TH * (SA_T / 8); i += SA_THREADS)
       {
         const int r = i >> 3, gc = i & 7;
         const int y = y0 + r, x = x0 + 8 * gc;

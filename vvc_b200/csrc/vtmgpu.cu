@@ -648,12 +648,12 @@ int launchAlf(vtmgpu_ctx* c, int first, int count)
   for (int s = first; s < first + count; s++) any |= c->slotsPinned[s].alfOn != 0;
   if (!any) return 0;
   const Geom& g = c->g;
-  const int tilesX = (g.w + SA_T - 1) / SA_T, tilesY = (g.h + SA_T - 1) / SA_T;
+  const int tilesX = (g.w + SA_T - 1) / SA_T, tilesY = (g.h + SA_TH - 1) / SA_TH;
   const int smem = saLayout(g.sx, g.sy, g.ncomp).total;
   return forRuns(c, first, count, [&](int s, int n, int src) {
     const int dst = src == 1 ? 2 : 1;
-    // persistent CTAs: two per SM (register limited), each walks the tiles round robin with double-buffered TMA loads
-    const int grid = std::min(tilesX * tilesY * n, 2 * c->numSms);
+    // persistent CTAs: four per SM (register limited), each walks the tiles round robin with double-buffered TMA loads
+    const int grid = std::min(tilesX * tilesY * n, 4 * c->numSms);
     SaStep st;
     st.dx = grid % tilesX;
     st.dy = (grid / tilesX) % tilesY;
