@@ -224,9 +224,30 @@ int vtmgpu_sao_reconstruct(vtmgpu_sao_ctu* ctu, int num_ctus, int width_in_ctus,
 int vtmgpu_deblock(vtmgpu_ctx* ctx, int first, int count);   /* loopFilterPic                              */
 int vtmgpu_sao    (vtmgpu_ctx* ctx, int first, int count);   /* SAOProcess (no-op where SAO is off)        */
 int vtmgpu_alf    (vtmgpu_ctx* ctx, int first, int count);   /* ALFProcess                                 */
+int vtmgpu_deblock_sao(vtmgpu_ctx* ctx, int first, int count);   /* loopFilterPic + SAOProcess in ONE pass (one kernel)   */
 int vtmgpu_sao_alf(vtmgpu_ctx* ctx, int first, int count);   /* SAOProcess + ALFProcess back to back, one sync */
 /* whole chain DBF -> SAO -> ALF in two kernels (deblocking + SAO, ALF + CC-ALF); same result as the three calls above */
 int vtmgpu_filter (vtmgpu_ctx* ctx, int first, int count);
+
+/* ---------------------------------------------------------------------------------------------
+ * band mode (one large picture split into CTU-row bands over several contexts / GPUs).
+ * Every context is created for the FULL picture geometry, so all CTU / virtual-boundary / picture-border rules keep
+ * their absolute positions; it uploads and filters only its band:
+ *   vtmgpu_set_rows(ctx, y0, y1)          stage calls filter luma rows [y0, y1) only (multiples of 128; y1 may be the height)
+ *   vtmgpu_upload_rows(.., y0-8, y1+8)    the band plus the 8 rows the deblocking of its border tiles reads
+ *   vtmgpu_deblock / vtmgpu_sao           exact for the band (they read pre-filter samples only)
+ *   vtmgpu_export_rows / import_rows      4 rows of SAO output on each side of a band border travel to the neighbour
+ *                                         (dense device buffers; the caller moves them with NCCL send/recv over NVLink)
+ *   vtmgpu_alf                            exact for the band (ALF reads 3 rows, the Laplacian classifier 3 rows across)
+ *   vtmgpu_download_rows(.., y0, y1)
+ * plane[k] / stride[k] in the *_rows calls describe the FULL host picture (row 0), as in vtmgpu_upload.
+ * --------------------------------------------------------------------------------------------- */
+int vtmgpu_set_rows(vtmgpu_ctx* ctx, int y_begin, int y_end);
+int vtmgpu_upload_rows  (vtmgpu_ctx* ctx, int slot, const int16_t* const plane[3], const ptrdiff_t stride[3], int y_begin, int y_end);
+int vtmgpu_download_rows(vtmgpu_ctx* ctx, int slot, int16_t* const plane[3], const ptrdiff_t stride[3], int y_begin, int y_end);
+/* rows [y0, y0+nrows) (in samples of component comp) of the slot's current state <-> dense device memory (width * nrows int16) */
+int vtmgpu_export_rows(vtmgpu_ctx* ctx, int slot, int comp, int y0, int nrows, void* dev_dst);
+int vtmgpu_import_rows(vtmgpu_ctx* ctx, int slot, int comp, int y0, int nrows, const void* dev_src);
 
 /* replay/benchmark support: enqueue the whole chain on the ctx stream without synchronising; timing by
  * CUDA events recorded on that same stream */

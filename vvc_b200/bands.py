@@ -1,0 +1,161 @@
+"""Band mode: ONE large picture (BASELINE config 4: 7680x4320) filtered by several GPUs, one CTU-row band each
+(SURVEY.md 8e).
+
+Every rank creates a context for the FULL picture geometry (so CTU positions, ALF virtual boundaries and picture-border
+rules keep their absolute coordinates -- HBM is not the constraint: an 8K 4:2:0 slot is 3 x 100 MB), uploads only its
+band plus the rows the deblocking of the border tiles reads, and runs
+
+    deblocking + SAO  (exact for the band: both read pre-filter samples only)
+    halo exchange     4 rows of SAO output on each side of every band border go to the neighbour rank
+    ALF / CC-ALF      (reads 3 rows across the border: filter taps and the Laplacian classifier)
+
+The exchange is the only data-path communication: a neighbour send/recv of width x 4 samples per plane (60 KB of luma
+at 8K), carried by torch.distributed (NCCL over NVLink on GPUs; gloo in the CPU test of the choreography).  The plan
+(`band_rows`, `halo_plan`) is pure host logic and is shared by the GPU path and the CPU test.
+"""
+import numpy as np
+
+from . import abi
+
+HALO = 4            # rows of SAO output the ALF stage reads across a band border (box of the tile loads: +-4)
+UPLOAD_MARGIN = 16  # pre-filter luma rows the deblocking of a band's border tiles reads (8 chroma rows at 4:2:0)
+BAND_ALIGN = 128    # band borders sit on multiples of 128 luma rows (vtmgpu_set_rows)
+
+
+def band_rows(height, world, align=BAND_ALIGN):
+    """Luma row ranges [(y0, y1)] of the `world` bands: whole units of `align` rows, the larger bands first
+    (4320 rows over 8 ranks -> CTU rows 5,5,4,4,4,4,4,4)."""
+    units = (height + align - 1) // align
+    if world > units:
+        raise ValueError("more ranks (%d) than %d-row units (%d)" % (world, align, units))
+    base, extra = divmod(units, world)
+    out, u = [], 0
+    for r in range(world):
+        n = base + (1 if r < extra else 0)
+        out.append((u * align, min((u + n) * align, height)))
+        u += n
+    return out
+
+
+def halo_plan(bands, rank, shifts):
+    """Messages of one rank: list of (peer, 'send'|'recv', comp, first_row, nrows) in plane rows of component comp.
+    shifts[comp] = vertical subsampling shift of the component.  Sends are the band's own outermost HALO rows, receives
+    land just outside the band."""
+    y0, y1 = bands[rank]
+    plan = []
+    for comp, sy in enumerate(shifts):
+        if rank > 0:                               # upper neighbour
+            plan.append((rank - 1, "send", comp, y0 >> sy, HALO))
+            plan.append((rank - 1, "recv", comp, (y0 >> sy) - HALO, HALO))
+        if rank + 1 < len(bands):                  # lower neighbour
+            plan.append((rank + 1, "send", comp, (y1 >> sy) - HALO, HALO))
+            plan.append((rank + 1, "recv", comp, y1 >> sy, HALO))
+    return plan
+
+
+def _wire(buf):
+    """NCCL has no int16: samples travel as bytes (same memory)."""
+    import torch
+    return buf.view(torch.uint8)
+
+
+def exchange(plan, export_fn, import_fn, dist, width_of, make_buffer):
+    """Runs a halo plan: export_fn(comp, row, n, buf), import_fn(comp, row, n, buf); buffers from make_buffer(n_samples).
+    Non-blocking sends/receives towards both neighbours, then the imports."""
+    ops, recvs, keep = [], [], []
+    for peer, kind, comp, row, n in plan:
+        buf = make_buffer(width_of(comp) * n)
+        keep.append(buf)
+        if kind == "send":
+            export_fn(comp, row, n, buf)
+            ops.append(dist.P2POp(dist.isend, _wire(buf), peer))
+        else:
+            ops.append(dist.P2POp(dist.irecv, _wire(buf), peer))
+            recvs.append((comp, row, n, buf))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        if keep[0].is_cuda:
+            # NCCL work completes on torch's stream; the imports run on the context's own stream
+            import torch
+            torch.cuda.synchronize()
+    for comp, row, n, buf in recvs:
+        import_fn(comp, row, n, buf)
+
+
+def filter_picture_in_bands(cap, ctx, rank, world, dist, out=None):
+    """DBF -> SAO -> [halo exchange] -> ALF of this rank's band of the captured picture `cap` on context `ctx` (slot 0,
+    created for the full geometry).  Returns (planes, (y0, y1)): full-size host planes whose rows [y0, y1) hold the result."""
+    import torch
+    from . import gpu
+    h = cap.height
+    bands = band_rows(h, world)
+    y0, y1 = bands[rank]
+    sx, sy = abi.chroma_shifts(cap.seq["chroma_format"])
+    shifts = [0] + ([sy, sy] if cap.ncomp == 3 else [])
+    ctx.set_rows(y0, y1)
+    ctx.upload_rows(0, cap.pre, max(0, y0 - UPLOAD_MARGIN), min(h, y1 + UPLOAD_MARGIN))
+    ctx.set_deblock(0, cap.deblock_params())
+    ctus = cap.sao_ctus()
+    if ctus is not None:
+        gpu.sao_reconstruct(ctus, cap.width_in_ctus, cap.ncomp, cap.sao_scale[0], cap.sao_scale[1])
+    ctx.set_sao(0, ctus)
+    ctx.set_alf(0, cap.alf_params())
+    ctx.deblock_sao(0, 1)                      # one kernel: the SAO of the band's border rows sees the deblocked rows across the border
+    dev = torch.device("cuda", ctx.device)
+    widths = [cap.width] + [cap.width >> sx] * (cap.ncomp - 1)
+    exchange(halo_plan(bands, rank, shifts),
+             lambda comp, row, n, buf: ctx.export_rows(0, comp, row, n, buf.data_ptr()),
+             lambda comp, row, n, buf: ctx.import_rows(0, comp, row, n, buf.data_ptr()),
+             dist, lambda comp: widths[comp], lambda n: torch.empty(n, dtype=torch.int16, device=dev))
+    ctx.alf(0, 1)
+    if out is None:
+        out = [np.zeros_like(p) for p in cap.pre]
+    ctx.download_rows(0, out, y0, y1)
+    return out, (y0, y1)
+
+
+def filter_picture_in_bands_local(cap, n_bands, device=0):
+    """The same band pipeline driven by ONE process on ONE GPU: n_bands contexts (all for the full geometry), the halo
+    rows travel through device buffers instead of NCCL.  Exercises set_rows / upload_rows / export / import / download_rows
+    exactly as the multi-GPU path does; returns the assembled full picture."""
+    import torch
+    from . import gpu
+    h = cap.height
+    bands = band_rows(h, n_bands)
+    sx, sy = abi.chroma_shifts(cap.seq["chroma_format"])
+    shifts = [0] + ([sy, sy] if cap.ncomp == 3 else [])
+    widths = [cap.width] + [cap.width >> sx] * (cap.ncomp - 1)
+    dev = torch.device("cuda", device)
+    ctxs = [gpu.Context(cap.seq, capacity=1, device=device) for _ in range(n_bands)]
+    out = [np.zeros_like(p) for p in cap.pre]
+    try:
+        for r, ctx in enumerate(ctxs):
+            y0, y1 = bands[r]
+            ctx.set_rows(y0, y1)
+            ctx.upload_rows(0, cap.pre, max(0, y0 - UPLOAD_MARGIN), min(h, y1 + UPLOAD_MARGIN))
+            ctx.set_deblock(0, cap.deblock_params())
+            ctus = cap.sao_ctus()
+            if ctus is not None:
+                gpu.sao_reconstruct(ctus, cap.width_in_ctus, cap.ncomp, cap.sao_scale[0], cap.sao_scale[1])
+            ctx.set_sao(0, ctus)
+            ctx.set_alf(0, cap.alf_params())
+            ctx.deblock_sao(0, 1)
+        mail = {}
+        for r, ctx in enumerate(ctxs):
+            for peer, kind, comp, row, n in halo_plan(bands, r, shifts):
+                if kind == "send":
+                    buf = torch.empty(widths[comp] * n, dtype=torch.int16, device=dev)
+                    ctx.export_rows(0, comp, row, n, buf.data_ptr())
+                    mail[(r, peer, comp)] = buf
+        for r, ctx in enumerate(ctxs):
+            for peer, kind, comp, row, n in halo_plan(bands, r, shifts):
+                if kind == "recv":
+                    ctx.import_rows(0, comp, row, n, mail[(peer, r, comp)].data_ptr())
+        for r, ctx in enumerate(ctxs):
+            ctx.alf(0, 1)
+            ctx.download_rows(0, out, bands[r][0], bands[r][1])
+    finally:
+        for ctx in ctxs:
+            ctx.close()
+    return out

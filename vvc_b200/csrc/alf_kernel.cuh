@@ -420,9 +420,9 @@ __device__ __forceinline__ void saAdvance(SaWalk& p, const SaStep& st, int tiles
 
 // issues the asynchronous loads of one tile into `stage`: three TMA boxes (one thread) + the control record of its CTU
 __device__ __forceinline__ void saPrefetch(unsigned char* smraw, const SaLayout& L, int stage, const SlotDev& S, const CUtensorMap* maps, const SaWalk& p,
-                                           const Geom& g)
+                                           const Geom& g, int ty0)
 {
-  const int tid = threadIdx.x, x0 = p.tx * SA_T, y0 = p.ty * SA_TH;
+  const int tid = threadIdx.x, x0 = p.tx * SA_T, y0 = (p.ty + ty0) * SA_TH;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smraw + L.offBar) + stage;
   if (tid == 0)
   {
@@ -442,7 +442,7 @@ __device__ __forceinline__ void saPrefetch(unsigned char* smraw, const SaLayout&
 // filters tile i, the TMA loads of tile i+1 are in flight (two stages).  maps = tensor maps of the source buffer of the
 // first slot: [slot][3 buffers][3 planes].
 __global__ void __launch_bounds__(SA_THREADS, 4) k_alf(const SlotDev* __restrict__ slots, const CUtensorMap* __restrict__ tmaps, int firstSlot, int numSlots,
-                                                           int srcBuf, int dstBuf, Geom g, int tilesX, int tilesY, SaStep step, int dbg)
+                                                           int srcBuf, int dstBuf, Geom g, int tilesX, int tilesY, int ty0, SaStep step, int dbg)
 {
   extern __shared__ __align__(128) unsigned char smraw[];
   const SaLayout L = saLayout(g.sx, g.sy, g.ncomp);
@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(SA_THREADS, 4) k_alf(const SlotDev* __restrict
   __syncthreads();
   {
     const SlotDev& S = slots[firstSlot + cur.slot];
-    saPrefetch(smraw, L, 0, S, tmaps + ((size_t)(firstSlot + cur.slot) * 3 + srcBuf) * 3, cur, g);
+    saPrefetch(smraw, L, 0, S, tmaps + ((size_t)(firstSlot + cur.slot) * 3 + srcBuf) * 3, cur, g, ty0);
     cpAsyncCommit();
   }
   for (uint32_t it = 0; cur.slot < numSlots; it++)
@@ -486,14 +486,14 @@ __global__ void __launch_bounds__(SA_THREADS, 4) k_alf(const SlotDev* __restrict
     if (nxt.slot < numSlots)
     {
       const SlotDev& Sn = slots[firstSlot + nxt.slot];
-      saPrefetch(smraw, L, stage ^ 1, Sn, tmaps + ((size_t)(firstSlot + nxt.slot) * 3 + srcBuf) * 3, nxt, g);
+      saPrefetch(smraw, L, stage ^ 1, Sn, tmaps + ((size_t)(firstSlot + nxt.slot) * 3 + srcBuf) * 3, nxt, g, ty0);
     }
     cpAsyncCommit();
     cpAsyncWait<1>();
     mbarWait(&bars[stage], (it >> 1) & 1);
     __syncthreads();                                         // tile and its parameters are in shared memory
 
-    const int x0 = cur.tx * SA_T, y0 = cur.ty * SA_TH;
+    const int x0 = cur.tx * SA_T, y0 = (cur.ty + ty0) * SA_TH;
     const CtuCtlDev ctl = reinterpret_cast<const CtuCtlDev*>(smraw + L.offPar)[stage];
     const bool alfOn = S.alfOn != 0;
     const bool alfY = alfOn && ctl.enY != 0 && !(dbg & 8), alfCb = alfOn && ctl.enCb != 0, alfCr = alfOn && ctl.enCr != 0;

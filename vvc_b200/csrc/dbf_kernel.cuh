@@ -312,8 +312,9 @@ __device__ void dbfChromaSegment(pel* x0, int o, int s, int n, int tc, int beta,
 
 struct DbfLaunch
 {
-  int tilesXL, tilesL;      // luma tile grid
+  int tilesXL, tilesL;      // luma tile grid (of the rows being filtered)
   int tilesXC, tilesC;      // per chroma plane
+  int ty0L, ty0C;           // first tile row (band mode: a CTU-row band of the picture; 0 for whole pictures)
 };
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------
@@ -346,7 +347,7 @@ __device__ __forceinline__ DbfTile dbfDecodeTile(int item, const DbfLaunch& L)
   if (item >= L.tilesL) { item -= L.tilesL; T.comp = 1; if (item >= L.tilesC) { item -= L.tilesC; T.comp = 2; } }
   const int tilesX = T.comp ? L.tilesXC : L.tilesXL, ty = item / tilesX;
   T.x0 = (item - ty * tilesX) * DBF_TW;
-  T.y0 = ty * DBF_TH;
+  T.y0 = (ty + (T.comp ? L.ty0C : L.ty0L)) * DBF_TH;
   return T;
 }
 

@@ -84,6 +84,7 @@ struct vtmgpu_ctx
   std::vector<int> cur;                // buffer index holding the current state of each slot
   int64_t launches = 0;
   int numSms = 0;
+  int rowBegin = 0, rowEnd = 0;         // luma rows the stage calls filter (band mode); whole picture by default
   CUtensorMap* tmapsDev = nullptr;     // [capacity][3 buffers][3 planes]: TMA descriptors of the plane buffers, box = smem tile of k_alf
   CUtensorMap* tmapsDbfDev = nullptr;  // the same planes, box = smem tile of k_dbf_sao
 
@@ -179,6 +180,7 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
   g.ctu = s.ctu_size; g.ctuLog2 = s.ctu_size == 128 ? 7 : 6;
   g.wCtus = (g.w + g.ctu - 1) / g.ctu; g.hCtus = (g.h + g.ctu - 1) / g.ctu;
   c->nCtus = g.wCtus * g.hCtus;
+  c->rowBegin = 0; c->rowEnd = g.h;
 
   SideLayout& L = c->lay;
   L.nL = (size_t)(g.w / 4) * (g.h / 4);
@@ -350,6 +352,85 @@ extern "C" int vtmgpu_upload(vtmgpu_ctx* c, int slot, const int16_t* const plane
 extern "C" int vtmgpu_download(vtmgpu_ctx* c, int slot, int16_t* const plane[3], const ptrdiff_t stride[3])
 {
   return vtmgpu_download_async(c, slot, plane, stride) ? -1 : vtmgpu_sync(c);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// band mode: one picture split into CTU-row bands over several contexts (GPUs)
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int vtmgpu_set_rows(vtmgpu_ctx* c, int y_begin, int y_end)
+{
+  if (!c) return -1;
+  const int h = c->g.h;
+  if (y_begin < 0 || y_end > h || y_begin >= y_end || (y_begin & 127) || ((y_end & 127) && y_end != h))
+    return c->fail("set_rows: [%d,%d) must be a non-empty range of multiples of 128 luma rows (the end may be the picture height %d)", y_begin, y_end, h);
+  c->rowBegin = y_begin; c->rowEnd = y_end;
+  return 0;
+}
+
+namespace
+{
+// rows [y0, y0+n) of one plane of a slot <-> host or device memory (pitch in samples), on the ctx stream
+int copyRows(vtmgpu_ctx* c, int slot, int comp, int buf, int y0, int n, void* mem, ptrdiff_t stride, cudaMemcpyKind kind, bool toSlot, const char* what)
+{
+  if (!c->slotOk(slot, 1)) return c->fail("%s: bad slot %d", what, slot);
+  if (comp < 0 || comp >= c->g.ncomp) return c->fail("%s: bad component %d", what, comp);
+  const PlaneDev& d = c->slotsPinned[slot].buf[buf][comp];
+  if (y0 < 0 || n < 0 || y0 + n > d.h) return c->fail("%s: rows [%d,%d) outside the plane (height %d)", what, y0, y0 + n, d.h);
+  if (!mem && n) return c->fail("%s: NULL buffer", what);
+  if (n == 0) return 0;
+  cudaSetDevice(c->seq.device);
+  pel* dev = d.p + (size_t)y0 * d.pitch;
+  return c->cuda(toSlot ? cudaMemcpy2DAsync(dev, (size_t)d.pitch * 2, mem, (size_t)stride * 2, (size_t)d.w * 2, n, kind, c->stream)
+                       : cudaMemcpy2DAsync(mem, (size_t)stride * 2, dev, (size_t)d.pitch * 2, (size_t)d.w * 2, n, kind, c->stream), what);
+}
+}   // namespace
+
+extern "C" int vtmgpu_upload_rows(vtmgpu_ctx* c, int slot, const int16_t* const plane[3], const ptrdiff_t stride[3], int y_begin, int y_end)
+{
+  if (!c) return -1;
+  if (y_begin < 0 || y_end > c->g.h || y_begin > y_end || ((y_begin | y_end) & 1)) return c->fail("upload_rows: bad row range [%d,%d)", y_begin, y_end);
+  for (int k = 0; k < c->g.ncomp; k++)
+  {
+    const int sy = k ? c->g.sy : 0;
+    if (!plane[k]) return c->fail("upload_rows: plane %d is NULL", k);
+    // plane[k] points at row 0 of the FULL picture plane; only the requested rows are read
+    if (copyRows(c, slot, k, 0, y_begin >> sy, (y_end - y_begin) >> sy, const_cast<int16_t*>(plane[k]) + (size_t)(y_begin >> sy) * stride[k], stride[k],
+                 cudaMemcpyHostToDevice, true, "upload_rows")) return -1;
+  }
+  c->cur[slot] = 0;
+  return c->cuda(cudaStreamSynchronize(c->stream), "upload_rows");
+}
+
+extern "C" int vtmgpu_download_rows(vtmgpu_ctx* c, int slot, int16_t* const plane[3], const ptrdiff_t stride[3], int y_begin, int y_end)
+{
+  if (!c) return -1;
+  if (y_begin < 0 || y_end > c->g.h || y_begin > y_end || ((y_begin | y_end) & 1)) return c->fail("download_rows: bad row range [%d,%d)", y_begin, y_end);
+  for (int k = 0; k < c->g.ncomp; k++)
+  {
+    const int sy = k ? c->g.sy : 0;
+    if (!plane[k]) return c->fail("download_rows: plane %d is NULL", k);
+    if (copyRows(c, slot, k, c->cur[slot], y_begin >> sy, (y_end - y_begin) >> sy, plane[k] + (size_t)(y_begin >> sy) * stride[k], stride[k],
+                 cudaMemcpyDeviceToHost, false, "download_rows")) return -1;
+  }
+  return c->cuda(cudaStreamSynchronize(c->stream), "download_rows");
+}
+
+// halo exchange between neighbouring bands: rows of the CURRENT state of a plane to / from a dense device buffer
+// (width x nrows int16) that the caller sends over NVLink (NCCL send/recv, peer copy)
+extern "C" int vtmgpu_export_rows(vtmgpu_ctx* c, int slot, int comp, int y0, int nrows, void* dev_dst)
+{
+  if (!c) return -1;
+  if (comp < 0 || comp >= c->g.ncomp) return c->fail("export_rows: bad component %d", comp);
+  if (copyRows(c, slot, comp, c->cur[slot], y0, nrows, dev_dst, c->slotsPinned[slot].buf[0][comp].w, cudaMemcpyDeviceToDevice, false, "export_rows")) return -1;
+  return c->cuda(cudaStreamSynchronize(c->stream), "export_rows");
+}
+
+extern "C" int vtmgpu_import_rows(vtmgpu_ctx* c, int slot, int comp, int y0, int nrows, const void* dev_src)
+{
+  if (!c) return -1;
+  if (comp < 0 || comp >= c->g.ncomp) return c->fail("import_rows: bad component %d", comp);
+  if (copyRows(c, slot, comp, c->cur[slot], y0, nrows, const_cast<void*>(dev_src), c->slotsPinned[slot].buf[0][comp].w, cudaMemcpyDeviceToDevice, true, "import_rows")) return -1;
+  return c->cuda(cudaStreamSynchronize(c->stream), "import_rows");
 }
 
 extern "C" int vtmgpu_rewind(vtmgpu_ctx* c, int first, int count)
@@ -623,10 +704,13 @@ int launchDbfSao(vtmgpu_ctx* c, int first, int count, int doDbf, int doSao)
   if (!any) return 0;
   const Geom& g = c->g;
   DbfLaunch L;
+  // rows [rowBegin, rowEnd) of the picture; vtmgpu_set_rows keeps both on multiples of 128 luma rows (or the picture end), so whole tile rows
   L.tilesXL = (g.w + DBF_TW - 1) / DBF_TW;
-  L.tilesL = L.tilesXL * ((g.h + DBF_TH - 1) / DBF_TH);
+  L.ty0L = c->rowBegin / DBF_TH;
+  L.tilesL = L.tilesXL * ((c->rowEnd + DBF_TH - 1) / DBF_TH - L.ty0L);
   L.tilesXC = g.ncomp > 1 ? ((g.w >> g.sx) + DBF_TW - 1) / DBF_TW : 0;
-  L.tilesC = g.ncomp > 1 ? L.tilesXC * (((g.h >> g.sy) + DBF_TH - 1) / DBF_TH) : 0;
+  L.ty0C = (c->rowBegin >> g.sy) / DBF_TH;
+  L.tilesC = g.ncomp > 1 ? L.tilesXC * (((c->rowEnd >> g.sy) + DBF_TH - 1) / DBF_TH - L.ty0C) : 0;
   return forRuns(c, first, count, [&](int s, int n, int src) {
     const int dst = src == 1 ? 2 : 1;
     // persistent CTAs: three per SM, each walks the plane tiles round robin with double-buffered TMA loads
@@ -648,7 +732,7 @@ int launchAlf(vtmgpu_ctx* c, int first, int count)
   for (int s = first; s < first + count; s++) any |= c->slotsPinned[s].alfOn != 0;
   if (!any) return 0;
   const Geom& g = c->g;
-  const int tilesX = (g.w + SA_T - 1) / SA_T, tilesY = (g.h + SA_TH - 1) / SA_TH;
+  const int tilesX = (g.w + SA_T - 1) / SA_T, ty0 = c->rowBegin / SA_TH, tilesY = (c->rowEnd + SA_TH - 1) / SA_TH - ty0;
   const int smem = saLayout(g.sx, g.sy, g.ncomp).total;
   return forRuns(c, first, count, [&](int s, int n, int src) {
     const int dst = src == 1 ? 2 : 1;
@@ -658,7 +742,7 @@ int launchAlf(vtmgpu_ctx* c, int first, int count)
     st.dx = grid % tilesX;
     st.dy = (grid / tilesX) % tilesY;
     st.ds = (grid / tilesX) / tilesY;
-    k_alf<<<grid, SA_THREADS, smem, c->stream>>>(c->slotsDev, c->tmapsDev, s, n, src, dst, g, tilesX, tilesY, st, getenv("VTMGPU_DEBUG") ? atoi(getenv("VTMGPU_DEBUG")) : 0);
+    k_alf<<<grid, SA_THREADS, smem, c->stream>>>(c->slotsDev, c->tmapsDev, s, n, src, dst, g, tilesX, tilesY, ty0, st, getenv("VTMGPU_DEBUG") ? atoi(getenv("VTMGPU_DEBUG")) : 0);
     c->launches++;
     for (int i = s; i < s + n; i++) c->cur[i] = dst;
     return c->cuda(cudaGetLastError(), "k_alf launch");
@@ -685,6 +769,7 @@ int runStages(vtmgpu_ctx* c, int first, int count, int stages, bool sync, const 
 extern "C" int vtmgpu_deblock(vtmgpu_ctx* c, int first, int count) { return runStages(c, first, count, ST_DBF, true, "deblock"); }
 extern "C" int vtmgpu_sao(vtmgpu_ctx* c, int first, int count) { return runStages(c, first, count, ST_SAO, true, "sao"); }
 extern "C" int vtmgpu_alf(vtmgpu_ctx* c, int first, int count) { return runStages(c, first, count, ST_ALF, true, "alf"); }
+extern "C" int vtmgpu_deblock_sao(vtmgpu_ctx* c, int first, int count) { return runStages(c, first, count, ST_DBF | ST_SAO, true, "deblock_sao"); }
 extern "C" int vtmgpu_sao_alf(vtmgpu_ctx* c, int first, int count) { return runStages(c, first, count, ST_SAO | ST_ALF, true, "sao_alf"); }
 extern "C" int vtmgpu_filter(vtmgpu_ctx* c, int first, int count) { return runStages(c, first, count, ST_DBF | ST_SAO | ST_ALF, true, "filter"); }
 extern "C" int vtmgpu_filter_async(vtmgpu_ctx* c, int first, int count) { return runStages(c, first, count, ST_DBF | ST_SAO | ST_ALF, false, "filter_async"); }

@@ -56,6 +56,7 @@ def load_library(path=None):
         "vtmgpu_sao_reconstruct": (C.c_int, [C.POINTER(abi.SaoCtu), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
         "vtmgpu_deblock": (C.c_int, [ctx, C.c_int, C.c_int]), "vtmgpu_sao": (C.c_int, [ctx, C.c_int, C.c_int]),
         "vtmgpu_alf": (C.c_int, [ctx, C.c_int, C.c_int]), "vtmgpu_sao_alf": (C.c_int, [ctx, C.c_int, C.c_int]),
+        "vtmgpu_deblock_sao": (C.c_int, [ctx, C.c_int, C.c_int]),
         "vtmgpu_filter": (C.c_int, [ctx, C.c_int, C.c_int]), "vtmgpu_filter_async": (C.c_int, [ctx, C.c_int, C.c_int]),
         "vtmgpu_sync": (C.c_int, [ctx]), "vtmgpu_timer_start": (C.c_int, [ctx]),
         "vtmgpu_timer_stop": (C.c_int, [ctx, C.POINTER(C.c_float)]),
@@ -63,6 +64,10 @@ def load_library(path=None):
         "vtmgpu_launch_count": (C.c_int64, [ctx]),
         "vtmgpu_set_profiling": (C.c_int, [ctx, C.c_int]),
         "vtmgpu_stage_ms": (C.c_int, [ctx, C.POINTER(C.c_float * 4)]),
+        "vtmgpu_set_rows": (C.c_int, [ctx, C.c_int, C.c_int]),
+        "vtmgpu_upload_rows": (C.c_int, planes_in + [C.c_int, C.c_int]), "vtmgpu_download_rows": (C.c_int, planes_in + [C.c_int, C.c_int]),
+        "vtmgpu_export_rows": (C.c_int, [ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+        "vtmgpu_import_rows": (C.c_int, [ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     }
     for name, (res, args) in proto.items():
         try:
@@ -108,6 +113,7 @@ class Context:
         if self.lib.vtmgpu_create(C.byref(sp), C.byref(self.h)):
             raise VtmGpuError(self.lib.vtmgpu_last_error(None).decode())
         self.capacity = capacity
+        self.device = device
         self.ncomp = 1 if seq["chroma_format"] == 0 else 3
         sx, sy = abi.chroma_shifts(seq["chroma_format"])
         w, h = seq["width"], seq["height"]
@@ -139,6 +145,25 @@ class Context:
         ptrs, strides = _plane_args(out)
         self._ck((self.lib.vtmgpu_download if sync else self.lib.vtmgpu_download_async)(self.h, slot, ptrs, strides), "download")
         return out
+
+    # ---- band mode (one picture over several contexts) -----------------------------------------------------
+    def set_rows(self, y_begin, y_end):
+        self._ck(self.lib.vtmgpu_set_rows(self.h, y_begin, y_end), "set_rows")
+
+    def upload_rows(self, slot, planes, y_begin, y_end):
+        """planes = the FULL host picture; only luma rows [y_begin, y_end) (and the collocated chroma rows) are copied."""
+        ptrs, strides = _plane_args(planes)
+        self._ck(self.lib.vtmgpu_upload_rows(self.h, slot, ptrs, strides, y_begin, y_end), "upload_rows")
+
+    def download_rows(self, slot, planes, y_begin, y_end):
+        ptrs, strides = _plane_args(planes)
+        self._ck(self.lib.vtmgpu_download_rows(self.h, slot, ptrs, strides, y_begin, y_end), "download_rows")
+
+    def export_rows(self, slot, comp, y0, nrows, dev_ptr):
+        self._ck(self.lib.vtmgpu_export_rows(self.h, slot, comp, y0, nrows, C.c_void_p(dev_ptr)), "export_rows")
+
+    def import_rows(self, slot, comp, y0, nrows, dev_ptr):
+        self._ck(self.lib.vtmgpu_import_rows(self.h, slot, comp, y0, nrows, C.c_void_p(dev_ptr)), "import_rows")
 
     # ---- side information --------------------------------------------------------------------------------
     def set_deblock(self, slot, params):
@@ -175,6 +200,9 @@ class Context:
 
     def alf(self, first=0, count=1):
         self._ck(self.lib.vtmgpu_alf(self.h, first, count), "alf")
+
+    def deblock_sao(self, first=0, count=1):
+        self._ck(self.lib.vtmgpu_deblock_sao(self.h, first, count), "deblock_sao")
 
     def sao_alf(self, first=0, count=1):
         self._ck(self.lib.vtmgpu_sao_alf(self.h, first, count), "sao_alf")
