@@ -243,6 +243,10 @@ int vtmgpu_filter (vtmgpu_ctx* ctx, int first, int count);
  * plane[k] / stride[k] in the *_rows calls describe the FULL host picture (row 0), as in vtmgpu_upload.
  * --------------------------------------------------------------------------------------------- */
 int vtmgpu_set_rows(vtmgpu_ctx* ctx, int y_begin, int y_end);
+/* Redirects all work of the ctx to the caller's CUDA stream (cudaStream_t; NULL = back to the ctx's own stream) so that it
+ * orders with the caller's other work on that stream (e.g. NCCL send/recv of the halo rows) without host synchronisation.
+ * async_stages != 0: stage calls and export/import only ENQUEUE; the caller synchronises (vtmgpu_sync). */
+int vtmgpu_set_stream(vtmgpu_ctx* ctx, void* cuda_stream, int async_stages);
 int vtmgpu_upload_rows  (vtmgpu_ctx* ctx, int slot, const int16_t* const plane[3], const ptrdiff_t stride[3], int y_begin, int y_end);
 int vtmgpu_download_rows(vtmgpu_ctx* ctx, int slot, int16_t* const plane[3], const ptrdiff_t stride[3], int y_begin, int y_end);
 /* rows [y0, y0+nrows) (in samples of component comp) of the slot's current state <-> dense device memory (width * nrows int16) */

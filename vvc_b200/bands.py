@@ -59,9 +59,10 @@ def _wire(buf):
     return buf.view(torch.uint8)
 
 
-def exchange(plan, export_fn, import_fn, dist, width_of, make_buffer):
+def exchange(plan, export_fn, import_fn, dist, width_of, make_buffer, host_sync=True):
     """Runs a halo plan: export_fn(comp, row, n, buf), import_fn(comp, row, n, buf); buffers from make_buffer(n_samples).
-    Non-blocking sends/receives towards both neighbours, then the imports."""
+    Non-blocking sends/receives towards both neighbours, then the imports.  host_sync=False when the context runs on
+    torch's current stream (Context.set_stream): NCCL then orders with the exports / imports on the device."""
     ops, recvs, keep = [], [], []
     for peer, kind, comp, row, n in plan:
         buf = make_buffer(width_of(comp) * n)
@@ -75,7 +76,7 @@ def exchange(plan, export_fn, import_fn, dist, width_of, make_buffer):
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
-        if keep[0].is_cuda:
+        if keep[0].is_cuda and host_sync:
             # NCCL work completes on torch's stream; the imports run on the context's own stream
             import torch
             torch.cuda.synchronize()

@@ -71,6 +71,8 @@ struct vtmgpu_ctx
   Geom g{};
   int nCtus = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t ownStream = nullptr;    // created by vtmgpu_create; `stream` may be redirected to a caller's stream (vtmgpu_set_stream)
+  bool asyncStages = false;            // vtmgpu_set_async: stage / row-copy calls only enqueue
   cudaEvent_t ev[2] = { nullptr, nullptr };
   cudaEvent_t stageEv[3] = { nullptr, nullptr, nullptr };
   bool profiling = false, stageValid = false;
@@ -148,7 +150,7 @@ extern "C" void vtmgpu_destroy(vtmgpu_ctx* c)
   if (c->tmapsDbfDev) cudaFree(c->tmapsDbfDev);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   for (auto& e : c->stageEv) if (e) cudaEventDestroy(e);
-  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->ownStream) cudaStreamDestroy(c->ownStream);
   delete c;
 }
 
@@ -196,7 +198,8 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
   L.total = off;
 
 #define CK(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_createError = std::string("vtmgpu_create: ") + what + ": " + cudaGetErrorString(e_); vtmgpu_destroy(c); return -1; } } while (0)
-  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "stream");
+  CK(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking), "stream");
+  c->stream = c->ownStream;
   for (auto& ev : c->ev) CK(cudaEventCreate(&ev), "event");
   for (auto& ev : c->stageEv) CK(cudaEventCreate(&ev), "event");
   CK(cudaHostAlloc((void**)&c->sidePinned, L.total * s.capacity, cudaHostAllocDefault), "pinned side info");
@@ -357,6 +360,16 @@ extern "C" int vtmgpu_download(vtmgpu_ctx* c, int slot, int16_t* const plane[3],
 // ------------------------------------------------------------------------------------------------------------
 // band mode: one picture split into CTU-row bands over several contexts (GPUs)
 // ------------------------------------------------------------------------------------------------------------
+extern "C" int vtmgpu_set_stream(vtmgpu_ctx* c, void* cuda_stream, int async_stages)
+{
+  if (!c) return -1;
+  cudaSetDevice(c->seq.device);
+  if (c->cuda(cudaStreamSynchronize(c->stream), "set_stream")) return -1;      // drain the stream being left
+  c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->ownStream;
+  c->asyncStages = async_stages != 0;
+  return 0;
+}
+
 extern "C" int vtmgpu_set_rows(vtmgpu_ctx* c, int y_begin, int y_end)
 {
   if (!c) return -1;
@@ -422,7 +435,7 @@ extern "C" int vtmgpu_export_rows(vtmgpu_ctx* c, int slot, int comp, int y0, int
   if (!c) return -1;
   if (comp < 0 || comp >= c->g.ncomp) return c->fail("export_rows: bad component %d", comp);
   if (copyRows(c, slot, comp, c->cur[slot], y0, nrows, dev_dst, c->slotsPinned[slot].buf[0][comp].w, cudaMemcpyDeviceToDevice, false, "export_rows")) return -1;
-  return c->cuda(cudaStreamSynchronize(c->stream), "export_rows");
+  return c->asyncStages ? 0 : c->cuda(cudaStreamSynchronize(c->stream), "export_rows");
 }
 
 extern "C" int vtmgpu_import_rows(vtmgpu_ctx* c, int slot, int comp, int y0, int nrows, const void* dev_src)
@@ -430,7 +443,7 @@ extern "C" int vtmgpu_import_rows(vtmgpu_ctx* c, int slot, int comp, int y0, int
   if (!c) return -1;
   if (comp < 0 || comp >= c->g.ncomp) return c->fail("import_rows: bad component %d", comp);
   if (copyRows(c, slot, comp, c->cur[slot], y0, nrows, const_cast<void*>(dev_src), c->slotsPinned[slot].buf[0][comp].w, cudaMemcpyDeviceToDevice, true, "import_rows")) return -1;
-  return c->cuda(cudaStreamSynchronize(c->stream), "import_rows");
+  return c->asyncStages ? 0 : c->cuda(cudaStreamSynchronize(c->stream), "import_rows");
 }
 
 extern "C" int vtmgpu_rewind(vtmgpu_ctx* c, int first, int count)
@@ -760,7 +773,7 @@ int runStages(vtmgpu_ctx* c, int first, int count, int stages, bool sync, const 
   if (c->profiling) cudaEventRecord(c->stageEv[1], c->stream);
   if ((stages & ST_ALF) && launchAlf(c, first, count)) return -1;
   if (c->profiling) { cudaEventRecord(c->stageEv[2], c->stream); c->stageValid = true; }
-  if (sync && c->cuda(cudaStreamSynchronize(c->stream), what)) return -1;
+  if (sync && !c->asyncStages && c->cuda(cudaStreamSynchronize(c->stream), what)) return -1;
   return 0;
 }
 

@@ -65,6 +65,7 @@ def load_library(path=None):
         "vtmgpu_set_profiling": (C.c_int, [ctx, C.c_int]),
         "vtmgpu_stage_ms": (C.c_int, [ctx, C.POINTER(C.c_float * 4)]),
         "vtmgpu_set_rows": (C.c_int, [ctx, C.c_int, C.c_int]),
+        "vtmgpu_set_stream": (C.c_int, [ctx, C.c_void_p, C.c_int]),
         "vtmgpu_upload_rows": (C.c_int, planes_in + [C.c_int, C.c_int]), "vtmgpu_download_rows": (C.c_int, planes_in + [C.c_int, C.c_int]),
         "vtmgpu_export_rows": (C.c_int, [ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
         "vtmgpu_import_rows": (C.c_int, [ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -149,6 +150,10 @@ class Context:
     # ---- band mode (one picture over several contexts) -----------------------------------------------------
     def set_rows(self, y_begin, y_end):
         self._ck(self.lib.vtmgpu_set_rows(self.h, y_begin, y_end), "set_rows")
+
+    def set_stream(self, cuda_stream, async_stages=True):
+        """cuda_stream: integer cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or None for the context's own stream."""
+        self._ck(self.lib.vtmgpu_set_stream(self.h, C.c_void_p(cuda_stream) if cuda_stream else None, int(async_stages)), "set_stream")
 
     def upload_rows(self, slot, planes, y_begin, y_end):
         """planes = the FULL host picture; only luma rows [y_begin, y_end) (and the collocated chroma rows) are copied."""
