@@ -31,6 +31,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 W4K, H4K = 3840, 2160
+METRIC = "DBF+SAO+ALF Mpixel/s at 3840x2160 10-bit"
+WORKLOAD = "3840x2160 10-bit 4:2:0 random-access (QP32, CC-ALF) in-loop filter chain DBF+SAO+ALF+CC-ALF, picture-parallel"
 B_ALG_CHAIN = 6.5          # algorithmic bytes per luma pixel of the whole chain at 4:2:0 (SURVEY.md 8d / BASELINE.md 3)
 B_ALG_DBF = 6.5            # k_dbf_sao : read 3 + write 3 + 0.5 segment records
 B_ALG_SAOALF = 6.0         # k_alf     : read 3 + write 3 (CTU parameters negligible)
@@ -183,10 +185,10 @@ def run_reference_arm(args):
         print(json.dumps({"impl": "reference", "unavailable": "neither oracle/_ref/DecoderApp_cap + data/streams nor the oracle port could run"}))
         return 0
     v = sum(vals) / len(vals)
-    line = {"impl": "reference", "metric": "DBF+SAO+ALF Mpixel/s", "value": round(v, 2), "unit": "Mpixel/s", "n_gpus": args.gpus, "steps": len(vals),
+    line = {"impl": "reference", "metric": METRIC, "value": round(v, 2), "unit": "Mpixel/s", "n_gpus": args.gpus, "steps": len(vals),
             "warmup": 0, "ms_per_step": round((time.perf_counter() - t0) * 1e3 / len(vals), 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-            "config": {"workload": "3840x2160 10-bit 4:2:0 RA (QP32) in-loop filter chain on the host CPU: " + res[3]},
+            "config": {"workload": WORKLOAD, "arm": "the reference's own filter classes on the host CPU: " + res[3]},
             "cpu_baseline": {"value": round(v, 2), "unit": "Mpixel/s", "cores": res[1], "kind": res[2], "sample": res[3]},
             "e2e": {"value": round(v, 2), "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -289,7 +291,9 @@ def main():
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
-            roofline["traffic"] = json.load(open(tr)).get(roofline["kernel"])
+            per_px = json.load(open(tr)).get(roofline["kernel"], {}).get("dram_bytes_per_luma_pixel")
+            if per_px is not None:
+                roofline["traffic"] = round(per_px * px_per_pic * B)      # ncu dram__bytes_read+write per luma pixel x pixels of one launch
         except Exception:
             pass
 
@@ -340,10 +344,10 @@ def main():
     for c in ectx:
         c.close()
 
-    line = {"metric": "DBF+SAO+ALF Mpixel/s at 3840x2160 10-bit", "value": round(value, 1), "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
+    line = {"metric": METRIC, "value": round(value, 1), "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int16", "data": "synthetic",
-            "config": {"workload": "3840x2160 10-bit 4:2:0 in-loop filter chain DBF+SAO+ALF+CC-ALF, %d pictures per step per GPU, picture-parallel; %s" % (B, workload),
+            "config": {"workload": WORKLOAD, "pictures_per_step_per_gpu": B, "pictures": workload,
                        "l2": "inputs of one step (%.0f MB per GPU) exceed the 126 MB L2, no flush needed" % (B * 24.9),
                        "activity": activity_summary(caps), "e2e_equals_resident": bool(ok)},
             "clocks": clocks, "roofline": roofline, "gpu_launches": int(launches),

@@ -328,12 +328,32 @@ struct DbfLaunch
 // Persistent CTAs walk the plane tiles of a batch of picture slots round robin (per slot: luma tiles, Cb tiles, Cr tiles).
 // While tile i is filtered, tile i+1 arrives: the samples (tile + 8 halo, zero filled outside the picture) by ONE TMA box,
 // the segment records of both passes by cp.async in exactly the order the passes consume them.
-constexpr int DBF_RECA_BYTES = 5632;                    // pass-1 records of a tile: luma 35x20 u32, chroma 17x40 u64
-constexpr int DBF_RECB_BYTES = 4864;                    // pass-2 records: luma 34x17 u32, chroma 66x9 u64
+constexpr int DBF_RECA_BYTES = 5888;                    // pass-1 records of a tile: luma 40x20 u32, chroma 18x40 u64 (multiples of 128 B)
+constexpr int DBF_RECB_BYTES = 4992;                    // pass-2 records: luma 40x17 u32, chroma 68x9 u64
 constexpr int DBF_TILE_BYTES = DBF_SH * DBF_PITCH * 2;  // 24320 (multiple of 128: TMA destination)
 constexpr int DBF_STAGE_BYTES = DBF_TILE_BYTES + DBF_RECA_BYTES + DBF_RECB_BYTES;
-constexpr int DBF_QUEUE = 96;                          // active-segment queue entries per warp (a warp scans <= 96 slots per pass)
+constexpr int DBF_RECL = 40;                            // columns of the luma record boxes
+constexpr int DBF_QUEUE = 128;                          // active-segment queue entries per warp (a warp scans <= 96 slots per pass)
 constexpr int DBF_SMEM_BYTES = 2 * DBF_STAGE_BYTES + 16 + (DBF_THREADS / 32) * DBF_QUEUE * 2;
+
+// record boxes of one tile (columns x rows, in records) for the arrays lumaV, lumaH, chromaV, chromaH.  TMA wants the first
+// element of a box row on a 16-byte boundary and the row length a multiple of 16 bytes, so the luma boxes start 4 records
+// left of the tile (3 unused + the edge x0-4) and the chroma horizontal-edge box 2 records left (1 unused + the extra segment)
+struct DbfRecBoxes
+{
+  int cols[4], rows[4];
+};
+
+__host__ __device__ inline DbfRecBoxes dbfRecBoxes(int sx, int sy)
+{
+  DbfRecBoxes B;
+  const int nv = 4 >> sy, nh = 4 >> sx;
+  B.cols[0] = DBF_RECL; B.rows[0] = DBF_SH / 4;              // vertical edges x0-4 .. x0+TW+4 (columns 3..37 used), segment rows of tile + halo
+  B.cols[1] = DBF_RECL; B.rows[1] = DBF_TH / 4 + 1;          // horizontal edges y0 .. y0+TH, segments of columns x0-4 .. x0+TW+3 (columns 3..36 used)
+  B.cols[2] = 18; B.rows[2] = DBF_SH / nv;                   // chroma vertical edges x0 .. x0+TW step 8 (17 used)
+  B.cols[3] = DBF_TW / nh + 4; B.rows[3] = DBF_TH / 8 + 1;   // chroma horizontal edges, one extra segment each side (columns 1 .. TW/nh+2 used)
+  return B;
+}
 
 struct DbfTile
 {
@@ -357,18 +377,20 @@ struct DbfPassGeom
   int ne1, ns1, n1;      // pass 1: ne1 edges per row of segments, ns1 segment rows
   int ne2, ns2, n2;      // pass 2: ne2 edge rows, ns2 segments per edge row
   int nv, nh;            // chroma: samples along the edge per record (vertical edges / horizontal edges)
+  int p1, p2;            // row pitch (records) of the two record boxes in shared memory
 };
 
 __device__ __forceinline__ DbfPassGeom dbfPassGeom(int comp, const Geom& g)
 {
   DbfPassGeom P;
-  if (comp == 0) { P.ne1 = DBF_TW / 4 + 3; P.ns1 = DBF_SH / 4; P.ne2 = DBF_TH / 4 + 1; P.ns2 = DBF_TW / 4 + 2; P.nv = P.nh = 4; }
+  if (comp == 0) { P.ne1 = DBF_TW / 4 + 3; P.ns1 = DBF_SH / 4; P.ne2 = DBF_TH / 4 + 1; P.ns2 = DBF_TW / 4 + 2; P.nv = P.nh = 4; P.p1 = P.p2 = DBF_RECL; }
   else
   {
     P.nv = 4 >> g.sy; P.nh = 4 >> g.sx;
     P.ne1 = DBF_TW / 8 + 1; P.ns1 = DBF_SH / P.nv; P.ne2 = DBF_TH / 8 + 1; P.ns2 = DBF_TW / P.nh + 2;
+    P.p1 = 18; P.p2 = P.ns2 + 2;
   }
-  P.n1 = P.ne1 * P.ns1; P.n2 = P.ne2 * P.ns2;
+  P.n1 = P.p1 * P.ns1; P.n2 = P.p2 * P.ne2;                   // slots scanned (incl. the padding column of pass 1)
   return P;
 }
 
@@ -381,7 +403,7 @@ template <class RecT, class Active> __device__ __forceinline__ int dbfCompact(co
   for (int i0 = warp * 32; i0 < n; i0 += DBF_THREADS)
   {
     const int i = i0 + lane;
-    const bool a = i < n && act(rec[i]);
+    const bool a = i < n && act(rec[i], i);
     const unsigned m = __ballot_sync(0xffffffffu, a);
     if (a) q[cnt + __popc(m & ((1u << lane) - 1))] = (uint16_t)i;
     cnt += __popc(m);
@@ -390,64 +412,36 @@ template <class RecT, class Active> __device__ __forceinline__ int dbfCompact(co
   return cnt;
 }
 
-// issues the asynchronous loads of one tile into a stage: the TMA box (one thread) and the records (all threads, cp.async)
-__device__ __forceinline__ void dbfPrefetch(unsigned char* stageMem, uint64_t* bar, const SlotDev& S, const CUtensorMap* map, const DbfTile& T, const Geom& g,
-                                            bool dbfOn)
+// issues the asynchronous loads of one tile into a stage (one thread): three TMA boxes on one mbarrier -- the samples
+// (tile + 8 halo) and the segment records of the two passes.  Everything outside the picture arrives as zeros = "no edge".
+__device__ __forceinline__ void dbfPrefetch(unsigned char* stageMem, uint64_t* bar, const CUtensorMap* planeMap, const CUtensorMap* recMaps, const DbfTile& T,
+                                            const Geom& g, bool dbfOn, int dbg = 0)
 {
-  const int tid = threadIdx.x;
-  if (tid == 0)
-  {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    mbarExpectTx(bar, DBF_TILE_BYTES);
-    tmaLoad2D(stageMem, map, T.x0 - DBF_HALO, T.y0 - DBF_HALO, bar);
-  }
+  if (threadIdx.x != 0) return;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  const DbfRecBoxes RB = dbfRecBoxes(g.sx, g.sy);
+  const int a = T.comp ? 2 : 0, words = T.comp ? 2 : 1;
+  uint32_t recBytes = dbfOn ? (uint32_t)(((dbg & 1) ? 0 : RB.cols[a] * RB.rows[a]) + ((dbg & 2) ? 0 : RB.cols[a + 1] * RB.rows[a + 1])) * words * 4 : 0u;
+  mbarExpectTx(bar, DBF_TILE_BYTES + recBytes);
+  tmaLoad2D(stageMem, planeMap, T.x0 - DBF_HALO, T.y0 - DBF_HALO, bar);
   if (!dbfOn) return;
-  const DbfPassGeom P = dbfPassGeom(T.comp, g);
-  // i / n == (i * ceil(65536 / n)) >> 16 for i < 4096
-  const int rcp1 = (65536 + P.ne1 - 1) / P.ne1, rcp2 = (65536 + P.ns2 - 1) / P.ns2;
   if (T.comp == 0)
   {
-    const int uw = g.w >> 2, uh = g.h >> 2;
-    uint32_t* ra = reinterpret_cast<uint32_t*>(stageMem + DBF_TILE_BYTES);
-    uint32_t* rb = reinterpret_cast<uint32_t*>(stageMem + DBF_TILE_BYTES + DBF_RECA_BYTES);
-    for (int i = tid; i < P.n1; i += DBF_THREADS)
-    {
-      const int sg = (i * rcp1) >> 16, e = i - sg * P.ne1;
-      const int ux = (T.x0 >> 2) - 1 + e, uy = ((T.y0 - DBF_HALO) >> 2) + sg;
-      if (ux > 0 && ux < uw && uy >= 0 && uy < uh) cpAsync4(&ra[i], &S.dbfL[0][uy * uw + ux]); else ra[i] = 0;
-    }
-    for (int i = tid; i < P.n2; i += DBF_THREADS)
-    {
-      const int e = (i * rcp2) >> 16, sg = i - e * P.ns2;
-      const int ux = (T.x0 >> 2) - 1 + sg, uy = (T.y0 >> 2) + e;
-      if (uy > 0 && uy < uh && ux >= 0 && ux < uw) cpAsync4(&rb[i], &S.dbfL[1][uy * uw + ux]); else rb[i] = 0;
-    }
+    if (!(dbg & 1)) tmaLoad2D(stageMem + DBF_TILE_BYTES, recMaps + 0, (T.x0 >> 2) - 4, (T.y0 - DBF_HALO) >> 2, bar);
+    if (!(dbg & 2)) tmaLoad2D(stageMem + DBF_TILE_BYTES + DBF_RECA_BYTES, recMaps + 1, (T.x0 >> 2) - 4, T.y0 >> 2, bar);
   }
   else
   {
-    // chroma planes: x0,y0 in chroma samples; record arrays are indexed in luma units (include/vtmgpu.h)
-    const int cw = g.w >> g.sx, ch = g.h >> g.sy;
-    const int cols0 = (g.w + (8 << g.sx) - 1) / (8 << g.sx), uw = g.w >> 2;
-    uint64_t* ra = reinterpret_cast<uint64_t*>(stageMem + DBF_TILE_BYTES);
-    uint64_t* rb = reinterpret_cast<uint64_t*>(stageMem + DBF_TILE_BYTES + DBF_RECA_BYTES);
-    for (int i = tid; i < P.n1; i += DBF_THREADS)
-    {
-      const int sg = (i * rcp1) >> 16, e = i - sg * P.ne1;
-      const int x = T.x0 + 8 * e, y = T.y0 - DBF_HALO + P.nv * sg;
-      if (x > 0 && x < cw && y >= 0 && y < ch) cpAsync8(&ra[i], &S.dbfC[0][(y >> (2 - g.sy)) * cols0 + (x >> 3)]); else ra[i] = 0;
-    }
-    for (int i = tid; i < P.n2; i += DBF_THREADS)
-    {
-      const int e = (i * rcp2) >> 16, sg = i - e * P.ns2;
-      const int x = T.x0 - P.nh + P.nh * sg, y = T.y0 + 8 * e;
-      if (y > 0 && y < ch && x >= 0 && x < cw) cpAsync8(&rb[i], &S.dbfC[1][(y >> 3) * uw + (x >> (2 - g.sx))]); else rb[i] = 0;
-    }
+    // x0,y0 in chroma samples; record arrays are indexed in luma units (include/vtmgpu.h); a record = 2 words
+    const int nvLog = 2 - g.sy, nhLog = 2 - g.sx;
+    tmaLoad2D(stageMem + DBF_TILE_BYTES, recMaps + 2, (T.x0 >> 3) * 2, (T.y0 - DBF_HALO) >> nvLog, bar);
+    tmaLoad2D(stageMem + DBF_TILE_BYTES + DBF_RECA_BYTES, recMaps + 3, ((T.x0 >> nhLog) - 2) * 2, T.y0 >> 3, bar);
   }
 }
 
 // maps = TMA descriptors of the plane buffers: [slot][3 buffers][3 planes], box = DBF_PITCH x DBF_SH samples
-__global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __restrict__ slots, const CUtensorMap* __restrict__ tmaps, int firstSlot, int numSlots,
-                                                             int srcBuf, int dstBuf, Geom g, DbfLaunch L, TileStep step, int doDbf, int doSao)
+__global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __restrict__ slots, const CUtensorMap* __restrict__ tmaps, const CUtensorMap* __restrict__ recMaps,
+                                                             int firstSlot, int numSlots, int srcBuf, int dstBuf, Geom g, DbfLaunch L, TileStep step, int doDbf, int doSao)
 {
   extern __shared__ __align__(128) unsigned char smraw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + 2 * DBF_STAGE_BYTES);
@@ -466,8 +460,7 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
   DbfTile T = dbfDecodeTile(item, L), Tn = T;
   {
     const SlotDev& S = slots[firstSlot + slot];
-    dbfPrefetch(smraw, &bars[0], S, tmaps + ((size_t)(firstSlot + slot) * 3 + srcBuf) * 3 + T.comp, T, g, doDbf && S.dbfOn);
-    cpAsyncCommit();
+    dbfPrefetch(smraw, &bars[0], tmaps + ((size_t)(firstSlot + slot) * 3 + srcBuf) * 3 + T.comp, recMaps + (size_t)(firstSlot + slot) * 4, T, g, doDbf && S.dbfOn, doDbf >> 1);
   }
   for (uint32_t it = 0; slot < numSlots; it++)
   {
@@ -480,10 +473,9 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
     {
       const SlotDev& Sn = slots[firstSlot + nslot];
       Tn = dbfDecodeTile(nitem, L);
-      dbfPrefetch(smraw + (stage ^ 1) * DBF_STAGE_BYTES, &bars[stage ^ 1], Sn, tmaps + ((size_t)(firstSlot + nslot) * 3 + srcBuf) * 3 + Tn.comp, Tn, g,
-                  doDbf && Sn.dbfOn);
+      dbfPrefetch(smraw + (stage ^ 1) * DBF_STAGE_BYTES, &bars[stage ^ 1], tmaps + ((size_t)(firstSlot + nslot) * 3 + srcBuf) * 3 + Tn.comp,
+                  recMaps + (size_t)(firstSlot + nslot) * 4, Tn, g, doDbf && Sn.dbfOn, doDbf >> 1);
     }
-    cpAsyncCommit();
 
     const int comp = T.comp, x0 = T.x0, y0 = T.y0;
     const PlaneDev dst = S.buf[dstBuf][comp];
@@ -496,12 +488,10 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
     uint4 pq = make_uint4(0, 0, 0, 0);
     if (doSao && S.saoOn && sx_ < w && sy_ < h) pq = __ldg(reinterpret_cast<const uint4*>(&S.sao[((sy_ >> chLog) * g.wCtus + (sx_ >> cwLog)) * 3 + comp]));
 
-    cpAsyncWait<1>();
-    mbarWait(&bars[stage], (it >> 1) & 1);
-    __syncthreads();                                         // samples and records of this tile are in shared memory
+    mbarWait(&bars[stage], (it >> 1) & 1);                   // samples and records of this tile are in shared memory
     pel* sm = reinterpret_cast<pel*>(stageMem);
 
-    if (doDbf && S.dbfOn)
+    if ((doDbf & 1) && !(doDbf >> 1) && S.dbfOn)
     {
       const int maxv = (1 << (comp ? g.bdC : g.bdL)) - 1;
       const DbfPassGeom P = dbfPassGeom(comp, g);
@@ -510,27 +500,27 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
         const uint32_t* ra = reinterpret_cast<const uint32_t*>(stageMem + DBF_TILE_BYTES);
         const uint32_t* rbv = reinterpret_cast<const uint32_t*>(stageMem + DBF_TILE_BYTES + DBF_RECA_BYTES);
         // pass 1: vertical edges x0-4 .. x0+TW+4 (step 4), all rows of tile + halo; 8 segments per warp round, one line per lane
-        constexpr int NE = DBF_TW / 4 + 3;
+        constexpr int NE = DBF_RECL, NEU = DBF_TW / 4 + 3;     // box pitch, edges used (box columns 3 .. 3+NEU-1)
         {
-          const int cnt = dbfCompact(ra, P.n1, queue, [](uint32_t r) { return (r & 0x7ff) != 0; });
+          const int cnt = dbfCompact(ra, P.n1, queue, [](uint32_t r, int i) { return (r & 0x7ff) != 0 && (unsigned)(i % NE - 3) < (unsigned)NEU; });
           for (int k0 = 0; k0 < cnt; k0 += 8)
           {
             const int k = k0 + (lane >> 2);
             const bool valid = k < cnt;
-            const int i = queue[valid ? k : k0], sg = i / NE, e = i - sg * NE;
+            const int i = queue[valid ? k : k0], sg = i / NE, e = i - sg * NE - 3;
             dbfLumaSegmentQuad(&sm[(4 * sg) * DBF_PITCH + DBF_HALO - 4 + 4 * e], 1, DBF_PITCH, ra[i], maxv, lane & 3, valid);
           }
         }
         __syncthreads();
         // pass 2: horizontal edges y0 .. y0+TH (step 4), columns x0-4 .. x0+TW+3
-        constexpr int NSH = DBF_TW / 4 + 2;
+        constexpr int NSH = DBF_RECL, NSU = DBF_TW / 4 + 2;
         {
-          const int cnt = dbfCompact(rbv, P.n2, queue, [](uint32_t r) { return (r & 0x7ff) != 0; });
+          const int cnt = dbfCompact(rbv, P.n2, queue, [](uint32_t r, int i) { return (r & 0x7ff) != 0 && (unsigned)(i % NSH - 3) < (unsigned)NSU; });
           for (int k0 = 0; k0 < cnt; k0 += 8)
           {
             const int k = k0 + (lane >> 2);
             const bool valid = k < cnt;
-            const int i = queue[valid ? k : k0], e = i / NSH, sg = i - e * NSH;
+            const int i = queue[valid ? k : k0], e = i / NSH, sg = i - e * NSH - 3;
             dbfLumaSegmentQuad(&sm[(DBF_HALO + 4 * e) * DBF_PITCH + DBF_HALO - 4 + 4 * sg], DBF_PITCH, 1, rbv[i], maxv, lane & 3, valid);
           }
         }
@@ -543,10 +533,10 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
         const int tcShift = c ? VTMGPU_DBF_C_TCCR_SHIFT : 0, betaShift = c ? VTMGPU_DBF_C_BETACR_SHIFT : VTMGPU_DBF_C_BETACB_SHIFT;
         // pass 1: vertical edges on the 8-sample chroma grid; one item = the chroma rows of one 4-luma-row unit
         {
-          const int cnt = dbfCompact(ra, P.n1, queue, [tcShift](uint64_t r) { return ((r >> tcShift) & 0x7ff) != 0; });
+          const int cnt = dbfCompact(ra, P.n1, queue, [tcShift](uint64_t r, int i) { return ((r >> tcShift) & 0x7ff) != 0 && (i % 18) < 17; });
           for (int k = lane; k < cnt; k += 32)
           {
-            const int i = queue[k], sg = i / P.ne1, e = i - sg * P.ne1;
+            const int i = queue[k], sg = i / 18, e = i - sg * 18;
             const uint64_t rec = ra[i];
             dbfChromaSegment(&sm[(P.nv * sg) * DBF_PITCH + DBF_HALO + 8 * e], 1, DBF_PITCH, P.nv, (int)(rec >> tcShift) & 0x7ff, (int)(rec >> betaShift) & 0x7ff,
                              (rec & VTMGPU_DBF_C_LARGE) != 0, (rec & VTMGPU_DBF_C_CTB) != 0, !(rec & VTMGPU_DBF_C_PNOFILT), !(rec & VTMGPU_DBF_C_QNOFILT), maxv);
@@ -555,10 +545,11 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
         __syncthreads();
         // pass 2: horizontal edges, one more segment of columns on each side of the tile
         {
-          const int cnt = dbfCompact(rbv, P.n2, queue, [tcShift](uint64_t r) { return ((r >> tcShift) & 0x7ff) != 0; });
+          const int p2 = P.p2, ns2 = P.ns2;
+          const int cnt = dbfCompact(rbv, P.n2, queue, [tcShift, p2, ns2](uint64_t r, int i) { return ((r >> tcShift) & 0x7ff) != 0 && (unsigned)(i % p2 - 1) < (unsigned)ns2; });
           for (int k = lane; k < cnt; k += 32)
           {
-            const int i = queue[k], e = i / P.ns2, sg = i - e * P.ns2;
+            const int i = queue[k], e = i / p2, sg = i - e * p2 - 1;
             const uint64_t rec = rbv[i];
             dbfChromaSegment(&sm[(DBF_HALO + 8 * e) * DBF_PITCH + DBF_HALO - P.nh + P.nh * sg], DBF_PITCH, 1, P.nh, (int)(rec >> tcShift) & 0x7ff,
                              (int)(rec >> betaShift) & 0x7ff, (rec & VTMGPU_DBF_C_LARGE) != 0, (rec & VTMGPU_DBF_C_CTB) != 0, !(rec & VTMGPU_DBF_C_PNOFILT),

@@ -30,7 +30,8 @@ std::string g_createError;
 struct SideLayout     // byte offsets inside a slot's side-info block
 {
   size_t dbfL[2], dbfC[2], sao, alfTab, ctuCtl, alf, total;
-  size_t nL, nC[2];
+  size_t nL, nC[2];          // records of the ABI arrays (dense)
+  int recW[4], recH[4], recP[4];   // device record arrays lumaV, lumaH, chromaV, chromaH: width, height, row pitch (records; pitch * size is a multiple of 16 B for TMA)
 };
 
 size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -89,6 +90,7 @@ struct vtmgpu_ctx
   int rowBegin = 0, rowEnd = 0;         // luma rows the stage calls filter (band mode); whole picture by default
   CUtensorMap* tmapsDev = nullptr;     // [capacity][3 buffers][3 planes]: TMA descriptors of the plane buffers, box = smem tile of k_alf
   CUtensorMap* tmapsDbfDev = nullptr;  // the same planes, box = smem tile of k_dbf_sao
+  CUtensorMap* tmapsRecDev = nullptr;  // [capacity][4]: deblocking record arrays lumaV, lumaH, chromaV, chromaH as u32 tensors, box = records of one tile
 
   int fail(const char* fmt, ...)
   {
@@ -148,6 +150,7 @@ extern "C" void vtmgpu_destroy(vtmgpu_ctx* c)
   if (c->slotsDev) cudaFree(c->slotsDev);
   if (c->tmapsDev) cudaFree(c->tmapsDev);
   if (c->tmapsDbfDev) cudaFree(c->tmapsDbfDev);
+  if (c->tmapsRecDev) cudaFree(c->tmapsRecDev);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   for (auto& e : c->stageEv) if (e) cudaEventDestroy(e);
   if (c->ownStream) cudaStreamDestroy(c->ownStream);
@@ -189,8 +192,12 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
   L.nC[0] = g.ncomp > 1 ? (size_t)((g.w + (8 << g.sx) - 1) / (8 << g.sx)) * (g.h / 4) : 0;
   L.nC[1] = g.ncomp > 1 ? (size_t)((g.h + (8 << g.sy) - 1) / (8 << g.sy)) * (g.w / 4) : 0;
   size_t off = 0;
-  for (int d = 0; d < 2; d++) { L.dbfL[d] = off; off = alignUp(off + L.nL * 4, 256); }
-  for (int d = 0; d < 2; d++) { L.dbfC[d] = off; off = alignUp(off + L.nC[d] * 8, 256); }
+  L.recW[0] = L.recW[1] = g.w / 4; L.recH[0] = L.recH[1] = g.h / 4;
+  L.recW[2] = g.ncomp > 1 ? (g.w + (8 << g.sx) - 1) / (8 << g.sx) : 0; L.recH[2] = g.ncomp > 1 ? g.h / 4 : 0;
+  L.recW[3] = g.ncomp > 1 ? g.w / 4 : 0;                                L.recH[3] = g.ncomp > 1 ? (g.h + (8 << g.sy) - 1) / (8 << g.sy) : 0;
+  for (int a = 0; a < 4; a++) L.recP[a] = (int)alignUp(L.recW[a], a < 2 ? 4 : 2);
+  for (int d = 0; d < 2; d++) { L.dbfL[d] = off; off = alignUp(off + (size_t)L.recP[d] * L.recH[d] * 4, 256); }
+  for (int d = 0; d < 2; d++) { L.dbfC[d] = off; off = alignUp(off + (size_t)L.recP[2 + d] * L.recH[2 + d] * 8, 256); }
   L.sao = off;    off = alignUp(off + (size_t)c->nCtus * 3 * sizeof(SaoDev), 256);
   L.alfTab = off; off = alignUp(off + sizeof(AlfLumaEntry) * VTMGPU_MAX_LUMA_SETS * 25 * 4, 256);
   L.ctuCtl = off; off = alignUp(off + (size_t)c->nCtus * sizeof(CtuCtlDev), 256);
@@ -278,6 +285,26 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
       CUtensorMap** dev = which ? &c->tmapsDbfDev : &c->tmapsDev;
       CK(cudaMalloc((void**)dev, maps.size() * sizeof(CUtensorMap)), "tensor maps");
       CK(cudaMemcpy(*dev, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice), "tensor maps upload");
+    }
+    {
+      // deblocking record arrays as 2-D u32 tensors (a chroma record = 2 words); box = the records one tile consumes
+      std::vector<CUtensorMap> maps((size_t)s.capacity * 4);
+      memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
+      const DbfRecBoxes RB = dbfRecBoxes(g.sx, g.sy);
+      for (int sl = 0; sl < s.capacity; sl++)
+        for (int a = 0; a < (g.ncomp > 1 ? 4 : 2); a++)
+        {
+          const int words = a < 2 ? 1 : 2;
+          void* base = c->sideDev[sl] + (a < 2 ? L.dbfL[a] : L.dbfC[a - 2]);
+          const cuuint64_t dims[2] = { (cuuint64_t)L.recW[a] * words, (cuuint64_t)L.recH[a] }, strides[1] = { (cuuint64_t)L.recP[a] * words * 4 };
+          const cuuint32_t box[2] = { (cuuint32_t)RB.cols[a] * words, (cuuint32_t)RB.rows[a] }, es[2] = { 1, 1 };
+          const CUresult r = reinterpret_cast<EncodeFn>(fn)(&maps[(size_t)sl * 4 + a], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, base, dims, strides, box, es,
+                                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          if (r != CUDA_SUCCESS) { g_createError = "vtmgpu_create: cuTensorMapEncodeTiled (records) failed (" + std::to_string((int)r) + ")"; vtmgpu_destroy(c); return -1; }
+        }
+      CK(cudaMalloc((void**)&c->tmapsRecDev, maps.size() * sizeof(CUtensorMap)), "tensor maps");
+      CK(cudaMemcpy(c->tmapsRecDev, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice), "tensor maps upload");
     }
   }
   {
@@ -467,14 +494,24 @@ extern "C" int vtmgpu_set_deblock(vtmgpu_ctx* c, int slot, const vtmgpu_deblock_
   if (p)
   {
     const SideLayout& L = c->lay;
+    // device arrays keep the ABI indexing but with a row pitch that is a multiple of 16 bytes (TMA); the records of the edges
+    // ON the picture border (column 0 of the vertical-edge arrays, row 0 of the horizontal-edge arrays) are never filtered
+    // (no neighbour, LoopFilter.cpp:918-933) and are cleared so that the kernel needs no position test
     for (int d = 0; d < 2; d++)
     {
       if (!p->luma[d]) return c->fail("set_deblock: luma[%d] is NULL", d);
-      memcpy(c->pinnedSide(slot) + L.dbfL[d], p->luma[d], L.nL * 4);
-      if (L.nC[d])
+      uint32_t* dl = reinterpret_cast<uint32_t*>(c->pinnedSide(slot) + L.dbfL[d]);
+      for (int r = 0; r < L.recH[d]; r++) memcpy(dl + (size_t)r * L.recP[d], p->luma[d] + (size_t)r * L.recW[d], (size_t)L.recW[d] * 4);
+      if (d == 0) for (int r = 0; r < L.recH[0]; r++) dl[(size_t)r * L.recP[0]] = 0;
+      else memset(dl, 0, (size_t)L.recW[1] * 4);
+      if (L.recW[2 + d])
       {
-        if (p->chroma[d]) memcpy(c->pinnedSide(slot) + L.dbfC[d], p->chroma[d], L.nC[d] * 8);
-        else memset(c->pinnedSide(slot) + L.dbfC[d], 0, L.nC[d] * 8);
+        uint64_t* dc = reinterpret_cast<uint64_t*>(c->pinnedSide(slot) + L.dbfC[d]);
+        const int a = 2 + d;
+        if (p->chroma[d]) for (int r = 0; r < L.recH[a]; r++) memcpy(dc + (size_t)r * L.recP[a], p->chroma[d] + (size_t)r * L.recW[a], (size_t)L.recW[a] * 8);
+        else memset(dc, 0, (size_t)L.recP[a] * L.recH[a] * 8);
+        if (d == 0) for (int r = 0; r < L.recH[a]; r++) dc[(size_t)r * L.recP[a]] = 0;
+        else memset(dc, 0, (size_t)L.recW[a] * 8);
       }
     }
     if (c->pushSide(slot, L.dbfL[0], L.sao - L.dbfL[0])) return -1;
@@ -731,7 +768,7 @@ int launchDbfSao(vtmgpu_ctx* c, int first, int count, int doDbf, int doSao)
     TileStep st;
     st.dSlot = grid / items;
     st.dItem = grid % items;
-    k_dbf_sao<<<grid, DBF_THREADS, DBF_SMEM_BYTES, c->stream>>>(c->slotsDev, c->tmapsDbfDev, s, n, src, dst, g, L, st, doDbf, doSao);
+    k_dbf_sao<<<grid, DBF_THREADS, DBF_SMEM_BYTES, c->stream>>>(c->slotsDev, c->tmapsDbfDev, c->tmapsRecDev, s, n, src, dst, g, L, st, doDbf | ((getenv("VTMGPU_DEBUG") ? atoi(getenv("VTMGPU_DEBUG")) : 0) << 1), doSao);
     c->launches++;
     for (int i = s; i < s + n; i++) c->cur[i] = dst;
     return c->cuda(cudaGetLastError(), "k_dbf_sao launch");
