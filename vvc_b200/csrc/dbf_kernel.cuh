@@ -333,8 +333,8 @@ constexpr int DBF_RECB_BYTES = 4992;                    // pass-2 records: luma 
 constexpr int DBF_TILE_BYTES = DBF_SH * DBF_PITCH * 2;  // 24320 (multiple of 128: TMA destination)
 constexpr int DBF_STAGE_BYTES = DBF_TILE_BYTES + DBF_RECA_BYTES + DBF_RECB_BYTES;
 constexpr int DBF_RECL = 40;                            // columns of the luma record boxes
-constexpr int DBF_QUEUE = 128;                          // active-segment queue entries per warp (a warp scans <= 96 slots per pass)
-constexpr int DBF_SMEM_BYTES = 2 * DBF_STAGE_BYTES + 16 + (DBF_THREADS / 32) * DBF_QUEUE * 2;
+constexpr int DBF_QUEUE = 832;                          // queue entries per pass (>= record slots of a pass)                          // active-segment queue entries per warp (a warp scans <= 96 slots per pass)
+constexpr int DBF_SMEM_BYTES = 2 * DBF_STAGE_BYTES + 32 + 2 * DBF_QUEUE * 2;      // stages, 2 mbarriers + 2 counters, 2 queues
 
 // record boxes of one tile (columns x rows, in records) for the arrays lumaV, lumaH, chromaV, chromaH.  TMA wants the first
 // element of a box row on a 16-byte boundary and the row length a multiple of 16 bytes, so the luma boxes start 4 records
@@ -394,22 +394,23 @@ __device__ __forceinline__ DbfPassGeom dbfPassGeom(int comp, const Geom& g)
   return P;
 }
 
-// Warp-local compaction: the warp scans its share of the n record slots (chunks of 32, interleaved over the 8 warps) and
-// queues the indices of the active ones (typically < 10 % of the slots) so that the filters run on full warps.
-template <class RecT, class Active> __device__ __forceinline__ int dbfCompact(const RecT* rec, int n, uint16_t* q, Active act)
+// CTA-wide compaction: all warps scan the n record slots of a pass (chunks of 32, interleaved over the warps) and append the
+// indices of the active ones (typically < 10 % of the slots) to one queue -- one shared-memory atomic per warp and chunk --
+// so that the filters run on full warps and every warp gets the same share.  *count must be 0 on entry.
+template <class RecT, class Active> __device__ __forceinline__ void dbfCompact(const RecT* rec, int n, uint16_t* q, int* count, Active act)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int cnt = 0;
   for (int i0 = warp * 32; i0 < n; i0 += DBF_THREADS)
   {
     const int i = i0 + lane;
     const bool a = i < n && act(rec[i], i);
     const unsigned m = __ballot_sync(0xffffffffu, a);
-    if (a) q[cnt + __popc(m & ((1u << lane) - 1))] = (uint16_t)i;
-    cnt += __popc(m);
+    if (m == 0) continue;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (a) q[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)i;
   }
-  __syncwarp();
-  return cnt;
 }
 
 // issues the asynchronous loads of one tile into a stage (one thread): three TMA boxes on one mbarrier -- the samples
@@ -446,7 +447,8 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
   extern __shared__ __align__(128) unsigned char smraw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + 2 * DBF_STAGE_BYTES);
   const int tid = threadIdx.x, lane = tid & 31;
-  uint16_t* queue = reinterpret_cast<uint16_t*>(smraw + 2 * DBF_STAGE_BYTES + 16) + (tid >> 5) * DBF_QUEUE;
+  int* qcount = reinterpret_cast<int*>(smraw + 2 * DBF_STAGE_BYTES + 16);          // [2]
+  uint16_t* queue1 = reinterpret_cast<uint16_t*>(smraw + 2 * DBF_STAGE_BYTES + 32), *queue2 = queue1 + DBF_QUEUE;
   const int itemsPerSlot = L.tilesL + 2 * L.tilesC;
   int slot = blockIdx.x / itemsPerSlot, item = blockIdx.x - slot * itemsPerSlot;
   if (slot >= numSlots) return;
@@ -455,6 +457,7 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
     mbarInit(&bars[0], 1);
     mbarInit(&bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    qcount[0] = qcount[1] = 0;
   }
   __syncthreads();
   DbfTile T = dbfDecodeTile(item, L), Tn = T;
@@ -499,28 +502,32 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
       {
         const uint32_t* ra = reinterpret_cast<const uint32_t*>(stageMem + DBF_TILE_BYTES);
         const uint32_t* rbv = reinterpret_cast<const uint32_t*>(stageMem + DBF_TILE_BYTES + DBF_RECA_BYTES);
-        // pass 1: vertical edges x0-4 .. x0+TW+4 (step 4), all rows of tile + halo; 8 segments per warp round, one line per lane
+        // both passes are compacted up front (the records are resident); then 8 segments per warp round, one line per lane
         constexpr int NE = DBF_RECL, NEU = DBF_TW / 4 + 3;     // box pitch, edges used (box columns 3 .. 3+NEU-1)
+        constexpr int NSH = DBF_RECL, NSU = DBF_TW / 4 + 2;
+        dbfCompact(ra, P.n1, queue1, &qcount[0], [](uint32_t r, int i) { return (r & 0x7ff) != 0 && (unsigned)(i % NE - 3) < (unsigned)NEU; });
+        dbfCompact(rbv, P.n2, queue2, &qcount[1], [](uint32_t r, int i) { return (r & 0x7ff) != 0 && (unsigned)(i % NSH - 3) < (unsigned)NSU; });
+        __syncthreads();
+        // pass 1: vertical edges x0-4 .. x0+TW+4 (step 4), all rows of tile + halo
         {
-          const int cnt = dbfCompact(ra, P.n1, queue, [](uint32_t r, int i) { return (r & 0x7ff) != 0 && (unsigned)(i % NE - 3) < (unsigned)NEU; });
-          for (int k0 = 0; k0 < cnt; k0 += 8)
+          const int cnt = qcount[0];
+          for (int k0 = (tid >> 5) * 8; k0 < cnt; k0 += DBF_THREADS / 4)
           {
             const int k = k0 + (lane >> 2);
             const bool valid = k < cnt;
-            const int i = queue[valid ? k : k0], sg = i / NE, e = i - sg * NE - 3;
+            const int i = queue1[valid ? k : k0], sg = i / NE, e = i - sg * NE - 3;
             dbfLumaSegmentQuad(&sm[(4 * sg) * DBF_PITCH + DBF_HALO - 4 + 4 * e], 1, DBF_PITCH, ra[i], maxv, lane & 3, valid);
           }
         }
         __syncthreads();
         // pass 2: horizontal edges y0 .. y0+TH (step 4), columns x0-4 .. x0+TW+3
-        constexpr int NSH = DBF_RECL, NSU = DBF_TW / 4 + 2;
         {
-          const int cnt = dbfCompact(rbv, P.n2, queue, [](uint32_t r, int i) { return (r & 0x7ff) != 0 && (unsigned)(i % NSH - 3) < (unsigned)NSU; });
-          for (int k0 = 0; k0 < cnt; k0 += 8)
+          const int cnt = qcount[1];
+          for (int k0 = (tid >> 5) * 8; k0 < cnt; k0 += DBF_THREADS / 4)
           {
             const int k = k0 + (lane >> 2);
             const bool valid = k < cnt;
-            const int i = queue[valid ? k : k0], e = i / NSH, sg = i - e * NSH - 3;
+            const int i = queue2[valid ? k : k0], e = i / NSH, sg = i - e * NSH - 3;
             dbfLumaSegmentQuad(&sm[(DBF_HALO + 4 * e) * DBF_PITCH + DBF_HALO - 4 + 4 * sg], DBF_PITCH, 1, rbv[i], maxv, lane & 3, valid);
           }
         }
@@ -531,12 +538,16 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
         const uint64_t* rbv = reinterpret_cast<const uint64_t*>(stageMem + DBF_TILE_BYTES + DBF_RECA_BYTES);
         const int c = comp - 1;
         const int tcShift = c ? VTMGPU_DBF_C_TCCR_SHIFT : 0, betaShift = c ? VTMGPU_DBF_C_BETACR_SHIFT : VTMGPU_DBF_C_BETACB_SHIFT;
+        const int p2 = P.p2, ns2 = P.ns2;
+        dbfCompact(ra, P.n1, queue1, &qcount[0], [tcShift](uint64_t r, int i) { return ((r >> tcShift) & 0x7ff) != 0 && (i % 18) < 17; });
+        dbfCompact(rbv, P.n2, queue2, &qcount[1], [tcShift, p2, ns2](uint64_t r, int i) { return ((r >> tcShift) & 0x7ff) != 0 && (unsigned)(i % p2 - 1) < (unsigned)ns2; });
+        __syncthreads();
         // pass 1: vertical edges on the 8-sample chroma grid; one item = the chroma rows of one 4-luma-row unit
         {
-          const int cnt = dbfCompact(ra, P.n1, queue, [tcShift](uint64_t r, int i) { return ((r >> tcShift) & 0x7ff) != 0 && (i % 18) < 17; });
-          for (int k = lane; k < cnt; k += 32)
+          const int cnt = qcount[0];
+          for (int k = tid; k < cnt; k += DBF_THREADS)
           {
-            const int i = queue[k], sg = i / 18, e = i - sg * 18;
+            const int i = queue1[k], sg = i / 18, e = i - sg * 18;
             const uint64_t rec = ra[i];
             dbfChromaSegment(&sm[(P.nv * sg) * DBF_PITCH + DBF_HALO + 8 * e], 1, DBF_PITCH, P.nv, (int)(rec >> tcShift) & 0x7ff, (int)(rec >> betaShift) & 0x7ff,
                              (rec & VTMGPU_DBF_C_LARGE) != 0, (rec & VTMGPU_DBF_C_CTB) != 0, !(rec & VTMGPU_DBF_C_PNOFILT), !(rec & VTMGPU_DBF_C_QNOFILT), maxv);
@@ -545,11 +556,10 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
         __syncthreads();
         // pass 2: horizontal edges, one more segment of columns on each side of the tile
         {
-          const int p2 = P.p2, ns2 = P.ns2;
-          const int cnt = dbfCompact(rbv, P.n2, queue, [tcShift, p2, ns2](uint64_t r, int i) { return ((r >> tcShift) & 0x7ff) != 0 && (unsigned)(i % p2 - 1) < (unsigned)ns2; });
-          for (int k = lane; k < cnt; k += 32)
+          const int cnt = qcount[1];
+          for (int k = tid; k < cnt; k += DBF_THREADS)
           {
-            const int i = queue[k], e = i / p2, sg = i - e * p2 - 1;
+            const int i = queue2[k], e = i / p2, sg = i - e * p2 - 1;
             const uint64_t rec = rbv[i];
             dbfChromaSegment(&sm[(DBF_HALO + 8 * e) * DBF_PITCH + DBF_HALO - P.nh + P.nh * sg], DBF_PITCH, 1, P.nh, (int)(rec >> tcShift) & 0x7ff,
                              (int)(rec >> betaShift) & 0x7ff, (rec & VTMGPU_DBF_C_LARGE) != 0, (rec & VTMGPU_DBF_C_CTB) != 0, !(rec & VTMGPU_DBF_C_PNOFILT),
@@ -564,6 +574,7 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
     if (sx_ < w && sy_ < h)
       saoStrip(dst.p + (size_t)sy_ * dst.pitch + sx_, dst.pitch, &sm[(DBF_HALO + 4 * rb) * DBF_PITCH + DBF_HALO + 8 * gcol], DBF_PITCH, min(4, h - sy_), sx_, sy_,
                pq, w, h, cwLog | chLog << 8 | (comp ? g.bdC : g.bdL) << 16);
+    if (tid == 0) qcount[0] = qcount[1] = 0;
     __syncthreads();                                         // the stage is free for the load after next
     slot = nslot; item = nitem; T = Tn;
   }
