@@ -122,16 +122,21 @@ def test_bad_arguments_fail_loudly():
     ctx.close()
 
 
-def test_decoder_drop_in_md5():
-    """The reference decoder with OUR filter entry points linked in (vvc_b200/_bin/DecoderApp_gpu) decodes a
-    reference-encoded stream (full CTC tool set, RA) and every picture matches the encoder's MD5 SEI."""
+STREAMS = [("ra_416x240.bin", 8), ("ld444_1080p.bin", 16), ("ra_1080p.bin", 32), ("ai_4320p.bin", 1)]
+
+
+@pytest.mark.parametrize("stream,pictures", STREAMS)
+def test_decoder_drop_in_md5(stream, pictures):
+    """The reference decoder with OUR filter entry points linked in (vvc_b200/_bin/DecoderApp_gpu) decodes reference-encoded
+    streams -- full CTC tool set RA 416x240, 4:4:4 low delay 1080p with chroma ALF + CC-ALF (BASELINE config 5), RA 1080p
+    (config 2), one 8K intra picture (config 4) -- and every picture matches the MD5 SEI the reference encoder wrote."""
     import os
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     dec = os.path.join(root, "vvc_b200", "_bin", "DecoderApp_gpu")
     if not os.path.exists(dec):
         pytest.skip("DecoderApp_gpu not built (needs the reference sources at build time)")
-    r = subprocess.run([dec, "-b", os.path.join(root, "tests", "golden", "streams", "ra_416x240.bin"), "-d", "0"],
-                       capture_output=True, text=True, timeout=300, env=dict(os.environ, VTMGPU_SHIM_BACKEND="gpu"))
+    r = subprocess.run([dec, "-b", os.path.join(root, "tests", "golden", "streams", stream), "-d", "0"],
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, VTMGPU_SHIM_BACKEND="gpu"))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert r.stdout.count("(OK)") == 8 and "ERROR" not in r.stdout, r.stdout[-2000:]
+    assert r.stdout.count("(OK)") == pictures and "ERROR" not in r.stdout, r.stdout[-2000:]

@@ -442,7 +442,7 @@ __device__ __forceinline__ void saPrefetch(unsigned char* smraw, const SaLayout&
 // filters tile i, the TMA loads of tile i+1 are in flight (two stages).  maps = tensor maps of the source buffer of the
 // first slot: [slot][3 buffers][3 planes].
 __global__ void __launch_bounds__(SA_THREADS, 4) k_alf(const SlotDev* __restrict__ slots, const CUtensorMap* __restrict__ tmaps, int firstSlot, int numSlots,
-                                                           int srcBuf, int dstBuf, Geom g, int tilesX, int tilesY, int ty0, SaStep step, int dbg)
+                                                           int srcBuf, int dstBuf, Geom g, int tilesX, int tilesY, int ty0, SaStep step)
 {
   extern __shared__ __align__(128) unsigned char smraw[];
   const SaLayout L = saLayout(g.sx, g.sy, g.ncomp);
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(SA_THREADS, 4) k_alf(const SlotDev* __restrict
     const int x0 = cur.tx * SA_T, y0 = (cur.ty + ty0) * SA_TH;
     const CtuCtlDev ctl = reinterpret_cast<const CtuCtlDev*>(smraw + L.offPar)[stage];
     const bool alfOn = S.alfOn != 0;
-    const bool alfY = alfOn && ctl.enY != 0 && !(dbg & 8), alfCb = alfOn && ctl.enCb != 0, alfCr = alfOn && ctl.enCr != 0;
+    const bool alfY = alfOn && ctl.enY != 0, alfCb = alfOn && ctl.enCb != 0, alfCr = alfOn && ctl.enCr != 0;
     const int ccCb = alfOn ? ctl.ccCb : 0, ccCr = alfOn ? ctl.ccCr : 0;
     pel* const A0 = reinterpret_cast<pel*>(smraw + L.offA(stage, 0));
     pel* const A1 = reinterpret_cast<pel*>(smraw + L.offA(stage, 1));
@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(SA_THREADS, 4) k_alf(const SlotDev* __restrict
     const int bx = x0 + 4 * bj, by = y0 + 4 * bi;
     const pel* c0 = &lumaB[(4 * bi + SA_HY) * SA_P + 4 * bj + SA_HX];
     const int yb = by & ctuMask;
-    const bool vbBlk = (yb == vbL - 4 || yb == vbL) && !(dbg & 1);             // uniform per warp (two block rows) for CTU sizes >= 32
+    const bool vbBlk = yb == vbL - 4 || yb == vbL;             // uniform per warp (two block rows) for CTU sizes >= 32
     if (alfY)
     {
       if (!vbBlk) alfOwnCells(cell, c0, bi, bj);
@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(SA_THREADS, 4) k_alf(const SlotDev* __restrict
           *reinterpret_cast<int4*>(dstY.p + (size_t)y * dstY.pitch + x) = *reinterpret_cast<const int4*>(&lumaB[(r + SA_HY) * SA_P + 8 * gc + SA_HX]);
       }
     }
-    if (g.ncomp > 1 && !(dbg & 4))
+    if (g.ncomp > 1)
     {
       // chroma: one item = 4 horizontally adjacent samples
       const int cx0 = x0 >> g.sx, cy0 = y0 >> g.sy, qShift = 4 - g.sx, quads = (tw >> 2) << thLogC;       // tw / 4 = 1 << qShift

@@ -416,20 +416,20 @@ template <class RecT, class Active> __device__ __forceinline__ void dbfCompact(c
 // issues the asynchronous loads of one tile into a stage (one thread): three TMA boxes on one mbarrier -- the samples
 // (tile + 8 halo) and the segment records of the two passes.  Everything outside the picture arrives as zeros = "no edge".
 __device__ __forceinline__ void dbfPrefetch(unsigned char* stageMem, uint64_t* bar, const CUtensorMap* planeMap, const CUtensorMap* recMaps, const DbfTile& T,
-                                            const Geom& g, bool dbfOn, int dbg = 0)
+                                            const Geom& g, bool dbfOn)
 {
   if (threadIdx.x != 0) return;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   const DbfRecBoxes RB = dbfRecBoxes(g.sx, g.sy);
   const int a = T.comp ? 2 : 0, words = T.comp ? 2 : 1;
-  uint32_t recBytes = dbfOn ? (uint32_t)(((dbg & 1) ? 0 : RB.cols[a] * RB.rows[a]) + ((dbg & 2) ? 0 : RB.cols[a + 1] * RB.rows[a + 1])) * words * 4 : 0u;
+  const uint32_t recBytes = dbfOn ? (uint32_t)(RB.cols[a] * RB.rows[a] + RB.cols[a + 1] * RB.rows[a + 1]) * words * 4 : 0u;
   mbarExpectTx(bar, DBF_TILE_BYTES + recBytes);
   tmaLoad2D(stageMem, planeMap, T.x0 - DBF_HALO, T.y0 - DBF_HALO, bar);
   if (!dbfOn) return;
   if (T.comp == 0)
   {
-    if (!(dbg & 1)) tmaLoad2D(stageMem + DBF_TILE_BYTES, recMaps + 0, (T.x0 >> 2) - 4, (T.y0 - DBF_HALO) >> 2, bar);
-    if (!(dbg & 2)) tmaLoad2D(stageMem + DBF_TILE_BYTES + DBF_RECA_BYTES, recMaps + 1, (T.x0 >> 2) - 4, T.y0 >> 2, bar);
+    tmaLoad2D(stageMem + DBF_TILE_BYTES, recMaps + 0, (T.x0 >> 2) - 4, (T.y0 - DBF_HALO) >> 2, bar);
+    tmaLoad2D(stageMem + DBF_TILE_BYTES + DBF_RECA_BYTES, recMaps + 1, (T.x0 >> 2) - 4, T.y0 >> 2, bar);
   }
   else
   {
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
   DbfTile T = dbfDecodeTile(item, L), Tn = T;
   {
     const SlotDev& S = slots[firstSlot + slot];
-    dbfPrefetch(smraw, &bars[0], tmaps + ((size_t)(firstSlot + slot) * 3 + srcBuf) * 3 + T.comp, recMaps + (size_t)(firstSlot + slot) * 4, T, g, doDbf && S.dbfOn, doDbf >> 1);
+    dbfPrefetch(smraw, &bars[0], tmaps + ((size_t)(firstSlot + slot) * 3 + srcBuf) * 3 + T.comp, recMaps + (size_t)(firstSlot + slot) * 4, T, g, doDbf && S.dbfOn);
   }
   for (uint32_t it = 0; slot < numSlots; it++)
   {
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
       const SlotDev& Sn = slots[firstSlot + nslot];
       Tn = dbfDecodeTile(nitem, L);
       dbfPrefetch(smraw + (stage ^ 1) * DBF_STAGE_BYTES, &bars[stage ^ 1], tmaps + ((size_t)(firstSlot + nslot) * 3 + srcBuf) * 3 + Tn.comp,
-                  recMaps + (size_t)(firstSlot + nslot) * 4, Tn, g, doDbf && Sn.dbfOn, doDbf >> 1);
+                  recMaps + (size_t)(firstSlot + nslot) * 4, Tn, g, doDbf && Sn.dbfOn);
     }
 
     const int comp = T.comp, x0 = T.x0, y0 = T.y0;
@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
     mbarWait(&bars[stage], (it >> 1) & 1);                   // samples and records of this tile are in shared memory
     pel* sm = reinterpret_cast<pel*>(stageMem);
 
-    if ((doDbf & 1) && !(doDbf >> 1) && S.dbfOn)
+    if (doDbf && S.dbfOn)
     {
       const int maxv = (1 << (comp ? g.bdC : g.bdL)) - 1;
       const DbfPassGeom P = dbfPassGeom(comp, g);

@@ -768,7 +768,7 @@ int launchDbfSao(vtmgpu_ctx* c, int first, int count, int doDbf, int doSao)
     TileStep st;
     st.dSlot = grid / items;
     st.dItem = grid % items;
-    k_dbf_sao<<<grid, DBF_THREADS, DBF_SMEM_BYTES, c->stream>>>(c->slotsDev, c->tmapsDbfDev, c->tmapsRecDev, s, n, src, dst, g, L, st, doDbf | ((getenv("VTMGPU_DEBUG") ? atoi(getenv("VTMGPU_DEBUG")) : 0) << 1), doSao);
+    k_dbf_sao<<<grid, DBF_THREADS, DBF_SMEM_BYTES, c->stream>>>(c->slotsDev, c->tmapsDbfDev, c->tmapsRecDev, s, n, src, dst, g, L, st, doDbf, doSao);
     c->launches++;
     for (int i = s; i < s + n; i++) c->cur[i] = dst;
     return c->cuda(cudaGetLastError(), "k_dbf_sao launch");
@@ -792,7 +792,7 @@ int launchAlf(vtmgpu_ctx* c, int first, int count)
     st.dx = grid % tilesX;
     st.dy = (grid / tilesX) % tilesY;
     st.ds = (grid / tilesX) / tilesY;
-    k_alf<<<grid, SA_THREADS, smem, c->stream>>>(c->slotsDev, c->tmapsDev, s, n, src, dst, g, tilesX, tilesY, ty0, st, getenv("VTMGPU_DEBUG") ? atoi(getenv("VTMGPU_DEBUG")) : 0);
+    k_alf<<<grid, SA_THREADS, smem, c->stream>>>(c->slotsDev, c->tmapsDev, s, n, src, dst, g, tilesX, tilesY, ty0, st);
     c->launches++;
     for (int i = s; i < s + n; i++) c->cur[i] = dst;
     return c->cuda(cudaGetLastError(), "k_alf launch");
