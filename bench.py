@@ -302,12 +302,25 @@ def main():
     ectx = [gpu.Context(seq, capacity=CH, device=local) for _ in range(NCTX)]
     pin_in = [[torch.from_numpy(p.copy()).pin_memory() for p in c.pre] for c in caps]
     pin_out = [[[torch.empty_like(t).pin_memory() for t in pin_in[0]] for _ in range(CH)] for _ in range(NCTX)]
+    import ctypes as C
+    from vvc_b200 import abi
     side = []
     for c in caps:
         ctus = c.sao_ctus()
         if ctus is not None:
             gpu.sao_reconstruct(ctus, c.width_in_ctus, c.ncomp, c.sao_scale[0], c.sao_scale[1])
-        side.append((c.deblock_params(), ctus, c.alf_params()))
+        # the decoder-side producer of the segment records writes them into page-locked memory: no staging copy in the library
+        dp, keep = abi.DeblockParams(), []
+        for d in range(2):
+            tl = torch.from_numpy(c.dbf_luma[d].view(np.int32).copy()).pin_memory()
+            keep.append(tl)
+            dp.luma[d] = C.cast(tl.data_ptr(), C.POINTER(C.c_uint32))
+            if c.dbf_chroma[d].size:
+                tc = torch.from_numpy(c.dbf_chroma[d].view(np.int64).copy()).pin_memory()
+                keep.append(tc)
+                dp.chroma[d] = C.cast(tc.data_ptr(), C.POINTER(C.c_uint64))
+        dp._keep = keep
+        side.append((dp, ctus, c.alf_params()))
     h2d = sum(t.numel() * 2 for t in pin_in[0]) + sum(a.nbytes for a in caps[0].dbf_luma) + sum(a.nbytes for a in caps[0].dbf_chroma)
     d2h = sum(t.numel() * 2 for t in pin_in[0])
 
@@ -319,7 +332,7 @@ def main():
             for j in range(CH):
                 i = (base + j) % len(caps)
                 cx.upload(j, [t.numpy() for t in pin_in[i]], sync=False)
-                cx.set_deblock(j, side[i][0])
+                cx.set_deblock(j, side[i][0], sync=False)
                 cx.set_sao(j, side[i][1])
                 cx.set_alf(j, side[i][2])
             cx.filter(0, CH, sync=False)

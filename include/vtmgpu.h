@@ -211,6 +211,9 @@ int vtmgpu_download_async(vtmgpu_ctx* ctx, int slot, int16_t* const plane[3], co
 
 /* per-picture side information (host pointers; copied before return, never retained) */
 int vtmgpu_set_deblock(vtmgpu_ctx* ctx, int slot, const vtmgpu_deblock_params* p);   /* NULL = stage off */
+/* the same without the staging copy: the record arrays are read by asynchronous copies on the ctx stream and must stay valid
+ * (and should be page-locked) until vtmgpu_sync */
+int vtmgpu_set_deblock_async(vtmgpu_ctx* ctx, int slot, const vtmgpu_deblock_params* p);
 int vtmgpu_set_sao    (vtmgpu_ctx* ctx, int slot, const vtmgpu_sao_params* p);       /* NULL = stage off */
 int vtmgpu_set_alf    (vtmgpu_ctx* ctx, int slot, const vtmgpu_alf_params* p);       /* NULL = stage off */
 

@@ -484,7 +484,27 @@ extern "C" int vtmgpu_rewind(vtmgpu_ctx* c, int first, int count)
 // ------------------------------------------------------------------------------------------------------------
 // side information
 // ------------------------------------------------------------------------------------------------------------
-extern "C" int vtmgpu_set_deblock(vtmgpu_ctx* c, int slot, const vtmgpu_deblock_params* p)
+namespace
+{
+// the records of the edges ON the picture border (column 0 of the vertical-edge arrays, row 0 of the horizontal-edge arrays)
+// are never filtered (no neighbour, LoopFilter.cpp:918-933): cleared on the device so that the kernel needs no position test
+int clearBorderRecords(vtmgpu_ctx* c, int slot)
+{
+  const SideLayout& L = c->lay;
+  unsigned char* d = c->sideDev[slot];
+  if (c->cuda(cudaMemset2DAsync(d + L.dbfL[0], (size_t)L.recP[0] * 4, 0, 4, L.recH[0], c->stream), "record clear")) return -1;
+  if (c->cuda(cudaMemsetAsync(d + L.dbfL[1], 0, (size_t)L.recW[1] * 4, c->stream), "record clear")) return -1;
+  if (L.recW[2])
+  {
+    if (c->cuda(cudaMemset2DAsync(d + L.dbfC[0], (size_t)L.recP[2] * 8, 0, 8, L.recH[2], c->stream), "record clear")) return -1;
+    if (c->cuda(cudaMemsetAsync(d + L.dbfC[1], 0, (size_t)L.recW[3] * 8, c->stream), "record clear")) return -1;
+  }
+  return 0;
+}
+
+// device arrays keep the ABI indexing but with a row pitch that is a multiple of 16 bytes (TMA).  direct = copy straight
+// from the caller's arrays (asynchronous when they are page-locked), else through the context's pinned staging block.
+int setDeblock(vtmgpu_ctx* c, int slot, const vtmgpu_deblock_params* p, bool direct)
 {
   if (!c) return -1;
   if (!c->slotOk(slot, 1)) return c->fail("set_deblock: bad slot %d", slot);
@@ -494,30 +514,39 @@ extern "C" int vtmgpu_set_deblock(vtmgpu_ctx* c, int slot, const vtmgpu_deblock_
   if (p)
   {
     const SideLayout& L = c->lay;
-    // device arrays keep the ABI indexing but with a row pitch that is a multiple of 16 bytes (TMA); the records of the edges
-    // ON the picture border (column 0 of the vertical-edge arrays, row 0 of the horizontal-edge arrays) are never filtered
-    // (no neighbour, LoopFilter.cpp:918-933) and are cleared so that the kernel needs no position test
-    for (int d = 0; d < 2; d++)
+    for (int a = 0; a < 4; a++)
     {
-      if (!p->luma[d]) return c->fail("set_deblock: luma[%d] is NULL", d);
-      uint32_t* dl = reinterpret_cast<uint32_t*>(c->pinnedSide(slot) + L.dbfL[d]);
-      for (int r = 0; r < L.recH[d]; r++) memcpy(dl + (size_t)r * L.recP[d], p->luma[d] + (size_t)r * L.recW[d], (size_t)L.recW[d] * 4);
-      if (d == 0) for (int r = 0; r < L.recH[0]; r++) dl[(size_t)r * L.recP[0]] = 0;
-      else memset(dl, 0, (size_t)L.recW[1] * 4);
-      if (L.recW[2 + d])
+      if (!L.recW[a]) continue;
+      const int d = a & 1, es = a < 2 ? 4 : 8;
+      const void* src = a < 2 ? (const void*)p->luma[d] : (const void*)p->chroma[d];
+      const size_t off = a < 2 ? L.dbfL[d] : L.dbfC[d];
+      if (a < 2 && !src) return c->fail("set_deblock: luma[%d] is NULL", d);
+      if (!src)
       {
-        uint64_t* dc = reinterpret_cast<uint64_t*>(c->pinnedSide(slot) + L.dbfC[d]);
-        const int a = 2 + d;
-        if (p->chroma[d]) for (int r = 0; r < L.recH[a]; r++) memcpy(dc + (size_t)r * L.recP[a], p->chroma[d] + (size_t)r * L.recW[a], (size_t)L.recW[a] * 8);
-        else memset(dc, 0, (size_t)L.recP[a] * L.recH[a] * 8);
-        if (d == 0) for (int r = 0; r < L.recH[a]; r++) dc[(size_t)r * L.recP[a]] = 0;
-        else memset(dc, 0, (size_t)L.recW[a] * 8);
+        if (c->cuda(cudaMemsetAsync(c->sideDev[slot] + off, 0, (size_t)L.recP[a] * L.recH[a] * es, c->stream), "set_deblock")) return -1;
+        continue;
+      }
+      if (direct)
+      {
+        if (c->cuda(cudaMemcpy2DAsync(c->sideDev[slot] + off, (size_t)L.recP[a] * es, src, (size_t)L.recW[a] * es, (size_t)L.recW[a] * es, L.recH[a],
+                                      cudaMemcpyHostToDevice, c->stream), "set_deblock")) return -1;
+      }
+      else
+      {
+        unsigned char* stage = c->pinnedSide(slot) + off;
+        if (L.recP[a] == L.recW[a]) memcpy(stage, src, (size_t)L.recW[a] * L.recH[a] * es);
+        else for (int r = 0; r < L.recH[a]; r++) memcpy(stage + (size_t)r * L.recP[a] * es, (const unsigned char*)src + (size_t)r * L.recW[a] * es, (size_t)L.recW[a] * es);
+        if (c->pushSide(slot, off, (size_t)L.recP[a] * L.recH[a] * es)) return -1;
       }
     }
-    if (c->pushSide(slot, L.dbfL[0], L.sao - L.dbfL[0])) return -1;
+    if (clearBorderRecords(c, slot)) return -1;
   }
   return c->pushSlot(slot);
 }
+}   // namespace
+
+extern "C" int vtmgpu_set_deblock(vtmgpu_ctx* c, int slot, const vtmgpu_deblock_params* p) { return setDeblock(c, slot, p, false); }
+extern "C" int vtmgpu_set_deblock_async(vtmgpu_ctx* c, int slot, const vtmgpu_deblock_params* p) { return setDeblock(c, slot, p, true); }
 
 extern "C" int vtmgpu_sao_reconstruct(vtmgpu_sao_ctu* ctu, int num_ctus, int width_in_ctus, int num_comps, int log2_scale_luma, int log2_scale_chroma)
 {

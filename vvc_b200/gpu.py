@@ -51,6 +51,7 @@ def load_library(path=None):
         "vtmgpu_upload": (C.c_int, planes_in), "vtmgpu_download": (C.c_int, planes_in),
         "vtmgpu_upload_async": (C.c_int, planes_in), "vtmgpu_download_async": (C.c_int, planes_in),
         "vtmgpu_set_deblock": (C.c_int, [ctx, C.c_int, C.POINTER(abi.DeblockParams)]),
+        "vtmgpu_set_deblock_async": (C.c_int, [ctx, C.c_int, C.POINTER(abi.DeblockParams)]),
         "vtmgpu_set_sao": (C.c_int, [ctx, C.c_int, C.POINTER(abi.SaoParams)]),
         "vtmgpu_set_alf": (C.c_int, [ctx, C.c_int, C.POINTER(abi.AlfParams)]),
         "vtmgpu_sao_reconstruct": (C.c_int, [C.POINTER(abi.SaoCtu), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
@@ -171,8 +172,10 @@ class Context:
         self._ck(self.lib.vtmgpu_import_rows(self.h, slot, comp, y0, nrows, C.c_void_p(dev_ptr)), "import_rows")
 
     # ---- side information --------------------------------------------------------------------------------
-    def set_deblock(self, slot, params):
-        self._ck(self.lib.vtmgpu_set_deblock(self.h, slot, C.byref(params) if params is not None else None), "set_deblock")
+    def set_deblock(self, slot, params, sync=True):
+        """sync=False: no staging copy, the record arrays (page-locked) are read asynchronously until the next sync()."""
+        fn = self.lib.vtmgpu_set_deblock if sync else self.lib.vtmgpu_set_deblock_async
+        self._ck(fn(self.h, slot, C.byref(params) if params is not None else None), "set_deblock")
 
     def set_sao(self, slot, ctus):
         """ctus: reconstructed (abi.SaoCtu * n) array, or None to switch the stage off."""
