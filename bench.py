@@ -298,7 +298,7 @@ def main():
             pass
 
     # ---- end to end through the C ABI with host buffers -------------------------------------------------------------
-    NCTX, CH = 4, 4                                 # 4 contexts (streams) x 4 slots: copies of one chunk overlap kernels of another
+    NCTX, CH = int(os.environ.get("VTMGPU_E2E_NCTX", "8")), int(os.environ.get("VTMGPU_E2E_CH", "1"))   # contexts (streams) x slots: copies of one chunk overlap kernels of another
     ectx = [gpu.Context(seq, capacity=CH, device=local) for _ in range(NCTX)]
     pin_in = [[torch.from_numpy(p.copy()).pin_memory() for p in c.pre] for c in caps]
     pin_out = [[[torch.empty_like(t).pin_memory() for t in pin_in[0]] for _ in range(CH)] for _ in range(NCTX)]
@@ -324,7 +324,10 @@ def main():
     h2d = sum(t.numel() * 2 for t in pin_in[0]) + sum(a.nbytes for a in caps[0].dbf_luma) + sum(a.nbytes for a in caps[0].dbf_chroma)
     d2h = sum(t.numel() * 2 for t in pin_in[0])
 
+    issue = [0.0]
+
     def e2e_step():
+        t_issue = time.perf_counter()
         for base in range(0, B, CH):
             cx = ectx[(base // CH) % NCTX]
             if base >= NCTX * CH:
@@ -338,10 +341,12 @@ def main():
             cx.filter(0, CH, sync=False)
             for j in range(CH):
                 cx.download(j, [t.numpy() for t in pin_out[(base // CH) % NCTX][j]], sync=False)
+        issue[0] += time.perf_counter() - t_issue
         for cx in ectx:
             cx.sync()
 
     e2e_step()
+    issue[0] = 0.0
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
@@ -365,7 +370,8 @@ def main():
                        "activity": activity_summary(caps), "e2e_equals_resident": bool(ok)},
             "clocks": clocks, "roofline": roofline, "gpu_launches": int(launches),
             "e2e": {"value": round(e2e_val, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": int(h2d * B), "d2h_bytes_per_step": int(d2h * B),
-                    "steps": args.e2e_steps, "gpu_launches": int(launches_total - launches)}}
+                    "steps": args.e2e_steps, "gpu_launches": int(launches_total - launches),
+                    "host_issue_ms_per_step": round(issue[0] * 1e3 / args.e2e_steps, 2), "ms_per_step": round(e2e_s * 1e3, 2)}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         res = cpu_reference_run()
         if res:

@@ -110,6 +110,29 @@ def test_full_size_4k_properties():
     _eq(a, pyoracle.filter_capture(cap)["final"], "4K forced-on vs oracle")
 
 
+def test_async_side_info_and_caller_stream():
+    """vtmgpu_set_deblock_async (no staging copy) and vtmgpu_set_stream (all work enqueued on the caller's stream) give
+    the same picture as the synchronous path."""
+    import torch
+    cap = synth.make_picture(640, 384, seed=21, density=0.8)
+    want = pyoracle.filter_capture(cap)["final"]
+    ctx = gpu.Context(cap.seq)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream, True)
+    ctx.upload(0, cap.pre, sync=False)
+    dp = cap.deblock_params()                       # stays alive until the sync below
+    ctx.set_deblock(0, dp, sync=False)
+    ctus = cap.sao_ctus()
+    gpu.sao_reconstruct(ctus, cap.width_in_ctus, cap.ncomp, cap.sao_scale[0], cap.sao_scale[1])
+    ctx.set_sao(0, ctus)
+    ctx.set_alf(0, cap.alf_params())
+    ctx.filter(0, 1)                                # only enqueues in this mode
+    stream.synchronize()
+    _eq(ctx.download(0), want, "caller-stream chain")
+    ctx.set_stream(None, False)
+    ctx.close()
+
+
 def test_bad_arguments_fail_loudly():
     cap = synth.make_picture(256, 128, seed=1)
     ctx = gpu.Context(cap.seq)

@@ -3,9 +3,10 @@
 // reference's unmodified headers (class layouts stay identical, DecLib embeds the objects by value) and linked
 // INSTEAD of the reference's LoopFilter.cpp / SampleAdaptiveOffset.cpp / AdaptiveLoopFilter.cpp (+ the ALF SIMD stubs).
 //
-//   loopFilterPic : derive segment records on the host -> upload planes -> device deblocking
-//   SAOProcess    : reconstruct SAO params -> (deferred, fused into the ALF pass when the SPS enables ALF)
-//   ALFProcess    : flatten slice/APS/CTU data -> device SAO+ALF+CC-ALF -> download planes
+//   loopFilterPic : derive segment records on the host -> upload planes (+ records); the device pass is deferred while a
+//                   later stage follows (nothing reads the reconstruction between the three calls of executeLoopFilters)
+//   SAOProcess    : reconstruct SAO params; deferred when the SPS enables ALF, else deblocking+SAO kernel -> download
+//   ALFProcess    : flatten slice/APS/CTU data -> vtmgpu_filter = (deblocking + SAO) kernel, (ALF + CC-ALF) kernel -> download
 //
 // No sample is filtered on the CPU here.  If libvtmgpu cannot be loaded or any call fails the shim THROWs
 // (reference error convention, TypeDef.h:1152) -- there is no fallback.
@@ -57,6 +58,8 @@ struct GpuApi
   decltype(&vtmgpu_sao) sao = nullptr;
   decltype(&vtmgpu_alf) alf = nullptr;
   decltype(&vtmgpu_sao_alf) sao_alf = nullptr;
+  decltype(&vtmgpu_deblock_sao) deblock_sao = nullptr;
+  decltype(&vtmgpu_filter) filter = nullptr;
 
   void load()
   {
@@ -66,7 +69,7 @@ struct GpuApi
     if (!so) THROW("vtmgpu shim: cannot load libvtmgpu.so (" << dlerror() << ") -- no CPU fallback");
 #define SYM(n) n = reinterpret_cast<decltype(n)>(dlsym(so, "vtmgpu_" #n)); if (!n) THROW("vtmgpu shim: missing symbol vtmgpu_" #n)
     SYM(abi_version); SYM(last_error); SYM(create); SYM(destroy); SYM(upload); SYM(download); SYM(set_deblock); SYM(set_sao);
-    SYM(set_alf); SYM(sao_reconstruct); SYM(deblock); SYM(sao); SYM(alf); SYM(sao_alf);
+    SYM(set_alf); SYM(sao_reconstruct); SYM(deblock); SYM(sao); SYM(alf); SYM(sao_alf); SYM(deblock_sao); SYM(filter);
 #undef SYM
     if (abi_version() != VTMGPU_ABI_VERSION) THROW("vtmgpu shim: ABI version mismatch");
   }
@@ -77,7 +80,7 @@ struct Shim
   GpuApi api;
   vtmgpu_ctx* ctx = nullptr;
   vtmgpu_seq_params seq{};
-  bool useRef = false, staged = false, saoPending = false;
+  bool useRef = false, staged = false, saoPending = false, dbfPending = false;
   std::string captureDir;
   int picCount = 0;
   // per-picture
@@ -230,7 +233,7 @@ void LoopFilter::loopFilterPic(CodingStructure& cs)
 {
   Shim& s = shim();
   s.ensureCtx(cs);
-  s.saoPending = false;
+  s.saoPending = s.dbfPending = false;
   s.lumaPixels += (long long)cs.pcv->lumaWidth * cs.pcv->lumaHeight;
   if (!s.useRef || !s.captureDir.empty() || !s.timing)   // the reference backend derives its own parameters; skip ours when only timing it
   {
@@ -259,8 +262,12 @@ void LoopFilter::loopFilterPic(CodingStructure& cs)
     s.check(s.api.set_deblock(s.ctx, 0, &p), "set_deblock");
     s.check(s.api.set_sao(s.ctx, 0, nullptr), "set_sao");
     s.check(s.api.set_alf(s.ctx, 0, nullptr), "set_alf");
-    s.check(s.api.deblock(s.ctx, 0, 1), "deblock");
-    if (s.staged || lastStage(cs, 0)) s.download(cs);
+    s.dbfPending = !(s.staged || lastStage(cs, 0));
+    if (!s.dbfPending)
+    {
+      s.check(s.api.deblock(s.ctx, 0, 1), "deblock");
+      s.download(cs);
+    }
   }
   s.toc(s.stageSec[0]);
   s.capturePlanes(cs, "dbf");
@@ -307,7 +314,9 @@ void SampleAdaptiveOffset::SAOProcess(CodingStructure& cs, SAOBlkParam* saoBlkPa
     s.check(s.api.set_sao(s.ctx, 0, &p), "set_sao");
     if (s.staged || lastStage(cs, 1))
     {
-      s.check(s.api.sao(s.ctx, 0, 1), "sao");
+      if (s.dbfPending) s.check(s.api.deblock_sao(s.ctx, 0, 1), "deblock_sao");     // one kernel: deblocking with the SAO epilogue
+      else              s.check(s.api.sao(s.ctx, 0, 1), "sao");
+      s.dbfPending = false;
       s.download(cs);
     }
     else
@@ -384,9 +393,10 @@ void AdaptiveLoopFilter::ALFProcess(CodingStructure& cs)
   else
   {
     s.check(s.api.set_alf(s.ctx, 0, p), "set_alf");
-    if (s.saoPending) s.check(s.api.sao_alf(s.ctx, 0, 1), "sao_alf");
-    else              s.check(s.api.alf(s.ctx, 0, 1), "alf");
-    s.saoPending = false;
+    if (s.dbfPending)      s.check(s.api.filter(s.ctx, 0, 1), "filter");        // whole chain: two kernels, one synchronisation
+    else if (s.saoPending) s.check(s.api.sao_alf(s.ctx, 0, 1), "sao_alf");
+    else                   s.check(s.api.alf(s.ctx, 0, 1), "alf");
+    s.saoPending = s.dbfPending = false;
     s.download(cs);
   }
   s.toc(s.stageSec[2]);
