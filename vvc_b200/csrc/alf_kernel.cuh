@@ -33,8 +33,8 @@ namespace vtmgpu
 {
 
 constexpr int SA_T = 64;                    // luma tile width
-constexpr int SA_TH = 32;                   // luma tile height
-constexpr int SA_THLOG = 5;
+constexpr int SA_TH = 64;                   // luma tile height
+constexpr int SA_THLOG = 6;
 constexpr int SA_THREADS = (SA_T / 4) * (SA_TH / 4);   // 128: one thread per 4x4 luma block; small CTAs (4 per SM) decorrelate the phases
 constexpr int SA_HX = 8, SA_HY = 4;         // halo loaded around a tile (x: one aligned group of 8)
 constexpr int SA_W = SA_T + 2 * SA_HX;      // 80
@@ -441,7 +441,7 @@ __device__ __forceinline__ void saPrefetch(unsigned char* smraw, const SaLayout&
 // Persistent kernel: gridDim.x CTAs walk the tiles of slots [firstSlot, firstSlot + numSlots) round robin; while a CTA
 // filters tile i, the TMA loads of tile i+1 are in flight (two stages).  maps = tensor maps of the source buffer of the
 // first slot: [slot][3 buffers][3 planes].
-__global__ void __launch_bounds__(SA_THREADS, 4) k_alf(const SlotDev* __restrict__ slots, const CUtensorMap* __restrict__ tmaps, int firstSlot, int numSlots,
+__global__ void __launch_bounds__(SA_THREADS, 2) k_alf(const SlotDev* __restrict__ slots, const CUtensorMap* __restrict__ tmaps, int firstSlot, int numSlots,
                                                            int srcBuf, int dstBuf, Geom g, int tilesX, int tilesY, int ty0, SaStep step)
 {
   extern __shared__ __align__(128) unsigned char smraw[];

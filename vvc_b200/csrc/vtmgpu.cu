@@ -816,7 +816,7 @@ int launchAlf(vtmgpu_ctx* c, int first, int count)
   return forRuns(c, first, count, [&](int s, int n, int src) {
     const int dst = src == 1 ? 2 : 1;
     // persistent CTAs: four per SM (register limited), each walks the tiles round robin with double-buffered TMA loads
-    const int grid = std::min(tilesX * tilesY * n, 4 * c->numSms);
+    const int grid = std::min(tilesX * tilesY * n, 2 * c->numSms);
     SaStep st;
     st.dx = grid % tilesX;
     st.dy = (grid / tilesX) % tilesY;

@@ -7,6 +7,11 @@
 #include "vtm_flatten.h"
 
 #include <algorithm>
+#include <exception>
+#include <thread>
+#include <vector>
+
+#include <algorithm>
 #include <cstring>
 
 #include "CodingStructure.h"
@@ -90,7 +95,9 @@ private:
   const PreCalcValues& m_pcv;
   FlatDeblock&         m_out;
   CtuState             m_st;
+  const Slice*         m_ctuSlice = nullptr;   // slice of the first CU of the CTU in flight (what the reference leaves in cs.slice)
   int  m_sx, m_sy, m_ctuX = 0, m_ctuY = 0, m_dir = VER;
+  void rows(int first, int step);
   bool m_left = false, m_top = false, m_internal = false;
 
   int uidx(int x, int y) const { return ((y & (int)m_pcv.maxCUHeightMask) >> 2) * kU + ((x & (int)m_pcv.maxCUWidthMask) >> 2); }
@@ -131,9 +138,35 @@ void Deriver::run()
   m_out.chroma[HOR].assign(chroma ? (size_t)((H + gy - 1) / gy) * (W / 4) : 0, 0);
 
   // two passes over the picture as in loopFilterPic (LoopFilter.cpp:165-240).  No record depends on samples
-  // (LADF is rejected above), so both passes can be derived before any filtering happens.
+  // (LADF is rejected above), so both passes can be derived before any filtering happens -- and CTUs are independent
+  // of each other: all state is CTU-local (LoopFilter.cpp:169-175), every record lies inside its own CTU and the
+  // coding structure is only read.  The CTU rows are therefore spread over a few host threads
+  // (VTMGPU_SHIM_THREADS, default min(8, cores); SURVEY.md 8f n1 "parallel host").
+  int nThreads = 1;
+  if (const char* e = getenv("VTMGPU_SHIM_THREADS")) nThreads = atoi(e);
+  else nThreads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+  nThreads = std::max(1, std::min(nThreads, (int)m_pcv.heightInCtus));
+  if (nThreads == 1) rows(0, 1);
+  else
+  {
+    std::vector<std::thread> pool;
+    std::vector<std::exception_ptr> err(nThreads);
+    for (int t = 0; t < nThreads; t++)
+      pool.emplace_back([this, t, nThreads, &err] {
+        try { Deriver d(m_cs, m_out); d.rows(t, nThreads); }
+        catch (...) { err[t] = std::current_exception(); }
+      });
+    for (auto& th : pool) th.join();
+    for (auto& e : err) if (e) std::rethrow_exception(e);
+  }
+  // side effect of the reference's CTU loop (LoopFilter.cpp:179,218): cs.slice ends up as the slice of the last CTU
+  m_cs.slice = m_cs.getCU(Position((m_pcv.widthInCtus - 1) << m_pcv.maxCUWidthLog2, (m_pcv.heightInCtus - 1) << m_pcv.maxCUHeightLog2), CH_L)->slice;
+}
+
+void Deriver::rows(int first, int step)
+{
   for (m_dir = VER; m_dir <= HOR; m_dir++)
-    for (int y = 0; y < (int)m_pcv.heightInCtus; y++)
+    for (int y = first; y < (int)m_pcv.heightInCtus; y += step)
       for (int x = 0; x < (int)m_pcv.widthInCtus; x++)
       {
         const UnitArea ctuArea(m_pcv.chrFormat, Area(x << m_pcv.maxCUWidthLog2, y << m_pcv.maxCUHeightLog2, m_pcv.maxCUWidth, m_pcv.maxCUWidth));
@@ -146,7 +179,7 @@ void Deriver::run()
 void Deriver::ctuPass(const UnitArea& ctuArea)
 {
   m_st.clear();
-  m_cs.slice = m_cs.getCU(ctuArea.lumaPos(), CH_L)->slice;   // side effect kept (LoopFilter.cpp:179,218)
+  m_ctuSlice = m_cs.getCU(ctuArea.lumaPos(), CH_L)->slice;    // the reference assigns this to cs.slice (LoopFilter.cpp:179,218); see run()
   for (auto& cu : m_cs.traverseCUs(CS::getArea(m_cs, ctuArea, CH_L), CH_L)) deriveCU(cu);
   if (CS::isDualITree(m_cs))
   {
@@ -322,7 +355,7 @@ void Deriver::emitLuma(const CodingUnit& cu, int edge)
   const PPS& pps = *cu.cs->pps;
   const Slice& slice = *cu.slice;
   const int bd = sps.getBitDepth(CHANNEL_TYPE_LUMA);
-  const ClpRng& clp = cu.cs->slice->clpRng(COMPONENT_Y);
+  const ClpRng& clp = m_ctuSlice->clpRng(COMPONENT_Y);
   CHECK(clp.min != 0 || clp.max != (1 << bd) - 1, "vtmgpu shim: non-default luma clipping range");
   const int n = m_dir == VER ? la.height / 4 : la.width / 4;
   const int tcOff = slice.getDeblockingFilterTcOffsetDiv2() * 2, betaOff = slice.getDeblockingFilterBetaOffsetDiv2() * 2;
@@ -398,7 +431,7 @@ void Deriver::emitChroma(const CodingUnit& cu, int edge)
     {
       if (!(bsC[c] == 2 || (large && bsC[c] == 1))) continue;
       const ComponentID comp = ComponentID(c + 1);
-      const ClpRng& clp = cu.cs->slice->clpRng(comp);
+      const ClpRng& clp = m_ctuSlice->clpRng(comp);
       CHECK(clp.min != 0 || clp.max != (1 << bd) - 1, "vtmgpu shim: non-default chroma clipping range");
       const int shP = cuP.Y().valid() ? 0 : getComponentScaleX(COMPONENT_Cb, cuP.firstPU->chromaFormat);
       const int svP = cuP.Y().valid() ? 0 : getComponentScaleY(COMPONENT_Cb, cuP.firstPU->chromaFormat);
