@@ -572,8 +572,19 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
 
     // ---- epilogue: SAO of the own region straight into the output plane (a plain 128-bit copy where SAO is off) -------
     if (sx_ < w && sy_ < h)
-      saoStrip(dst.p + (size_t)sy_ * dst.pitch + sx_, dst.pitch, &sm[(DBF_HALO + 4 * rb) * DBF_PITCH + DBF_HALO + 8 * gcol], DBF_PITCH, min(4, h - sy_), sx_, sy_,
-               pq, w, h, cwLog | chLog << 8 | (comp ? g.bdC : g.bdL) << 16);
+    {
+      const pel* a = &sm[(DBF_HALO + 4 * rb) * DBF_PITCH + DBF_HALO + 8 * gcol];
+      pel* o = dst.p + (size_t)sy_ * dst.pitch + sx_;
+      const int nrows = min(4, h - sy_);
+      if ((pq.x & 0xff) == 0)
+      {
+        // SAO off for this CTU (the common case): 128-bit copy of the strip
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (k < nrows) *reinterpret_cast<uint4*>(o + (size_t)k * dst.pitch) = *reinterpret_cast<const uint4*>(a + k * DBF_PITCH);
+      }
+      else saoStrip(o, dst.pitch, a, DBF_PITCH, nrows, sx_, sy_, pq, w, h, cwLog | chLog << 8 | (comp ? g.bdC : g.bdL) << 16);
+    }
     if (tid == 0) qcount[0] = qcount[1] = 0;
     __syncthreads();                                         // the stage is free for the load after next
     slot = nslot; item = nitem; T = Tn;
