@@ -255,6 +255,10 @@ int vtmgpu_download_rows(vtmgpu_ctx* ctx, int slot, int16_t* const plane[3], con
 /* rows [y0, y0+nrows) (in samples of component comp) of the slot's current state <-> dense device memory (width * nrows int16) */
 int vtmgpu_export_rows(vtmgpu_ctx* ctx, int slot, int comp, int y0, int nrows, void* dev_dst);
 int vtmgpu_import_rows(vtmgpu_ctx* ctx, int slot, int comp, int y0, int nrows, const void* dev_src);
+/* the same for all components at once: nrows rows of every plane starting at row y[comp], packed luma, Cb, Cr
+ * (one buffer = one message per band border and direction) */
+int vtmgpu_export_halo(vtmgpu_ctx* ctx, int slot, const int y[3], int nrows, void* dev_dst);
+int vtmgpu_import_halo(vtmgpu_ctx* ctx, int slot, const int y[3], int nrows, const void* dev_src);
 
 /* replay/benchmark support: enqueue the whole chain on the ctx stream without synchronising; timing by
  * CUDA events recorded on that same stream */

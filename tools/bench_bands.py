@@ -56,28 +56,15 @@ def main():
     shifts = [0] + ([sy, sy] if cap.ncomp == 3 else [])
     widths = [cap.width] + [cap.width >> sx] * (cap.ncomp - 1)
     dev = torch.device("cuda", local)
-    plan = bands.halo_plan(bnds, rank, shifts)
-
-    # everything of one iteration on torch's current stream: kernels, row copies and the NCCL send/recv order on the device
-    bufs = {}
-
-    def buffer(n):
-        k = (n, len([b for b in bufs if b[0] == n and b in used]))
-        used.add(k)
-        if k not in bufs:
-            bufs[k] = torch.empty(n, dtype=torch.int16, device=dev)
-        return bufs[k]
-
-    used = set()
+    plan = bands.halo_plan_packed(bnds, rank, shifts)
+    bufs = [torch.empty(sum(widths) * bands.HALO, dtype=torch.int16, device=dev) for _ in plan]
+    # everything of one iteration on torch's current stream: kernels, halo copies and the NCCL send/recv order on the device
     ctx.set_stream(torch.cuda.current_stream().cuda_stream, True)
 
     def step():
-        used.clear()
         ctx.rewind(0, 1)
         ctx.deblock_sao(0, 1)
-        bands.exchange(plan, lambda comp, row, n, buf: ctx.export_rows(0, comp, row, n, buf.data_ptr()),
-                       lambda comp, row, n, buf: ctx.import_rows(0, comp, row, n, buf.data_ptr()),
-                       dist, lambda comp: widths[comp], buffer, host_sync=False)
+        bands.exchange_packed(plan, ctx, dist, bufs, host_sync=False)
         ctx.alf(0, 1)
 
     for _ in range(args.warmup):

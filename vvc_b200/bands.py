@@ -53,6 +53,40 @@ def halo_plan(bands, rank, shifts):
     return plan
 
 
+def halo_plan_packed(bands, rank, shifts):
+    """The same exchange with ONE message per neighbour and direction: list of (peer, 'send'|'recv', [first row per component])."""
+    y0, y1 = bands[rank]
+    plan = []
+    if rank > 0:
+        plan.append((rank - 1, "send", [y0 >> s for s in shifts]))
+        plan.append((rank - 1, "recv", [(y0 >> s) - HALO for s in shifts]))
+    if rank + 1 < len(bands):
+        plan.append((rank + 1, "send", [(y1 >> s) - HALO for s in shifts]))
+        plan.append((rank + 1, "recv", [y1 >> s for s in shifts]))
+    return plan
+
+
+def exchange_packed(plan, ctx, dist, buffers, host_sync=True):
+    """Packed halo exchange on a gpu.Context: buffers[i] = device int16 tensor of (sum of plane widths) * HALO samples for
+    plan entry i (allocated once by the caller and reused)."""
+    ops, recvs = [], []
+    for (peer, kind, rows), buf in zip(plan, buffers):
+        if kind == "send":
+            ctx.export_halo(0, rows, HALO, buf.data_ptr())
+            ops.append(dist.P2POp(dist.isend, _wire(buf), peer))
+        else:
+            ops.append(dist.P2POp(dist.irecv, _wire(buf), peer))
+            recvs.append((rows, buf))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        if host_sync:
+            import torch
+            torch.cuda.synchronize()
+    for rows, buf in recvs:
+        ctx.import_halo(0, rows, HALO, buf.data_ptr())
+
+
 def _wire(buf):
     """NCCL has no int16: samples travel as bytes (same memory)."""
     import torch
@@ -105,10 +139,8 @@ def filter_picture_in_bands(cap, ctx, rank, world, dist, out=None):
     ctx.deblock_sao(0, 1)                      # one kernel: the SAO of the band's border rows sees the deblocked rows across the border
     dev = torch.device("cuda", ctx.device)
     widths = [cap.width] + [cap.width >> sx] * (cap.ncomp - 1)
-    exchange(halo_plan(bands, rank, shifts),
-             lambda comp, row, n, buf: ctx.export_rows(0, comp, row, n, buf.data_ptr()),
-             lambda comp, row, n, buf: ctx.import_rows(0, comp, row, n, buf.data_ptr()),
-             dist, lambda comp: widths[comp], lambda n: torch.empty(n, dtype=torch.int16, device=dev))
+    plan = halo_plan_packed(bands, rank, shifts)
+    exchange_packed(plan, ctx, dist, [torch.empty(sum(widths) * HALO, dtype=torch.int16, device=dev) for _ in plan])
     ctx.alf(0, 1)
     if out is None:
         out = [np.zeros_like(p) for p in cap.pre]

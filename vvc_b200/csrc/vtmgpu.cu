@@ -473,6 +473,34 @@ extern "C" int vtmgpu_import_rows(vtmgpu_ctx* c, int slot, int comp, int y0, int
   return c->asyncStages ? 0 : c->cuda(cudaStreamSynchronize(c->stream), "import_rows");
 }
 
+// all components at once: nrows rows of every plane, starting at row y[comp] of component comp, packed one plane after the other
+// (luma, Cb, Cr; each width x nrows int16) -- one buffer and one message per band border and direction
+extern "C" int vtmgpu_export_halo(vtmgpu_ctx* c, int slot, const int y[3], int nrows, void* dev_dst)
+{
+  if (!c) return -1;
+  int16_t* d = static_cast<int16_t*>(dev_dst);
+  for (int k = 0; k < c->g.ncomp; k++)
+  {
+    const int w = c->slotsPinned[slot].buf[0][k].w;
+    if (copyRows(c, slot, k, c->cur[slot], y[k], nrows, d, w, cudaMemcpyDeviceToDevice, false, "export_halo")) return -1;
+    d += (size_t)w * nrows;
+  }
+  return c->asyncStages ? 0 : c->cuda(cudaStreamSynchronize(c->stream), "export_halo");
+}
+
+extern "C" int vtmgpu_import_halo(vtmgpu_ctx* c, int slot, const int y[3], int nrows, const void* dev_src)
+{
+  if (!c) return -1;
+  int16_t* d = static_cast<int16_t*>(const_cast<void*>(dev_src));
+  for (int k = 0; k < c->g.ncomp; k++)
+  {
+    const int w = c->slotsPinned[slot].buf[0][k].w;
+    if (copyRows(c, slot, k, c->cur[slot], y[k], nrows, d, w, cudaMemcpyDeviceToDevice, true, "import_halo")) return -1;
+    d += (size_t)w * nrows;
+  }
+  return c->asyncStages ? 0 : c->cuda(cudaStreamSynchronize(c->stream), "import_halo");
+}
+
 extern "C" int vtmgpu_rewind(vtmgpu_ctx* c, int first, int count)
 {
   if (!c) return -1;

@@ -70,6 +70,8 @@ def load_library(path=None):
         "vtmgpu_upload_rows": (C.c_int, planes_in + [C.c_int, C.c_int]), "vtmgpu_download_rows": (C.c_int, planes_in + [C.c_int, C.c_int]),
         "vtmgpu_export_rows": (C.c_int, [ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
         "vtmgpu_import_rows": (C.c_int, [ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+        "vtmgpu_export_halo": (C.c_int, [ctx, C.c_int, C.POINTER(C.c_int * 3), C.c_int, C.c_void_p]),
+        "vtmgpu_import_halo": (C.c_int, [ctx, C.c_int, C.POINTER(C.c_int * 3), C.c_int, C.c_void_p]),
     }
     for name, (res, args) in proto.items():
         try:
@@ -170,6 +172,15 @@ class Context:
 
     def import_rows(self, slot, comp, y0, nrows, dev_ptr):
         self._ck(self.lib.vtmgpu_import_rows(self.h, slot, comp, y0, nrows, C.c_void_p(dev_ptr)), "import_rows")
+
+    def export_halo(self, slot, rows, nrows, dev_ptr):
+        """rows = first row per component; all planes packed into one device buffer."""
+        y = (C.c_int * 3)(*(list(rows) + [0, 0])[:3])
+        self._ck(self.lib.vtmgpu_export_halo(self.h, slot, C.byref(y), nrows, C.c_void_p(dev_ptr)), "export_halo")
+
+    def import_halo(self, slot, rows, nrows, dev_ptr):
+        y = (C.c_int * 3)(*(list(rows) + [0, 0])[:3])
+        self._ck(self.lib.vtmgpu_import_halo(self.h, slot, C.byref(y), nrows, C.c_void_p(dev_ptr)), "import_halo")
 
     # ---- side information --------------------------------------------------------------------------------
     def set_deblock(self, slot, params, sync=True):
