@@ -20,6 +20,8 @@
 #include <dlfcn.h>
 
 #include <chrono>
+#include <exception>
+#include <thread>
 
 #include <cstdio>
 #include <cstdlib>
@@ -235,12 +237,19 @@ void LoopFilter::loopFilterPic(CodingStructure& cs)
   s.ensureCtx(cs);
   s.saoPending = s.dbfPending = false;
   s.lumaPixels += (long long)cs.pcv->lumaWidth * cs.pcv->lumaHeight;
+  // the upload of the reconstruction (a staged copy out of pageable decoder memory) runs beside the host derivation
+  std::thread uploader;
+  std::exception_ptr uploadError;
+  if (!s.useRef) uploader = std::thread([&] { try { s.upload(cs); } catch (...) { uploadError = std::current_exception(); } });
   if (!s.useRef || !s.captureDir.empty() || !s.timing)   // the reference backend derives its own parameters; skip ours when only timing it
   {
     s.tic();
-    deriveDeblockRecords(cs, s.dbf);
+    try { deriveDeblockRecords(cs, s.dbf); }
+    catch (...) { if (uploader.joinable()) uploader.join(); throw; }
     s.toc(s.deriveSec);
   }
+  if (uploader.joinable()) uploader.join();
+  if (uploadError) std::rethrow_exception(uploadError);
   if (!s.captureDir.empty())
   {
     s.cap.clear();
@@ -258,7 +267,6 @@ void LoopFilter::loopFilterPic(CodingStructure& cs)
   else
   {
     const vtmgpu_deblock_params p = s.dbf.view();
-    s.upload(cs);
     s.check(s.api.set_deblock(s.ctx, 0, &p), "set_deblock");
     s.check(s.api.set_sao(s.ctx, 0, nullptr), "set_sao");
     s.check(s.api.set_alf(s.ctx, 0, nullptr), "set_alf");
