@@ -150,7 +150,6 @@ __device__ __forceinline__ void alfClassify(int sumV, int sumH, int sumD0, int s
   tIdx = (0x31322010 >> (4 * (mainDir * 2 + (secDir >> 1)))) & 0xf;              // transposeTable = {0,1,0,2,2,3,1,3}
 }
 
-typedef uint2 (*CellRows)[SA_CELLP];
 
 // one 4x4 luma block, any row position: classification incl. the virtual-boundary rules and the 7x7 filter with row clamping
 __device__ __noinline__ void alfLumaBlockGeneric(const uint2 (*cell)[SA_CELLP], const pel* c0, pel* out, int pitchOut, int bi, int bj, int by,
