@@ -52,6 +52,13 @@ SYNTH = [
     (384, 256, 1, 12, 128, 0.8),      # 12-bit
     (384, 320, 1, 10, 64, 0.8),       # CTU 64
     (1920, 1080, 1, 10, 128, 0.5),
+    # degenerate geometries: pictures smaller than one tile / one TMA box, single rows of units
+    (8, 8, 1, 10, 128, 1.0),
+    (16, 8, 1, 10, 128, 1.0),
+    (72, 40, 1, 10, 128, 1.0),
+    (24, 136, 3, 10, 128, 1.0),
+    (64, 64, 2, 10, 64, 1.0),
+    (200, 8, 1, 10, 128, 1.0),
 ]
 
 
