@@ -221,14 +221,16 @@ __device__ __forceinline__ void alfOwnCells(uint2 (*cell)[SA_CELLP], const pel* 
 }
 
 // 7x7 diamond on one 4x4 block, two pixels per register.  e = pre-expanded {coefficient, clip} entry of the block's
-// (filter set, class, transpose).  clamp(n - cur, -c, c) + c  ==  max(min(n + (c - cur), 2c), 0)  is ONE instruction;
-// the excess sum(coef * 2c) is folded into e->bias together with the rounding offset 64 (filterBlk :1249-1297).
+// (filter set, class, transpose).  clamp(n - cur, -c, c) + c  ==  max(min(n + (c - cur), 2c), 0)  is ONE
+// instruction; the excess sum(coef * 2c) is folded into e->bias together with the rounding offset 64 (filterBlk :1249-1297).
 //
-// VB = 0: block away from the virtual boundary.  VB = 1 / 2: the block directly above / below the boundary (CTU rows
-// vbPos-4..vbPos-1 / vbPos..vbPos+3): tap rows are clamped to the rows on the block's side of the boundary
-// (filterBlk :1227-1247: row offset min(|dy|, lim) with lim = 3 - orow above, orow below) and the row adjacent to the
-// boundary is rounded with >> 10 (:1288-1295).  All of it folds into compile-time register indices.
-template <int VB> __device__ __forceinline__ void alfLumaBlockFast(const pel* c0, pel* out, int pitchOut, const AlfLumaEntry* __restrict__ e, uint32_t maxvP)
+// The four output rows are a REAL loop (not unrolled): both kernels of the chain are bound by instruction fetch (the SM
+// instruction cache misses into the GPC-level cache, profiles/: gcc instruction requests at 75 % of peak with the fully
+// unrolled version), so the body is kept small (~200 instructions) and each row re-reads its 7 input rows from shared
+// memory (68 LDS.64 per block instead of 30).  With the rows addressed at run time the virtual-boundary clamping of
+// filterBlk :1227-1247 (row offset min(|dy|, lim), >> 10 on the row next to the boundary) needs no separate code:
+// vb = 0 away from the boundary, 1 / 2 for the block directly above / below it.
+__device__ __forceinline__ void alfLumaBlockFast(const pel* c0, pel* out, int pitchOut, const AlfLumaEntry* __restrict__ e, uint32_t maxvP, int vb)
 {
   uint32_t coefB[12], clipP1[12], clip2[12];
   {
@@ -243,49 +245,61 @@ template <int VB> __device__ __forceinline__ void alfLumaBlockFast(const pel* c0
     }
   }
   const int bias = __ldg(&e->bias);
-  // w[ir][j] = samples (4bj - 4 + 2j, +1) of input row ir - 3 ; o[ir][j] = the pair starting one sample later
-  uint32_t w[10][6], o[10][5];
-#pragma unroll
-  for (int ir = 0; ir < 10; ir++)
-  {
-    const uint2* rp = reinterpret_cast<const uint2*>(c0 + (ir - 3) * SA_P - 4);
-    const uint2 q0 = rp[0], q1 = rp[1], q2 = rp[2];
-    w[ir][0] = q0.x; w[ir][1] = q0.y; w[ir][2] = q1.x; w[ir][3] = q1.y; w[ir][4] = q2.x; w[ir][5] = q2.y;
-#pragma unroll
-    for (int j = 0; j < 5; j++) o[ir][j] = mid16(w[ir][j], w[ir][j + 1]);
-  }
-#define ALF_PAIR(IR, C) ((((C) & 1) != 0) ? o[IR][((C) + 3) >> 1] : w[IR][((C) + 4) >> 1])
-#define ALF_ROW(DY) ((DY) < lim ? (DY) : lim)
-#define ALF_TAP(K, DX, DY)                                                                                              \
-  {                                                                                                                     \
-    const uint32_t cb = __vadd2(clipP1[K], ncur);                                                                       \
-    const uint32_t s = addClamp0(ALF_PAIR(orow + 3 + ALF_ROW(DY), 2 * px + (DX)), cb, clip2[K]) +                       \
-                       addClamp0(ALF_PAIR(orow + 3 - ALF_ROW(DY), 2 * px - (DX)), cb, clip2[K]);                        \
-    acc0 = __dp2a_lo((int)s, (int)coefB[K], acc0);                                                                      \
-    acc1 = __dp2a_hi((int)s, (int)coefB[K], acc1);                                                                      \
-  }
-#pragma unroll
+#pragma unroll 1
   for (int orow = 0; orow < 4; orow++)
   {
-    const int lim = VB == 0 ? 3 : (VB == 1 ? 3 - orow : orow);                 // rows available on this side of the virtual boundary
-    const int sh = (VB == 1 && orow == 3) || (VB == 2 && orow == 0) ? 10 : 7;
+    const int lim = vb == 0 ? 3 : (vb == 1 ? 3 - orow : orow);                 // rows available on this side of the virtual boundary
+    const int sh = (vb == 1 && orow == 3) || (vb == 2 && orow == 0) ? 10 : 7;
+    const int o1 = min(1, lim) * SA_P, o2 = min(2, lim) * SA_P, o3 = lim * SA_P;
+    const pel* rc = c0 + orow * SA_P;
+    // w*[j] = samples (4bj - 4 + 2j, +1) of a row ; o*[j] = the pair starting one sample later
+    uint32_t wc[6], oc[5], wp1[6], op1[5], wm1[6], om1[5], wp2[6], op2[5], wm2[6], om2[5], wp3[2], wm3[2];
+#define ALF_LOADROW(W, O, PTR)                                                                                          \
+    {                                                                                                                   \
+      const uint2* rp_ = reinterpret_cast<const uint2*>((PTR) - 4);                                                     \
+      const uint2 q0 = rp_[0], q1 = rp_[1], q2 = rp_[2];                                                                \
+      W[0] = q0.x; W[1] = q0.y; W[2] = q1.x; W[3] = q1.y; W[4] = q2.x; W[5] = q2.y;                                     \
+      _Pragma("unroll") for (int j = 0; j < 5; j++) O[j] = mid16(W[j], W[j + 1]);                                       \
+    }
+    ALF_LOADROW(wc, oc, rc)
+    ALF_LOADROW(wp1, op1, rc + o1) ALF_LOADROW(wm1, om1, rc - o1)
+    ALF_LOADROW(wp2, op2, rc + o2) ALF_LOADROW(wm2, om2, rc - o2)
+    { const uint2 q = *reinterpret_cast<const uint2*>(rc + o3); wp3[0] = q.x; wp3[1] = q.y; }
+    { const uint2 q = *reinterpret_cast<const uint2*>(rc - o3); wm3[0] = q.x; wm3[1] = q.y; }
+#undef ALF_LOADROW
+    // pair of a row that starts at sample C relative to the block (C = 2 px + dx): even C -> W[(C+4)/2], odd C -> O[(C+3)/2]
+#define ALF_PAIR(W, O, C) ((((C) & 1) != 0) ? O[((C) + 3) >> 1] : W[((C) + 4) >> 1])
+#define ALF_TAP(K, DX, NP, NM)                                                                                          \
+    {                                                                                                                   \
+      const uint32_t cb = __vadd2(clipP1[K], ncur);                                                                     \
+      const uint32_t s = addClamp0(NP, cb, clip2[K]) + addClamp0(NM, cb, clip2[K]);                                     \
+      acc0 = __dp2a_lo((int)s, (int)coefB[K], acc0);                                                                    \
+      acc1 = __dp2a_hi((int)s, (int)coefB[K], acc1);                                                                    \
+    }
     uint32_t res[2];
 #pragma unroll
     for (int px = 0; px < 2; px++)
     {
-      const uint32_t cur = w[orow + 3][2 + px], ncur = ~cur;                   // clipP1 + ~cur = clip - cur per lane
+      const uint32_t cur = wc[2 + px], ncur = ~cur;                            // clipP1 + ~cur = clip - cur per lane
       int acc0 = bias, acc1 = bias;
-      ALF_TAP(0, 0, 3)
-      ALF_TAP(1, 1, 2) ALF_TAP(2, 0, 2) ALF_TAP(3, -1, 2)
-      ALF_TAP(4, 2, 1) ALF_TAP(5, 1, 1) ALF_TAP(6, 0, 1) ALF_TAP(7, -1, 1) ALF_TAP(8, -2, 1)
-      ALF_TAP(9, 3, 0) ALF_TAP(10, 2, 0) ALF_TAP(11, 1, 0)
+      ALF_TAP(0, 0, wp3[px], wm3[px])
+      ALF_TAP(1, 1, ALF_PAIR(wp2, op2, 2 * px + 1), ALF_PAIR(wm2, om2, 2 * px - 1))
+      ALF_TAP(2, 0, ALF_PAIR(wp2, op2, 2 * px), ALF_PAIR(wm2, om2, 2 * px))
+      ALF_TAP(3, -1, ALF_PAIR(wp2, op2, 2 * px - 1), ALF_PAIR(wm2, om2, 2 * px + 1))
+      ALF_TAP(4, 2, ALF_PAIR(wp1, op1, 2 * px + 2), ALF_PAIR(wm1, om1, 2 * px - 2))
+      ALF_TAP(5, 1, ALF_PAIR(wp1, op1, 2 * px + 1), ALF_PAIR(wm1, om1, 2 * px - 1))
+      ALF_TAP(6, 0, ALF_PAIR(wp1, op1, 2 * px), ALF_PAIR(wm1, om1, 2 * px))
+      ALF_TAP(7, -1, ALF_PAIR(wp1, op1, 2 * px - 1), ALF_PAIR(wm1, om1, 2 * px + 1))
+      ALF_TAP(8, -2, ALF_PAIR(wp1, op1, 2 * px - 2), ALF_PAIR(wm1, om1, 2 * px + 2))
+      ALF_TAP(9, 3, ALF_PAIR(wc, oc, 2 * px + 3), ALF_PAIR(wc, oc, 2 * px - 3))
+      ALF_TAP(10, 2, ALF_PAIR(wc, oc, 2 * px + 2), ALF_PAIR(wc, oc, 2 * px - 2))
+      ALF_TAP(11, 1, ALF_PAIR(wc, oc, 2 * px + 1), ALF_PAIR(wc, oc, 2 * px - 1))
       res[px] = addClamp0(cur, prmt((uint32_t)(acc0 >> sh), (uint32_t)(acc1 >> sh), 0x5410u), maxvP);
     }
     *reinterpret_cast<uint2*>(out + (size_t)orow * pitchOut) = make_uint2(res[0], res[1]);
-  }
 #undef ALF_TAP
-#undef ALF_ROW
 #undef ALF_PAIR
+  }
 }
 
 // ---- chroma 5x5 + CC-ALF, packed (four horizontally adjacent chroma samples per thread) ----------------------------
@@ -570,9 +584,7 @@ __global__ void __launch_bounds__(SA_THREADS, 2) k_alf(const SlotDev* __restrict
           alfClassify(sumV, sumH, sumD0, sumD1, vb ? 96 : 64, g.bdL, cls, tIdx);
           const AlfLumaEntry* e = S.lumaTab + ((size_t)(setIdx * 25 + cls) * 4 + tIdx);
           const uint32_t maxvP = dup16((1 << g.bdL) - 1);
-          if (vb == 0) alfLumaBlockFast<0>(c0, out, dstY.pitch, e, maxvP);          // vb is uniform per warp for CTU sizes >= 32
-          else if (vb == 1) alfLumaBlockFast<1>(c0, out, dstY.pitch, e, maxvP);
-          else alfLumaBlockFast<2>(c0, out, dstY.pitch, e, maxvP);
+          alfLumaBlockFast(c0, out, dstY.pitch, e, maxvP, vb);
         }
       }
     }
