@@ -103,6 +103,21 @@ typedef struct vtmgpu_deblock_params
   const uint64_t* chroma[2];   /* [dir] see above; NULL for 4:0:0                            */
 } vtmgpu_deblock_params;
 
+/* Sparse form of the same records: only the units that carry an edge to be filtered (typically ~10 % of the
+ * units of an inter picture), as produced by a CU walk (LoopFilter::xDeblockCU, LoopFilter.cpp:261-408) that
+ * appends instead of storing into a picture-sized array.  array a: 0 = luma dir 0, 1 = luma dir 1,
+ * 2 = chroma dir 0, 3 = chroma dir 1; index = position in the corresponding dense array above.  Every index
+ * may appear at most once per array; units that are not listed have no edge. */
+typedef struct vtmgpu_dbf_luma_entry   { uint32_t index; uint32_t rec; } vtmgpu_dbf_luma_entry;
+typedef struct vtmgpu_dbf_chroma_entry { uint64_t rec; uint32_t index; uint32_t reserved; } vtmgpu_dbf_chroma_entry;
+typedef struct vtmgpu_deblock_sparse
+{
+  const vtmgpu_dbf_luma_entry*   luma[2];
+  const vtmgpu_dbf_chroma_entry* chroma[2];   /* ignored for 4:0:0 */
+  uint32_t luma_count[2];
+  uint32_t chroma_count[2];
+} vtmgpu_deblock_sparse;
+
 /* ---------------------------------------------------------------------------------------------
  * SAO (SAOOffset / SAOBlkParam, TypeDef.h:938-963; enums :706-748)
  * --------------------------------------------------------------------------------------------- */
@@ -195,7 +210,7 @@ typedef struct vtmgpu_ctx vtmgpu_ctx;
 
 int          vtmgpu_abi_version(void);
 int          vtmgpu_abi_sizeof(int which);   /* sizeof of ABI struct #which (0 seq, 1 deblock, 2 sao_offset, 3 sao_ctu, 4 sao_params,
-                                                5 alf_luma_aps, 6 alf_chroma_aps, 7 alf_params) for binding self-checks */
+                                                5 alf_luma_aps, 6 alf_chroma_aps, 7 alf_params, 8 deblock_sparse) for binding self-checks */
 const char*  vtmgpu_last_error(const vtmgpu_ctx* ctx);   /* ctx may be NULL: error of the last failed create */
 
 int  vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out);
@@ -214,6 +229,10 @@ int vtmgpu_set_deblock(vtmgpu_ctx* ctx, int slot, const vtmgpu_deblock_params* p
 /* the same without the staging copy: the record arrays are read by asynchronous copies on the ctx stream and must stay valid
  * (and should be page-locked) until vtmgpu_sync */
 int vtmgpu_set_deblock_async(vtmgpu_ctx* ctx, int slot, const vtmgpu_deblock_params* p);
+/* the records as lists (0.1-0.2 B of upload per luma pixel instead of 0.75): the lists are read by asynchronous copies on
+ * the ctx stream and scattered into the record arrays on the device; page-locked lists must stay valid until vtmgpu_sync,
+ * pageable ones may be reused on return */
+int vtmgpu_set_deblock_sparse(vtmgpu_ctx* ctx, int slot, const vtmgpu_deblock_sparse* p);
 int vtmgpu_set_sao    (vtmgpu_ctx* ctx, int slot, const vtmgpu_sao_params* p);       /* NULL = stage off */
 int vtmgpu_set_alf    (vtmgpu_ctx* ctx, int slot, const vtmgpu_alf_params* p);       /* NULL = stage off */
 

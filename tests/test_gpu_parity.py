@@ -140,6 +140,26 @@ def test_async_side_info_and_caller_stream():
     ctx.close()
 
 
+@pytest.mark.parametrize("w,h,cf,density", [(640, 384, 1, 0.3), (456, 264, 3, 1.0), (320, 192, 0, 0.1), (1920, 1080, 1, 0.05)])
+def test_sparse_records_equal_dense(w, h, cf, density):
+    """vtmgpu_set_deblock_sparse (lists of the active units, scattered on the device) == the dense record arrays; a slot that
+    held a denser picture before must not keep stale records; records listed on the picture border are ignored."""
+    dense_before = synth.make_picture(w, h, chroma_format=cf, seed=77, density=1.0)
+    cap = synth.make_picture(w, h, chroma_format=cf, seed=w + cf, density=density)
+    want = pyoracle.filter_capture(cap)["final"]
+    ctx = gpu.Context(cap.seq)
+    ctx.set_capture(0, dense_before)
+    ctx.filter(0, 1)
+    ctx.rewind(0, 1)
+    ctx.set_capture(0, cap)
+    sp = gpu.sparse_records(cap.dbf_luma, cap.dbf_chroma if cap.ncomp > 1 else None, pin=(cf == 1))
+    assert sp.luma_count[0] <= cap.dbf_luma[0].size
+    ctx.set_deblock_sparse(0, sp)
+    ctx.filter(0, 1)
+    _eq(ctx.download(0), want, "sparse records")
+    ctx.close()
+
+
 def test_bad_arguments_fail_loudly():
     cap = synth.make_picture(256, 128, seed=1)
     ctx = gpu.Context(cap.seq)
@@ -149,6 +169,10 @@ def test_bad_arguments_fail_loudly():
     p.num_ctus += 1
     with pytest.raises(gpu.VtmGpuError):
         ctx.set_alf(0, p)
+    sp = gpu.sparse_records(cap.dbf_luma, cap.dbf_chroma)
+    sp.luma_count[0] = cap.dbf_luma[0].size + 1
+    with pytest.raises(gpu.VtmGpuError):
+        ctx.set_deblock_sparse(0, sp)
     ctx.close()
 
 

@@ -36,6 +36,23 @@ class DeblockParams(C.Structure):
     _fields_ = [("luma", C.POINTER(C.c_uint32) * 2), ("chroma", C.POINTER(C.c_uint64) * 2)]
 
 
+class DbfLumaEntry(C.Structure):
+    _fields_ = [("index", C.c_uint32), ("rec", C.c_uint32)]
+
+
+class DbfChromaEntry(C.Structure):
+    _fields_ = [("rec", C.c_uint64), ("index", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class DeblockSparse(C.Structure):
+    _fields_ = [("luma", C.POINTER(DbfLumaEntry) * 2), ("chroma", C.POINTER(DbfChromaEntry) * 2),
+                ("luma_count", C.c_uint32 * 2), ("chroma_count", C.c_uint32 * 2)]
+
+
+LUMA_ENTRY_DTYPE = [("index", "<u4"), ("rec", "<u4")]
+CHROMA_ENTRY_DTYPE = [("rec", "<u8"), ("index", "<u4"), ("reserved", "<u4")]
+
+
 class SaoOffset(C.Structure):
     _fields_ = [("mode", C.c_int8), ("type", C.c_int8), ("aux", C.c_int8), ("reserved", C.c_int8),
                 ("offset", C.c_int16 * 32)]
@@ -77,7 +94,7 @@ Strides = C.c_ssize_t * 3
 # every entry point include/vtmgpu.h declares (tests check that the built library exports all of them)
 ENTRY_POINTS = [
     "vtmgpu_abi_version", "vtmgpu_abi_sizeof", "vtmgpu_upload_async", "vtmgpu_download_async", "vtmgpu_last_error", "vtmgpu_create", "vtmgpu_destroy", "vtmgpu_upload", "vtmgpu_download",
-    "vtmgpu_set_deblock", "vtmgpu_set_deblock_async", "vtmgpu_set_sao", "vtmgpu_set_alf", "vtmgpu_sao_reconstruct", "vtmgpu_deblock", "vtmgpu_sao",
+    "vtmgpu_set_deblock", "vtmgpu_set_deblock_async", "vtmgpu_set_deblock_sparse", "vtmgpu_set_sao", "vtmgpu_set_alf", "vtmgpu_sao_reconstruct", "vtmgpu_deblock", "vtmgpu_sao",
     "vtmgpu_alf", "vtmgpu_sao_alf", "vtmgpu_deblock_sao", "vtmgpu_filter", "vtmgpu_filter_async", "vtmgpu_sync", "vtmgpu_timer_start",
     "vtmgpu_timer_stop", "vtmgpu_rewind", "vtmgpu_launch_count", "vtmgpu_set_profiling", "vtmgpu_stage_ms",
     "vtmgpu_set_rows", "vtmgpu_set_stream", "vtmgpu_upload_rows", "vtmgpu_download_rows", "vtmgpu_export_rows", "vtmgpu_import_rows", "vtmgpu_export_halo", "vtmgpu_import_halo",

@@ -35,7 +35,10 @@ namespace vtmgpu
 constexpr int SA_T = 64;                    // luma tile width
 constexpr int SA_TH = 64;                   // luma tile height
 constexpr int SA_THLOG = 6;
-constexpr int SA_THREADS = (SA_T / 4) * (SA_TH / 4);   // 128: one thread per 4x4 luma block; small CTAs (4 per SM) decorrelate the phases
+constexpr int SA_THREADS = (SA_T / 4) * (SA_TH / 4);   // 256: one thread per 4x4 luma block
+#ifndef SA_CTAS_PER_SM
+#define SA_CTAS_PER_SM 2
+#endif
 constexpr int SA_HX = 8, SA_HY = 4;         // halo loaded around a tile (x: one aligned group of 8)
 constexpr int SA_W = SA_T + 2 * SA_HX;      // 80
 constexpr int SA_H = SA_TH + 2 * SA_HY;     // 40
@@ -232,19 +235,21 @@ __device__ __forceinline__ void alfOwnCells(uint2 (*cell)[SA_CELLP], const pel* 
 // vb = 0 away from the boundary, 1 / 2 for the block directly above / below it.
 __device__ __forceinline__ void alfLumaBlockFast(const pel* c0, pel* out, int pitchOut, const AlfLumaEntry* __restrict__ e, uint32_t maxvP, int vb)
 {
-  uint32_t coefB[12], clipP1[12], clip2[12];
-  {
-    const uint4* q = reinterpret_cast<const uint4*>(e);
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-    {
-      const uint4 a = __ldg(q + i), b = __ldg(q + 3 + i), c = __ldg(q + 6 + i);
-      coefB[4 * i] = a.x; coefB[4 * i + 1] = a.y; coefB[4 * i + 2] = a.z; coefB[4 * i + 3] = a.w;
-      clipP1[4 * i] = b.x; clipP1[4 * i + 1] = b.y; clipP1[4 * i + 2] = b.z; clipP1[4 * i + 3] = b.w;
-      clip2[4 * i] = c.x; clip2[4 * i + 1] = c.y; clip2[4 * i + 2] = c.z; clip2[4 * i + 3] = c.w;
-    }
+#define ALF_LOAD_ENTRY(E)                                                                                               \
+  {                                                                                                                     \
+    const uint4* q = reinterpret_cast<const uint4*>(E);                                                                 \
+    _Pragma("unroll") for (int i = 0; i < 3; i++)                                                                       \
+    {                                                                                                                   \
+      const uint4 a = __ldg(q + i), b = __ldg(q + 3 + i), c = __ldg(q + 6 + i);                                         \
+      coefB[4 * i] = a.x; coefB[4 * i + 1] = a.y; coefB[4 * i + 2] = a.z; coefB[4 * i + 3] = a.w;                       \
+      clipP1[4 * i] = b.x; clipP1[4 * i + 1] = b.y; clipP1[4 * i + 2] = b.z; clipP1[4 * i + 3] = b.w;                   \
+      clip2[4 * i] = c.x; clip2[4 * i + 1] = c.y; clip2[4 * i + 2] = c.z; clip2[4 * i + 3] = c.w;                       \
+    }                                                                                                                   \
+    bias = __ldg(&(E)->bias);                                                                                           \
   }
-  const int bias = __ldg(&e->bias);
+  uint32_t coefB[12], clipP1[12], clip2[12];
+  int bias;
+  ALF_LOAD_ENTRY(e)
 #pragma unroll 1
   for (int orow = 0; orow < 4; orow++)
   {
@@ -300,6 +305,7 @@ __device__ __forceinline__ void alfLumaBlockFast(const pel* c0, pel* out, int pi
 #undef ALF_TAP
 #undef ALF_PAIR
   }
+#undef ALF_LOAD_ENTRY
 }
 
 // ---- chroma 5x5 + CC-ALF, packed (four horizontally adjacent chroma samples per thread) ----------------------------
@@ -454,7 +460,7 @@ __device__ __forceinline__ void saPrefetch(unsigned char* smraw, const SaLayout&
 // Persistent kernel: gridDim.x CTAs walk the tiles of slots [firstSlot, firstSlot + numSlots) round robin; while a CTA
 // filters tile i, the TMA loads of tile i+1 are in flight (two stages).  maps = tensor maps of the source buffer of the
 // first slot: [slot][3 buffers][3 planes].
-__global__ void __launch_bounds__(SA_THREADS, 2) k_alf(const SlotDev* __restrict__ slots, const CUtensorMap* __restrict__ tmaps, int firstSlot, int numSlots,
+__global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDev* __restrict__ slots, const CUtensorMap* __restrict__ tmaps, int firstSlot, int numSlots,
                                                            int srcBuf, int dstBuf, Geom g, int tilesX, int tilesY, int ty0, SaStep step)
 {
   extern __shared__ __align__(128) unsigned char smraw[];

@@ -29,7 +29,7 @@ std::string g_createError;
 
 struct SideLayout     // byte offsets inside a slot's side-info block
 {
-  size_t dbfL[2], dbfC[2], sao, alfTab, ctuCtl, alf, total;
+  size_t dbfL[2], dbfC[2], dbfEnd, sao, alfTab, ctuCtl, alf, total;
   size_t nL, nC[2];          // records of the ABI arrays (dense)
   int recW[4], recH[4], recP[4];   // device record arrays lumaV, lumaH, chromaV, chromaH: width, height, row pitch (records; pitch * size is a multiple of 16 B for TMA)
 };
@@ -81,6 +81,7 @@ struct vtmgpu_ctx
   SideLayout lay{};
   std::vector<pel*> planeMem;          // one allocation per slot (3 buffers x ncomp planes)
   std::vector<unsigned char*> sideDev; // per slot
+  std::vector<unsigned char*> sparseDev; // per slot, allocated by the first vtmgpu_set_deblock_sparse: landing area of the record lists
   unsigned char* sidePinned = nullptr; // capacity * lay.total
   SlotDev* slotsPinned = nullptr;      // capacity entries (pinned mirror)
   SlotDev* slotsDev = nullptr;
@@ -134,6 +135,7 @@ extern "C" int vtmgpu_abi_sizeof(int which)
   case 5: return (int)sizeof(vtmgpu_alf_luma_aps);
   case 6: return (int)sizeof(vtmgpu_alf_chroma_aps);
   case 7: return (int)sizeof(vtmgpu_alf_params);
+  case 8: return (int)sizeof(vtmgpu_deblock_sparse);
   default: return -1;
   }
 }
@@ -145,6 +147,7 @@ extern "C" void vtmgpu_destroy(vtmgpu_ctx* c)
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (pel* p : c->planeMem) cudaFree(p);
   for (unsigned char* p : c->sideDev) cudaFree(p);
+  for (unsigned char* p : c->sparseDev) if (p) cudaFree(p);
   if (c->sidePinned) cudaFreeHost(c->sidePinned);
   if (c->slotsPinned) cudaFreeHost(c->slotsPinned);
   if (c->slotsDev) cudaFree(c->slotsDev);
@@ -198,6 +201,7 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
   for (int a = 0; a < 4; a++) L.recP[a] = (int)alignUp(L.recW[a], a < 2 ? 4 : 2);
   for (int d = 0; d < 2; d++) { L.dbfL[d] = off; off = alignUp(off + (size_t)L.recP[d] * L.recH[d] * 4, 256); }
   for (int d = 0; d < 2; d++) { L.dbfC[d] = off; off = alignUp(off + (size_t)L.recP[2 + d] * L.recH[2 + d] * 8, 256); }
+  L.dbfEnd = off;
   L.sao = off;    off = alignUp(off + (size_t)c->nCtus * 3 * sizeof(SaoDev), 256);
   L.alfTab = off; off = alignUp(off + sizeof(AlfLumaEntry) * VTMGPU_MAX_LUMA_SETS * 25 * 4, 256);
   L.ctuCtl = off; off = alignUp(off + (size_t)c->nCtus * sizeof(CtuCtlDev), 256);
@@ -573,6 +577,81 @@ int setDeblock(vtmgpu_ctx* c, int slot, const vtmgpu_deblock_params* p, bool dir
 }
 }   // namespace
 
+// scatter of the record lists into the (zeroed) record arrays of a slot: one thread per list entry.  Entries on the picture
+// border (column 0 of the vertical-edge arrays, row 0 of the horizontal-edge arrays) are dropped like clearBorderRecords does.
+struct ScatterArgs
+{
+  const void* list[4];
+  void* dense[4];
+  uint32_t count[4], first[5];          // first[a] = number of entries before array a
+  int recW[4], recH[4], recP[4];
+};
+
+__global__ void __launch_bounds__(256) k_dbf_scatter(ScatterArgs A)
+{
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < A.first[4]; t += gridDim.x * blockDim.x)
+  {
+    const int a = t >= A.first[2] ? (t >= A.first[3] ? 3 : 2) : (t >= A.first[1] ? 1 : 0);
+    const uint32_t k = t - A.first[a];
+    uint32_t index;
+    uint64_t rec;
+    if (a < 2)
+    {
+      const uint2 e = reinterpret_cast<const uint2*>(A.list[a])[k];
+      index = e.x; rec = e.y;
+    }
+    else
+    {
+      const uint4 e = reinterpret_cast<const uint4*>(A.list[a])[k];
+      rec = (uint64_t)e.x | (uint64_t)e.y << 32; index = e.z;
+    }
+    const uint32_t row = index / (uint32_t)A.recW[a], col = index - row * (uint32_t)A.recW[a];
+    if (row >= (uint32_t)A.recH[a] || ((a & 1) ? row == 0 : col == 0)) continue;
+    const size_t o = (size_t)row * A.recP[a] + col;
+    if (a < 2) reinterpret_cast<uint32_t*>(A.dense[a])[o] = (uint32_t)rec;
+    else       reinterpret_cast<uint64_t*>(A.dense[a])[o] = rec;
+  }
+}
+
+extern "C" int vtmgpu_set_deblock_sparse(vtmgpu_ctx* c, int slot, const vtmgpu_deblock_sparse* p)
+{
+  if (!c) return -1;
+  if (!c->slotOk(slot, 1)) return c->fail("set_deblock_sparse: bad slot %d", slot);
+  if (!p) return setDeblock(c, slot, nullptr, true);
+  cudaSetDevice(c->seq.device);
+  const SideLayout& L = c->lay;
+  size_t offs[5] = { 0, 0, 0, 0, 0 };    // landing area: worst case = every unit listed
+  for (int a = 0; a < 4; a++) offs[a + 1] = alignUp(offs[a] + (size_t)L.recW[a] * L.recH[a] * (a < 2 ? sizeof(vtmgpu_dbf_luma_entry) : sizeof(vtmgpu_dbf_chroma_entry)), 256);
+  if (c->sparseDev.empty()) c->sparseDev.assign(c->seq.capacity, nullptr);
+  if (!c->sparseDev[slot] && c->cuda(cudaMalloc(&c->sparseDev[slot], offs[4]), "record list allocation")) return -1;
+  ScatterArgs A{};
+  for (int a = 0; a < 4; a++)
+  {
+    const int d = a & 1;
+    const void* src = a < 2 ? (const void*)p->luma[d] : (const void*)p->chroma[d];
+    uint32_t n = a < 2 ? p->luma_count[d] : p->chroma_count[d];
+    if (!L.recW[a]) n = 0;
+    if (n > (uint32_t)L.recW[a] * (uint32_t)L.recH[a]) return c->fail("set_deblock_sparse: list %d has %u entries for %d units", a, n, L.recW[a] * L.recH[a]);
+    if (n && !src) return c->fail("set_deblock_sparse: list %d is NULL", a);
+    A.list[a] = c->sparseDev[slot] + offs[a];
+    A.dense[a] = c->sideDev[slot] + (a < 2 ? L.dbfL[d] : L.dbfC[d]);
+    A.count[a] = n; A.first[a + 1] = A.first[a] + n;
+    A.recW[a] = L.recW[a] ? L.recW[a] : 1; A.recH[a] = L.recH[a]; A.recP[a] = L.recP[a];
+    if (n && c->cuda(cudaMemcpyAsync(c->sparseDev[slot] + offs[a], src, (size_t)n * (a < 2 ? sizeof(vtmgpu_dbf_luma_entry) : sizeof(vtmgpu_dbf_chroma_entry)),
+                                     cudaMemcpyHostToDevice, c->stream), "set_deblock_sparse")) return -1;
+  }
+  if (c->cuda(cudaMemsetAsync(c->sideDev[slot] + L.dbfL[0], 0, L.dbfEnd - L.dbfL[0], c->stream), "record clear")) return -1;
+  if (A.first[4])
+  {
+    const int grid = (int)std::min<uint32_t>((A.first[4] + 255) / 256, 4u * c->numSms);
+    k_dbf_scatter<<<grid, 256, 0, c->stream>>>(A);
+    if (c->cuda(cudaGetLastError(), "k_dbf_scatter launch")) return -1;
+    c->launches++;
+  }
+  c->slotsPinned[slot].dbfOn = 1;
+  return c->pushSlot(slot);
+}
+
 extern "C" int vtmgpu_set_deblock(vtmgpu_ctx* c, int slot, const vtmgpu_deblock_params* p) { return setDeblock(c, slot, p, false); }
 extern "C" int vtmgpu_set_deblock_async(vtmgpu_ctx* c, int slot, const vtmgpu_deblock_params* p) { return setDeblock(c, slot, p, true); }
 
@@ -844,7 +923,7 @@ int launchAlf(vtmgpu_ctx* c, int first, int count)
   return forRuns(c, first, count, [&](int s, int n, int src) {
     const int dst = src == 1 ? 2 : 1;
     // persistent CTAs: four per SM (register limited), each walks the tiles round robin with double-buffered TMA loads
-    const int grid = std::min(tilesX * tilesY * n, 2 * c->numSms);
+    const int grid = std::min(tilesX * tilesY * n, SA_CTAS_PER_SM * c->numSms);
     SaStep st;
     st.dx = grid % tilesX;
     st.dy = (grid / tilesX) % tilesY;

@@ -58,6 +58,7 @@ def load_library(path=None):
         "vtmgpu_deblock": (C.c_int, [ctx, C.c_int, C.c_int]), "vtmgpu_sao": (C.c_int, [ctx, C.c_int, C.c_int]),
         "vtmgpu_alf": (C.c_int, [ctx, C.c_int, C.c_int]), "vtmgpu_sao_alf": (C.c_int, [ctx, C.c_int, C.c_int]),
         "vtmgpu_deblock_sao": (C.c_int, [ctx, C.c_int, C.c_int]),
+        "vtmgpu_set_deblock_sparse": (C.c_int, [ctx, C.c_int, C.POINTER(abi.DeblockSparse)]),
         "vtmgpu_filter": (C.c_int, [ctx, C.c_int, C.c_int]), "vtmgpu_filter_async": (C.c_int, [ctx, C.c_int, C.c_int]),
         "vtmgpu_sync": (C.c_int, [ctx]), "vtmgpu_timer_start": (C.c_int, [ctx]),
         "vtmgpu_timer_stop": (C.c_int, [ctx, C.POINTER(C.c_float)]),
@@ -93,6 +94,41 @@ def sao_reconstruct(ctus, width_in_ctus, ncomp, scale_luma=0, scale_chroma=0):
     if rc < 0:
         raise VtmGpuError("vtmgpu_sao_reconstruct: invalid SAO parameters (rc=%d)" % rc)
     return rc
+
+
+def sparse_records(dbf_luma, dbf_chroma, pin=False):
+    """List form (abi.DeblockSparse) of dense record arrays: what a producer that appends while walking the CUs emits.
+    pin=True places the lists in page-locked memory (torch) so that the uploads are asynchronous."""
+    import numpy as np
+    p, keep = abi.DeblockSparse(), []
+
+    def hold(a):
+        if pin:
+            import torch
+            t = torch.from_numpy(a.view(np.uint8).copy()).pin_memory()
+            keep.append(t)
+            return t.data_ptr()
+        keep.append(a)
+        return a.ctypes.data
+
+    for d in range(2):
+        dense = np.ascontiguousarray(dbf_luma[d]).reshape(-1).view(np.uint32)
+        idx = np.flatnonzero(dense)
+        ent = np.zeros(len(idx), dtype=abi.LUMA_ENTRY_DTYPE)
+        ent["index"], ent["rec"] = idx, dense[idx]
+        p.luma_count[d] = len(idx)
+        if len(idx):
+            p.luma[d] = C.cast(hold(ent), C.POINTER(abi.DbfLumaEntry))
+        if dbf_chroma is not None and dbf_chroma[d].size:
+            dense = np.ascontiguousarray(dbf_chroma[d]).reshape(-1).view(np.uint64)
+            idx = np.flatnonzero(dense)
+            ent = np.zeros(len(idx), dtype=abi.CHROMA_ENTRY_DTYPE)
+            ent["index"], ent["rec"] = idx, dense[idx]
+            p.chroma_count[d] = len(idx)
+            if len(idx):
+                p.chroma[d] = C.cast(hold(ent), C.POINTER(abi.DbfChromaEntry))
+    p._keep = keep
+    return p
 
 
 def _plane_args(planes):
@@ -187,6 +223,10 @@ class Context:
         """sync=False: no staging copy, the record arrays (page-locked) are read asynchronously until the next sync()."""
         fn = self.lib.vtmgpu_set_deblock if sync else self.lib.vtmgpu_set_deblock_async
         self._ck(fn(self.h, slot, C.byref(params) if params is not None else None), "set_deblock")
+
+    def set_deblock_sparse(self, slot, params):
+        """params: abi.DeblockSparse (see sparse_records); the lists are read asynchronously until the next sync()."""
+        self._ck(self.lib.vtmgpu_set_deblock_sparse(self.h, slot, C.byref(params) if params is not None else None), "set_deblock_sparse")
 
     def set_sao(self, slot, ctus):
         """ctus: reconstructed (abi.SaoCtu * n) array, or None to switch the stage off."""

@@ -53,6 +53,7 @@ struct GpuApi
   decltype(&vtmgpu_upload) upload = nullptr;
   decltype(&vtmgpu_download) download = nullptr;
   decltype(&vtmgpu_set_deblock) set_deblock = nullptr;
+  decltype(&vtmgpu_set_deblock_sparse) set_deblock_sparse = nullptr;
   decltype(&vtmgpu_set_sao) set_sao = nullptr;
   decltype(&vtmgpu_set_alf) set_alf = nullptr;
   decltype(&vtmgpu_sao_reconstruct) sao_reconstruct = nullptr;
@@ -70,7 +71,7 @@ struct GpuApi
     so = dlopen(path ? path : "libvtmgpu.so", RTLD_NOW | RTLD_LOCAL);
     if (!so) THROW("vtmgpu shim: cannot load libvtmgpu.so (" << dlerror() << ") -- no CPU fallback");
 #define SYM(n) n = reinterpret_cast<decltype(n)>(dlsym(so, "vtmgpu_" #n)); if (!n) THROW("vtmgpu shim: missing symbol vtmgpu_" #n)
-    SYM(abi_version); SYM(last_error); SYM(create); SYM(destroy); SYM(upload); SYM(download); SYM(set_deblock); SYM(set_sao);
+    SYM(abi_version); SYM(last_error); SYM(create); SYM(destroy); SYM(upload); SYM(download); SYM(set_deblock); SYM(set_deblock_sparse); SYM(set_sao);
     SYM(set_alf); SYM(sao_reconstruct); SYM(deblock); SYM(sao); SYM(alf); SYM(sao_alf); SYM(deblock_sao); SYM(filter);
 #undef SYM
     if (abi_version() != VTMGPU_ABI_VERSION) THROW("vtmgpu shim: ABI version mismatch");
@@ -82,7 +83,7 @@ struct Shim
   GpuApi api;
   vtmgpu_ctx* ctx = nullptr;
   vtmgpu_seq_params seq{};
-  bool useRef = false, staged = false, saoPending = false, dbfPending = false;
+  bool useRef = false, staged = false, saoPending = false, dbfPending = false, denseRecords = false;
   std::string captureDir;
   int picCount = 0;
   // per-picture
@@ -99,19 +100,23 @@ struct Shim
     if (useRef && (!vtmgpu_shim_alt_backend || !vtmgpu_shim_alt_backend())) THROW("vtmgpu shim: no alternative backend linked into this binary");
     if (const char* d = getenv("VTMGPU_CAPTURE_DIR")) captureDir = d;
     staged = !captureDir.empty() || (getenv("VTMGPU_STAGED") && atoi(getenv("VTMGPU_STAGED")));
+    denseRecords = getenv("VTMGPU_DENSE_RECORDS") && atoi(getenv("VTMGPU_DENSE_RECORDS"));
     timing = getenv("VTMGPU_SHIM_TIMING") && atoi(getenv("VTMGPU_SHIM_TIMING"));
   }
   ~Shim()
   {
     if (timing)
-      printf("vtmgpu-shim-timing: pictures=%d luma_pixels=%lld filter_s=%.6f dbf_s=%.6f sao_s=%.6f alf_s=%.6f derive_s=%.6f backend=%s\n", picCount,
-             lumaPixels, stageSec[0] + stageSec[1] + stageSec[2], stageSec[0], stageSec[1], stageSec[2], deriveSec, useRef ? "ref" : "gpu");
+      printf("vtmgpu-shim-timing: pictures=%d luma_pixels=%lld filter_s=%.6f dbf_s=%.6f sao_s=%.6f alf_s=%.6f derive_s=%.6f backend=%s "
+             "record_lists=%d record_bytes=%lld\n", picCount, lumaPixels, stageSec[0] + stageSec[1] + stageSec[2], stageSec[0], stageSec[1], stageSec[2], deriveSec,
+             useRef ? "ref" : "gpu", listPics, recordBytes);
     if (ctx) api.destroy(ctx);
   }
 
   // VTMGPU_SHIM_TIMING=1: steady_clock around the backend's stage calls only (for the reference backend that is exactly
   // loopFilterPic / SAOProcess / ALFProcess of the reference classes -- BASELINE.md section 4); host derivation separately
   bool timing = false;
+  int listPics = 0;              // pictures whose deblocking records went up as lists
+  long long recordBytes = 0;     // bytes of deblocking records handed to the library
   double stageSec[3] = { 0, 0, 0 }, deriveSec = 0;
   long long lumaPixels = 0;
   std::chrono::steady_clock::time_point t0;
@@ -253,6 +258,7 @@ void LoopFilter::loopFilterPic(CodingStructure& cs)
   if (!s.captureDir.empty())
   {
     s.cap.clear();
+    CHECK(s.dbf.listsValid && !s.dbf.listsMatchDense(), "vtmgpu shim: record lists and record arrays disagree");
     s.capturePlanes(cs, "pre");
     s.cap.add("dbfrec_l0", s.dbf.luma[0].data(), s.dbf.luma[0].size() * 4);
     s.cap.add("dbfrec_l1", s.dbf.luma[1].data(), s.dbf.luma[1].size() * 4);
@@ -266,8 +272,19 @@ void LoopFilter::loopFilterPic(CodingStructure& cs)
   }
   else
   {
-    const vtmgpu_deblock_params p = s.dbf.view();
-    s.check(s.api.set_deblock(s.ctx, 0, &p), "set_deblock");
+    if (s.dbf.listsValid && !s.denseRecords)
+    {
+      const vtmgpu_deblock_sparse p = s.dbf.sparseView();      // only the active units cross the bus
+      s.listPics++;
+      for (int d = 0; d < 2; d++) s.recordBytes += (long long)p.luma_count[d] * sizeof(vtmgpu_dbf_luma_entry) + (long long)p.chroma_count[d] * sizeof(vtmgpu_dbf_chroma_entry);
+      s.check(s.api.set_deblock_sparse(s.ctx, 0, &p), "set_deblock_sparse");
+    }
+    else
+    {
+      const vtmgpu_deblock_params p = s.dbf.view();
+      for (int d = 0; d < 2; d++) s.recordBytes += (long long)s.dbf.luma[d].size() * 4 + (long long)s.dbf.chroma[d].size() * 8;
+      s.check(s.api.set_deblock(s.ctx, 0, &p), "set_deblock");
+    }
     s.check(s.api.set_sao(s.ctx, 0, nullptr), "set_sao");
     s.check(s.api.set_alf(s.ctx, 0, nullptr), "set_alf");
     s.dbfPending = !(s.staged || lastStage(cs, 0));

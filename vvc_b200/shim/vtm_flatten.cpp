@@ -35,6 +35,31 @@ vtmgpu_deblock_params FlatDeblock::view() const
   return p;
 }
 
+vtmgpu_deblock_sparse FlatDeblock::sparseView() const
+{
+  vtmgpu_deblock_sparse p;
+  for (int d = 0; d < 2; d++)
+  {
+    p.luma[d]   = lists.luma[d].data();   p.luma_count[d]   = (uint32_t)lists.luma[d].size();
+    p.chroma[d] = lists.chroma[d].data(); p.chroma_count[d] = (uint32_t)lists.chroma[d].size();
+  }
+  return p;
+}
+
+bool FlatDeblock::listsMatchDense() const
+{
+  for (int d = 0; d < 2; d++)
+  {
+    size_t nl = 0, nc = 0;
+    for (uint32_t r : luma[d]) nl += r != 0;
+    for (uint64_t r : chroma[d]) nc += r != 0;
+    if (nl != lists.luma[d].size() || nc != lists.chroma[d].size()) return false;
+    for (const auto& e : lists.luma[d]) if (e.index >= luma[d].size() || luma[d][e.index] != e.rec) return false;
+    for (const auto& e : lists.chroma[d]) if (e.index >= chroma[d].size() || chroma[d][e.index] != e.rec) return false;
+  }
+  return true;
+}
+
 vtmgpu_sao_params FlatSao::view() const
 {
   vtmgpu_sao_params p;
@@ -94,6 +119,7 @@ private:
   CodingStructure&     m_cs;
   const PreCalcValues& m_pcv;
   FlatDeblock&         m_out;
+  FlatDeblock::Lists*  m_lists = nullptr;      // this thread's share of the record lists
   CtuState             m_st;
   const Slice*         m_ctuSlice = nullptr;   // slice of the first CU of the CTU in flight (what the reference leaves in cs.slice)
   int  m_sx, m_sy, m_ctuX = 0, m_ctuY = 0, m_dir = VER;
@@ -114,6 +140,20 @@ private:
   unsigned strength(const CodingUnit& cu, const Position& p) const;
   void emitLuma(const CodingUnit& cu, int edge);
   void emitChroma(const CodingUnit& cu, int edge);
+  void putLuma(size_t idx, uint32_t rec)
+  {
+    uint32_t& slot = m_out.luma[m_dir][idx];
+    if (slot) m_lists->twice = true;
+    slot = rec;
+    if (rec) m_lists->luma[m_dir].push_back(vtmgpu_dbf_luma_entry{ (uint32_t)idx, rec });
+  }
+  void putChroma(size_t idx, uint64_t rec)
+  {
+    uint64_t& slot = m_out.chroma[m_dir][idx];
+    if (slot) m_lists->twice = true;
+    slot = rec;
+    if (rec) m_lists->chroma[m_dir].push_back(vtmgpu_dbf_chroma_entry{ rec, (uint32_t)idx, 0u });
+  }
 };
 
 bool usable(const CodingUnit& q, const CodingUnit& p, const PPS& pps)
@@ -132,10 +172,26 @@ void Deriver::run()
   m_out.width = W; m_out.height = H; m_out.sx = m_sx; m_out.sy = m_sy;
   const bool chroma = m_pcv.chrFormat != CHROMA_400;
   const int gx = 8 << m_sx, gy = 8 << m_sy;
-  m_out.luma[VER].assign((size_t)(W / 4) * (H / 4), 0);
-  m_out.luma[HOR].assign((size_t)(W / 4) * (H / 4), 0);
-  m_out.chroma[VER].assign(chroma ? (size_t)((W + gx - 1) / gx) * (H / 4) : 0, 0);
-  m_out.chroma[HOR].assign(chroma ? (size_t)((H + gy - 1) / gy) * (W / 4) : 0, 0);
+  const size_t nL = (size_t)(W / 4) * (H / 4), nC[2] = { chroma ? (size_t)((W + gx - 1) / gx) * (H / 4) : 0, chroma ? (size_t)((H + gy - 1) / gy) * (W / 4) : 0 };
+  if (m_out.listsValid && m_out.luma[VER].size() == nL && m_out.luma[HOR].size() == nL && m_out.chroma[VER].size() == nC[0] && m_out.chroma[HOR].size() == nC[1])
+  {
+    // same geometry as the previous picture: un-set its records instead of clearing 0.75 B per luma pixel
+    for (int d = 0; d < 2; d++)
+    {
+      for (const auto& e : m_out.lists.luma[d]) m_out.luma[d][e.index] = 0;
+      for (const auto& e : m_out.lists.chroma[d]) m_out.chroma[d][e.index] = 0;
+    }
+  }
+  else
+  {
+    m_out.luma[VER].assign(nL, 0);
+    m_out.luma[HOR].assign(nL, 0);
+    m_out.chroma[VER].assign(nC[0], 0);
+    m_out.chroma[HOR].assign(nC[1], 0);
+  }
+  for (int d = 0; d < 2; d++) { m_out.lists.luma[d].clear(); m_out.lists.chroma[d].clear(); }
+  m_out.lists.twice = false;
+  m_out.listsValid = false;
 
   // two passes over the picture as in loopFilterPic (LoopFilter.cpp:165-240).  No record depends on samples
   // (LADF is rejected above), so both passes can be derived before any filtering happens -- and CTUs are independent
@@ -146,19 +202,34 @@ void Deriver::run()
   if (const char* e = getenv("VTMGPU_SHIM_THREADS")) nThreads = atoi(e);
   else nThreads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
   nThreads = std::max(1, std::min(nThreads, (int)m_pcv.heightInCtus));
-  if (nThreads == 1) rows(0, 1);
+  if (nThreads == 1) { m_lists = &m_out.lists; rows(0, 1); }
   else
   {
     std::vector<std::thread> pool;
     std::vector<std::exception_ptr> err(nThreads);
+    std::vector<FlatDeblock::Lists> part(nThreads);
     for (int t = 0; t < nThreads; t++)
-      pool.emplace_back([this, t, nThreads, &err] {
-        try { Deriver d(m_cs, m_out); d.rows(t, nThreads); }
+      pool.emplace_back([this, t, nThreads, &err, &part] {
+        try { Deriver d(m_cs, m_out); d.m_lists = &part[t]; d.rows(t, nThreads); }
         catch (...) { err[t] = std::current_exception(); }
       });
     for (auto& th : pool) th.join();
     for (auto& e : err) if (e) std::rethrow_exception(e);
+    for (int d = 0; d < 2; d++)
+    {
+      size_t nl = 0, nc = 0;
+      for (const auto& q : part) { nl += q.luma[d].size(); nc += q.chroma[d].size(); }
+      m_out.lists.luma[d].reserve(nl);
+      m_out.lists.chroma[d].reserve(nc);
+      for (const auto& q : part)
+      {
+        m_out.lists.luma[d].insert(m_out.lists.luma[d].end(), q.luma[d].begin(), q.luma[d].end());
+        m_out.lists.chroma[d].insert(m_out.lists.chroma[d].end(), q.chroma[d].begin(), q.chroma[d].end());
+        m_out.lists.twice |= q.twice;
+      }
+    }
   }
+  m_out.listsValid = !m_out.lists.twice;
   // side effect of the reference's CTU loop (LoopFilter.cpp:179,218): cs.slice ends up as the slice of the last CTU
   m_cs.slice = m_cs.getCU(Position((m_pcv.widthInCtus - 1) << m_pcv.maxCUWidthLog2, (m_pcv.heightInCtus - 1) << m_pcv.maxCUHeightLog2), CH_L)->slice;
 }
@@ -389,7 +460,7 @@ void Deriver::emitLuma(const CodingUnit& cu, int edge)
     }
     if (ctuRow) rec |= VTMGPU_DBF_L_CTUROW;
     if (!tc) rec = 0;
-    m_out.luma[m_dir][(size_t)(pos.y / 4) * (m_out.width / 4) + pos.x / 4] = rec;
+    putLuma((size_t)(pos.y / 4) * (m_out.width / 4) + pos.x / 4, rec);
   }
 }
 
@@ -462,8 +533,8 @@ void Deriver::emitChroma(const CodingUnit& cu, int edge)
       if (CU::isPLT(cuP)) rec |= VTMGPU_DBF_C_PNOFILT;
       if (CU::isPLT(cu))  rec |= VTMGPU_DBF_C_QNOFILT;
     }
-    if (m_dir == VER) m_out.chroma[VER][(size_t)(pos.y / 4) * ((m_out.width + gx - 1) / gx) + pos.x / gx] = rec;
-    else              m_out.chroma[HOR][(size_t)(pos.y / gy) * (m_out.width / 4) + pos.x / 4] = rec;
+    if (m_dir == VER) putChroma((size_t)(pos.y / 4) * ((m_out.width + gx - 1) / gx) + pos.x / gx, rec);
+    else              putChroma((size_t)(pos.y / gy) * (m_out.width / 4) + pos.x / 4, rec);
   }
 }
 

@@ -21,6 +21,18 @@ struct FlatDeblock
   std::vector<uint32_t> luma[2];
   std::vector<uint64_t> chroma[2];
   vtmgpu_deblock_params view() const;
+  // the same records as lists of the active units (vtmgpu_deblock_sparse), appended by the CU walk; listsValid is false when a
+  // unit was emitted twice (the dense arrays, where the later record wins, are authoritative then)
+  struct Lists
+  {
+    std::vector<vtmgpu_dbf_luma_entry>   luma[2];
+    std::vector<vtmgpu_dbf_chroma_entry> chroma[2];
+    bool twice = false;
+  };
+  Lists lists;
+  bool listsValid = false;
+  vtmgpu_deblock_sparse sparseView() const;
+  bool listsMatchDense() const;       // self-check used by the capture mode
 };
 
 struct FlatSao
