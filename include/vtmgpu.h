@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define VTMGPU_ABI_VERSION 1
+#define VTMGPU_ABI_VERSION 2
 
 /* chroma_format values follow ChromaFormat (TypeDef.h): 0 = 4:0:0, 1 = 4:2:0, 2 = 4:2:2, 3 = 4:4:4 */
 typedef struct vtmgpu_seq_params
@@ -188,6 +188,17 @@ typedef struct vtmgpu_alf_chroma_aps
   int16_t clip_idx[VTMGPU_ALF_MAX_ALTS][VTMGPU_ALF_CHROMA_COEFF];
 } vtmgpu_alf_chroma_aps;
 
+/* ALF at slice / tile boundaries with loop filtering across them disabled (ALFProcess :452-555): samples beyond a clipped
+ * side of the CTU are replaced by the nearest sample inside (copy + extendBorderPel of the reference); PAD_TL / PAD_BR: the
+ * top-left / bottom-right neighbour CTU belongs to another raster-scan slice although the top and left (bottom and right)
+ * neighbours do not -- the corner is padded horizontally from the CTU's first / last column (padBorderPel, Buffer.h:571). */
+#define VTMGPU_ALF_CLIP_TOP     1
+#define VTMGPU_ALF_CLIP_BOTTOM  2
+#define VTMGPU_ALF_CLIP_LEFT    4
+#define VTMGPU_ALF_CLIP_RIGHT   8
+#define VTMGPU_ALF_PAD_TL       16
+#define VTMGPU_ALF_PAD_BR       32
+
 typedef struct vtmgpu_alf_params
 {
   int32_t enabled[3];                   /* slice getTileGroupAlfEnabledFlag(Y/Cb/Cr) (AdaptiveLoopFilter.cpp:429) */
@@ -201,6 +212,8 @@ typedef struct vtmgpu_alf_params
   int16_t ccalf_coeff[2][VTMGPU_CCALF_MAX_FILTERS][VTMGPU_CCALF_COEFF];
   const uint8_t* ccalf_idc[2];          /* m_ccAlfFilterControl[comp-1] [ctus]; 0 = off, k = filter k-1        */
   int32_t num_ctus;
+  const uint8_t* ctu_clip;              /* [ctus] VTMGPU_ALF_CLIP_* / PAD_*, or NULL: picture partition boundaries that the
+                                           filter must not cross (isCrossedByVirtualBoundaries, AdaptiveLoopFilter.cpp:79-202) */
 } vtmgpu_alf_params;
 
 /* ---------------------------------------------------------------------------------------------

@@ -49,6 +49,17 @@ STREAMS = {
     "ra_2160p_b":   (3840, 2160, 420, 64, 9160, 14, 32, [RA], K, 32),    # frames 32..63
     "ai_4320p":     (7680, 4320, 420, 1, 4320, 14, 32, [AI], K + ["--TemporalSubsampleRatio=1"], 0),
     "ld444_1080p":  (1920, 1080, 444, 16, 444, 14, 32, [LD, "444/yuv444.cfg"], K, 0),
+    # picture partitioning with in-loop filtering across the partition boundaries switched off (ALF clip / pad
+    # path, SAO availability, deblocking edge suppression): 4x4 tiles in one slice; 3x3 tiles in two raster-scan slices (1 + 8
+    # tiles: the second slice wraps around the first one, which exercises the raster-slice corner padding)
+    "tiles_832x480": (832, 480, 420, 5, 31, 14, 32, [RA], K + ["--EnablePicPartitioning=1", "--TileColumnWidthArray=2,2", "--TileRowHeightArray=1,1",
+                                                               "--DisableLoopFilterAcrossTiles=1"], 0),
+    "slices_832x480": (832, 480, 420, 5, 32, 14, 32, [RA], K + ["--EnablePicPartitioning=1", "--TileColumnWidthArray=2,2,3", "--TileRowHeightArray=1,1,2",
+                                                                "--RasterScanSlices=1", "--RasterSliceSizes=1,8", "--DisableLoopFilterAcrossSlices=1",
+                                                                "--DisableLoopFilterAcrossTiles=0"], 0),
+    "slices45_832x480": (832, 480, 420, 3, 33, 14, 30, [RA], K + ["--EnablePicPartitioning=1", "--TileColumnWidthArray=2,2,3", "--TileRowHeightArray=1,1,2",
+                                                                  "--RasterScanSlices=1", "--RasterSliceSizes=4,5", "--DisableLoopFilterAcrossSlices=1",
+                                                                  "--DisableLoopFilterAcrossTiles=0"], 0),     # slice 0 ends mid tile row: bottom-right corner padding
     # short 4K clip for fast turnaround (first 8 pictures of the config-3 source)
     "ra_2160p_8":   (3840, 2160, 420, 8, 9160, 14, 32, [RA], K, 0),
 }

@@ -488,8 +488,26 @@ int vvco_alf_luma_set(const vtmgpu_alf_params* p, int set, int bd_luma, int16_t 
 
 static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-typedef struct { const pel* s; int w, h; } cplane;   /* tightly packed copy with replicate-border access */
-static inline int at(const cplane* c, int x, int y) { return c->s[(size_t)clampi(y, 0, c->h - 1) * c->w + clampi(x, 0, c->w - 1)]; }
+/* tightly packed copy of a plane with replicate-border access.  The window [xlo,xhi] x [ylo,yhi] is the picture, narrowed per
+ * CTU to the sides that must not be read across (ALFProcess :452-477: copy of the CTU + extendBorderPel = nearest sample
+ * inside); tl / br: raster-slice corner padding (padBorderPel, Buffer.h:571-607): left of tlx and above tly the sample of
+ * column tlx in the same row is used, right of brx and below bry the one of column brx. */
+typedef struct { const pel* s; int w, h, xlo, xhi, ylo, yhi, tl, tlx, tly, br, brx, bry; } cplane;
+static inline int at(const cplane* c, int x, int y)
+{
+  if (c->tl && x < c->tlx && y < c->tly) x = c->tlx;
+  if (c->br && x > c->brx && y > c->bry) x = c->brx;
+  return c->s[(size_t)clampi(y, c->ylo, c->yhi) * c->w + clampi(x, c->xlo, c->xhi)];
+}
+
+/* narrows the access window of component plane S to CTU [x0,x1) x [y0,y1) (component samples) on the clipped sides */
+static void alf_window(cplane* S, int x0, int y0, int x1, int y1, int clip)
+{
+  S->xlo = (clip & VTMGPU_ALF_CLIP_LEFT) ? x0 : 0;       S->xhi = (clip & VTMGPU_ALF_CLIP_RIGHT) ? x1 - 1 : S->w - 1;
+  S->ylo = (clip & VTMGPU_ALF_CLIP_TOP) ? y0 : 0;        S->yhi = (clip & VTMGPU_ALF_CLIP_BOTTOM) ? y1 - 1 : S->h - 1;
+  S->tl = (clip & VTMGPU_ALF_PAD_TL) != 0; S->tlx = x0; S->tly = y0;
+  S->br = (clip & VTMGPU_ALF_PAD_BR) != 0; S->brx = x1 - 1; S->bry = y1 - 1;
+}
 
 /* deriveClassificationBlk for the 4x4 block at (bx,by) (AdaptiveLoopFilter.cpp:873-1082) */
 static void alf_classify(const cplane* L, int bx, int by, int bd, int ctu, int* cls, int* tr)
@@ -560,7 +578,8 @@ static int alf_sample(const cplane* S, int x, int y, int ntap, const int8_t (*ta
   return clip3(0, maxv, sum + cur);
 }
 
-/* ALFProcess (AdaptiveLoopFilter.cpp:393-618), fast path only (no slice/tile/signalled virtual boundaries) */
+/* ALFProcess (AdaptiveLoopFilter.cpp:393-618) incl. the clip / pad path at slice and tile boundaries (p->ctu_clip); signalled
+ * virtual boundaries inside a CTU are not covered */
 int vvco_alf(int16_t* const plane[3], const ptrdiff_t stride[3], int width, int height, int chroma_format,
              int bd_luma, int bd_chroma, int ctu_size, const vtmgpu_alf_params* p)
 {
@@ -578,6 +597,7 @@ int vvco_alf(int16_t* const plane[3], const ptrdiff_t stride[3], int width, int 
     if (!copy[c]) return -1;
     for (int y = 0; y < h; y++) memcpy(copy[c] + (size_t)y * w, plane[c] + y * stride[c], sizeof(pel) * w);
     S[c].s = copy[c]; S[c].w = w; S[c].h = h;
+    alf_window(&S[c], 0, 0, w, h, 0);
   }
   int rc = 0;
   int16_t lc[25][12], lk[25][12];
@@ -589,6 +609,8 @@ int vvco_alf(int16_t* const plane[3], const ptrdiff_t stride[3], int width, int 
       const int a = cy * wctu + cx;
       const int x0 = cx * ctu_size, y0 = cy * ctu_size;
       const int x1 = x0 + ctu_size < width ? x0 + ctu_size : width, y1 = y0 + ctu_size < height ? y0 + ctu_size : height;
+      const int clip = p->ctu_clip ? p->ctu_clip[a] : 0;
+      for (int c = 0; c < ncomp; c++) alf_window(&S[c], x0 >> (c ? sx : 0), y0 >> (c ? sy : 0), x1 >> (c ? sx : 0), y1 >> (c ? sy : 0), clip);
       if (p->ctu_enable[0][a])
       {
         const int set = p->ctu_filter_idx[a];

@@ -73,6 +73,18 @@ def test_synthetic_vs_oracle(w, h, cf, bd, ctu, density):
     _eq(fused, want["final"], "fused chain")
 
 
+@pytest.mark.parametrize("w,h,cf,ctu", [(512, 384, 1, 128), (456, 264, 3, 128), (448, 256, 2, 64), (320, 320, 0, 64), (1920, 1080, 1, 128)])
+def test_partition_boundaries_vs_oracle(w, h, cf, ctu):
+    """ALF at slice / tile boundaries that must not be crossed: random per-CTU clip and corner-pad flags,
+    forced-on ALF / CC-ALF; the fixtures tiles_* / slices_* pin the same path against the reference itself."""
+    cap = synth.make_picture(w, h, chroma_format=cf, ctu_size=ctu, seed=3 * w + cf, density=1.0, partitions=True)
+    assert cap.alf["clip"].any()
+    want = pyoracle.filter_capture(cap)
+    got = gpu.execute_loop_filters(cap, fused=False)
+    _eq(got["alf"], want["alf"], "ALF with partition boundaries")
+    _eq(gpu.execute_loop_filters(cap, fused=True)["final"], want["final"], "fused chain")
+
+
 def test_stage_switches():
     """NULL side info switches a stage off: the picture must pass through unchanged."""
     cap = synth.make_picture(256, 128, seed=5)
@@ -176,7 +188,9 @@ def test_bad_arguments_fail_loudly():
     ctx.close()
 
 
-STREAMS = [("ra_416x240.bin", 8), ("ld444_1080p.bin", 16), ("ra_1080p.bin", 32), ("ai_4320p.bin", 1)]
+STREAMS = [("ra_416x240.bin", 8), ("ld444_1080p.bin", 16), ("ra_1080p.bin", 32), ("ai_4320p.bin", 1),
+           # tiles / raster-scan slices with in-loop filtering across their boundaries disabled
+           ("tiles_832x480.bin", 5), ("slices_832x480.bin", 5), ("slices45_832x480.bin", 3)]
 
 
 @pytest.mark.parametrize("stream,pictures", STREAMS)

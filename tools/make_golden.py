@@ -33,13 +33,23 @@ SELECT = {
     "ld444_cc_416x240": [1],           # 4:4:4 with CC-ALF
     "ra_q22_416x240": [0, 2],          # low QP: many APS filter sets, SAO on
     "ld_q37_832x480": [1],             # high QP low delay (strong / long deblocking filters)
+    "tiles_832x480": [0, 2],           # 4x4 tiles, no in-loop filtering across tile boundaries (ALF clip path, SAO availability)
+    "slices45_832x480": [0],           # slices of 4 + 5 tiles: bottom-right corner padding
+    "slices_832x480": [0, 3],          # 3x3 tiles in two raster-scan slices, no filtering across slices (ALF corner padding)
 }
 
 
 def main():
     os.makedirs(OUT, exist_ok=True)
     manifest = {}
+    mpath = os.path.join(OUT, "manifest.json")
+    only = sys.argv[1:]                       # optional: regenerate only these streams, keep the other manifest entries
+    if only and os.path.exists(mpath):
+        with open(mpath) as f:
+            manifest = {k: v for k, v in json.load(f).items() if v["stream"] not in only}
     for stream, keep in SELECT.items():
+        if only and stream not in only:
+            continue
         bs = os.path.join(STREAMS, stream + ".bin")
         if not os.path.exists(bs):
             print("skip (no stream):", stream)

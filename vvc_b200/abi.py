@@ -5,7 +5,7 @@ Keep in sync with the header; tests/test_abi.py checks sizes/offsets against the
 """
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 ALF_CLASSES, ALF_LUMA_COEFF, ALF_CHROMA_COEFF = 25, 13, 7
 ALF_MAX_APS, ALF_MAX_ALTS, ALF_FIXED_SETS = 8, 8, 16
@@ -85,7 +85,10 @@ class AlfParams(C.Structure):
                 ("ctu_enable", C.POINTER(C.c_uint8) * 3), ("ctu_filter_idx", C.POINTER(C.c_int16)),
                 ("ctu_alt", C.POINTER(C.c_uint8) * 2), ("ccalf_enabled", C.c_int32 * 2),
                 ("ccalf_coeff", ((C.c_int16 * CCALF_COEFF) * CCALF_MAX_FILTERS) * 2),
-                ("ccalf_idc", C.POINTER(C.c_uint8) * 2), ("num_ctus", C.c_int32)]
+                ("ccalf_idc", C.POINTER(C.c_uint8) * 2), ("num_ctus", C.c_int32), ("ctu_clip", C.POINTER(C.c_uint8))]
+
+
+ALF_CLIP_TOP, ALF_CLIP_BOTTOM, ALF_CLIP_LEFT, ALF_CLIP_RIGHT, ALF_PAD_TL, ALF_PAD_BR = 1, 2, 4, 8, 16, 32
 
 
 PlanePtrs = C.POINTER(C.c_int16) * 3

@@ -55,7 +55,8 @@ class Capture:
                             filter_idx=np.frombuffer(s["alf_fidx"], dtype=np.int16).copy(),
                             ctu_alt=[np.frombuffer(s["alf_alt%d" % c], dtype=np.uint8).copy() for c in range(2)],
                             cc_coeff=np.frombuffer(s["alf_cccoef"], dtype=np.int16).reshape(2, 4, 8).copy(),
-                            cc_idc=[np.frombuffer(s["alf_ccidc%d" % c], dtype=np.uint8).copy() for c in range(2)])
+                            cc_idc=[np.frombuffer(s["alf_ccidc%d" % c], dtype=np.uint8).copy() for c in range(2)],
+                            clip=np.frombuffer(s["alf_clip"], dtype=np.uint8).copy() if s.get("alf_clip") else None)
         self._sections = s
 
     # ---- geometry -------------------------------------------------------------------------------------
@@ -131,6 +132,8 @@ class Capture:
                 for k in range(8):
                     p.ccalf_coeff[c][f][k] = int(a["cc_coeff"][c, f, k])
         p.num_ctus = a["num_ctus"]
+        if a.get("clip") is not None:
+            p.ctu_clip = a["clip"].ctypes.data_as(C.POINTER(C.c_uint8))
         p._keep = keep + [a]
         return p
 

@@ -81,27 +81,53 @@ __host__ __device__ inline SaLayout saLayout(int sx, int sy, int ncomp)
 }
 
 // TMA fills positions outside the picture with zeros; the filters want the border samples replicated
-// (rows / columns of tile +- margin that lie outside take the value of the clamped position)
-__device__ __noinline__ void saReplicateBorder(pel* s, int bx0, int by0, int w, int h, int pitch, int tw, int th, int margin)
+// (rows / columns of tile +- margin that lie outside take the value of the clamped position).  The valid window
+// [xlo,xhi) x [ylo,yhi) is the picture, narrowed to the CTU on the sides the ALF must not read across (slice / tile
+// boundaries, ALFProcess :452-477: copy of the CTU + extendBorderPel = the same clamping).
+__device__ __noinline__ void saReplicateBorder(pel* s, int bx0, int by0, int xlo, int xhi, int ylo, int yhi, int pitch, int tw, int th, int margin)
 {
   const int xl = bx0 + SA_HX - margin, yt = by0 + SA_HY - margin;
   const int cols = tw + 2 * margin, rows = th + 2 * margin;
-  const int nl = max(0, -xl), cr = min(cols, max(0, w - xl));          // columns [0,nl) and [cr,cols) of the region are outside
+  const int nl = max(0, xlo - xl), cr = min(cols, max(0, xhi - xl));    // columns [0,nl) and [cr,cols) of the region are outside
   for (int rr = threadIdx.x >> 5; rr < rows; rr += SA_THREADS / 32)
   {
-    const int py = yt + rr, sy_ = min(max(py, 0), h - 1);
+    const int py = yt + rr, sy_ = min(max(py, ylo), yhi - 1);
     const pel* srow = s + (sy_ - by0) * pitch - bx0;
     pel* drow = s + (py - by0) * pitch - bx0;
     if (py != sy_)
     {
-      for (int cc = threadIdx.x & 31; cc < cols; cc += 32) { const int px = xl + cc; drow[px] = srow[min(max(px, 0), w - 1)]; }
+      for (int cc = threadIdx.x & 31; cc < cols; cc += 32) { const int px = xl + cc; drow[px] = srow[min(max(px, xlo), xhi - 1)]; }
     }
     else
     {
       const int lane = threadIdx.x & 31;
-      if (lane < nl) drow[xl + lane] = srow[0];
-      for (int cc = cr + lane; cc < cols; cc += 32) drow[xl + cc] = srow[w - 1];
+      if (lane < nl) drow[xl + lane] = srow[xlo];
+      for (int cc = cr + lane; cc < cols; cc += 32) drow[xl + cc] = srow[xhi - 1];
     }
+  }
+}
+
+// raster-scan slices (ALFProcess :478-488, padBorderPel): the CTU's top-left (bottom-right) neighbour is in another slice
+// while the adjacent ones are not -- in the corner outside the CTU [cx0,cx1) x [cy0,cy1) every row takes the sample of the
+// CTU's first (last) column of the same row.  Rows above / below the CTU hold real samples here (those sides are not clipped).
+__device__ __forceinline__ void saPadCorners(pel* s, int bx0, int by0, int cx0, int cy0, int cx1, int cy1, int pitch, int tw, int th, int margin, int clip)
+{
+  const int t = threadIdx.x;
+  if (t >= 2 * margin * margin) return;
+  const bool br = t >= margin * margin;
+  const int k = br ? t - margin * margin : t, dy = k / margin, dx = k - dy * margin;
+  const int tx0 = bx0 + SA_HX, ty0 = by0 + SA_HY;                            // tile origin in plane coordinates
+  if (!br)
+  {
+    if (!(clip & VTMGPU_ALF_PAD_TL) || tx0 != cx0 || ty0 != cy0) return;
+    pel* row = s + (cy0 - 1 - dy - by0) * pitch - bx0;
+    row[cx0 - 1 - dx] = row[cx0];
+  }
+  else
+  {
+    if (!(clip & VTMGPU_ALF_PAD_BR) || tx0 + tw != cx1 || ty0 + th != cy1) return;
+    pel* row = s + (cy1 + dy - by0) * pitch - bx0;
+    row[cx1 + dx] = row[cx1 - 1];
   }
 }
 
@@ -521,13 +547,27 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDe
     pel* const A1 = reinterpret_cast<pel*>(smraw + L.offA(stage, 1));
     pel* const A2 = reinterpret_cast<pel*>(smraw + L.offA(stage, 2));
     // tiles on the picture border: replicate the border samples into the zero-filled outside
-    // (= UnitBuf::extendBorderPel of the ALF input, AdaptiveLoopFilter.cpp:411)
-    const bool onBorder = x0 == 0 || y0 == 0 || x0 + SA_T + 8 > g.w || y0 + SA_TH + 8 > g.h;
+    // (= UnitBuf::extendBorderPel of the ALF input, AdaptiveLoopFilter.cpp:411); tiles of a CTU with a slice / tile boundary
+    // the filter must not read across: the same replication at the CTU's clipped sides (:452-490)
+    const int clip = ctl.clip;
+    const bool onBorder = x0 == 0 || y0 == 0 || x0 + SA_T + 8 > g.w || y0 + SA_TH + 8 > g.h || clip != 0;
     if (onBorder)
     {
-      if (alfY || ccCb || ccCr) saReplicateBorder(A0, x0 - SA_HX, y0 - SA_HY, g.w, g.h, SA_P, SA_T, SA_TH, 3);
-      if (alfCb) saReplicateBorder(A1, (x0 >> g.sx) - SA_HX, (y0 >> g.sy) - SA_HY, cw, chh, L.pitchC, tw, th, 3);
-      if (alfCr) saReplicateBorder(A2, (x0 >> g.sx) - SA_HX, (y0 >> g.sy) - SA_HY, cw, chh, L.pitchC, tw, th, 3);
+      const int cx0 = x0 & ~ctuMask, cy0 = y0 & ~ctuMask, cx1 = min(cx0 + g.ctu, g.w), cy1 = min(cy0 + g.ctu, g.h);
+      const int xlo = (clip & VTMGPU_ALF_CLIP_LEFT) ? cx0 : 0, xhi = (clip & VTMGPU_ALF_CLIP_RIGHT) ? cx1 : g.w;
+      const int ylo = (clip & VTMGPU_ALF_CLIP_TOP) ? cy0 : 0, yhi = (clip & VTMGPU_ALF_CLIP_BOTTOM) ? cy1 : g.h;
+      const int bxc = (x0 >> g.sx) - SA_HX, byc = (y0 >> g.sy) - SA_HY;
+      if (alfY || ccCb || ccCr) saReplicateBorder(A0, x0 - SA_HX, y0 - SA_HY, xlo, xhi, ylo, yhi, SA_P, SA_T, SA_TH, 3);
+      if (alfCb) saReplicateBorder(A1, bxc, byc, xlo >> g.sx, xhi >> g.sx, ylo >> g.sy, yhi >> g.sy, L.pitchC, tw, th, 3);
+      if (alfCr) saReplicateBorder(A2, bxc, byc, xlo >> g.sx, xhi >> g.sx, ylo >> g.sy, yhi >> g.sy, L.pitchC, tw, th, 3);
+      if (clip & (VTMGPU_ALF_PAD_TL | VTMGPU_ALF_PAD_BR))
+      {
+        // no barrier needed in between: the corners lie outside the clamp window's replicated ranges (their sides are not clipped)
+        const int tileW = min(SA_T, g.w - x0), tileH = min(SA_TH, g.h - y0);     // the CTU's last tile may be partial
+        if (alfY || ccCb || ccCr) saPadCorners(A0, x0 - SA_HX, y0 - SA_HY, cx0, cy0, cx1, cy1, SA_P, tileW, tileH, 3, clip);
+        if (alfCb) saPadCorners(A1, bxc, byc, cx0 >> g.sx, cy0 >> g.sy, cx1 >> g.sx, cy1 >> g.sy, L.pitchC, tileW >> g.sx, tileH >> g.sy, 3, clip);
+        if (alfCr) saPadCorners(A2, bxc, byc, cx0 >> g.sx, cy0 >> g.sy, cx1 >> g.sx, cy1 >> g.sy, L.pitchC, tileW >> g.sx, tileH >> g.sy, 3, clip);
+      }
       __syncthreads();
     }
     const pel* const B0 = A0;

@@ -828,6 +828,7 @@ extern "C" int vtmgpu_set_alf(vtmgpu_ctx* c, int slot, const vtmgpu_alf_params* 
     {
       CtuCtlDev& r = ctl[a];
       r.enCb = r.enCr = r.altCb = r.altCr = r.ccCb = r.ccCr = r.setIdx = 0;
+      r.clip = p->ctu_clip ? (uint8_t)(p->ctu_clip[a] & 63) : 0;
       r.enY = p->ctu_enable[0] && p->ctu_enable[0][a];
       if (r.enY)
       {

@@ -72,7 +72,8 @@ struct CtuCtlDev
   uint8_t altCb, altCr;          // chroma filter alternative
   uint8_t ccCb, ccCr;            // CC-ALF filter idc (0 = off)
   uint8_t setIdx;                // luma filter set: < 16 fixed, else APS
-  uint8_t pad[8];
+  uint8_t clip;                  // VTMGPU_ALF_CLIP_* / PAD_*: partition boundaries the filter must not read across
+  uint8_t pad[7];
 };
 
 struct SlotDev

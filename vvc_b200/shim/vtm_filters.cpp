@@ -408,6 +408,7 @@ void AdaptiveLoopFilter::ALFProcess(CodingStructure& cs)
     s.cap.add("alf_fidx", s.alf.filterIdx.data(), s.alf.filterIdx.size() * 2);
     for (int c = 0; c < 2; c++) s.cap.add(("alf_alt" + std::to_string(c)).c_str(), s.alf.ctuAlt[c].data(), s.alf.ctuAlt[c].size());
     s.cap.add("alf_cccoef", p->ccalf_coeff, sizeof(p->ccalf_coeff));
+    if (!s.alf.ctuClip.empty()) s.cap.add("alf_clip", s.alf.ctuClip.data(), s.alf.ctuClip.size());
     for (int c = 0; c < 2; c++) s.cap.add(("alf_ccidc" + std::to_string(c)).c_str(), s.alf.ccIdc[c].data(), s.alf.ccIdc[c].size());
   }
   s.tic();

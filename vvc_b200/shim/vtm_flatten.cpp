@@ -75,6 +75,7 @@ const vtmgpu_alf_params* FlatAlf::view()
   for (int c = 0; c < 3; c++) p.ctu_enable[c] = ctuEnable[c].data();
   for (int c = 0; c < 2; c++) { p.ctu_alt[c] = ctuAlt[c].data(); p.ccalf_idc[c] = ccIdc[c].data(); }
   p.ctu_filter_idx = filterIdx.data();
+  p.ctu_clip = ctuClip.empty() ? nullptr : ctuClip.data();
   return &p;
 }
 
@@ -686,24 +687,39 @@ void flattenAlf(CodingStructure& cs, const CcAlfFilterParam& cc, uint8_t* const 
     CHECK(!same, "vtmgpu shim: slices with different ALF parameters in one picture are not supported");
   }
   cs.slice = cs.getCU(Position(((n - 1) % pcv.widthInCtus) * pcv.maxCUWidth, ((n - 1) / pcv.widthInCtus) * pcv.maxCUHeight), CH_L)->slice;
-  // the clip/pad path of ALFProcess (:458-555) is entered when a CTU touches a slice/tile boundary that must not be
-  // crossed (isCrossedByVirtualBoundaries, :79-202); that path is not implemented on the device yet
+  // the clip / pad path of ALFProcess (:452-555) is entered when a CTU touches a slice or tile boundary that must not be
+  // crossed: the per-CTU flags of isCrossedByVirtualBoundaries (:79-202).  Signalled virtual boundaries (which may lie
+  // inside a CTU) are not implemented on the device.
   CHECK(cs.picHeader->getLoopFilterAcrossVirtualBoundariesDisabledFlag(), "vtmgpu shim: signalled virtual boundaries are not supported");
   const bool acrossSlices = cs.pps->getLoopFilterAcrossSlicesEnabledFlag(), acrossTiles = cs.pps->getLoopFilterAcrossTilesEnabledFlag();
   if (!acrossSlices || !acrossTiles)
+  {
+    const int wc = pcv.widthInCtus, hc = pcv.heightInCtus;
+    auto ctuCU = [&](int cx, int cy) { return cs.getCU(Position(cx * pcv.maxCUWidth, cy * pcv.maxCUHeight), CH_L); };
+    auto blocked = [&](const CodingUnit* a, const CodingUnit* b) {
+      return (!acrossSlices && !CU::isSameSlice(*a, *b)) || (!acrossTiles && !CU::isSameTile(*a, *b));
+    };
+    bool any = false;
+    out.ctuClip.assign(n, 0);
     for (int a = 0; a < n; a++)
     {
-      const int cx = a % pcv.widthInCtus, cy = a / pcv.widthInCtus;
-      const CodingUnit* cur = cs.getCU(Position(cx * pcv.maxCUWidth, cy * pcv.maxCUHeight), CH_L);
-      const int dx[3] = { -1, 0, -1 }, dy[3] = { 0, -1, -1 };
-      for (int k = 0; k < 3; k++)
-      {
-        if (cx + dx[k] < 0 || cy + dy[k] < 0) continue;
-        const CodingUnit* nb = cs.getCU(Position((cx + dx[k]) * pcv.maxCUWidth, (cy + dy[k]) * pcv.maxCUHeight), CH_L);
-        const bool blocked = (!acrossSlices && !CU::isSameSlice(*cur, *nb)) || (k < 2 && !acrossTiles && !CU::isSameTile(*cur, *nb));
-        CHECK(blocked, "vtmgpu shim: ALF across-slice/tile clipping is not supported");
-      }
+      const int cx = a % wc, cy = a / wc;
+      const CodingUnit* cur = ctuCU(cx, cy);
+      int f = 0;
+      if (cy > 0 && blocked(cur, ctuCU(cx, cy - 1))) f |= VTMGPU_ALF_CLIP_TOP;
+      if (cy + 1 < hc && blocked(cur, ctuCU(cx, cy + 1))) f |= VTMGPU_ALF_CLIP_BOTTOM;
+      if (cx > 0 && blocked(cur, ctuCU(cx - 1, cy))) f |= VTMGPU_ALF_CLIP_LEFT;
+      if (cx + 1 < wc && blocked(cur, ctuCU(cx + 1, cy))) f |= VTMGPU_ALF_CLIP_RIGHT;
+      // raster-scan slices: the diagonal neighbour may belong to another slice although the two adjacent ones do not (:178-200)
+      if (!(f & (VTMGPU_ALF_CLIP_TOP | VTMGPU_ALF_CLIP_LEFT)) && cx > 0 && cy > 0 && !acrossSlices && !CU::isSameSlice(*cur, *ctuCU(cx - 1, cy - 1)))
+        f |= VTMGPU_ALF_PAD_TL;
+      if (!(f & (VTMGPU_ALF_CLIP_BOTTOM | VTMGPU_ALF_CLIP_RIGHT)) && cx + 1 < wc && cy + 1 < hc && !acrossSlices && !CU::isSameSlice(*cur, *ctuCU(cx + 1, cy + 1)))
+        f |= VTMGPU_ALF_PAD_BR;
+      out.ctuClip[a] = (uint8_t)f;
+      any |= f != 0;
     }
+    if (!any) out.ctuClip.clear();
+  }
 
   for (int c = 0; c < 3; c++) out.p.enabled[c] = first->getTileGroupAlfEnabledFlag(ComponentID(c));
   APS** apss = first->getAlfAPSs();

@@ -50,6 +50,7 @@ struct FlatAlf
   vtmgpu_alf_chroma_aps chromaAps{};
   bool hasChromaAps = false;
   std::vector<uint8_t> ctuEnable[3], ctuAlt[2], ccIdc[2];
+  std::vector<uint8_t> ctuClip;      // VTMGPU_ALF_CLIP_* / PAD_* per CTU; empty = no partition boundary restricts the filter
   std::vector<int16_t> filterIdx;
   const vtmgpu_alf_params* view();
 };

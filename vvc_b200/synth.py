@@ -189,8 +189,9 @@ def _plane(rng, h, w, bd, phase):
 
 
 def make_picture(width, height, chroma_format=1, bit_depth=10, ctu_size=128, seed=0, density=0.6, p_split=0.55,
-                 dbf=True, sao=True, alf=True):
-    """Returns a Capture (pre planes + side info, no reference stage outputs)."""
+                 dbf=True, sao=True, alf=True, partitions=False):
+    """Returns a Capture (pre planes + side info, no reference stage outputs).  partitions: random per-CTU ALF clip / corner-pad
+    flags as slice and tile boundaries without cross-boundary filtering produce them (any combination is a legal input)."""
     assert width % 8 == 0 and height % 8 == 0
     rng = np.random.default_rng(seed)
     sx, sy = abi.chroma_shifts(chroma_format)
@@ -212,4 +213,20 @@ def make_picture(width, height, chroma_format=1, bit_depth=10, ctu_size=128, see
         sec["sao_scale"] = np.array([0, 0], dtype=np.int32).tobytes()
     if alf:
         sec.update(_alf_sections(rng, nctus, density, ncomp == 3))
+        if partitions:
+            prng = np.random.default_rng(seed + 777)       # separate stream: the other sections do not depend on this option
+            clip = np.zeros(nctus, dtype=np.uint8)
+            for a in range(nctus):
+                cx, cy = a % wctus, a // wctus
+                f = int(prng.integers(0, 16)) if prng.random() < 0.7 else 0
+                if cy == 0: f &= ~abi.ALF_CLIP_TOP
+                if cy == hctus - 1: f &= ~abi.ALF_CLIP_BOTTOM
+                if cx == 0: f &= ~abi.ALF_CLIP_LEFT
+                if cx == wctus - 1: f &= ~abi.ALF_CLIP_RIGHT
+                if not f & (abi.ALF_CLIP_TOP | abi.ALF_CLIP_LEFT) and cx > 0 and cy > 0 and prng.random() < 0.5:
+                    f |= abi.ALF_PAD_TL
+                if not f & (abi.ALF_CLIP_BOTTOM | abi.ALF_CLIP_RIGHT) and cx < wctus - 1 and cy < hctus - 1 and prng.random() < 0.5:
+                    f |= abi.ALF_PAD_BR
+                clip[a] = f
+            sec["alf_clip"] = clip.tobytes()
     return Capture(sec)
