@@ -97,10 +97,27 @@ typedef struct vtmgpu_seq_params
 #define VTMGPU_DBF_C_PNOFILT    (1ull << 46)
 #define VTMGPU_DBF_C_QNOFILT    (1ull << 47)
 
+/* LADF (luma adaptive deblocking filter QP offset, an SPS tool; deriveLADFShift, LoopFilter.cpp:815-841): the QP of a
+ * luma edge segment gets an offset selected by the mean of four reconstructed samples next to the edge -- for horizontal
+ * edges those are samples AFTER the vertical pass, which only the device has.  With ladf != NULL the luma records
+ * therefore carry QPs instead of thresholds,
+ *      tc   field = 128 + QP + 2 * (bS - 1) + 2 * slice_tc_offset_div2      (before the LADF offset, unclipped; :971)
+ *      beta field = 128 + QP + 2 * slice_beta_offset_div2                    (:972)
+ * and the kernel adds the offset and looks tc / beta up (tables :66-74, bit-depth scaling :974-975).  Chroma records are
+ * unchanged (LADF is luma only). */
+typedef struct vtmgpu_ladf
+{
+  int32_t num_intervals;       /* SPS getLadfNumIntervals(), 2..5                              */
+  int32_t qp_offset[5];        /* getLadfQpOffset(k)                                           */
+  int32_t lower_bound[5];      /* getLadfIntervalLowerBound(k), k >= 1 ([0] unused)            */
+} vtmgpu_ladf;
+#define VTMGPU_DBF_LADF_BIAS 128
+
 typedef struct vtmgpu_deblock_params
 {
   const uint32_t* luma[2];     /* [dir] width/4 * height/4 records                         */
   const uint64_t* chroma[2];   /* [dir] see above; NULL for 4:0:0                            */
+  const vtmgpu_ladf* ladf;     /* NULL unless the SPS enables LADF                            */
 } vtmgpu_deblock_params;
 
 /* Sparse form of the same records: only the units that carry an edge to be filtered (typically ~10 % of the
@@ -116,6 +133,7 @@ typedef struct vtmgpu_deblock_sparse
   const vtmgpu_dbf_chroma_entry* chroma[2];   /* ignored for 4:0:0 */
   uint32_t luma_count[2];
   uint32_t chroma_count[2];
+  const vtmgpu_ladf* ladf;     /* as in vtmgpu_deblock_params */
 } vtmgpu_deblock_sparse;
 
 /* ---------------------------------------------------------------------------------------------
@@ -223,7 +241,7 @@ typedef struct vtmgpu_ctx vtmgpu_ctx;
 
 int          vtmgpu_abi_version(void);
 int          vtmgpu_abi_sizeof(int which);   /* sizeof of ABI struct #which (0 seq, 1 deblock, 2 sao_offset, 3 sao_ctu, 4 sao_params,
-                                                5 alf_luma_aps, 6 alf_chroma_aps, 7 alf_params, 8 deblock_sparse) for binding self-checks */
+                                                5 alf_luma_aps, 6 alf_chroma_aps, 7 alf_params, 8 deblock_sparse, 9 ladf) for binding self-checks */
 const char*  vtmgpu_last_error(const vtmgpu_ctx* ctx);   /* ctx may be NULL: error of the last failed create */
 
 int  vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out);

@@ -60,6 +60,8 @@ STREAMS = {
     "slices45_832x480": (832, 480, 420, 3, 33, 14, 30, [RA], K + ["--EnablePicPartitioning=1", "--TileColumnWidthArray=2,2,3", "--TileRowHeightArray=1,1,2",
                                                                   "--RasterScanSlices=1", "--RasterSliceSizes=4,5", "--DisableLoopFilterAcrossSlices=1",
                                                                   "--DisableLoopFilterAcrossTiles=0"], 0),     # slice 0 ends mid tile row: bottom-right corner padding
+    # LADF (luma adaptive deblocking QP offset): tc / beta depend on reconstructed samples next to the edge
+    "ladf_832x480": (832, 480, 420, 5, 34, 14, 32, [RA], K + ["--LADF=1"], 0),
     # short 4K clip for fast turnaround (first 8 pictures of the config-3 source)
     "ra_2160p_8":   (3840, 2160, 420, 8, 9160, 14, 32, [RA], K, 0),
 }

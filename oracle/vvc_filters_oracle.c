@@ -156,11 +156,32 @@ static void dbf_luma_line(pel* x, ptrdiff_t o, int tc, int strong, int writeP, i
 }
 
 /* one 4-line luma segment; x = q0 of line 0, o = across, s = along */
-static void dbf_luma_segment(pel* x0, ptrdiff_t o, ptrdiff_t s, uint32_t rec, int bd)
+/* tc / beta tables (LoopFilter.cpp:66-74) */
+static const uint16_t tc_table[66] = { 0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,3,4,4,4,4,5,5,5,5,7,7,8,9,10,10,11,13,14,15,17,19,21,24,25,29,33,36,
+                                       41,45,51,57,64,71,80,89,100,112,125,141,157,177,198,222,250,280,314,352,395 };
+static const uint8_t beta_table[64] = { 0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,6,7,8,9,10,11,12,13,14,15,16,17,18,20,22,24,26,28,30,32,34,36,38,40,
+                                        42,44,46,48,50,52,54,56,58,60,62,64,66,68,70,72,74,76,78,80,82,84,86,88 };
+
+static void dbf_luma_segment(pel* x0, ptrdiff_t o, ptrdiff_t s, uint32_t rec, int bd, const vtmgpu_ladf* ladf)
 {
-  const int tc = rec & 0x7ff;
+  int tc = rec & 0x7ff;
   if (!tc) return;
-  const int beta = (rec >> VTMGPU_DBF_L_BETA_SHIFT) & 0x7ff;
+  int beta = (rec >> VTMGPU_DBF_L_BETA_SHIFT) & 0x7ff;
+  if (ladf)
+  {
+    /* deriveLADFShift (LoopFilter.cpp:815-841) on the picture in its current state, then :971-975 */
+    const int level = (x0[0] + x0[3 * s] + x0[-o] + x0[3 * s - o]) >> 2;
+    int shift = ladf->qp_offset[0];
+    for (int k = 1; k < ladf->num_intervals; k++)
+    {
+      if (level > ladf->lower_bound[k]) shift = ladf->qp_offset[k];
+      else break;
+    }
+    const int t = tc_table[clip3(0, 65, tc - VTMGPU_DBF_LADF_BIAS + shift)];
+    tc = bd < 10 ? (t + 2) >> (10 - bd) : t << (bd - 10);
+    beta = beta_table[clip3(0, 63, beta - VTMGPU_DBF_LADF_BIAS + shift)] << (bd - 8);
+    if (!tc) return;
+  }
   const int lenP = (rec >> VTMGPU_DBF_L_LENP_SHIFT) & 7, lenQ = (rec >> VTMGPU_DBF_L_LENQ_SHIFT) & 7;
   const int writeP = !(rec & VTMGPU_DBF_L_PNOFILT), writeQ = !(rec & VTMGPU_DBF_L_QNOFILT);
   const int largeP = lenP > 3 && !(rec & VTMGPU_DBF_L_CTUROW), largeQ = lenQ > 3;
@@ -301,8 +322,8 @@ int vvco_deblock(int16_t* const plane[3], const ptrdiff_t stride[3], int width, 
       for (int ux = 0; ux < uw; ux++)
       {
         pel* x = plane[0] + (ptrdiff_t)(uy * 4) * stride[0] + ux * 4;
-        if (dir == 0) dbf_luma_segment(x, 1, stride[0], rl[uy * uw + ux], bd_luma);
-        else          dbf_luma_segment(x, stride[0], 1, rl[uy * uw + ux], bd_luma);
+        if (dir == 0) dbf_luma_segment(x, 1, stride[0], rl[uy * uw + ux], bd_luma, p->ladf);
+        else          dbf_luma_segment(x, stride[0], 1, rl[uy * uw + ux], bd_luma, p->ladf);
       }
     if (chroma_format == 0 || !p->chroma[dir]) continue;
     const uint64_t* rc = p->chroma[dir];

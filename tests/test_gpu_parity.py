@@ -85,6 +85,22 @@ def test_partition_boundaries_vs_oracle(w, h, cf, ctu):
     _eq(gpu.execute_loop_filters(cap, fused=True)["final"], want["final"], "fused chain")
 
 
+@pytest.mark.parametrize("w,h,cf,bd", [(512, 384, 1, 10), (456, 264, 3, 8), (448, 256, 2, 12), (1920, 1080, 1, 10)])
+def test_ladf_vs_oracle(w, h, cf, bd):
+    """LADF (deriveLADFShift, LoopFilter.cpp:815-841): records carry QPs, tc / beta are derived on the device from the
+    reconstructed samples next to the edge (after the vertical pass for horizontal edges); dense and list form."""
+    cap = synth.make_picture(w, h, chroma_format=cf, bit_depth=bd, seed=w + bd, density=0.9, ladf=True)
+    want = pyoracle.filter_capture(cap)
+    got = gpu.execute_loop_filters(cap, fused=False)
+    _eq(got["dbf"], want["dbf"], "deblocking with LADF")
+    ctx = gpu.Context(cap.seq)
+    ctx.set_capture(0, cap)
+    ctx.set_deblock_sparse(0, gpu.sparse_records(cap.dbf_luma, cap.dbf_chroma if cap.ncomp > 1 else None, ladf=cap.ladf_struct()))
+    ctx.filter(0, 1)
+    _eq(ctx.download(0), want["final"], "LADF, records as lists")
+    ctx.close()
+
+
 def test_stage_switches():
     """NULL side info switches a stage off: the picture must pass through unchanged."""
     cap = synth.make_picture(256, 128, seed=5)
@@ -190,7 +206,8 @@ def test_bad_arguments_fail_loudly():
 
 STREAMS = [("ra_416x240.bin", 8), ("ld444_1080p.bin", 16), ("ra_1080p.bin", 32), ("ai_4320p.bin", 1),
            # tiles / raster-scan slices with in-loop filtering across their boundaries disabled
-           ("tiles_832x480.bin", 5), ("slices_832x480.bin", 5), ("slices45_832x480.bin", 3)]
+           ("tiles_832x480.bin", 5), ("slices_832x480.bin", 5), ("slices45_832x480.bin", 3),
+           ("ladf_832x480.bin", 5)]       # LADF: deblocking thresholds derived on the device
 
 
 @pytest.mark.parametrize("stream,pictures", STREAMS)

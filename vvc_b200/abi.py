@@ -32,8 +32,15 @@ class SeqParams(C.Structure):
                 ("capacity", C.c_int32), ("device", C.c_int32)]
 
 
+class Ladf(C.Structure):
+    _fields_ = [("num_intervals", C.c_int32), ("qp_offset", C.c_int32 * 5), ("lower_bound", C.c_int32 * 5)]
+
+
+DBF_LADF_BIAS = 128
+
+
 class DeblockParams(C.Structure):
-    _fields_ = [("luma", C.POINTER(C.c_uint32) * 2), ("chroma", C.POINTER(C.c_uint64) * 2)]
+    _fields_ = [("luma", C.POINTER(C.c_uint32) * 2), ("chroma", C.POINTER(C.c_uint64) * 2), ("ladf", C.POINTER(Ladf))]
 
 
 class DbfLumaEntry(C.Structure):
@@ -46,7 +53,7 @@ class DbfChromaEntry(C.Structure):
 
 class DeblockSparse(C.Structure):
     _fields_ = [("luma", C.POINTER(DbfLumaEntry) * 2), ("chroma", C.POINTER(DbfChromaEntry) * 2),
-                ("luma_count", C.c_uint32 * 2), ("chroma_count", C.c_uint32 * 2)]
+                ("luma_count", C.c_uint32 * 2), ("chroma_count", C.c_uint32 * 2), ("ladf", C.POINTER(Ladf))]
 
 
 LUMA_ENTRY_DTYPE = [("index", "<u4"), ("rec", "<u4")]

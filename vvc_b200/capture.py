@@ -43,6 +43,7 @@ class Capture:
         self.stage = {k: planes(k) for k in STAGES}
         self.dbf_luma = [np.frombuffer(s["dbfrec_l%d" % d], dtype=np.uint32).copy() for d in range(2)]
         self.dbf_chroma = [np.frombuffer(s["dbfrec_c%d" % d], dtype=np.uint64).copy() for d in range(2)]
+        self.ladf = np.frombuffer(s["dbf_ladf"], dtype=np.int32).copy() if s.get("dbf_ladf") else None    # vtmgpu_ladf as 11 int32
         self.sao_raw = bytes(s["sao_raw"]) if "sao_raw" in s else None
         self.sao_scale = [int(v) for v in np.frombuffer(s["sao_scale"], dtype=np.int32)] if "sao_scale" in s else [0, 0]
         self.alf = None
@@ -93,8 +94,16 @@ class Capture:
                 b = np.ascontiguousarray(self.dbf_chroma[d])
                 keep.append(b)
                 p.chroma[d] = b.ctypes.data_as(C.POINTER(C.c_uint64))
+        lad = self.ladf_struct()
+        if lad is not None:
+            keep.append(lad)
+            p.ladf = C.pointer(lad)
         p._keep = keep
         return p
+
+    def ladf_struct(self):
+        """abi.Ladf of the sequence, or None when LADF is off (then the luma records carry tc / beta)."""
+        return abi.Ladf.from_buffer_copy(self.ladf.tobytes()) if self.ladf is not None else None
 
     def sao_ctus(self):
         """Fresh, writable array of SaoCtu as parsed (NOT yet reconstructed); None when the stream has no SAO stage."""

@@ -29,6 +29,12 @@ constexpr int DBF_PITCH = DBF_SW + 8;                   // 152 samples = 304 B: 
 constexpr int DBF_THREADS = 256;
 
 // x points at q0 of one line in shared memory; o = step across the edge; P(k) = x[-(k+1)*o], Q(k) = x[k*o]
+// tc / beta tables of the standard (LoopFilter.cpp:66-74), only needed on the device with LADF
+__constant__ uint16_t kDbfTcTable[66] = { 0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,3,4,4,4,4,5,5,5,5,7,7,8,9,10,10,11,13,14,15,17,19,21,24,25,29,33,36,
+                                          41,45,51,57,64,71,80,89,100,112,125,141,157,177,198,222,250,280,314,352,395 };
+__constant__ uint8_t kDbfBetaTable[64] = { 0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,6,7,8,9,10,11,12,13,14,15,16,17,18,20,22,24,26,28,30,32,34,36,38,40,
+                                           42,44,46,48,50,52,54,56,58,60,62,64,66,68,70,72,74,76,78,80,82,84,86,88 };
+
 #define PK(k) ((int)x[-((k) + 1) * o])
 #define QK(k) ((int)x[(k) * o])
 
@@ -154,58 +160,30 @@ __device__ __forceinline__ void dbfLumaLine(pel* x, int o, int tc, bool strong, 
   }
 }
 
-// one 4-line luma segment; x0 = q0 of line 0, o = across, s = along
-__device__ void dbfLumaSegment(pel* x0, int o, int s, uint32_t rec, int maxv)
+// LADF: a luma record that carries QPs (include/vtmgpu.h, vtmgpu_ladf) is turned into the usual {tc, beta} record.  The QP
+// offset is selected by the mean of p0 / q0 of lines 0 and 3 of the segment in their current state (deriveLADFShift,
+// LoopFilter.cpp:815-841), tc / beta come from the tables (:971-975).  Called by all 32 lanes, lane ln of a quad owns line ln;
+// tc = 0 in the result means "nothing to filter" (the host drops such records when it derives tc itself).
+__device__ __noinline__ uint32_t dbfLadfRecord(uint32_t rec, const pel* x0, int o, int s, int ln, int bd, const LadfDev* ladf)
 {
-  const int tc = rec & 0x7ff;
-  const int beta = (rec >> VTMGPU_DBF_L_BETA_SHIFT) & 0x7ff;
-  const int lenP = (rec >> VTMGPU_DBF_L_LENP_SHIFT) & 7, lenQ = (rec >> VTMGPU_DBF_L_LENQ_SHIFT) & 7;
-  const bool wP = !(rec & VTMGPU_DBF_L_PNOFILT), wQ = !(rec & VTMGPU_DBF_L_QNOFILT);
-  const bool largeP = lenP > 3 && !(rec & VTMGPU_DBF_L_CTUROW), largeQ = lenQ > 3;
-  const int sideThr = (beta + (beta >> 1)) >> 3;
-  const pel* x = x0;
-  const int dp0 = iabs(PK(2) - 2 * PK(1) + PK(0)), dq0 = iabs(QK(0) - 2 * QK(1) + QK(2));
-  x = x0 + 3 * s;
-  const int dp3 = iabs(PK(2) - 2 * PK(1) + PK(0)), dq3 = iabs(QK(0) - 2 * QK(1) + QK(2));
-
-  if (largeP || largeQ)
+  const pel* x = x0 + ln * s;
+  const unsigned qb = threadIdx.x & 28u;
+  const int own = PK(0) + QK(0);
+  const int level = (__shfl_sync(0xffffffffu, own, qb) + __shfl_sync(0xffffffffu, own, qb + 3)) >> 2;
+  int shift = ladf->off[0];
+  for (int k = 1; k < ladf->n; k++)
   {
-    int dp0L = dp0, dq0L = dq0, dp3L = dp3, dq3L = dq3;
-    if (largeP)
-    {
-      x = x0;         dp0L = (dp0L + iabs(PK(5) - 2 * PK(4) + PK(3)) + 1) >> 1;
-      x = x0 + 3 * s; dp3L = (dp3L + iabs(PK(5) - 2 * PK(4) + PK(3)) + 1) >> 1;
-    }
-    if (largeQ)
-    {
-      x = x0;         dq0L = (dq0L + iabs(QK(3) - 2 * QK(4) + QK(5)) + 1) >> 1;
-      x = x0 + 3 * s; dq3L = (dq3L + iabs(QK(3) - 2 * QK(4) + QK(5)) + 1) >> 1;
-    }
-    const int d0L = dp0L + dq0L, d3L = dp3L + dq3L;
-    if (d0L + d3L < beta && dbfStrongLong(x0, o, 2 * d0L, beta, tc, largeP, largeQ, lenP, lenQ) &&
-        dbfStrongLong(x0 + 3 * s, o, 2 * d3L, beta, tc, largeP, largeQ, lenP, lenQ))
-    {
-      for (int i = 0; i < 4; i++) dbfLongLine(x0 + i * s, o, largeP ? lenP : 3, largeQ ? lenQ : 3, tc, wP, wQ);
-      return;
-    }
+    if (level > ladf->lb[k]) shift = ladf->off[k];
+    else break;
   }
-  const int d0 = dp0 + dq0, d3 = dp3 + dq3;
-  if (d0 + d3 < beta)
-  {
-    bool secondP = false, secondQ = false, strong = false;
-    if (lenP > 1 && lenQ > 1)
-    {
-      secondP = (dp0 + dp3) < sideThr;
-      secondQ = (dq0 + dq3) < sideThr;
-    }
-    if (lenP > 2 && lenQ > 2)
-      strong = dbfStrongShort(x0, o, 2 * d0, beta, tc, false) && dbfStrongShort(x0 + 3 * s, o, 2 * d3, beta, tc, false);
-#pragma unroll
-    for (int i = 0; i < 4; i++) dbfLumaLine(x0 + i * s, o, tc, strong, wP, wQ, secondP, secondQ, maxv);
-  }
+  const int t = kDbfTcTable[clip3(0, 65, (int)(rec & 0x7ff) - VTMGPU_DBF_LADF_BIAS + shift)];
+  const int tc = bd < 10 ? (t + 2) >> (10 - bd) : t << (bd - 10);
+  const int beta = (int)kDbfBetaTable[clip3(0, 63, (int)((rec >> VTMGPU_DBF_L_BETA_SHIFT) & 0x7ff) - VTMGPU_DBF_LADF_BIAS + shift)] << (bd - 8);
+  return (rec & ~0x3fffffu) | (uint32_t)tc | (uint32_t)beta << VTMGPU_DBF_L_BETA_SHIFT;
 }
 
-// The same decisions as dbfLumaSegment, spread over the 4 lanes of a quad: lane ln owns line ln of the segment, computes the
+// One 4-line luma segment (x0 = q0 of line 0, o = step across the edge, s = step along it), spread over the 4 lanes of a quad:
+// lane ln owns line ln of the segment, computes the
 // gradients / strong-filter tests of its own line, lines 0 and 3 are broadcast with shuffles (xEdgeFilterLuma evaluates the
 // first and the last line of a segment, LoopFilter.cpp:977-1043), then every lane filters its own line.  All 32 lanes of
 // the warp must call this together; `valid` = false marks a quad without work (reads stay legal, nothing is written).
@@ -213,12 +191,12 @@ __device__ __forceinline__ void dbfLumaSegmentQuad(pel* x0, int o, int s, uint32
 {
   const int tc = rec & 0x7ff;
   const int beta = (rec >> VTMGPU_DBF_L_BETA_SHIFT) & 0x7ff;
+  pel* xl = x0 + ln * s;
+  const pel* x = xl;
   const int lenP = (rec >> VTMGPU_DBF_L_LENP_SHIFT) & 7, lenQ = (rec >> VTMGPU_DBF_L_LENQ_SHIFT) & 7;
   const bool wP = valid && !(rec & VTMGPU_DBF_L_PNOFILT), wQ = valid && !(rec & VTMGPU_DBF_L_QNOFILT);
   const bool largeP = lenP > 3 && !(rec & VTMGPU_DBF_L_CTUROW), largeQ = lenQ > 3;
   const int sideThr = (beta + (beta >> 1)) >> 3;
-  pel* xl = x0 + ln * s;
-  const pel* x = xl;
   const int dp = iabs(PK(2) - 2 * PK(1) + PK(0)), dq = iabs(QK(0) - 2 * QK(1) + QK(2));
   int dpL = dp, dqL = dq;
   if (largeP) dpL = (dp + iabs(PK(5) - 2 * PK(4) + PK(3)) + 1) >> 1;
@@ -498,6 +476,7 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
     {
       const int maxv = (1 << (comp ? g.bdC : g.bdL)) - 1;
       const DbfPassGeom P = dbfPassGeom(comp, g);
+      const LadfDev* const ladf = S.ladf.n > 0 ? &S.ladf : nullptr;
       if (comp == 0)
       {
         const uint32_t* ra = reinterpret_cast<const uint32_t*>(stageMem + DBF_TILE_BYTES);
@@ -516,7 +495,10 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
             const int k = k0 + (lane >> 2);
             const bool valid = k < cnt;
             const int i = queue1[valid ? k : k0], sg = i / NE, e = i - sg * NE - 3;
-            dbfLumaSegmentQuad(&sm[(4 * sg) * DBF_PITCH + DBF_HALO - 4 + 4 * e], 1, DBF_PITCH, ra[i], maxv, lane & 3, valid);
+            pel* seg = &sm[(4 * sg) * DBF_PITCH + DBF_HALO - 4 + 4 * e];
+            uint32_t rec = ra[i];
+            if (ladf) rec = dbfLadfRecord(rec, seg, 1, DBF_PITCH, lane & 3, g.bdL, ladf);
+            dbfLumaSegmentQuad(seg, 1, DBF_PITCH, rec, maxv, lane & 3, valid && (rec & 0x7ff) != 0);
           }
         }
         __syncthreads();
@@ -528,7 +510,10 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
             const int k = k0 + (lane >> 2);
             const bool valid = k < cnt;
             const int i = queue2[valid ? k : k0], e = i / NSH, sg = i - e * NSH - 3;
-            dbfLumaSegmentQuad(&sm[(DBF_HALO + 4 * e) * DBF_PITCH + DBF_HALO - 4 + 4 * sg], DBF_PITCH, 1, rbv[i], maxv, lane & 3, valid);
+            pel* seg = &sm[(DBF_HALO + 4 * e) * DBF_PITCH + DBF_HALO - 4 + 4 * sg];
+            uint32_t rec = rbv[i];
+            if (ladf) rec = dbfLadfRecord(rec, seg, DBF_PITCH, 1, lane & 3, g.bdL, ladf);
+            dbfLumaSegmentQuad(seg, DBF_PITCH, 1, rec, maxv, lane & 3, valid && (rec & 0x7ff) != 0);
           }
         }
       }

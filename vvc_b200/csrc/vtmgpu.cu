@@ -136,6 +136,7 @@ extern "C" int vtmgpu_abi_sizeof(int which)
   case 6: return (int)sizeof(vtmgpu_alf_chroma_aps);
   case 7: return (int)sizeof(vtmgpu_alf_params);
   case 8: return (int)sizeof(vtmgpu_deblock_sparse);
+  case 9: return (int)sizeof(vtmgpu_ladf);
   default: return -1;
   }
 }
@@ -536,6 +537,17 @@ int clearBorderRecords(vtmgpu_ctx* c, int slot)
 
 // device arrays keep the ABI indexing but with a row pitch that is a multiple of 16 bytes (TMA).  direct = copy straight
 // from the caller's arrays (asynchronous when they are page-locked), else through the context's pinned staging block.
+int setLadf(vtmgpu_ctx* c, int slot, const vtmgpu_ladf* l)
+{
+  LadfDev& d = c->slotsPinned[slot].ladf;
+  d = LadfDev{};
+  if (!l) return 0;
+  if (l->num_intervals < 2 || l->num_intervals > 5) return c->fail("set_deblock: LADF needs 2..5 intervals, got %d", l->num_intervals);
+  d.n = l->num_intervals;
+  for (int k = 0; k < d.n; k++) { d.off[k] = l->qp_offset[k]; d.lb[k] = l->lower_bound[k]; }
+  return 0;
+}
+
 int setDeblock(vtmgpu_ctx* c, int slot, const vtmgpu_deblock_params* p, bool direct)
 {
   if (!c) return -1;
@@ -543,6 +555,7 @@ int setDeblock(vtmgpu_ctx* c, int slot, const vtmgpu_deblock_params* p, bool dir
   cudaSetDevice(c->seq.device);
   SlotDev& sd = c->slotsPinned[slot];
   sd.dbfOn = p != nullptr;
+  if (setLadf(c, slot, p ? p->ladf : nullptr)) return -1;
   if (p)
   {
     const SideLayout& L = c->lay;
@@ -649,6 +662,7 @@ extern "C" int vtmgpu_set_deblock_sparse(vtmgpu_ctx* c, int slot, const vtmgpu_d
     c->launches++;
   }
   c->slotsPinned[slot].dbfOn = 1;
+  if (setLadf(c, slot, p->ladf)) return -1;
   return c->pushSlot(slot);
 }
 

@@ -76,6 +76,11 @@ struct CtuCtlDev
   uint8_t pad[7];
 };
 
+struct LadfDev                   // vtmgpu_ladf; n = 0: off (the luma records carry tc / beta)
+{
+  int32_t n, off[5], lb[5], pad;
+};
+
 struct SlotDev
 {
   PlaneDev buf[3][3];            // [buffer][component]; buffer 0 = pristine upload, 1/2 = working
@@ -87,6 +92,7 @@ struct SlotDev
   const AlfLumaEntry* lumaTab;   // [sets][25 classes][4 transposes]
   int32_t dbfOn, saoOn, alfOn;   // alfOn: parameters set AND the slice enables ALF for at least one component
   int32_t alfWide;               // a luma coefficient does not fit the s8 operand of IDP.2A: generic path
+  LadfDev ladf;
 };
 
 struct Geom

@@ -96,7 +96,7 @@ def sao_reconstruct(ctus, width_in_ctus, ncomp, scale_luma=0, scale_chroma=0):
     return rc
 
 
-def sparse_records(dbf_luma, dbf_chroma, pin=False):
+def sparse_records(dbf_luma, dbf_chroma, pin=False, ladf=None):
     """List form (abi.DeblockSparse) of dense record arrays: what a producer that appends while walking the CUs emits.
     pin=True places the lists in page-locked memory (torch) so that the uploads are asynchronous."""
     import numpy as np
@@ -127,6 +127,9 @@ def sparse_records(dbf_luma, dbf_chroma, pin=False):
             p.chroma_count[d] = len(idx)
             if len(idx):
                 p.chroma[d] = C.cast(hold(ent), C.POINTER(abi.DbfChromaEntry))
+    if ladf is not None:
+        keep.append(ladf)
+        p.ladf = C.pointer(ladf)
     p._keep = keep
     return p
 

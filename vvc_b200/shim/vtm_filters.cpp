@@ -264,6 +264,7 @@ void LoopFilter::loopFilterPic(CodingStructure& cs)
     s.cap.add("dbfrec_l1", s.dbf.luma[1].data(), s.dbf.luma[1].size() * 4);
     s.cap.add("dbfrec_c0", s.dbf.chroma[0].data(), s.dbf.chroma[0].size() * 8);
     s.cap.add("dbfrec_c1", s.dbf.chroma[1].data(), s.dbf.chroma[1].size() * 8);
+    if (s.dbf.hasLadf) s.cap.add("dbf_ladf", &s.dbf.ladf, sizeof(s.dbf.ladf));
   }
   s.tic();
   if (s.useRef)

@@ -32,6 +32,7 @@ vtmgpu_deblock_params FlatDeblock::view() const
     p.luma[d]   = luma[d].data();
     p.chroma[d] = chroma[d].empty() ? nullptr : chroma[d].data();
   }
+  p.ladf = hasLadf ? &ladf : nullptr;
   return p;
 }
 
@@ -43,6 +44,7 @@ vtmgpu_deblock_sparse FlatDeblock::sparseView() const
     p.luma[d]   = lists.luma[d].data();   p.luma_count[d]   = (uint32_t)lists.luma[d].size();
     p.chroma[d] = lists.chroma[d].data(); p.chroma_count[d] = (uint32_t)lists.chroma[d].size();
   }
+  p.ladf = hasLadf ? &ladf : nullptr;
   return p;
 }
 
@@ -169,7 +171,17 @@ void Deriver::run()
   const int W = m_pcv.lumaWidth, H = m_pcv.lumaHeight;
   CHECK(m_pcv.maxCUWidth > 128 || m_pcv.minCUWidth != 4 || m_pcv.minCUHeight != 4, "vtmgpu shim: unsupported CTU / min CU size");
   CHECK(m_cs.picHeader->getLoopFilterAcrossVirtualBoundariesDisabledFlag(), "vtmgpu shim: signalled virtual boundaries are not supported");
-  CHECK(m_cs.sps->getLadfEnabled(), "vtmgpu shim: LADF (sample dependent deblocking QP) is not supported");
+  m_out.hasLadf = m_cs.sps->getLadfEnabled();
+  if (m_out.hasLadf)
+  {
+    m_out.ladf = vtmgpu_ladf{};
+    m_out.ladf.num_intervals = m_cs.sps->getLadfNumIntervals();
+    for (int k = 0; k < m_out.ladf.num_intervals && k < 5; k++)
+    {
+      m_out.ladf.qp_offset[k] = m_cs.sps->getLadfQpOffset(k);
+      m_out.ladf.lower_bound[k] = m_cs.sps->getLadfIntervalLowerBound(k);
+    }
+  }
   m_out.width = W; m_out.height = H; m_out.sx = m_sx; m_out.sy = m_sy;
   const bool chroma = m_pcv.chrFormat != CHROMA_400;
   const int gx = 8 << m_sx, gy = 8 << m_sy;
@@ -450,8 +462,15 @@ void Deriver::emitLuma(const CodingUnit& cu, int edge)
     const bool ctuRow = m_dir == HOR && pos.y % (int)slice.getSPS()->getCTUSize() == 0;
     const int iTc = Clip3(0, MAX_QP + 2, qp + 2 * (int(bs) - 1) + tcOff);
     const int iB  = Clip3(0, MAX_QP, qp + betaOff);
-    const unsigned tc   = bd < 10 ? (kTc[iTc] + 2) >> (10 - bd) : kTc[iTc] << (bd - 10);
-    const unsigned beta = kBeta[iB] << (bd - 8);
+    unsigned tc   = bd < 10 ? (kTc[iTc] + 2) >> (10 - bd) : kTc[iTc] << (bd - 10);
+    unsigned beta = kBeta[iB] << (bd - 8);
+    if (sps.getLadfEnabled())
+    {
+      // LADF: the QP offset depends on reconstructed samples (deriveLADFShift, LoopFilter.cpp:815-841) -> the record carries
+      // the QPs before the offset and the device derives tc / beta (include/vtmgpu.h, vtmgpu_ladf)
+      tc   = VTMGPU_DBF_LADF_BIAS + qp + 2 * (int(bs) - 1) + tcOff;
+      beta = VTMGPU_DBF_LADF_BIAS + qp + betaOff;
+    }
     CHECK(tc > 0x7ff || beta > 0x7ff, "vtmgpu shim: tc/beta out of record range");
     uint32_t rec = tc | (beta << VTMGPU_DBF_L_BETA_SHIFT) | (uint32_t(lp) << VTMGPU_DBF_L_LENP_SHIFT) | (uint32_t(lq) << VTMGPU_DBF_L_LENQ_SHIFT);
     if (sps.getPLTMode())

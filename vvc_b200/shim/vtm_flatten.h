@@ -20,6 +20,8 @@ struct FlatDeblock
   int width = 0, height = 0, sx = 0, sy = 0;
   std::vector<uint32_t> luma[2];
   std::vector<uint64_t> chroma[2];
+  bool hasLadf = false;             // SPS LADF: the luma records carry QPs, see vtmgpu_ladf
+  vtmgpu_ladf ladf{};
   vtmgpu_deblock_params view() const;
   // the same records as lists of the active units (vtmgpu_deblock_sparse), appended by the CU walk; listsValid is false when a
   // unit was emitted twice (the dense arrays, where the later record wins, are authoritative then)

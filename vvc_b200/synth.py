@@ -189,9 +189,10 @@ def _plane(rng, h, w, bd, phase):
 
 
 def make_picture(width, height, chroma_format=1, bit_depth=10, ctu_size=128, seed=0, density=0.6, p_split=0.55,
-                 dbf=True, sao=True, alf=True, partitions=False):
+                 dbf=True, sao=True, alf=True, partitions=False, ladf=False):
     """Returns a Capture (pre planes + side info, no reference stage outputs).  partitions: random per-CTU ALF clip / corner-pad
-    flags as slice and tile boundaries without cross-boundary filtering produce them (any combination is a legal input)."""
+    flags as slice and tile boundaries without cross-boundary filtering produce them (any combination is a legal input).
+    ladf: the luma deblocking records carry QPs and the sequence has LADF intervals (include/vtmgpu.h, vtmgpu_ladf)."""
     assert width % 8 == 0 and height % 8 == 0
     rng = np.random.default_rng(seed)
     sx, sy = abi.chroma_shifts(chroma_format)
@@ -205,6 +206,19 @@ def make_picture(width, height, chroma_format=1, bit_depth=10, ctu_size=128, see
             sec["pre_%d" % c] = _plane(rng, height >> sy, width >> sx, bit_depth, seed + 3 * c).tobytes()
     size = _quadtree(rng, width, height, ctu_size, p_split)
     luma, chroma = _records(rng, size, width, height, ctu_size, sx, sy, density if dbf else 0.0, bit_depth)
+    if ladf:
+        lrng = np.random.default_rng(seed + 555)
+        for d in range(2):
+            n = luma[d].size
+            qp_tc = lrng.integers(8, 70, size=n).astype(np.uint32)
+            qp_b = (qp_tc.astype(np.int64) + lrng.integers(-6, 7, size=n)).clip(0, 80).astype(np.uint32)
+            rec = (luma[d] & np.uint32(~0x3FFFFF & 0xFFFFFFFF)) | (qp_tc + abi.DBF_LADF_BIAS) | ((qp_b + abi.DBF_LADF_BIAS) << 11)
+            luma[d] = np.where(luma[d] != 0, rec, 0).astype(np.uint32)
+        full = 1 << bit_depth
+        nint = int(lrng.integers(2, 6))
+        offs = [int(v) for v in lrng.integers(-6, 7, size=5)]
+        lbs = [0] + sorted(int(v) for v in lrng.integers(full // 8, full - full // 8, size=4))
+        sec["dbf_ladf"] = np.array([nint] + offs + lbs, dtype=np.int32).tobytes()
     for d in range(2):
         sec["dbfrec_l%d" % d] = luma[d].tobytes()
         sec["dbfrec_c%d" % d] = chroma[d].tobytes() if ncomp == 3 else b""
