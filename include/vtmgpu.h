@@ -171,10 +171,22 @@ typedef struct vtmgpu_sao_ctu
   uint8_t reserved;
 } vtmgpu_sao_ctu;
 
+/* Virtual boundaries signalled in the picture header with loop_filter_across_virtual_boundaries_disabled_flag (a tool for
+ * 360-degree video; positions are multiples of 8 luma samples, at least one CTU apart, strictly inside the picture).  Deblocking
+ * drops the edges on them on the host (xDeriveEdgefilterParam, LoopFilter.cpp:435-452); SAO skips the edge-offset samples next
+ * to a boundary its class looks across (isProcessDisabled, SampleAdaptiveOffset.h:96); ALF treats every part of a CTU between
+ * boundaries as a separately padded block (ALFProcess :452-490). */
+typedef struct vtmgpu_virtual_boundaries
+{
+  int32_t num_ver, num_hor;    /* 0..3 each                                                     */
+  int32_t pos_x[3], pos_y[3];  /* luma samples                                                  */
+} vtmgpu_virtual_boundaries;
+
 typedef struct vtmgpu_sao_params
 {
   const vtmgpu_sao_ctu* ctu;   /* [ctus], raster; ALREADY reconstructed (vtmgpu_sao_reconstruct)    */
   int32_t num_ctus;
+  const vtmgpu_virtual_boundaries* vb;   /* NULL: none                                         */
 } vtmgpu_sao_params;
 
 /* ---------------------------------------------------------------------------------------------
@@ -232,6 +244,7 @@ typedef struct vtmgpu_alf_params
   int32_t num_ctus;
   const uint8_t* ctu_clip;              /* [ctus] VTMGPU_ALF_CLIP_* / PAD_*, or NULL: picture partition boundaries that the
                                            filter must not cross (isCrossedByVirtualBoundaries, AdaptiveLoopFilter.cpp:79-202) */
+  const vtmgpu_virtual_boundaries* vb;  /* signalled virtual boundaries, or NULL                                             */
 } vtmgpu_alf_params;
 
 /* ---------------------------------------------------------------------------------------------
@@ -241,7 +254,7 @@ typedef struct vtmgpu_ctx vtmgpu_ctx;
 
 int          vtmgpu_abi_version(void);
 int          vtmgpu_abi_sizeof(int which);   /* sizeof of ABI struct #which (0 seq, 1 deblock, 2 sao_offset, 3 sao_ctu, 4 sao_params,
-                                                5 alf_luma_aps, 6 alf_chroma_aps, 7 alf_params, 8 deblock_sparse, 9 ladf) for binding self-checks */
+                                                5 alf_luma_aps, 6 alf_chroma_aps, 7 alf_params, 8 deblock_sparse, 9 ladf, 10 virtual_boundaries) for binding self-checks */
 const char*  vtmgpu_last_error(const vtmgpu_ctx* ctx);   /* ctx may be NULL: error of the last failed create */
 
 int  vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out);

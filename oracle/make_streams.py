@@ -62,6 +62,10 @@ STREAMS = {
                                                                   "--DisableLoopFilterAcrossTiles=0"], 0),     # slice 0 ends mid tile row: bottom-right corner padding
     # LADF (luma adaptive deblocking QP offset): tc / beta depend on reconstructed samples next to the edge
     "ladf_832x480": (832, 480, 420, 5, 34, 14, 32, [RA], K + ["--LADF=1"], 0),
+    # signalled virtual boundaries (360-degree video tool): no in-loop filtering across x = 200 (inside a CTU), x = 512 (a CTU
+    # boundary), y = 248 (4 rows above the ALF virtual boundary of its CTU row), y = 384 (a CTU boundary)
+    "vb_832x480": (832, 480, 420, 5, 35, 14, 32, [RA], K + ["--LoopFilterAcrossVirtualBoundariesDisabledFlag=1", "--NumVerVirtualBoundaries=2",
+                                                            "--NumHorVirtualBoundaries=2", "--VirtualBoundariesPosX=200,512", "--VirtualBoundariesPosY=248,384"], 0),
     # short 4K clip for fast turnaround (first 8 pictures of the config-3 source)
     "ra_2160p_8":   (3840, 2160, 420, 8, 9160, 14, 32, [RA], K, 0),
 }

@@ -71,10 +71,10 @@ def sao_reconstruct(ctus, width_in_ctus, ncomp, scale_luma, scale_chroma):
     return rc
 
 
-def sao(seq, planes, ctus):
-    """ctus: RECONSTRUCTED (abi.SaoCtu * n)."""
+def sao(seq, planes, ctus, vb=None):
+    """ctus: RECONSTRUCTED (abi.SaoCtu * n); vb: abi.VirtualBoundaries or None."""
     ptrs, strides = _planes(planes)
-    p = abi.SaoParams(C.cast(ctus, C.POINTER(abi.SaoCtu)), len(ctus))
+    p = abi.SaoParams(C.cast(ctus, C.POINTER(abi.SaoCtu)), len(ctus), C.pointer(vb) if vb is not None else None)
     rc = lib().vvco_sao(ptrs, strides, *_seq(seq), seq["ctu_size"], C.byref(p))
     if rc:
         raise RuntimeError("vvco_sao rc=%d" % rc)
@@ -97,7 +97,7 @@ def filter_capture(cap, stages=("dbf", "sao", "alf")):
     ctus = cap.sao_ctus()
     if "sao" in stages and ctus is not None:
         sao_reconstruct(ctus, cap.width_in_ctus, cap.ncomp, cap.sao_scale[0], cap.sao_scale[1])
-        sao(cap.seq, planes, ctus)
+        sao(cap.seq, planes, ctus, cap.vb_struct())
         out["sao"] = [p.copy() for p in planes]
     ap = cap.alf_params()
     if "alf" in stages and ap is not None:

@@ -454,6 +454,15 @@ int vvco_sao(int16_t* const plane[3], const ptrdiff_t stride[3], int width, int 
         }
         const int* d = nb[o->type];
         int ok = 1, e = 0;
+        if (p->vb)
+        {
+          /* isProcessDisabled (SampleAdaptiveOffset.h:96-116): classes that look across a vertical / horizontal boundary leave the
+           * two samples next to it untouched (EO 0: vertical boundaries only, :319; EO 90: horizontal only, :362; diagonals: both) */
+          if (o->type != VTMGPU_SAO_EO_90)
+            for (int i = 0; i < p->vb->num_ver; i++) { const int b = p->vb->pos_x[i] >> csx; if (x == b || x == b - 1) ok = 0; }
+          if (o->type != VTMGPU_SAO_EO_0)
+            for (int i = 0; i < p->vb->num_hor; i++) { const int b = p->vb->pos_y[i] >> csy; if (y == b || y == b - 1) ok = 0; }
+        }
         for (int k = 0; k < 2 && ok; k++)
         {
           const int nx = x + d[2 * k], ny = y + d[2 * k + 1];
@@ -630,14 +639,45 @@ int vvco_alf(int16_t* const plane[3], const ptrdiff_t stride[3], int width, int 
       const int a = cy * wctu + cx;
       const int x0 = cx * ctu_size, y0 = cy * ctu_size;
       const int x1 = x0 + ctu_size < width ? x0 + ctu_size : width, y1 = y0 + ctu_size < height ? y0 + ctu_size : height;
-      const int clip = p->ctu_clip ? p->ctu_clip[a] : 0;
-      for (int c = 0; c < ncomp; c++) alf_window(&S[c], x0 >> (c ? sx : 0), y0 >> (c ? sy : 0), x1 >> (c ? sx : 0), y1 >> (c ? sy : 0), clip);
+      const int clip0 = p->ctu_clip ? p->ctu_clip[a] : 0;
+      /* virtual boundaries strictly inside the CTU split it into up to 2 x 2 separately padded parts; one that coincides with a
+       * CTU edge clips that side (isCrossedByVirtualBoundaries :86-120, sub-block loop :452-477) */
+      int xs[3] = { x0, x1, x1 }, ys[3] = { y0, y1, y1 }, nxs = 1, nys = 1, clipv = 0;
+      if (p->vb)
+      {
+        for (int i = 0; i < p->vb->num_ver; i++)
+        {
+          const int b = p->vb->pos_x[i];
+          if (b == x0) clipv |= VTMGPU_ALF_CLIP_LEFT; else if (b == x1) clipv |= VTMGPU_ALF_CLIP_RIGHT;
+          else if (b > x0 && b < x1) { xs[1] = b; xs[2] = x1; nxs = 2; }
+        }
+        for (int i = 0; i < p->vb->num_hor; i++)
+        {
+          const int b = p->vb->pos_y[i];
+          if (b == y0) clipv |= VTMGPU_ALF_CLIP_TOP; else if (b == y1) clipv |= VTMGPU_ALF_CLIP_BOTTOM;
+          else if (b > y0 && b < y1) { ys[1] = b; ys[2] = y1; nys = 2; }
+        }
+      }
+      for (int pj = 0; pj < nys && !rc; pj++)
+      for (int pi = 0; pi < nxs && !rc; pi++)
+      {
+      const int px0 = xs[pi], px1 = xs[pi + 1], py0 = ys[pj], py1 = ys[pj + 1];
+      int clip = (clip0 | clipv) & 15;
+      if (pi > 0) clip |= VTMGPU_ALF_CLIP_LEFT;
+      if (pi < nxs - 1) clip |= VTMGPU_ALF_CLIP_RIGHT;
+      if (pj > 0) clip |= VTMGPU_ALF_CLIP_TOP;
+      if (pj < nys - 1) clip |= VTMGPU_ALF_CLIP_BOTTOM;
+      /* raster-slice corner padding applies to the part that holds the CTU's corner (:478-488); the reference derives the pad
+       * flags only when the corresponding sides are not clipped, virtual boundaries included (:178-200) */
+      if ((clip0 & VTMGPU_ALF_PAD_TL) && pi == 0 && pj == 0 && !(clipv & (VTMGPU_ALF_CLIP_TOP | VTMGPU_ALF_CLIP_LEFT))) clip |= VTMGPU_ALF_PAD_TL;
+      if ((clip0 & VTMGPU_ALF_PAD_BR) && pi == nxs - 1 && pj == nys - 1 && !(clipv & (VTMGPU_ALF_CLIP_BOTTOM | VTMGPU_ALF_CLIP_RIGHT))) clip |= VTMGPU_ALF_PAD_BR;
+      for (int c = 0; c < ncomp; c++) alf_window(&S[c], px0 >> (c ? sx : 0), py0 >> (c ? sy : 0), px1 >> (c ? sx : 0), py1 >> (c ? sy : 0), clip);
       if (p->ctu_enable[0][a])
       {
         const int set = p->ctu_filter_idx[a];
         if (set != cur_set) { rc = vvco_alf_luma_set(p, set, bd_luma, lc, lk); cur_set = set; if (rc) break; }
-        for (int by = y0; by < y1; by += 4)
-          for (int bx = x0; bx < x1; bx += 4)
+        for (int by = py0; by < py1; by += 4)
+          for (int bx = px0; bx < px1; bx += 4)
           {
             int cls, tr;
             alf_classify(&S[0], bx, by, bd_luma, ctu_size, &cls, &tr);
@@ -659,16 +699,16 @@ int vvco_alf(int16_t* const plane[3], const ptrdiff_t stride[3], int width, int 
             cc[k] = p->chroma_aps->coeff[alt][k];
             ck[k] = (int16_t)clipc[p->chroma_aps->nonlinear ? p->chroma_aps->clip_idx[alt][k] : 0];
           }
-          for (int y = y0 >> sy; y < (y1 >> sy); y++)
-            for (int x = x0 >> sx; x < (x1 >> sx); x++)
+          for (int y = py0 >> sy; y < (py1 >> sy); y++)
+            for (int x = px0 >> sx; x < (px1 >> sx); x++)
               plane[c][y * stride[c] + x] = (pel)alf_sample(&S[c], x, y, 6, tap5, cc, ck, 0, vbh, vbp, maxv);
         }
         if (p->ccalf_enabled[c - 1] && p->ccalf_idc[c - 1][a] != 0)
         {
           const int16_t* f = p->ccalf_coeff[c - 1][p->ccalf_idc[c - 1][a] - 1];
           const int half = (1 << bd_chroma) >> 1;
-          for (int y = y0 >> sy; y < (y1 >> sy); y++)
-            for (int x = x0 >> sx; x < (x1 >> sx); x++)
+          for (int y = py0 >> sy; y < (py1 >> sy); y++)
+            for (int x = px0 >> sx; x < (px1 >> sx); x++)
             {
               const int lx = x << sx, ly = y << sy, pos = ly & (ctu_size - 1), vb = ctu_size - 4;
               int o1 = 1, o2 = -1, o3 = 2;
@@ -684,6 +724,7 @@ int vvco_alf(int16_t* const plane[3], const ptrdiff_t stride[3], int width, int 
               *d = (pel)clip3(0, maxv, sum + *d);
             }
         }
+      }
       }
     }
   for (int c = 0; c < 3; c++) free(copy[c]);

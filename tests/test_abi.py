@@ -33,7 +33,7 @@ def test_exports_every_declared_symbol(lib):
 
 
 def test_struct_sizes(lib):
-    mirrors = [abi.SeqParams, abi.DeblockParams, abi.SaoOffset, abi.SaoCtu, abi.SaoParams, abi.AlfLumaAps, abi.AlfChromaAps, abi.AlfParams, abi.DeblockSparse, abi.Ladf]
+    mirrors = [abi.SeqParams, abi.DeblockParams, abi.SaoOffset, abi.SaoCtu, abi.SaoParams, abi.AlfLumaAps, abi.AlfChromaAps, abi.AlfParams, abi.DeblockSparse, abi.Ladf, abi.VirtualBoundaries]
     for i, m in enumerate(mirrors):
         assert lib.vtmgpu_abi_sizeof(i) == C.sizeof(m), m.__name__
 

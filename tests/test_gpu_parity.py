@@ -101,6 +101,29 @@ def test_ladf_vs_oracle(w, h, cf, bd):
     ctx.close()
 
 
+VB_CASES = [
+    # width, height, chroma_format, ctu, vertical boundaries, horizontal boundaries, partitions
+    (512, 384, 1, 128, [200, 384], [248], False),         # inside a CTU / on a CTU edge; 4 rows above the ALF boundary of the CTU row
+    (512, 384, 1, 128, [64, 256], [128, 320], True),      # on tile edges inside a CTU, on CTU edges, combined with slice / tile clipping
+    (456, 264, 3, 128, [8, 448], [256], False),           # 4:4:4, next to the picture border, last (partial) tile
+    (448, 256, 2, 64, [40, 104, 232], [24, 120, 184], False),   # 4:2:2, CTU 64, three per direction, 2 x 2 parts in one tile
+    (320, 320, 0, 64, [160], [], False),                  # 4:0:0
+    (1920, 1080, 1, 128, [960], [544], False),
+]
+
+
+@pytest.mark.parametrize("w,h,cf,ctu,vx,vy,parts", VB_CASES)
+def test_virtual_boundaries_vs_oracle(w, h, cf, ctu, vx, vy, parts):
+    """Signalled virtual boundaries (picture header): SAO leaves the samples next to them alone for the edge classes that look
+    across, ALF pads every part of a CTU between boundaries separately (tiles cut by a boundary are filtered part by part)."""
+    cap = synth.make_picture(w, h, chroma_format=cf, ctu_size=ctu, seed=5 * w + cf, density=1.0, partitions=parts, vb=(vx, vy))
+    want = pyoracle.filter_capture(cap)
+    got = gpu.execute_loop_filters(cap, fused=False)
+    _eq(got["sao"], want["sao"], "SAO with virtual boundaries")
+    _eq(got["alf"], want["alf"], "ALF with virtual boundaries")
+    _eq(gpu.execute_loop_filters(cap, fused=True)["final"], want["final"], "fused chain")
+
+
 def test_stage_switches():
     """NULL side info switches a stage off: the picture must pass through unchanged."""
     cap = synth.make_picture(256, 128, seed=5)
@@ -207,7 +230,8 @@ def test_bad_arguments_fail_loudly():
 STREAMS = [("ra_416x240.bin", 8), ("ld444_1080p.bin", 16), ("ra_1080p.bin", 32), ("ai_4320p.bin", 1),
            # tiles / raster-scan slices with in-loop filtering across their boundaries disabled
            ("tiles_832x480.bin", 5), ("slices_832x480.bin", 5), ("slices45_832x480.bin", 3),
-           ("ladf_832x480.bin", 5)]       # LADF: deblocking thresholds derived on the device
+           ("ladf_832x480.bin", 5),       # LADF: deblocking thresholds derived on the device
+           ("vb_832x480.bin", 5)]         # signalled virtual boundaries inside CTUs and on CTU edges
 
 
 @pytest.mark.parametrize("stream,pictures", STREAMS)

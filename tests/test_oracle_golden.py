@@ -31,7 +31,7 @@ def test_oracle_stage_by_stage(name):
         planes = [p.copy() for p in prev]
         ctus = cap.sao_ctus()
         pyoracle.sao_reconstruct(ctus, cap.width_in_ctus, cap.ncomp, *cap.sao_scale)
-        pyoracle.sao(cap.seq, planes, ctus)
+        pyoracle.sao(cap.seq, planes, ctus, cap.vb_struct())
         for c in range(cap.ncomp):
             assert np.array_equal(planes[c], cap.stage["sao"][c]), "SAO differs in component %d" % c
         prev = cap.stage["sao"]

@@ -36,6 +36,7 @@ SELECT = {
     "tiles_832x480": [0, 2],           # 4x4 tiles, no in-loop filtering across tile boundaries (ALF clip path, SAO availability)
     "slices45_832x480": [0],           # slices of 4 + 5 tiles: bottom-right corner padding
     "ladf_832x480": [0, 2],            # LADF: luma records carry QPs, thresholds derived from the samples
+    "vb_832x480": [0, 2],              # signalled virtual boundaries inside CTUs and on CTU edges
     "slices_832x480": [0, 3],          # 3x3 tiles in two raster-scan slices, no filtering across slices (ALF corner padding)
 }
 

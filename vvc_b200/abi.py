@@ -70,8 +70,12 @@ class SaoCtu(C.Structure):
                 ("merge_above_ok", C.c_uint8), ("reserved", C.c_uint8)]
 
 
+class VirtualBoundaries(C.Structure):
+    _fields_ = [("num_ver", C.c_int32), ("num_hor", C.c_int32), ("pos_x", C.c_int32 * 3), ("pos_y", C.c_int32 * 3)]
+
+
 class SaoParams(C.Structure):
-    _fields_ = [("ctu", C.POINTER(SaoCtu)), ("num_ctus", C.c_int32)]
+    _fields_ = [("ctu", C.POINTER(SaoCtu)), ("num_ctus", C.c_int32), ("vb", C.POINTER(VirtualBoundaries))]
 
 
 class AlfLumaAps(C.Structure):
@@ -92,7 +96,8 @@ class AlfParams(C.Structure):
                 ("ctu_enable", C.POINTER(C.c_uint8) * 3), ("ctu_filter_idx", C.POINTER(C.c_int16)),
                 ("ctu_alt", C.POINTER(C.c_uint8) * 2), ("ccalf_enabled", C.c_int32 * 2),
                 ("ccalf_coeff", ((C.c_int16 * CCALF_COEFF) * CCALF_MAX_FILTERS) * 2),
-                ("ccalf_idc", C.POINTER(C.c_uint8) * 2), ("num_ctus", C.c_int32), ("ctu_clip", C.POINTER(C.c_uint8))]
+                ("ccalf_idc", C.POINTER(C.c_uint8) * 2), ("num_ctus", C.c_int32), ("ctu_clip", C.POINTER(C.c_uint8)),
+                ("vb", C.POINTER(VirtualBoundaries))]
 
 
 ALF_CLIP_TOP, ALF_CLIP_BOTTOM, ALF_CLIP_LEFT, ALF_CLIP_RIGHT, ALF_PAD_TL, ALF_PAD_BR = 1, 2, 4, 8, 16, 32

@@ -44,6 +44,7 @@ class Capture:
         self.dbf_luma = [np.frombuffer(s["dbfrec_l%d" % d], dtype=np.uint32).copy() for d in range(2)]
         self.dbf_chroma = [np.frombuffer(s["dbfrec_c%d" % d], dtype=np.uint64).copy() for d in range(2)]
         self.ladf = np.frombuffer(s["dbf_ladf"], dtype=np.int32).copy() if s.get("dbf_ladf") else None    # vtmgpu_ladf as 11 int32
+        self.vb = np.frombuffer(s["vb"], dtype=np.int32).copy() if s.get("vb") else None          # vtmgpu_virtual_boundaries as 8 int32
         self.sao_raw = bytes(s["sao_raw"]) if "sao_raw" in s else None
         self.sao_scale = [int(v) for v in np.frombuffer(s["sao_scale"], dtype=np.int32)] if "sao_scale" in s else [0, 0]
         self.alf = None
@@ -101,6 +102,10 @@ class Capture:
         p._keep = keep
         return p
 
+    def vb_struct(self):
+        """abi.VirtualBoundaries signalled for the picture, or None."""
+        return abi.VirtualBoundaries.from_buffer_copy(self.vb.tobytes()) if self.vb is not None else None
+
     def ladf_struct(self):
         """abi.Ladf of the sequence, or None when LADF is off (then the luma records carry tc / beta)."""
         return abi.Ladf.from_buffer_copy(self.ladf.tobytes()) if self.ladf is not None else None
@@ -143,6 +148,10 @@ class Capture:
         p.num_ctus = a["num_ctus"]
         if a.get("clip") is not None:
             p.ctu_clip = a["clip"].ctypes.data_as(C.POINTER(C.c_uint8))
+        vb = self.vb_struct()
+        if vb is not None:
+            keep.append(vb)
+            p.vb = C.pointer(vb)
         p._keep = keep + [a]
         return p
 

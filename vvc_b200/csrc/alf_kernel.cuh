@@ -101,7 +101,7 @@ __device__ __noinline__ void saReplicateBorder(pel* s, int bx0, int by0, int xlo
     else
     {
       const int lane = threadIdx.x & 31;
-      if (lane < nl) drow[xl + lane] = srow[xlo];
+      for (int cc = lane; cc < nl; cc += 32) drow[xl + cc] = srow[xlo];
       for (int cc = cr + lane; cc < cols; cc += 32) drow[xl + cc] = srow[xhi - 1];
     }
   }
@@ -129,6 +129,44 @@ __device__ __forceinline__ void saPadCorners(pel* s, int bx0, int by0, int cx0, 
     pel* row = s + (cy1 + dy - by0) * pitch - bx0;
     row[cx1 + dx] = row[cx1 - 1];
   }
+}
+
+// signalled virtual boundaries (cold path, kept out of line): cuts strictly inside the tile, and whether any boundary touches it
+__device__ __noinline__ int saVbCuts(const VbDev* v, int x0, int y0, int tileW, int tileH)
+{
+  int cutX = 0, cutY = 0, touch = 0;
+#pragma unroll 1
+  for (int i = 0; i < v->nv; i++) { const int b = v->x[i]; if (b > x0 && b < x0 + tileW) cutX = b; touch |= b >= x0 && b <= x0 + tileW; }
+#pragma unroll 1
+  for (int i = 0; i < v->nh; i++) { const int b = v->y[i]; if (b > y0 && b < y0 + tileH) cutY = b; touch |= b >= y0 && b <= y0 + tileH; }
+  return cutX | cutY << 14 | touch << 28;                 // positions < 2^14
+}
+
+// a virtual boundary on an edge of the part (tile edge, CTU edge or the cut) closes that side of the clamp window win = {xlo, xhi,
+// ylo, yhi}; the raster-slice corner pads belong to the part that holds the CTU's corner and are dropped when a virtual boundary
+// clips that corner's sides (isCrossedByVirtualBoundaries :178-200).  Returns the pad flags that remain.
+__device__ __noinline__ int saVbWindow(const VbDev* v, int4 part, int4 ctu, bool first, bool last, int pad, int* win)
+{
+  bool cL = false, cR = false, cT = false, cB = false;
+#pragma unroll 1
+  for (int i = 0; i < v->nv; i++)
+  {
+    const int b = v->x[i];
+    if (b == part.x) win[0] = b;
+    if (b == part.y) win[1] = b;
+    cL |= b == ctu.x; cR |= b == ctu.y;
+  }
+#pragma unroll 1
+  for (int i = 0; i < v->nh; i++)
+  {
+    const int b = v->y[i];
+    if (b == part.z) win[2] = b;
+    if (b == part.w) win[3] = b;
+    cT |= b == ctu.z; cB |= b == ctu.w;
+  }
+  if (!first || cL || cT) pad &= ~VTMGPU_ALF_PAD_TL;
+  if (!last || cR || cB) pad &= ~VTMGPU_ALF_PAD_BR;
+  return pad;
 }
 
 // ---- ALF: generic scalar routines (virtual-boundary rows, halo cells, wide coefficients, non-4:2:0 CC-ALF) ----------
@@ -483,9 +521,12 @@ __device__ __forceinline__ void saPrefetch(unsigned char* smraw, const SaLayout&
   if (tid == 32) cpAsync16(reinterpret_cast<CtuCtlDev*>(smraw + L.offPar) + stage, &S.ctuCtl[(y0 >> g.ctuLog2) * g.wCtus + (x0 >> g.ctuLog2)]);
 }
 
+// kVirtualBoundaries = false compiles the part loop of signalled virtual boundaries away (it costs the common path 10 % otherwise);
+// the host launches the <true> instantiation only for batches that contain a picture with virtual boundaries.
 // Persistent kernel: gridDim.x CTAs walk the tiles of slots [firstSlot, firstSlot + numSlots) round robin; while a CTA
 // filters tile i, the TMA loads of tile i+1 are in flight (two stages).  maps = tensor maps of the source buffer of the
 // first slot: [slot][3 buffers][3 planes].
+template <bool kVirtualBoundaries>
 __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDev* __restrict__ slots, const CUtensorMap* __restrict__ tmaps, int firstSlot, int numSlots,
                                                            int srcBuf, int dstBuf, Geom g, int tilesX, int tilesY, int ty0, SaStep step)
 {
@@ -497,7 +538,7 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDe
   const int vbL = g.ctu - 4, ctuMask = g.ctu - 1;
   const int bi = tid >> 4, bj = tid & 15;
   const int tw = SA_T >> g.sx, th = SA_TH >> g.sy, thLogC = SA_THLOG - g.sy;
-  const int cw = g.w >> g.sx, chh = g.h >> g.sy, ctuH = g.ctu >> g.sy;
+  const int ctuH = g.ctu >> g.sy;
   const int vbC = ctuH - 2, maxc = (1 << g.bdC) - 1, half = (1 << g.bdC) >> 1;
   const uint32_t maxcP = dup16(maxc), halfP = dup16(half);
 
@@ -546,33 +587,66 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDe
     pel* const A0 = reinterpret_cast<pel*>(smraw + L.offA(stage, 0));
     pel* const A1 = reinterpret_cast<pel*>(smraw + L.offA(stage, 1));
     pel* const A2 = reinterpret_cast<pel*>(smraw + L.offA(stage, 2));
-    // tiles on the picture border: replicate the border samples into the zero-filled outside
-    // (= UnitBuf::extendBorderPel of the ALF input, AdaptiveLoopFilter.cpp:411); tiles of a CTU with a slice / tile boundary
-    // the filter must not read across: the same replication at the CTU's clipped sides (:452-490)
+    // Parts of the tile.  Normally one: the whole tile.  Signalled virtual boundaries (vtmgpu_virtual_boundaries, multiples of 8
+    // luma samples, at least a CTU apart) cut a tile into up to 2 x 2 parts that the reference filters as separately padded blocks
+    // (ALFProcess :452-490); each part is then filtered from its own padded copy of the tile.
     const int clip = ctl.clip;
-    const bool onBorder = x0 == 0 || y0 == 0 || x0 + SA_T + 8 > g.w || y0 + SA_TH + 8 > g.h || clip != 0;
+    const int tileW = min(SA_T, g.w - x0), tileH = min(SA_TH, g.h - y0);          // the last tile of a row / column may be partial
+    const int cx0 = x0 & ~ctuMask, cy0 = y0 & ~ctuMask, cx1 = min(cx0 + g.ctu, g.w), cy1 = min(cy0 + g.ctu, g.h);
+    const VbDev& pvb = S.vbAlf;
+    const bool anyVb = kVirtualBoundaries && alfOn && (pvb.nv | pvb.nh) != 0;
+    int cutX = 0, cutY = 0;
+    bool vbTile = false;
+    if (anyVb)
+    {
+      const int r = saVbCuts(&pvb, x0, y0, tileW, tileH);
+      cutX = r & 0x3fff; cutY = (r >> 14) & 0x3fff; vbTile = (r >> 28) != 0;
+    }
+    const int nparts = (cutX ? 2 : 1) * (cutY ? 2 : 1);
+    // tiles on the picture border: replicate the border samples into the zero-filled outside
+    // (= UnitBuf::extendBorderPel of the ALF input, AdaptiveLoopFilter.cpp:411); tiles of a CTU with a slice / tile / virtual
+    // boundary the filter must not read across: the same replication at the clipped sides (:452-490)
+    const bool onBorder = x0 == 0 || y0 == 0 || x0 + SA_T + 8 > g.w || y0 + SA_TH + 8 > g.h || clip != 0 || vbTile;
+    const pel* const B0 = A0;
+    const pel* const B1 = A1;
+    const pel* const B2 = A2;
+    const PlaneDev dstY = S.buf[dstBuf][0];
+#pragma unroll 1
+    for (int part = 0; part < nparts; part++)
+    {
+    const int pi = cutX ? (part & 1) : 0, pj = cutX ? (part >> 1) : part;
+    const int px0 = pi ? cutX : x0, px1 = (cutX && !pi) ? cutX : x0 + tileW;      // luma rectangle of this part
+    const int py0 = pj ? cutY : y0, py1 = (cutY && !pj) ? cutY : y0 + tileH;
+    if (nparts > 1)
+    {
+      // the padding of a part overwrites its neighbours' samples: the first part saves the tile, the others start from that copy
+      uint4* stg = reinterpret_cast<uint4*>(smraw + L.offA(stage, 0));
+      uint4* scr = reinterpret_cast<uint4*>(smraw + L.total);
+      const int n16 = (L.lumaBytes + 2 * L.chromaBytes) >> 4;
+      if (part == 0) { for (int i = tid; i < n16; i += SA_THREADS) scr[i] = stg[i]; }
+      else           { for (int i = tid; i < n16; i += SA_THREADS) stg[i] = scr[i]; }
+      __syncthreads();
+    }
     if (onBorder)
     {
-      const int cx0 = x0 & ~ctuMask, cy0 = y0 & ~ctuMask, cx1 = min(cx0 + g.ctu, g.w), cy1 = min(cy0 + g.ctu, g.h);
-      const int xlo = (clip & VTMGPU_ALF_CLIP_LEFT) ? cx0 : 0, xhi = (clip & VTMGPU_ALF_CLIP_RIGHT) ? cx1 : g.w;
-      const int ylo = (clip & VTMGPU_ALF_CLIP_TOP) ? cy0 : 0, yhi = (clip & VTMGPU_ALF_CLIP_BOTTOM) ? cy1 : g.h;
+      int win[4] = { (clip & VTMGPU_ALF_CLIP_LEFT) ? cx0 : 0, (clip & VTMGPU_ALF_CLIP_RIGHT) ? cx1 : g.w,
+                     (clip & VTMGPU_ALF_CLIP_TOP) ? cy0 : 0, (clip & VTMGPU_ALF_CLIP_BOTTOM) ? cy1 : g.h };
+      int pad = clip & (VTMGPU_ALF_PAD_TL | VTMGPU_ALF_PAD_BR);
+      if (anyVb) pad = saVbWindow(&pvb, make_int4(px0, px1, py0, py1), make_int4(cx0, cx1, cy0, cy1), part == 0, part == nparts - 1, pad, win);
+      const int xlo = win[0], xhi = win[1], ylo = win[2], yhi = win[3];
       const int bxc = (x0 >> g.sx) - SA_HX, byc = (y0 >> g.sy) - SA_HY;
       if (alfY || ccCb || ccCr) saReplicateBorder(A0, x0 - SA_HX, y0 - SA_HY, xlo, xhi, ylo, yhi, SA_P, SA_T, SA_TH, 3);
       if (alfCb) saReplicateBorder(A1, bxc, byc, xlo >> g.sx, xhi >> g.sx, ylo >> g.sy, yhi >> g.sy, L.pitchC, tw, th, 3);
       if (alfCr) saReplicateBorder(A2, bxc, byc, xlo >> g.sx, xhi >> g.sx, ylo >> g.sy, yhi >> g.sy, L.pitchC, tw, th, 3);
-      if (clip & (VTMGPU_ALF_PAD_TL | VTMGPU_ALF_PAD_BR))
+      if (pad)
       {
         // no barrier needed in between: the corners lie outside the clamp window's replicated ranges (their sides are not clipped)
-        const int tileW = min(SA_T, g.w - x0), tileH = min(SA_TH, g.h - y0);     // the CTU's last tile may be partial
-        if (alfY || ccCb || ccCr) saPadCorners(A0, x0 - SA_HX, y0 - SA_HY, cx0, cy0, cx1, cy1, SA_P, tileW, tileH, 3, clip);
-        if (alfCb) saPadCorners(A1, bxc, byc, cx0 >> g.sx, cy0 >> g.sy, cx1 >> g.sx, cy1 >> g.sy, L.pitchC, tileW >> g.sx, tileH >> g.sy, 3, clip);
-        if (alfCr) saPadCorners(A2, bxc, byc, cx0 >> g.sx, cy0 >> g.sy, cx1 >> g.sx, cy1 >> g.sy, L.pitchC, tileW >> g.sx, tileH >> g.sy, 3, clip);
+        if (alfY || ccCb || ccCr) saPadCorners(A0, x0 - SA_HX, y0 - SA_HY, cx0, cy0, cx1, cy1, SA_P, tileW, tileH, 3, pad);
+        if (alfCb) saPadCorners(A1, bxc, byc, cx0 >> g.sx, cy0 >> g.sy, cx1 >> g.sx, cy1 >> g.sy, L.pitchC, tileW >> g.sx, tileH >> g.sy, 3, pad);
+        if (alfCr) saPadCorners(A2, bxc, byc, cx0 >> g.sx, cy0 >> g.sy, cx1 >> g.sx, cy1 >> g.sy, L.pitchC, tileW >> g.sx, tileH >> g.sy, 3, pad);
       }
       __syncthreads();
     }
-    const pel* const B0 = A0;
-    const pel* const B1 = A1;
-    const pel* const B2 = A2;
 
     // ---- phase 1: Laplacian cells (luma ALF only) -------------------------------------------------------------------
     const pel* lumaB = B0;
@@ -603,10 +677,9 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDe
     }
 
     // ---- phase 2: filters; every plane is written once ----------------------------------------------------------------
-    const PlaneDev dstY = S.buf[dstBuf][0];
     if (alfY)
     {
-      if (bx < g.w && by < g.h)
+      if (bx >= px0 && bx < px1 && by >= py0 && by < py1)
       {
         pel* out = dstY.p + (size_t)by * dstY.pitch + bx;
         const int setIdx = ctl.setIdx;
@@ -641,14 +714,14 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDe
       {
         const int r = i >> 3, gc = i & 7;
         const int y = y0 + r, x = x0 + 8 * gc;
-        if (y < g.h && x < g.w)
+        if (y >= py0 && y < py1 && x >= px0 && x < px1)
           *reinterpret_cast<int4*>(dstY.p + (size_t)y * dstY.pitch + x) = *reinterpret_cast<const int4*>(&lumaB[(r + SA_HY) * SA_P + 8 * gc + SA_HX]);
       }
     }
     if (g.ncomp > 1)
     {
       // chroma: one item = 4 horizontally adjacent samples
-      const int cx0 = x0 >> g.sx, cy0 = y0 >> g.sy, qShift = 4 - g.sx, quads = (tw >> 2) << thLogC;       // tw / 4 = 1 << qShift
+      const int tcx0 = x0 >> g.sx, tcy0 = y0 >> g.sy, qShift = 4 - g.sx, quads = (tw >> 2) << thLogC;       // tw / 4 = 1 << qShift
 #pragma unroll 1
       for (int c = 0; c < 2; c++)
       {
@@ -662,8 +735,8 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDe
         for (int j = tid; j < quads; j += SA_THREADS)
         {
           const int r = j >> qShift, qx = (j & ((1 << qShift) - 1)) * 4;
-          const int x = cx0 + qx, y = cy0 + r;
-          if (x >= cw || y >= chh) continue;
+          const int x = tcx0 + qx, y = tcy0 + r;
+          if (x < (px0 >> g.sx) || x >= (px1 >> g.sx) || y < (py0 >> g.sy) || y >= (py1 >> g.sy)) continue;
           const pel* cb = &Bc[(r + SA_HY) * L.pitchC + qx + SA_HX];
           uint2 v = *reinterpret_cast<const uint2*>(cb);
           if (fOn)
@@ -708,6 +781,8 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDe
           *reinterpret_cast<uint2*>(dstC.p + (size_t)y * dstC.pitch + x) = v;
         }
       }
+    }
+    if (part + 1 < nparts) __syncthreads();                  // the next part re-pads the tile and recomputes the cells
     }
     __syncthreads();                                         // all reads of stage buffers / B / cells are done before they are refilled
     cur = nxt;

@@ -568,7 +568,8 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
         for (int k = 0; k < 4; k++)
           if (k < nrows) *reinterpret_cast<uint4*>(o + (size_t)k * dst.pitch) = *reinterpret_cast<const uint4*>(a + k * DBF_PITCH);
       }
-      else saoStrip(o, dst.pitch, a, DBF_PITCH, nrows, sx_, sy_, pq, w, h, cwLog | chLog << 8 | (comp ? g.bdC : g.bdL) << 16);
+      else saoStrip(o, dst.pitch, a, DBF_PITCH, nrows, sx_, sy_, pq, w, h, cwLog | chLog << 8 | (comp ? g.bdC : g.bdL) << 16,
+                    (S.vbSao.nv | S.vbSao.nh) ? &S.vbSao : nullptr, comp ? (g.sx | g.sy << 8) : 0);
     }
     if (tid == 0) qcount[0] = qcount[1] = 0;
     __syncthreads();                                         // the stage is free for the load after next

@@ -100,13 +100,38 @@ template <int DXA, int DYA> __device__ __forceinline__ uint4 saoEdge(const pel* 
 
 __device__ __forceinline__ uint32_t laneMask2(uint32_t bits) { return ((bits & 1u) ? 0xffffu : 0u) | ((bits & 2u) ? 0xffff0000u : 0u); }
 
+// lanes of the 8-sample group at (x,y) (component coordinates) that lie next to a signalled virtual boundary the edge class looks
+// across (isProcessDisabled, SampleAdaptiveOffset.h:96-116: EO 0 tests the vertical boundaries only, EO 90 the horizontal ones only,
+// the diagonal classes both; band offset is not affected).  type: 1 = EO 0, 2 = EO 90, 3 = EO 135, 4 = EO 45
+__device__ __noinline__ uint32_t saoVbLanes(const VbDev* vb, int type, int x, int y, int csx, int csy)
+{
+  uint32_t m = 0;
+  if (type != 2)
+#pragma unroll 1
+    for (int i = 0; i < vb->nv; i++)
+    {
+      const int d = (vb->x[i] >> csx) - x;               // lane of the first sample right of the boundary
+      if (d >= 0 && d < 8) m |= 1u << d;
+      if (d >= 1 && d < 9) m |= 1u << (d - 1);
+    }
+  if (type != 1)
+#pragma unroll 1
+    for (int i = 0; i < vb->nh; i++)
+    {
+      const int b = vb->y[i] >> csy;
+      if (y == b || y == b - 1) m = 0xffu;
+    }
+  return m;
+}
+
 // SAO of a vertical strip of nrows 8-sample groups inside ONE CTU (one parameter set pq = the SaoDev as 4 words:
 // .x = type | band << 8 | avail << 16, .y = off0 | off1 << 16, .z = off2 | off3 << 16, .w = off4).
 //   a    deblocked samples of the first group in shared memory (pitch ap samples; the 8-aligned neighbours are resident)
 //   out  destination of the first group in global memory (pitch op samples)
 //   x,y  plane position of the first group; logs = cwLog | chLog << 8 | bitDepth << 16 (CTU size of this plane)
+//   vb   signalled virtual boundaries (NULL: none); csxy = subsampling shifts of this plane, x | y << 8
 // One copy of this code serves every component and tile shape.
-__device__ __noinline__ void saoStrip(pel* out, int op, const pel* a, int ap, int nrows, int x, int y, uint4 pq, int w, int h, int logs)
+__device__ __noinline__ void saoStrip(pel* out, int op, const pel* a, int ap, int nrows, int x, int y, uint4 pq, int w, int h, int logs, const VbDev* vb, int csxy)
 {
   const int cwLog = logs & 0xff, chLog = (logs >> 8) & 0xff, bd = logs >> 16;
   const int type = pq.x & 0xff;
@@ -151,7 +176,8 @@ __device__ __noinline__ void saoStrip(pel* out, int op, const pel* a, int ap, in
     else if (type == 2) o = saoEdge<0, -1>(apk, ap, v, lutLo, lutHi, maxvP);
     else if (type == 3) o = saoEdge<-1, -1>(apk, ap, v, lutLo, lutHi, maxvP);
     else                o = saoEdge<1, -1>(apk, ap, v, lutLo, lutHi, maxvP);
-    const uint32_t skip = saoSkipLanes(x, y + k, dxa, dya, avail, w, h, cwLog, chLog);
+    uint32_t skip = saoSkipLanes(x, y + k, dxa, dya, avail, w, h, cwLog, chLog);
+    if (vb) skip |= saoVbLanes(vb, type, x, y + k, csxy & 0xff, csxy >> 8);
     if (skip)
     {
       const uint32_t m0 = laneMask2(skip), m1 = laneMask2(skip >> 2), m2 = laneMask2(skip >> 4), m3 = laneMask2(skip >> 6);

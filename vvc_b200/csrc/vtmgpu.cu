@@ -137,6 +137,7 @@ extern "C" int vtmgpu_abi_sizeof(int which)
   case 7: return (int)sizeof(vtmgpu_alf_params);
   case 8: return (int)sizeof(vtmgpu_deblock_sparse);
   case 9: return (int)sizeof(vtmgpu_ladf);
+  case 10: return (int)sizeof(vtmgpu_virtual_boundaries);
   default: return -1;
   }
 }
@@ -330,7 +331,11 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
   }
   CK(cudaMemcpyAsync(c->slotsDev, c->slotsPinned, sizeof(SlotDev) * s.capacity, cudaMemcpyHostToDevice, c->stream), "slot table upload");
   CK(cudaFuncSetAttribute(k_dbf_sao, cudaFuncAttributeMaxDynamicSharedMemorySize, DBF_SMEM_BYTES), "smem attribute");
-  CK(cudaFuncSetAttribute(k_alf, cudaFuncAttributeMaxDynamicSharedMemorySize, saLayout(g.sx, g.sy, g.ncomp).total), "smem attribute");
+  {
+    const SaLayout SL = saLayout(g.sx, g.sy, g.ncomp);      // + one more tile: scratch copy for tiles cut by a virtual boundary
+    CK(cudaFuncSetAttribute(k_alf<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL.total), "smem attribute");
+    CK(cudaFuncSetAttribute(k_alf<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL.total + SL.lumaBytes + 2 * SL.chromaBytes), "smem attribute");
+  }
   CK(cudaDeviceGetAttribute(&c->numSms, cudaDevAttrMultiProcessorCount, s.device), "device attribute");
   CK(cudaStreamSynchronize(c->stream), "sync");
 #undef CK
@@ -716,6 +721,32 @@ extern "C" int vtmgpu_sao_reconstruct(vtmgpu_sao_ctu* ctu, int num_ctus, int wid
   return mask;
 }
 
+namespace
+{
+// validates and copies signalled virtual boundaries (multiples of 8 luma samples strictly inside the picture, at least one CTU
+// apart in each direction -- the kernels rely on at most one cut per tile and direction)
+int setVb(vtmgpu_ctx* c, VbDev& d, const vtmgpu_virtual_boundaries* v, const char* who)
+{
+  d = VbDev{};
+  if (!v) return 0;
+  if (v->num_ver < 0 || v->num_ver > 3 || v->num_hor < 0 || v->num_hor > 3) return c->fail("%s: 0..3 virtual boundaries per direction", who);
+  for (int dir = 0; dir < 2; dir++)
+  {
+    const int n = dir ? v->num_hor : v->num_ver, lim = dir ? c->g.h : c->g.w;
+    const int32_t* pos = dir ? v->pos_y : v->pos_x;
+    for (int i = 0; i < n; i++)
+    {
+      if (pos[i] <= 0 || pos[i] >= lim || (pos[i] & 7)) return c->fail("%s: virtual boundary %d is not a multiple of 8 inside the picture", who, pos[i]);
+      for (int j = 0; j < i; j++)
+        if (std::abs(pos[i] - pos[j]) < c->g.ctu) return c->fail("%s: virtual boundaries %d and %d are less than a CTU apart", who, pos[j], pos[i]);
+      (dir ? d.y : d.x)[i] = pos[i];
+    }
+  }
+  d.nv = v->num_ver; d.nh = v->num_hor;
+  return 0;
+}
+}   // namespace
+
 extern "C" int vtmgpu_set_sao(vtmgpu_ctx* c, int slot, const vtmgpu_sao_params* p)
 {
   if (!c) return -1;
@@ -723,6 +754,7 @@ extern "C" int vtmgpu_set_sao(vtmgpu_ctx* c, int slot, const vtmgpu_sao_params* 
   cudaSetDevice(c->seq.device);
   SlotDev& sd = c->slotsPinned[slot];
   sd.saoOn = 0;
+  if (setVb(c, sd.vbSao, p ? p->vb : nullptr, "set_sao")) return -1;
   if (p)
   {
     if (!p->ctu || p->num_ctus != c->nCtus) return c->fail("set_sao: expected %d CTUs, got %d", c->nCtus, p->num_ctus);
@@ -766,6 +798,7 @@ extern "C" int vtmgpu_set_alf(vtmgpu_ctx* c, int slot, const vtmgpu_alf_params* 
   cudaSetDevice(c->seq.device);
   SlotDev& sd = c->slotsPinned[slot];
   sd.alfOn = 0;
+  if (setVb(c, sd.vbAlf, p ? p->vb : nullptr, "set_alf")) return -1;
   if (p)
   {
     const int n = c->nCtus;
@@ -934,16 +967,20 @@ int launchAlf(vtmgpu_ctx* c, int first, int count)
   if (!any) return 0;
   const Geom& g = c->g;
   const int tilesX = (g.w + SA_T - 1) / SA_T, ty0 = c->rowBegin / SA_TH, tilesY = (c->rowEnd + SA_TH - 1) / SA_TH - ty0;
-  const int smem = saLayout(g.sx, g.sy, g.ncomp).total;
+  const SaLayout SL = saLayout(g.sx, g.sy, g.ncomp);
   return forRuns(c, first, count, [&](int s, int n, int src) {
     const int dst = src == 1 ? 2 : 1;
+    bool vb = false;                                             // tiles cut by a virtual boundary need a scratch copy of the tile
+    for (int i = s; i < s + n; i++) vb |= (c->slotsPinned[i].vbAlf.nv | c->slotsPinned[i].vbAlf.nh) != 0;
+    const int smem = SL.total + (vb ? SL.lumaBytes + 2 * SL.chromaBytes : 0);
     // persistent CTAs: four per SM (register limited), each walks the tiles round robin with double-buffered TMA loads
     const int grid = std::min(tilesX * tilesY * n, SA_CTAS_PER_SM * c->numSms);
     SaStep st;
     st.dx = grid % tilesX;
     st.dy = (grid / tilesX) % tilesY;
     st.ds = (grid / tilesX) / tilesY;
-    k_alf<<<grid, SA_THREADS, smem, c->stream>>>(c->slotsDev, c->tmapsDev, s, n, src, dst, g, tilesX, tilesY, ty0, st);
+    if (vb) k_alf<true><<<grid, SA_THREADS, smem, c->stream>>>(c->slotsDev, c->tmapsDev, s, n, src, dst, g, tilesX, tilesY, ty0, st);
+    else    k_alf<false><<<grid, SA_THREADS, smem, c->stream>>>(c->slotsDev, c->tmapsDev, s, n, src, dst, g, tilesX, tilesY, ty0, st);
     c->launches++;
     for (int i = s; i < s + n; i++) c->cur[i] = dst;
     return c->cuda(cudaGetLastError(), "k_alf launch");

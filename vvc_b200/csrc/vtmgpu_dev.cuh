@@ -81,6 +81,11 @@ struct LadfDev                   // vtmgpu_ladf; n = 0: off (the luma records ca
   int32_t n, off[5], lb[5], pad;
 };
 
+struct VbDev                     // vtmgpu_virtual_boundaries (luma sample positions); nv = nh = 0: none
+{
+  int32_t nv, nh, x[3], y[3];
+};
+
 struct SlotDev
 {
   PlaneDev buf[3][3];            // [buffer][component]; buffer 0 = pristine upload, 1/2 = working
@@ -93,6 +98,7 @@ struct SlotDev
   int32_t dbfOn, saoOn, alfOn;   // alfOn: parameters set AND the slice enables ALF for at least one component
   int32_t alfWide;               // a luma coefficient does not fit the s8 operand of IDP.2A: generic path
   LadfDev ladf;
+  VbDev vbSao, vbAlf;            // as given to vtmgpu_set_sao / vtmgpu_set_alf
 };
 
 struct Geom

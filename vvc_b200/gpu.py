@@ -231,12 +231,12 @@ class Context:
         """params: abi.DeblockSparse (see sparse_records); the lists are read asynchronously until the next sync()."""
         self._ck(self.lib.vtmgpu_set_deblock_sparse(self.h, slot, C.byref(params) if params is not None else None), "set_deblock_sparse")
 
-    def set_sao(self, slot, ctus):
-        """ctus: reconstructed (abi.SaoCtu * n) array, or None to switch the stage off."""
+    def set_sao(self, slot, ctus, vb=None):
+        """ctus: reconstructed (abi.SaoCtu * n) array, or None to switch the stage off; vb: abi.VirtualBoundaries or None."""
         if ctus is None:
             self._ck(self.lib.vtmgpu_set_sao(self.h, slot, None), "set_sao")
             return
-        p = abi.SaoParams(C.cast(ctus, C.POINTER(abi.SaoCtu)), len(ctus))
+        p = abi.SaoParams(C.cast(ctus, C.POINTER(abi.SaoCtu)), len(ctus), C.pointer(vb) if vb is not None else None)
         self._ck(self.lib.vtmgpu_set_sao(self.h, slot, C.byref(p)), "set_sao")
 
     def set_alf(self, slot, params):
@@ -250,7 +250,7 @@ class Context:
         ctus = cap.sao_ctus()
         if ctus is not None:
             sao_reconstruct(ctus, cap.width_in_ctus, cap.ncomp, cap.sao_scale[0], cap.sao_scale[1])
-        self.set_sao(slot, ctus)
+        self.set_sao(slot, ctus, cap.vb_struct())
         self.set_alf(slot, cap.alf_params())
 
     # ---- stages ------------------------------------------------------------------------------------------
@@ -342,7 +342,7 @@ class SampleAdaptiveOffset:
         if sao_ctus is None:
             raise VtmGpuError("No parameters present")           # CHECK at SampleAdaptiveOffset.cpp:621
         sao_reconstruct(sao_ctus, pic.cap.width_in_ctus, pic.cap.ncomp, pic.cap.sao_scale[0], pic.cap.sao_scale[1])
-        self.lf.ctx.set_sao(0, sao_ctus)
+        self.lf.ctx.set_sao(0, sao_ctus, pic.cap.vb_struct())
         self.lf.ctx.sao(0, 1)
         self.lf.ctx.download(0, pic.reco)
 

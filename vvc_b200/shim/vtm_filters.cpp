@@ -265,6 +265,8 @@ void LoopFilter::loopFilterPic(CodingStructure& cs)
     s.cap.add("dbfrec_c0", s.dbf.chroma[0].data(), s.dbf.chroma[0].size() * 8);
     s.cap.add("dbfrec_c1", s.dbf.chroma[1].data(), s.dbf.chroma[1].size() * 8);
     if (s.dbf.hasLadf) s.cap.add("dbf_ladf", &s.dbf.ladf, sizeof(s.dbf.ladf));
+    const vtmgpu_virtual_boundaries vb = flattenVirtualBoundaries(cs);
+    if (vb.num_ver || vb.num_hor) s.cap.add("vb", &vb, sizeof(vb));
   }
   s.tic();
   if (s.useRef)

@@ -24,6 +24,19 @@
 namespace vtmshim
 {
 
+vtmgpu_virtual_boundaries flattenVirtualBoundaries(const CodingStructure& cs)
+{
+  vtmgpu_virtual_boundaries v{};
+  const PicHeader* ph = cs.picHeader;
+  if (!ph->getLoopFilterAcrossVirtualBoundariesDisabledFlag()) return v;
+  v.num_ver = (int)ph->getNumVerVirtualBoundaries();
+  v.num_hor = (int)ph->getNumHorVirtualBoundaries();
+  CHECK(v.num_ver > 3 || v.num_hor > 3, "vtmgpu shim: more than 3 virtual boundaries per direction");
+  for (int i = 0; i < v.num_ver; i++) v.pos_x[i] = (int)ph->getVirtualBoundariesPosX(i);
+  for (int i = 0; i < v.num_hor; i++) v.pos_y[i] = (int)ph->getVirtualBoundariesPosY(i);
+  return v;
+}
+
 vtmgpu_deblock_params FlatDeblock::view() const
 {
   vtmgpu_deblock_params p;
@@ -67,6 +80,7 @@ vtmgpu_sao_params FlatSao::view() const
   vtmgpu_sao_params p;
   p.ctu      = ctu.data();
   p.num_ctus = (int)ctu.size();
+  p.vb       = (vb.num_ver || vb.num_hor) ? &vb : nullptr;
   return p;
 }
 
@@ -78,6 +92,7 @@ const vtmgpu_alf_params* FlatAlf::view()
   for (int c = 0; c < 2; c++) { p.ctu_alt[c] = ctuAlt[c].data(); p.ccalf_idc[c] = ccIdc[c].data(); }
   p.ctu_filter_idx = filterIdx.data();
   p.ctu_clip = ctuClip.empty() ? nullptr : ctuClip.data();
+  p.vb = (vb.num_ver || vb.num_hor) ? &vb : nullptr;
   return &p;
 }
 
@@ -123,6 +138,14 @@ private:
   const PreCalcValues& m_pcv;
   FlatDeblock&         m_out;
   FlatDeblock::Lists*  m_lists = nullptr;      // this thread's share of the record lists
+  vtmgpu_virtual_boundaries m_vb{};
+  // xDeriveEdgefilterParam (LoopFilter.cpp:435-452): an edge that lies on a signalled virtual boundary is not filtered
+  bool onVb(int dir, const Area& a) const
+  {
+    if (dir == VER) { for (int i = 0; i < m_vb.num_ver; i++) if (m_vb.pos_x[i] == (int)a.x) return true; }
+    else            { for (int i = 0; i < m_vb.num_hor; i++) if (m_vb.pos_y[i] == (int)a.y) return true; }
+    return false;
+  }
   CtuState             m_st;
   const Slice*         m_ctuSlice = nullptr;   // slice of the first CU of the CTU in flight (what the reference leaves in cs.slice)
   int  m_sx, m_sy, m_ctuX = 0, m_ctuY = 0, m_dir = VER;
@@ -170,7 +193,7 @@ void Deriver::run()
 {
   const int W = m_pcv.lumaWidth, H = m_pcv.lumaHeight;
   CHECK(m_pcv.maxCUWidth > 128 || m_pcv.minCUWidth != 4 || m_pcv.minCUHeight != 4, "vtmgpu shim: unsupported CTU / min CU size");
-  CHECK(m_cs.picHeader->getLoopFilterAcrossVirtualBoundariesDisabledFlag(), "vtmgpu shim: signalled virtual boundaries are not supported");
+  m_vb = flattenVirtualBoundaries(m_cs);
   m_out.hasLadf = m_cs.sps->getLadfEnabled();
   if (m_out.hasLadf)
   {
@@ -223,7 +246,7 @@ void Deriver::run()
     std::vector<FlatDeblock::Lists> part(nThreads);
     for (int t = 0; t < nThreads; t++)
       pool.emplace_back([this, t, nThreads, &err, &part] {
-        try { Deriver d(m_cs, m_out); d.m_lists = &part[t]; d.rows(t, nThreads); }
+        try { Deriver d(m_cs, m_out); d.m_lists = &part[t]; d.m_vb = m_vb; d.rows(t, nThreads); }
         catch (...) { err[t] = std::current_exception(); }
       });
     for (auto& th : pool) th.join();
@@ -573,8 +596,8 @@ void Deriver::deriveCU(CodingUnit& cu)
   for (auto& tu : CU::traverseTUs(cu))
   {
     const Area at = hasLuma ? Area(tu.block(COMPONENT_Y)) : area;
-    mark(VER, at, m_internal, false);
-    mark(HOR, at, m_internal, false);
+    mark(VER, at, m_internal && !onVb(VER, at), false);
+    mark(HOR, at, m_internal && !onVb(HOR, at), false);
     lengthsFromTU(cu, tu);
     edges.push_back(edgeOf(tu.blocks[cu.chType], 0));
   }
@@ -585,8 +608,8 @@ void Deriver::deriveCU(CodingUnit& cu)
   {
     const Area ap = hasLuma ? Area(pu.block(COMPONENT_Y)) : area;
     const bool xOff = pu.blocks[cu.chType].x != own.x, yOff = pu.blocks[cu.chType].y != own.y;
-    mark(VER, ap, xOff ? m_internal : m_left, xOff);
-    mark(HOR, ap, yOff ? m_internal : m_top, yOff);
+    mark(VER, ap, (xOff ? m_internal : m_left) && !onVb(VER, ap), xOff);
+    mark(HOR, ap, (yOff ? m_internal : m_top) && !onVb(HOR, ap), yOff);
     edges.push_back(edgeOf(pu.blocks[cu.chType], 0));
     if ((pu.mergeFlag && pu.mergeType == MRG_TYPE_SUBPU_ATMVP) || cu.affine)
     {
@@ -595,7 +618,7 @@ void Deriver::deriveCU(CodingUnit& cu)
       for (int off = sub; off < extent; off += sub)
       {
         const Area blk = m_dir == HOR ? Area(cu.Y().x, cu.Y().y + off, cu.Y().width, 4) : Area(cu.Y().x + off, cu.Y().y, 4, cu.Y().height);
-        mark(m_dir, blk, m_internal, true);
+        mark(m_dir, blk, m_internal && !onVb(m_dir, blk), true);
         edges.push_back(edgeOf(pu.blocks[cu.chType], off));
       }
     }
@@ -632,7 +655,7 @@ void deriveDeblockRecords(CodingStructure& cs, FlatDeblock& out)
 void flattenSao(CodingStructure& cs, const SAOBlkParam* blk, int log2ScaleLuma, int log2ScaleChroma, FlatSao& out)
 {
   const PreCalcValues& pcv = *cs.pcv;
-  CHECK(cs.picHeader->getLoopFilterAcrossVirtualBoundariesDisabledFlag(), "vtmgpu shim: signalled virtual boundaries are not supported");
+  out.vb = flattenVirtualBoundaries(cs);
   out.widthInCtus = pcv.widthInCtus;
   out.numComps = getNumberValidComponents(pcv.chrFormat);
   out.log2ScaleLuma = log2ScaleLuma;
@@ -707,9 +730,9 @@ void flattenAlf(CodingStructure& cs, const CcAlfFilterParam& cc, uint8_t* const 
   }
   cs.slice = cs.getCU(Position(((n - 1) % pcv.widthInCtus) * pcv.maxCUWidth, ((n - 1) / pcv.widthInCtus) * pcv.maxCUHeight), CH_L)->slice;
   // the clip / pad path of ALFProcess (:452-555) is entered when a CTU touches a slice or tile boundary that must not be
-  // crossed: the per-CTU flags of isCrossedByVirtualBoundaries (:79-202).  Signalled virtual boundaries (which may lie
-  // inside a CTU) are not implemented on the device.
-  CHECK(cs.picHeader->getLoopFilterAcrossVirtualBoundariesDisabledFlag(), "vtmgpu shim: signalled virtual boundaries are not supported");
+  // crossed: the per-CTU flags of isCrossedByVirtualBoundaries (:79-202).  Signalled virtual boundaries go down as positions
+  // (they may lie inside a CTU); one that coincides with a CTU edge suppresses the slice/tile test and the corner pad of that side.
+  out.vb = flattenVirtualBoundaries(cs);
   const bool acrossSlices = cs.pps->getLoopFilterAcrossSlicesEnabledFlag(), acrossTiles = cs.pps->getLoopFilterAcrossTilesEnabledFlag();
   if (!acrossSlices || !acrossTiles)
   {

@@ -37,11 +37,15 @@ struct FlatDeblock
   bool listsMatchDense() const;       // self-check used by the capture mode
 };
 
+// picture-header virtual boundaries (empty when the flag is off)
+vtmgpu_virtual_boundaries flattenVirtualBoundaries(const CodingStructure& cs);
+
 struct FlatSao
 {
   std::vector<vtmgpu_sao_ctu> ctu;   // raw (as parsed) until reconstruct() is called
   int widthInCtus = 0, numComps = 3, log2ScaleLuma = 0, log2ScaleChroma = 0;
   int enabledMask = 0;               // m_picSAOEnabled after reconstruct
+  vtmgpu_virtual_boundaries vb{};
   vtmgpu_sao_params view() const;
 };
 
@@ -52,6 +56,7 @@ struct FlatAlf
   vtmgpu_alf_chroma_aps chromaAps{};
   bool hasChromaAps = false;
   std::vector<uint8_t> ctuEnable[3], ctuAlt[2], ccIdc[2];
+  vtmgpu_virtual_boundaries vb{};
   std::vector<uint8_t> ctuClip;      // VTMGPU_ALF_CLIP_* / PAD_* per CTU; empty = no partition boundary restricts the filter
   std::vector<int16_t> filterIdx;
   const vtmgpu_alf_params* view();

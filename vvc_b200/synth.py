@@ -189,10 +189,11 @@ def _plane(rng, h, w, bd, phase):
 
 
 def make_picture(width, height, chroma_format=1, bit_depth=10, ctu_size=128, seed=0, density=0.6, p_split=0.55,
-                 dbf=True, sao=True, alf=True, partitions=False, ladf=False):
+                 dbf=True, sao=True, alf=True, partitions=False, ladf=False, vb=None):
     """Returns a Capture (pre planes + side info, no reference stage outputs).  partitions: random per-CTU ALF clip / corner-pad
     flags as slice and tile boundaries without cross-boundary filtering produce them (any combination is a legal input).
-    ladf: the luma deblocking records carry QPs and the sequence has LADF intervals (include/vtmgpu.h, vtmgpu_ladf)."""
+    ladf: the luma deblocking records carry QPs and the sequence has LADF intervals (include/vtmgpu.h, vtmgpu_ladf).
+    vb: ([x positions], [y positions]) of signalled virtual boundaries (multiples of 8, at least a CTU apart), seen by SAO and ALF."""
     assert width % 8 == 0 and height % 8 == 0
     rng = np.random.default_rng(seed)
     sx, sy = abi.chroma_shifts(chroma_format)
@@ -222,6 +223,9 @@ def make_picture(width, height, chroma_format=1, bit_depth=10, ctu_size=128, see
     for d in range(2):
         sec["dbfrec_l%d" % d] = luma[d].tobytes()
         sec["dbfrec_c%d" % d] = chroma[d].tobytes() if ncomp == 3 else b""
+    if vb is not None:
+        vx, vy = list(vb[0]), list(vb[1])
+        sec["vb"] = np.array([len(vx), len(vy)] + (vx + [0, 0, 0])[:3] + (vy + [0, 0, 0])[:3], dtype=np.int32).tobytes()
     if sao:
         sec["sao_raw"] = bytes(_sao(rng, nctus, wctus, hctus, ncomp, density, bit_depth))
         sec["sao_scale"] = np.array([0, 0], dtype=np.int32).tobytes()
