@@ -334,6 +334,7 @@ def main():
     d2h = plane_bytes
 
     issue = [0.0]
+    ncalls = [0]
 
     def e2e_step():
         t_issue = time.perf_counter()
@@ -344,6 +345,8 @@ def main():
             for j in range(CH):
                 i = (base + j) % len(caps)
                 cx.upload(j, [t.numpy() for t in pin_in[i]], sync=False)
+                if os.environ.get("VTMGPU_E2E_SKIP_SIDE") == "1" and ncalls[0] > 0:
+                    continue                 # experiment switch (tools/abtest.sh): what the per-picture side information costs
                 if dense_records:
                     cx.set_deblock(j, side[i][0], sync=False)
                 else:
@@ -354,6 +357,7 @@ def main():
             for j in range(CH):
                 cx.download(j, [t.numpy() for t in pin_out[(base // CH) % NCTX][j]], sync=False)
         issue[0] += time.perf_counter() - t_issue
+        ncalls[0] += 1
         for cx in ectx:
             cx.sync()
 

@@ -124,7 +124,8 @@ typedef struct vtmgpu_deblock_params
  * units of an inter picture), as produced by a CU walk (LoopFilter::xDeblockCU, LoopFilter.cpp:261-408) that
  * appends instead of storing into a picture-sized array.  array a: 0 = luma dir 0, 1 = luma dir 1,
  * 2 = chroma dir 0, 3 = chroma dir 1; index = position in the corresponding dense array above.  Every index
- * may appear at most once per array; units that are not listed have no edge. */
+ * may appear at most once per array; units that are not listed have no edge.  If the four lists sit in one buffer, in array
+ * order, each starting on the next 16-byte boundary after the previous one, they are uploaded with a single copy. */
 typedef struct vtmgpu_dbf_luma_entry   { uint32_t index; uint32_t rec; } vtmgpu_dbf_luma_entry;
 typedef struct vtmgpu_dbf_chroma_entry { uint64_t rec; uint32_t index; uint32_t reserved; } vtmgpu_dbf_chroma_entry;
 typedef struct vtmgpu_deblock_sparse

@@ -24,3 +24,5 @@ t("set_sao", lambda: ctx.set_sao(0, ctus))
 t("set_alf", lambda: ctx.set_alf(0, ap))
 t("filter (async)", lambda: ctx.filter(0, 1, sync=False))
 t("download (async, pinned)", lambda: ctx.download(0, [x.numpy() for x in out], sync=False))
+sp = gpu.sparse_records(cap.dbf_luma, cap.dbf_chroma, pin=True)
+t("set_deblock_sparse", lambda: ctx.set_deblock_sparse(0, sp))

@@ -110,7 +110,35 @@ struct vtmgpu_ctx
   }
   bool slotOk(int first, int count) { return first >= 0 && count >= 1 && first + count <= seq.capacity; }
   unsigned char* pinnedSide(int slot) { return sidePinned + (size_t)slot * lay.total; }
-  int pushSlot(int slot) { return cuda(cudaMemcpyAsync(slotsDev + slot, slotsPinned + slot, sizeof(SlotDev), cudaMemcpyHostToDevice, stream), "slot table upload"); }
+  // Small per-picture side information is uploaded lazily: vtmgpu_set_* fill the pinned mirror and mark it, the stage calls
+  // push one range per slot and one run of slot descriptors (every H2D operation costs several microseconds of copy-engine
+  // time whatever its size, which is what bounds the end-to-end rate once the planes themselves move at PCIe speed).
+  std::vector<size_t> dirtyLo, dirtyHi;     // per slot: byte range of the side block to upload (lo >= hi: clean)
+  std::vector<char> slotDirty;
+  int pushSlot(int slot) { slotDirty[slot] = 1; return 0; }
+  void markSide(int slot, size_t off, size_t bytes)
+  {
+    dirtyLo[slot] = dirtyLo[slot] < dirtyHi[slot] ? std::min(dirtyLo[slot], off) : off;
+    dirtyHi[slot] = std::max(dirtyHi[slot], off + bytes);
+  }
+  int flush(int first, int count)
+  {
+    for (int s = first; s < first + count; s++)
+      if (dirtyLo[s] < dirtyHi[s])
+      {
+        if (pushSide(s, dirtyLo[s], dirtyHi[s] - dirtyLo[s])) return -1;
+        dirtyLo[s] = dirtyHi[s] = 0;
+      }
+    for (int s = first; s < first + count; s++)
+    {
+      if (!slotDirty[s]) continue;
+      int e = s;
+      while (e < first + count && slotDirty[e]) slotDirty[e++] = 0;
+      if (cuda(cudaMemcpyAsync(slotsDev + s, slotsPinned + s, sizeof(SlotDev) * (e - s), cudaMemcpyHostToDevice, stream), "slot table upload")) return -1;
+      s = e - 1;
+    }
+    return 0;
+  }
   int pushSide(int slot, size_t off, size_t bytes)
   {
     return cuda(cudaMemcpyAsync(sideDev[slot] + off, pinnedSide(slot) + off, bytes, cudaMemcpyHostToDevice, stream), "side info upload");
@@ -204,10 +232,11 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
   for (int d = 0; d < 2; d++) { L.dbfL[d] = off; off = alignUp(off + (size_t)L.recP[d] * L.recH[d] * 4, 256); }
   for (int d = 0; d < 2; d++) { L.dbfC[d] = off; off = alignUp(off + (size_t)L.recP[2 + d] * L.recH[2 + d] * 8, 256); }
   L.dbfEnd = off;
-  L.sao = off;    off = alignUp(off + (size_t)c->nCtus * 3 * sizeof(SaoDev), 256);
+  // the per-picture parts (APS filter tables, CTU control, ALF parameters, SAO parameters) are adjacent: one upload per picture
   L.alfTab = off; off = alignUp(off + sizeof(AlfLumaEntry) * VTMGPU_MAX_LUMA_SETS * 25 * 4, 256);
   L.ctuCtl = off; off = alignUp(off + (size_t)c->nCtus * sizeof(CtuCtlDev), 256);
   L.alf = off;    off = alignUp(off + sizeof(AlfDev), 256);
+  L.sao = off;    off = alignUp(off + (size_t)c->nCtus * 3 * sizeof(SaoDev), 256);
   L.total = off;
 
 #define CK(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_createError = std::string("vtmgpu_create: ") + what + ": " + cudaGetErrorString(e_); vtmgpu_destroy(c); return -1; } } while (0)
@@ -221,6 +250,9 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
   memset(c->sidePinned, 0, L.total * s.capacity);
   memset(c->slotsPinned, 0, sizeof(SlotDev) * s.capacity);
   c->cur.assign(s.capacity, 0);
+  c->dirtyLo.assign(s.capacity, 0);
+  c->dirtyHi.assign(s.capacity, 0);
+  c->slotDirty.assign(s.capacity, 1);
 
   // plane geometry: pitch multiple of 64 samples (128 B)
   int pw[3], ph[3], pitch[3];
@@ -643,21 +675,40 @@ extern "C" int vtmgpu_set_deblock_sparse(vtmgpu_ctx* c, int slot, const vtmgpu_d
   if (c->sparseDev.empty()) c->sparseDev.assign(c->seq.capacity, nullptr);
   if (!c->sparseDev[slot] && c->cuda(cudaMalloc(&c->sparseDev[slot], offs[4]), "record list allocation")) return -1;
   ScatterArgs A{};
+  // the lists land packed (16-byte aligned, in array order); a producer that keeps them in ONE buffer with this very layout
+  // gets a single copy instead of four
+  const void* src[4];
+  size_t esz[4], poff[5] = { 0, 0, 0, 0, 0 };
   for (int a = 0; a < 4; a++)
   {
     const int d = a & 1;
-    const void* src = a < 2 ? (const void*)p->luma[d] : (const void*)p->chroma[d];
+    src[a] = a < 2 ? (const void*)p->luma[d] : (const void*)p->chroma[d];
+    esz[a] = a < 2 ? sizeof(vtmgpu_dbf_luma_entry) : sizeof(vtmgpu_dbf_chroma_entry);
     uint32_t n = a < 2 ? p->luma_count[d] : p->chroma_count[d];
     if (!L.recW[a]) n = 0;
     if (n > (uint32_t)L.recW[a] * (uint32_t)L.recH[a]) return c->fail("set_deblock_sparse: list %d has %u entries for %d units", a, n, L.recW[a] * L.recH[a]);
-    if (n && !src) return c->fail("set_deblock_sparse: list %d is NULL", a);
-    A.list[a] = c->sparseDev[slot] + offs[a];
+    if (n && !src[a]) return c->fail("set_deblock_sparse: list %d is NULL", a);
+    poff[a + 1] = alignUp(poff[a] + (size_t)n * esz[a], 16);
+    A.list[a] = c->sparseDev[slot] + poff[a];
     A.dense[a] = c->sideDev[slot] + (a < 2 ? L.dbfL[d] : L.dbfC[d]);
     A.count[a] = n; A.first[a + 1] = A.first[a] + n;
     A.recW[a] = L.recW[a] ? L.recW[a] : 1; A.recH[a] = L.recH[a]; A.recP[a] = L.recP[a];
-    if (n && c->cuda(cudaMemcpyAsync(c->sparseDev[slot] + offs[a], src, (size_t)n * (a < 2 ? sizeof(vtmgpu_dbf_luma_entry) : sizeof(vtmgpu_dbf_chroma_entry)),
-                                     cudaMemcpyHostToDevice, c->stream), "set_deblock_sparse")) return -1;
   }
+  int firstList = -1;
+  bool packed = true;
+  for (int a = 0; a < 4; a++)
+  {
+    if (!A.count[a]) continue;
+    if (firstList < 0) firstList = a;
+    packed = packed && (const unsigned char*)src[a] == (const unsigned char*)src[firstList] + (poff[a] - poff[firstList]);
+  }
+  if (firstList >= 0 && packed)
+  {
+    if (c->cuda(cudaMemcpyAsync(c->sparseDev[slot] + poff[firstList], src[firstList], poff[4] - poff[firstList], cudaMemcpyHostToDevice, c->stream), "set_deblock_sparse")) return -1;
+  }
+  else
+    for (int a = 0; a < 4; a++)
+      if (A.count[a] && c->cuda(cudaMemcpyAsync(c->sparseDev[slot] + poff[a], src[a], (size_t)A.count[a] * esz[a], cudaMemcpyHostToDevice, c->stream), "set_deblock_sparse")) return -1;
   if (c->cuda(cudaMemsetAsync(c->sideDev[slot] + L.dbfL[0], 0, L.dbfEnd - L.dbfL[0], c->stream), "record clear")) return -1;
   if (A.first[4])
   {
@@ -786,7 +837,7 @@ extern "C" int vtmgpu_set_sao(vtmgpu_ctx* c, int slot, const vtmgpu_sao_params* 
         d[a * 3 + k] = z;
       }
     sd.saoOn = any;     // SAOProcess returns early when no CTU has SAO on (SampleAdaptiveOffset.cpp:626-637)
-    if (c->pushSide(slot, c->lay.sao, (size_t)c->nCtus * 3 * sizeof(SaoDev))) return -1;
+    c->markSide(slot, c->lay.sao, (size_t)c->nCtus * 3 * sizeof(SaoDev));
   }
   return c->pushSlot(slot);
 }
@@ -902,8 +953,8 @@ extern "C" int vtmgpu_set_alf(vtmgpu_ctx* c, int slot, const vtmgpu_alf_params* 
     }
     sd.alfOn = (A.enabled[0] | A.enabled[1] | A.enabled[2]) != 0;    // ALFProcess skips the picture otherwise (AdaptiveLoopFilter.cpp:429)
     sd.alfWide = wide;
-    if (p->num_luma_aps && c->pushSide(slot, c->lay.alfTab + sizeof(AlfLumaEntry) * VTMGPU_ALF_FIXED_SETS * 100, sizeof(AlfLumaEntry) * 100 * p->num_luma_aps)) return -1;
-    if (c->pushSide(slot, c->lay.ctuCtl, c->lay.total - c->lay.ctuCtl)) return -1;
+    if (p->num_luma_aps) c->markSide(slot, c->lay.alfTab + sizeof(AlfLumaEntry) * VTMGPU_ALF_FIXED_SETS * 100, sizeof(AlfLumaEntry) * 100 * p->num_luma_aps);
+    c->markSide(slot, c->lay.ctuCtl, c->lay.sao - c->lay.ctuCtl);
   }
   return c->pushSlot(slot);
 }
@@ -993,6 +1044,7 @@ int runStages(vtmgpu_ctx* c, int first, int count, int stages, bool sync, const 
   if (!c->slotOk(first, count)) return c->fail("%s: bad slot range [%d,%d)", what, first, first + count);
   cudaSetDevice(c->seq.device);
   c->stageValid = false;
+  if (c->flush(first, count)) return -1;
   if (c->profiling) cudaEventRecord(c->stageEv[0], c->stream);
   if ((stages & (ST_DBF | ST_SAO)) && launchDbfSao(c, first, count, (stages & ST_DBF) != 0, (stages & ST_SAO) != 0)) return -1;
   if (c->profiling) cudaEventRecord(c->stageEv[1], c->stream);

@@ -97,40 +97,54 @@ def sao_reconstruct(ctus, width_in_ctus, ncomp, scale_luma=0, scale_chroma=0):
 
 
 def sparse_records(dbf_luma, dbf_chroma, pin=False, ladf=None):
-    """List form (abi.DeblockSparse) of dense record arrays: what a producer that appends while walking the CUs emits.
-    pin=True places the lists in page-locked memory (torch) so that the uploads are asynchronous."""
+    """List form (abi.DeblockSparse) of dense record arrays: what a producer that appends while walking the CUs emits.  The four
+    lists are laid out in ONE buffer (array order, each on a 16-byte boundary) so that the library uploads them with one copy.
+    pin=True places that buffer in page-locked memory (torch) so that the upload is asynchronous."""
     import numpy as np
-    p, keep = abi.DeblockSparse(), []
-
-    def hold(a):
-        if pin:
-            import torch
-            t = torch.from_numpy(a.view(np.uint8).copy()).pin_memory()
-            keep.append(t)
-            return t.data_ptr()
-        keep.append(a)
-        return a.ctypes.data
-
+    p = abi.DeblockSparse()
+    lists = []
     for d in range(2):
         dense = np.ascontiguousarray(dbf_luma[d]).reshape(-1).view(np.uint32)
         idx = np.flatnonzero(dense)
         ent = np.zeros(len(idx), dtype=abi.LUMA_ENTRY_DTYPE)
         ent["index"], ent["rec"] = idx, dense[idx]
-        p.luma_count[d] = len(idx)
-        if len(idx):
-            p.luma[d] = C.cast(hold(ent), C.POINTER(abi.DbfLumaEntry))
+        lists.append(ent)
+    for d in range(2):
         if dbf_chroma is not None and dbf_chroma[d].size:
             dense = np.ascontiguousarray(dbf_chroma[d]).reshape(-1).view(np.uint64)
             idx = np.flatnonzero(dense)
             ent = np.zeros(len(idx), dtype=abi.CHROMA_ENTRY_DTYPE)
             ent["index"], ent["rec"] = idx, dense[idx]
-            p.chroma_count[d] = len(idx)
-            if len(idx):
-                p.chroma[d] = C.cast(hold(ent), C.POINTER(abi.DbfChromaEntry))
+        else:
+            ent = np.zeros(0, dtype=abi.CHROMA_ENTRY_DTYPE)
+        lists.append(ent)
+    offs, total = [], 0
+    for ent in lists:
+        offs.append(total)
+        total = (total + ent.nbytes + 15) & ~15
+    if pin:
+        import torch
+        holder = torch.empty(max(total, 16), dtype=torch.uint8).pin_memory()
+        buf, base = holder.numpy(), holder.data_ptr()
+    else:
+        holder = np.zeros(max(total, 16) + 16, dtype=np.uint8)
+        skew = (-holder.ctypes.data) & 15
+        buf, base = holder[skew:], holder.ctypes.data + skew
+    for ent, off in zip(lists, offs):
+        buf[off:off + ent.nbytes] = ent.view(np.uint8).reshape(-1)
+    for d in range(2):
+        p.luma_count[d] = len(lists[d])
+        p.chroma_count[d] = len(lists[2 + d])
+        if len(lists[d]):
+            p.luma[d] = C.cast(base + offs[d], C.POINTER(abi.DbfLumaEntry))
+        if len(lists[2 + d]):
+            p.chroma[d] = C.cast(base + offs[2 + d], C.POINTER(abi.DbfChromaEntry))
+    keep = [holder]
     if ladf is not None:
         keep.append(ladf)
         p.ladf = C.pointer(ladf)
     p._keep = keep
+    p.nbytes = total
     return p
 
 
