@@ -5,7 +5,7 @@ Joins `ncu -i REP --page source --csv` (per-SASS-instruction counters, in progra
 `nvdisasm --print-line-info CUBIN` for the same kernel and prints the hottest CUDA source lines: share of executed
 warp instructions, share of stall samples and the dominant stall reason.
 
-usage: ncu_lines.py REPORT.ncu-rep CUBIN KERNEL_REGEX [TOP_N]
+usage: ncu_lines.py REPORT.ncu-rep CUBIN KERNEL_REGEX[:CUBIN_SECTION_SUBSTRING] [TOP_N]
 """
 import csv
 import io
@@ -18,20 +18,27 @@ from collections import defaultdict
 def main():
     rep, cubin, kern = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+    sec = kern.split(":")[1] if ":" in kern else kern       # substring of the (mangled) cubin section, e.g. k_alfILb0 for k_alf<false>
+    kern = kern.split(":")[0]
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     h = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     hdr = rows[h]
     ix = {n: i for i, n in enumerate(hdr)}
-    data = [r for r in rows[h + 1:] if len(r) == len(hdr)]
+    data = []
+    for r in rows[h + 1:]:
+        if r and r[0] == "Address":
+            break                                           # a second result of the same kernel
+        if len(r) == len(hdr):
+            data.append(r)
     stall_cols = [n for n in hdr if n.startswith("stall_") and "Not Issued" not in n]
 
     dis = subprocess.run(["nvdisasm", "--print-line-info", cubin], capture_output=True, text=True).stdout
     lines, cur, on = [], None, False
     for ln in dis.splitlines():
         if ln.startswith("\t.section\t.text."):
-            on = re.search(kern, ln) is not None
+            on = sec in ln
             continue
         if not on:
             continue
