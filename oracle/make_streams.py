@@ -66,6 +66,13 @@ STREAMS = {
     # boundary), y = 248 (4 rows above the ALF virtual boundary of its CTU row), y = 384 (a CTU boundary)
     "vb_832x480": (832, 480, 420, 5, 35, 14, 32, [RA], K + ["--LoopFilterAcrossVirtualBoundariesDisabledFlag=1", "--NumVerVirtualBoundaries=2",
                                                             "--NumHorVirtualBoundaries=2", "--VirtualBoundariesPosX=200,512", "--VirtualBoundariesPosY=248,384"], 0),
+    # 4:2:2: chroma deblocking grid 16 x 8 luma samples, its own chroma QP mapping, ALF / CC-ALF with sx = 1, sy = 0
+    "ld422_416x240": (416, 240, 422, 4, 422, 14, 30, [LD], ["--ChromaFormatIDC=422"], 0),
+    # sequence-level variants of the hot path: CTU 64, 12-bit internal depth (this reference snapshot cannot decode its own 8-bit streams), non-zero deblocking offsets
+    "ctu64_416x240": (416, 240, 420, 4, 64, 14, 32, [RA], K + ["--CTUSize=64"], 0),
+    "bd12_416x240": (416, 240, 420, 3, 12, 14, 32, [RA], K + ["--InternalBitDepth=12"], 0),
+    # (4:0:0 makes the encoder of this reference snapshot abort, TypeDef.h:1229: monochrome is covered by seeded pictures vs the oracle only)
+    "dbfoffs_416x240": (416, 240, 420, 4, 66, 14, 34, [LD], K + ["--LoopFilterBetaOffset_div2=3", "--LoopFilterTcOffset_div2=-4"], 0),
     # short 4K clip for fast turnaround (first 8 pictures of the config-3 source)
     "ra_2160p_8":   (3840, 2160, 420, 8, 9160, 14, 32, [RA], K, 0),
 }
@@ -75,9 +82,10 @@ def gen_yuv(path, W, H, chroma, frames, seed, sigma):
     """Seeded synthetic clip, planar little-endian u16, values 0..1023."""
     rng = np.random.default_rng(seed)
     yy, xx = np.mgrid[0:H, 0:W]
-    sx = sy = 2 if chroma == 420 else 1
+    sx = 2 if chroma in (420, 422) else 1
+    sy = 2 if chroma == 420 else 1
     cy, cx = np.mgrid[0:H // sy, 0:W // sx]
-    cs = 1.0 if chroma == 420 else 2.0   # keep chroma feature sizes similar at full resolution
+    cs = 1.0 if chroma == 420 else 2.0   # keep chroma feature sizes similar at full resolution (4:2:2: stretched vertically, fine)
     with open(path, "wb") as f:
         for t in range(frames):
             y = (512 + 260 * np.sin((xx + 6 * t) / 41.0) * np.cos((yy - 4 * t) / 29.0)
@@ -88,7 +96,7 @@ def gen_yuv(path, W, H, chroma, frames, seed, sigma):
             v = (512 + 200 * np.cos((cy / cs + 2 * t) / 23.0) + 60 * (((cx / cs + 4 * t) // 24) % 2)
                  + rng.normal(0, sigma / 2, cy.shape))
             if seed >= 9000:   # CC-ALF content: chroma carries a blurred copy of the luma structure
-                yd = y[::sy, ::sx] if chroma == 420 else y
+                yd = y[::sy, ::sx]
                 u = 512 + 0.45 * (yd - 512) + rng.normal(0, sigma / 2, cy.shape)
                 v = 512 - 0.35 * (yd - 512) + 40 * np.sin(cx / 17.0) + rng.normal(0, sigma / 2, cy.shape)
             for p in (y, u, v):

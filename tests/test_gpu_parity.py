@@ -231,7 +231,9 @@ STREAMS = [("ra_416x240.bin", 8), ("ld444_1080p.bin", 16), ("ra_1080p.bin", 32),
            # tiles / raster-scan slices with in-loop filtering across their boundaries disabled
            ("tiles_832x480.bin", 5), ("slices_832x480.bin", 5), ("slices45_832x480.bin", 3),
            ("ladf_832x480.bin", 5),       # LADF: deblocking thresholds derived on the device
-           ("vb_832x480.bin", 5)]         # signalled virtual boundaries inside CTUs and on CTU edges
+           ("vb_832x480.bin", 5),         # signalled virtual boundaries inside CTUs and on CTU edges
+           ("ld422_416x240.bin", 4),      # 4:2:2, full CTC tool set
+           ("ctu64_416x240.bin", 4), ("bd12_416x240.bin", 3), ("dbfoffs_416x240.bin", 4)]   # CTU 64, 12-bit, beta / tc offsets
 
 
 @pytest.mark.parametrize("stream,pictures", STREAMS)

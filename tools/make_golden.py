@@ -37,6 +37,10 @@ SELECT = {
     "slices45_832x480": [0],           # slices of 4 + 5 tiles: bottom-right corner padding
     "ladf_832x480": [0, 2],            # LADF: luma records carry QPs, thresholds derived from the samples
     "vb_832x480": [0, 2],              # signalled virtual boundaries inside CTUs and on CTU edges
+    "ld422_416x240": [0, 2],           # 4:2:2: chroma deblocking grid / QP mapping, ALF and CC-ALF with sx = 1, sy = 0
+    "ctu64_416x240": [0, 2],           # CTU 64: tile = CTU in k_alf, 16 chroma rows per CTU row in the SAO / ALF boundary logic
+    "bd12_416x240": [0, 1],            # 12-bit: tc / beta scaling, clip tables, IDP operand ranges
+    "dbfoffs_416x240": [1, 3],         # slice-level beta / tc offsets
     "slices_832x480": [0, 3],          # 3x3 tiles in two raster-scan slices, no filtering across slices (ALF corner padding)
 }
 
