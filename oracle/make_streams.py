@@ -73,6 +73,10 @@ STREAMS = {
     "bd12_416x240": (416, 240, 420, 3, 12, 14, 32, [RA], K + ["--InternalBitDepth=12"], 0),
     # (4:0:0 makes the encoder of this reference snapshot abort, TypeDef.h:1229: monochrome is covered by seeded pictures vs the oracle only)
     "dbfoffs_416x240": (416, 240, 420, 4, 66, 14, 34, [LD], K + ["--LoopFilterBetaOffset_div2=3", "--LoopFilterTcOffset_div2=-4"], 0),
+    # screen-content tools on noise-free blocky 4:4:4 content: palette CUs are not deblocked on their own side (bPartP/QNoFilter),
+    # BDPCM edges get bS 0 when both sides use it, IBC CUs take the motion test; P slices (one reference list)
+    "scc444_416x240": (416, 240, 444, 3, 8445, 0, 27, [LD, "444/yuv444.cfg"], ["--PLT=1", "--IBC=1", "--BDPCM=1", "--HashME=1"], 0),
+    "ldp_416x240": (416, 240, 420, 4, 67, 14, 32, ["encoder_lowdelay_P_vtm.cfg"], K, 0),
     # short 4K clip for fast turnaround (first 8 pictures of the config-3 source)
     "ra_2160p_8":   (3840, 2160, 420, 8, 9160, 14, 32, [RA], K, 0),
 }
@@ -95,6 +99,10 @@ def gen_yuv(path, W, H, chroma, frames, seed, sigma):
                  + rng.normal(0, sigma / 2, cy.shape))
             v = (512 + 200 * np.cos((cy / cs + 2 * t) / 23.0) + 60 * (((cx / cs + 4 * t) // 24) % 2)
                  + rng.normal(0, sigma / 2, cy.shape))
+            if 8000 <= seed < 9000:   # screen content: a few flat colours in sharp-edged rectangles and thin lines (palette / IBC friendly)
+                y = 128.0 + 256 * (((xx + 3 * t) // 24 + yy // 18) % 3) + 300 * ((xx % 16 == 5) | (yy % 20 == 7))
+                u = 300.0 + 200 * (((cx + 2 * t) // 20 + cy // 14) % 3)
+                v = 700.0 - 180 * ((cx // 28 + (cy + t) // 10) % 4)
             if seed >= 9000:   # CC-ALF content: chroma carries a blurred copy of the luma structure
                 yd = y[::sy, ::sx]
                 u = 512 + 0.45 * (yd - 512) + rng.normal(0, sigma / 2, cy.shape)

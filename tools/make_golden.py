@@ -41,6 +41,8 @@ SELECT = {
     "ctu64_416x240": [0, 2],           # CTU 64: tile = CTU in k_alf, 16 chroma rows per CTU row in the SAO / ALF boundary logic
     "bd12_416x240": [0, 1],            # 12-bit: tc / beta scaling, clip tables, IDP operand ranges
     "dbfoffs_416x240": [1, 3],         # slice-level beta / tc offsets
+    "scc444_416x240": [0, 1],          # palette / IBC / BDPCM on blocky 4:4:4 content
+    "ldp_416x240": [1, 3],             # P slices
     "slices_832x480": [0, 3],          # 3x3 tiles in two raster-scan slices, no filtering across slices (ALF corner padding)
 }
 
