@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <exception>
+#include <atomic>
 #include <thread>
 #include <vector>
 
@@ -149,7 +150,7 @@ private:
   CtuState             m_st;
   const Slice*         m_ctuSlice = nullptr;   // slice of the first CU of the CTU in flight (what the reference leaves in cs.slice)
   int  m_sx, m_sy, m_ctuX = 0, m_ctuY = 0, m_dir = VER;
-  void rows(int first, int step);
+  void work(std::atomic<int>& next);
   bool m_left = false, m_top = false, m_internal = false;
 
   int uidx(int x, int y) const { return ((y & (int)m_pcv.maxCUHeightMask) >> 2) * kU + ((x & (int)m_pcv.maxCUWidthMask) >> 2); }
@@ -230,23 +231,24 @@ void Deriver::run()
   m_out.listsValid = false;
 
   // two passes over the picture as in loopFilterPic (LoopFilter.cpp:165-240).  No record depends on samples
-  // (LADF is rejected above), so both passes can be derived before any filtering happens -- and CTUs are independent
-  // of each other: all state is CTU-local (LoopFilter.cpp:169-175), every record lies inside its own CTU and the
-  // coding structure is only read.  The CTU rows are therefore spread over a few host threads
-  // (VTMGPU_SHIM_THREADS, default min(8, cores); SURVEY.md 8f n1 "parallel host").
+  // (with LADF the records carry QPs and the device resolves them), so both passes can be derived before any filtering happens
+  // -- and CTUs are independent of each other: all state is CTU-local (LoopFilter.cpp:169-175), every record lies inside its
+  // own CTU and the coding structure is only read.  The CTU passes are therefore handed out dynamically to a few host threads
+  // (VTMGPU_SHIM_THREADS, default min(16, cores); SURVEY.md 8f n1 "parallel host").
   int nThreads = 1;
   if (const char* e = getenv("VTMGPU_SHIM_THREADS")) nThreads = atoi(e);
-  else nThreads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
-  nThreads = std::max(1, std::min(nThreads, (int)m_pcv.heightInCtus));
-  if (nThreads == 1) { m_lists = &m_out.lists; rows(0, 1); }
+  else nThreads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  nThreads = std::max(1, std::min(nThreads, (int)m_pcv.sizeInCtus));
+  std::atomic<int> next(0);
+  if (nThreads == 1) { m_lists = &m_out.lists; work(next); }
   else
   {
     std::vector<std::thread> pool;
     std::vector<std::exception_ptr> err(nThreads);
     std::vector<FlatDeblock::Lists> part(nThreads);
     for (int t = 0; t < nThreads; t++)
-      pool.emplace_back([this, t, nThreads, &err, &part] {
-        try { Deriver d(m_cs, m_out); d.m_lists = &part[t]; d.m_vb = m_vb; d.rows(t, nThreads); }
+      pool.emplace_back([this, t, &err, &part, &next] {
+        try { Deriver d(m_cs, m_out); d.m_lists = &part[t]; d.m_vb = m_vb; d.work(next); }
         catch (...) { err[t] = std::current_exception(); }
       });
     for (auto& th : pool) th.join();
@@ -270,17 +272,20 @@ void Deriver::run()
   m_cs.slice = m_cs.getCU(Position((m_pcv.widthInCtus - 1) << m_pcv.maxCUWidthLog2, (m_pcv.heightInCtus - 1) << m_pcv.maxCUHeightLog2), CH_L)->slice;
 }
 
-void Deriver::rows(int first, int step)
+// CTU passes are handed out one at a time (all vertical-edge passes, then all horizontal-edge passes): every pass is independent
+// of every other one -- CTU-local state (LoopFilter.cpp:169-175), records inside the CTU, read-only coding structure
+void Deriver::work(std::atomic<int>& next)
 {
-  for (m_dir = VER; m_dir <= HOR; m_dir++)
-    for (int y = first; y < (int)m_pcv.heightInCtus; y += step)
-      for (int x = 0; x < (int)m_pcv.widthInCtus; x++)
-      {
-        const UnitArea ctuArea(m_pcv.chrFormat, Area(x << m_pcv.maxCUWidthLog2, y << m_pcv.maxCUHeightLog2, m_pcv.maxCUWidth, m_pcv.maxCUWidth));
-        m_ctuX = x << m_pcv.maxCUWidthLog2;
-        m_ctuY = y << m_pcv.maxCUHeightLog2;
-        ctuPass(ctuArea);
-      }
+  const int w = (int)m_pcv.widthInCtus, n = w * (int)m_pcv.heightInCtus;
+  for (int i; (i = next.fetch_add(1, std::memory_order_relaxed)) < 2 * n;)
+  {
+    m_dir = i < n ? VER : HOR;
+    const int a = i < n ? i : i - n, x = a % w, y = a / w;
+    const UnitArea ctuArea(m_pcv.chrFormat, Area(x << m_pcv.maxCUWidthLog2, y << m_pcv.maxCUHeightLog2, m_pcv.maxCUWidth, m_pcv.maxCUWidth));
+    m_ctuX = x << m_pcv.maxCUWidthLog2;
+    m_ctuY = y << m_pcv.maxCUHeightLog2;
+    ctuPass(ctuArea);
+  }
 }
 
 void Deriver::ctuPass(const UnitArea& ctuArea)
