@@ -77,6 +77,8 @@ STREAMS = {
     # BDPCM edges get bS 0 when both sides use it, IBC CUs take the motion test; P slices (one reference list)
     "scc444_416x240": (416, 240, 444, 3, 8445, 0, 27, [LD, "444/yuv444.cfg"], ["--PLT=1", "--IBC=1", "--BDPCM=1", "--HashME=1"], 0),
     "ldp_416x240": (416, 240, 420, 4, 67, 14, 32, ["encoder_lowdelay_P_vtm.cfg"], K, 0),
+    # full CTC tool set at a size with 128-wide CUs (affine / ATMVP sub-block edges inside large CUs, long filters clamped next to affine)
+    "ra_full_832x480": (832, 480, 420, 6, 36, 12, 30, [RA], [], 0),
     # short 4K clip for fast turnaround (first 8 pictures of the config-3 source)
     "ra_2160p_8":   (3840, 2160, 420, 8, 9160, 14, 32, [RA], K, 0),
 }

@@ -440,7 +440,7 @@ __device__ __forceinline__ uint2 alfChromaQuad(const pel* cb, int o1, int o2, bo
 // CC-ALF correction for 4 chroma samples in 4:2:0 / 4:2:2 (sx = 1): collocated luma column = 2 * chroma column.
 // l = luma sample collocated with the first chroma sample (smem, SAO output); l1,l2,l3 = row offsets (filterBlkCcAlf
 // :1376-1386).  Returns the packed corrections (already clipped to the chroma range around 0).
-__device__ __forceinline__ uint2 ccAlfQuad420(const pel* l, int l1, int l2, int l3, const int16_t* __restrict__ ccg, uint32_t maxcP, uint32_t halfP)
+__device__ __forceinline__ uint2 ccAlfQuad420(const pel* l, int l1, int l2, int l3, const uint32_t* __restrict__ ccw, uint32_t maxcP, uint32_t halfP)
 {
   // luma words of a row relative to l: W(-2), W(0), W(2), W(4), W(6)
   uint32_t ctr[2], up[2], lf[2], rt[2], dl[2], dm[2], dr[2], d2[2];
@@ -465,10 +465,10 @@ __device__ __forceinline__ uint2 ccAlfQuad420(const pel* l, int l1, int l2, int 
     const uint2 r = *reinterpret_cast<const uint2*>(l + l3), t = *reinterpret_cast<const uint2*>(l + l3 + 4);
     d2[0] = prmt(r.x, r.y, 0x5410u); d2[1] = prmt(t.x, t.y, 0x5410u);
   }
-  uint32_t cB[7];
-  int fsum = 0;
-#pragma unroll
-  for (int k = 0; k < 7; k++) { const int c = __ldg(&ccg[k]); cB[k] = (uint32_t)(c & 0xff) * 0x01000001u; fsum += c; }
+  // coefficients as IDP.2A byte operands + their sum, expanded on the host (AlfDev::ccB)
+  const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(ccw)), w1 = __ldg(reinterpret_cast<const uint4*>(ccw) + 1);
+  const uint32_t cB[7] = { w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z };
+  const int fsum = (int)w1.w;
   uint32_t res[2];
 #pragma unroll
   for (int px = 0; px < 2; px++)
@@ -754,7 +754,7 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDe
             else if (lpos == vbL - 1 || lpos == vbL) l1 = l2 = l3 = 0;
             if (g.sx == 1)
             {
-              const uint2 d = ccAlfQuad420(&lumaB[ly * SA_P + (qx << 1) + SA_HX], l1, l2, l3, ccg, maxcP, halfP);
+              const uint2 d = ccAlfQuad420(&lumaB[ly * SA_P + (qx << 1) + SA_HX], l1, l2, l3, S.alf->ccB[c][idc - 1], maxcP, halfP);
               v.x = addClamp0(v.x, d.x, maxcP);
               v.y = addClamp0(v.y, d.y, maxcP);
             }

@@ -920,6 +920,18 @@ extern "C" int vtmgpu_set_alf(vtmgpu_ctx* c, int slot, const vtmgpu_alf_params* 
     {
       A.ccEnabled[k] = chroma && p->ccalf_enabled[k];
       memcpy(A.cc[k], p->ccalf_coeff[k], sizeof(A.cc[k]));
+      for (int f = 0; f < VTMGPU_CCALF_MAX_FILTERS; f++)
+      {
+        int sum = 0;
+        for (int t = 0; t < 7; t++)
+        {
+          const int co = p->ccalf_coeff[k][f][t];
+          if (A.ccEnabled[k] && (co < -128 || co > 127)) return c->fail("set_alf: CC-ALF coefficient %d out of range", co);
+          A.ccB[k][f][t] = (uint32_t)(co & 0xff) * 0x01000001u;
+          sum += co;
+        }
+        A.ccB[k][f][7] = (uint32_t)sum;
+      }
     }
     // per-CTU control
     for (int a = 0; a < n; a++)
