@@ -80,3 +80,27 @@ def test_sao_reconstruct_rejects_missing_merge_target(lib):
     ctus[0].comp[0].type = abi.SAO_MERGE_LEFT      # CTU 0 has no left neighbour
     with pytest.raises(gpu.VtmGpuError):
         gpu.sao_reconstruct(ctus, 2, 3)
+
+
+def test_sparse_records_layout():
+    """gpu.sparse_records: lists of the non-zero records, in ONE buffer in array order, each list on the next 16-byte boundary
+    (the layout for which vtmgpu_set_deblock_sparse needs a single upload)."""
+    import numpy as np
+    from vvc_b200 import synth
+    cap = synth.make_picture(256, 128, seed=3, density=0.4)
+    sp = gpu.sparse_records(cap.dbf_luma, cap.dbf_chroma)
+    base = C.cast(sp.luma[0], C.c_void_p).value
+    off = 0
+    for d in range(2):
+        n = int(np.count_nonzero(cap.dbf_luma[d]))
+        assert sp.luma_count[d] == n
+        assert C.cast(sp.luma[d], C.c_void_p).value == base + off
+        ent = np.ctypeslib.as_array(C.cast(sp.luma[d], C.POINTER(C.c_uint32)), shape=(n, 2))
+        assert np.array_equal(cap.dbf_luma[d][ent[:, 0]], ent[:, 1]) and len(set(ent[:, 0].tolist())) == n
+        off = (off + n * C.sizeof(abi.DbfLumaEntry) + 15) & ~15
+    for d in range(2):
+        n = int(np.count_nonzero(cap.dbf_chroma[d]))
+        assert sp.chroma_count[d] == n
+        assert C.cast(sp.chroma[d], C.c_void_p).value == base + off
+        off = (off + n * C.sizeof(abi.DbfChromaEntry) + 15) & ~15
+    assert base % 16 == 0 and sp.nbytes == off
