@@ -614,175 +614,175 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDe
 #pragma unroll 1
     for (int part = 0; part < nparts; part++)
     {
-    const int pi = cutX ? (part & 1) : 0, pj = cutX ? (part >> 1) : part;
-    const int px0 = pi ? cutX : x0, px1 = (cutX && !pi) ? cutX : x0 + tileW;      // luma rectangle of this part
-    const int py0 = pj ? cutY : y0, py1 = (cutY && !pj) ? cutY : y0 + tileH;
-    if (nparts > 1)
-    {
-      // the padding of a part overwrites its neighbours' samples: the first part saves the tile, the others start from that copy
-      uint4* stg = reinterpret_cast<uint4*>(smraw + L.offA(stage, 0));
-      uint4* scr = reinterpret_cast<uint4*>(smraw + L.total);
-      const int n16 = (L.lumaBytes + 2 * L.chromaBytes) >> 4;
-      if (part == 0) { for (int i = tid; i < n16; i += SA_THREADS) scr[i] = stg[i]; }
-      else           { for (int i = tid; i < n16; i += SA_THREADS) stg[i] = scr[i]; }
-      __syncthreads();
-    }
-    if (onBorder)
-    {
-      int win[4] = { (clip & VTMGPU_ALF_CLIP_LEFT) ? cx0 : 0, (clip & VTMGPU_ALF_CLIP_RIGHT) ? cx1 : g.w,
-                     (clip & VTMGPU_ALF_CLIP_TOP) ? cy0 : 0, (clip & VTMGPU_ALF_CLIP_BOTTOM) ? cy1 : g.h };
-      int pad = clip & (VTMGPU_ALF_PAD_TL | VTMGPU_ALF_PAD_BR);
-      if (anyVb) pad = saVbWindow(&pvb, make_int4(px0, px1, py0, py1), make_int4(cx0, cx1, cy0, cy1), part == 0, part == nparts - 1, pad, win);
-      const int xlo = win[0], xhi = win[1], ylo = win[2], yhi = win[3];
-      const int bxc = (x0 >> g.sx) - SA_HX, byc = (y0 >> g.sy) - SA_HY;
-      if (alfY || ccCb || ccCr) saReplicateBorder(A0, x0 - SA_HX, y0 - SA_HY, xlo, xhi, ylo, yhi, SA_P, SA_T, SA_TH, 3);
-      if (alfCb) saReplicateBorder(A1, bxc, byc, xlo >> g.sx, xhi >> g.sx, ylo >> g.sy, yhi >> g.sy, L.pitchC, tw, th, 3);
-      if (alfCr) saReplicateBorder(A2, bxc, byc, xlo >> g.sx, xhi >> g.sx, ylo >> g.sy, yhi >> g.sy, L.pitchC, tw, th, 3);
-      if (pad)
+      const int pi = cutX ? (part & 1) : 0, pj = cutX ? (part >> 1) : part;
+      const int px0 = pi ? cutX : x0, px1 = (cutX && !pi) ? cutX : x0 + tileW;      // luma rectangle of this part
+      const int py0 = pj ? cutY : y0, py1 = (cutY && !pj) ? cutY : y0 + tileH;
+      if (nparts > 1)
       {
-        // no barrier needed in between: the corners lie outside the clamp window's replicated ranges (their sides are not clipped)
-        if (alfY || ccCb || ccCr) saPadCorners(A0, x0 - SA_HX, y0 - SA_HY, cx0, cy0, cx1, cy1, SA_P, tileW, tileH, 3, pad);
-        if (alfCb) saPadCorners(A1, bxc, byc, cx0 >> g.sx, cy0 >> g.sy, cx1 >> g.sx, cy1 >> g.sy, L.pitchC, tileW >> g.sx, tileH >> g.sy, 3, pad);
-        if (alfCr) saPadCorners(A2, bxc, byc, cx0 >> g.sx, cy0 >> g.sy, cx1 >> g.sx, cy1 >> g.sy, L.pitchC, tileW >> g.sx, tileH >> g.sy, 3, pad);
+        // the padding of a part overwrites its neighbours' samples: the first part saves the tile, the others start from that copy
+        uint4* stg = reinterpret_cast<uint4*>(smraw + L.offA(stage, 0));
+        uint4* scr = reinterpret_cast<uint4*>(smraw + L.total);
+        const int n16 = (L.lumaBytes + 2 * L.chromaBytes) >> 4;
+        if (part == 0) { for (int i = tid; i < n16; i += SA_THREADS) scr[i] = stg[i]; }
+        else           { for (int i = tid; i < n16; i += SA_THREADS) stg[i] = scr[i]; }
+        __syncthreads();
       }
-      __syncthreads();
-    }
-
-    // ---- phase 1: Laplacian cells (luma ALF only) -------------------------------------------------------------------
-    const pel* lumaB = B0;
-    const int bx = x0 + 4 * bj, by = y0 + 4 * bi;
-    const pel* c0 = &lumaB[(4 * bi + SA_HY) * SA_P + 4 * bj + SA_HX];
-    const int yb = by & ctuMask;
-    const bool vbBlk = yb == vbL - 4 || yb == vbL;             // uniform per warp (two block rows) for CTU sizes >= 32
-    if (alfY)
-    {
-      if (!vbBlk) alfOwnCells(cell, c0, bi, bj);
-      else
+      if (onBorder)
       {
-        for (int k = 0; k < 4; k++)
+        int win[4] = { (clip & VTMGPU_ALF_CLIP_LEFT) ? cx0 : 0, (clip & VTMGPU_ALF_CLIP_RIGHT) ? cx1 : g.w,
+                       (clip & VTMGPU_ALF_CLIP_TOP) ? cy0 : 0, (clip & VTMGPU_ALF_CLIP_BOTTOM) ? cy1 : g.h };
+        int pad = clip & (VTMGPU_ALF_PAD_TL | VTMGPU_ALF_PAD_BR);
+        if (anyVb) pad = saVbWindow(&pvb, make_int4(px0, px1, py0, py1), make_int4(cx0, cx1, cy0, cy1), part == 0, part == nparts - 1, pad, win);
+        const int xlo = win[0], xhi = win[1], ylo = win[2], yhi = win[3];
+        const int bxc = (x0 >> g.sx) - SA_HX, byc = (y0 >> g.sy) - SA_HY;
+        if (alfY || ccCb || ccCr) saReplicateBorder(A0, x0 - SA_HX, y0 - SA_HY, xlo, xhi, ylo, yhi, SA_P, SA_T, SA_TH, 3);
+        if (alfCb) saReplicateBorder(A1, bxc, byc, xlo >> g.sx, xhi >> g.sx, ylo >> g.sy, yhi >> g.sy, L.pitchC, tw, th, 3);
+        if (alfCr) saReplicateBorder(A2, bxc, byc, xlo >> g.sx, xhi >> g.sx, ylo >> g.sy, yhi >> g.sy, L.pitchC, tw, th, 3);
+        if (pad)
         {
-          const int li = 2 * bi + 1 + (k >> 1), lj = 2 * bj + 1 + (k & 1);
-          cell[li][lj] = alfCellGeneric(&lumaB[(2 * li + SA_HY - 2) * SA_P + 2 * lj + SA_HX - 2], y0 - 2 + 2 * li, ctuMask, vbL);
+          // no barrier needed in between: the corners lie outside the clamp window's replicated ranges (their sides are not clipped)
+          if (alfY || ccCb || ccCr) saPadCorners(A0, x0 - SA_HX, y0 - SA_HY, cx0, cy0, cx1, cy1, SA_P, tileW, tileH, 3, pad);
+          if (alfCb) saPadCorners(A1, bxc, byc, cx0 >> g.sx, cy0 >> g.sy, cx1 >> g.sx, cy1 >> g.sy, L.pitchC, tileW >> g.sx, tileH >> g.sy, 3, pad);
+          if (alfCr) saPadCorners(A2, bxc, byc, cx0 >> g.sx, cy0 >> g.sy, cx1 >> g.sx, cy1 >> g.sy, L.pitchC, tileW >> g.sx, tileH >> g.sy, 3, pad);
         }
+        __syncthreads();
       }
-      // ring of halo cells: top and bottom cell rows, left and right cell columns
-      for (int q = tid; q < 2 * SA_CELLS + 2 * (SA_CELLR - 2); q += SA_THREADS)
-      {
-        int li, lj;
-        if (q < 2 * SA_CELLS) { li = q < SA_CELLS ? 0 : SA_CELLR - 1; lj = q < SA_CELLS ? q : q - SA_CELLS; }
-        else { const int k = q - 2 * SA_CELLS; li = 1 + (k >> 1); lj = (k & 1) ? SA_CELLS - 1 : 0; }
-        cell[li][lj] = alfCellGeneric(&lumaB[(2 * li + SA_HY - 2) * SA_P + 2 * lj + SA_HX - 2], y0 - 2 + 2 * li, ctuMask, vbL);
-      }
-      __syncthreads();
-    }
 
-    // ---- phase 2: filters; every plane is written once ----------------------------------------------------------------
-    if (alfY)
-    {
-      if (bx >= px0 && bx < px1 && by >= py0 && by < py1)
+      // ---- phase 1: Laplacian cells (luma ALF only) -------------------------------------------------------------------
+      const pel* lumaB = B0;
+      const int bx = x0 + 4 * bj, by = y0 + 4 * bi;
+      const pel* c0 = &lumaB[(4 * bi + SA_HY) * SA_P + 4 * bj + SA_HX];
+      const int yb = by & ctuMask;
+      const bool vbBlk = yb == vbL - 4 || yb == vbL;             // uniform per warp (two block rows) for CTU sizes >= 32
+      if (alfY)
       {
-        pel* out = dstY.p + (size_t)by * dstY.pitch + bx;
-        const int setIdx = ctl.setIdx;
-        if (S.alfWide) alfLumaBlockGeneric(cell, c0, out, dstY.pitch, bi, bj, by, &S.alf->luma[setIdx][0][0], ctuMask, vbL, g.bdL);
+        if (!vbBlk) alfOwnCells(cell, c0, bi, bj);
         else
         {
-          // window = cells (2bi .. 2bi+3) x (2bj .. 2bj+3); row sums stay below 2^16 per lane for any bit depth <= 12.
-          // Blocks at the virtual boundary use 3 of the 4 cell rows and the scale 96 (deriveClassificationBlk :977-1010)
-          const int vb = yb == vbL - 4 ? 1 : (yb == vbL ? 2 : 0);
-          int sumV = 0, sumH = 0, sumD0 = 0, sumD1 = 0;
-#pragma unroll
-          for (int i = 0; i < 4; i++)
+          for (int k = 0; k < 4; k++)
           {
-            if ((vb == 1 && i == 3) || (vb == 2 && i == 0)) continue;
-            const uint4* rp = reinterpret_cast<const uint4*>(&cell[2 * bi + i][2 * bj]);
-            const uint4 q0 = rp[0], q1 = rp[1];
-            const uint32_t vh = q0.x + q0.z + q1.x + q1.z, dd = q0.y + q0.w + q1.y + q1.w;
-            sumV += vh & 0xffff; sumH += vh >> 16; sumD0 += dd & 0xffff; sumD1 += dd >> 16;
+            const int li = 2 * bi + 1 + (k >> 1), lj = 2 * bj + 1 + (k & 1);
+            cell[li][lj] = alfCellGeneric(&lumaB[(2 * li + SA_HY - 2) * SA_P + 2 * lj + SA_HX - 2], y0 - 2 + 2 * li, ctuMask, vbL);
           }
-          int cls, tIdx;
-          alfClassify(sumV, sumH, sumD0, sumD1, vb ? 96 : 64, g.bdL, cls, tIdx);
-          const AlfLumaEntry* e = S.lumaTab + ((size_t)(setIdx * 25 + cls) * 4 + tIdx);
-          const uint32_t maxvP = dup16((1 << g.bdL) - 1);
-          alfLumaBlockFast(c0, out, dstY.pitch, e, maxvP, vb);
         }
-      }
-    }
-    else
-    {
-      // no luma ALF in this CTU: copy (128-bit rows)
-      for (int i = tid; i < SA_TH * (SA_T / 8); i += SA_THREADS)
-      {
-        const int r = i >> 3, gc = i & 7;
-        const int y = y0 + r, x = x0 + 8 * gc;
-        if (y >= py0 && y < py1 && x >= px0 && x < px1)
-          *reinterpret_cast<int4*>(dstY.p + (size_t)y * dstY.pitch + x) = *reinterpret_cast<const int4*>(&lumaB[(r + SA_HY) * SA_P + 8 * gc + SA_HX]);
-      }
-    }
-    if (g.ncomp > 1)
-    {
-      // chroma: one item = 4 horizontally adjacent samples
-      const int tcx0 = x0 >> g.sx, tcy0 = y0 >> g.sy, qShift = 4 - g.sx, quads = (tw >> 2) << thLogC;       // tw / 4 = 1 << qShift
-#pragma unroll 1
-      for (int c = 0; c < 2; c++)
-      {
-        const PlaneDev dstC = S.buf[dstBuf][1 + c];
-        const pel* Bc = c ? B2 : B1;
-        const bool fOn = c ? alfCr : alfCb;
-        const int idc = c ? ccCr : ccCb;
-        ChromaCoef C;
-        if (fOn) C = chromaCoef(&S.alf->chromaTab[c ? ctl.altCr : ctl.altCb]);
-        const int16_t* ccg = S.alf->cc[c][idc ? idc - 1 : 0];
-        for (int j = tid; j < quads; j += SA_THREADS)
+        // ring of halo cells: top and bottom cell rows, left and right cell columns
+        for (int q = tid; q < 2 * SA_CELLS + 2 * (SA_CELLR - 2); q += SA_THREADS)
         {
-          const int r = j >> qShift, qx = (j & ((1 << qShift) - 1)) * 4;
-          const int x = tcx0 + qx, y = tcy0 + r;
-          if (x < (px0 >> g.sx) || x >= (px1 >> g.sx) || y < (py0 >> g.sy) || y >= (py1 >> g.sy)) continue;
-          const pel* cb = &Bc[(r + SA_HY) * L.pitchC + qx + SA_HX];
-          uint2 v = *reinterpret_cast<const uint2*>(cb);
-          if (fOn)
+          int li, lj;
+          if (q < 2 * SA_CELLS) { li = q < SA_CELLS ? 0 : SA_CELLR - 1; lj = q < SA_CELLS ? q : q - SA_CELLS; }
+          else { const int k = q - 2 * SA_CELLS; li = 1 + (k >> 1); lj = (k & 1) ? SA_CELLS - 1 : 0; }
+          cell[li][lj] = alfCellGeneric(&lumaB[(2 * li + SA_HY - 2) * SA_P + 2 * lj + SA_HX - 2], y0 - 2 + 2 * li, ctuMask, vbL);
+        }
+        __syncthreads();
+      }
+
+      // ---- phase 2: filters; every plane is written once ----------------------------------------------------------------
+      if (alfY)
+      {
+        if (bx >= px0 && bx < px1 && by >= py0 && by < py1)
+        {
+          pel* out = dstY.p + (size_t)by * dstY.pitch + bx;
+          const int setIdx = ctl.setIdx;
+          if (S.alfWide) alfLumaBlockGeneric(cell, c0, out, dstY.pitch, bi, bj, by, &S.alf->luma[setIdx][0][0], ctuMask, vbL, g.bdL);
+          else
           {
-            int lim; bool nearVb;
-            vbLimit(y & (ctuH - 1), vbC, 2, lim, nearVb);
-            v = alfChromaQuad(cb, min(1, lim) * L.pitchC, min(2, lim) * L.pitchC, nearVb, C, maxcP);
-          }
-          if (idc)
-          {
-            // CC-ALF row offsets in the luma tile (filterBlkCcAlf :1376-1386)
-            const int ly = (r << g.sy) + SA_HY, lpos = (y << g.sy) & ctuMask;
-            int l1 = SA_P, l2 = -SA_P, l3 = 2 * SA_P;
-            if (lpos == vbL - 2 || lpos == vbL + 1) l3 = SA_P;
-            else if (lpos == vbL - 1 || lpos == vbL) l1 = l2 = l3 = 0;
-            if (g.sx == 1)
-            {
-              const uint2 d = ccAlfQuad420(&lumaB[ly * SA_P + (qx << 1) + SA_HX], l1, l2, l3, S.alf->ccB[c][idc - 1], maxcP, halfP);
-              v.x = addClamp0(v.x, d.x, maxcP);
-              v.y = addClamp0(v.y, d.y, maxcP);
-            }
-            else
-            {
-              int res[4] = { (int)(v.x & 0xffff), (int)(v.x >> 16), (int)(v.y & 0xffff), (int)(v.y >> 16) };
-              int cc[7];
+            // window = cells (2bi .. 2bi+3) x (2bj .. 2bj+3); row sums stay below 2^16 per lane for any bit depth <= 12.
+            // Blocks at the virtual boundary use 3 of the 4 cell rows and the scale 96 (deriveClassificationBlk :977-1010)
+            const int vb = yb == vbL - 4 ? 1 : (yb == vbL ? 2 : 0);
+            int sumV = 0, sumH = 0, sumD0 = 0, sumD1 = 0;
 #pragma unroll
-              for (int k = 0; k < 7; k++) cc[k] = __ldg(&ccg[k]);
-#pragma unroll
-              for (int q = 0; q < 4; q++)
-              {
-                const pel* l = &lumaB[ly * SA_P + qx + q + SA_HX];
-                const int cur = l[0];
-                int s = cc[0] * (l[l2] - cur) + cc[1] * (l[-1] - cur) + cc[2] * (l[1] - cur) + cc[3] * (l[l1 - 1] - cur) + cc[4] * (l[l1] - cur) +
-                        cc[5] * (l[l1 + 1] - cur) + cc[6] * (l[l3] - cur);
-                s = (s + 64) >> 7;
-                s = clip3(0, maxc, s + half) - half;
-                res[q] = clip3(0, maxc, res[q] + s);
-              }
-              v = make_uint2((uint32_t)res[0] | (uint32_t)res[1] << 16, (uint32_t)res[2] | (uint32_t)res[3] << 16);
+            for (int i = 0; i < 4; i++)
+            {
+              if ((vb == 1 && i == 3) || (vb == 2 && i == 0)) continue;
+              const uint4* rp = reinterpret_cast<const uint4*>(&cell[2 * bi + i][2 * bj]);
+              const uint4 q0 = rp[0], q1 = rp[1];
+              const uint32_t vh = q0.x + q0.z + q1.x + q1.z, dd = q0.y + q0.w + q1.y + q1.w;
+              sumV += vh & 0xffff; sumH += vh >> 16; sumD0 += dd & 0xffff; sumD1 += dd >> 16;
             }
+            int cls, tIdx;
+            alfClassify(sumV, sumH, sumD0, sumD1, vb ? 96 : 64, g.bdL, cls, tIdx);
+            const AlfLumaEntry* e = S.lumaTab + ((size_t)(setIdx * 25 + cls) * 4 + tIdx);
+            const uint32_t maxvP = dup16((1 << g.bdL) - 1);
+            alfLumaBlockFast(c0, out, dstY.pitch, e, maxvP, vb);
           }
-          *reinterpret_cast<uint2*>(dstC.p + (size_t)y * dstC.pitch + x) = v;
         }
       }
-    }
-    if (part + 1 < nparts) __syncthreads();                  // the next part re-pads the tile and recomputes the cells
+      else
+      {
+        // no luma ALF in this CTU: copy (128-bit rows)
+        for (int i = tid; i < SA_TH * (SA_T / 8); i += SA_THREADS)
+        {
+          const int r = i >> 3, gc = i & 7;
+          const int y = y0 + r, x = x0 + 8 * gc;
+          if (y >= py0 && y < py1 && x >= px0 && x < px1)
+            *reinterpret_cast<int4*>(dstY.p + (size_t)y * dstY.pitch + x) = *reinterpret_cast<const int4*>(&lumaB[(r + SA_HY) * SA_P + 8 * gc + SA_HX]);
+        }
+      }
+      if (g.ncomp > 1)
+      {
+        // chroma: one item = 4 horizontally adjacent samples
+        const int tcx0 = x0 >> g.sx, tcy0 = y0 >> g.sy, qShift = 4 - g.sx, quads = (tw >> 2) << thLogC;       // tw / 4 = 1 << qShift
+#pragma unroll 1
+        for (int c = 0; c < 2; c++)
+        {
+          const PlaneDev dstC = S.buf[dstBuf][1 + c];
+          const pel* Bc = c ? B2 : B1;
+          const bool fOn = c ? alfCr : alfCb;
+          const int idc = c ? ccCr : ccCb;
+          ChromaCoef C;
+          if (fOn) C = chromaCoef(&S.alf->chromaTab[c ? ctl.altCr : ctl.altCb]);
+          const int16_t* ccg = S.alf->cc[c][idc ? idc - 1 : 0];
+          for (int j = tid; j < quads; j += SA_THREADS)
+          {
+            const int r = j >> qShift, qx = (j & ((1 << qShift) - 1)) * 4;
+            const int x = tcx0 + qx, y = tcy0 + r;
+            if (x < (px0 >> g.sx) || x >= (px1 >> g.sx) || y < (py0 >> g.sy) || y >= (py1 >> g.sy)) continue;
+            const pel* cb = &Bc[(r + SA_HY) * L.pitchC + qx + SA_HX];
+            uint2 v = *reinterpret_cast<const uint2*>(cb);
+            if (fOn)
+            {
+              int lim; bool nearVb;
+              vbLimit(y & (ctuH - 1), vbC, 2, lim, nearVb);
+              v = alfChromaQuad(cb, min(1, lim) * L.pitchC, min(2, lim) * L.pitchC, nearVb, C, maxcP);
+            }
+            if (idc)
+            {
+              // CC-ALF row offsets in the luma tile (filterBlkCcAlf :1376-1386)
+              const int ly = (r << g.sy) + SA_HY, lpos = (y << g.sy) & ctuMask;
+              int l1 = SA_P, l2 = -SA_P, l3 = 2 * SA_P;
+              if (lpos == vbL - 2 || lpos == vbL + 1) l3 = SA_P;
+              else if (lpos == vbL - 1 || lpos == vbL) l1 = l2 = l3 = 0;
+              if (g.sx == 1)
+              {
+                const uint2 d = ccAlfQuad420(&lumaB[ly * SA_P + (qx << 1) + SA_HX], l1, l2, l3, S.alf->ccB[c][idc - 1], maxcP, halfP);
+                v.x = addClamp0(v.x, d.x, maxcP);
+                v.y = addClamp0(v.y, d.y, maxcP);
+              }
+              else
+              {
+                int res[4] = { (int)(v.x & 0xffff), (int)(v.x >> 16), (int)(v.y & 0xffff), (int)(v.y >> 16) };
+                int cc[7];
+#pragma unroll
+                for (int k = 0; k < 7; k++) cc[k] = __ldg(&ccg[k]);
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                {
+                  const pel* l = &lumaB[ly * SA_P + qx + q + SA_HX];
+                  const int cur = l[0];
+                  int s = cc[0] * (l[l2] - cur) + cc[1] * (l[-1] - cur) + cc[2] * (l[1] - cur) + cc[3] * (l[l1 - 1] - cur) + cc[4] * (l[l1] - cur) +
+                          cc[5] * (l[l1 + 1] - cur) + cc[6] * (l[l3] - cur);
+                  s = (s + 64) >> 7;
+                  s = clip3(0, maxc, s + half) - half;
+                  res[q] = clip3(0, maxc, res[q] + s);
+                }
+                v = make_uint2((uint32_t)res[0] | (uint32_t)res[1] << 16, (uint32_t)res[2] | (uint32_t)res[3] << 16);
+              }
+            }
+            *reinterpret_cast<uint2*>(dstC.p + (size_t)y * dstC.pitch + x) = v;
+          }
+        }
+      }
+      if (part + 1 < nparts) __syncthreads();                  // the next part re-pads the tile and recomputes the cells
     }
     __syncthreads();                                         // all reads of stage buffers / B / cells are done before they are refilled
     cur = nxt;
