@@ -234,7 +234,8 @@ STREAMS = [("ra_416x240.bin", 8), ("ld444_1080p.bin", 16), ("ra_1080p.bin", 32),
            ("vb_832x480.bin", 5),         # signalled virtual boundaries inside CTUs and on CTU edges
            ("ld422_416x240.bin", 4),      # 4:2:2, full CTC tool set
            ("ctu64_416x240.bin", 4), ("bd12_416x240.bin", 3), ("dbfoffs_416x240.bin", 4),   # CTU 64, 12-bit, beta / tc offsets
-           ("scc444_416x240.bin", 3), ("ldp_416x240.bin", 4)]   # palette / IBC / BDPCM on screen content (4:4:4); P slices
+           ("scc444_416x240.bin", 3), ("ldp_416x240.bin", 4),
+           ("ra_full_832x480.bin", 6)]    # full CTC tool set at a size with 128-wide CUs   # palette / IBC / BDPCM on screen content (4:4:4); P slices
 
 
 @pytest.mark.parametrize("stream,pictures", STREAMS)

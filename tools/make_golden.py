@@ -43,6 +43,7 @@ SELECT = {
     "dbfoffs_416x240": [1, 3],         # slice-level beta / tc offsets
     "scc444_416x240": [0, 1],          # palette / IBC / BDPCM on blocky 4:4:4 content
     "ldp_416x240": [1, 3],             # P slices
+    "ra_full_832x480": [1, 4],         # full CTC tool set with 128-wide CUs (affine / sub-block edges, long filters)
     "slices_832x480": [0, 3],          # 3x3 tiles in two raster-scan slices, no filtering across slices (ALF corner padding)
 }
 
