@@ -10,15 +10,16 @@
  *                                        SampleAdaptiveOffset::create/destroy  CommonLib/SampleAdaptiveOffset.cpp:127,143
  *                                        AdaptiveLoopFilter::create/destroy    CommonLib/AdaptiveLoopFilter.cpp:715,816
  *   vtmgpu_upload / vtmgpu_download     Picture::getRecoBuf() planes          CommonLib/Picture.cpp:317  (PelStorage, int16 Pel)
- *   vtmgpu_set_deblock + vtmgpu_deblock LoopFilter::loopFilterPic             CommonLib/LoopFilter.cpp:145
+ *   vtmgpu_set_deblock[_sparse] + vtmgpu_deblock   LoopFilter::loopFilterPic  CommonLib/LoopFilter.cpp:145
  *                                        (edge filtering xEdgeFilterLuma :844, xEdgeFilterChroma :1087; the per-4x4
  *                                        bS / tc / beta / filter-length DERIVATION :261-812 stays on the host and arrives
- *                                        here as packed segment records)
+ *                                        here as packed segment records -- picture-sized arrays or lists of the active units;
+ *                                        with LADF, deriveLADFShift :815, the records carry QPs and tc / beta are derived here)
  *   vtmgpu_sao_reconstruct              SampleAdaptiveOffset::xReconstructBlkSAOParams   SampleAdaptiveOffset.cpp:266
  *   vtmgpu_set_sao + vtmgpu_sao         SampleAdaptiveOffset::SAOProcess      CommonLib/SampleAdaptiveOffset.cpp:618
  *   vtmgpu_set_alf + vtmgpu_alf         AdaptiveLoopFilter::ALFProcess        CommonLib/AdaptiveLoopFilter.cpp:393
  *                                        (incl. reconstructCoeffAPSs :620, deriveClassificationBlk :873, filterBlk :1084,
- *                                        filterBlkCcAlf :1327)
+ *                                        filterBlkCcAlf :1327, the clip / pad path at slice, tile and virtual boundaries :452-555)
  *   vtmgpu_filter                       DecLib::executeLoopFilters            DecoderLib/DecLib.cpp:560  (whole chain, batched)
  *
  * Error convention: every call returns 0 on success, non-zero on failure; vtmgpu_last_error() gives the text
@@ -51,7 +52,7 @@ typedef struct vtmgpu_seq_params
   int32_t chroma_format;
   int32_t bit_depth_luma;    /* 8..12 */
   int32_t bit_depth_chroma;  /* 8..12 */
-  int32_t ctu_size;          /* 32, 64 or 128 (sps CTUSize) */
+  int32_t ctu_size;          /* 64 or 128 (sps CTUSize; 32 is rejected by vtmgpu_create: the ALF kernel works on 64x64 tiles of ONE CTU) */
   int32_t capacity;          /* number of picture slots (>= 1) */
   int32_t device;            /* CUDA device ordinal */
 } vtmgpu_seq_params;
