@@ -546,21 +546,27 @@ void Deriver::emitChroma(const CodingUnit& cu, int edge)
     const bool large = m_st.lenP[COMPONENT_Cb][x][y] >= 3 && m_st.lenQ[COMPONENT_Cb][x][y] >= 3;
     const bool ctb   = m_dir == HOR && pos.y % (int)cuP.slice->getSPS()->getCTUSize() == 0;
     uint64_t rec = 0;
+    const TransformUnit *tuQp = nullptr, *tuPp = nullptr;      // the same for Cb and Cr: looked up once per unit, when needed
     for (int c = 0; c < 2; c++)
     {
       if (!(bsC[c] == 2 || (large && bsC[c] == 1))) continue;
       const ComponentID comp = ComponentID(c + 1);
       const ClpRng& clp = m_ctuSlice->clpRng(comp);
       CHECK(clp.min != 0 || clp.max != (1 << bd) - 1, "vtmgpu shim: non-default chroma clipping range");
-      const int shP = cuP.Y().valid() ? 0 : getComponentScaleX(COMPONENT_Cb, cuP.firstPU->chromaFormat);
-      const int svP = cuP.Y().valid() ? 0 : getComponentScaleY(COMPONENT_Cb, cuP.firstPU->chromaFormat);
-      const int shQ = hasLuma ? 0 : getComponentScaleX(COMPONENT_Cb, cu.firstPU->chromaFormat);
-      const int svQ = hasLuma ? 0 : getComponentScaleY(COMPONENT_Cb, cu.firstPU->chromaFormat);
-      const Position posQ(pos.x >> shQ, pos.y >> svQ);
-      const Position posP1(pos.x >> shP, pos.y >> svP);
-      const Position posP = m_dir == VER ? posP1.offset(-1, 0) : posP1.offset(0, -1);
-      const TransformUnit& tuQ = *cu.cs->getTU(posQ, cu.chType);
-      const TransformUnit& tuP = *cuP.cs->getTU(posP, cuP.chType);
+      if (!tuQp)
+      {
+        const int shP = cuP.Y().valid() ? 0 : getComponentScaleX(COMPONENT_Cb, cuP.firstPU->chromaFormat);
+        const int svP = cuP.Y().valid() ? 0 : getComponentScaleY(COMPONENT_Cb, cuP.firstPU->chromaFormat);
+        const int shQ = hasLuma ? 0 : getComponentScaleX(COMPONENT_Cb, cu.firstPU->chromaFormat);
+        const int svQ = hasLuma ? 0 : getComponentScaleY(COMPONENT_Cb, cu.firstPU->chromaFormat);
+        const Position posQ(pos.x >> shQ, pos.y >> svQ);
+        const Position posP1(pos.x >> shP, pos.y >> svP);
+        const Position posP = m_dir == VER ? posP1.offset(-1, 0) : posP1.offset(0, -1);
+        tuQp = cu.cs->getTU(posQ, cu.chType);
+        tuPp = cuP.cs->getTU(posP, cuP.chType);
+      }
+      const TransformUnit& tuQ = *tuQp;
+      const TransformUnit& tuP = *tuPp;
       const QpParam qpP(tuP, comp, -MAX_INT, false);
       const QpParam qpQ(tuQ, comp, -MAX_INT, false);
       const int bdOff = tuP.cs->sps->getQpBDOffset(toChannelType(comp));
