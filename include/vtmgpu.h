@@ -52,7 +52,7 @@ typedef struct vtmgpu_seq_params
   int32_t chroma_format;
   int32_t bit_depth_luma;    /* 8..12 */
   int32_t bit_depth_chroma;  /* 8..12 */
-  int32_t ctu_size;          /* 64 or 128 (sps CTUSize; 32 is rejected by vtmgpu_create: the ALF kernel works on 64x64 tiles of ONE CTU) */
+  int32_t ctu_size;          /* 32, 64 or 128 (sps CTUSize) */
   int32_t capacity;          /* number of picture slots (>= 1) */
   int32_t device;            /* CUDA device ordinal */
 } vtmgpu_seq_params;

@@ -70,6 +70,7 @@ STREAMS = {
     "ld422_416x240": (416, 240, 422, 4, 422, 14, 30, [LD], ["--ChromaFormatIDC=422"], 0),
     # sequence-level variants of the hot path: CTU 64, 12-bit internal depth (this reference snapshot cannot decode its own 8-bit streams), non-zero deblocking offsets
     "ctu64_416x240": (416, 240, 420, 4, 64, 14, 32, [RA], K + ["--CTUSize=64"], 0),
+    "ctu32_416x240": (416, 240, 420, 4, 32, 14, 32, [RA], K + ["--CTUSize=32"], 0),
     "bd12_416x240": (416, 240, 420, 3, 12, 14, 32, [RA], K + ["--InternalBitDepth=12"], 0),
     # (4:0:0 makes the encoder of this reference snapshot abort, TypeDef.h:1229: monochrome is covered by seeded pictures vs the oracle only)
     "dbfoffs_416x240": (416, 240, 420, 4, 66, 14, 34, [LD], K + ["--LoopFilterBetaOffset_div2=3", "--LoopFilterTcOffset_div2=-4"], 0),

@@ -51,6 +51,8 @@ SYNTH = [
     (384, 256, 1, 8, 128, 0.8),       # 8-bit
     (384, 256, 1, 12, 128, 0.8),      # 12-bit
     (384, 320, 1, 10, 64, 0.8),       # CTU 64
+    (416, 240, 1, 10, 32, 0.8),       # CTU 32: 2 x 2 CTUs per ALF tile, partial tiles
+    (328, 200, 3, 10, 32, 1.0),       # CTU 32, 4:4:4, ragged
     (1920, 1080, 1, 10, 128, 0.5),
     # degenerate geometries: pictures smaller than one tile / one TMA box, single rows of units
     (8, 8, 1, 10, 128, 1.0),
@@ -73,7 +75,8 @@ def test_synthetic_vs_oracle(w, h, cf, bd, ctu, density):
     _eq(fused, want["final"], "fused chain")
 
 
-@pytest.mark.parametrize("w,h,cf,ctu", [(512, 384, 1, 128), (456, 264, 3, 128), (448, 256, 2, 64), (320, 320, 0, 64), (1920, 1080, 1, 128)])
+@pytest.mark.parametrize("w,h,cf,ctu", [(512, 384, 1, 128), (456, 264, 3, 128), (448, 256, 2, 64), (320, 320, 0, 64), (1920, 1080, 1, 128),
+                                         (416, 240, 1, 32), (328, 200, 3, 32)])
 def test_partition_boundaries_vs_oracle(w, h, cf, ctu):
     """ALF at slice / tile boundaries that must not be crossed: random per-CTU clip and corner-pad flags,
     forced-on ALF / CC-ALF; the fixtures tiles_* / slices_* pin the same path against the reference itself."""
@@ -109,6 +112,8 @@ VB_CASES = [
     (448, 256, 2, 64, [40, 104, 232], [24, 120, 184], False),   # 4:2:2, CTU 64, three per direction, 2 x 2 parts in one tile
     (320, 320, 0, 64, [160], [], False),                  # 4:0:0
     (1920, 1080, 1, 128, [960], [544], False),
+    (448, 256, 1, 32, [40, 104, 168], [24, 56, 200], True),     # CTU 32: CTU cuts and virtual-boundary cuts in one tile
+    (416, 240, 1, 32, [32, 64, 224], [96], False),              # CTU 32: boundaries on CTU edges
 ]
 
 
@@ -233,7 +238,7 @@ STREAMS = [("ra_416x240.bin", 8), ("ld444_1080p.bin", 16), ("ra_1080p.bin", 32),
            ("ladf_832x480.bin", 5),       # LADF: deblocking thresholds derived on the device
            ("vb_832x480.bin", 5),         # signalled virtual boundaries inside CTUs and on CTU edges
            ("ld422_416x240.bin", 4),      # 4:2:2, full CTC tool set
-           ("ctu64_416x240.bin", 4), ("bd12_416x240.bin", 3), ("dbfoffs_416x240.bin", 4),   # CTU 64, 12-bit, beta / tc offsets
+           ("ctu64_416x240.bin", 4), ("ctu32_416x240.bin", 4), ("bd12_416x240.bin", 3), ("dbfoffs_416x240.bin", 4),   # CTU 64, 12-bit, beta / tc offsets
            ("scc444_416x240.bin", 3), ("ldp_416x240.bin", 4),
            ("ra_full_832x480.bin", 6)]    # full CTC tool set at a size with 128-wide CUs   # palette / IBC / BDPCM on screen content (4:4:4); P slices
 

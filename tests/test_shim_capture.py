@@ -16,7 +16,7 @@ from vvc_b200 import capture
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DEC = os.path.join(ROOT, "oracle", "_ref", "DecoderApp_cap")
-STREAMS = ["ra_416x240", "ra_full_832x480", "ld422_416x240", "ctu64_416x240", "bd12_416x240", "dbfoffs_416x240", "scc444_416x240", "ldp_416x240", "tiles_832x480", "slices_832x480", "slices45_832x480", "ladf_832x480", "vb_832x480"]
+STREAMS = ["ra_416x240", "ra_full_832x480", "ld422_416x240", "ctu64_416x240", "ctu32_416x240", "bd12_416x240", "dbfoffs_416x240", "scc444_416x240", "ldp_416x240", "tiles_832x480", "slices_832x480", "slices45_832x480", "ladf_832x480", "vb_832x480"]
 PLANE_PREFIXES = ("pre_", "dbf_", "sao_", "alf_")
 
 

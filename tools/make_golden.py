@@ -39,6 +39,7 @@ SELECT = {
     "vb_832x480": [0, 2],              # signalled virtual boundaries inside CTUs and on CTU edges
     "ld422_416x240": [0, 2],           # 4:2:2: chroma deblocking grid / QP mapping, ALF and CC-ALF with sx = 1, sy = 0
     "ctu64_416x240": [0, 2],           # CTU 64: tile = CTU in k_alf, 16 chroma rows per CTU row in the SAO / ALF boundary logic
+    "ctu32_416x240": [0, 2],           # CTU 32: four CTUs per 64x64 ALF tile
     "bd12_416x240": [0, 1],            # 12-bit: tc / beta scaling, clip tables, IDP operand ranges
     "dbfoffs_416x240": [1, 3],         # slice-level beta / tc offsets
     "scc444_416x240": [0, 1],          # palette / IBC / BDPCM on blocky 4:4:4 content

@@ -75,7 +75,7 @@ __host__ __device__ inline SaLayout saLayout(int sx, int sy, int ncomp)
   L.chromaBytes = ncomp > 1 ? L.rowsC * L.pitchC * 2 : 0;
   L.offCell = 2 * (L.lumaBytes + 2 * L.chromaBytes);
   L.offPar = L.offCell + SA_CELLR * SA_CELLP * 8;
-  L.offBar = L.offPar + 2 * (int)sizeof(CtuCtlDev);
+  L.offBar = L.offPar + 2 * 4 * (int)sizeof(CtuCtlDev);      // per stage: the control records of the (up to 2 x 2) CTUs under the tile
   L.total = L.offBar + 16;
   return L;
 }
@@ -110,42 +110,65 @@ __device__ __noinline__ void saReplicateBorder(pel* s, int bx0, int by0, int xlo
 // raster-scan slices (ALFProcess :478-488, padBorderPel): the CTU's top-left (bottom-right) neighbour is in another slice
 // while the adjacent ones are not -- in the corner outside the CTU [cx0,cx1) x [cy0,cy1) every row takes the sample of the
 // CTU's first (last) column of the same row.  Rows above / below the CTU hold real samples here (those sides are not clipped).
-__device__ __forceinline__ void saPadCorners(pel* s, int bx0, int by0, int cx0, int cy0, int cx1, int cy1, int pitch, int tw, int th, int margin, int clip)
+// pad = the pad flags of the part in flight (the caller keeps them only for the part that holds that corner of the CTU).
+__device__ __forceinline__ void saPadCorners(pel* s, int bx0, int by0, int cx0, int cy0, int cx1, int cy1, int pitch, int margin, int pad)
 {
   const int t = threadIdx.x;
   if (t >= 2 * margin * margin) return;
   const bool br = t >= margin * margin;
   const int k = br ? t - margin * margin : t, dy = k / margin, dx = k - dy * margin;
-  const int tx0 = bx0 + SA_HX, ty0 = by0 + SA_HY;                            // tile origin in plane coordinates
   if (!br)
   {
-    if (!(clip & VTMGPU_ALF_PAD_TL) || tx0 != cx0 || ty0 != cy0) return;
+    if (!(pad & VTMGPU_ALF_PAD_TL)) return;
     pel* row = s + (cy0 - 1 - dy - by0) * pitch - bx0;
     row[cx0 - 1 - dx] = row[cx0];
   }
   else
   {
-    if (!(clip & VTMGPU_ALF_PAD_BR) || tx0 + tw != cx1 || ty0 + th != cy1) return;
+    if (!(pad & VTMGPU_ALF_PAD_BR)) return;
     pel* row = s + (cy1 + dy - by0) * pitch - bx0;
     row[cx1 + dx] = row[cx1 - 1];
   }
 }
 
-// signalled virtual boundaries (cold path, kept out of line): cuts strictly inside the tile, and whether any boundary touches it
-__device__ __noinline__ int saVbCuts(const VbDev* v, int x0, int y0, int tileW, int tileH)
+// Cuts of a tile (cold path, kept out of line).  A tile is filtered in parts when a signalled virtual boundary lies strictly inside it
+// or when it covers several CTUs (CTU size 32: every CTU has its own control record and clip flags).  xs / ys receive the part
+// boundaries in ascending order, first = tile origin, last = tile end (at most 5 entries each: virtual boundaries are at least one
+// CTU apart).  Returns nx | ny << 4 | touch << 8, touch = a virtual boundary lies on or inside the tile.
+__device__ __noinline__ int saTileCuts(const VbDev* v, int ctu, int x0, int y0, int tileW, int tileH, int* xs, int* ys)
 {
-  int cutX = 0, cutY = 0, touch = 0;
+  int touch = 0, n[2];
 #pragma unroll 1
-  for (int i = 0; i < v->nv; i++) { const int b = v->x[i]; if (b > x0 && b < x0 + tileW) cutX = b; touch |= b >= x0 && b <= x0 + tileW; }
+  for (int dir = 0; dir < 2; dir++)
+  {
+    int* o = dir ? ys : xs;
+    const int lo = dir ? y0 : x0, hi = lo + (dir ? tileH : tileW), nb = dir ? v->nh : v->nv;
+    int m = 0;
+    o[m++] = lo;
+    if (ctu < SA_T && lo + ctu < hi) o[m++] = lo + ctu;
 #pragma unroll 1
-  for (int i = 0; i < v->nh; i++) { const int b = v->y[i]; if (b > y0 && b < y0 + tileH) cutY = b; touch |= b >= y0 && b <= y0 + tileH; }
-  return cutX | cutY << 14 | touch << 28;                 // positions < 2^14
+    for (int i = 0; i < nb; i++)
+    {
+      const int b = dir ? v->y[i] : v->x[i];
+      touch |= b >= lo && b <= hi;
+      if (b <= lo || b >= hi) continue;
+      bool dup = false;
+      for (int k = 0; k < m; k++) dup |= o[k] == b;
+      if (dup || m >= 4) continue;
+      int k = m++;
+      while (k > 0 && o[k - 1] > b) { o[k] = o[k - 1]; k--; }      // insertion keeps the list sorted
+      o[k] = b;
+    }
+    o[m++] = hi;
+    n[dir] = m - 1;
+  }
+  return n[0] | n[1] << 4 | touch << 8;
 }
 
 // a virtual boundary on an edge of the part (tile edge, CTU edge or the cut) closes that side of the clamp window win = {xlo, xhi,
-// ylo, yhi}; the raster-slice corner pads belong to the part that holds the CTU's corner and are dropped when a virtual boundary
-// clips that corner's sides (isCrossedByVirtualBoundaries :178-200).  Returns the pad flags that remain.
-__device__ __noinline__ int saVbWindow(const VbDev* v, int4 part, int4 ctu, bool first, bool last, int pad, int* win)
+// ylo, yhi}; the raster-slice corner pads are dropped when a virtual boundary clips that corner's sides
+// (isCrossedByVirtualBoundaries :178-200).  Returns the pad flags that remain.
+__device__ __noinline__ int saVbWindow(const VbDev* v, int4 part, int4 ctu, int pad, int* win)
 {
   bool cL = false, cR = false, cT = false, cB = false;
 #pragma unroll 1
@@ -164,8 +187,8 @@ __device__ __noinline__ int saVbWindow(const VbDev* v, int4 part, int4 ctu, bool
     if (b == part.w) win[3] = b;
     cT |= b == ctu.z; cB |= b == ctu.w;
   }
-  if (!first || cL || cT) pad &= ~VTMGPU_ALF_PAD_TL;
-  if (!last || cR || cB) pad &= ~VTMGPU_ALF_PAD_BR;
+  if (cL || cT) pad &= ~VTMGPU_ALF_PAD_TL;
+  if (cR || cB) pad &= ~VTMGPU_ALF_PAD_BR;
   return pad;
 }
 
@@ -518,7 +541,13 @@ __device__ __forceinline__ void saPrefetch(unsigned char* smraw, const SaLayout&
       tmaLoad2D(smraw + L.offA(stage, 2), maps + 2, (x0 >> g.sx) - SA_HX, (y0 >> g.sy) - SA_HY, bar);
     }
   }
-  if (tid == 32) cpAsync16(reinterpret_cast<CtuCtlDev*>(smraw + L.offPar) + stage, &S.ctuCtl[(y0 >> g.ctuLog2) * g.wCtus + (x0 >> g.ctuLog2)]);
+  // control record(s) of the CTU(s) under the tile: one for CTU sizes >= 64, 2 x 2 for CTU size 32 (record k = CTU (k & 1, k >> 1))
+  if (tid >= 32 && tid < 36)
+  {
+    const int k = tid - 32, cx = (x0 >> g.ctuLog2) + (k & 1), cy = (y0 >> g.ctuLog2) + (k >> 1);
+    if ((k == 0 || g.ctu < SA_T) && cx < g.wCtus && cy < g.hCtus)
+      cpAsync16(reinterpret_cast<CtuCtlDev*>(smraw + L.offPar) + stage * 4 + k, &S.ctuCtl[cy * g.wCtus + cx]);
+  }
 }
 
 // kVirtualBoundaries = false compiles the part loop of signalled virtual boundaries away (it costs the common path 10 % otherwise);
@@ -580,33 +609,26 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDe
     __syncthreads();                                         // tile and its parameters are in shared memory
 
     const int x0 = cur.tx * SA_T, y0 = (cur.ty + ty0) * SA_TH;
-    const CtuCtlDev ctl = reinterpret_cast<const CtuCtlDev*>(smraw + L.offPar)[stage];
     const bool alfOn = S.alfOn != 0;
-    const bool alfY = alfOn && ctl.enY != 0, alfCb = alfOn && ctl.enCb != 0, alfCr = alfOn && ctl.enCr != 0;
-    const int ccCb = alfOn ? ctl.ccCb : 0, ccCr = alfOn ? ctl.ccCr : 0;
     pel* const A0 = reinterpret_cast<pel*>(smraw + L.offA(stage, 0));
     pel* const A1 = reinterpret_cast<pel*>(smraw + L.offA(stage, 1));
     pel* const A2 = reinterpret_cast<pel*>(smraw + L.offA(stage, 2));
     // Parts of the tile.  Normally one: the whole tile.  Signalled virtual boundaries (vtmgpu_virtual_boundaries, multiples of 8
-    // luma samples, at least a CTU apart) cut a tile into up to 2 x 2 parts that the reference filters as separately padded blocks
-    // (ALFProcess :452-490); each part is then filtered from its own padded copy of the tile.
-    const int clip = ctl.clip;
+    // luma samples, at least a CTU apart) cut a tile into parts that the reference filters as separately padded blocks
+    // (ALFProcess :452-490), and with CTU size 32 a tile covers 2 x 2 CTUs with their own control records and clip flags; each
+    // part is then filtered from its own padded copy of the tile.
     const int tileW = min(SA_T, g.w - x0), tileH = min(SA_TH, g.h - y0);          // the last tile of a row / column may be partial
-    const int cx0 = x0 & ~ctuMask, cy0 = y0 & ~ctuMask, cx1 = min(cx0 + g.ctu, g.w), cy1 = min(cy0 + g.ctu, g.h);
     const VbDev& pvb = S.vbAlf;
     const bool anyVb = kVirtualBoundaries && alfOn && (pvb.nv | pvb.nh) != 0;
-    int cutX = 0, cutY = 0;
+    int xs[5], ys[5], nx = 1, ny = 1;
     bool vbTile = false;
-    if (anyVb)
+    xs[0] = x0; xs[1] = x0 + tileW; ys[0] = y0; ys[1] = y0 + tileH;
+    if (kVirtualBoundaries && (anyVb || g.ctu < SA_T))
     {
-      const int r = saVbCuts(&pvb, x0, y0, tileW, tileH);
-      cutX = r & 0x3fff; cutY = (r >> 14) & 0x3fff; vbTile = (r >> 28) != 0;
+      const int r = saTileCuts(&pvb, g.ctu, x0, y0, tileW, tileH, xs, ys);
+      nx = r & 15; ny = (r >> 4) & 15; vbTile = anyVb && (r >> 8) != 0;
     }
-    const int nparts = (cutX ? 2 : 1) * (cutY ? 2 : 1);
-    // tiles on the picture border: replicate the border samples into the zero-filled outside
-    // (= UnitBuf::extendBorderPel of the ALF input, AdaptiveLoopFilter.cpp:411); tiles of a CTU with a slice / tile / virtual
-    // boundary the filter must not read across: the same replication at the clipped sides (:452-490)
-    const bool onBorder = x0 == 0 || y0 == 0 || x0 + SA_T + 8 > g.w || y0 + SA_TH + 8 > g.h || clip != 0 || vbTile;
+    const int nparts = nx * ny;
     const pel* const B0 = A0;
     const pel* const B1 = A1;
     const pel* const B2 = A2;
@@ -614,9 +636,15 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDe
 #pragma unroll 1
     for (int part = 0; part < nparts; part++)
     {
-      const int pi = cutX ? (part & 1) : 0, pj = cutX ? (part >> 1) : part;
-      const int px0 = pi ? cutX : x0, px1 = (cutX && !pi) ? cutX : x0 + tileW;      // luma rectangle of this part
-      const int py0 = pj ? cutY : y0, py1 = (cutY && !pj) ? cutY : y0 + tileH;
+      const int pj = part / nx, pi = part - pj * nx;
+      const int px0 = xs[pi], px1 = xs[pi + 1], py0 = ys[pj], py1 = ys[pj + 1];       // luma rectangle of this part
+      // control record of the part's CTU
+      const int cidx = (kVirtualBoundaries && g.ctu < SA_T) ? (((px0 - x0) >> g.ctuLog2) | ((py0 - y0) >> g.ctuLog2) << 1) : 0;
+      const CtuCtlDev ctl = reinterpret_cast<const CtuCtlDev*>(smraw + L.offPar)[stage * 4 + cidx];
+      const bool alfY = alfOn && ctl.enY != 0, alfCb = alfOn && ctl.enCb != 0, alfCr = alfOn && ctl.enCr != 0;
+      const int ccCb = alfOn ? ctl.ccCb : 0, ccCr = alfOn ? ctl.ccCr : 0;
+      const int clip = ctl.clip;
+      const int cx0 = px0 & ~ctuMask, cy0 = py0 & ~ctuMask, cx1 = min(cx0 + g.ctu, g.w), cy1 = min(cy0 + g.ctu, g.h);
       if (nparts > 1)
       {
         // the padding of a part overwrites its neighbours' samples: the first part saves the tile, the others start from that copy
@@ -627,12 +655,18 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDe
         else           { for (int i = tid; i < n16; i += SA_THREADS) stg[i] = scr[i]; }
         __syncthreads();
       }
+      // tiles on the picture border: replicate the border samples into the zero-filled outside
+      // (= UnitBuf::extendBorderPel of the ALF input, AdaptiveLoopFilter.cpp:411); parts of a CTU with a slice / tile / virtual
+      // boundary the filter must not read across: the same replication at the clipped sides (:452-490)
+      const bool onBorder = x0 == 0 || y0 == 0 || x0 + SA_T + 8 > g.w || y0 + SA_TH + 8 > g.h || clip != 0 || vbTile;
       if (onBorder)
       {
         int win[4] = { (clip & VTMGPU_ALF_CLIP_LEFT) ? cx0 : 0, (clip & VTMGPU_ALF_CLIP_RIGHT) ? cx1 : g.w,
                        (clip & VTMGPU_ALF_CLIP_TOP) ? cy0 : 0, (clip & VTMGPU_ALF_CLIP_BOTTOM) ? cy1 : g.h };
-        int pad = clip & (VTMGPU_ALF_PAD_TL | VTMGPU_ALF_PAD_BR);
-        if (anyVb) pad = saVbWindow(&pvb, make_int4(px0, px1, py0, py1), make_int4(cx0, cx1, cy0, cy1), part == 0, part == nparts - 1, pad, win);
+        int pad = clip & (VTMGPU_ALF_PAD_TL | VTMGPU_ALF_PAD_BR);      // only for the part that holds that corner of the CTU
+        if (px0 != cx0 || py0 != cy0) pad &= ~VTMGPU_ALF_PAD_TL;
+        if (px1 != cx1 || py1 != cy1) pad &= ~VTMGPU_ALF_PAD_BR;
+        if (anyVb) pad = saVbWindow(&pvb, make_int4(px0, px1, py0, py1), make_int4(cx0, cx1, cy0, cy1), pad, win);
         const int xlo = win[0], xhi = win[1], ylo = win[2], yhi = win[3];
         const int bxc = (x0 >> g.sx) - SA_HX, byc = (y0 >> g.sy) - SA_HY;
         if (alfY || ccCb || ccCr) saReplicateBorder(A0, x0 - SA_HX, y0 - SA_HY, xlo, xhi, ylo, yhi, SA_P, SA_T, SA_TH, 3);
@@ -641,9 +675,9 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDe
         if (pad)
         {
           // no barrier needed in between: the corners lie outside the clamp window's replicated ranges (their sides are not clipped)
-          if (alfY || ccCb || ccCr) saPadCorners(A0, x0 - SA_HX, y0 - SA_HY, cx0, cy0, cx1, cy1, SA_P, tileW, tileH, 3, pad);
-          if (alfCb) saPadCorners(A1, bxc, byc, cx0 >> g.sx, cy0 >> g.sy, cx1 >> g.sx, cy1 >> g.sy, L.pitchC, tileW >> g.sx, tileH >> g.sy, 3, pad);
-          if (alfCr) saPadCorners(A2, bxc, byc, cx0 >> g.sx, cy0 >> g.sy, cx1 >> g.sx, cy1 >> g.sy, L.pitchC, tileW >> g.sx, tileH >> g.sy, 3, pad);
+          if (alfY || ccCb || ccCr) saPadCorners(A0, x0 - SA_HX, y0 - SA_HY, cx0, cy0, cx1, cy1, SA_P, 3, pad);
+          if (alfCb) saPadCorners(A1, bxc, byc, cx0 >> g.sx, cy0 >> g.sy, cx1 >> g.sx, cy1 >> g.sy, L.pitchC, 3, pad);
+          if (alfCr) saPadCorners(A2, bxc, byc, cx0 >> g.sx, cy0 >> g.sy, cx1 >> g.sx, cy1 >> g.sy, L.pitchC, 3, pad);
         }
         __syncthreads();
       }

@@ -199,7 +199,7 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
   if (s.width <= 0 || s.height <= 0 || (s.width & 7) || (s.height & 7)) return bad("width/height must be positive multiples of 8");
   if (s.chroma_format < 0 || s.chroma_format > 3) return bad("bad chroma_format");
   if (s.bit_depth_luma < 8 || s.bit_depth_luma > 12 || s.bit_depth_chroma < 8 || s.bit_depth_chroma > 12) return bad("bit depth must be 8..12");
-  if (s.ctu_size != 64 && s.ctu_size != 128) return bad("ctu_size must be 64 or 128");
+  if (s.ctu_size != 32 && s.ctu_size != 64 && s.ctu_size != 128) return bad("ctu_size must be 32, 64 or 128");
   if (s.capacity < 1) return bad("capacity must be >= 1");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -215,7 +215,7 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
   g.sy = (s.chroma_format == 1) ? 1 : 0;
   g.ncomp = s.chroma_format == 0 ? 1 : 3;
   g.bdL = s.bit_depth_luma; g.bdC = s.bit_depth_chroma;
-  g.ctu = s.ctu_size; g.ctuLog2 = s.ctu_size == 128 ? 7 : 6;
+  g.ctu = s.ctu_size; g.ctuLog2 = s.ctu_size == 128 ? 7 : (s.ctu_size == 64 ? 6 : 5);
   g.wCtus = (g.w + g.ctu - 1) / g.ctu; g.hCtus = (g.h + g.ctu - 1) / g.ctu;
   c->nCtus = g.wCtus * g.hCtus;
   c->rowBegin = 0; c->rowEnd = g.h;
@@ -1033,7 +1033,7 @@ int launchAlf(vtmgpu_ctx* c, int first, int count)
   const SaLayout SL = saLayout(g.sx, g.sy, g.ncomp);
   return forRuns(c, first, count, [&](int s, int n, int src) {
     const int dst = src == 1 ? 2 : 1;
-    bool vb = false;                                             // tiles cut by a virtual boundary need a scratch copy of the tile
+    bool vb = g.ctu < SA_T;                                      // tiles filtered in parts (virtual boundaries, several CTUs per tile) need a scratch copy of the tile
     for (int i = s; i < s + n; i++) vb |= (c->slotsPinned[i].vbAlf.nv | c->slotsPinned[i].vbAlf.nh) != 0;
     const int smem = SL.total + (vb ? SL.lumaBytes + 2 * SL.chromaBytes : 0);
     // persistent CTAs: four per SM (register limited), each walks the tiles round robin with double-buffered TMA loads
