@@ -208,6 +208,7 @@ def main():
     ap.add_argument("--distinct", type=int, default=8, help="distinct pictures replicated to fill the batch")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stress", action="store_true", help="skip the forced-on synthetic leg (N=1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -388,6 +389,26 @@ def main():
             "e2e": {"value": round(e2e_val, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": int(h2d * B), "d2h_bytes_per_step": int(d2h * B),
                     "steps": args.e2e_steps, "gpu_launches": int(launches_total - launches),
                     "host_issue_ms_per_step": round(issue[0] * 1e3 / args.e2e_steps, 2), "deblock_records": "dense arrays" if dense_records else "lists of active units", "ms_per_step": round(e2e_s * 1e3, 2)}}
+    if world == 1 and not args.no_stress:
+        # content-independent stress number: seeded pictures with every tool forced on in every CTU (SAO, luma / chroma
+        # ALF with non-linear APS filters, CC-ALF) and dense small blocks for the deblocking, replayed device-resident
+        from vvc_b200 import synth
+        ns = min(16, B)
+        scaps = [synth.make_picture(W4K, H4K, seed=4100 + i, density=1.0, p_split=0.9) for i in range(2)]
+        for k in range(ns):
+            ctx.set_capture(k, scaps[k % 2])
+        ctx.sync()
+        for _ in range(3):
+            ctx.rewind(0, ns)
+            ctx.filter(0, ns, sync=False)
+        ctx.timer_start()
+        for _ in range(5):
+            ctx.rewind(0, ns)
+            ctx.filter(0, ns, sync=False)
+        ms = ctx.timer_stop() / 5
+        line["stress_forced_on"] = {"value": round(ns * W4K * H4K / (ms * 1e-3) / 1e6, 1), "unit": "Mpixel/s", "pictures_per_step": ns,
+                                    "what": "seeded 4K pictures, every tool on in every CTU (vvc_b200/synth.py density 1.0, p_split 0.9), device-resident",
+                                    "activity": activity_summary(scaps)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         res = cpu_reference_run()
         if res:
