@@ -16,8 +16,14 @@
 //   IDP.2A                s16 x s8 dot product into s32   (__dp2a_lo / __dp2a_hi): the ALF multiply-accumulate
 //   PRMT / SHF            16-bit lane shuffles
 // A filter tap pair costs 4 ALU-pipe + 2 FMA-pipe instructions per two pixels (scalar code: ~14 per two pixels).
-// Rows that touch an ALF virtual boundary (2 of 32 block rows per CTU) and non-4:2:0 CC-ALF use the generic scalar
-// routines in this file; they follow the reference line by line.
+// The 7x7 luma filter handles the rows next to the ALF virtual boundary (CTU height - 4) in the same packed loop (row offsets
+// clamped at run time); their Laplacian cells, wide coefficients and non-4:2:0 CC-ALF use the generic scalar routines in this
+// file, which follow the reference line by line.
+//
+// Sides the filter must not read across -- the picture border, slice / tile boundaries (one clip byte per CTU) and signalled
+// virtual boundaries -- are all the same operation: the samples outside a clamp window are replaced by the nearest sample inside
+// (saReplicateBorder).  A tile that a virtual boundary cuts, or that covers several CTUs (CTU size 32), is filtered part by part
+// (instantiation k_alf<true>, only launched for such pictures): every part pads its own copy of the tile.
 //
 // Per luma pixel algorithmic HBM bytes at 4:2:0: read 3, write 3 (+ CTU params, negligible).
 #pragma once
