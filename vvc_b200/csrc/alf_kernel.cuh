@@ -532,7 +532,7 @@ __device__ __forceinline__ void saAdvance(SaWalk& p, const SaStep& st, int tiles
 
 // issues the asynchronous loads of one tile into `stage`: three TMA boxes (one thread) + the control record of its CTU
 __device__ __forceinline__ void saPrefetch(unsigned char* smraw, const SaLayout& L, int stage, const SlotDev& S, const CUtensorMap* maps, const SaWalk& p,
-                                           const Geom& g, int ty0)
+                                           const Geom& g, int ty0, bool ctlToShared)
 {
   const int tid = threadIdx.x, x0 = p.tx * SA_T, y0 = (p.ty + ty0) * SA_TH;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smraw + L.offBar) + stage;
@@ -548,7 +548,7 @@ __device__ __forceinline__ void saPrefetch(unsigned char* smraw, const SaLayout&
     }
   }
   // control record(s) of the CTU(s) under the tile: one for CTU sizes >= 64, 2 x 2 for CTU size 32 (record k = CTU (k & 1, k >> 1))
-  if (tid >= 32 && tid < 36)
+  if (ctlToShared && tid >= 32 && tid < 36)
   {
     const int k = tid - 32, cx = (x0 >> g.ctuLog2) + (k & 1), cy = (y0 >> g.ctuLog2) + (k >> 1);
     if ((k == 0 || g.ctu < SA_T) && cx < g.wCtus && cy < g.hCtus)
@@ -592,11 +592,15 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDe
     mbarInit(&bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // k_alf<false>: one CTU per tile -- its control record travels through registers, loaded one tile ahead, and the tile needs no
+  // CTA barrier between the arrival of its samples (every thread waits on the mbarrier itself) and the first phase
+  uint4 ctlNext = make_uint4(0, 0, 0, 0);
   __syncthreads();
   {
     const SlotDev& S = slots[firstSlot + cur.slot];
-    saPrefetch(smraw, L, 0, S, tmaps + ((size_t)(firstSlot + cur.slot) * 3 + srcBuf) * 3, cur, g, ty0);
+    saPrefetch(smraw, L, 0, S, tmaps + ((size_t)(firstSlot + cur.slot) * 3 + srcBuf) * 3, cur, g, ty0, kVirtualBoundaries);
     cpAsyncCommit();
+    if (!kVirtualBoundaries) ctlNext = __ldg(reinterpret_cast<const uint4*>(&S.ctuCtl[(((cur.ty + ty0) * SA_TH) >> g.ctuLog2) * g.wCtus + ((cur.tx * SA_T) >> g.ctuLog2)]));
   }
   for (uint32_t it = 0; cur.slot < numSlots; it++)
   {
@@ -607,12 +611,22 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDe
     if (nxt.slot < numSlots)
     {
       const SlotDev& Sn = slots[firstSlot + nxt.slot];
-      saPrefetch(smraw, L, stage ^ 1, Sn, tmaps + ((size_t)(firstSlot + nxt.slot) * 3 + srcBuf) * 3, nxt, g, ty0);
+      saPrefetch(smraw, L, stage ^ 1, Sn, tmaps + ((size_t)(firstSlot + nxt.slot) * 3 + srcBuf) * 3, nxt, g, ty0, kVirtualBoundaries);
     }
-    cpAsyncCommit();
-    cpAsyncWait<1>();
-    mbarWait(&bars[stage], (it >> 1) & 1);
-    __syncthreads();                                         // tile and its parameters are in shared memory
+    const uint4 ctlCur = ctlNext;
+    if (kVirtualBoundaries)
+    {
+      cpAsyncCommit();
+      cpAsyncWait<1>();
+      mbarWait(&bars[stage], (it >> 1) & 1);
+      __syncthreads();                                       // tile and its control records are in shared memory
+    }
+    else
+    {
+      if (nxt.slot < numSlots)
+        ctlNext = __ldg(reinterpret_cast<const uint4*>(&slots[firstSlot + nxt.slot].ctuCtl[(((nxt.ty + ty0) * SA_TH) >> g.ctuLog2) * g.wCtus + ((nxt.tx * SA_T) >> g.ctuLog2)]));
+      mbarWait(&bars[stage], (it >> 1) & 1);                 // the TMA writes of this tile are visible to this thread
+    }
 
     const int x0 = cur.tx * SA_T, y0 = (cur.ty + ty0) * SA_TH;
     const bool alfOn = S.alfOn != 0;
@@ -646,7 +660,9 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDe
       const int px0 = xs[pi], px1 = xs[pi + 1], py0 = ys[pj], py1 = ys[pj + 1];       // luma rectangle of this part
       // control record of the part's CTU
       const int cidx = (kVirtualBoundaries && g.ctu < SA_T) ? (((px0 - x0) >> g.ctuLog2) | ((py0 - y0) >> g.ctuLog2) << 1) : 0;
-      const CtuCtlDev ctl = reinterpret_cast<const CtuCtlDev*>(smraw + L.offPar)[stage * 4 + cidx];
+      CtuCtlDev ctl;
+      if (kVirtualBoundaries) ctl = reinterpret_cast<const CtuCtlDev*>(smraw + L.offPar)[stage * 4 + cidx];
+      else                    *reinterpret_cast<uint4*>(&ctl) = ctlCur;
       const bool alfY = alfOn && ctl.enY != 0, alfCb = alfOn && ctl.enCb != 0, alfCr = alfOn && ctl.enCr != 0;
       const int ccCb = alfOn ? ctl.ccCb : 0, ccCr = alfOn ? ctl.ccCr : 0;
       const int clip = ctl.clip;

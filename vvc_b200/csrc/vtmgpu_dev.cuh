@@ -67,7 +67,7 @@ struct AlfLumaEntry
 
 // Per-CTU control record (16 bytes, one 128-bit load per tile): ALF control (Picture::getAlfCtuEnableFlag /
 // getAlfCtbFilterIndex / getAlfCtuAlternativeData, m_ccAlfFilterControl) written by vtmgpu_set_alf.
-struct CtuCtlDev
+struct alignas(16) CtuCtlDev
 {
   uint8_t enY, enCb, enCr;       // ALF CTU enable flags
   uint8_t altCb, altCr;          // chroma filter alternative
