@@ -100,9 +100,10 @@ def test_band_exchange_gloo_world2():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("w,h,n", [(416, 384, 2), (256, 640, 3), (1920, 1080, 4)])
-def test_bands_on_one_gpu_match_oracle(w, h, n):
-    cap = synth.make_picture(w, h, seed=w + n, density=0.8)
+@pytest.mark.parametrize("w,h,n,feat", [(416, 384, 2, False), (256, 640, 3, False), (1920, 1080, 4, False), (512, 640, 3, True)])
+def test_bands_on_one_gpu_match_oracle(w, h, n, feat):
+    # feat: slice / tile clip flags and signalled virtual boundaries (one of them 8 rows above a band border) in band mode
+    cap = synth.make_picture(w, h, seed=w + n, density=0.8, partitions=feat, vb=([200], [248, 504]) if feat else None)
     want = pyoracle.filter_capture(cap)["final"]
     got = bands.filter_picture_in_bands_local(cap, n)
     for c in range(3):

@@ -134,7 +134,7 @@ def filter_picture_in_bands(cap, ctx, rank, world, dist, out=None):
     ctus = cap.sao_ctus()
     if ctus is not None:
         gpu.sao_reconstruct(ctus, cap.width_in_ctus, cap.ncomp, cap.sao_scale[0], cap.sao_scale[1])
-    ctx.set_sao(0, ctus)
+    ctx.set_sao(0, ctus, cap.vb_struct())
     ctx.set_alf(0, cap.alf_params())
     ctx.deblock_sao(0, 1)                      # one kernel: the SAO of the band's border rows sees the deblocked rows across the border
     dev = torch.device("cuda", ctx.device)
@@ -171,7 +171,7 @@ def filter_picture_in_bands_local(cap, n_bands, device=0):
             ctus = cap.sao_ctus()
             if ctus is not None:
                 gpu.sao_reconstruct(ctus, cap.width_in_ctus, cap.ncomp, cap.sao_scale[0], cap.sao_scale[1])
-            ctx.set_sao(0, ctus)
+            ctx.set_sao(0, ctus, cap.vb_struct())
             ctx.set_alf(0, cap.alf_params())
             ctx.deblock_sao(0, 1)
         mail = {}
