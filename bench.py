@@ -198,6 +198,32 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local):
+    """Multi-rank runs: keep this rank's threads -- and with them its page-locked staging buffers (first touch) -- on the NUMA node
+    the GPU hangs off; the end-to-end leg moves ~50 MB per picture through host memory.  Returns the node or None."""
+    try:
+        r = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)], capture_output=True, text=True, timeout=30)
+        bus = r.stdout.strip().lower()
+        if bus.count(":") == 2 and len(bus.split(":")[0]) == 8:
+            bus = bus[4:]                                   # 00000000:1b:00.0 -> 0000:1b:00.0
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read())
+        if node < 0:
+            return None
+        cpus = set()
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -222,6 +248,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the filter chain has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 and os.environ.get("VTMGPU_BENCH_NUMA", "1") == "1" else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -388,7 +415,7 @@ def main():
             "clocks": clocks, "roofline": roofline, "gpu_launches": int(launches),
             "e2e": {"value": round(e2e_val, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": int(h2d * B), "d2h_bytes_per_step": int(d2h * B),
                     "steps": args.e2e_steps, "gpu_launches": int(launches_total - launches),
-                    "host_issue_ms_per_step": round(issue[0] * 1e3 / args.e2e_steps, 2), "deblock_records": "dense arrays" if dense_records else "lists of active units", "ms_per_step": round(e2e_s * 1e3, 2)}}
+                    "host_issue_ms_per_step": round(issue[0] * 1e3 / args.e2e_steps, 2), "numa_node_of_rank0": numa, "deblock_records": "dense arrays" if dense_records else "lists of active units", "ms_per_step": round(e2e_s * 1e3, 2)}}
     if world == 1 and not args.no_stress:
         # content-independent stress number: seeded pictures with every tool forced on in every CTU (SAO, luma / chroma
         # ALF with non-linear APS filters, CC-ALF) and dense small blocks for the deblocking, replayed device-resident
