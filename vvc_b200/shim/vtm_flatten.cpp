@@ -396,7 +396,8 @@ unsigned Deriver::strength(const CodingUnit& cu, const Position& lumaPos) const
   const Position posQ(lumaPos.x >> sh, lumaPos.y >> sv);
   const Position posP = m_dir == VER ? posQ.offset(-1, 0) : posQ.offset(0, -1);
   const CodingUnit& cuQ = cu;
-  const CodingUnit& cuP = *cu.cs->getCU(posP, cu.chType);
+  // internal edges (TU / PU / sub-block boundaries inside the CU): the P side is the CU itself, no look-up
+  const CodingUnit& cuP = cu.blocks[cu.chType].contains(posP) ? cu : *cu.cs->getCU(posP, cu.chType);
   const bool intraP = cuP.predMode == MODE_INTRA, intraQ = cuQ.predMode == MODE_INTRA;
   if (intraP || intraQ)
   {
@@ -477,7 +478,8 @@ void Deriver::emitLuma(const CodingUnit& cu, int edge)
     const int id = uidx(pos.x, pos.y);
     const unsigned bs = m_st.code[id] & 3;
     if (!bs) continue;
-    const CodingUnit& cuP = *cu.cs->getCU(m_dir == VER ? pos.offset(-4, 0) : pos.offset(0, -4), cu.chType);
+    const Position posP = m_dir == VER ? pos.offset(-4, 0) : pos.offset(0, -4);
+    const CodingUnit& cuP = la.contains(posP) ? cu : *cu.cs->getCU(posP, cu.chType);
     if (!usable(cu, cuP, pps))
     {
       m_st.code[id] = 0;      // also suppresses the chroma filtering of this unit (LoopFilter.cpp:918-933)
