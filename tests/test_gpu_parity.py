@@ -243,6 +243,21 @@ STREAMS = [("ra_416x240.bin", 8), ("ld444_1080p.bin", 16), ("ra_1080p.bin", 32),
            ("ra_full_832x480.bin", 6)]    # full CTC tool set at a size with 128-wide CUs   # palette / IBC / BDPCM on screen content (4:4:4); P slices
 
 
+def _fuzz_streams():
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "streams", "fuzz_manifest.json")
+    if not os.path.exists(path):
+        return []
+    with open(path) as f:
+        return [(name, m["pictures"]) for name, m in sorted(json.load(f).items())]
+
+
+# random encoder configurations (tools/fuzz_parity_streams.py; options in tests/golden/streams/fuzz_manifest.json): combinations of the
+# path features above that no hand-picked stream has -- e.g. 4:4:4 + raster slices + virtual boundaries, 4:2:2 + CTU 32 + LADF
+STREAMS += _fuzz_streams()
+
+
 @pytest.mark.parametrize("stream,pictures", STREAMS)
 def test_decoder_drop_in_md5(stream, pictures):
     """The reference decoder with OUR filter entry points linked in (vvc_b200/_bin/DecoderApp_gpu) decodes reference-encoded
