@@ -140,6 +140,7 @@ private:
   FlatDeblock&         m_out;
   FlatDeblock::Lists*  m_lists = nullptr;      // this thread's share of the record lists
   vtmgpu_virtual_boundaries m_vb{};
+  mutable const TransformUnit *m_tuQ = nullptr, *m_tuP = nullptr;    // memo of strength()
   // xDeriveEdgefilterParam (LoopFilter.cpp:435-452): an edge that lies on a signalled virtual boundary is not filtered
   bool onVb(int dir, const Area& a) const
   {
@@ -341,11 +342,13 @@ void Deriver::lengthsFromTU(const CodingUnit& cu, const TransformUnit& tu)
     const int step   = 4 >> (c ? (m_dir == HOR ? m_sx : m_sy) : 0);
     const int extent = m_dir == HOR ? (int)tu.blocks[c].width : (int)tu.blocks[c].height;
     const int sizeQ  = m_dir == HOR ? tb.height : tb.width;
+    const TransformUnit* tuPp = nullptr;                     // neighbouring TU of the previous unit: usually still the one across the edge
     for (int k = 0; k < extent; k += step)
     {
       const Position posQ = m_dir == HOR ? Position(tu.blocks[ch].x + k, tu.blocks[ch].y) : Position(tu.blocks[ch].x, tu.blocks[ch].y + k);
       const Position posP = m_dir == HOR ? posQ.offset(0, -1) : posQ.offset(-1, 0);
-      const TransformUnit& tuP = *cu.cs->getTU(posP, ch);
+      if (!tuPp || !tuPp->blocks[ch].valid() || !tuPp->blocks[ch].contains(posP)) tuPp = cu.cs->getTU(posP, ch);
+      const TransformUnit& tuP = *tuPp;
       const int sizeP = m_dir == HOR ? tuP.block(comp).height : tuP.block(comp).width;
       const int x = m_dir == HOR ? ux(c, tb.x + k) : ux(c, tb.x);
       const int y = m_dir == HOR ? uy(c, tb.y) : uy(c, tb.y + k);
@@ -405,8 +408,11 @@ unsigned Deriver::strength(const CodingUnit& cu, const Position& lumaPos) const
     const unsigned c = (intraP && cuP.bdpcmModeChroma && intraQ && cuQ.bdpcmModeChroma) ? 0 : 2;
     return y | (c << 2) | (c << 4);
   }
-  const TransformUnit& tuQ = *cuQ.cs->getTU(posQ, cuQ.chType);
-  const TransformUnit& tuP = *cuP.cs->getTU(posP, cuQ.chType);
+  // consecutive units along an edge mostly stay inside the same two transform units: one-entry memo per side
+  if (!m_tuQ || m_tuQ->cu != &cuQ || !m_tuQ->blocks[cuQ.chType].valid() || !m_tuQ->blocks[cuQ.chType].contains(posQ)) m_tuQ = cuQ.cs->getTU(posQ, cuQ.chType);
+  if (!m_tuP || m_tuP->cu != &cuP || !m_tuP->blocks[cuQ.chType].valid() || !m_tuP->blocks[cuQ.chType].contains(posP)) m_tuP = cuP.cs->getTU(posP, cuQ.chType);
+  const TransformUnit& tuQ = *m_tuQ;
+  const TransformUnit& tuP = *m_tuP;
   const uint8_t code = m_st.code[uidx(lumaPos.x, lumaPos.y)];
   const bool ciip = cuP.firstPU->ciipFlag || cuQ.firstPU->ciipFlag;
   if (code && ciip) return 2 | (2 << 2) | (2 << 4);
