@@ -104,3 +104,15 @@ def test_sparse_records_layout():
         assert C.cast(sp.chroma[d], C.c_void_p).value == base + off
         off = (off + n * C.sizeof(abi.DbfChromaEntry) + 15) & ~15
     assert base % 16 == 0 and sp.nbytes == off
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/vtmgpu.h is the boundary for cgo / JNI / ctypes style bindings: it must compile as C99 without C++ or CUDA headers."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "vtmgpu.h")
+    r = subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
