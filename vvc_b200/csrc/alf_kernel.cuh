@@ -34,6 +34,7 @@
 #include "packed16.cuh"
 #include "vtmgpu_dev.cuh"
 #include "vtmgpu.h"
+#include "alf_fast.cuh"
 
 namespace vtmgpu
 {
@@ -65,7 +66,7 @@ __constant__ int8_t c_perm7[4][12] = { { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11 },
 struct SaLayout
 {
   int pitchC, rowsC;               // chroma tile buffers: pitch in samples, rows
-  int lumaBytes, chromaBytes, offCell, offPar, offBar, total;
+  int lumaBytes, chromaBytes, offCell, offV, offPar, offBar, total;
   __host__ __device__ int comp(int c) const { return c ? lumaBytes + (c - 1) * chromaBytes : 0; }
   __host__ __device__ int offA(int stage, int c) const { return stage * (lumaBytes + 2 * chromaBytes) + comp(c); }
 };
@@ -75,12 +76,13 @@ __host__ __device__ inline SaLayout saLayout(int sx, int sy, int ncomp)
 {
   SaLayout L;
   const int tw = SA_T >> sx, th = SA_TH >> sy;
-  L.pitchC = tw + 2 * SA_HX + 8;
+  L.pitchC = tw + 2 * SA_HX;            // 48 samples = 24 words at 4:2:0: chroma rows r and r + 2 are 16 banks apart
   L.rowsC = th + 2 * SA_HY;
   L.lumaBytes = SA_H * SA_P * 2;
   L.chromaBytes = ncomp > 1 ? L.rowsC * L.pitchC * 2 : 0;
   L.offCell = 2 * (L.lumaBytes + 2 * L.chromaBytes);
-  L.offPar = L.offCell + SA_CELLR * SA_CELLP * 8;
+  L.offV = L.offCell + SA_CELLR * SA_CELLP * 8;                // vertical-pair copy of the luma tile (alf_fast.cuh), 16-byte aligned
+  L.offPar = L.offV + AV_BYTES;
   L.offBar = L.offPar + 2 * 4 * (int)sizeof(CtuCtlDev);      // per stage: the control records of the (up to 2 x 2) CTUs under the tile
   L.total = L.offBar + 16;
   return L;
@@ -561,10 +563,10 @@ __device__ __forceinline__ void saPrefetch(unsigned char* smraw, const SaLayout&
 // Persistent kernel: gridDim.x CTAs walk the tiles of slots [firstSlot, firstSlot + numSlots) round robin; while a CTA
 // filters tile i, the TMA loads of tile i+1 are in flight (two stages).  maps = tensor maps of the source buffer of the
 // first slot: [slot][3 buffers][3 planes].
-template <bool kVirtualBoundaries>
-__global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDev* __restrict__ slots, const CUtensorMap* __restrict__ tmaps, int firstSlot, int numSlots,
+__global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf_parts(const SlotDev* __restrict__ slots, const CUtensorMap* __restrict__ tmaps, int firstSlot, int numSlots,
                                                            int srcBuf, int dstBuf, Geom g, int tilesX, int tilesY, int ty0, SaStep step)
 {
+  constexpr bool kVirtualBoundaries = true;
   extern __shared__ __align__(128) unsigned char smraw[];
   const SaLayout L = saLayout(g.sx, g.sy, g.ncomp);
   const int tid = threadIdx.x;
@@ -841,6 +843,308 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDe
       if (part + 1 < nparts) __syncthreads();                  // the next part re-pads the tile and recomputes the cells
     }
     __syncthreads();                                         // all reads of stage buffers / B / cells are done before they are refilled
+    cur = nxt;
+  }
+}
+
+
+// ---- the common kernel: one CTU per tile, no signalled virtual boundary ------------------------------------------------------
+// (pictures with signalled virtual boundaries or CTU size 32 take k_alf_parts above.)  Per tile:
+//   wait      the TMA loads of the tile (issued one tile ahead) have landed
+//   pad       only tiles on a picture border or with a clipped CTU side: replicate samples into the outside (CTA barrier)
+//   phase 1   every thread: Laplacian cells of its 4x4 block (packed diagonal pairs) and its part of the vertical-pair copy of the
+//             luma tile; spare threads: the ring of halo cells and the border of the copy                       (CTA barrier)
+//   phase 2   class of the block from the 4x4 cell window, loads of the filter entry, then -- while those are in flight -- the
+//             chroma 5x5 + CC-ALF quads of the thread, then the 7x7 luma block from the vertical-pair copy          (CTA barrier)
+// The control record of the tile's CTU travels through registers, loaded one tile ahead.  k420 = true compiles the chroma
+// geometry of 4:2:0 in (one quad per thread and plane, no loop); the other formats take the run-time instantiation.
+// Everything that does not depend on the tile (thread offsets into the shared-memory arrays, packed constants) is computed
+// once per CTA: round 1 spent 28 of its 138 instructions per pixel on per-tile bookkeeping.
+template <bool k420>
+__global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDev* __restrict__ slots, const CUtensorMap* __restrict__ tmaps, int firstSlot, int numSlots,
+                                                                    int srcBuf, int dstBuf, Geom g, int tilesX, int tilesY, int ty0, SaStep step, int pitchY, int pitchCh)
+{
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int sx = k420 ? 1 : g.sx, sy = k420 ? 1 : g.sy, ncomp = k420 ? 3 : g.ncomp;
+  const SaLayout L = saLayout(sx, sy, ncomp);
+  const int tid = threadIdx.x;
+  uint2 (*cell)[SA_CELLP] = reinterpret_cast<uint2 (*)[SA_CELLP]>(smraw + L.offCell);
+  uint32_t* const V = reinterpret_cast<uint32_t*>(smraw + L.offV);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + L.offBar);
+  const int vbL = g.ctu - 4, ctuMask = g.ctu - 1;
+  const int bi = tid >> 4, bj = tid & 15;
+  const int ctuH = g.ctu >> sy, vbC = ctuH - 2;
+  const uint32_t maxcP = dup16((1 << g.bdC) - 1), halfP = dup16((1 << g.bdC) >> 1), maxvP = dup16((1 << g.bdL) - 1);
+  const int stageBytes = L.lumaBytes + 2 * L.chromaBytes;
+  const int wC = g.w >> sx, hC = g.h >> sy;
+  // thread constants: block origin in the row-major tile, in the vertical-pair copy, in the cell array
+  const int hOff = (4 * bi + SA_HY) * SA_P + 4 * bj + SA_HX;
+  uint32_t* const vBlk = V + (4 * bi + 4) * AV_COLS + 4 * bj;
+  // 4:2:0: the thread's chroma quad.  The rows of a warp are visited in the order 0, 2, 1, 3 so that the two rows of a half warp
+  // lie 16 banks apart in shared memory (chroma pitch 24 words).
+  const int rC = ((tid >> 3) & ~3) | (((tid >> 3) & 1) << 1) | ((tid >> 4) & 1), qC = (tid & 7) * 4;
+  const int cOff = (rC + SA_HY) * L.pitchC + qC + SA_HX, lOff = (2 * rC + SA_HY) * SA_P + 2 * qC + SA_HX;
+  // phase-1 side jobs: border of the vertical-pair copy (threads 0..217), ring of halo cells (the last 132 threads)
+  int cpH = -1, cpV = 0;
+  if (tid < 90 + 128)
+  {
+    int rr, lx;
+    if (tid < 90) { const int q = tid / 18; rr = q < 3 ? 1 + q : 65 + q; lx = (tid - q * 18) * 4; }    // row pairs 1..3, 68, 69 x 18 column quads
+    else          { const int q = tid - 90; rr = 4 + (q >> 1); lx = (q & 1) ? 68 : 0; }                // columns 0..3 and 68..71 of row pairs 4..67
+    cpH = rr * SA_P + lx + SA_HX - 4; cpV = rr * AV_COLS + lx;
+  }
+  constexpr int kRing = 2 * SA_CELLS + 2 * (SA_CELLR - 2);
+  int ringI = -1, ringJ = 0;
+  if (tid >= SA_THREADS - kRing)
+  {
+    const int q = tid - (SA_THREADS - kRing);
+    if (q < 2 * SA_CELLS) { ringI = q < SA_CELLS ? 0 : SA_CELLR - 1; ringJ = q < SA_CELLS ? q : q - SA_CELLS; }
+    else { const int k = q - 2 * SA_CELLS; ringI = 1 + (k >> 1); ringJ = (k & 1) ? SA_CELLS - 1 : 0; }
+  }
+
+  SaWalk cur;
+  {
+    const int tilesPerPic = tilesX * tilesY, t = blockIdx.x;
+    cur.slot = t / tilesPerPic;
+    const int rem = t - cur.slot * tilesPerPic;
+    cur.ty = rem / tilesX;
+    cur.tx = rem - cur.ty * tilesX;
+  }
+  if (cur.slot >= numSlots) return;
+  if (tid == 0)
+  {
+    mbarInit(&bars[0], 1);
+    mbarInit(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint4 ctlNext;
+  __syncthreads();
+  {
+    const SlotDev& S = slots[firstSlot + cur.slot];
+    saPrefetch(smraw, L, 0, S, tmaps + ((size_t)(firstSlot + cur.slot) * 3 + srcBuf) * 3, cur, g, ty0, false);
+    ctlNext = __ldg(reinterpret_cast<const uint4*>(&S.ctuCtl[(((cur.ty + ty0) * SA_TH) >> g.ctuLog2) * g.wCtus + ((cur.tx * SA_T) >> g.ctuLog2)]));
+  }
+  for (uint32_t it = 0; cur.slot < numSlots; it++)
+  {
+    const int stage = it & 1;
+    const SlotDev& S = slots[firstSlot + cur.slot];
+    SaWalk nxt = cur;
+    saAdvance(nxt, step, tilesX, tilesY);
+    const uint4 ctlCur = ctlNext;
+    if (nxt.slot < numSlots)
+    {
+      const SlotDev& Sn = slots[firstSlot + nxt.slot];
+      saPrefetch(smraw, L, stage ^ 1, Sn, tmaps + ((size_t)(firstSlot + nxt.slot) * 3 + srcBuf) * 3, nxt, g, ty0, false);
+      ctlNext = __ldg(reinterpret_cast<const uint4*>(&Sn.ctuCtl[(((nxt.ty + ty0) * SA_TH) >> g.ctuLog2) * g.wCtus + ((nxt.tx * SA_T) >> g.ctuLog2)]));
+    }
+    // the slot's destination planes and ALF data (uniform loads, consumed after the first barrier)
+    pel* const dY = S.buf[dstBuf][0].p;
+    pel* const dCb = ncomp > 1 ? S.buf[dstBuf][1].p : nullptr;
+    pel* const dCr = ncomp > 1 ? S.buf[dstBuf][2].p : nullptr;
+    const int2 onWide = *reinterpret_cast<const int2*>(&S.alfOn);        // { alfOn, alfWide }
+    const AlfDev* const alfDev = S.alf;
+    const AlfLumaEntry* const lumaTab = S.lumaTab;
+    CtuCtlDev ctl;
+    *reinterpret_cast<uint4*>(&ctl) = ctlCur;
+    const bool alfOn = onWide.x != 0, wide = onWide.y != 0;
+    const bool alfY = alfOn && ctl.enY != 0, alfCb = alfOn && ctl.enCb != 0, alfCr = alfOn && ctl.enCr != 0;
+    const int ccCb = alfOn ? ctl.ccCb : 0, ccCr = alfOn ? ctl.ccCr : 0;
+    const int clip = ctl.clip;
+    const int x0 = cur.tx * SA_T, y0 = (cur.ty + ty0) * SA_TH;
+    pel* const A0 = reinterpret_cast<pel*>(smraw + stage * stageBytes);
+    pel* const A1 = reinterpret_cast<pel*>(smraw + stage * stageBytes + L.lumaBytes);
+    pel* const A2 = reinterpret_cast<pel*>(smraw + stage * stageBytes + L.lumaBytes + L.chromaBytes);
+
+    mbarWait(&bars[stage], (it >> 1) & 1);                   // the TMA writes of this tile are visible to this thread
+
+    // tiles on the picture border: replicate the border samples into the zero-filled outside
+    // (= UnitBuf::extendBorderPel of the ALF input, AdaptiveLoopFilter.cpp:411); CTU sides at a slice / tile boundary the
+    // filter must not read across: the same replication at the clipped sides (:452-490)
+    if (x0 == 0 || y0 == 0 || x0 + SA_T + 8 > g.w || y0 + SA_TH + 8 > g.h || clip != 0)
+    {
+      const int cx0 = x0 & ~ctuMask, cy0 = y0 & ~ctuMask, cx1 = min(cx0 + g.ctu, g.w), cy1 = min(cy0 + g.ctu, g.h);
+      const int xlo = (clip & VTMGPU_ALF_CLIP_LEFT) ? cx0 : 0, xhi = (clip & VTMGPU_ALF_CLIP_RIGHT) ? cx1 : g.w;
+      const int ylo = (clip & VTMGPU_ALF_CLIP_TOP) ? cy0 : 0, yhi = (clip & VTMGPU_ALF_CLIP_BOTTOM) ? cy1 : g.h;
+      int pad = clip & (VTMGPU_ALF_PAD_TL | VTMGPU_ALF_PAD_BR);      // only for the tile that holds that corner of the CTU
+      if (x0 != cx0 || y0 != cy0) pad &= ~VTMGPU_ALF_PAD_TL;
+      if (min(x0 + SA_T, g.w) != cx1 || min(y0 + SA_TH, g.h) != cy1) pad &= ~VTMGPU_ALF_PAD_BR;
+      const int bxc = (x0 >> sx) - SA_HX, byc = (y0 >> sy) - SA_HY, twc = SA_T >> sx, thc = SA_TH >> sy;
+      if (alfY || ccCb || ccCr) saReplicateBorder(A0, x0 - SA_HX, y0 - SA_HY, xlo, xhi, ylo, yhi, SA_P, SA_T, SA_TH, 4);
+      if (alfCb) saReplicateBorder(A1, bxc, byc, xlo >> sx, xhi >> sx, ylo >> sy, yhi >> sy, L.pitchC, twc, thc, 3);
+      if (alfCr) saReplicateBorder(A2, bxc, byc, xlo >> sx, xhi >> sx, ylo >> sy, yhi >> sy, L.pitchC, twc, thc, 3);
+      if (pad)
+      {
+        // no barrier needed in between: the corners lie outside the clamp window's replicated ranges (their sides are not clipped)
+        if (alfY || ccCb || ccCr) saPadCorners(A0, x0 - SA_HX, y0 - SA_HY, cx0, cy0, cx1, cy1, SA_P, 4, pad);
+        if (alfCb) saPadCorners(A1, bxc, byc, cx0 >> sx, cy0 >> sy, cx1 >> sx, cy1 >> sy, L.pitchC, 3, pad);
+        if (alfCr) saPadCorners(A2, bxc, byc, cx0 >> sx, cy0 >> sy, cx1 >> sx, cy1 >> sy, L.pitchC, 3, pad);
+      }
+      __syncthreads();
+    }
+
+    const pel* const c0 = A0 + hOff;
+    const int yb = (y0 + 4 * bi) & ctuMask;
+    const int vb = yb == vbL - 4 ? 1 : (yb == vbL ? 2 : 0);        // uniform per warp (two block rows)
+
+    // ---- phase 1: Laplacian cells + vertical-pair copy (luma ALF only) -------------------------------------------------
+    if (alfY)
+    {
+      alfBlockCellsAndCopy<SA_P, SA_CELLP>(c0, cell, vBlk + 4, bi, bj, vb == 0);
+      if (vb)
+      {
+#pragma unroll 1
+        for (int k = 0; k < 4; k++)
+        {
+          const int li = 2 * bi + 1 + (k >> 1), lj = 2 * bj + 1 + (k & 1);
+          cell[li][lj] = alfCellAny<SA_P>(&A0[(2 * li + SA_HY - 2) * SA_P + 2 * lj + SA_HX - 2], y0 - 2 + 2 * li, ctuMask, vbL);
+        }
+      }
+      if (cpH >= 0) alfCopyQuad<SA_P>(A0 + cpH, V + cpV);
+      if (ringI >= 0) cell[ringI][ringJ] = alfCellAny<SA_P>(&A0[(2 * ringI + SA_HY - 2) * SA_P + 2 * ringJ + SA_HX - 2], y0 - 2 + 2 * ringI, ctuMask, vbL);
+      __syncthreads();
+    }
+
+    // ---- phase 2 ----------------------------------------------------------------------------------------------------
+    const bool lumaBlk = alfY && x0 + 4 * bj < g.w && y0 + 4 * bi < g.h;         // the last tile of a row / column may be partial
+    const AlfLumaEntry* e = nullptr;
+    LumaCoef K;
+    if (lumaBlk && !wide)
+    {
+      // window = cells (2bi .. 2bi+3) x (2bj .. 2bj+3).  Blocks at the virtual boundary use 3 of the 4 cell rows and the
+      // scale 96 (deriveClassificationBlk :977-1010).  Packed 16-bit sums: a cell holds at most 4 * (2^bd - 1) per direction, so
+      // up to 10 bits the whole window (16 cells) stays below 2^16 per lane; above, every cell row is unpacked on its own.
+      int sumV, sumH, sumD0, sumD1;
+      const uint4* rp = reinterpret_cast<const uint4*>(&cell[2 * bi][2 * bj]);
+      if (g.bdL <= 10)
+      {
+        uint32_t vh = 0, dd = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+          if ((vb == 1 && i == 3) || (vb == 2 && i == 0)) continue;
+          const uint4 q0 = rp[i * (SA_CELLP / 2)], q1 = rp[i * (SA_CELLP / 2) + 1];
+          vh += q0.x + q0.z + q1.x + q1.z; dd += q0.y + q0.w + q1.y + q1.w;
+        }
+        sumV = vh & 0xffff; sumH = vh >> 16; sumD0 = dd & 0xffff; sumD1 = dd >> 16;
+      }
+      else
+      {
+        sumV = sumH = sumD0 = sumD1 = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+          if ((vb == 1 && i == 3) || (vb == 2 && i == 0)) continue;
+          const uint4 q0 = rp[i * (SA_CELLP / 2)], q1 = rp[i * (SA_CELLP / 2) + 1];
+          const uint32_t vh = q0.x + q0.z + q1.x + q1.z, dd = q0.y + q0.w + q1.y + q1.w;
+          sumV += vh & 0xffff; sumH += vh >> 16; sumD0 += dd & 0xffff; sumD1 += dd >> 16;
+        }
+      }
+      int cls, tIdx;
+      alfClassify(sumV, sumH, sumD0, sumD1, vb ? 96 : 64, g.bdL, cls, tIdx);
+      e = lumaTab + ((ctl.setIdx * 25 + cls) * 4 + tIdx);
+      if (!vb) K = loadLumaCoef(e);                          // in flight during the chroma work below
+    }
+
+    if (ncomp > 1)
+    {
+#pragma unroll 1
+      for (int c = 0; c < 2; c++)
+      {
+        pel* const dC = c ? dCr : dCb;
+        const pel* Bc = c ? A2 : A1;
+        const bool fOn = c ? alfCr : alfCb;
+        const int idc = c ? ccCr : ccCb;
+        ChromaCoef C;
+        if (fOn) C = chromaCoef(&alfDev->chromaTab[c ? ctl.altCr : ctl.altCb]);
+        uint4 ck = make_uint4(0, 0, 0, 0);
+        if (idc && sx == 1) ck = __ldg(reinterpret_cast<const uint4*>(alfDev->ccK[c][idc - 1]));
+        const int qShift = 4 - sx, quads = k420 ? SA_THREADS : ((SA_T >> sx) >> 2) << (SA_THLOG - sy);
+#pragma unroll 1
+        for (int j = tid; j < quads; j += SA_THREADS)
+        {
+          int r, qx, co, lo;
+          if (k420) { r = rC; qx = qC; co = cOff; lo = lOff; }
+          else
+          {
+            r = j >> qShift;
+            if (qShift == 3) r = (r & ~3) | ((r & 1) << 1) | ((r >> 1) & 1);
+            qx = (j & ((1 << qShift) - 1)) * 4;
+            co = (r + SA_HY) * L.pitchC + qx + SA_HX; lo = ((r << sy) + SA_HY) * SA_P + (qx << sx) + SA_HX;
+          }
+          const int x = (x0 >> sx) + qx, y = (y0 >> sy) + r;
+          if (x >= wC || y >= hC) continue;
+          const pel* cb = Bc + co;
+          uint2 v = *reinterpret_cast<const uint2*>(cb);
+          if (fOn)
+          {
+            int lim; bool nearVb;
+            vbLimit(y & (ctuH - 1), vbC, 2, lim, nearVb);
+            v = alfChromaQuad(cb, min(1, lim) * L.pitchC, min(2, lim) * L.pitchC, nearVb, C, maxcP);
+          }
+          if (idc)
+          {
+            // CC-ALF row offsets in the luma tile (filterBlkCcAlf :1376-1386)
+            const int lpos = (y << sy) & ctuMask;
+            int l1 = SA_P, l2 = -SA_P, l3 = 2 * SA_P;
+            if (lpos == vbL - 2 || lpos == vbL + 1) l3 = SA_P;
+            else if (lpos == vbL - 1 || lpos == vbL) l1 = l2 = l3 = 0;
+            const pel* l = A0 + lo;
+            if (sx == 1)
+            {
+              const uint2 d = ck.w ? ccAlfQuadDual(l, l1, l2, l3, ck.x, ck.y, ck.z, maxcP, halfP)
+                                   : ccAlfQuad420(l, l1, l2, l3, alfDev->ccB[c][idc - 1], maxcP, halfP);
+              v.x = addClamp0(v.x, d.x, maxcP);
+              v.y = addClamp0(v.y, d.y, maxcP);
+            }
+            else
+            {
+              const int16_t* ccg = alfDev->cc[c][idc - 1];
+              const int maxc = (1 << g.bdC) - 1, half = (1 << g.bdC) >> 1;
+              int res[4] = { (int)(v.x & 0xffff), (int)(v.x >> 16), (int)(v.y & 0xffff), (int)(v.y >> 16) };
+              int cc[7];
+#pragma unroll
+              for (int k = 0; k < 7; k++) cc[k] = __ldg(&ccg[k]);
+#pragma unroll
+              for (int q = 0; q < 4; q++)
+              {
+                const pel* lq = l + q;
+                const int cu = lq[0];
+                int s = cc[0] * (lq[l2] - cu) + cc[1] * (lq[-1] - cu) + cc[2] * (lq[1] - cu) + cc[3] * (lq[l1 - 1] - cu) + cc[4] * (lq[l1] - cu) +
+                        cc[5] * (lq[l1 + 1] - cu) + cc[6] * (lq[l3] - cu);
+                s = (s + 64) >> 7;
+                s = clip3(0, maxc, s + half) - half;
+                res[q] = clip3(0, maxc, res[q] + s);
+              }
+              v = make_uint2((uint32_t)res[0] | (uint32_t)res[1] << 16, (uint32_t)res[2] | (uint32_t)res[3] << 16);
+            }
+          }
+          *reinterpret_cast<uint2*>(dC + y * pitchCh + x) = v;
+        }
+      }
+    }
+
+    if (alfY)
+    {
+      if (lumaBlk)
+      {
+        pel* out = dY + (y0 + 4 * bi) * pitchY + x0 + 4 * bj;
+        if (wide)    alfLumaBlockGeneric(cell, c0, out, pitchY, bi, bj, y0 + 4 * bi, &alfDev->luma[ctl.setIdx][0][0], ctuMask, vbL, g.bdL);
+        else if (vb) alfLumaBlockFast(c0, out, pitchY, e, maxvP, vb);
+        else         alfLumaBlockV<1>(vBlk, out, pitchY, K, maxvP);
+      }
+    }
+    else
+    {
+      // no luma ALF in this CTU: copy (128-bit rows)
+      for (int i = tid; i < SA_TH * (SA_T / 8); i += SA_THREADS)
+      {
+        const int r = i >> 3, gc = i & 7;
+        const int y = y0 + r, x = x0 + 8 * gc;
+        if (y < g.h && x < g.w)
+          *reinterpret_cast<int4*>(dY + y * pitchY + x) = *reinterpret_cast<const int4*>(&A0[(r + SA_HY) * SA_P + 8 * gc + SA_HX]);
+      }
+    }
+    __syncthreads();                                         // all reads of the stage buffers, the copy and the cells are done before they are refilled
     cur = nxt;
   }
 }

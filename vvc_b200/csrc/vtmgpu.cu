@@ -365,8 +365,9 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
   CK(cudaFuncSetAttribute(k_dbf_sao, cudaFuncAttributeMaxDynamicSharedMemorySize, DBF_SMEM_BYTES), "smem attribute");
   {
     const SaLayout SL = saLayout(g.sx, g.sy, g.ncomp);      // + one more tile: scratch copy for tiles cut by a virtual boundary
+    CK(cudaFuncSetAttribute(k_alf<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL.total), "smem attribute");
     CK(cudaFuncSetAttribute(k_alf<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL.total), "smem attribute");
-    CK(cudaFuncSetAttribute(k_alf<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL.total + SL.lumaBytes + 2 * SL.chromaBytes), "smem attribute");
+    CK(cudaFuncSetAttribute(k_alf_parts, cudaFuncAttributeMaxDynamicSharedMemorySize, SL.total + SL.lumaBytes + 2 * SL.chromaBytes), "smem attribute");
   }
   CK(cudaDeviceGetAttribute(&c->numSms, cudaDevAttrMultiProcessorCount, s.device), "device attribute");
   CK(cudaStreamSynchronize(c->stream), "sync");
@@ -931,6 +932,13 @@ extern "C" int vtmgpu_set_alf(vtmgpu_ctx* c, int slot, const vtmgpu_alf_params* 
           sum += co;
         }
         A.ccB[k][f][7] = (uint32_t)sum;
+        // two taps per IDP.2A (ccAlfQuadDual): (f0, 0, f6, 0), (0, f1, 0, f3), (-sum, f2, f4, f5)
+        const int16_t* co = p->ccalf_coeff[k][f];
+        auto b = [](int v) { return (uint32_t)(v & 0xff); };
+        A.ccK[k][f][0] = b(co[0]) | b(co[6]) << 16;
+        A.ccK[k][f][1] = b(co[1]) << 8 | b(co[3]) << 24;
+        A.ccK[k][f][2] = b(-sum) | b(co[2]) << 8 | b(co[4]) << 16 | b(co[5]) << 24;
+        A.ccK[k][f][3] = -sum >= -128 && -sum <= 127;
       }
     }
     // per-CTU control
@@ -1042,8 +1050,13 @@ int launchAlf(vtmgpu_ctx* c, int first, int count)
     st.dx = grid % tilesX;
     st.dy = (grid / tilesX) % tilesY;
     st.ds = (grid / tilesX) / tilesY;
-    if (vb) k_alf<true><<<grid, SA_THREADS, smem, c->stream>>>(c->slotsDev, c->tmapsDev, s, n, src, dst, g, tilesX, tilesY, ty0, st);
-    else    k_alf<false><<<grid, SA_THREADS, smem, c->stream>>>(c->slotsDev, c->tmapsDev, s, n, src, dst, g, tilesX, tilesY, ty0, st);
+    if (vb) k_alf_parts<<<grid, SA_THREADS, smem, c->stream>>>(c->slotsDev, c->tmapsDev, s, n, src, dst, g, tilesX, tilesY, ty0, st);
+    else
+    {
+      const int pitchY = c->slotsPinned[s].buf[0][0].pitch, pitchC = g.ncomp > 1 ? c->slotsPinned[s].buf[0][1].pitch : 0;
+      if (g.ncomp == 3 && g.sx == 1 && g.sy == 1) k_alf<true><<<grid, SA_THREADS, smem, c->stream>>>(c->slotsDev, c->tmapsDev, s, n, src, dst, g, tilesX, tilesY, ty0, st, pitchY, pitchC);
+      else                                        k_alf<false><<<grid, SA_THREADS, smem, c->stream>>>(c->slotsDev, c->tmapsDev, s, n, src, dst, g, tilesX, tilesY, ty0, st, pitchY, pitchC);
+    }
     c->launches++;
     for (int i = s; i < s + n; i++) c->cur[i] = dst;
     return c->cuda(cudaGetLastError(), "k_alf launch");

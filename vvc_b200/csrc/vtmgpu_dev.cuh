@@ -48,6 +48,7 @@ struct AlfDev
   int32_t wide;                                      // a luma coefficient does not fit the s8 operand of IDP.2A: generic path
   int32_t pad;
   uint32_t ccB[2][4][8];                             // CC-ALF coefficients as IDP.2A byte operands (bytes 0 and 3); [7] = sum of the 7 (16-byte aligned rows)
+  uint32_t ccK[2][4][4];                             // the same as two-tap operands of ccAlfQuadDual (alf_fast.cuh); [3] = 1 when the coefficient sum fits a byte
   short2  luma[VTMGPU_MAX_LUMA_SETS][25][12];        // {coeff, clip} per set, class, tap (transpose 0 order)
   short2  chroma[8][6];                              // {coeff, clip} per alternative, tap
   AlfChromaEntry chromaTab[8];                       // the same, expanded into the operands of the packed 5x5 kernel
