@@ -20,7 +20,8 @@ __device__ __forceinline__ uint32_t hash32(uint32_t x)
   return x;
 }
 
-template <int MODE> __global__ void __launch_bounds__(256, 2) k(const AlfLumaEntry* __restrict__ tab, pel* __restrict__ out, long long* cyc)
+// VAR bit 0: no CTA barrier between iterations ; bit 1: the filter entry is loaded once, before the loop
+template <int MODE, int VAR = 0> __global__ void __launch_bounds__(256, 2) k(const AlfLumaEntry* __restrict__ tab, pel* __restrict__ out, long long* cyc)
 {
   extern __shared__ __align__(128) unsigned char sm[];
   pel* H = reinterpret_cast<pel*>(sm);                                       // [SA_H][SA_P], tile origin at (SA_HY, SA_HX)
@@ -39,14 +40,16 @@ template <int MODE> __global__ void __launch_bounds__(256, 2) k(const AlfLumaEnt
   const pel* c0 = &H[(4 * bi + SA_HY) * SA_P + 4 * bj + SA_HX];
   const uint32_t* v = V + (4 * bi + 4) * AV_COLS + 4 * bj;
   const uint32_t maxvP = dup16(1023);
+  const LumaCoef K0 = loadLumaCoef(tab + hash32(tid * 977 + blockIdx.x) % 100);
   const long long t0 = clock64();
 #pragma unroll 1
   for (int it = 0; it < ITER; it++)
   {
     const AlfLumaEntry* e = tab + hash32(tid * 977 + it * 131 + blockIdx.x) % 100;
     if (MODE == 0) alfLumaBlockFast(c0, o, 64, e, maxvP, 0);
+    else if (VAR & 2) alfLumaBlockV<MODE - 1>(v, o + (it & 1) * 4096, 64, K0, maxvP);
     else           alfLumaBlockV<MODE - 1>(v, o, 64, loadLumaCoef(e), maxvP);
-    __syncthreads();
+    if (!(VAR & 1)) __syncthreads();
   }
   const long long t1 = clock64();
   if (tid == 0) cyc[blockIdx.x] = t1 - t0;
@@ -76,7 +79,7 @@ int main()
   AlfLumaEntry* dtab; pel* dout[2]; long long* dcyc;
   cudaMalloc(&dtab, sizeof(AlfLumaEntry) * 100);
   cudaMemcpy(dtab, tab.data(), sizeof(AlfLumaEntry) * 100, cudaMemcpyHostToDevice);
-  for (auto& d : dout) { cudaMalloc(&d, (size_t)grid * 4096 * 2); cudaMemset(d, 0, (size_t)grid * 4096 * 2); }
+  for (auto& d : dout) { cudaMalloc(&d, (size_t)(grid + 1) * 4096 * 2); cudaMemset(d, 0, (size_t)(grid + 1) * 4096 * 2); }
   cudaMalloc(&dcyc, sizeof(long long) * grid);
   const int smem = SA_H * SA_P * 2 + AV_BYTES;
   cudaFuncSetAttribute(k<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -106,6 +109,22 @@ int main()
     // one 4K picture = 60 x 34 tiles over 2 * nsm resident CTAs
     printf("%-48s %8.0f clocks per tile and CTA  -> %6.2f us per 3840x2160 picture at %.3f GHz (luma 7x7 alone)\n",
            names[mode], avg, avg * (60.0 * 34.0 / grid) / (p.clockRate * 1e-3), p.clockRate * 1e-6);
+  }
+  {
+    auto runv = [&](const char* name, auto kern) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      for (int rep = 0; rep < 2; rep++) { kern<<<grid, 256, smem>>>(dtab, dout[1], dcyc); cudaDeviceSynchronize(); }
+      cudaMemcpy(h.data(), dcyc, sizeof(long long) * grid, cudaMemcpyDeviceToHost);
+      double avg = 0;
+      for (long long c : h) avg += (double)c;
+      avg /= grid * ITER;
+      printf("%-48s %8.0f clocks per tile and CTA  -> %6.2f us per 3840x2160 picture\n", name, avg, avg * (60.0 * 34.0 / grid) / (p.clockRate * 1e-3));
+    };
+    runv("alfLumaBlockV<1>, no barrier", k<2, 1>);
+    runv("alfLumaBlockV<1>, entry loaded once", k<2, 2>);
+    runv("alfLumaBlockV<1>, no barrier, entry loaded once", k<2, 3>);
+    k<2, 0><<<grid, 256, smem>>>(dtab, dout[1], dcyc);      // leaves the reference result of the comparison below in dout[1]
+    cudaDeviceSynchronize();
   }
   std::vector<pel> a((size_t)grid * 4096), b((size_t)grid * 4096);
   cudaMemcpy(a.data(), dout[0], a.size() * 2, cudaMemcpyDeviceToHost);

@@ -33,7 +33,7 @@ constexpr int AV_BYTES = AV_ROWS * AV_COLS * 4;
 // with IDP.2A (tools/microbench/mb_mix.cu); VIADDMNMX with an unreachable bound is the same add on the other pipe
 __device__ __forceinline__ uint32_t addAlu(uint32_t a, uint32_t b) { return __viaddmin_s16x2(a, b, 0x7fff7fffu); }
 
-// the operands of one filter entry in registers (ten 128-bit loads, issued by the caller ahead of the filter)
+// the operands of one filter entry in registers (nine 128-bit loads + the bias)
 struct LumaCoef
 {
   uint32_t coefB[12], clipP1[12], clip2[12];
@@ -47,12 +47,12 @@ __device__ __forceinline__ LumaCoef loadLumaCoef(const AlfLumaEntry* __restrict_
 #pragma unroll
   for (int i = 0; i < 3; i++)
   {
-    const uint4 a = __ldg(q + i), b = __ldg(q + 3 + i), c = __ldg(q + 6 + i);
+    const uint4 a = q[i], b = q[3 + i], c = q[6 + i];            // plain loads: k_alf keeps the tile's filter set in shared memory
     K.coefB[4 * i] = a.x; K.coefB[4 * i + 1] = a.y; K.coefB[4 * i + 2] = a.z; K.coefB[4 * i + 3] = a.w;
     K.clipP1[4 * i] = b.x; K.clipP1[4 * i + 1] = b.y; K.clipP1[4 * i + 2] = b.z; K.clipP1[4 * i + 3] = b.w;
     K.clip2[4 * i] = c.x; K.clip2[4 * i + 1] = c.y; K.clip2[4 * i + 2] = c.z; K.clip2[4 * i + 3] = c.w;
   }
-  K.bias = __ldg(&e->bias);
+  K.bias = e->bias;
   return K;
 }
 

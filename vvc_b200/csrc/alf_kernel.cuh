@@ -66,13 +66,17 @@ __constant__ int8_t c_perm7[4][12] = { { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11 },
 struct SaLayout
 {
   int pitchC, rowsC;               // chroma tile buffers: pitch in samples, rows
-  int lumaBytes, chromaBytes, offCell, offV, offPar, offBar, total;
+  int lumaBytes, chromaBytes, stageBytes, offSet, offSmall, offCell, offV, offPar, offBar, total;
   __host__ __device__ int comp(int c) const { return c ? lumaBytes + (c - 1) * chromaBytes : 0; }
-  __host__ __device__ int offA(int stage, int c) const { return stage * (lumaBytes + 2 * chromaBytes) + comp(c); }
+  __host__ __device__ int offA(int stage, int c) const { return stage * stageBytes + comp(c); }
 };
 
+constexpr int AT_SET_BYTES = 100 * (int)sizeof(AlfLumaEntry);      // one luma filter set: 25 classes x 4 transposes (17 600 bytes)
+
 // all tile buffer sizes are multiples of 128 bytes (TMA destination alignment)
-__host__ __device__ inline SaLayout saLayout(int sx, int sy, int ncomp)
+// tables = true (k_alf): every stage also holds the luma filter set of the tile's CTU and the chroma / CC-ALF operand tables of its
+// picture, brought in by bulk copies next to the sample tiles
+__host__ __device__ inline SaLayout saLayout(int sx, int sy, int ncomp, bool tables = false)
 {
   SaLayout L;
   const int tw = SA_T >> sx, th = SA_TH >> sy;
@@ -80,7 +84,10 @@ __host__ __device__ inline SaLayout saLayout(int sx, int sy, int ncomp)
   L.rowsC = th + 2 * SA_HY;
   L.lumaBytes = SA_H * SA_P * 2;
   L.chromaBytes = ncomp > 1 ? L.rowsC * L.pitchC * 2 : 0;
-  L.offCell = 2 * (L.lumaBytes + 2 * L.chromaBytes);
+  L.offSet = L.lumaBytes + 2 * L.chromaBytes;                  // inside a stage
+  L.offSmall = L.offSet + (tables ? (AT_SET_BYTES + 127) / 128 * 128 : 0);
+  L.stageBytes = L.offSmall + (tables ? ALF_SMALL_BYTES : 0);
+  L.offCell = 2 * L.stageBytes;
   L.offV = L.offCell + SA_CELLR * SA_CELLP * 8;                // vertical-pair copy of the luma tile (alf_fast.cuh), 16-byte aligned
   L.offPar = L.offV + AV_BYTES;
   L.offBar = L.offPar + 2 * 4 * (int)sizeof(CtuCtlDev);      // per stage: the control records of the (up to 2 x 2) CTUs under the tile
@@ -335,12 +342,12 @@ __device__ __forceinline__ void alfLumaBlockFast(const pel* c0, pel* out, int pi
     const uint4* q = reinterpret_cast<const uint4*>(E);                                                                 \
     _Pragma("unroll") for (int i = 0; i < 3; i++)                                                                       \
     {                                                                                                                   \
-      const uint4 a = __ldg(q + i), b = __ldg(q + 3 + i), c = __ldg(q + 6 + i);                                         \
+      const uint4 a = q[i], b = q[3 + i], c = q[6 + i];                  /* plain loads: the entry may sit in shared memory */ \
       coefB[4 * i] = a.x; coefB[4 * i + 1] = a.y; coefB[4 * i + 2] = a.z; coefB[4 * i + 3] = a.w;                       \
       clipP1[4 * i] = b.x; clipP1[4 * i + 1] = b.y; clipP1[4 * i + 2] = b.z; clipP1[4 * i + 3] = b.w;                   \
       clip2[4 * i] = c.x; clip2[4 * i + 1] = c.y; clip2[4 * i + 2] = c.z; clip2[4 * i + 3] = c.w;                       \
     }                                                                                                                   \
-    bias = __ldg(&(E)->bias);                                                                                           \
+    bias = (E)->bias;                                                                                                   \
   }
   uint32_t coefB[12], clipP1[12], clip2[12];
   int bias;
@@ -414,7 +421,7 @@ __device__ __forceinline__ ChromaCoef chromaCoef(const AlfChromaEntry* __restric
 {
   ChromaCoef c;
   const uint4* q = reinterpret_cast<const uint4*>(e);
-  const uint4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4);
+  const uint4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4];          // plain loads: the table may sit in shared memory
   c.coefB[0] = q0.x; c.coefB[1] = q0.y; c.coefB[2] = q0.z; c.coefB[3] = q0.w; c.coefB[4] = q1.x; c.coefB[5] = q1.y;
   c.clipP1[0] = q1.z; c.clipP1[1] = q1.w; c.clipP1[2] = q2.x; c.clipP1[3] = q2.y; c.clipP1[4] = q2.z; c.clipP1[5] = q2.w;
   c.clip2[0] = q3.x; c.clip2[1] = q3.y; c.clip2[2] = q3.z; c.clip2[3] = q3.w; c.clip2[4] = q4.x; c.clip2[5] = q4.y;
@@ -850,23 +857,55 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf_parts(const 
 
 // ---- the common kernel: one CTU per tile, no signalled virtual boundary ------------------------------------------------------
 // (pictures with signalled virtual boundaries or CTU size 32 take k_alf_parts above.)  Per tile:
-//   wait      the TMA loads of the tile (issued one tile ahead) have landed
+//   wait      the loads of the tile (issued one tile ahead) have landed: three TMA boxes of samples + two bulk copies of operand
+//             tables -- the luma filter set of the tile's CTU (25 classes x 4 transposes, 17.6 KB) and the chroma / CC-ALF
+//             tables of its picture.  Round 2 measurement (tools/microbench/mb_alf_luma.cu): gathering the ten 128-bit words of
+//             a block's filter entry from global memory -- every thread of a warp another entry -- cost a third of the luma
+//             filter's time; from shared memory the same gather is ten LDS.128.
 //   pad       only tiles on a picture border or with a clipped CTU side: replicate samples into the outside (CTA barrier)
 //   phase 1   every thread: Laplacian cells of its 4x4 block (packed diagonal pairs) and its part of the vertical-pair copy of the
 //             luma tile; spare threads: the ring of halo cells and the border of the copy                       (CTA barrier)
-//   phase 2   class of the block from the 4x4 cell window, loads of the filter entry, then -- while those are in flight -- the
-//             chroma 5x5 + CC-ALF quads of the thread, then the 7x7 luma block from the vertical-pair copy          (CTA barrier)
-// The control record of the tile's CTU travels through registers, loaded one tile ahead.  k420 = true compiles the chroma
-// geometry of 4:2:0 in (one quad per thread and plane, no loop); the other formats take the run-time instantiation.
-// Everything that does not depend on the tile (thread offsets into the shared-memory arrays, packed constants) is computed
-// once per CTA: round 1 spent 28 of its 138 instructions per pixel on per-tile bookkeeping.
+//   phase 2   class of the block from the 4x4 cell window, then the chroma 5x5 + CC-ALF quads of the thread, then the 7x7 luma
+//             block from the vertical-pair copy                                                                    (CTA barrier)
+// The control record of a tile's CTU is all the kernel reads from global memory besides the samples; it travels through
+// registers, loaded two tiles ahead (the tile after next needs it when its table copy is issued).  Plane and table addresses
+// are computed from the slot number (AlfAddr).  k420 = true compiles the chroma geometry of 4:2:0 in (one quad per thread and
+// plane, no loop); the other formats take the run-time instantiation.
+__device__ __forceinline__ uint4 alfLoadCtl(const AlfAddr& A, const Geom& g, int firstSlot, const SaWalk& p, int ty0)
+{
+  const CtuCtlDev* ctl = reinterpret_cast<const CtuCtlDev*>(A.side + (size_t)(firstSlot + p.slot) * A.sideStride + A.offCtl);
+  return __ldg(reinterpret_cast<const uint4*>(&ctl[(((p.ty + ty0) * SA_TH) >> g.ctuLog2) * g.wCtus + ((p.tx * SA_T) >> g.ctuLog2)]));
+}
+
+// asynchronous loads of one tile into `stage` (one thread): sample boxes + operand tables
+__device__ __forceinline__ void alfPrefetch(unsigned char* smraw, const SaLayout& L, int stage, const AlfAddr& A, const CUtensorMap* maps, int slotAbs, const SaWalk& p,
+                                            const Geom& g, int ncomp, int sx, int sy, int ty0, uint4 ctlv)
+{
+  const int x0 = p.tx * SA_T, y0 = (p.ty + ty0) * SA_TH;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smraw + L.offBar) + stage;
+  unsigned char* st = smraw + stage * L.stageBytes;
+  const uint32_t flags = (ctlv.z >> 8) & 0xff, enY = ctlv.x & 0xff, setIdx = ctlv.y >> 24;
+  const bool small = (flags & 1) != 0, tab = small && enY != 0 && !(flags & 2);
+  const unsigned char* side = A.side + (size_t)slotAbs * A.sideStride;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic-proxy accesses to the stage buffers are ordered before the async writes
+  mbarExpectTx(bar, (uint32_t)(L.lumaBytes + 2 * L.chromaBytes + (tab ? AT_SET_BYTES : 0) + (small ? ALF_SMALL_BYTES : 0)));
+  tmaLoad2D(st, maps, x0 - SA_HX, y0 - SA_HY, bar);
+  if (ncomp > 1)
+  {
+    tmaLoad2D(st + L.lumaBytes, maps + 1, (x0 >> sx) - SA_HX, (y0 >> sy) - SA_HY, bar);
+    tmaLoad2D(st + L.lumaBytes + L.chromaBytes, maps + 2, (x0 >> sx) - SA_HX, (y0 >> sy) - SA_HY, bar);
+  }
+  if (tab) bulkLoad(st + L.offSet, side + A.offTab + (size_t)setIdx * AT_SET_BYTES, AT_SET_BYTES, bar);
+  if (small) bulkLoad(st + L.offSmall, side + A.offAlf, ALF_SMALL_BYTES, bar);
+}
+
 template <bool k420>
-__global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDev* __restrict__ slots, const CUtensorMap* __restrict__ tmaps, int firstSlot, int numSlots,
-                                                                    int srcBuf, int dstBuf, Geom g, int tilesX, int tilesY, int ty0, SaStep step, int pitchY, int pitchCh)
+__global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAddr A, const CUtensorMap* __restrict__ tmaps, int firstSlot, int numSlots,
+                                                                    int srcBuf, int dstBuf, Geom g, int tilesX, int tilesY, int ty0, SaStep step)
 {
   extern __shared__ __align__(128) unsigned char smraw[];
   const int sx = k420 ? 1 : g.sx, sy = k420 ? 1 : g.sy, ncomp = k420 ? 3 : g.ncomp;
-  const SaLayout L = saLayout(sx, sy, ncomp);
+  const SaLayout L = saLayout(sx, sy, ncomp, true);
   const int tid = threadIdx.x;
   uint2 (*cell)[SA_CELLP] = reinterpret_cast<uint2 (*)[SA_CELLP]>(smraw + L.offCell);
   uint32_t* const V = reinterpret_cast<uint32_t*>(smraw + L.offV);
@@ -875,9 +914,9 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDe
   const int bi = tid >> 4, bj = tid & 15;
   const int ctuH = g.ctu >> sy, vbC = ctuH - 2;
   const uint32_t maxcP = dup16((1 << g.bdC) - 1), halfP = dup16((1 << g.bdC) >> 1), maxvP = dup16((1 << g.bdL) - 1);
-  const int stageBytes = L.lumaBytes + 2 * L.chromaBytes;
   const int wC = g.w >> sx, hC = g.h >> sy;
-  // thread constants: block origin in the row-major tile, in the vertical-pair copy, in the cell array
+  const int pitchY = A.pitchY, pitchCh = A.pitchC;
+  // thread constants: block origin in the row-major tile and in the vertical-pair copy
   const int hOff = (4 * bi + SA_HY) * SA_P + 4 * bj + SA_HX;
   uint32_t* const vBlk = V + (4 * bi + 4) * AV_COLS + 4 * bj;
   // 4:2:0: the thread's chroma quad.  The rows of a warp are visited in the order 0, 2, 1, 3 so that the two rows of a half warp
@@ -917,45 +956,38 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDe
     mbarInit(&bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  uint4 ctlNext;
+  SaWalk nxt = cur;
+  saAdvance(nxt, step, tilesX, tilesY);
+  uint4 ctl0 = alfLoadCtl(A, g, firstSlot, cur, ty0), ctl1 = make_uint4(0, 0, 0, 0);
+  if (nxt.slot < numSlots) ctl1 = alfLoadCtl(A, g, firstSlot, nxt, ty0);
   __syncthreads();
-  {
-    const SlotDev& S = slots[firstSlot + cur.slot];
-    saPrefetch(smraw, L, 0, S, tmaps + ((size_t)(firstSlot + cur.slot) * 3 + srcBuf) * 3, cur, g, ty0, false);
-    ctlNext = __ldg(reinterpret_cast<const uint4*>(&S.ctuCtl[(((cur.ty + ty0) * SA_TH) >> g.ctuLog2) * g.wCtus + ((cur.tx * SA_T) >> g.ctuLog2)]));
-  }
+  if (tid == 0) alfPrefetch(smraw, L, 0, A, tmaps + ((size_t)(firstSlot + cur.slot) * 3 + srcBuf) * 3, firstSlot + cur.slot, cur, g, ncomp, sx, sy, ty0, ctl0);
   for (uint32_t it = 0; cur.slot < numSlots; it++)
   {
     const int stage = it & 1;
-    const SlotDev& S = slots[firstSlot + cur.slot];
-    SaWalk nxt = cur;
-    saAdvance(nxt, step, tilesX, tilesY);
-    const uint4 ctlCur = ctlNext;
-    if (nxt.slot < numSlots)
-    {
-      const SlotDev& Sn = slots[firstSlot + nxt.slot];
-      saPrefetch(smraw, L, stage ^ 1, Sn, tmaps + ((size_t)(firstSlot + nxt.slot) * 3 + srcBuf) * 3, nxt, g, ty0, false);
-      ctlNext = __ldg(reinterpret_cast<const uint4*>(&Sn.ctuCtl[(((nxt.ty + ty0) * SA_TH) >> g.ctuLog2) * g.wCtus + ((nxt.tx * SA_T) >> g.ctuLog2)]));
-    }
-    // the slot's destination planes and ALF data (uniform loads, consumed after the first barrier)
-    pel* const dY = S.buf[dstBuf][0].p;
-    pel* const dCb = ncomp > 1 ? S.buf[dstBuf][1].p : nullptr;
-    pel* const dCr = ncomp > 1 ? S.buf[dstBuf][2].p : nullptr;
-    const int2 onWide = *reinterpret_cast<const int2*>(&S.alfOn);        // { alfOn, alfWide }
-    const AlfDev* const alfDev = S.alf;
-    const AlfLumaEntry* const lumaTab = S.lumaTab;
+    SaWalk nx2 = nxt;
+    saAdvance(nx2, step, tilesX, tilesY);
+    uint4 ctl2 = make_uint4(0, 0, 0, 0);
+    if (nx2.slot < numSlots) ctl2 = alfLoadCtl(A, g, firstSlot, nx2, ty0);
+    if (tid == 0 && nxt.slot < numSlots)
+      alfPrefetch(smraw, L, stage ^ 1, A, tmaps + ((size_t)(firstSlot + nxt.slot) * 3 + srcBuf) * 3, firstSlot + nxt.slot, nxt, g, ncomp, sx, sy, ty0, ctl1);
+
+    pel* const dY = A.planes + (size_t)(firstSlot + cur.slot) * A.slotStride + (size_t)dstBuf * A.bufStride;
+    const AlfDev* const alfDev = reinterpret_cast<const AlfDev*>(A.side + (size_t)(firstSlot + cur.slot) * A.sideStride + A.offAlf);
     CtuCtlDev ctl;
-    *reinterpret_cast<uint4*>(&ctl) = ctlCur;
-    const bool alfOn = onWide.x != 0, wide = onWide.y != 0;
+    *reinterpret_cast<uint4*>(&ctl) = ctl0;
+    const bool alfOn = (ctl.flags & 1) != 0, wide = (ctl.flags & 2) != 0;
     const bool alfY = alfOn && ctl.enY != 0, alfCb = alfOn && ctl.enCb != 0, alfCr = alfOn && ctl.enCr != 0;
     const int ccCb = alfOn ? ctl.ccCb : 0, ccCr = alfOn ? ctl.ccCr : 0;
     const int clip = ctl.clip;
     const int x0 = cur.tx * SA_T, y0 = (cur.ty + ty0) * SA_TH;
-    pel* const A0 = reinterpret_cast<pel*>(smraw + stage * stageBytes);
-    pel* const A1 = reinterpret_cast<pel*>(smraw + stage * stageBytes + L.lumaBytes);
-    pel* const A2 = reinterpret_cast<pel*>(smraw + stage * stageBytes + L.lumaBytes + L.chromaBytes);
+    unsigned char* const st = smraw + stage * L.stageBytes;
+    pel* const A0 = reinterpret_cast<pel*>(st);
+    pel* const A1 = reinterpret_cast<pel*>(st + L.lumaBytes);
+    pel* const A2 = reinterpret_cast<pel*>(st + L.lumaBytes + L.chromaBytes);
+    const AlfDev* const small = reinterpret_cast<const AlfDev*>(st + L.offSmall);      // only chromaTab and ccK are there
 
-    mbarWait(&bars[stage], (it >> 1) & 1);                   // the TMA writes of this tile are visible to this thread
+    mbarWait(&bars[stage], (it >> 1) & 1);                   // the async writes of this tile are visible to this thread
 
     // tiles on the picture border: replicate the border samples into the zero-filled outside
     // (= UnitBuf::extendBorderPel of the ALF input, AdaptiveLoopFilter.cpp:411); CTU sides at a slice / tile boundary the
@@ -1007,7 +1039,6 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDe
     // ---- phase 2 ----------------------------------------------------------------------------------------------------
     const bool lumaBlk = alfY && x0 + 4 * bj < g.w && y0 + 4 * bi < g.h;         // the last tile of a row / column may be partial
     const AlfLumaEntry* e = nullptr;
-    LumaCoef K;
     if (lumaBlk && !wide)
     {
       // window = cells (2bi .. 2bi+3) x (2bj .. 2bj+3).  Blocks at the virtual boundary use 3 of the 4 cell rows and the
@@ -1041,8 +1072,7 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDe
       }
       int cls, tIdx;
       alfClassify(sumV, sumH, sumD0, sumD1, vb ? 96 : 64, g.bdL, cls, tIdx);
-      e = lumaTab + ((ctl.setIdx * 25 + cls) * 4 + tIdx);
-      if (!vb) K = loadLumaCoef(e);                          // in flight during the chroma work below
+      e = reinterpret_cast<const AlfLumaEntry*>(st + L.offSet) + (cls * 4 + tIdx);
     }
 
     if (ncomp > 1)
@@ -1050,14 +1080,14 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDe
 #pragma unroll 1
       for (int c = 0; c < 2; c++)
       {
-        pel* const dC = c ? dCr : dCb;
+        pel* const dC = dY + (c ? A.compOff[2] : A.compOff[1]);
         const pel* Bc = c ? A2 : A1;
         const bool fOn = c ? alfCr : alfCb;
         const int idc = c ? ccCr : ccCb;
         ChromaCoef C;
-        if (fOn) C = chromaCoef(&alfDev->chromaTab[c ? ctl.altCr : ctl.altCb]);
+        if (fOn) C = chromaCoef(&small->chromaTab[c ? ctl.altCr : ctl.altCb]);
         uint4 ck = make_uint4(0, 0, 0, 0);
-        if (idc && sx == 1) ck = __ldg(reinterpret_cast<const uint4*>(alfDev->ccK[c][idc - 1]));
+        if (idc && sx == 1) ck = *reinterpret_cast<const uint4*>(small->ccK[c][idc - 1]);
         const int qShift = 4 - sx, quads = k420 ? SA_THREADS : ((SA_T >> sx) >> 2) << (SA_THLOG - sy);
 #pragma unroll 1
         for (int j = tid; j < quads; j += SA_THREADS)
@@ -1130,7 +1160,7 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDe
         pel* out = dY + (y0 + 4 * bi) * pitchY + x0 + 4 * bj;
         if (wide)    alfLumaBlockGeneric(cell, c0, out, pitchY, bi, bj, y0 + 4 * bi, &alfDev->luma[ctl.setIdx][0][0], ctuMask, vbL, g.bdL);
         else if (vb) alfLumaBlockFast(c0, out, pitchY, e, maxvP, vb);
-        else         alfLumaBlockV<1>(vBlk, out, pitchY, K, maxvP);
+        else         alfLumaBlockV<1>(vBlk, out, pitchY, loadLumaCoef(e), maxvP);
       }
     }
     else
@@ -1145,7 +1175,7 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const SlotDe
       }
     }
     __syncthreads();                                         // all reads of the stage buffers, the copy and the cells are done before they are refilled
-    cur = nxt;
+    cur = nxt; nxt = nx2; ctl0 = ctl1; ctl1 = ctl2;
   }
 }
 

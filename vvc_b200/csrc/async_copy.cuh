@@ -48,6 +48,13 @@ __device__ __forceinline__ void tmaLoad2D(void* dst, const CUtensorMap* map, int
                ::"r"(smemAddr(dst)), "l"(map), "r"(x), "r"(y), "r"(smemAddr(bar)) : "memory");
 }
 
+// contiguous bytes (multiple of 16, both addresses 16-byte aligned) into shared memory, completing on the same kind of mbarrier (SASS UBLKCP)
+__device__ __forceinline__ void bulkLoad(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smemAddr(dst)), "l"(src), "r"(bytes), "r"(smemAddr(bar)) : "memory");
+}
+
 // position of a CTA in its round-robin walk over the work items of a batch of picture slots, and one step of the walk
 // (= gridDim.x items) decomposed on the host so that the loop needs no division
 struct TileStep

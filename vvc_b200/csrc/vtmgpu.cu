@@ -79,8 +79,11 @@ struct vtmgpu_ctx
   bool profiling = false, stageValid = false;
   std::string err;
   SideLayout lay{};
-  std::vector<pel*> planeMem;          // one allocation per slot (3 buffers x ncomp planes)
-  std::vector<unsigned char*> sideDev; // per slot
+  std::vector<pel*> planeMem;          // per slot (3 buffers x ncomp planes), all slots in ONE allocation at a constant stride: k_alf computes
+  std::vector<unsigned char*> sideDev; // per slot                                 plane and table addresses instead of loading them
+  pel* planeAll = nullptr;
+  unsigned char* sideAll = nullptr;
+  AlfAddr alfAddr{};
   std::vector<unsigned char*> sparseDev; // per slot, allocated by the first vtmgpu_set_deblock_sparse: landing area of the record lists
   unsigned char* sidePinned = nullptr; // capacity * lay.total
   SlotDev* slotsPinned = nullptr;      // capacity entries (pinned mirror)
@@ -175,8 +178,8 @@ extern "C" void vtmgpu_destroy(vtmgpu_ctx* c)
   if (!c) return;
   cudaSetDevice(c->seq.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  for (pel* p : c->planeMem) cudaFree(p);
-  for (unsigned char* p : c->sideDev) cudaFree(p);
+  if (c->planeAll) cudaFree(c->planeAll);
+  if (c->sideAll) cudaFree(c->sideAll);
   for (unsigned char* p : c->sparseDev) if (p) cudaFree(p);
   if (c->sidePinned) cudaFreeHost(c->sidePinned);
   if (c->slotsPinned) cudaFreeHost(c->slotsPinned);
@@ -265,16 +268,23 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
     planeElems[k] = alignUp((size_t)pitch[k] * ph[k], 128);
     slotElems += planeElems[k];
   }
+  CK(cudaMalloc((void**)&c->planeAll, slotElems * 3 * sizeof(pel) * s.capacity), "plane memory");
+  CK(cudaMemsetAsync(c->planeAll, 0, slotElems * 3 * sizeof(pel) * s.capacity, c->stream), "memset");
+  CK(cudaMalloc((void**)&c->sideAll, L.total * s.capacity), "side info memory");
+  CK(cudaMemsetAsync(c->sideAll, 0, L.total * s.capacity, c->stream), "memset");
+  {
+    AlfAddr& a = c->alfAddr;
+    a.planes = c->planeAll; a.slotStride = slotElems * 3; a.bufStride = slotElems;
+    a.compOff[0] = 0; a.compOff[1] = planeElems[0]; a.compOff[2] = g.ncomp > 1 ? planeElems[0] + planeElems[1] : 0;
+    a.pitchY = pitch[0]; a.pitchC = g.ncomp > 1 ? pitch[1] : 0;
+    a.side = c->sideAll; a.sideStride = L.total; a.offTab = L.alfTab; a.offAlf = L.alf; a.offCtl = L.ctuCtl;
+  }
   for (int sl = 0; sl < s.capacity; sl++)
   {
-    pel* mem = nullptr;
-    unsigned char* side = nullptr;
-    CK(cudaMalloc((void**)&mem, slotElems * 3 * sizeof(pel)), "plane memory");
+    pel* mem = c->planeAll + (size_t)sl * slotElems * 3;
+    unsigned char* side = c->sideAll + (size_t)sl * L.total;
     c->planeMem.push_back(mem);
-    CK(cudaMemsetAsync(mem, 0, slotElems * 3 * sizeof(pel), c->stream), "memset");
-    CK(cudaMalloc((void**)&side, L.total), "side info memory");
     c->sideDev.push_back(side);
-    CK(cudaMemsetAsync(side, 0, L.total, c->stream), "memset");
     SlotDev& sd = c->slotsPinned[sl];
     pel* p = mem;
     for (int b = 0; b < 3; b++)
@@ -364,9 +374,9 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
   CK(cudaMemcpyAsync(c->slotsDev, c->slotsPinned, sizeof(SlotDev) * s.capacity, cudaMemcpyHostToDevice, c->stream), "slot table upload");
   CK(cudaFuncSetAttribute(k_dbf_sao, cudaFuncAttributeMaxDynamicSharedMemorySize, DBF_SMEM_BYTES), "smem attribute");
   {
-    const SaLayout SL = saLayout(g.sx, g.sy, g.ncomp);      // + one more tile: scratch copy for tiles cut by a virtual boundary
-    CK(cudaFuncSetAttribute(k_alf<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL.total), "smem attribute");
-    CK(cudaFuncSetAttribute(k_alf<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL.total), "smem attribute");
+    const SaLayout SL = saLayout(g.sx, g.sy, g.ncomp), ST = saLayout(g.sx, g.sy, g.ncomp, true);      // parts: + one more tile: scratch copy for tiles cut by a virtual boundary
+    CK(cudaFuncSetAttribute(k_alf<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST.total), "smem attribute");
+    CK(cudaFuncSetAttribute(k_alf<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST.total), "smem attribute");
     CK(cudaFuncSetAttribute(k_alf_parts, cudaFuncAttributeMaxDynamicSharedMemorySize, SL.total + SL.lumaBytes + 2 * SL.chromaBytes), "smem attribute");
   }
   CK(cudaDeviceGetAttribute(&c->numSms, cudaDevAttrMultiProcessorCount, s.device), "device attribute");
@@ -942,10 +952,12 @@ extern "C" int vtmgpu_set_alf(vtmgpu_ctx* c, int slot, const vtmgpu_alf_params* 
       }
     }
     // per-CTU control
+    const uint8_t flags = (uint8_t)(((A.enabled[0] | A.enabled[1] | A.enabled[2]) != 0 ? 1 : 0) | (wide ? 2 : 0));
     for (int a = 0; a < n; a++)
     {
       CtuCtlDev& r = ctl[a];
       r.enCb = r.enCr = r.altCb = r.altCr = r.ccCb = r.ccCr = r.setIdx = 0;
+      r.flags = flags;
       r.clip = p->ctu_clip ? (uint8_t)(p->ctu_clip[a] & 63) : 0;
       r.enY = p->ctu_enable[0] && p->ctu_enable[0][a];
       if (r.enY)
@@ -975,6 +987,12 @@ extern "C" int vtmgpu_set_alf(vtmgpu_ctx* c, int slot, const vtmgpu_alf_params* 
     sd.alfWide = wide;
     if (p->num_luma_aps) c->markSide(slot, c->lay.alfTab + sizeof(AlfLumaEntry) * VTMGPU_ALF_FIXED_SETS * 100, sizeof(AlfLumaEntry) * 100 * p->num_luma_aps);
     c->markSide(slot, c->lay.ctuCtl, c->lay.sao - c->lay.ctuCtl);
+  }
+  else
+  {
+    // ALF off for this picture: k_alf reads nothing but the control records, so their flags are cleared
+    memset(c->pinnedSide(slot) + c->lay.ctuCtl, 0, (size_t)c->nCtus * sizeof(CtuCtlDev));
+    c->markSide(slot, c->lay.ctuCtl, (size_t)c->nCtus * sizeof(CtuCtlDev));
   }
   return c->pushSlot(slot);
 }
@@ -1043,7 +1061,7 @@ int launchAlf(vtmgpu_ctx* c, int first, int count)
     const int dst = src == 1 ? 2 : 1;
     bool vb = g.ctu < SA_T;                                      // tiles filtered in parts (virtual boundaries, several CTUs per tile) need a scratch copy of the tile
     for (int i = s; i < s + n; i++) vb |= (c->slotsPinned[i].vbAlf.nv | c->slotsPinned[i].vbAlf.nh) != 0;
-    const int smem = SL.total + (vb ? SL.lumaBytes + 2 * SL.chromaBytes : 0);
+    const int smem = vb ? SL.total + SL.lumaBytes + 2 * SL.chromaBytes : saLayout(g.sx, g.sy, g.ncomp, true).total;
     // persistent CTAs: four per SM (register limited), each walks the tiles round robin with double-buffered TMA loads
     const int grid = std::min(tilesX * tilesY * n, SA_CTAS_PER_SM * c->numSms);
     SaStep st;
@@ -1051,12 +1069,8 @@ int launchAlf(vtmgpu_ctx* c, int first, int count)
     st.dy = (grid / tilesX) % tilesY;
     st.ds = (grid / tilesX) / tilesY;
     if (vb) k_alf_parts<<<grid, SA_THREADS, smem, c->stream>>>(c->slotsDev, c->tmapsDev, s, n, src, dst, g, tilesX, tilesY, ty0, st);
-    else
-    {
-      const int pitchY = c->slotsPinned[s].buf[0][0].pitch, pitchC = g.ncomp > 1 ? c->slotsPinned[s].buf[0][1].pitch : 0;
-      if (g.ncomp == 3 && g.sx == 1 && g.sy == 1) k_alf<true><<<grid, SA_THREADS, smem, c->stream>>>(c->slotsDev, c->tmapsDev, s, n, src, dst, g, tilesX, tilesY, ty0, st, pitchY, pitchC);
-      else                                        k_alf<false><<<grid, SA_THREADS, smem, c->stream>>>(c->slotsDev, c->tmapsDev, s, n, src, dst, g, tilesX, tilesY, ty0, st, pitchY, pitchC);
-    }
+    else if (g.ncomp == 3 && g.sx == 1 && g.sy == 1) k_alf<true><<<grid, SA_THREADS, smem, c->stream>>>(c->alfAddr, c->tmapsDev, s, n, src, dst, g, tilesX, tilesY, ty0, st);
+    else                                             k_alf<false><<<grid, SA_THREADS, smem, c->stream>>>(c->alfAddr, c->tmapsDev, s, n, src, dst, g, tilesX, tilesY, ty0, st);
     c->launches++;
     for (int i = s; i < s + n; i++) c->cur[i] = dst;
     return c->cuda(cudaGetLastError(), "k_alf launch");

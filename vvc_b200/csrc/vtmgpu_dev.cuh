@@ -39,19 +39,21 @@ struct AlfChromaEntry
   int32_t  pad;
 };
 
-// ALF data of one picture
+// ALF data of one picture.  The chroma / CC-ALF operand tables come first: k_alf copies these ALF_SMALL_BYTES into shared
+// memory with one bulk copy per tile.
+#define ALF_SMALL_BYTES 768
 struct AlfDev
 {
+  AlfChromaEntry chromaTab[8];                       // chroma alternatives expanded into the operands of the packed 5x5 kernel
+  uint32_t ccK[2][4][4];                             // CC-ALF coefficients as two-tap operands of ccAlfQuadDual (alf_fast.cuh); [3] = 1 when the coefficient sum fits a byte
   int32_t enabled[3];
   int32_t ccEnabled[2];
   int32_t numSets;                                   // 16 fixed + APS sets
   int32_t wide;                                      // a luma coefficient does not fit the s8 operand of IDP.2A: generic path
   int32_t pad;
   uint32_t ccB[2][4][8];                             // CC-ALF coefficients as IDP.2A byte operands (bytes 0 and 3); [7] = sum of the 7 (16-byte aligned rows)
-  uint32_t ccK[2][4][4];                             // the same as two-tap operands of ccAlfQuadDual (alf_fast.cuh); [3] = 1 when the coefficient sum fits a byte
   short2  luma[VTMGPU_MAX_LUMA_SETS][25][12];        // {coeff, clip} per set, class, tap (transpose 0 order)
   short2  chroma[8][6];                              // {coeff, clip} per alternative, tap
-  AlfChromaEntry chromaTab[8];                       // the same, expanded into the operands of the packed 5x5 kernel
   int16_t cc[2][4][8];                               // CC-ALF coefficients (7 used)
 };
 
@@ -63,7 +65,7 @@ struct AlfLumaEntry
   uint32_t clipP1[12];   // (clip + 1) in both 16-bit lanes
   uint32_t clip2[12];    // (2 * clip) in both 16-bit lanes
   int32_t  bias;         // 64 - sum(coef * 2 * clip)
-  int32_t  pad[3];
+  int32_t  pad[7];       // 176 bytes = 44 words: entries e and e + 1 start 12 banks apart when a filter set sits in shared memory
 };
 
 // Per-CTU control record (16 bytes, one 128-bit load per tile): ALF control (Picture::getAlfCtuEnableFlag /
@@ -75,7 +77,8 @@ struct alignas(16) CtuCtlDev
   uint8_t ccCb, ccCr;            // CC-ALF filter idc (0 = off)
   uint8_t setIdx;                // luma filter set: < 16 fixed, else APS
   uint8_t clip;                  // VTMGPU_ALF_CLIP_* / PAD_*: partition boundaries the filter must not read across
-  uint8_t pad[7];
+  uint8_t flags;                 // bit 0: the picture runs ALF (SlotDev::alfOn), bit 1: SlotDev::alfWide -- so that k_alf needs nothing but this record
+  uint8_t pad[6];
 };
 
 struct LadfDev                   // vtmgpu_ladf; n = 0: off (the luma records carry tc / beta)
@@ -101,6 +104,17 @@ struct SlotDev
   int32_t alfWide;               // a luma coefficient does not fit the s8 operand of IDP.2A: generic path
   LadfDev ladf;
   VbDev vbSao, vbAlf;            // as given to vtmgpu_set_sao / vtmgpu_set_alf
+};
+
+// where the planes and the ALF side information of a slot live: all slots of a context share one allocation each, so k_alf
+// computes its addresses from the slot number (round 1 loaded five pointers per tile from the slot table)
+struct AlfAddr
+{
+  pel* planes;                   // slot s, buffer b, component k: planes + s * slotStride + b * bufStride + compOff[k]
+  size_t slotStride, bufStride, compOff[3];
+  int pitchY, pitchC;            // plane pitches in samples
+  const unsigned char* side;     // slot s: side + s * sideStride ; + offTab = AlfLumaEntry[sets][100], + offAlf = AlfDev, + offCtl = CtuCtlDev[ctus]
+  size_t sideStride, offTab, offAlf, offCtl;
 };
 
 struct Geom
