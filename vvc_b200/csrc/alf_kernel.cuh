@@ -46,6 +46,9 @@ constexpr int SA_THREADS = (SA_T / 4) * (SA_TH / 4);   // 256: one thread per 4x
 #ifndef SA_CTAS_PER_SM
 #define SA_CTAS_PER_SM 2
 #endif
+#ifndef ALF_BAL
+#define ALF_BAL 2               // which adds of the luma tap run on the ALU pipe (alfLumaBlockV): bit 0 the tap sum, bit 1 clip - cur
+#endif
 constexpr int SA_HX = 8, SA_HY = 4;         // halo loaded around a tile (x: one aligned group of 8)
 constexpr int SA_W = SA_T + 2 * SA_HX;      // 80
 constexpr int SA_H = SA_TH + 2 * SA_HY;     // 40
@@ -66,7 +69,7 @@ __constant__ int8_t c_perm7[4][12] = { { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11 },
 struct SaLayout
 {
   int pitchC, rowsC;               // chroma tile buffers: pitch in samples, rows
-  int lumaBytes, chromaBytes, stageBytes, offSet, offSmall, offCell, offV, offPar, offBar, total;
+  int lumaBytes, chromaBytes, stageBytes, offSet, offSmall, offCell, offV, offPar, offBar, offDesc, total;
   __host__ __device__ int comp(int c) const { return c ? lumaBytes + (c - 1) * chromaBytes : 0; }
   __host__ __device__ int offA(int stage, int c) const { return stage * stageBytes + comp(c); }
 };
@@ -91,7 +94,8 @@ __host__ __device__ inline SaLayout saLayout(int sx, int sy, int ncomp, bool tab
   L.offV = L.offCell + SA_CELLR * SA_CELLP * 8;                // vertical-pair copy of the luma tile (alf_fast.cuh), 16-byte aligned
   L.offPar = L.offV + AV_BYTES;
   L.offBar = L.offPar + 2 * 4 * (int)sizeof(CtuCtlDev);      // per stage: the control records of the (up to 2 x 2) CTUs under the tile
-  L.total = L.offBar + 16;
+  L.offDesc = L.offBar + 16;                                 // per stage: tile descriptor written by the walking thread (k_alf)
+  L.total = L.offDesc + 2 * 32;
   return L;
 }
 
@@ -899,6 +903,13 @@ __device__ __forceinline__ void alfPrefetch(unsigned char* smraw, const SaLayout
   if (small) bulkLoad(st + L.offSmall, side + A.offAlf, ALF_SMALL_BYTES, bar);
 }
 
+// what every thread needs to know about a tile: written to shared memory by the one thread that walks the tile sequence
+struct alignas(16) AlfTileDesc
+{
+  int x0, y0, slotAbs, valid;
+  uint4 ctl;                     // CtuCtlDev of the tile's CTU
+};
+
 template <bool k420>
 __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAddr A, const CUtensorMap* __restrict__ tmaps, int firstSlot, int numSlots,
                                                                     int srcBuf, int dstBuf, Geom g, int tilesX, int tilesY, int ty0, SaStep step)
@@ -910,6 +921,7 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
   uint2 (*cell)[SA_CELLP] = reinterpret_cast<uint2 (*)[SA_CELLP]>(smraw + L.offCell);
   uint32_t* const V = reinterpret_cast<uint32_t*>(smraw + L.offV);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + L.offBar);
+  AlfTileDesc* const desc = reinterpret_cast<AlfTileDesc*>(smraw + L.offDesc);
   const int vbL = g.ctu - 4, ctuMask = g.ctu - 1;
   const int bi = tid >> 4, bj = tid & 15;
   const int ctuH = g.ctu >> sy, vbC = ctuH - 2;
@@ -941,46 +953,59 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
     else { const int k = q - 2 * SA_CELLS; ringI = 1 + (k >> 1); ringJ = (k & 1) ? SA_CELLS - 1 : 0; }
   }
 
-  SaWalk cur;
+  // ---- the tile walk lives in thread 0: it loads the control records two tiles ahead, issues the loads of the next tile and
+  // leaves a descriptor per tile in shared memory (round 2: the walk replicated in every thread was 4 instructions per pixel)
+  SaWalk nxt;
+  uint4 ctlB = make_uint4(0, 0, 0, 0);
   {
+    SaWalk cur;
     const int tilesPerPic = tilesX * tilesY, t = blockIdx.x;
     cur.slot = t / tilesPerPic;
     const int rem = t - cur.slot * tilesPerPic;
     cur.ty = rem / tilesX;
     cur.tx = rem - cur.ty * tilesX;
+    if (cur.slot >= numSlots) return;
+    nxt = cur;
+    if (tid == 0)
+    {
+      mbarInit(&bars[0], 1);
+      mbarInit(&bars[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      saAdvance(nxt, step, tilesX, tilesY);
+      const uint4 ctlA = alfLoadCtl(A, g, firstSlot, cur, ty0);
+      if (nxt.slot < numSlots) ctlB = alfLoadCtl(A, g, firstSlot, nxt, ty0);
+      desc[0].x0 = cur.tx * SA_T; desc[0].y0 = (cur.ty + ty0) * SA_TH; desc[0].slotAbs = firstSlot + cur.slot; desc[0].valid = 1; desc[0].ctl = ctlA;
+      alfPrefetch(smraw, L, 0, A, tmaps + ((size_t)(firstSlot + cur.slot) * 3 + srcBuf) * 3, firstSlot + cur.slot, cur, g, ncomp, sx, sy, ty0, ctlA);
+    }
   }
-  if (cur.slot >= numSlots) return;
-  if (tid == 0)
-  {
-    mbarInit(&bars[0], 1);
-    mbarInit(&bars[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  SaWalk nxt = cur;
-  saAdvance(nxt, step, tilesX, tilesY);
-  uint4 ctl0 = alfLoadCtl(A, g, firstSlot, cur, ty0), ctl1 = make_uint4(0, 0, 0, 0);
-  if (nxt.slot < numSlots) ctl1 = alfLoadCtl(A, g, firstSlot, nxt, ty0);
   __syncthreads();
-  if (tid == 0) alfPrefetch(smraw, L, 0, A, tmaps + ((size_t)(firstSlot + cur.slot) * 3 + srcBuf) * 3, firstSlot + cur.slot, cur, g, ncomp, sx, sy, ty0, ctl0);
-  for (uint32_t it = 0; cur.slot < numSlots; it++)
+  for (uint32_t it = 0;; it++)
   {
     const int stage = it & 1;
-    SaWalk nx2 = nxt;
-    saAdvance(nx2, step, tilesX, tilesY);
-    uint4 ctl2 = make_uint4(0, 0, 0, 0);
-    if (nx2.slot < numSlots) ctl2 = alfLoadCtl(A, g, firstSlot, nx2, ty0);
-    if (tid == 0 && nxt.slot < numSlots)
-      alfPrefetch(smraw, L, stage ^ 1, A, tmaps + ((size_t)(firstSlot + nxt.slot) * 3 + srcBuf) * 3, firstSlot + nxt.slot, nxt, g, ncomp, sx, sy, ty0, ctl1);
-
-    pel* const dY = A.planes + (size_t)(firstSlot + cur.slot) * A.slotStride + (size_t)dstBuf * A.bufStride;
-    const AlfDev* const alfDev = reinterpret_cast<const AlfDev*>(A.side + (size_t)(firstSlot + cur.slot) * A.sideStride + A.offAlf);
+    const int4 dsc = *reinterpret_cast<const int4*>(&desc[stage]);
+    if (!dsc.w) break;
+    const uint4 ctl0 = desc[stage].ctl;
+    if (tid == 0)
+    {
+      const bool more = nxt.slot < numSlots;
+      AlfTileDesc& d = desc[stage ^ 1];
+      d.x0 = nxt.tx * SA_T; d.y0 = (nxt.ty + ty0) * SA_TH; d.slotAbs = firstSlot + nxt.slot; d.valid = more; d.ctl = ctlB;
+      if (more)
+      {
+        alfPrefetch(smraw, L, stage ^ 1, A, tmaps + ((size_t)(firstSlot + nxt.slot) * 3 + srcBuf) * 3, firstSlot + nxt.slot, nxt, g, ncomp, sx, sy, ty0, ctlB);
+        saAdvance(nxt, step, tilesX, tilesY);
+        ctlB = nxt.slot < numSlots ? alfLoadCtl(A, g, firstSlot, nxt, ty0) : make_uint4(0, 0, 0, 0);
+      }
+    }
+    const int x0 = dsc.x, y0 = dsc.y;
+    pel* const dY = A.planes + (size_t)dsc.z * A.slotStride + (size_t)dstBuf * A.bufStride;
+    const AlfDev* const alfDev = reinterpret_cast<const AlfDev*>(A.side + (size_t)dsc.z * A.sideStride + A.offAlf);
     CtuCtlDev ctl;
     *reinterpret_cast<uint4*>(&ctl) = ctl0;
     const bool alfOn = (ctl.flags & 1) != 0, wide = (ctl.flags & 2) != 0;
     const bool alfY = alfOn && ctl.enY != 0, alfCb = alfOn && ctl.enCb != 0, alfCr = alfOn && ctl.enCr != 0;
     const int ccCb = alfOn ? ctl.ccCb : 0, ccCr = alfOn ? ctl.ccCr : 0;
     const int clip = ctl.clip;
-    const int x0 = cur.tx * SA_T, y0 = (cur.ty + ty0) * SA_TH;
     unsigned char* const st = smraw + stage * L.stageBytes;
     pel* const A0 = reinterpret_cast<pel*>(st);
     pel* const A1 = reinterpret_cast<pel*>(st + L.lumaBytes);
@@ -1077,50 +1102,45 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
 
     if (ncomp > 1)
     {
+      const int qShift = 4 - sx, quads = k420 ? SA_THREADS : ((SA_T >> sx) >> 2) << (SA_THLOG - sy);
 #pragma unroll 1
-      for (int c = 0; c < 2; c++)
+      for (int j = tid; j < quads; j += SA_THREADS)
       {
-        pel* const dC = dY + (c ? A.compOff[2] : A.compOff[1]);
-        const pel* Bc = c ? A2 : A1;
-        const bool fOn = c ? alfCr : alfCb;
-        const int idc = c ? ccCr : ccCb;
-        ChromaCoef C;
-        if (fOn) C = chromaCoef(&small->chromaTab[c ? ctl.altCr : ctl.altCb]);
-        uint4 ck = make_uint4(0, 0, 0, 0);
-        if (idc && sx == 1) ck = *reinterpret_cast<const uint4*>(small->ccK[c][idc - 1]);
-        const int qShift = 4 - sx, quads = k420 ? SA_THREADS : ((SA_T >> sx) >> 2) << (SA_THLOG - sy);
-#pragma unroll 1
-        for (int j = tid; j < quads; j += SA_THREADS)
+        // one item = 4 horizontally adjacent chroma samples, both planes (what depends only on the position is computed once)
+        int r, qx, co, lo;
+        if (k420) { r = rC; qx = qC; co = cOff; lo = lOff; }
+        else
         {
-          int r, qx, co, lo;
-          if (k420) { r = rC; qx = qC; co = cOff; lo = lOff; }
-          else
-          {
-            r = j >> qShift;
-            if (qShift == 3) r = (r & ~3) | ((r & 1) << 1) | ((r >> 1) & 1);
-            qx = (j & ((1 << qShift) - 1)) * 4;
-            co = (r + SA_HY) * L.pitchC + qx + SA_HX; lo = ((r << sy) + SA_HY) * SA_P + (qx << sx) + SA_HX;
-          }
-          const int x = (x0 >> sx) + qx, y = (y0 >> sy) + r;
-          if (x >= wC || y >= hC) continue;
-          const pel* cb = Bc + co;
+          r = j >> qShift;
+          if (qShift == 3) r = (r & ~3) | ((r & 1) << 1) | ((r >> 1) & 1);
+          qx = (j & ((1 << qShift) - 1)) * 4;
+          co = (r + SA_HY) * L.pitchC + qx + SA_HX; lo = ((r << sy) + SA_HY) * SA_P + (qx << sx) + SA_HX;
+        }
+        const int x = (x0 >> sx) + qx, y = (y0 >> sy) + r;
+        if (x >= wC || y >= hC) continue;
+        int lim; bool nearVb;
+        vbLimit(y & (ctuH - 1), vbC, 2, lim, nearVb);
+        const int o1 = min(1, lim) * L.pitchC, o2 = min(2, lim) * L.pitchC;
+        // CC-ALF row offsets in the luma tile (filterBlkCcAlf :1376-1386)
+        const int lpos = (y << sy) & ctuMask;
+        int l1 = SA_P, l2 = -SA_P, l3 = 2 * SA_P;
+        if (lpos == vbL - 2 || lpos == vbL + 1) l3 = SA_P;
+        else if (lpos == vbL - 1 || lpos == vbL) l1 = l2 = l3 = 0;
+        const pel* l = A0 + lo;
+        const int dOff = y * pitchCh + x;
+#pragma unroll 1
+        for (int c = 0; c < 2; c++)
+        {
+          const bool fOn = c ? alfCr : alfCb;
+          const int idc = c ? ccCr : ccCb;
+          const pel* cb = (c ? A2 : A1) + co;
           uint2 v = *reinterpret_cast<const uint2*>(cb);
-          if (fOn)
-          {
-            int lim; bool nearVb;
-            vbLimit(y & (ctuH - 1), vbC, 2, lim, nearVb);
-            v = alfChromaQuad(cb, min(1, lim) * L.pitchC, min(2, lim) * L.pitchC, nearVb, C, maxcP);
-          }
+          if (fOn) v = alfChromaQuad(cb, o1, o2, nearVb, chromaCoef(&small->chromaTab[c ? ctl.altCr : ctl.altCb]), maxcP);
           if (idc)
           {
-            // CC-ALF row offsets in the luma tile (filterBlkCcAlf :1376-1386)
-            const int lpos = (y << sy) & ctuMask;
-            int l1 = SA_P, l2 = -SA_P, l3 = 2 * SA_P;
-            if (lpos == vbL - 2 || lpos == vbL + 1) l3 = SA_P;
-            else if (lpos == vbL - 1 || lpos == vbL) l1 = l2 = l3 = 0;
-            const pel* l = A0 + lo;
             if (sx == 1)
             {
+              const uint4 ck = *reinterpret_cast<const uint4*>(small->ccK[c][idc - 1]);
               const uint2 d = ck.w ? ccAlfQuadDual(l, l1, l2, l3, ck.x, ck.y, ck.z, maxcP, halfP)
                                    : ccAlfQuad420(l, l1, l2, l3, alfDev->ccB[c][idc - 1], maxcP, halfP);
               v.x = addClamp0(v.x, d.x, maxcP);
@@ -1148,7 +1168,7 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
               v = make_uint2((uint32_t)res[0] | (uint32_t)res[1] << 16, (uint32_t)res[2] | (uint32_t)res[3] << 16);
             }
           }
-          *reinterpret_cast<uint2*>(dC + y * pitchCh + x) = v;
+          *reinterpret_cast<uint2*>(dY + (c ? A.compOff[2] : A.compOff[1]) + dOff) = v;
         }
       }
     }
@@ -1160,7 +1180,7 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
         pel* out = dY + (y0 + 4 * bi) * pitchY + x0 + 4 * bj;
         if (wide)    alfLumaBlockGeneric(cell, c0, out, pitchY, bi, bj, y0 + 4 * bi, &alfDev->luma[ctl.setIdx][0][0], ctuMask, vbL, g.bdL);
         else if (vb) alfLumaBlockFast(c0, out, pitchY, e, maxvP, vb);
-        else         alfLumaBlockV<1>(vBlk, out, pitchY, loadLumaCoef(e), maxvP);
+        else         alfLumaBlockV<ALF_BAL>(vBlk, out, pitchY, loadLumaCoef(e), maxvP);
       }
     }
     else
@@ -1175,7 +1195,6 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
       }
     }
     __syncthreads();                                         // all reads of the stage buffers, the copy and the cells are done before they are refilled
-    cur = nxt; nxt = nx2; ctl0 = ctl1; ctl1 = ctl2;
   }
 }
 
