@@ -37,6 +37,8 @@ B_ALG_CHAIN = 6.5          # algorithmic bytes per luma pixel of the whole chain
 B_ALG_DBF = 6.5            # k_dbf_sao : read 3 + write 3 + 0.5 segment records
 B_ALG_SAOALF = 6.0         # k_alf     : read 3 + write 3 (CTU parameters negligible)
 STREAM_4K = os.path.join(ROOT, "tests", "golden", "streams", "ra_2160p_8.bin")
+# BASELINE config 3 is quoted on 64 frames: ra_2160p_b.bin holds frames 32..63 of the same synthetic sequence (32 pictures), ra_2160p_8.bin frames 0..7
+STREAMS_4K = [os.path.join(ROOT, "tests", "golden", "streams", n) for n in ("ra_2160p_b.bin", "ra_2160p_8.bin")]
 DEC_GPU = os.path.join(ROOT, "vvc_b200", "_bin", "DecoderApp_gpu")
 
 
@@ -95,20 +97,32 @@ def load_pictures(distinct, device):
     import shutil
     import tempfile
     from vvc_b200 import capture, synth
-    if os.path.exists(STREAM_4K) and os.path.exists(DEC_GPU) and not os.environ.get("VTMGPU_BENCH_SYNTH"):
-        tmp = tempfile.mkdtemp(prefix="vtmgpu_cap_")
-        try:
-            env = dict(os.environ, VTMGPU_SHIM_BACKEND="gpu", VTMGPU_CAPTURE_DIR=tmp, VTMGPU_DEVICE=str(device))
-            r = subprocess.run([DEC_GPU, "-b", STREAM_4K, "-d", "0"], env=env, capture_output=True, text=True, timeout=600)
-            ok = r.stdout.count("(OK)")
-            files = sorted(glob.glob(os.path.join(tmp, "*.cap")))
-            if r.returncode == 0 and ok == len(files) and ok >= 1 and "ERROR" not in r.stdout:
-                caps = [capture.load(f) for f in files[:distinct]]
-                return caps, ("captured: VTM-encoded (RA, QP32, CC-ALF) synthetic 4K YUV decoded by DecoderApp_gpu, %d/%d pictures MD5 (OK), "
-                              "%d distinct pictures replayed" % (ok, len(files), len(caps)))
-            sys.stderr.write("bench.py: DecoderApp_gpu capture failed (rc=%d, OK=%d): %s\n" % (r.returncode, ok, (r.stdout + r.stderr)[-400:]))
-        finally:
-            shutil.rmtree(tmp, ignore_errors=True)
+    streams = [f for f in STREAMS_4K if os.path.exists(f)]
+    if streams and os.path.exists(DEC_GPU) and not os.environ.get("VTMGPU_BENCH_SYNTH"):
+        caps, oks, total = [], 0, 0
+        for stream in streams:
+            if len(caps) >= distinct:
+                break
+            tmp = tempfile.mkdtemp(prefix="vtmgpu_cap_")
+            try:
+                env = dict(os.environ, VTMGPU_SHIM_BACKEND="gpu", VTMGPU_CAPTURE_DIR=tmp, VTMGPU_CAPTURE_PRE_ONLY="1", VTMGPU_DEVICE=str(device))
+                if not env.get("VTMGPU_LIB"):
+                    env.pop("VTMGPU_LIB", None)
+                r = subprocess.run([DEC_GPU, "-b", stream, "-d", "0"], env=env, capture_output=True, text=True, timeout=900)
+                ok = r.stdout.count("(OK)")
+                files = sorted(glob.glob(os.path.join(tmp, "*.cap")))
+                if not (r.returncode == 0 and ok == len(files) and ok >= 1 and "ERROR" not in r.stdout):
+                    sys.stderr.write("bench.py: DecoderApp_gpu capture of %s failed (rc=%d, OK=%d): %s\n" % (os.path.basename(stream), r.returncode, ok, (r.stdout + r.stderr)[-400:]))
+                    caps = []
+                    break
+                oks += ok
+                total += len(files)
+                caps += [capture.load(f) for f in files[:distinct - len(caps)]]
+            finally:
+                shutil.rmtree(tmp, ignore_errors=True)
+        if caps:
+            return caps, ("captured: VTM-encoded (RA, QP32, CC-ALF) synthetic 4K YUV (%s) decoded by DecoderApp_gpu, %d/%d pictures MD5 (OK), "
+                          "%d distinct pictures replayed" % (" + ".join(os.path.basename(f) for f in streams), oks, total, len(caps)))
     caps = [synth.make_picture(W4K, H4K, seed=2160 + i, density=0.6) for i in range(distinct)]
     return caps, "synthetic planes + synthetic side info (vvc_b200/synth.py density 0.6), %d distinct pictures" % distinct
 
@@ -150,7 +164,9 @@ def cpu_reference_run(max_procs=None, repeats=1):
                 px += int(m.group(2))
             if secs:
                 v = px / max(secs) / 1e6
-                best = v if best is None else max(best, v)
+                if best is None or v > best:
+                    best = v
+                    cpu_reference_run.per_process = round(px / len(secs) / (sum(secs) / len(secs)) / 1e6, 2)     # what ONE decoder process gets (all cores busy)
         if best is not None:
             return best, cores, "reference", "%s decoded by %d pinned processes (one per core), filter stages only" % (os.path.basename(stream), cores)
     # fall back to the plain-C port of the oracle (single thread)
@@ -167,6 +183,31 @@ def cpu_reference_run(max_procs=None, repeats=1):
         return n * cap.luma_pixels() / (time.perf_counter() - t0) / 1e6, 1, "port", "%d synthetic 4K pictures through oracle/vvc_filters_oracle.c, 1 thread" % n
     except Exception:
         return None
+
+
+def decoder_e2e_run(device):
+    """The real drop-in: ONE DecoderApp_gpu process decodes the 8-picture 4K stream (pageable decoder buffers, synchronous
+    per-picture calls, host derivation of the deblocking records included); the shim's steady_clock timers bracket our three
+    entry points.  Returns a dict or None."""
+    if not (os.path.exists(STREAM_4K) and os.path.exists(DEC_GPU)):
+        return None
+    env = dict(os.environ, VTMGPU_SHIM_BACKEND="gpu", VTMGPU_SHIM_TIMING="1", VTMGPU_DEVICE=str(device))
+    if not env.get("VTMGPU_LIB"):
+        env.pop("VTMGPU_LIB", None)
+    best = None
+    for _ in range(2):
+        r = subprocess.run([DEC_GPU, "-b", STREAM_4K, "-d", "0"], env=env, capture_output=True, text=True, timeout=600)
+        m = re.search(r"vtmgpu-shim-timing: pictures=(\d+) luma_pixels=(\d+) filter_s=([0-9.eE+-]+) dbf_s=([0-9.eE+-]+) sao_s=([0-9.eE+-]+) alf_s=([0-9.eE+-]+) derive_s=([0-9.eE+-]+)", r.stdout)
+        if r.returncode != 0 or not m or "ERROR" in r.stdout or r.stdout.count("(OK)") != int(m.group(1)):
+            return None
+        pics, px, filt, der = int(m.group(1)), int(m.group(2)), float(m.group(3)), float(m.group(7))
+        tot = filt + der
+        if best is None or tot < best["seconds"]:
+            best = {"value": round(px / tot / 1e6, 1), "unit": "Mpixel/s", "pictures": pics, "seconds": round(tot, 5), "filter_calls_s": round(filt, 5),
+                    "host_derivation_s": round(der, 5), "ms_per_picture": round(tot * 1e3 / pics, 3),
+                    "what": "one DecoderApp_gpu process on ra_2160p_8.bin: time inside loopFilterPic + SAOProcess + ALFProcess incl. host derivation, "
+                            "pageable picture buffers, synchronous per-picture calls, all pictures MD5 (OK)"}
+    return best
 
 
 def run_reference_arm(args):
@@ -231,10 +272,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="pictures per step per GPU (BASELINE config 3: 64 frames)")
-    ap.add_argument("--distinct", type=int, default=8, help="distinct pictures replicated to fill the batch")
+    ap.add_argument("--distinct", type=int, default=40, help="distinct pictures (the two committed 4K streams hold 32 + 8) replicated to fill the batch")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stress", action="store_true", help="skip the forced-on synthetic leg (N=1 only)")
+    ap.add_argument("--no-decoder", action="store_true", help="skip the in-decoder leg (N=1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -319,20 +361,24 @@ def main():
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
-            per_px = json.load(open(tr)).get(roofline["kernel"], {}).get("dram_bytes_per_luma_pixel")
+            ent = json.load(open(tr)).get(roofline["kernel"], {})
+            per_px = ent.get("dram_bytes_per_luma_pixel")
             if per_px is not None:
                 roofline["traffic"] = round(per_px * px_per_pic * B)      # ncu dram__bytes_read+write per luma pixel x pixels of one launch
+                roofline["traffic_source"] = "extrapolated: ncu --set full of one %s-picture launch (%s), bytes per luma pixel x the pixels of this launch" % (
+                    ent.get("pictures_in_launch", "?"), ent.get("report", "profiles/"))
         except Exception:
             pass
 
     # ---- end to end through the C ABI with host buffers -------------------------------------------------------------
-    NCTX, CH = int(os.environ.get("VTMGPU_E2E_NCTX", "8")), int(os.environ.get("VTMGPU_E2E_CH", "1"))   # contexts (streams) x slots: copies of one chunk overlap kernels of another
-    ectx = [gpu.Context(seq, capacity=CH, device=local) for _ in range(NCTX)]
-    pin_in = [[torch.from_numpy(p.copy()).pin_memory() for p in c.pre] for c in caps]
-    pin_out = [[[torch.empty_like(t).pin_memory() for t in pin_in[0]] for _ in range(CH)] for _ in range(NCTX)]
+    # ONE C call per step (vtmgpu_batch_filter): the library walks the pictures round robin over LANES single-picture contexts
+    # (streams) -- pinned H2D of the planes, record lists, SAO / ALF parameters, the chain, pinned D2H -- issued by this thread
     import ctypes as C
     from vvc_b200 import abi
-    dense_records = os.environ.get("VTMGPU_E2E_DENSE_RECORDS", "0") == "1"
+    LANES = int(os.environ.get("VTMGPU_E2E_LANES", "8"))
+    batch = gpu.Batch(seq, lanes=LANES, device=local)
+    pin_in = [[torch.from_numpy(p.copy()).pin_memory() for p in c.pre] for c in caps]
+    pin_out = [[torch.empty_like(t).pin_memory() for t in pin_in[0]] for _ in range(LANES)]
     side = []
     for c in caps:
         ctus = c.sao_ctus()
@@ -340,71 +386,61 @@ def main():
             gpu.sao_reconstruct(ctus, c.width_in_ctus, c.ncomp, c.sao_scale[0], c.sao_scale[1])
         # the decoder-side producer of the segment records (the shim's CU walk) appends the active units to lists in
         # page-locked memory: no staging copy in the library, ~0.15 instead of 0.75 B of records per luma pixel on the bus
-        if dense_records:
-            dp, keep, nbytes = abi.DeblockParams(), [], 0
-            for d in range(2):
-                tl = torch.from_numpy(c.dbf_luma[d].view(np.int32).copy()).pin_memory()
-                keep.append(tl)
-                nbytes += c.dbf_luma[d].nbytes
-                dp.luma[d] = C.cast(tl.data_ptr(), C.POINTER(C.c_uint32))
-                if c.dbf_chroma[d].size:
-                    tc = torch.from_numpy(c.dbf_chroma[d].view(np.int64).copy()).pin_memory()
-                    keep.append(tc)
-                    nbytes += c.dbf_chroma[d].nbytes
-                    dp.chroma[d] = C.cast(tc.data_ptr(), C.POINTER(C.c_uint64))
-            dp._keep = keep
-        else:
-            dp = gpu.sparse_records(c.dbf_luma, c.dbf_chroma if c.ncomp > 1 else None, pin=True)
-            nbytes = sum(dp.luma_count[d] * C.sizeof(abi.DbfLumaEntry) + dp.chroma_count[d] * C.sizeof(abi.DbfChromaEntry) for d in range(2))
-        side.append((dp, ctus, c.alf_params(), nbytes))
+        dp = gpu.sparse_records(c.dbf_luma, c.dbf_chroma if c.ncomp > 1 else None, pin=True)
+        nbytes = sum(dp.luma_count[d] * C.sizeof(abi.DbfLumaEntry) + dp.chroma_count[d] * C.sizeof(abi.DbfChromaEntry) for d in range(2))
+        side.append((dp, ctus, c.alf_params(), nbytes, c.vb_struct()))
     plane_bytes = sum(t.numel() * 2 for t in pin_in[0])
     h2d = sum(plane_bytes + side[k % len(caps)][3] for k in range(B)) / B       # per picture, averaged over the batch
     d2h = plane_bytes
+    pics = [gpu.host_picture([t.numpy() for t in pin_in[k % len(caps)]], [t.numpy() for t in pin_out[k % LANES]], side[k % len(caps)][0],
+                             side[k % len(caps)][1], side[k % len(caps)][2], side[k % len(caps)][4]) for k in range(B)]
+    arr = (abi.HostPicture * B)(*pics)
 
-    issue = [0.0]
-    ncalls = [0]
-
-    def e2e_step():
-        t_issue = time.perf_counter()
-        for base in range(0, B, CH):
-            cx = ectx[(base // CH) % NCTX]
-            if base >= NCTX * CH:
-                cx.sync()                            # the chunk this context handled one round ago must have drained
-            for j in range(CH):
-                i = (base + j) % len(caps)
-                cx.upload(j, [t.numpy() for t in pin_in[i]], sync=False)
-                if os.environ.get("VTMGPU_E2E_SKIP_SIDE") == "1" and ncalls[0] > 0:
-                    continue                 # experiment switch (tools/abtest.sh): what the per-picture side information costs
-                if dense_records:
-                    cx.set_deblock(j, side[i][0], sync=False)
-                else:
-                    cx.set_deblock_sparse(j, side[i][0])
-                cx.set_sao(j, side[i][1])
-                cx.set_alf(j, side[i][2])
-            cx.filter(0, CH, sync=False)
-            for j in range(CH):
-                cx.download(j, [t.numpy() for t in pin_out[(base // CH) % NCTX][j]], sync=False)
-        issue[0] += time.perf_counter() - t_issue
-        ncalls[0] += 1
-        for cx in ectx:
-            cx.sync()
-
-    e2e_step()
-    issue[0] = 0.0
+    batch.filter(arr)                                 # warm-up (allocations of the record landing areas, first-touch)
+    e2e_launch0 = batch.launch_count()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
+        batch.filter(arr)                             # returns when every output has landed in host memory
     e2e_s = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
     barrier()
     e2e_val = world * B * px_per_pic / e2e_s / 1e6
-    launches_total = launches + sum(c.launch_count() for c in ectx)
-    # the e2e result must equal the device-resident result (spot check on one picture)
-    ref_out = ctx.download(0)
-    ok = all(np.array_equal(ref_out[k], pin_out[0][0][k].numpy()) for k in range(len(ref_out)))
-    for c in ectx:
-        c.close()
+    e2e_launches = batch.launch_count() - e2e_launch0
+    # the e2e result must equal the device-resident result: the last picture of lane 0 against the same picture's slot
+    last = max(k for k in range(B) if k % LANES == 0)
+    pic = last % len(caps)
+    ref_out = ctx.download(pic)                  # resident slot s holds picture s % len(caps), and pic < min(B, len(caps))
+    ok = all(np.array_equal(ref_out[k], pin_out[0][k].numpy()) for k in range(len(ref_out)))
+    batch.close()
+    if not ok:
+        raise SystemExit("bench.py: the end-to-end output of picture %d differs from the device-resident output -- no number is reported" % pic)
+
+    # what the host <-> device path of THIS box allows for these byte counts: the same bytes per picture as plain concurrent copies
+    # (one H2D stream, one D2H stream, page-locked, nothing else running) -- all ranks at once, like the e2e leg
+    dev_in = torch.empty(int(h2d) // 2, dtype=torch.int16, device="cuda")
+    dev_out = torch.empty(int(d2h) // 2, dtype=torch.int16, device="cuda")
+    host_in = torch.empty(int(h2d) // 2, dtype=torch.int16).pin_memory()
+    host_out = torch.empty(int(d2h) // 2, dtype=torch.int16).pin_memory()
+    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def copy_step():
+        for _ in range(B):
+            with torch.cuda.stream(s_up):
+                dev_in.copy_(host_in, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                host_out.copy_(dev_out, non_blocking=True)
+        s_up.synchronize()
+        s_dn.synchronize()
+
+    copy_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        copy_step()
+    copy_s = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
+    barrier()
+    ceiling = world * B * px_per_pic / copy_s / 1e6
+    del dev_in, dev_out, host_in, host_out
 
     line = {"metric": METRIC, "value": round(value, 1), "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -414,8 +450,13 @@ def main():
                        "activity": activity_summary(caps), "e2e_equals_resident": bool(ok)},
             "clocks": clocks, "roofline": roofline, "gpu_launches": int(launches),
             "e2e": {"value": round(e2e_val, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": int(h2d * B), "d2h_bytes_per_step": int(d2h * B),
-                    "steps": args.e2e_steps, "gpu_launches": int(launches_total - launches),
-                    "host_issue_ms_per_step": round(issue[0] * 1e3 / args.e2e_steps, 2), "numa_node_of_rank0": numa, "deblock_records": "dense arrays" if dense_records else "lists of active units", "ms_per_step": round(e2e_s * 1e3, 2)}}
+                    "steps": args.e2e_steps, "gpu_launches": int(e2e_launches // max(1, args.e2e_steps)),
+                    "api": "vtmgpu_batch_filter: one C call per step, %d lanes (streams), one issuing thread per GPU" % LANES,
+                    "numa_node_of_rank0": numa, "deblock_records": "lists of active units", "ms_per_step": round(e2e_s * 1e3, 2),
+                    "pcie_ceiling": {"value": round(ceiling, 1), "unit": "Mpixel/s", "ms_per_step": round(copy_s * 1e3, 2),
+                                     "h2d_gbs": round(h2d * B / copy_s / 1e9, 1), "d2h_gbs": round(d2h * B / copy_s / 1e9, 1),
+                                     "what": "the same bytes per picture as plain concurrent pinned copies (one H2D + one D2H stream per rank, all ranks at once), measured in this run"},
+                    "frac_of_pcie_ceiling": round(e2e_val / ceiling, 3)}}
     if world == 1 and not args.no_stress:
         # content-independent stress number: seeded pictures with every tool forced on in every CTU (SAO, luma / chroma
         # ALF with non-linear APS filters, CC-ALF) and dense small blocks for the deblocking, replayed device-resident
@@ -434,12 +475,22 @@ def main():
             ctx.filter(0, ns, sync=False)
         ms = ctx.timer_stop() / 5
         line["stress_forced_on"] = {"value": round(ns * W4K * H4K / (ms * 1e-3) / 1e6, 1), "unit": "Mpixel/s", "pictures_per_step": ns,
+                                    "chain_frac": round(B_ALG_CHAIN * ns * W4K * H4K / (ms * 1e-3) / 1e9 / peak, 4),
                                     "what": "seeded 4K pictures, every tool on in every CTU (vvc_b200/synth.py density 1.0, p_split 0.9), device-resident",
                                     "activity": activity_summary(scaps)}
+    if rank == 0 and world == 1 and not args.no_decoder:
+        # the drop-in as a decoder user meets it (host derivation, pageable buffers, synchronous calls); bench "e2e" above replays
+        # pre-derived side information from pinned memory through pipelined contexts -- both are reported, neither hides the other
+        dec = decoder_e2e_run(local)
+        if dec:
+            line["e2e_decoder"] = dec
+            line["e2e"]["host_derivation_excluded"] = True
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         res = cpu_reference_run()
         if res:
             line["cpu_baseline"] = {"value": round(res[0], 2), "unit": "Mpixel/s", "cores": res[1], "kind": res[2], "sample": res[3]}
+            if getattr(cpu_reference_run, "per_process", None):
+                line["cpu_baseline"]["per_process"] = cpu_reference_run.per_process
     if rank == 0:
         print(json.dumps(line))
     ctx.close()

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define VTMGPU_ABI_VERSION 2
+#define VTMGPU_ABI_VERSION 3
 
 /* chroma_format values follow ChromaFormat (TypeDef.h): 0 = 4:0:0, 1 = 4:2:0, 2 = 4:2:2, 3 = 4:4:4 */
 typedef struct vtmgpu_seq_params
@@ -302,7 +302,8 @@ int vtmgpu_filter (vtmgpu_ctx* ctx, int first, int count);
  * Every context is created for the FULL picture geometry, so all CTU / virtual-boundary / picture-border rules keep
  * their absolute positions; it uploads and filters only its band:
  *   vtmgpu_set_rows(ctx, y0, y1)          stage calls filter luma rows [y0, y1) only (multiples of 128; y1 may be the height)
- *   vtmgpu_upload_rows(.., y0-8, y1+8)    the band plus the 8 rows the deblocking of its border tiles reads
+ *   vtmgpu_upload_rows(.., y0-16, y1+16)  the band plus the 16 luma rows (8 chroma rows at 4:2:0) the deblocking of its border tiles
+ *                                         reads: 8 for the filters + 8 so that the chroma rows are whole (vvc_b200/bands.py UPLOAD_MARGIN)
  *   vtmgpu_deblock / vtmgpu_sao           exact for the band (they read pre-filter samples only)
  *   vtmgpu_export_rows / import_rows      4 rows of SAO output on each side of a band border travel to the neighbour
  *                                         (dense device buffers; the caller moves them with NCCL send/recv over NVLink)
@@ -325,13 +326,41 @@ int vtmgpu_import_rows(vtmgpu_ctx* ctx, int slot, int comp, int y0, int nrows, c
 int vtmgpu_export_halo(vtmgpu_ctx* ctx, int slot, const int y[3], int nrows, void* dev_dst);
 int vtmgpu_import_halo(vtmgpu_ctx* ctx, int slot, const int y[3], int nrows, const void* dev_src);
 
+/* ---------------------------------------------------------------------------------------------
+ * host batches: the whole boundary for a run of independent pictures that live in HOST memory, in ONE call.
+ * A batch object owns `lanes` single-picture contexts (each with its own CUDA stream); vtmgpu_batch_filter walks the pictures
+ * round robin over the lanes -- upload of the planes, record lists, SAO / ALF parameters, the chain, download -- so that the
+ * copies of one picture overlap the kernels of another, all issued by the calling thread (one issuing thread per GPU; a
+ * decoder that holds several reconstructed pictures of a GOP calls this once instead of ~10 entry points per picture).
+ * Page-locked buffers make every copy asynchronous; pageable buffers work but serialise.  Returns when every output has landed.
+ * in / out may alias (in-place, like DecLib::executeLoopFilters on the picture's reco buffer).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct vtmgpu_host_picture
+{
+  const int16_t* in[3];                  /* pre-filter planes (Picture::getRecoBuf), strides in samples */
+  ptrdiff_t      in_stride[3];
+  int16_t*       out[3];                 /* filtered planes */
+  ptrdiff_t      out_stride[3];
+  const vtmgpu_deblock_sparse* deblock;  /* NULL: deblocking off for this picture */
+  const vtmgpu_sao_params*     sao;      /* reconstructed (vtmgpu_sao_reconstruct); NULL: SAO off */
+  const vtmgpu_alf_params*     alf;      /* NULL: ALF off */
+} vtmgpu_host_picture;
+
+typedef struct vtmgpu_batch vtmgpu_batch;
+int  vtmgpu_batch_create(const vtmgpu_seq_params* seq, int lanes, vtmgpu_batch** batch);   /* seq->capacity is ignored (one slot per lane) */
+void vtmgpu_batch_destroy(vtmgpu_batch* batch);
+int  vtmgpu_batch_filter(vtmgpu_batch* batch, const vtmgpu_host_picture* pictures, int count);
+const char* vtmgpu_batch_last_error(const vtmgpu_batch* batch);
+int64_t vtmgpu_batch_launch_count(const vtmgpu_batch* batch);
+
 /* replay/benchmark support: enqueue the whole chain on the ctx stream without synchronising; timing by
  * CUDA events recorded on that same stream */
 int vtmgpu_filter_async(vtmgpu_ctx* ctx, int first, int count);
 int vtmgpu_sync(vtmgpu_ctx* ctx);
 int vtmgpu_timer_start(vtmgpu_ctx* ctx);                 /* records an event on the ctx stream          */
 int vtmgpu_timer_stop (vtmgpu_ctx* ctx, float* ms);      /* records + synchronises, elapsed ms          */
-/* restores slot's working planes from its pristine uploaded copy (device-to-device) so a replay can repeat */
+/* makes the pristine upload the current state of the slots again so that a replay can repeat the chain: the uploaded buffer is
+ * never written by a kernel (the stages ping-pong between the two working buffers), so this only resets the slots' state -- no copy */
 int vtmgpu_rewind(vtmgpu_ctx* ctx, int first, int count);
 /* number of kernel launches issued by this ctx so far (bench.py "gpu_launches") */
 int64_t vtmgpu_launch_count(const vtmgpu_ctx* ctx);

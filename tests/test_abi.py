@@ -33,7 +33,7 @@ def test_exports_every_declared_symbol(lib):
 
 
 def test_struct_sizes(lib):
-    mirrors = [abi.SeqParams, abi.DeblockParams, abi.SaoOffset, abi.SaoCtu, abi.SaoParams, abi.AlfLumaAps, abi.AlfChromaAps, abi.AlfParams, abi.DeblockSparse, abi.Ladf, abi.VirtualBoundaries]
+    mirrors = [abi.SeqParams, abi.DeblockParams, abi.SaoOffset, abi.SaoCtu, abi.SaoParams, abi.AlfLumaAps, abi.AlfChromaAps, abi.AlfParams, abi.DeblockSparse, abi.Ladf, abi.VirtualBoundaries, abi.HostPicture]
     for i, m in enumerate(mirrors):
         assert lib.vtmgpu_abi_sizeof(i) == C.sizeof(m), m.__name__
 
@@ -54,7 +54,7 @@ def test_no_cpu_fallback_without_device(lib):
         assert b"no CUDA device" in lib.vtmgpu_last_error(None) or b"CUDA" in lib.vtmgpu_last_error(None)
 
 
-@pytest.mark.parametrize("bad", [dict(width=100), dict(height=0), dict(chroma_format=4), dict(bit_depth_luma=7), dict(ctu_size=32), dict(capacity=0)])
+@pytest.mark.parametrize("bad", [dict(width=100), dict(height=0), dict(chroma_format=4), dict(bit_depth_luma=7), dict(ctu_size=16), dict(ctu_size=256), dict(capacity=0)])
 def test_create_rejects_bad_geometry(lib, bad):
     kw = dict(width=64, height=64, chroma_format=1, bit_depth_luma=10, bit_depth_chroma=10, ctu_size=128, capacity=1, device=0)
     kw.update(bad)

@@ -216,6 +216,33 @@ def test_sparse_records_equal_dense(w, h, cf, density):
     ctx.close()
 
 
+def test_host_batch_equals_oracle():
+    """vtmgpu_batch_filter: a run of host pictures through the whole boundary in one C call (round robin over the lanes, more
+    pictures than lanes, pictures with stages switched off, in-place output) -- every output equals the oracle's."""
+    caps = [synth.make_picture(448, 256, chroma_format=1, seed=40 + i, density=0.3 + 0.1 * i) for i in range(7)]
+    want = [pyoracle.filter_capture(c)["final"] for c in caps]
+    batch = gpu.Batch(caps[0].seq, lanes=3)
+    pics, outs = [], []
+    for i, c in enumerate(caps):
+        ctus = c.sao_ctus()
+        gpu.sao_reconstruct(ctus, c.width_in_ctus, c.ncomp, c.sao_scale[0], c.sao_scale[1])
+        inp = [np.ascontiguousarray(p) for p in c.pre]
+        out = inp if i == 2 else [np.zeros_like(p) for p in inp]                 # picture 2 is filtered in place
+        outs.append(out)
+        pics.append(gpu.host_picture(inp, out, gpu.sparse_records(c.dbf_luma, c.dbf_chroma), ctus, c.alf_params()))
+    batch.filter(pics)
+    for i in range(len(caps)):
+        _eq(outs[i], want[i], "host batch picture %d" % i)
+    # all stages off: the pictures come back unchanged
+    c = caps[0]
+    inp = [np.ascontiguousarray(p) for p in c.pre]
+    out = [np.zeros_like(p) for p in inp]
+    batch.filter([gpu.host_picture(inp, out)])
+    _eq(out, c.pre, "host batch, stages off")
+    assert batch.launch_count() > 0
+    batch.close()
+
+
 def test_bad_arguments_fail_loudly():
     cap = synth.make_picture(256, 128, seed=1)
     ctx = gpu.Context(cap.seq)
@@ -229,10 +256,29 @@ def test_bad_arguments_fail_loudly():
     sp.luma_count[0] = cap.dbf_luma[0].size + 1
     with pytest.raises(gpu.VtmGpuError):
         ctx.set_deblock_sparse(0, sp)
+    # band-mode row / halo copies: slot index and buffers are validated before anything is indexed or enqueued
+    import torch
+    buf = torch.zeros(4 * 3 * 256, dtype=torch.int16, device="cuda")
+    for bad_slot in (-1, 1, 1 << 20):
+        with pytest.raises(gpu.VtmGpuError):
+            ctx.export_halo(bad_slot, [0, 0, 0], 4, buf.data_ptr())
+        with pytest.raises(gpu.VtmGpuError):
+            ctx.import_halo(bad_slot, [0, 0, 0], 4, buf.data_ptr())
+        with pytest.raises(gpu.VtmGpuError):
+            ctx.export_rows(bad_slot, 0, 0, 4, buf.data_ptr())
+        with pytest.raises(gpu.VtmGpuError):
+            ctx.import_rows(bad_slot, 0, 0, 4, buf.data_ptr())
+    with pytest.raises(gpu.VtmGpuError):
+        ctx.export_halo(0, [0, 0, 0], 4, None)
+    with pytest.raises(gpu.VtmGpuError):
+        ctx.import_halo(0, [0, 0, 0], 4, None)
+    ctx.export_halo(0, [0, 0, 0], 4, buf.data_ptr())          # and the good call still works
+    ctx.sync()
     ctx.close()
 
 
 STREAMS = [("ra_416x240.bin", 8), ("ld444_1080p.bin", 16), ("ra_1080p.bin", 32), ("ai_4320p.bin", 1),
+           ("ra_2160p_8.bin", 8), ("ra_2160p_b.bin", 32),     # BASELINE config 3: 3840x2160 RA with CC-ALF (the benchmark content: frames 0..7 and 32..63)
            # tiles / raster-scan slices with in-loop filtering across their boundaries disabled
            ("tiles_832x480.bin", 5), ("slices_832x480.bin", 5), ("slices45_832x480.bin", 3),
            ("ladf_832x480.bin", 5),       # LADF: deblocking thresholds derived on the device
@@ -273,3 +319,28 @@ def test_decoder_drop_in_md5(stream, pictures):
                        capture_output=True, text=True, timeout=600, env=dict(os.environ, VTMGPU_SHIM_BACKEND="gpu"))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("(OK)") == pictures and "ERROR" not in r.stdout, r.stdout[-2000:]
+
+
+YUV_STREAMS = ["ra_416x240.bin", "ra_1080p.bin", "ld444_1080p.bin", "ra_2160p_8.bin"]      # BASELINE configs 1, 2, 5, 3
+
+
+@pytest.mark.parametrize("stream", YUV_STREAMS)
+def test_decoder_output_yuv_byte_identical(stream, tmp_path):
+    """north_star: "byte-identical output YUV".  The reconstructed YUV written by the decoder with OUR filters (DecoderApp_gpu -o)
+    equals, byte for byte, the file the UNMODIFIED reference decoder (oracle/_ref/DecoderApp -o, its own CPU filters) writes for the
+    same stream -- this also covers what the MD5 SEI does not (output order, bit depth conversion, cropping of the written file)."""
+    import filecmp
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dec, ref = os.path.join(root, "vvc_b200", "_bin", "DecoderApp_gpu"), os.path.join(root, "oracle", "_ref", "DecoderApp")
+    if not (os.path.exists(dec) and os.path.exists(ref)):
+        pytest.skip("DecoderApp_gpu / the reference DecoderApp are not built (they need the reference sources at build time)")
+    bits = os.path.join(root, "tests", "golden", "streams", stream)
+    ours, theirs = str(tmp_path / "gpu.yuv"), str(tmp_path / "ref.yuv")
+    r = subprocess.run([dec, "-b", bits, "-o", ours, "-d", "0"], capture_output=True, text=True, timeout=900, env=dict(os.environ, VTMGPU_SHIM_BACKEND="gpu"))
+    assert r.returncode == 0 and "ERROR" not in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    r = subprocess.run([ref, "-b", bits, "-o", theirs, "-d", "0"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "ERROR" not in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert os.path.getsize(ours) > 0 and os.path.getsize(ours) == os.path.getsize(theirs)
+    assert filecmp.cmp(ours, theirs, shallow=False), "%s: the GPU decoder's YUV differs from the reference decoder's" % stream

@@ -5,7 +5,7 @@ Keep in sync with the header; tests/test_abi.py checks sizes/offsets against the
 """
 import ctypes as C
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 ALF_CLASSES, ALF_LUMA_COEFF, ALF_CHROMA_COEFF = 25, 13, 7
 ALF_MAX_APS, ALF_MAX_ALTS, ALF_FIXED_SETS = 8, 8, 16
@@ -106,6 +106,12 @@ ALF_CLIP_TOP, ALF_CLIP_BOTTOM, ALF_CLIP_LEFT, ALF_CLIP_RIGHT, ALF_PAD_TL, ALF_PA
 PlanePtrs = C.POINTER(C.c_int16) * 3
 Strides = C.c_ssize_t * 3
 
+
+class HostPicture(C.Structure):
+    """vtmgpu_host_picture: one picture of a host batch (vtmgpu_batch_filter)."""
+    _fields_ = [("inp", PlanePtrs), ("in_stride", Strides), ("out", PlanePtrs), ("out_stride", Strides),
+                ("deblock", C.POINTER(DeblockSparse)), ("sao", C.POINTER(SaoParams)), ("alf", C.POINTER(AlfParams))]
+
 # every entry point include/vtmgpu.h declares (tests check that the built library exports all of them)
 ENTRY_POINTS = [
     "vtmgpu_abi_version", "vtmgpu_abi_sizeof", "vtmgpu_upload_async", "vtmgpu_download_async", "vtmgpu_last_error", "vtmgpu_create", "vtmgpu_destroy", "vtmgpu_upload", "vtmgpu_download",
@@ -113,6 +119,7 @@ ENTRY_POINTS = [
     "vtmgpu_alf", "vtmgpu_sao_alf", "vtmgpu_deblock_sao", "vtmgpu_filter", "vtmgpu_filter_async", "vtmgpu_sync", "vtmgpu_timer_start",
     "vtmgpu_timer_stop", "vtmgpu_rewind", "vtmgpu_launch_count", "vtmgpu_set_profiling", "vtmgpu_stage_ms",
     "vtmgpu_set_rows", "vtmgpu_set_stream", "vtmgpu_upload_rows", "vtmgpu_download_rows", "vtmgpu_export_rows", "vtmgpu_import_rows", "vtmgpu_export_halo", "vtmgpu_import_halo",
+    "vtmgpu_batch_create", "vtmgpu_batch_destroy", "vtmgpu_batch_filter", "vtmgpu_batch_last_error", "vtmgpu_batch_launch_count",
 ]
 
 

@@ -51,10 +51,10 @@ constexpr int SA_THREADS = (SA_T / 4) * (SA_TH / 4);   // 256: one thread per 4x
 #endif
 constexpr int SA_HX = 8, SA_HY = 4;         // halo loaded around a tile (x: one aligned group of 8)
 constexpr int SA_W = SA_T + 2 * SA_HX;      // 80
-constexpr int SA_H = SA_TH + 2 * SA_HY;     // 40
+constexpr int SA_H = SA_TH + 2 * SA_HY;     // 72
 constexpr int SA_P = SA_W + 8;              // smem pitch in samples (88 -> 176 B: rows shift by 12 banks)
 constexpr int SA_CELLS = SA_T / 2 + 2;      // 34 Laplacian cells (2x2 samples) per row: tile + 2 samples each side
-constexpr int SA_CELLR = SA_TH / 2 + 2;     // 18 cell rows
+constexpr int SA_CELLR = SA_TH / 2 + 2;     // 34 cell rows
 constexpr int SA_CELLP = SA_CELLS + 2;      // cell row pitch (uint2 units)
 
 __constant__ int8_t c_perm7[4][12] = { { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11 }, { 9, 4, 10, 8, 1, 5, 11, 7, 3, 0, 2, 6 },

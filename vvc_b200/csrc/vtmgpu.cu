@@ -1,13 +1,14 @@
 // vtmgpu.cu -- libvtmgpu: host side of the C ABI (include/vtmgpu.h) + kernel launches.  sm_100a only, no CPU path.
 //
-// HBM layout per picture slot (sized for 180 GB: a 3840x2160 4:2:0 slot is 3 x 24.9 MB planes + 6.3 MB side info):
-//   buf[0]  pristine upload (kept so a replay can rewind without another H2D)
-//   buf[1]  deblocked picture            (k_deblock: buf[0] -> buf[1])
-//   buf[2]  final picture                (k_sao_alf: buf[1] -> buf[2])
-//   side    one contiguous block: luma/chroma segment records of both directions, SaoDev[ctus][3], ALF per-CTU
-//           control bytes, filter indices, AlfDev (coefficient tables) -- mirrored in pinned host memory so the
-//           set_* calls are a pack + one async H2D each.
-// All work of a ctx is enqueued on its own stream; stage calls synchronise unless named *_async.
+// HBM layout per picture slot (sized for 180 GB: a 3840x2160 4:2:0 slot is 3 x 24.9 MB planes + 6.7 MB side info; all slots
+// of a context share one plane allocation and one side-info allocation at constant strides):
+//   buf[0]  pristine upload (never written by a kernel, so a replay can rewind without another H2D)
+//   buf[1], buf[2]  working buffers: every stage kernel reads the slot's current buffer and writes the other working one
+//           (k_dbf_sao: deblocking + SAO, k_alf / k_alf_parts: ALF + CC-ALF; vtmgpu_filter = buf[0] -> buf[1] -> buf[2])
+//   side    one contiguous block: luma / chroma segment records of both directions (ABI indexing, TMA row pitch), the
+//           expanded luma filter tables (16 fixed sets + APS sets), CtuCtlDev[ctus], AlfDev, SaoDev[ctus][3] -- mirrored in
+//           pinned host memory: vtmgpu_set_* pack into the mirror, the next stage call uploads the changed range.
+// All work of a ctx is enqueued on its stream; stage calls synchronise unless named *_async.
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -118,6 +119,18 @@ struct vtmgpu_ctx
   // time whatever its size, which is what bounds the end-to-end rate once the planes themselves move at PCIe speed).
   std::vector<size_t> dirtyLo, dirtyHi;     // per slot: byte range of the side block to upload (lo >= hi: clean)
   std::vector<char> slotDirty;
+  // the uploads read the pinned mirror asynchronously: an event per slot marks the last upload that read it, and every vtmgpu_set_*
+  // waits for it before it packs into the mirror again (a caller that pipelines pictures through one ctx with the *_async calls)
+  std::vector<cudaEvent_t> mirrorEv;
+  std::vector<char> mirrorBusy;
+  void mirrorRead(int slot)
+  {
+    if (cudaEventRecord(mirrorEv[slot], stream) == cudaSuccess) mirrorBusy[slot] = 1;
+  }
+  void mirrorWrite(int slot)
+  {
+    if (mirrorBusy[slot]) { cudaEventSynchronize(mirrorEv[slot]); mirrorBusy[slot] = 0; }
+  }
   int pushSlot(int slot) { slotDirty[slot] = 1; return 0; }
   void markSide(int slot, size_t off, size_t bytes)
   {
@@ -131,6 +144,7 @@ struct vtmgpu_ctx
       {
         if (pushSide(s, dirtyLo[s], dirtyHi[s] - dirtyLo[s])) return -1;
         dirtyLo[s] = dirtyHi[s] = 0;
+        mirrorRead(s);
       }
     for (int s = first; s < first + count; s++)
     {
@@ -138,6 +152,7 @@ struct vtmgpu_ctx
       int e = s;
       while (e < first + count && slotDirty[e]) slotDirty[e++] = 0;
       if (cuda(cudaMemcpyAsync(slotsDev + s, slotsPinned + s, sizeof(SlotDev) * (e - s), cudaMemcpyHostToDevice, stream), "slot table upload")) return -1;
+      for (int k = s; k < e; k++) mirrorRead(k);
       s = e - 1;
     }
     return 0;
@@ -169,6 +184,7 @@ extern "C" int vtmgpu_abi_sizeof(int which)
   case 8: return (int)sizeof(vtmgpu_deblock_sparse);
   case 9: return (int)sizeof(vtmgpu_ladf);
   case 10: return (int)sizeof(vtmgpu_virtual_boundaries);
+  case 11: return (int)sizeof(vtmgpu_host_picture);
   default: return -1;
   }
 }
@@ -189,6 +205,7 @@ extern "C" void vtmgpu_destroy(vtmgpu_ctx* c)
   if (c->tmapsRecDev) cudaFree(c->tmapsRecDev);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   for (auto& e : c->stageEv) if (e) cudaEventDestroy(e);
+  for (auto& e : c->mirrorEv) if (e) cudaEventDestroy(e);
   if (c->ownStream) cudaStreamDestroy(c->ownStream);
   delete c;
 }
@@ -256,6 +273,9 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
   c->dirtyLo.assign(s.capacity, 0);
   c->dirtyHi.assign(s.capacity, 0);
   c->slotDirty.assign(s.capacity, 1);
+  c->mirrorEv.assign(s.capacity, nullptr);
+  c->mirrorBusy.assign(s.capacity, 0);
+  for (auto& ev : c->mirrorEv) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event");
 
   // plane geometry: pitch multiple of 64 samples (128 B)
   int pw[3], ph[3], pitch[3];
@@ -513,6 +533,7 @@ extern "C" int vtmgpu_download_rows(vtmgpu_ctx* c, int slot, int16_t* const plan
 extern "C" int vtmgpu_export_rows(vtmgpu_ctx* c, int slot, int comp, int y0, int nrows, void* dev_dst)
 {
   if (!c) return -1;
+  if (!c->slotOk(slot, 1)) return c->fail("export_rows: bad slot %d", slot);
   if (comp < 0 || comp >= c->g.ncomp) return c->fail("export_rows: bad component %d", comp);
   if (copyRows(c, slot, comp, c->cur[slot], y0, nrows, dev_dst, c->slotsPinned[slot].buf[0][comp].w, cudaMemcpyDeviceToDevice, false, "export_rows")) return -1;
   return c->asyncStages ? 0 : c->cuda(cudaStreamSynchronize(c->stream), "export_rows");
@@ -521,6 +542,7 @@ extern "C" int vtmgpu_export_rows(vtmgpu_ctx* c, int slot, int comp, int y0, int
 extern "C" int vtmgpu_import_rows(vtmgpu_ctx* c, int slot, int comp, int y0, int nrows, const void* dev_src)
 {
   if (!c) return -1;
+  if (!c->slotOk(slot, 1)) return c->fail("import_rows: bad slot %d", slot);
   if (comp < 0 || comp >= c->g.ncomp) return c->fail("import_rows: bad component %d", comp);
   if (copyRows(c, slot, comp, c->cur[slot], y0, nrows, const_cast<void*>(dev_src), c->slotsPinned[slot].buf[0][comp].w, cudaMemcpyDeviceToDevice, true, "import_rows")) return -1;
   return c->asyncStages ? 0 : c->cuda(cudaStreamSynchronize(c->stream), "import_rows");
@@ -531,6 +553,8 @@ extern "C" int vtmgpu_import_rows(vtmgpu_ctx* c, int slot, int comp, int y0, int
 extern "C" int vtmgpu_export_halo(vtmgpu_ctx* c, int slot, const int y[3], int nrows, void* dev_dst)
 {
   if (!c) return -1;
+  if (!c->slotOk(slot, 1)) return c->fail("export_halo: bad slot %d", slot);
+  if (!y || (!dev_dst && nrows)) return c->fail("export_halo: NULL argument");
   int16_t* d = static_cast<int16_t*>(dev_dst);
   for (int k = 0; k < c->g.ncomp; k++)
   {
@@ -544,6 +568,8 @@ extern "C" int vtmgpu_export_halo(vtmgpu_ctx* c, int slot, const int y[3], int n
 extern "C" int vtmgpu_import_halo(vtmgpu_ctx* c, int slot, const int y[3], int nrows, const void* dev_src)
 {
   if (!c) return -1;
+  if (!c->slotOk(slot, 1)) return c->fail("import_halo: bad slot %d", slot);
+  if (!y || (!dev_src && nrows)) return c->fail("import_halo: NULL argument");
   int16_t* d = static_cast<int16_t*>(const_cast<void*>(dev_src));
   for (int k = 0; k < c->g.ncomp; k++)
   {
@@ -601,8 +627,10 @@ int setDeblock(vtmgpu_ctx* c, int slot, const vtmgpu_deblock_params* p, bool dir
   if (!c) return -1;
   if (!c->slotOk(slot, 1)) return c->fail("set_deblock: bad slot %d", slot);
   cudaSetDevice(c->seq.device);
+  c->mirrorWrite(slot);
   SlotDev& sd = c->slotsPinned[slot];
   sd.dbfOn = p != nullptr;
+  c->pushSlot(slot);
   if (setLadf(c, slot, p ? p->ladf : nullptr)) return -1;
   if (p)
   {
@@ -680,6 +708,7 @@ extern "C" int vtmgpu_set_deblock_sparse(vtmgpu_ctx* c, int slot, const vtmgpu_d
   if (!c->slotOk(slot, 1)) return c->fail("set_deblock_sparse: bad slot %d", slot);
   if (!p) return setDeblock(c, slot, nullptr, true);
   cudaSetDevice(c->seq.device);
+  c->mirrorWrite(slot);
   const SideLayout& L = c->lay;
   size_t offs[5] = { 0, 0, 0, 0, 0 };    // landing area: worst case = every unit listed
   for (int a = 0; a < 4; a++) offs[a + 1] = alignUp(offs[a] + (size_t)L.recW[a] * L.recH[a] * (a < 2 ? sizeof(vtmgpu_dbf_luma_entry) : sizeof(vtmgpu_dbf_chroma_entry)), 256);
@@ -705,17 +734,20 @@ extern "C" int vtmgpu_set_deblock_sparse(vtmgpu_ctx* c, int slot, const vtmgpu_d
     A.count[a] = n; A.first[a + 1] = A.first[a] + n;
     A.recW[a] = L.recW[a] ? L.recW[a] : 1; A.recH[a] = L.recH[a]; A.recP[a] = L.recP[a];
   }
-  int firstList = -1;
+  int firstList = -1, lastList = -1, nLists = 0;
   bool packed = true;
   for (int a = 0; a < 4; a++)
   {
     if (!A.count[a]) continue;
     if (firstList < 0) firstList = a;
+    lastList = a; nLists++;
     packed = packed && (const unsigned char*)src[a] == (const unsigned char*)src[firstList] + (poff[a] - poff[firstList]);
   }
-  if (firstList >= 0 && packed)
+  if (nLists >= 2 && packed)
   {
-    if (c->cuda(cudaMemcpyAsync(c->sparseDev[slot] + poff[firstList], src[firstList], poff[4] - poff[firstList], cudaMemcpyHostToDevice, c->stream), "set_deblock_sparse")) return -1;
+    // one copy from the start of the first list to the END OF THE LAST ENTRY (the caller owes no padding after the last list)
+    const size_t bytes = poff[lastList] + (size_t)A.count[lastList] * esz[lastList] - poff[firstList];
+    if (c->cuda(cudaMemcpyAsync(c->sparseDev[slot] + poff[firstList], src[firstList], bytes, cudaMemcpyHostToDevice, c->stream), "set_deblock_sparse")) return -1;
   }
   else
     for (int a = 0; a < 4; a++)
@@ -814,8 +846,10 @@ extern "C" int vtmgpu_set_sao(vtmgpu_ctx* c, int slot, const vtmgpu_sao_params* 
   if (!c) return -1;
   if (!c->slotOk(slot, 1)) return c->fail("set_sao: bad slot %d", slot);
   cudaSetDevice(c->seq.device);
+  c->mirrorWrite(slot);
   SlotDev& sd = c->slotsPinned[slot];
   sd.saoOn = 0;
+  c->pushSlot(slot);                     // also on the error returns below: the device must not keep a stale "on" with half-updated parameters
   if (setVb(c, sd.vbSao, p ? p->vb : nullptr, "set_sao")) return -1;
   if (p)
   {
@@ -858,8 +892,10 @@ extern "C" int vtmgpu_set_alf(vtmgpu_ctx* c, int slot, const vtmgpu_alf_params* 
   if (!c) return -1;
   if (!c->slotOk(slot, 1)) return c->fail("set_alf: bad slot %d", slot);
   cudaSetDevice(c->seq.device);
+  c->mirrorWrite(slot);
   SlotDev& sd = c->slotsPinned[slot];
   sd.alfOn = 0;
+  c->pushSlot(slot);                     // also on the error returns below
   if (setVb(c, sd.vbAlf, p ? p->vb : nullptr, "set_alf")) return -1;
   if (p)
   {
@@ -1102,6 +1138,69 @@ extern "C" int vtmgpu_deblock_sao(vtmgpu_ctx* c, int first, int count) { return 
 extern "C" int vtmgpu_sao_alf(vtmgpu_ctx* c, int first, int count) { return runStages(c, first, count, ST_SAO | ST_ALF, true, "sao_alf"); }
 extern "C" int vtmgpu_filter(vtmgpu_ctx* c, int first, int count) { return runStages(c, first, count, ST_DBF | ST_SAO | ST_ALF, true, "filter"); }
 extern "C" int vtmgpu_filter_async(vtmgpu_ctx* c, int first, int count) { return runStages(c, first, count, ST_DBF | ST_SAO | ST_ALF, false, "filter_async"); }
+
+// ------------------------------------------------------------------------------------------------------------
+// host batches
+// ------------------------------------------------------------------------------------------------------------
+struct vtmgpu_batch
+{
+  std::vector<vtmgpu_ctx*> lane;
+  std::string err;
+};
+
+extern "C" const char* vtmgpu_batch_last_error(const vtmgpu_batch* b) { return b ? b->err.c_str() : g_createError.c_str(); }
+
+extern "C" void vtmgpu_batch_destroy(vtmgpu_batch* b)
+{
+  if (!b) return;
+  for (vtmgpu_ctx* c : b->lane) vtmgpu_destroy(c);
+  delete b;
+}
+
+extern "C" int vtmgpu_batch_create(const vtmgpu_seq_params* seq, int lanes, vtmgpu_batch** out)
+{
+  if (!seq || !out || lanes < 1 || lanes > 64) { g_createError = "vtmgpu_batch_create: bad argument (1..64 lanes)"; return -1; }
+  *out = nullptr;
+  vtmgpu_batch* b = new vtmgpu_batch();
+  vtmgpu_seq_params s = *seq;
+  s.capacity = 1;
+  for (int k = 0; k < lanes; k++)
+  {
+    vtmgpu_ctx* c = nullptr;
+    if (vtmgpu_create(&s, &c)) { vtmgpu_batch_destroy(b); return -1; }      // g_createError holds the reason
+    b->lane.push_back(c);
+  }
+  *out = b;
+  return 0;
+}
+
+extern "C" int64_t vtmgpu_batch_launch_count(const vtmgpu_batch* b)
+{
+  int64_t n = 0;
+  if (b) for (const vtmgpu_ctx* c : b->lane) n += c->launches;
+  return b ? n : -1;
+}
+
+extern "C" int vtmgpu_batch_filter(vtmgpu_batch* b, const vtmgpu_host_picture* pics, int count)
+{
+  if (!b) return -1;
+  if (count < 0 || (count && !pics)) { b->err = "batch_filter: bad argument"; return -1; }
+  auto lastError = [&](vtmgpu_ctx* c, int i) { b->err = "batch_filter: picture " + std::to_string(i) + ": " + c->err; return -1; };
+  int rc = 0;
+  for (int i = 0; i < count && !rc; i++)
+  {
+    vtmgpu_ctx* c = b->lane[i % b->lane.size()];
+    const vtmgpu_host_picture& p = pics[i];
+    // everything below only enqueues on the lane's stream; the lane's previous picture is ordered before it by the stream, and the
+    // vtmgpu_set_* calls wait (mirror events) until the side-information upload of that picture has left the pinned mirror
+    if (vtmgpu_upload_async(c, 0, p.in, p.in_stride) || vtmgpu_set_deblock_sparse(c, 0, p.deblock) || vtmgpu_set_sao(c, 0, p.sao) ||
+        vtmgpu_set_alf(c, 0, p.alf) || vtmgpu_filter_async(c, 0, 1) || vtmgpu_download_async(c, 0, p.out, p.out_stride))
+      rc = lastError(c, i);
+  }
+  for (vtmgpu_ctx* c : b->lane)
+    if (vtmgpu_sync(c) && !rc) rc = lastError(c, -1);
+  return rc;
+}
 
 extern "C" int vtmgpu_timer_start(vtmgpu_ctx* c)
 {

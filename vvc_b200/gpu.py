@@ -73,6 +73,11 @@ def load_library(path=None):
         "vtmgpu_import_rows": (C.c_int, [ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
         "vtmgpu_export_halo": (C.c_int, [ctx, C.c_int, C.POINTER(C.c_int * 3), C.c_int, C.c_void_p]),
         "vtmgpu_import_halo": (C.c_int, [ctx, C.c_int, C.POINTER(C.c_int * 3), C.c_int, C.c_void_p]),
+        "vtmgpu_batch_create": (C.c_int, [C.POINTER(abi.SeqParams), C.c_int, C.POINTER(ctx)]),
+        "vtmgpu_batch_destroy": (None, [ctx]),
+        "vtmgpu_batch_filter": (C.c_int, [ctx, C.POINTER(abi.HostPicture), C.c_int]),
+        "vtmgpu_batch_last_error": (C.c_char_p, [ctx]),
+        "vtmgpu_batch_launch_count": (C.c_int64, [ctx]),
     }
     for name, (res, args) in proto.items():
         try:
@@ -156,6 +161,62 @@ def _plane_args(planes):
         ptrs[c] = C.cast(p.ctypes.data, C.POINTER(C.c_int16))
         strides[c] = p.strides[0] // 2
     return ptrs, strides
+
+
+def host_picture(planes_in, planes_out, deblock=None, sao_ctus=None, alf=None, vb=None):
+    """abi.HostPicture for vtmgpu_batch_filter from numpy planes (C-contiguous int16; page-locked memory makes the copies
+    asynchronous), an abi.DeblockSparse, a reconstructed (abi.SaoCtu * n) array and an abi.AlfParams.  The returned object keeps
+    everything it points to alive."""
+    hp = abi.HostPicture()
+    keep = [planes_in, planes_out, deblock, sao_ctus, alf, vb]
+    for k, (a, b) in enumerate(zip(planes_in, planes_out)):
+        assert a.dtype == np.int16 and b.dtype == np.int16 and a.flags["C_CONTIGUOUS"] and b.flags["C_CONTIGUOUS"]
+        hp.inp[k] = a.ctypes.data_as(C.POINTER(C.c_int16))
+        hp.out[k] = b.ctypes.data_as(C.POINTER(C.c_int16))
+        hp.in_stride[k] = a.strides[0] // 2
+        hp.out_stride[k] = b.strides[0] // 2
+    if deblock is not None:
+        hp.deblock = C.pointer(deblock)
+    if sao_ctus is not None:
+        sp = abi.SaoParams(C.cast(sao_ctus, C.POINTER(abi.SaoCtu)), len(sao_ctus), C.pointer(vb) if vb is not None else None)
+        keep.append(sp)
+        hp.sao = C.pointer(sp)
+    if alf is not None:
+        hp.alf = C.pointer(alf)
+    hp._keep = keep
+    return hp
+
+
+class Batch:
+    """vtmgpu_batch: `lanes` single-picture contexts; filter() takes a run of host pictures through the whole boundary in ONE
+    C call (copies of one picture overlap the kernels of another; one issuing thread)."""
+
+    def __init__(self, seq, lanes=4, device=0):
+        self.lib = load_library()
+        sp = abi.SeqParams(seq["width"], seq["height"], seq["chroma_format"], seq["bit_depth_luma"], seq["bit_depth_chroma"], seq["ctu_size"], 1, device)
+        self.h = C.c_void_p()
+        if self.lib.vtmgpu_batch_create(C.byref(sp), lanes, C.byref(self.h)):
+            raise VtmGpuError(self.lib.vtmgpu_last_error(None).decode())
+
+    def filter(self, pictures):
+        """pictures: list of abi.HostPicture (see host_picture) or a ready (abi.HostPicture * n) array."""
+        arr = pictures if isinstance(pictures, C.Array) else (abi.HostPicture * len(pictures))(*pictures)
+        if self.lib.vtmgpu_batch_filter(self.h, arr, len(arr)):
+            raise VtmGpuError(self.lib.vtmgpu_batch_last_error(self.h).decode())
+
+    def launch_count(self):
+        return int(self.lib.vtmgpu_batch_launch_count(self.h))
+
+    def close(self):
+        if self.h:
+            self.lib.vtmgpu_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Context:

@@ -34,7 +34,12 @@
 #include "SampleAdaptiveOffset.h"
 
 #include "capture_format.h"
-#include "shim_backend.h"
+#ifdef VTMGPU_SHIM_TEST_BACKEND
+#include "shim_backend.h"               // test binaries only (oracle/_ref/DecoderApp_cap): the reference's own classes as a second backend
+#define SHIM_ALT(CALL) vtmgpu_shim_alt_backend()->CALL
+#else
+#define SHIM_ALT(CALL) ((void)0)        // product object: the hook is compiled out, `useRef` is a constant false
+#endif
 #include "vtm_flatten.h"
 #include "vtmgpu.h"
 
@@ -83,7 +88,13 @@ struct Shim
   GpuApi api;
   vtmgpu_ctx* ctx = nullptr;
   vtmgpu_seq_params seq{};
-  bool useRef = false, staged = false, saoPending = false, dbfPending = false, denseRecords = false;
+#ifdef VTMGPU_SHIM_TEST_BACKEND
+  bool useRef = false;
+#else
+  static constexpr bool useRef = false;
+#endif
+  bool staged = false, saoPending = false, dbfPending = false, denseRecords = false;
+  bool capturePreOnly = false;   // VTMGPU_CAPTURE_PRE_ONLY=1: captures hold the pre-filter planes and the side information only (a quarter of the size)
   std::string captureDir;
   int picCount = 0;
   // per-picture
@@ -96,9 +107,14 @@ struct Shim
   Shim()
   {
     const char* b = getenv("VTMGPU_SHIM_BACKEND");
+#ifdef VTMGPU_SHIM_TEST_BACKEND
     useRef = b && std::string(b) == "ref";
     if (useRef && (!vtmgpu_shim_alt_backend || !vtmgpu_shim_alt_backend())) THROW("vtmgpu shim: no alternative backend linked into this binary");
+#else
+    if (b && std::string(b) == "ref") THROW("vtmgpu shim: this binary has no alternative backend (VTMGPU_SHIM_BACKEND=ref is a test-binary switch)");
+#endif
     if (const char* d = getenv("VTMGPU_CAPTURE_DIR")) captureDir = d;
+    capturePreOnly = getenv("VTMGPU_CAPTURE_PRE_ONLY") && atoi(getenv("VTMGPU_CAPTURE_PRE_ONLY"));
     staged = !captureDir.empty() || (getenv("VTMGPU_STAGED") && atoi(getenv("VTMGPU_STAGED")));
     denseRecords = getenv("VTMGPU_DENSE_RECORDS") && atoi(getenv("VTMGPU_DENSE_RECORDS"));
     timing = getenv("VTMGPU_SHIM_TIMING") && atoi(getenv("VTMGPU_SHIM_TIMING"));
@@ -161,7 +177,7 @@ struct Shim
 
   void capturePlanes(CodingStructure& cs, const char* stage)
   {
-    if (captureDir.empty()) return;
+    if (captureDir.empty() || (capturePreOnly && std::string(stage) != "pre")) return;
     int16_t* p[3]; ptrdiff_t st[3]; int w[3], h[3];
     planes(cs, p, st, w, h);
     for (int c = 0; c < 3; c++)
@@ -232,7 +248,7 @@ LoopFilter::~LoopFilter() {}
 void LoopFilter::create(const unsigned uiMaxCUDepth)
 {
   m_enc = false;
-  if (shim().useRef) vtmgpu_shim_alt_backend()->lfCreate(uiMaxCUDepth);
+  if (shim().useRef) SHIM_ALT(lfCreate(uiMaxCUDepth));
 }
 void LoopFilter::destroy() {}
 
@@ -271,7 +287,7 @@ void LoopFilter::loopFilterPic(CodingStructure& cs)
   s.tic();
   if (s.useRef)
   {
-    vtmgpu_shim_alt_backend()->lfRun(cs);
+    SHIM_ALT(lfRun(cs));
   }
   else
   {
@@ -314,7 +330,7 @@ void SampleAdaptiveOffset::create(int picWidth, int picHeight, ChromaFormat form
   m_numberOfComponents = getNumberValidComponents(format);
   shim().saoLog2Scale[0] = lumaBitShift;
   shim().saoLog2Scale[1] = chromaBitShift;
-  if (shim().useRef) vtmgpu_shim_alt_backend()->saoCreate(picWidth, picHeight, (int)format, maxCUWidth, maxCUHeight, maxCUDepth, lumaBitShift, chromaBitShift);
+  if (shim().useRef) SHIM_ALT(saoCreate(picWidth, picHeight, (int)format, maxCUWidth, maxCUHeight, maxCUDepth, lumaBitShift, chromaBitShift));
 }
 void SampleAdaptiveOffset::destroy() {}
 
@@ -331,7 +347,7 @@ void SampleAdaptiveOffset::SAOProcess(CodingStructure& cs, SAOBlkParam* saoBlkPa
   s.tic();
   if (s.useRef)
   {
-    vtmgpu_shim_alt_backend()->saoRun(cs, saoBlkParams);
+    SHIM_ALT(saoRun(cs, saoBlkParams));
   }
   else
   {
@@ -380,7 +396,7 @@ void AdaptiveLoopFilter::create(const int picWidth, const int picHeight, const C
   m_picWidth = picWidth; m_picHeight = picHeight; m_maxCUWidth = maxCUWidth; m_maxCUHeight = maxCUHeight; m_maxCUDepth = maxCUDepth;
   m_chromaFormat = format;
   m_numCTUsInPic = ctus;
-  if (shim().useRef) vtmgpu_shim_alt_backend()->alfCreate(picWidth, picHeight, (int)format, maxCUWidth, maxCUHeight, maxCUDepth, inputBitDepth);
+  if (shim().useRef) SHIM_ALT(alfCreate(picWidth, picHeight, (int)format, maxCUWidth, maxCUHeight, maxCUDepth, inputBitDepth));
   if (m_created) return;
   m_ccAlfFilterControl[0] = new uint8_t[ctus]();     // CABACReader writes the per-CTU CC-ALF idc here (DecLib.cpp:1154-1155)
   m_ccAlfFilterControl[1] = new uint8_t[ctus]();
@@ -417,7 +433,7 @@ void AdaptiveLoopFilter::ALFProcess(CodingStructure& cs)
   s.tic();
   if (s.useRef)
   {
-    vtmgpu_shim_alt_backend()->alfRun(cs, m_ccAlfFilterParam, m_ccAlfFilterControl, p->num_ctus);
+    SHIM_ALT(alfRun(cs, m_ccAlfFilterParam, m_ccAlfFilterControl, p->num_ctus));
   }
   else
   {

@@ -745,6 +745,16 @@ void flattenAlf(CodingStructure& cs, const CcAlfFilterParam& cc, uint8_t* const 
     bool same = s->getTileGroupNumAps() == first->getTileGroupNumAps() && s->getTileGroupApsIdLuma() == first->getTileGroupApsIdLuma() &&
                 s->getTileGroupApsIdChroma() == first->getTileGroupApsIdChroma();
     for (int c = 0; c < 3; c++) same = same && s->getTileGroupAlfEnabledFlag(ComponentID(c)) == first->getTileGroupAlfEnabledFlag(ComponentID(c));
+    // CC-ALF is tested per CTU against the CTU's own slice (AdaptiveLoopFilter.cpp:451,532): its enable flags, APS ids and the
+    // coefficients the slice header resolved must agree too, or the picture would be filtered with another slice's CC-ALF data
+    for (int c = 0; c < 2; c++)
+    {
+      same = same && s->m_ccAlfFilterParam.ccAlfFilterEnabled[c] == first->m_ccAlfFilterParam.ccAlfFilterEnabled[c];
+      if (s->m_ccAlfFilterParam.ccAlfFilterEnabled[c])
+        same = same && memcmp(s->m_ccAlfFilterParam.ccAlfCoeff[c], first->m_ccAlfFilterParam.ccAlfCoeff[c], sizeof(first->m_ccAlfFilterParam.ccAlfCoeff[c])) == 0 &&
+               memcmp(s->m_ccAlfFilterParam.ccAlfFilterIdxEnabled[c], first->m_ccAlfFilterParam.ccAlfFilterIdxEnabled[c], sizeof(first->m_ccAlfFilterParam.ccAlfFilterIdxEnabled[c])) == 0;
+    }
+    same = same && s->getTileGroupCcAlfCbApsId() == first->getTileGroupCcAlfCbApsId() && s->getTileGroupCcAlfCrApsId() == first->getTileGroupCcAlfCrApsId();
     CHECK(!same, "vtmgpu shim: slices with different ALF parameters in one picture are not supported");
   }
   cs.slice = cs.getCU(Position(((n - 1) % pcv.widthInCtus) * pcv.maxCUWidth, ((n - 1) / pcv.widthInCtus) * pcv.maxCUHeight), CH_L)->slice;
