@@ -210,6 +210,79 @@ def decoder_e2e_run(device):
     return best
 
 
+def band_leg(local, rank, world, dist, iters=200, warm=10):
+    """BASELINE config 4 (world > 1): ONE VTM-encoded 7680x4320 intra picture filtered by all ranks in CTU-row bands over PEER
+    MEMORY -- k_dbf_sao stores the halo rows into the neighbours' planes and releases flags, k_alf acquires them; no copies, no
+    NCCL, no host synchronisation inside an iteration (vvc_b200/bands.py, vtmgpu_band_*).  Device-resident replay, CUDA events on
+    the context's stream, max over ranks; every rank checks its band bit for bit against the whole picture filtered on its own GPU."""
+    import glob as _glob
+    import shutil
+    import tempfile
+    import numpy as np
+    import torch
+    from vvc_b200 import abi, bands, capture, gpu
+    stream = os.path.join(ROOT, "tests", "golden", "streams", "ai_4320p.bin")
+    if not (os.path.exists(stream) and os.path.exists(DEC_GPU)):
+        return None
+    tmp = tempfile.mkdtemp(prefix="vtmgpu_cap8k_")
+    try:
+        env = dict(os.environ, VTMGPU_SHIM_BACKEND="gpu", VTMGPU_CAPTURE_DIR=tmp, VTMGPU_CAPTURE_PRE_ONLY="1", VTMGPU_DEVICE=str(local))
+        if not env.get("VTMGPU_LIB"):
+            env.pop("VTMGPU_LIB", None)
+        r = subprocess.run([DEC_GPU, "-b", stream, "-d", "0"], env=env, capture_output=True, text=True, timeout=900)
+        files = sorted(_glob.glob(os.path.join(tmp, "*.cap")))
+        if r.returncode != 0 or "(OK)" not in r.stdout or "ERROR" in r.stdout or not files:
+            return None
+        cap = capture.load(files[0])
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    dev = torch.device("cuda", local)
+    # the whole picture on this GPU: the reference for the bit check, and the single-GPU time
+    one = gpu.Context(cap.seq, capacity=1, device=local)
+    one.set_capture(0, cap)
+    one.filter(0, 1)
+    want = one.download(0)
+    for _ in range(5):
+        one.rewind(0, 1)
+        one.filter(0, 1, sync=False)
+    one.timer_start()
+    for _ in range(50):
+        one.rewind(0, 1)
+        one.filter(0, 1, sync=False)
+    ms_one = one.timer_stop() / 50
+    one.close()
+    ctx = gpu.Context(cap.seq, capacity=1, device=local)
+    y0, y1 = bands.load_band(cap, ctx, rank, world)
+    bands.connect_peers(ctx, rank, world, dist, dev)
+    for _ in range(warm):
+        ctx.rewind(0, 1)
+        ctx.band_filter(0)
+    ctx.sync()
+    dist.barrier()
+    ctx.timer_start()
+    for _ in range(iters):
+        ctx.rewind(0, 1)
+        ctx.band_filter(0)
+    ms = ctx.timer_stop() / iters
+    t = torch.tensor([ms, ms_one], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out = [np.zeros_like(p) for p in cap.pre]
+    ctx.download_rows(0, out, y0, y1)
+    sy = abi.chroma_shifts(cap.seq["chroma_format"])[1]
+    ok = all(np.array_equal(out[c][y0 >> (sy if c else 0):y1 >> (sy if c else 0)], want[c][y0 >> (sy if c else 0):y1 >> (sy if c else 0)]) for c in range(cap.ncomp))
+    oks = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(oks, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    ctx.band_disconnect()
+    ctx.close()
+    ms, ms_one = float(t[0].item()), float(t[1].item())
+    px = cap.width * cap.height
+    return {"metric": "DBF+SAO+ALF Mpixel/s, one 7680x4320 intra picture in CTU-row bands", "value": round(px / (ms * 1e-3) / 1e6, 1), "unit": "Mpixel/s",
+            "n_gpus": world, "iterations": iters, "ms_per_picture": round(ms, 4), "single_gpu_ms_per_picture": round(ms_one, 4), "speedup_vs_single_gpu": round(ms_one / ms, 2),
+            "scaling": "strong", "bands": bands.band_rows(cap.height, world), "bit_exact_vs_single_gpu": bool(oks.item()),
+            "halo": "4 rows per plane and border stored into the neighbour's plane by k_dbf_sao (NVLink peer stores) + release / acquire flags; no copies, no NCCL, no host sync per iteration"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -277,6 +350,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stress", action="store_true", help="skip the forced-on synthetic leg (N=1 only)")
     ap.add_argument("--no-decoder", action="store_true", help="skip the in-decoder leg (N=1 only)")
+    ap.add_argument("--no-bands", action="store_true", help="skip the 8K band leg (N>1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -478,6 +552,13 @@ def main():
                                     "chain_frac": round(B_ALG_CHAIN * ns * W4K * H4K / (ms * 1e-3) / 1e9 / peak, 4),
                                     "what": "seeded 4K pictures, every tool on in every CTU (vvc_b200/synth.py density 1.0, p_split 0.9), device-resident",
                                     "activity": activity_summary(scaps)}
+    if world > 1 and not args.no_bands:
+        try:
+            res = band_leg(local, rank, world, dist)
+        except Exception as e:                       # the picture-parallel line must survive a box without peer access
+            res = {"error": repr(e)[:300]}
+        if res is not None:
+            line["band_8k"] = res
     if rank == 0 and world == 1 and not args.no_decoder:
         # the drop-in as a decoder user meets it (host derivation, pageable buffers, synchronous calls); bench "e2e" above replays
         # pre-derived side information from pinned memory through pipelined contexts -- both are reported, neither hides the other

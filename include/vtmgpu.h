@@ -327,6 +327,24 @@ int vtmgpu_export_halo(vtmgpu_ctx* ctx, int slot, const int y[3], int nrows, voi
 int vtmgpu_import_halo(vtmgpu_ctx* ctx, int slot, const int y[3], int nrows, const void* dev_src);
 
 /* ---------------------------------------------------------------------------------------------
+ * band mode over PEER MEMORY (NVLink / NVSwitch): no copies, no NCCL, no host synchronisation inside an iteration.
+ * Every rank (one process per GPU) exports a handle of its plane memory and flag block, the handles travel by any host channel
+ * (vvc_b200/bands.py: torch.distributed all_gather), and every rank connects to the ranks that own the bands above and below.
+ * vtmgpu_band_filter_async then enqueues the whole chain for the rank's band: the deblocking + SAO kernel stores the four rows on
+ * each side of a band border ALSO into the neighbour's plane and releases a flag there, the ALF kernel acquires the flags before
+ * it loads the tiles of the band's first / last tile row.  All ranks must issue the same sequence of
+ * vtmgpu_band_filter_async calls (the flags count iterations).  Contexts of all ranks need the same geometry and capacity;
+ * pictures that need the virtual-boundary / CTU-32 kernel are not supported in this mode (use the export / import calls above).
+ * --------------------------------------------------------------------------------------------- */
+#define VTMGPU_BAND_HANDLE_BYTES 160
+typedef struct vtmgpu_band_handle { unsigned char bytes[VTMGPU_BAND_HANDLE_BYTES]; } vtmgpu_band_handle;
+int vtmgpu_band_export(vtmgpu_ctx* ctx, vtmgpu_band_handle* handle);
+/* above / below: handles of the ranks that own the neighbouring bands (NULL: picture border); call after vtmgpu_set_rows */
+int vtmgpu_band_connect(vtmgpu_ctx* ctx, const vtmgpu_band_handle* above, const vtmgpu_band_handle* below);
+int vtmgpu_band_filter_async(vtmgpu_ctx* ctx, int slot);
+int vtmgpu_band_disconnect(vtmgpu_ctx* ctx);      /* every rank: after its last iteration has completed on ALL ranks (a host barrier) */
+
+/* ---------------------------------------------------------------------------------------------
  * host batches: the whole boundary for a run of independent pictures that live in HOST memory, in ONE call.
  * A batch object owns `lanes` single-picture contexts (each with its own CUDA stream); vtmgpu_batch_filter walks the pictures
  * round robin over the lanes -- upload of the planes, record lists, SAO / ALF parameters, the chain, download -- so that the

@@ -134,6 +134,54 @@ def _gpu_rank(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _gpu_rank_peer(rank, world, port, q):
+    """Peer band mode: several iterations back to back (the flag protocol must order iteration i+1's stores after the
+    neighbour's reads of iteration i), a picture with every stage on and one with SAO / ALF off (the kernels must still signal)."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from vvc_b200 import gpu
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        ok = True
+        for seed, density, iters in ((5, 0.8, 7), (9, 0.0, 3), (11, 1.0, 2)):
+            cap = synth.make_picture(1920, 1080, seed=seed, density=density)
+            want = pyoracle.filter_capture(cap)["final"]
+            ctx = gpu.Context(cap.seq, capacity=1, device=rank)
+            out, (y0, y1) = bands.filter_picture_in_bands_peer(cap, ctx, rank, world, dist, iterations=iters)
+            ctx.close()
+            ok = ok and all(np.array_equal(out[c][y0 >> (0 if c == 0 else 1):y1 >> (0 if c == 0 else 1)],
+                                           want[c][y0 >> (0 if c == 0 else 1):y1 >> (0 if c == 0 else 1)]) for c in range(3))
+        q.put((rank, bool(ok)))
+    except Exception as e:                                         # report instead of letting the parent time out
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_bands_peer_memory(world):
+    """The band pipeline over peer memory (halo rows stored into the neighbours' planes by k_dbf_sao, flags acquired by k_alf):
+    bit-exact against the oracle on `world` GPUs, one process per GPU."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gpu_rank_peer, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert res == [(r, True) for r in range(world)], res
+
+
 @pytest.mark.gpu
 def test_bands_two_gpus_nccl():
     import torch

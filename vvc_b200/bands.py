@@ -118,6 +118,54 @@ def exchange(plan, export_fn, import_fn, dist, width_of, make_buffer, host_sync=
         import_fn(comp, row, n, buf)
 
 
+def connect_peers(ctx, rank, world, dist, device):
+    """Peer band mode: every rank exports the handle of its plane memory / flag block, the handles travel by all_gather, and every
+    rank maps the memory of the ranks above and below (CUDA IPC -> NVLink peer access).  Call after ctx.set_rows()."""
+    import torch
+    mine = torch.tensor(list(ctx.band_export()), dtype=torch.uint8, device=device)
+    every = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(every, mine)
+    hs = [bytes(t.cpu().numpy().tobytes()) for t in every]
+    ctx.band_connect(hs[rank - 1] if rank > 0 else None, hs[rank + 1] if rank + 1 < world else None)
+    dist.barrier()
+
+
+def load_band(cap, ctx, rank, world):
+    """Uploads this rank's band of the captured picture (plus the rows the deblocking of its border tiles reads) and all side
+    information into slot 0 of a context created for the full geometry.  Returns (y0, y1)."""
+    from . import gpu
+    h = cap.height
+    y0, y1 = band_rows(h, world)[rank]
+    ctx.set_rows(y0, y1)
+    ctx.upload_rows(0, cap.pre, max(0, y0 - UPLOAD_MARGIN), min(h, y1 + UPLOAD_MARGIN))
+    ctx.set_deblock(0, cap.deblock_params())
+    ctus = cap.sao_ctus()
+    if ctus is not None:
+        gpu.sao_reconstruct(ctus, cap.width_in_ctus, cap.ncomp, cap.sao_scale[0], cap.sao_scale[1])
+    ctx.set_sao(0, ctus, cap.vb_struct())
+    ctx.set_alf(0, cap.alf_params())
+    return y0, y1
+
+
+def filter_picture_in_bands_peer(cap, ctx, rank, world, dist, out=None, iterations=1):
+    """The band pipeline over peer memory: one call per iteration (vtmgpu_band_filter_async), the halo rows are stored into the
+    neighbours' planes by the deblocking + SAO kernel itself and the ALF kernel waits for the neighbours' flags -- no copies, no
+    NCCL, no host synchronisation inside an iteration.  Returns (planes, (y0, y1)) like filter_picture_in_bands."""
+    import torch
+    y0, y1 = load_band(cap, ctx, rank, world)
+    connect_peers(ctx, rank, world, dist, torch.device("cuda", ctx.device))
+    for _ in range(iterations):
+        ctx.rewind(0, 1)
+        ctx.band_filter(0)
+    ctx.sync()
+    if out is None:
+        out = [np.zeros_like(p) for p in cap.pre]
+    ctx.download_rows(0, out, y0, y1)
+    dist.barrier()                       # nobody unmaps while a neighbour may still store into its planes
+    ctx.band_disconnect()
+    return out, (y0, y1)
+
+
 def filter_picture_in_bands(cap, ctx, rank, world, dist, out=None):
     """DBF -> SAO -> [halo exchange] -> ALF of this rank's band of the captured picture `cap` on context `ctx` (slot 0,
     created for the full geometry).  Returns (planes, (y0, y1)): full-size host planes whose rows [y0, y1) hold the result."""

@@ -903,6 +903,16 @@ __device__ __forceinline__ void alfPrefetch(unsigned char* smraw, const SaLayout
   if (small) bulkLoad(st + L.offSmall, side + A.offAlf, ALF_SMALL_BYTES, bar);
 }
 
+// peer band mode: a tile of the band's first (last) tile row reads the four rows above (below) the band, which the neighbour's
+// k_dbf_sao stores into this rank's plane -- the walking thread waits for the neighbour's flag before it issues the tile's loads
+__device__ __forceinline__ void alfBandWait(const BandDev& band, int ty, int tilesY)
+{
+  if (!band.myFlags) return;
+  if (ty == 0 && band.peerPlanes[0]) while (ldAcquireSys(&band.myFlags[0]) < band.iter) { }
+  if (ty == tilesY - 1 && band.peerPlanes[1]) while (ldAcquireSys(&band.myFlags[1]) < band.iter) { }
+  asm volatile("fence.proxy.async.global;" ::: "memory");        // the rows were written through the generic proxy, the tile loads read through the async proxy
+}
+
 // what every thread needs to know about a tile: written to shared memory by the one thread that walks the tile sequence
 struct alignas(16) AlfTileDesc
 {
@@ -912,7 +922,7 @@ struct alignas(16) AlfTileDesc
 
 template <bool k420>
 __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAddr A, const CUtensorMap* __restrict__ tmaps, int firstSlot, int numSlots,
-                                                                    int srcBuf, int dstBuf, Geom g, int tilesX, int tilesY, int ty0, SaStep step)
+                                                                    int srcBuf, int dstBuf, Geom g, int tilesX, int tilesY, int ty0, SaStep step, const BandDev band)
 {
   extern __shared__ __align__(128) unsigned char smraw[];
   const int sx = k420 ? 1 : g.sx, sy = k420 ? 1 : g.sy, ncomp = k420 ? 3 : g.ncomp;
@@ -975,6 +985,7 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
       const uint4 ctlA = alfLoadCtl(A, g, firstSlot, cur, ty0);
       if (nxt.slot < numSlots) ctlB = alfLoadCtl(A, g, firstSlot, nxt, ty0);
       desc[0].x0 = cur.tx * SA_T; desc[0].y0 = (cur.ty + ty0) * SA_TH; desc[0].slotAbs = firstSlot + cur.slot; desc[0].valid = 1; desc[0].ctl = ctlA;
+      alfBandWait(band, cur.ty, tilesY);
       alfPrefetch(smraw, L, 0, A, tmaps + ((size_t)(firstSlot + cur.slot) * 3 + srcBuf) * 3, firstSlot + cur.slot, cur, g, ncomp, sx, sy, ty0, ctlA);
     }
   }
@@ -992,6 +1003,7 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
       d.x0 = nxt.tx * SA_T; d.y0 = (nxt.ty + ty0) * SA_TH; d.slotAbs = firstSlot + nxt.slot; d.valid = more; d.ctl = ctlB;
       if (more)
       {
+        alfBandWait(band, nxt.ty, tilesY);
         alfPrefetch(smraw, L, stage ^ 1, A, tmaps + ((size_t)(firstSlot + nxt.slot) * 3 + srcBuf) * 3, firstSlot + nxt.slot, nxt, g, ncomp, sx, sy, ty0, ctlB);
         saAdvance(nxt, step, tilesX, tilesY);
         ctlB = nxt.slot < numSlots ? alfLoadCtl(A, g, firstSlot, nxt, ty0) : make_uint4(0, 0, 0, 0);
@@ -1195,6 +1207,18 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
       }
     }
     __syncthreads();                                         // all reads of the stage buffers, the copy and the cells are done before they are refilled
+  }
+  if (band.myFlags && tid == 0)
+  {
+    // peer band mode: the last CTA to finish tells both neighbours that this rank has read its halo rows of this iteration
+    __threadfence_system();
+    if (atomicAdd(&band.myFlags[5], 1u) == gridDim.x - 1)
+    {
+      band.myFlags[5] = 0;
+      __threadfence_system();
+      if (band.peerFlags[0]) stReleaseSys(&band.peerFlags[0][3], band.iter);        // above: "the neighbour below has finished its ALF"
+      if (band.peerFlags[1]) stReleaseSys(&band.peerFlags[1][2], band.iter);        // below: "the neighbour above has finished its ALF"
+    }
   }
 }
 

@@ -420,7 +420,8 @@ __device__ __forceinline__ void dbfPrefetch(unsigned char* stageMem, uint64_t* b
 
 // maps = TMA descriptors of the plane buffers: [slot][3 buffers][3 planes], box = DBF_PITCH x DBF_SH samples
 __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __restrict__ slots, const CUtensorMap* __restrict__ tmaps, const CUtensorMap* __restrict__ recMaps,
-                                                             int firstSlot, int numSlots, int srcBuf, int dstBuf, Geom g, DbfLaunch L, TileStep step, int doDbf, int doSao)
+                                                             int firstSlot, int numSlots, int srcBuf, int dstBuf, Geom g, DbfLaunch L, TileStep step, int doDbf, int doSao,
+                                                             const BandDev band)
 {
   extern __shared__ __align__(128) unsigned char smraw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + 2 * DBF_STAGE_BYTES);
@@ -570,10 +571,48 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
       }
       else saoStrip(o, dst.pitch, a, DBF_PITCH, nrows, sx_, sy_, pq, w, h, cwLog | chLog << 8 | (comp ? g.bdC : g.bdL) << 16,
                     (S.vbSao.nv | S.vbSao.nh) ? &S.vbSao : nullptr, comp ? (g.sx | g.sy << 8) : 0);
+      if (band.myFlags)
+      {
+        // peer band mode: the first / last four rows of the band also go into the neighbour's plane (same layout, peer-mapped)
+        const int sh = comp ? g.sy : 0, bb = band.rowBegin >> sh, be = min(band.rowEnd >> sh, h);
+#pragma unroll 1
+        for (int side = 0; side < 2; side++)
+        {
+          if (!band.peerPlanes[side] || sy_ != (side ? be - 4 : bb)) continue;
+          // the neighbour's ALF of the previous iteration must have finished reading the rows this store overwrites
+          while (ldAcquireSys(&band.myFlags[2 + side]) + 1 < band.iter) { }
+          pel* po = band.peerPlanes[side] + (o - band.myPlanes);
+          if ((pq.x & 0xff) == 0)
+          {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+              if (k < nrows) *reinterpret_cast<uint4*>(po + (size_t)k * dst.pitch) = *reinterpret_cast<const uint4*>(a + k * DBF_PITCH);
+          }
+          else saoStrip(po, dst.pitch, a, DBF_PITCH, nrows, sx_, sy_, pq, w, h, cwLog | chLog << 8 | (comp ? g.bdC : g.bdL) << 16,
+                        (S.vbSao.nv | S.vbSao.nh) ? &S.vbSao : nullptr, comp ? (g.sx | g.sy << 8) : 0);
+          __threadfence_system();
+        }
+      }
     }
     if (tid == 0) qcount[0] = qcount[1] = 0;
     __syncthreads();                                         // the stage is free for the load after next
     slot = nslot; item = nitem; T = Tn;
+  }
+  if (band.myFlags)
+  {
+    // the last CTA to get here tells both neighbours that their halo rows of this iteration have landed
+    __syncthreads();
+    if (tid == 0)
+    {
+      __threadfence_system();
+      if (atomicAdd(&band.myFlags[4], 1u) == gridDim.x - 1)
+      {
+        band.myFlags[4] = 0;
+        __threadfence_system();
+        if (band.peerFlags[0]) stReleaseSys(&band.peerFlags[0][1], band.iter);      // above: "rows from below have landed"
+        if (band.peerFlags[1]) stReleaseSys(&band.peerFlags[1][0], band.iter);      // below: "rows from above have landed"
+      }
+    }
   }
 }
 

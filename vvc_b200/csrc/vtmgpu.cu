@@ -84,7 +84,13 @@ struct vtmgpu_ctx
   std::vector<unsigned char*> sideDev; // per slot                                 plane and table addresses instead of loading them
   pel* planeAll = nullptr;
   unsigned char* sideAll = nullptr;
+  size_t planeAllBytes = 0;
   AlfAddr alfAddr{};
+  // peer band mode (vtmgpu_band_*): flag block of this rank, the neighbours' mapped memory, iteration counter
+  uint32_t* bandFlags = nullptr;
+  void* bandPeerMem[2][2] = { { nullptr, nullptr }, { nullptr, nullptr } };     // [above / below][planes, flags] as opened (for cudaIpcCloseMemHandle)
+  BandDev band{};
+  bool bandOn = false, bandCall = false;   // connected ; inside vtmgpu_band_filter_async (only those launches carry the flags)
   std::vector<unsigned char*> sparseDev; // per slot, allocated by the first vtmgpu_set_deblock_sparse: landing area of the record lists
   unsigned char* sidePinned = nullptr; // capacity * lay.total
   SlotDev* slotsPinned = nullptr;      // capacity entries (pinned mirror)
@@ -189,11 +195,15 @@ extern "C" int vtmgpu_abi_sizeof(int which)
   }
 }
 
+extern "C" int vtmgpu_band_disconnect(vtmgpu_ctx* c);
+
 extern "C" void vtmgpu_destroy(vtmgpu_ctx* c)
 {
   if (!c) return;
   cudaSetDevice(c->seq.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  vtmgpu_band_disconnect(c);
+  if (c->bandFlags) cudaFree(c->bandFlags);
   if (c->planeAll) cudaFree(c->planeAll);
   if (c->sideAll) cudaFree(c->sideAll);
   for (unsigned char* p : c->sparseDev) if (p) cudaFree(p);
@@ -288,6 +298,7 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
     planeElems[k] = alignUp((size_t)pitch[k] * ph[k], 128);
     slotElems += planeElems[k];
   }
+  c->planeAllBytes = slotElems * 3 * sizeof(pel) * s.capacity;
   CK(cudaMalloc((void**)&c->planeAll, slotElems * 3 * sizeof(pel) * s.capacity), "plane memory");
   CK(cudaMemsetAsync(c->planeAll, 0, slotElems * 3 * sizeof(pel) * s.capacity, c->stream), "memset");
   CK(cudaMalloc((void**)&c->sideAll, L.total * s.capacity), "side info memory");
@@ -1060,7 +1071,7 @@ int launchDbfSao(vtmgpu_ctx* c, int first, int count, int doDbf, int doSao)
 {
   bool any = false;
   for (int s = first; s < first + count; s++) any |= (doDbf && c->slotsPinned[s].dbfOn) || (doSao && c->slotsPinned[s].saoOn);
-  if (!any) return 0;
+  if (!any && !c->bandCall) return 0;
   const Geom& g = c->g;
   DbfLaunch L;
   // rows [rowBegin, rowEnd) of the picture; vtmgpu_set_rows keeps both on multiples of 128 luma rows (or the picture end), so whole tile rows
@@ -1077,7 +1088,7 @@ int launchDbfSao(vtmgpu_ctx* c, int first, int count, int doDbf, int doSao)
     TileStep st;
     st.dSlot = grid / items;
     st.dItem = grid % items;
-    k_dbf_sao<<<grid, DBF_THREADS, DBF_SMEM_BYTES, c->stream>>>(c->slotsDev, c->tmapsDbfDev, c->tmapsRecDev, s, n, src, dst, g, L, st, doDbf, doSao);
+    k_dbf_sao<<<grid, DBF_THREADS, DBF_SMEM_BYTES, c->stream>>>(c->slotsDev, c->tmapsDbfDev, c->tmapsRecDev, s, n, src, dst, g, L, st, doDbf, doSao, c->bandCall ? c->band : BandDev{});
     c->launches++;
     for (int i = s; i < s + n; i++) c->cur[i] = dst;
     return c->cuda(cudaGetLastError(), "k_dbf_sao launch");
@@ -1089,7 +1100,7 @@ int launchAlf(vtmgpu_ctx* c, int first, int count)
 {
   bool any = false;
   for (int s = first; s < first + count; s++) any |= c->slotsPinned[s].alfOn != 0;
-  if (!any) return 0;
+  if (!any && !c->bandCall) return 0;
   const Geom& g = c->g;
   const int tilesX = (g.w + SA_T - 1) / SA_T, ty0 = c->rowBegin / SA_TH, tilesY = (c->rowEnd + SA_TH - 1) / SA_TH - ty0;
   const SaLayout SL = saLayout(g.sx, g.sy, g.ncomp);
@@ -1104,9 +1115,10 @@ int launchAlf(vtmgpu_ctx* c, int first, int count)
     st.dx = grid % tilesX;
     st.dy = (grid / tilesX) % tilesY;
     st.ds = (grid / tilesX) / tilesY;
+    if (vb && c->bandCall) return c->fail("band_filter: pictures with virtual boundaries / CTU size 32 are not supported in peer band mode");
     if (vb) k_alf_parts<<<grid, SA_THREADS, smem, c->stream>>>(c->slotsDev, c->tmapsDev, s, n, src, dst, g, tilesX, tilesY, ty0, st);
-    else if (g.ncomp == 3 && g.sx == 1 && g.sy == 1) k_alf<true><<<grid, SA_THREADS, smem, c->stream>>>(c->alfAddr, c->tmapsDev, s, n, src, dst, g, tilesX, tilesY, ty0, st);
-    else                                             k_alf<false><<<grid, SA_THREADS, smem, c->stream>>>(c->alfAddr, c->tmapsDev, s, n, src, dst, g, tilesX, tilesY, ty0, st);
+    else if (g.ncomp == 3 && g.sx == 1 && g.sy == 1) k_alf<true><<<grid, SA_THREADS, smem, c->stream>>>(c->alfAddr, c->tmapsDev, s, n, src, dst, g, tilesX, tilesY, ty0, st, c->bandCall ? c->band : BandDev{});
+    else                                             k_alf<false><<<grid, SA_THREADS, smem, c->stream>>>(c->alfAddr, c->tmapsDev, s, n, src, dst, g, tilesX, tilesY, ty0, st, c->bandCall ? c->band : BandDev{});
     c->launches++;
     for (int i = s; i < s + n; i++) c->cur[i] = dst;
     return c->cuda(cudaGetLastError(), "k_alf launch");
@@ -1138,6 +1150,93 @@ extern "C" int vtmgpu_deblock_sao(vtmgpu_ctx* c, int first, int count) { return 
 extern "C" int vtmgpu_sao_alf(vtmgpu_ctx* c, int first, int count) { return runStages(c, first, count, ST_SAO | ST_ALF, true, "sao_alf"); }
 extern "C" int vtmgpu_filter(vtmgpu_ctx* c, int first, int count) { return runStages(c, first, count, ST_DBF | ST_SAO | ST_ALF, true, "filter"); }
 extern "C" int vtmgpu_filter_async(vtmgpu_ctx* c, int first, int count) { return runStages(c, first, count, ST_DBF | ST_SAO | ST_ALF, false, "filter_async"); }
+
+// ------------------------------------------------------------------------------------------------------------
+// band mode over peer memory
+// ------------------------------------------------------------------------------------------------------------
+namespace
+{
+struct BandHandle      // the bytes of vtmgpu_band_handle
+{
+  cudaIpcMemHandle_t planes, flags;
+  int32_t width, height, chroma_format, capacity, device;
+  uint64_t planeBytes;
+};
+static_assert(sizeof(BandHandle) <= VTMGPU_BAND_HANDLE_BYTES, "vtmgpu_band_handle too small");
+}   // namespace
+
+extern "C" int vtmgpu_band_export(vtmgpu_ctx* c, vtmgpu_band_handle* out)
+{
+  if (!c) return -1;
+  if (!out) return c->fail("band_export: NULL handle");
+  cudaSetDevice(c->seq.device);
+  if (!c->bandFlags)
+  {
+    if (c->cuda(cudaMalloc((void**)&c->bandFlags, 64), "band flags")) return -1;
+    if (c->cuda(cudaMemset(c->bandFlags, 0, 64), "band flags")) return -1;
+  }
+  BandHandle h{};
+  if (c->cuda(cudaIpcGetMemHandle(&h.planes, c->planeAll), "cudaIpcGetMemHandle (planes)")) return -1;
+  if (c->cuda(cudaIpcGetMemHandle(&h.flags, c->bandFlags), "cudaIpcGetMemHandle (flags)")) return -1;
+  h.width = c->seq.width; h.height = c->seq.height; h.chroma_format = c->seq.chroma_format; h.capacity = c->seq.capacity; h.device = c->seq.device;
+  h.planeBytes = c->planeAllBytes;
+  memset(out, 0, sizeof(*out));
+  memcpy(out->bytes, &h, sizeof(h));
+  return 0;
+}
+
+extern "C" int vtmgpu_band_disconnect(vtmgpu_ctx* c)
+{
+  if (!c) return -1;
+  if (!c->bandOn && !c->bandPeerMem[0][0] && !c->bandPeerMem[1][0]) return 0;
+  cudaSetDevice(c->seq.device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& side : c->bandPeerMem)
+    for (void*& p : side)
+      if (p) { cudaIpcCloseMemHandle(p); p = nullptr; }
+  c->bandOn = false;
+  c->band = BandDev{};
+  return 0;
+}
+
+extern "C" int vtmgpu_band_connect(vtmgpu_ctx* c, const vtmgpu_band_handle* above, const vtmgpu_band_handle* below)
+{
+  if (!c) return -1;
+  if (!c->bandFlags) return c->fail("band_connect: call vtmgpu_band_export first (it creates this rank's flag block)");
+  if (vtmgpu_band_disconnect(c)) return -1;
+  cudaSetDevice(c->seq.device);
+  if (c->cuda(cudaMemset(c->bandFlags, 0, 64), "band flags")) return -1;
+  BandDev b{};
+  b.myPlanes = c->planeAll; b.myFlags = c->bandFlags; b.iter = 0; b.rowBegin = c->rowBegin; b.rowEnd = c->rowEnd;
+  const vtmgpu_band_handle* hs[2] = { above, below };
+  for (int side = 0; side < 2; side++)
+  {
+    if (!hs[side]) continue;
+    BandHandle h;
+    memcpy(&h, hs[side]->bytes, sizeof(h));
+    if (h.width != c->seq.width || h.height != c->seq.height || h.chroma_format != c->seq.chroma_format || h.capacity != c->seq.capacity || h.planeBytes != c->planeAllBytes)
+      return c->fail("band_connect: the neighbour's context has another geometry or capacity");
+    if (c->cuda(cudaIpcOpenMemHandle(&c->bandPeerMem[side][0], h.planes, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle (planes)")) return -1;
+    if (c->cuda(cudaIpcOpenMemHandle(&c->bandPeerMem[side][1], h.flags, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle (flags)")) return -1;
+    b.peerPlanes[side] = static_cast<pel*>(c->bandPeerMem[side][0]);
+    b.peerFlags[side] = static_cast<uint32_t*>(c->bandPeerMem[side][1]);
+  }
+  c->band = b;
+  c->bandOn = true;
+  return c->cuda(cudaDeviceSynchronize(), "band_connect");
+}
+
+extern "C" int vtmgpu_band_filter_async(vtmgpu_ctx* c, int slot)
+{
+  if (!c) return -1;
+  if (!c->bandOn) return c->fail("band_filter: not connected (vtmgpu_band_connect)");
+  c->band.iter++;
+  c->band.rowBegin = c->rowBegin; c->band.rowEnd = c->rowEnd;
+  c->bandCall = true;            // both kernels are launched even when their stages are off for the picture: the neighbours wait for the flags
+  const int rc = runStages(c, slot, 1, ST_DBF | ST_SAO | ST_ALF, false, "band_filter");
+  c->bandCall = false;
+  return rc;
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // host batches

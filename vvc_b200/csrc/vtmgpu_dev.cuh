@@ -117,6 +117,32 @@ struct AlfAddr
   size_t sideStride, offTab, offAlf, offCtl;
 };
 
+// Band mode over peer memory (one picture split into CTU-row bands, one GPU per band): the neighbours' plane
+// allocations are mapped into this GPU's address space (CUDA IPC over NVLink).  k_dbf_sao stores the four rows of SAO output on
+// each side of a band border ALSO into the neighbour's plane -- the rows its ALF reads across the border -- and the last CTA to
+// finish releases a flag in the neighbour's memory; k_alf's walking thread acquires the flag before it loads a tile of the band's
+// first / last tile row.  A second pair of flags travels the other way (ALF finished reading) so that the next iteration's stores
+// do not overtake the neighbour's reads.  No host synchronisation and no copy kernels inside an iteration.
+//   flags (uint32, in the memory of the rank that WAITS on them): [0] rows from above have landed, [1] rows from below,
+//   [2] the neighbour above has finished its ALF, [3] the neighbour below, [4] [5] exit counters of this rank's two kernels
+struct BandDev
+{
+  pel* myPlanes;                 // base of this context's plane allocation (the neighbours' have the same layout)
+  pel* peerPlanes[2];            // the neighbour above / below, peer-mapped; nullptr = no neighbour on that side
+  uint32_t* peerFlags[2];
+  uint32_t* myFlags;             // nullptr: not in peer band mode
+  uint32_t iter;                 // 1, 2, ... : the value the flags carry
+  int rowBegin, rowEnd;          // luma rows of this band
+};
+
+__device__ __forceinline__ uint32_t ldAcquireSys(const uint32_t* p)
+{
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void stReleaseSys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
 struct Geom
 {
   int w, h;             // luma

@@ -73,6 +73,10 @@ def load_library(path=None):
         "vtmgpu_import_rows": (C.c_int, [ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
         "vtmgpu_export_halo": (C.c_int, [ctx, C.c_int, C.POINTER(C.c_int * 3), C.c_int, C.c_void_p]),
         "vtmgpu_import_halo": (C.c_int, [ctx, C.c_int, C.POINTER(C.c_int * 3), C.c_int, C.c_void_p]),
+        "vtmgpu_band_export": (C.c_int, [ctx, C.POINTER(abi.BandHandle)]),
+        "vtmgpu_band_connect": (C.c_int, [ctx, C.POINTER(abi.BandHandle), C.POINTER(abi.BandHandle)]),
+        "vtmgpu_band_filter_async": (C.c_int, [ctx, C.c_int]),
+        "vtmgpu_band_disconnect": (C.c_int, [ctx]),
         "vtmgpu_batch_create": (C.c_int, [C.POINTER(abi.SeqParams), C.c_int, C.POINTER(ctx)]),
         "vtmgpu_batch_destroy": (None, [ctx]),
         "vtmgpu_batch_filter": (C.c_int, [ctx, C.POINTER(abi.HostPicture), C.c_int]),
@@ -295,6 +299,25 @@ class Context:
     def import_halo(self, slot, rows, nrows, dev_ptr):
         y = (C.c_int * 3)(*(list(rows) + [0, 0])[:3])
         self._ck(self.lib.vtmgpu_import_halo(self.h, slot, C.byref(y), nrows, C.c_void_p(dev_ptr)), "import_halo")
+
+    # ---- band mode over peer memory ---------------------------------------------------------------------
+    def band_export(self):
+        """bytes of this rank's vtmgpu_band_handle (to be handed to the neighbouring ranks by any host channel)."""
+        h = abi.BandHandle()
+        self._ck(self.lib.vtmgpu_band_export(self.h, C.byref(h)), "band_export")
+        return bytes(h.bytes)
+
+    def band_connect(self, above=None, below=None):
+        """above / below: handle bytes of the ranks that own the neighbouring bands, or None at the picture border."""
+        hs = [abi.BandHandle.from_buffer_copy(b) if b is not None else None for b in (above, below)]
+        self._ck(self.lib.vtmgpu_band_connect(self.h, C.byref(hs[0]) if hs[0] is not None else None, C.byref(hs[1]) if hs[1] is not None else None), "band_connect")
+
+    def band_filter(self, slot=0):
+        """Enqueues the whole chain for this rank's band with the halo rows stored straight into the neighbours' planes."""
+        self._ck(self.lib.vtmgpu_band_filter_async(self.h, slot), "band_filter")
+
+    def band_disconnect(self):
+        self._ck(self.lib.vtmgpu_band_disconnect(self.h), "band_disconnect")
 
     # ---- side information --------------------------------------------------------------------------------
     def set_deblock(self, slot, params, sync=True):
