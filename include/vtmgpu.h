@@ -327,6 +327,23 @@ int vtmgpu_export_halo(vtmgpu_ctx* ctx, int slot, const int y[3], int nrows, voi
 int vtmgpu_import_halo(vtmgpu_ctx* ctx, int slot, const int y[3], int nrows, const void* dev_src);
 
 /* ---------------------------------------------------------------------------------------------
+ * decoded-picture hash ON THE DEVICE: the hash of the decoded picture hash SEI over the CURRENT state of the
+ * slots' planes, so that a filtered picture can be verified (or its SEI written) without leaving HBM.
+ *   VTMGPU_HASH_MD5       calcMD5       CommonLib/PicYuvMD5.cpp:188   16 bytes per component
+ *   VTMGPU_HASH_CRC       calcCRC       CommonLib/PicYuvMD5.cpp:130    2 bytes per component
+ *   VTMGPU_HASH_CHECKSUM  calcChecksum  CommonLib/PicYuvMD5.cpp:169    4 bytes per component
+ * digest receives, per slot, the components' digests one after the other exactly as PictureHash::hash holds them
+ * (48 bytes are reserved per slot); *bytes_per_component returns 16 / 2 / 4.  Called from DecLib.cpp:699-708 in the reference
+ * (calcAndPrintHashStatus).  CRC and checksum are parallel reductions; MD5 is one serial chain per component (all components and
+ * slots of the call run in parallel, so it pays for batches -- for a single picture the host is faster).
+ * --------------------------------------------------------------------------------------------- */
+#define VTMGPU_HASH_MD5      1
+#define VTMGPU_HASH_CRC      2
+#define VTMGPU_HASH_CHECKSUM 3
+#define VTMGPU_HASH_SLOT_BYTES 48
+int vtmgpu_hash(vtmgpu_ctx* ctx, int first, int count, int kind, uint8_t* digest, int* bytes_per_component);
+
+/* ---------------------------------------------------------------------------------------------
  * band mode over PEER MEMORY (NVLink / NVSwitch): no copies, no NCCL, no host synchronisation inside an iteration.
  * Every rank (one process per GPU) exports a handle of its plane memory and flag block, the handles travel by any host channel
  * (vvc_b200/bands.py: torch.distributed all_gather), and every rank connects to the ranks that own the bands above and below.

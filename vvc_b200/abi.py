@@ -107,6 +107,7 @@ PlanePtrs = C.POINTER(C.c_int16) * 3
 Strides = C.c_ssize_t * 3
 
 
+HASH_MD5, HASH_CRC, HASH_CHECKSUM, HASH_SLOT_BYTES = 1, 2, 3, 48
 BAND_HANDLE_BYTES = 160
 
 
@@ -127,6 +128,7 @@ ENTRY_POINTS = [
     "vtmgpu_alf", "vtmgpu_sao_alf", "vtmgpu_deblock_sao", "vtmgpu_filter", "vtmgpu_filter_async", "vtmgpu_sync", "vtmgpu_timer_start",
     "vtmgpu_timer_stop", "vtmgpu_rewind", "vtmgpu_launch_count", "vtmgpu_set_profiling", "vtmgpu_stage_ms",
     "vtmgpu_set_rows", "vtmgpu_set_stream", "vtmgpu_upload_rows", "vtmgpu_download_rows", "vtmgpu_export_rows", "vtmgpu_import_rows", "vtmgpu_export_halo", "vtmgpu_import_halo",
+    "vtmgpu_hash",
     "vtmgpu_band_export", "vtmgpu_band_connect", "vtmgpu_band_filter_async", "vtmgpu_band_disconnect",
     "vtmgpu_batch_create", "vtmgpu_batch_destroy", "vtmgpu_batch_filter", "vtmgpu_batch_last_error", "vtmgpu_batch_launch_count",
 ]

@@ -19,6 +19,7 @@
 
 #include "dbf_kernel.cuh"
 #include "alf_kernel.cuh"
+#include "hash_kernel.cuh"
 #include "vtmgpu.h"
 #include "vvc_alf_fixed_tables.h"
 
@@ -1150,6 +1151,58 @@ extern "C" int vtmgpu_deblock_sao(vtmgpu_ctx* c, int first, int count) { return 
 extern "C" int vtmgpu_sao_alf(vtmgpu_ctx* c, int first, int count) { return runStages(c, first, count, ST_SAO | ST_ALF, true, "sao_alf"); }
 extern "C" int vtmgpu_filter(vtmgpu_ctx* c, int first, int count) { return runStages(c, first, count, ST_DBF | ST_SAO | ST_ALF, true, "filter"); }
 extern "C" int vtmgpu_filter_async(vtmgpu_ctx* c, int first, int count) { return runStages(c, first, count, ST_DBF | ST_SAO | ST_ALF, false, "filter_async"); }
+
+// ------------------------------------------------------------------------------------------------------------
+// decoded-picture hash on the device
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int vtmgpu_hash(vtmgpu_ctx* c, int first, int count, int kind, uint8_t* digest, int* bytes_per_component)
+{
+  if (!c) return -1;
+  if (!c->slotOk(first, count)) return c->fail("hash: bad slot range [%d,%d)", first, first + count);
+  if (!digest) return c->fail("hash: NULL digest");
+  if (kind != VTMGPU_HASH_MD5 && kind != VTMGPU_HASH_CRC && kind != VTMGPU_HASH_CHECKSUM) return c->fail("hash: unknown kind %d", kind);
+  cudaSetDevice(c->seq.device);
+  const int nc = c->g.ncomp, n = count * nc, words = kind == VTMGPU_HASH_MD5 ? 4 : 1;
+  std::vector<HashPlane> hp(n);
+  unsigned char* dev = nullptr;
+  const size_t planeBytes = sizeof(HashPlane) * n, outBytes = sizeof(uint32_t) * words * n;
+  if (c->cuda(cudaMalloc((void**)&dev, planeBytes + outBytes), "hash scratch")) return -1;
+  uint32_t* out = reinterpret_cast<uint32_t*>(dev + planeBytes);
+  for (int s = 0; s < count; s++)
+    for (int k = 0; k < nc; k++)
+    {
+      const PlaneDev& d = c->slotsPinned[first + s].buf[c->cur[first + s]][k];
+      hp[s * nc + k] = HashPlane{ d.p, d.pitch, d.w, d.h, k ? c->g.bdC : c->g.bdL, out + (size_t)(s * nc + k) * words };
+    }
+  int rc = 0;
+  std::vector<uint32_t> res((size_t)words * n);
+  if (c->cuda(cudaMemcpyAsync(dev, hp.data(), planeBytes, cudaMemcpyHostToDevice, c->stream), "hash upload") ||
+      c->cuda(cudaMemsetAsync(out, 0, outBytes, c->stream), "hash clear")) rc = -1;
+  if (!rc)
+  {
+    if (kind == VTMGPU_HASH_MD5)           k_hash_md5<<<n, 32, 0, c->stream>>>(reinterpret_cast<const HashPlane*>(dev), n);
+    else if (kind == VTMGPU_HASH_CRC)      k_hash_crc<<<dim3(64, n), 128, 0, c->stream>>>(reinterpret_cast<const HashPlane*>(dev), n);
+    else                                   k_hash_checksum<<<dim3(64, n), 256, 0, c->stream>>>(reinterpret_cast<const HashPlane*>(dev), n);
+    c->launches++;
+    if (c->cuda(cudaGetLastError(), "hash launch") || c->cuda(cudaMemcpyAsync(res.data(), out, outBytes, cudaMemcpyDeviceToHost, c->stream), "hash download") ||
+        c->cuda(cudaStreamSynchronize(c->stream), "hash")) rc = -1;
+  }
+  cudaFree(dev);
+  if (rc) return rc;
+  const int len = kind == VTMGPU_HASH_MD5 ? 16 : (kind == VTMGPU_HASH_CRC ? 2 : 4);
+  memset(digest, 0, (size_t)count * VTMGPU_HASH_SLOT_BYTES);
+  for (int s = 0; s < count; s++)
+    for (int k = 0; k < nc; k++)
+    {
+      uint8_t* d = digest + (size_t)s * VTMGPU_HASH_SLOT_BYTES + k * len;
+      const uint32_t* r = &res[(size_t)(s * nc + k) * words];
+      if (kind == VTMGPU_HASH_MD5) for (int i = 0; i < 16; i++) d[i] = (uint8_t)(r[i >> 2] >> (8 * (i & 3)));         // state words, little endian
+      else if (kind == VTMGPU_HASH_CRC) { d[0] = (uint8_t)(r[0] >> 8); d[1] = (uint8_t)r[0]; }                          // :127-128
+      else for (int i = 0; i < 4; i++) d[i] = (uint8_t)(r[0] >> (24 - 8 * i));                                          // :180-183
+    }
+  if (bytes_per_component) *bytes_per_component = len;
+  return 0;
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // band mode over peer memory

@@ -73,6 +73,7 @@ def load_library(path=None):
         "vtmgpu_import_rows": (C.c_int, [ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
         "vtmgpu_export_halo": (C.c_int, [ctx, C.c_int, C.POINTER(C.c_int * 3), C.c_int, C.c_void_p]),
         "vtmgpu_import_halo": (C.c_int, [ctx, C.c_int, C.POINTER(C.c_int * 3), C.c_int, C.c_void_p]),
+        "vtmgpu_hash": (C.c_int, [ctx, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_int)]),
         "vtmgpu_band_export": (C.c_int, [ctx, C.POINTER(abi.BandHandle)]),
         "vtmgpu_band_connect": (C.c_int, [ctx, C.POINTER(abi.BandHandle), C.POINTER(abi.BandHandle)]),
         "vtmgpu_band_filter_async": (C.c_int, [ctx, C.c_int]),
@@ -299,6 +300,16 @@ class Context:
     def import_halo(self, slot, rows, nrows, dev_ptr):
         y = (C.c_int * 3)(*(list(rows) + [0, 0])[:3])
         self._ck(self.lib.vtmgpu_import_halo(self.h, slot, C.byref(y), nrows, C.c_void_p(dev_ptr)), "import_halo")
+
+    # ---- decoded-picture hash on the device -----------------------------------------------------------------
+    def hash(self, first=0, count=1, kind=abi.HASH_MD5):
+        """Digests of the current planes of slots [first, first + count) computed on the device: list (per slot) of bytes holding
+        the components' digests one after the other, as in the decoded picture hash SEI (kind: abi.HASH_MD5 / HASH_CRC / HASH_CHECKSUM)."""
+        buf = (C.c_uint8 * (abi.HASH_SLOT_BYTES * count))()
+        n = C.c_int(0)
+        self._ck(self.lib.vtmgpu_hash(self.h, first, count, kind, buf, C.byref(n)), "hash")
+        raw = bytes(buf)
+        return [raw[s * abi.HASH_SLOT_BYTES:s * abi.HASH_SLOT_BYTES + n.value * self.ncomp] for s in range(count)]
 
     # ---- band mode over peer memory ---------------------------------------------------------------------
     def band_export(self):
