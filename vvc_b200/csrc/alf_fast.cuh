@@ -129,8 +129,10 @@ __device__ __forceinline__ void alfLumaBlockV(const uint32_t* __restrict__ v, pe
 // c0 = first sample of the block in the row-major tile (pitch P samples); W[r][j] = word j (columns x-4+2j, +1) of row y-1+r.
 // cells = false (block rows next to the ALF virtual boundary: the caller computes their cells with the row-replacing routine)
 // only writes the copy.
-template <int P, int CELLP>
-__device__ __forceinline__ void alfBlockCellsAndCopy(const pel* __restrict__ c0, uint2 (*cell)[CELLP], uint32_t* __restrict__ vOwn, int bi, int bj, bool cells)
+// gate() is called once after the loads and before the first store: the caller waits there until the previous tile's readers of the
+// copy and the cells are done (k_alf: split barrier), so the loads and the arithmetic of this phase overlap the stragglers.
+template <int P, int CELLP, class Gate>
+__device__ __forceinline__ void alfBlockCellsAndCopy(const pel* __restrict__ c0, uint2 (*cell)[CELLP], uint32_t* __restrict__ vOwn, int bi, int bj, bool cells, Gate gate)
 {
   uint32_t W[6][5];                                                    // words 1..4 of each row are used (index 0 is never read)
 #pragma unroll
@@ -141,11 +143,18 @@ __device__ __forceinline__ void alfBlockCellsAndCopy(const pel* __restrict__ c0,
     W[r][1] = *reinterpret_cast<const uint32_t*>(row - 2); W[r][2] = q.x; W[r][3] = q.y; W[r][4] = *reinterpret_cast<const uint32_t*>(row + 4);
   }
   // vertical pairs of the block's own columns: row pairs (y+k, y+k+1), k = 0..3
+  uint4 vp[4];
 #pragma unroll
   for (int k = 0; k < 4; k++)
-    *reinterpret_cast<uint4*>(vOwn + k * AV_COLS) = make_uint4(prmt(W[k + 1][2], W[k + 2][2], 0x5410u), prmt(W[k + 1][2], W[k + 2][2], 0x7632u),
-                                                                prmt(W[k + 1][3], W[k + 2][3], 0x5410u), prmt(W[k + 1][3], W[k + 2][3], 0x7632u));
-  if (!cells) return;
+    vp[k] = make_uint4(prmt(W[k + 1][2], W[k + 2][2], 0x5410u), prmt(W[k + 1][2], W[k + 2][2], 0x7632u),
+                       prmt(W[k + 1][3], W[k + 2][3], 0x5410u), prmt(W[k + 1][3], W[k + 2][3], 0x7632u));
+  if (!cells)
+  {
+    gate();
+#pragma unroll
+    for (int k = 0; k < 4; k++) *reinterpret_cast<uint4*>(vOwn + k * AV_COLS) = vp[k];
+    return;
+  }
   // D[ri][ci] = (S[y-1+ri][x-1+ci], S[y+ri][x+ci]), ri, ci = 0..4
   uint32_t D[5][5];
 #pragma unroll
@@ -157,6 +166,7 @@ __device__ __forceinline__ void alfBlockCellsAndCopy(const pel* __restrict__ c0,
     D[ri][3] = prmt(W[ri][3], W[ri + 1][3], 0x7610u);
     D[ri][4] = prmt(W[ri][3], W[ri + 1][4], 0x5432u);
   }
+  uint2 cv[2][2];
 #pragma unroll
   for (int cy = 0; cy < 2; cy++)
 #pragma unroll
@@ -168,8 +178,18 @@ __device__ __forceinline__ void alfBlockCellsAndCopy(const pel* __restrict__ c0,
       const int v = AV_LAP(D[r - 1][c], D[r + 1][c]), h = AV_LAP(D[r][c - 1], D[r][c + 1]);
       const int d0 = AV_LAP(D[r - 1][c - 1], D[r + 1][c + 1]), d1 = AV_LAP(D[r + 1][c - 1], D[r - 1][c + 1]);
 #undef AV_LAP
-      cell[2 * bi + 1 + cy][2 * bj + 1 + cx] = make_uint2((uint32_t)v | (uint32_t)h << 16, (uint32_t)d0 | (uint32_t)d1 << 16);
+      cv[cy][cx] = make_uint2((uint32_t)v | (uint32_t)h << 16, (uint32_t)d0 | (uint32_t)d1 << 16);
     }
+  gate();
+#pragma unroll
+  for (int k = 0; k < 4; k++) *reinterpret_cast<uint4*>(vOwn + k * AV_COLS) = vp[k];
+  // the two cells of a cell row are adjacent: one 128-bit store per row (cell index 2 bj + 1 is odd: 8-byte aligned only -> two 64-bit stores)
+#pragma unroll
+  for (int cy = 0; cy < 2; cy++)
+  {
+    cell[2 * bi + 1 + cy][2 * bj + 1] = cv[cy][0];
+    cell[2 * bi + 1 + cy][2 * bj + 2] = cv[cy][1];
+  }
 }
 
 // One Laplacian cell anywhere in the tile (ring of halo cells, block rows next to the ALF virtual boundary), same packed scheme.

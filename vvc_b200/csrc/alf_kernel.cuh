@@ -94,7 +94,7 @@ __host__ __device__ inline SaLayout saLayout(int sx, int sy, int ncomp, bool tab
   L.offV = L.offCell + SA_CELLR * SA_CELLP * 8;                // vertical-pair copy of the luma tile (alf_fast.cuh), 16-byte aligned
   L.offPar = L.offV + AV_BYTES;
   L.offBar = L.offPar + 2 * 4 * (int)sizeof(CtuCtlDev);      // per stage: the control records of the (up to 2 x 2) CTUs under the tile
-  L.offDesc = L.offBar + 16;                                 // per stage: tile descriptor written by the walking thread (k_alf)
+  L.offDesc = L.offBar + 32;                                 // per stage: tile descriptor written by the walking thread (k_alf); bars: 2 x tile loads, cells ready, tile done
   L.total = L.offDesc + 2 * 32;
   return L;
 }
@@ -980,6 +980,8 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
     {
       mbarInit(&bars[0], 1);
       mbarInit(&bars[1], 1);
+      mbarInit(&bars[2], SA_THREADS / 32);                     // "cells ready": one arrival per warp and tile
+      mbarInit(&bars[3], SA_THREADS / 32);                     // "tile done"
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       saAdvance(nxt, step, tilesX, tilesY);
       const uint4 ctlA = alfLoadCtl(A, g, firstSlot, cur, ty0);
@@ -996,19 +998,28 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
     const int4 dsc = *reinterpret_cast<const int4*>(&desc[stage]);
     if (!dsc.w) break;
     const uint4 ctl0 = desc[stage].ctl;
-    if (tid == 0)
+    // Split barriers (mbarriers 2 and 3, one arrival per warp): a warp waits for the others only where it needs their results.
+    //   gate   before a thread's first store of phase 1: the previous tile is done everywhere (its readers of the copy, the cells and
+    //          the other stage are finished); the walking thread then describes the next tile and issues its loads
+    //   cells  after the chroma quads, before the classification: the cells and the copy of this tile are complete
+    // The loads and the arithmetic of phase 1 and the chroma quads run while slower warps are still in the previous phase.
+    auto gate = [&]()
     {
-      const bool more = nxt.slot < numSlots;
-      AlfTileDesc& d = desc[stage ^ 1];
-      d.x0 = nxt.tx * SA_T; d.y0 = (nxt.ty + ty0) * SA_TH; d.slotAbs = firstSlot + nxt.slot; d.valid = more; d.ctl = ctlB;
-      if (more)
+      if (it > 0) mbarWait(&bars[3], (it - 1) & 1);
+      if (tid == 0)
       {
-        alfBandWait(band, nxt.ty, tilesY);
-        alfPrefetch(smraw, L, stage ^ 1, A, tmaps + ((size_t)(firstSlot + nxt.slot) * 3 + srcBuf) * 3, firstSlot + nxt.slot, nxt, g, ncomp, sx, sy, ty0, ctlB);
-        saAdvance(nxt, step, tilesX, tilesY);
-        ctlB = nxt.slot < numSlots ? alfLoadCtl(A, g, firstSlot, nxt, ty0) : make_uint4(0, 0, 0, 0);
+        const bool more = nxt.slot < numSlots;
+        AlfTileDesc& d = desc[stage ^ 1];
+        d.x0 = nxt.tx * SA_T; d.y0 = (nxt.ty + ty0) * SA_TH; d.slotAbs = firstSlot + nxt.slot; d.valid = more; d.ctl = ctlB;
+        if (more)
+        {
+          alfBandWait(band, nxt.ty, tilesY);
+          alfPrefetch(smraw, L, stage ^ 1, A, tmaps + ((size_t)(firstSlot + nxt.slot) * 3 + srcBuf) * 3, firstSlot + nxt.slot, nxt, g, ncomp, sx, sy, ty0, ctlB);
+          saAdvance(nxt, step, tilesX, tilesY);
+          ctlB = nxt.slot < numSlots ? alfLoadCtl(A, g, firstSlot, nxt, ty0) : make_uint4(0, 0, 0, 0);
+        }
       }
-    }
+    };
     const int x0 = dsc.x, y0 = dsc.y;
     pel* const dY = A.planes + (size_t)dsc.z * A.slotStride + (size_t)dstBuf * A.bufStride;
     const AlfDev* const alfDev = reinterpret_cast<const AlfDev*>(A.side + (size_t)dsc.z * A.sideStride + A.offAlf);
@@ -1058,7 +1069,7 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
     // ---- phase 1: Laplacian cells + vertical-pair copy (luma ALF only) -------------------------------------------------
     if (alfY)
     {
-      alfBlockCellsAndCopy<SA_P, SA_CELLP>(c0, cell, vBlk + 4, bi, bj, vb == 0);
+      alfBlockCellsAndCopy<SA_P, SA_CELLP>(c0, cell, vBlk + 4, bi, bj, vb == 0, gate);
       if (vb)
       {
 #pragma unroll 1
@@ -1070,47 +1081,13 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
       }
       if (cpH >= 0) alfCopyQuad<SA_P>(A0 + cpH, V + cpV);
       if (ringI >= 0) cell[ringI][ringJ] = alfCellAny<SA_P>(&A0[(2 * ringI + SA_HY - 2) * SA_P + 2 * ringJ + SA_HX - 2], y0 - 2 + 2 * ringI, ctuMask, vbL);
-      __syncthreads();
     }
+    else gate();
+    __syncwarp();
+    if ((tid & 31) == 0) mbarArrive(&bars[2]);
 
     // ---- phase 2 ----------------------------------------------------------------------------------------------------
     const bool lumaBlk = alfY && x0 + 4 * bj < g.w && y0 + 4 * bi < g.h;         // the last tile of a row / column may be partial
-    const AlfLumaEntry* e = nullptr;
-    if (lumaBlk && !wide)
-    {
-      // window = cells (2bi .. 2bi+3) x (2bj .. 2bj+3).  Blocks at the virtual boundary use 3 of the 4 cell rows and the
-      // scale 96 (deriveClassificationBlk :977-1010).  Packed 16-bit sums: a cell holds at most 4 * (2^bd - 1) per direction, so
-      // up to 10 bits the whole window (16 cells) stays below 2^16 per lane; above, every cell row is unpacked on its own.
-      int sumV, sumH, sumD0, sumD1;
-      const uint4* rp = reinterpret_cast<const uint4*>(&cell[2 * bi][2 * bj]);
-      if (g.bdL <= 10)
-      {
-        uint32_t vh = 0, dd = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-        {
-          if ((vb == 1 && i == 3) || (vb == 2 && i == 0)) continue;
-          const uint4 q0 = rp[i * (SA_CELLP / 2)], q1 = rp[i * (SA_CELLP / 2) + 1];
-          vh += q0.x + q0.z + q1.x + q1.z; dd += q0.y + q0.w + q1.y + q1.w;
-        }
-        sumV = vh & 0xffff; sumH = vh >> 16; sumD0 = dd & 0xffff; sumD1 = dd >> 16;
-      }
-      else
-      {
-        sumV = sumH = sumD0 = sumD1 = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-        {
-          if ((vb == 1 && i == 3) || (vb == 2 && i == 0)) continue;
-          const uint4 q0 = rp[i * (SA_CELLP / 2)], q1 = rp[i * (SA_CELLP / 2) + 1];
-          const uint32_t vh = q0.x + q0.z + q1.x + q1.z, dd = q0.y + q0.w + q1.y + q1.w;
-          sumV += vh & 0xffff; sumH += vh >> 16; sumD0 += dd & 0xffff; sumD1 += dd >> 16;
-        }
-      }
-      int cls, tIdx;
-      alfClassify(sumV, sumH, sumD0, sumD1, vb ? 96 : 64, g.bdL, cls, tIdx);
-      e = reinterpret_cast<const AlfLumaEntry*>(st + L.offSet) + (cls * 4 + tIdx);
-    }
 
     if (ncomp > 1)
     {
@@ -1185,6 +1162,45 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
       }
     }
 
+    mbarWait(&bars[2], it & 1);                              // the cells and the copy of this tile are complete
+    const AlfLumaEntry* e = nullptr;
+    if (lumaBlk && !wide)
+    {
+      // window = cells (2bi .. 2bi+3) x (2bj .. 2bj+3).  Blocks at the virtual boundary use 3 of the 4 cell rows and the
+      // scale 96 (deriveClassificationBlk :977-1010).  Packed 16-bit sums: a cell holds at most 4 * (2^bd - 1) per direction, so
+      // up to 10 bits the whole window (16 cells) stays below 2^16 per lane; above, every cell row is unpacked on its own.
+      int sumV, sumH, sumD0, sumD1;
+      const uint4* rp = reinterpret_cast<const uint4*>(&cell[2 * bi][2 * bj]);
+      if (g.bdL <= 10)
+      {
+        uint32_t vh = 0, dd = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+          if ((vb == 1 && i == 3) || (vb == 2 && i == 0)) continue;
+          const uint4 q0 = rp[i * (SA_CELLP / 2)], q1 = rp[i * (SA_CELLP / 2) + 1];
+          vh += q0.x + q0.z + q1.x + q1.z; dd += q0.y + q0.w + q1.y + q1.w;
+        }
+        sumV = vh & 0xffff; sumH = vh >> 16; sumD0 = dd & 0xffff; sumD1 = dd >> 16;
+      }
+      else
+      {
+        sumV = sumH = sumD0 = sumD1 = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+          if ((vb == 1 && i == 3) || (vb == 2 && i == 0)) continue;
+          const uint4 q0 = rp[i * (SA_CELLP / 2)], q1 = rp[i * (SA_CELLP / 2) + 1];
+          const uint32_t vh = q0.x + q0.z + q1.x + q1.z, dd = q0.y + q0.w + q1.y + q1.w;
+          sumV += vh & 0xffff; sumH += vh >> 16; sumD0 += dd & 0xffff; sumD1 += dd >> 16;
+        }
+      }
+      int cls, tIdx;
+      alfClassify(sumV, sumH, sumD0, sumD1, vb ? 96 : 64, g.bdL, cls, tIdx);
+      e = reinterpret_cast<const AlfLumaEntry*>(st + L.offSet) + (cls * 4 + tIdx);
+    }
+
+
     if (alfY)
     {
       if (lumaBlk)
@@ -1206,7 +1222,8 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
           *reinterpret_cast<int4*>(dY + y * pitchY + x) = *reinterpret_cast<const int4*>(&A0[(r + SA_HY) * SA_P + 8 * gc + SA_HX]);
       }
     }
-    __syncthreads();                                         // all reads of the stage buffers, the copy and the cells are done before they are refilled
+    __syncwarp();
+    if ((tid & 31) == 0) mbarArrive(&bars[3]);               // this warp's reads of the stage buffers, the copy and the cells are done
   }
   if (band.myFlags && tid == 0)
   {

@@ -41,6 +41,9 @@ __device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity)
     "MBAR_DONE_%=:\n"
     "}\n" ::"r"(smemAddr(bar)), "r"(parity) : "memory");
 }
+// plain arrival of one thread (release): the split CTA barriers of k_alf -- every warp arrives when its part is done and waits
+// (mbarWait) only where it needs the others' results
+__device__ __forceinline__ void mbarArrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(bar)) : "memory"); }
 // one 2-D box of a plane (element coordinates, may start outside: those elements arrive as zeros) into shared memory
 __device__ __forceinline__ void tmaLoad2D(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar)
 {
