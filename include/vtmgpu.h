@@ -281,6 +281,16 @@ int vtmgpu_set_deblock_async(vtmgpu_ctx* ctx, int slot, const vtmgpu_deblock_par
 int vtmgpu_set_deblock_sparse(vtmgpu_ctx* ctx, int slot, const vtmgpu_deblock_sparse* p);
 int vtmgpu_set_sao    (vtmgpu_ctx* ctx, int slot, const vtmgpu_sao_params* p);       /* NULL = stage off */
 int vtmgpu_set_alf    (vtmgpu_ctx* ctx, int slot, const vtmgpu_alf_params* p);       /* NULL = stage off */
+/* Pictures whose slices carry DIFFERENT ALF parameters: ALFProcess reloads the APS data whenever the CTU's slice changes
+ * (AdaptiveLoopFilter.cpp:429-441) and tests the slice's own enable flags per CTU (:429, :451, :532).
+ *   slices[k]      what slice k signals: enabled[], num_luma_aps / luma_aps, chroma_aps, ccalf_enabled[]
+ *   ctu_slice[ctu] index of the slice the CTU belongs to
+ * Everything that is per picture in the reference is taken from slices[0]: the per-CTU arrays, ctu_clip, vb, num_ctus and --
+ * like the reference, whose ALF object holds ONE copy of them (DecLib.cpp:589, AdaptiveLoopFilter.cpp:537,610) --
+ * ccalf_coeff.  ctu_filter_idx >= 16 counts in the CTU's own slice's luma_aps list.  Slices with equal parameters share their
+ * tables; at most VTMGPU_ALF_MAX_SLICE_SETS distinct parameter sets and VTMGPU_ALF_MAX_APS distinct luma APSs per picture. */
+#define VTMGPU_ALF_MAX_SLICE_SETS 8
+int vtmgpu_set_alf_slices(vtmgpu_ctx* ctx, int slot, int num_slices, const vtmgpu_alf_params* slices, const uint8_t* ctu_slice);
 
 /* host-only helper: resolves MERGE / scales NEW offsets in place, raster order
  * (xReconstructBlkSAOParams, SampleAdaptiveOffset.cpp:266-290).  Returns <0 on error, else a 3-bit mask

@@ -87,6 +87,65 @@ def alf(seq, planes, alf_params):
         raise RuntimeError("vvco_alf rc=%d" % rc)
 
 
+def alf_slices(seq, planes, slices, ctu_slice):
+    """ALF of a picture whose slices carry different parameters, in place.  ALFProcess reloads the APS data whenever the CTU's
+    slice changes and reads the slice's own enable flags (AdaptiveLoopFilter.cpp:429-441, :451, :532); the filters read only the
+    pre-ALF picture, so the result is the per-slice run of the single-set oracle on the slice's own CTUs (every other CTU switched
+    off), composed CTU by CTU.  The per-CTU arrays and the CC-ALF coefficients are per picture: taken from slices[0]."""
+    n = slices[0].num_ctus
+    ctu = seq["ctu_size"]
+    wc = (seq["width"] + ctu - 1) // ctu
+    sx, sy = abi.chroma_shifts(seq["chroma_format"])
+    src = [p.copy() for p in planes]
+    p0 = slices[0]
+
+    def arr(ptr, dt):
+        return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dt).copy() if ptr else None
+
+    en = [arr(p0.ctu_enable[c], np.uint8) for c in range(3)]
+    idc = [arr(p0.ccalf_idc[c], np.uint8) for c in range(2)]
+    for k, q in enumerate(slices):
+        mine = np.asarray(ctu_slice) == k
+        if not mine.any():
+            continue
+        r = abi.AlfParams()
+        C.memmove(C.byref(r), C.byref(p0), C.sizeof(abi.AlfParams))         # per-picture members (arrays, clip flags, vb, CC-ALF coefficients)
+        for c in range(3):
+            r.enabled[c] = q.enabled[c]
+        r.num_luma_aps, r.luma_aps, r.chroma_aps = q.num_luma_aps, q.luma_aps, q.chroma_aps
+        keep = []
+        for c in range(3):
+            if en[c] is not None:
+                m = np.where(mine, en[c], 0).astype(np.uint8)
+                keep.append(m)
+                r.ctu_enable[c] = m.ctypes.data_as(C.POINTER(C.c_uint8))
+        for c in range(2):
+            r.ccalf_enabled[c] = q.ccalf_enabled[c]
+            if idc[c] is not None:
+                m = np.where(mine, idc[c], 0).astype(np.uint8)
+                keep.append(m)
+                r.ccalf_idc[c] = m.ctypes.data_as(C.POINTER(C.c_uint8))
+        # CTUs of other slices may point at filter sets / alternatives this slice does not have: they are off, keep the indices legal
+        if p0.ctu_filter_idx:
+            f = np.ctypeslib.as_array(p0.ctu_filter_idx, shape=(n,)).copy()
+            f[~mine] = 0
+            keep.append(f)
+            r.ctu_filter_idx = f.ctypes.data_as(C.POINTER(C.c_int16))
+        for c in range(2):
+            if p0.ctu_alt[c]:
+                a = np.ctypeslib.as_array(p0.ctu_alt[c], shape=(n,)).copy()
+                a[~mine] = 0
+                keep.append(a)
+                r.ctu_alt[c] = a.ctypes.data_as(C.POINTER(C.c_uint8))
+        run = [p.copy() for p in src]
+        alf(seq, run, r)
+        for a in np.nonzero(mine)[0]:
+            x0, y0 = (a % wc) * ctu, (a // wc) * ctu
+            planes[0][y0:y0 + ctu, x0:x0 + ctu] = run[0][y0:y0 + ctu, x0:x0 + ctu]
+            for c in range(1, len(planes)):
+                planes[c][y0 >> sy:(y0 + ctu) >> sy, x0 >> sx:(x0 + ctu) >> sx] = run[c][y0 >> sy:(y0 + ctu) >> sy, x0 >> sx:(x0 + ctu) >> sx]
+
+
 def filter_capture(cap, stages=("dbf", "sao", "alf")):
     """Runs the chain of the oracle on a vvc_b200.capture.Capture; returns {stage: [planes]} after each stage."""
     planes = [p.copy() for p in cap.pre]

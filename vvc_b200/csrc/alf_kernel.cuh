@@ -676,9 +676,11 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf_parts(const 
       CtuCtlDev ctl;
       if (kVirtualBoundaries) ctl = reinterpret_cast<const CtuCtlDev*>(smraw + L.offPar)[stage * 4 + cidx];
       else                    *reinterpret_cast<uint4*>(&ctl) = ctlCur;
-      const bool alfY = alfOn && ctl.enY != 0, alfCb = alfOn && ctl.enCb != 0, alfCr = alfOn && ctl.enCr != 0;
-      const int ccCb = alfOn ? ctl.ccCb : 0, ccCr = alfOn ? ctl.ccCr : 0;
+      const bool ctuOn = alfOn && (ctl.flags & 1) != 0;          // the CTU's own slice runs ALF (ALFProcess :429)
+      const bool alfY = ctuOn && ctl.enY != 0, alfCb = ctuOn && ctl.enCb != 0, alfCr = ctuOn && ctl.enCr != 0;
+      const int ccCb = ctuOn ? ctl.ccCb : 0, ccCr = ctuOn ? ctl.ccCr : 0;
       const int clip = ctl.clip;
+      const AlfDev* const alfG = S.alf + ctl.grp;                // chroma / CC-ALF data of the CTU's slice (the luma sets are S.alf[0]'s)
       const int cx0 = px0 & ~ctuMask, cy0 = py0 & ~ctuMask, cx1 = min(cx0 + g.ctu, g.w), cy1 = min(cy0 + g.ctu, g.h);
       if (nparts > 1)
       {
@@ -799,8 +801,8 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf_parts(const 
           const bool fOn = c ? alfCr : alfCb;
           const int idc = c ? ccCr : ccCb;
           ChromaCoef C;
-          if (fOn) C = chromaCoef(&S.alf->chromaTab[c ? ctl.altCr : ctl.altCb]);
-          const int16_t* ccg = S.alf->cc[c][idc ? idc - 1 : 0];
+          if (fOn) C = chromaCoef(&alfG->chromaTab[c ? ctl.altCr : ctl.altCb]);
+          const int16_t* ccg = alfG->cc[c][idc ? idc - 1 : 0];
           for (int j = tid; j < quads; j += SA_THREADS)
           {
             const int r = j >> qShift, qx = (j & ((1 << qShift) - 1)) * 4;
@@ -823,7 +825,7 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf_parts(const 
               else if (lpos == vbL - 1 || lpos == vbL) l1 = l2 = l3 = 0;
               if (g.sx == 1)
               {
-                const uint2 d = ccAlfQuad420(&lumaB[ly * SA_P + (qx << 1) + SA_HX], l1, l2, l3, S.alf->ccB[c][idc - 1], maxcP, halfP);
+                const uint2 d = ccAlfQuad420(&lumaB[ly * SA_P + (qx << 1) + SA_HX], l1, l2, l3, alfG->ccB[c][idc - 1], maxcP, halfP);
                 v.x = addClamp0(v.x, d.x, maxcP);
                 v.y = addClamp0(v.y, d.y, maxcP);
               }
@@ -888,7 +890,7 @@ __device__ __forceinline__ void alfPrefetch(unsigned char* smraw, const SaLayout
   const int x0 = p.tx * SA_T, y0 = (p.ty + ty0) * SA_TH;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smraw + L.offBar) + stage;
   unsigned char* st = smraw + stage * L.stageBytes;
-  const uint32_t flags = (ctlv.z >> 8) & 0xff, enY = ctlv.x & 0xff, setIdx = ctlv.y >> 24;
+  const uint32_t flags = (ctlv.z >> 8) & 0xff, enY = ctlv.x & 0xff, setIdx = ctlv.y >> 24, grp = (ctlv.z >> 16) & 0xff;
   const bool small = (flags & 1) != 0, tab = small && enY != 0 && !(flags & 2);
   const unsigned char* side = A.side + (size_t)slotAbs * A.sideStride;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic-proxy accesses to the stage buffers are ordered before the async writes
@@ -900,7 +902,7 @@ __device__ __forceinline__ void alfPrefetch(unsigned char* smraw, const SaLayout
     tmaLoad2D(st + L.lumaBytes + L.chromaBytes, maps + 2, (x0 >> sx) - SA_HX, (y0 >> sy) - SA_HY, bar);
   }
   if (tab) bulkLoad(st + L.offSet, side + A.offTab + (size_t)setIdx * AT_SET_BYTES, AT_SET_BYTES, bar);
-  if (small) bulkLoad(st + L.offSmall, side + A.offAlf, ALF_SMALL_BYTES, bar);
+  if (small) bulkLoad(st + L.offSmall, side + A.offAlf + grp * sizeof(AlfDev), ALF_SMALL_BYTES, bar);
 }
 
 // peer band mode: a tile of the band's first (last) tile row reads the four rows above (below) the band, which the neighbour's
@@ -1022,9 +1024,10 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
     };
     const int x0 = dsc.x, y0 = dsc.y;
     pel* const dY = A.planes + (size_t)dsc.z * A.slotStride + (size_t)dstBuf * A.bufStride;
-    const AlfDev* const alfDev = reinterpret_cast<const AlfDev*>(A.side + (size_t)dsc.z * A.sideStride + A.offAlf);
+    const AlfDev* const alfDev0 = reinterpret_cast<const AlfDev*>(A.side + (size_t)dsc.z * A.sideStride + A.offAlf);     // the luma sets of the picture
     CtuCtlDev ctl;
     *reinterpret_cast<uint4*>(&ctl) = ctl0;
+    const AlfDev* const alfDev = alfDev0 + ctl.grp;             // chroma / CC-ALF data of the CTU's slice
     const bool alfOn = (ctl.flags & 1) != 0, wide = (ctl.flags & 2) != 0;
     const bool alfY = alfOn && ctl.enY != 0, alfCb = alfOn && ctl.enCb != 0, alfCr = alfOn && ctl.enCr != 0;
     const int ccCb = alfOn ? ctl.ccCb : 0, ccCr = alfOn ? ctl.ccCr : 0;
@@ -1206,7 +1209,7 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
       if (lumaBlk)
       {
         pel* out = dY + (y0 + 4 * bi) * pitchY + x0 + 4 * bj;
-        if (wide)    alfLumaBlockGeneric(cell, c0, out, pitchY, bi, bj, y0 + 4 * bi, &alfDev->luma[ctl.setIdx][0][0], ctuMask, vbL, g.bdL);
+        if (wide)    alfLumaBlockGeneric(cell, c0, out, pitchY, bi, bj, y0 + 4 * bi, &alfDev0->luma[ctl.setIdx][0][0], ctuMask, vbL, g.bdL);
         else if (vb) alfLumaBlockFast(c0, out, pitchY, e, maxvP, vb);
         else         alfLumaBlockV<ALF_BAL>(vBlk, out, pitchY, loadLumaCoef(e), maxvP);
       }

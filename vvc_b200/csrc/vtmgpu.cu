@@ -266,7 +266,7 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
   // the per-picture parts (APS filter tables, CTU control, ALF parameters, SAO parameters) are adjacent: one upload per picture
   L.alfTab = off; off = alignUp(off + sizeof(AlfLumaEntry) * VTMGPU_MAX_LUMA_SETS * 25 * 4, 256);
   L.ctuCtl = off; off = alignUp(off + (size_t)c->nCtus * sizeof(CtuCtlDev), 256);
-  L.alf = off;    off = alignUp(off + sizeof(AlfDev), 256);
+  L.alf = off;    off = alignUp(off + sizeof(AlfDev) * ALF_MAX_GROUPS, 256);
   L.sao = off;    off = alignUp(off + (size_t)c->nCtus * 3 * sizeof(SaoDev), 256);
   L.total = off;
 
@@ -899,74 +899,143 @@ extern "C" int vtmgpu_set_sao(vtmgpu_ctx* c, int slot, const vtmgpu_sao_params* 
   return c->pushSlot(slot);
 }
 
-extern "C" int vtmgpu_set_alf(vtmgpu_ctx* c, int slot, const vtmgpu_alf_params* p)
+namespace
 {
-  if (!c) return -1;
-  if (!c->slotOk(slot, 1)) return c->fail("set_alf: bad slot %d", slot);
+
+// what makes two slices of a picture share their ALF tables (vtmgpu_set_alf_slices): everything a slice signals
+bool sameLumaAps(const vtmgpu_alf_luma_aps& a, const vtmgpu_alf_luma_aps& b)
+{
+  if (a.num_filters != b.num_filters || (a.nonlinear != 0) != (b.nonlinear != 0)) return false;
+  if (memcmp(a.delta_idx, b.delta_idx, sizeof(a.delta_idx)) || memcmp(a.coeff, b.coeff, sizeof(a.coeff))) return false;
+  return !a.nonlinear || memcmp(a.clip_idx, b.clip_idx, sizeof(a.clip_idx)) == 0;
+}
+
+bool sameSliceAlf(const vtmgpu_alf_params& a, const vtmgpu_alf_params& b, bool chroma)
+{
+  for (int k = 0; k < 3; k++) if ((a.enabled[k] != 0) != (b.enabled[k] != 0)) return false;
+  if (a.num_luma_aps != b.num_luma_aps) return false;
+  for (int i = 0; i < a.num_luma_aps; i++) if (!sameLumaAps(a.luma_aps[i], b.luma_aps[i])) return false;
+  if ((a.chroma_aps != nullptr) != (b.chroma_aps != nullptr)) return false;
+  if (a.chroma_aps && memcmp(a.chroma_aps, b.chroma_aps, sizeof(*a.chroma_aps))) return false;
+  for (int k = 0; k < 2 && chroma; k++) if ((a.ccalf_enabled[k] != 0) != (b.ccalf_enabled[k] != 0)) return false;
+  return true;
+}
+
+// ALF side information of one picture.  slices[0 .. ns) = the parameter sets of its slices, ctuSlice = slice index per CTU (NULL
+// with one slice); per-picture data (CTU arrays, clip flags, virtual boundaries, CC-ALF coefficients) come from slices[0].
+int setAlf(vtmgpu_ctx* c, int slot, int ns, const vtmgpu_alf_params* slices, const uint8_t* ctuSlice, const char* who)
+{
+  if (!c->slotOk(slot, 1)) return c->fail("%s: bad slot %d", who, slot);
   cudaSetDevice(c->seq.device);
   c->mirrorWrite(slot);
   SlotDev& sd = c->slotsPinned[slot];
   sd.alfOn = 0;
   c->pushSlot(slot);                     // also on the error returns below
-  if (setVb(c, sd.vbAlf, p ? p->vb : nullptr, "set_alf")) return -1;
-  if (p)
+  const vtmgpu_alf_params* p = slices;
+  if (setVb(c, sd.vbAlf, p ? p->vb : nullptr, who)) return -1;
+  if (!p)
   {
-    const int n = c->nCtus;
-    if (p->num_ctus != n) return c->fail("set_alf: expected %d CTUs, got %d", n, p->num_ctus);
-    if (p->num_luma_aps < 0 || p->num_luma_aps > VTMGPU_ALF_MAX_APS) return c->fail("set_alf: bad num_luma_aps");
-    const bool chroma = c->g.ncomp > 1;
-    AlfDev& A = *reinterpret_cast<AlfDev*>(c->pinnedSide(slot) + c->lay.alf);
-    CtuCtlDev* ctl = reinterpret_cast<CtuCtlDev*>(c->pinnedSide(slot) + c->lay.ctuCtl);
-    memset(&A, 0, sizeof(A));
-    for (int k = 0; k < 3; k++) A.enabled[k] = p->enabled[k] != 0;
-    A.numSets = VTMGPU_ALF_FIXED_SETS + p->num_luma_aps;
-    // coefficient tables: reconstructCoeff (AdaptiveLoopFilter.cpp:651-713), clip values :743-762, fixed sets :792-807
-    const int bdL = c->g.bdL, bdC = c->g.bdC;
-    const int clipL[4] = { 1 << bdL, 1 << (bdL - 3), 1 << (bdL - 5), 1 << (bdL - 7) };
-    const int clipC[4] = { 1 << bdC, 1 << (bdC - 3), 1 << (bdC - 5), 1 << (bdC - 7) };
-    for (int s = 0; s < VTMGPU_ALF_FIXED_SETS; s++)
-      for (int cl = 0; cl < 25; cl++)
-        for (int k = 0; k < 12; k++) A.luma[s][cl][k] = make_short2(vvc_alf_fix_coeff[vvc_alf_class_to_filt[s * 25 + cl] * 12 + k], (short)clipL[0]);
-    for (int s = 0; s < p->num_luma_aps; s++)
+    // ALF off for this picture: k_alf reads nothing but the control records, so their flags are cleared
+    memset(c->pinnedSide(slot) + c->lay.ctuCtl, 0, (size_t)c->nCtus * sizeof(CtuCtlDev));
+    c->markSide(slot, c->lay.ctuCtl, (size_t)c->nCtus * sizeof(CtuCtlDev));
+    return c->pushSlot(slot);
+  }
+  const int n = c->nCtus;
+  if (p->num_ctus != n) return c->fail("%s: expected %d CTUs, got %d", who, n, p->num_ctus);
+  if (ns > 1 && !ctuSlice) return c->fail("%s: ctu_slice is NULL", who);
+  const bool chroma = c->g.ncomp > 1;
+  // slices -> groups of equal parameters ; luma APSs of all groups -> one list of distinct sets
+  std::vector<int> grpOf(ns), grpRep;
+  for (int s = 0; s < ns; s++)
+  {
+    const vtmgpu_alf_params& q = slices[s];
+    if (q.num_luma_aps < 0 || q.num_luma_aps > VTMGPU_ALF_MAX_APS) return c->fail("%s: bad num_luma_aps", who);
+    if (q.num_luma_aps && !q.luma_aps) return c->fail("%s: luma_aps is NULL", who);
+    int gi = -1;
+    for (size_t k = 0; k < grpRep.size() && gi < 0; k++) if (sameSliceAlf(slices[grpRep[k]], q, chroma)) gi = (int)k;
+    if (gi < 0)
     {
-      if (!p->luma_aps) return c->fail("set_alf: luma_aps is NULL");
-      const vtmgpu_alf_luma_aps& a = p->luma_aps[s];
-      for (int cl = 0; cl < 25; cl++)
+      if ((int)grpRep.size() == ALF_MAX_GROUPS) return c->fail("%s: more than %d distinct ALF parameter sets in one picture", who, ALF_MAX_GROUPS);
+      gi = (int)grpRep.size();
+      grpRep.push_back(s);
+    }
+    grpOf[s] = gi;
+  }
+  const int ng = (int)grpRep.size();
+  std::vector<const vtmgpu_alf_luma_aps*> sets;                       // distinct luma APSs of the picture
+  int setOf[ALF_MAX_GROUPS][VTMGPU_ALF_MAX_APS];                      // group, position in its list -> picture-global APS set
+  for (int gi = 0; gi < ng; gi++)
+  {
+    const vtmgpu_alf_params& q = slices[grpRep[gi]];
+    for (int i = 0; i < q.num_luma_aps; i++)
+    {
+      int si = -1;
+      for (size_t k = 0; k < sets.size() && si < 0; k++) if (sameLumaAps(*sets[k], q.luma_aps[i])) si = (int)k;
+      if (si < 0)
       {
-        const int f = a.delta_idx[cl];
-        if (f < 0 || f >= a.num_filters || f >= 25) return c->fail("set_alf: bad coeff delta idx in APS %d", s);
-        for (int k = 0; k < 12; k++)
-        {
-          const int ci = a.nonlinear ? a.clip_idx[f][k] : 0;
-          if (ci < 0 || ci > 3) return c->fail("set_alf: bad clip idx in APS %d", s);
-          A.luma[VTMGPU_ALF_FIXED_SETS + s][cl][k] = make_short2(a.coeff[f][k], (short)clipL[ci]);
-        }
+        if ((int)sets.size() == VTMGPU_ALF_MAX_APS) return c->fail("%s: more than %d distinct luma APSs in one picture", who, VTMGPU_ALF_MAX_APS);
+        si = (int)sets.size();
+        sets.push_back(&q.luma_aps[i]);
+      }
+      setOf[gi][i] = si;
+    }
+  }
+  AlfDev* const AG = reinterpret_cast<AlfDev*>(c->pinnedSide(slot) + c->lay.alf);
+  CtuCtlDev* ctl = reinterpret_cast<CtuCtlDev*>(c->pinnedSide(slot) + c->lay.ctuCtl);
+  memset(AG, 0, sizeof(AlfDev) * ng);
+  // coefficient tables: reconstructCoeff (AdaptiveLoopFilter.cpp:651-713), clip values :743-762, fixed sets :792-807
+  const int bdL = c->g.bdL, bdC = c->g.bdC;
+  const int clipL[4] = { 1 << bdL, 1 << (bdL - 3), 1 << (bdL - 5), 1 << (bdL - 7) };
+  const int clipC[4] = { 1 << bdC, 1 << (bdC - 3), 1 << (bdC - 5), 1 << (bdC - 7) };
+  AlfDev& A0 = AG[0];                    // the luma sets of the picture live in the first group's record
+  A0.numSets = VTMGPU_ALF_FIXED_SETS + (int)sets.size();
+  for (int s = 0; s < VTMGPU_ALF_FIXED_SETS; s++)
+    for (int cl = 0; cl < 25; cl++)
+      for (int k = 0; k < 12; k++) A0.luma[s][cl][k] = make_short2(vvc_alf_fix_coeff[vvc_alf_class_to_filt[s * 25 + cl] * 12 + k], (short)clipL[0]);
+  for (size_t s = 0; s < sets.size(); s++)
+  {
+    const vtmgpu_alf_luma_aps& a = *sets[s];
+    for (int cl = 0; cl < 25; cl++)
+    {
+      const int f = a.delta_idx[cl];
+      if (f < 0 || f >= a.num_filters || f >= 25) return c->fail("%s: bad coeff delta idx in a luma APS", who);
+      for (int k = 0; k < 12; k++)
+      {
+        const int ci = a.nonlinear ? a.clip_idx[f][k] : 0;
+        if (ci < 0 || ci > 3) return c->fail("%s: bad clip idx in a luma APS", who);
+        A0.luma[VTMGPU_ALF_FIXED_SETS + s][cl][k] = make_short2(a.coeff[f][k], (short)clipL[ci]);
       }
     }
-    AlfLumaEntry* tab = reinterpret_cast<AlfLumaEntry*>(c->pinnedSide(slot) + c->lay.alfTab);
-    bool wide = false;
-    for (int s = 0; s < p->num_luma_aps; s++) wide |= expandLumaSet(A.luma[VTMGPU_ALF_FIXED_SETS + s], tab + (VTMGPU_ALF_FIXED_SETS + s) * 100);
+  }
+  AlfLumaEntry* tab = reinterpret_cast<AlfLumaEntry*>(c->pinnedSide(slot) + c->lay.alfTab);
+  bool wide = false;
+  for (size_t s = 0; s < sets.size(); s++) wide |= expandLumaSet(A0.luma[VTMGPU_ALF_FIXED_SETS + s], tab + (VTMGPU_ALF_FIXED_SETS + s) * 100);
+  int numAlts[ALF_MAX_GROUPS];
+  bool anyOn = false;
+  for (int gi = 0; gi < ng; gi++)
+  {
+    const vtmgpu_alf_params& q = slices[grpRep[gi]];
+    AlfDev& A = AG[gi];
+    for (int k = 0; k < 3; k++) A.enabled[k] = q.enabled[k] != 0;
+    anyOn |= (A.enabled[0] | A.enabled[1] | A.enabled[2]) != 0;
+    A.numSets = VTMGPU_ALF_FIXED_SETS + (gi ? q.num_luma_aps : (int)sets.size());
     A.wide = wide;
-    int numAlts = 0;
-    if (p->chroma_aps)
+    numAlts[gi] = 0;
+    if (q.chroma_aps)
     {
-      numAlts = p->chroma_aps->num_alts;
-      if (numAlts < 1 || numAlts > VTMGPU_ALF_MAX_ALTS) return c->fail("set_alf: bad number of chroma alternatives");
-      for (int a = 0; a < numAlts; a++)
-        for (int k = 0; k < 6; k++)
-        {
-          const int ci = p->chroma_aps->nonlinear ? p->chroma_aps->clip_idx[a][k] : 0;
-          if (ci < 0 || ci > 3) return c->fail("set_alf: bad chroma clip idx");
-          A.chroma[a][k] = make_short2(p->chroma_aps->coeff[a][k], (short)clipC[ci]);
-        }
-      for (int a = 0; a < numAlts; a++)
+      const int na = numAlts[gi] = q.chroma_aps->num_alts;
+      if (na < 1 || na > VTMGPU_ALF_MAX_ALTS) return c->fail("%s: bad number of chroma alternatives", who);
+      for (int a = 0; a < na; a++)
       {
         AlfChromaEntry& e = A.chromaTab[a];
         int bias = 64;
         for (int k = 0; k < 6; k++)
         {
-          const int co = A.chroma[a][k].x, clp = A.chroma[a][k].y;      // AlfCoeffC is restricted to -127..127 by the parser (VLCReader.cpp:3840)
-          if (co < -128 || co > 127) return c->fail("set_alf: chroma coefficient %d out of range", co);
+          const int ci = q.chroma_aps->nonlinear ? q.chroma_aps->clip_idx[a][k] : 0;
+          if (ci < 0 || ci > 3) return c->fail("%s: bad chroma clip idx", who);
+          const int co = q.chroma_aps->coeff[a][k], clp = clipC[ci];      // AlfCoeffC is restricted to -127..127 by the parser (VLCReader.cpp:3840)
+          if (co < -128 || co > 127) return c->fail("%s: chroma coefficient %d out of range", who, co);
+          A.chroma[a][k] = make_short2((short)co, (short)clp);
           e.coefB[k] = (uint32_t)(co & 0xff) * 0x01000001u;
           e.clipP1[k] = (uint32_t)((clp + 1) & 0xffff) * 0x10001u;
           e.clip2[k] = (uint32_t)((2 * clp) & 0xffff) * 0x10001u;
@@ -977,15 +1046,15 @@ extern "C" int vtmgpu_set_alf(vtmgpu_ctx* c, int slot, const vtmgpu_alf_params* 
     }
     for (int k = 0; k < 2; k++)
     {
-      A.ccEnabled[k] = chroma && p->ccalf_enabled[k];
-      memcpy(A.cc[k], p->ccalf_coeff[k], sizeof(A.cc[k]));
+      A.ccEnabled[k] = chroma && q.ccalf_enabled[k];
+      memcpy(A.cc[k], p->ccalf_coeff[k], sizeof(A.cc[k]));               // the coefficients are per picture (see vtmgpu.h)
       for (int f = 0; f < VTMGPU_CCALF_MAX_FILTERS; f++)
       {
         int sum = 0;
         for (int t = 0; t < 7; t++)
         {
           const int co = p->ccalf_coeff[k][f][t];
-          if (A.ccEnabled[k] && (co < -128 || co > 127)) return c->fail("set_alf: CC-ALF coefficient %d out of range", co);
+          if (A.ccEnabled[k] && (co < -128 || co > 127)) return c->fail("%s: CC-ALF coefficient %d out of range", who, co);
           A.ccB[k][f][t] = (uint32_t)(co & 0xff) * 0x01000001u;
           sum += co;
         }
@@ -999,50 +1068,68 @@ extern "C" int vtmgpu_set_alf(vtmgpu_ctx* c, int slot, const vtmgpu_alf_params* 
         A.ccK[k][f][3] = -sum >= -128 && -sum <= 127;
       }
     }
-    // per-CTU control
-    const uint8_t flags = (uint8_t)(((A.enabled[0] | A.enabled[1] | A.enabled[2]) != 0 ? 1 : 0) | (wide ? 2 : 0));
-    for (int a = 0; a < n; a++)
+  }
+  // per-CTU control: a CTU is skipped when its slice runs no ALF at all (ALFProcess :429), the CC-ALF test reads the slice's own
+  // enable flag (:451, :532), the filter set index counts in the slice's own APS list (:436-441)
+  for (int a = 0; a < n; a++)
+  {
+    int gi = 0;
+    if (ns > 1)
     {
-      CtuCtlDev& r = ctl[a];
-      r.enCb = r.enCr = r.altCb = r.altCr = r.ccCb = r.ccCr = r.setIdx = 0;
-      r.flags = flags;
-      r.clip = p->ctu_clip ? (uint8_t)(p->ctu_clip[a] & 63) : 0;
-      r.enY = p->ctu_enable[0] && p->ctu_enable[0][a];
-      if (r.enY)
+      if (ctuSlice[a] >= ns) return c->fail("%s: CTU %d: bad slice index %d", who, a, ctuSlice[a]);
+      gi = grpOf[ctuSlice[a]];
+    }
+    const AlfDev& A = AG[gi];
+    const vtmgpu_alf_params& q = slices[grpRep[gi]];
+    CtuCtlDev& r = ctl[a];
+    memset(&r, 0, sizeof(r));
+    r.flags = (uint8_t)(((A.enabled[0] | A.enabled[1] | A.enabled[2]) != 0 ? 1 : 0) | (wide ? 2 : 0));
+    r.grp = (uint8_t)gi;
+    r.clip = p->ctu_clip ? (uint8_t)(p->ctu_clip[a] & 63) : 0;
+    r.enY = p->ctu_enable[0] && p->ctu_enable[0][a];
+    if (r.enY && (r.flags & 1))
+    {
+      const int fi = p->ctu_filter_idx ? p->ctu_filter_idx[a] : -1;
+      if (fi < 0 || fi >= VTMGPU_ALF_FIXED_SETS + q.num_luma_aps) return c->fail("%s: CTU %d: bad filter set index", who, a);
+      r.setIdx = (uint8_t)(fi < VTMGPU_ALF_FIXED_SETS ? fi : VTMGPU_ALF_FIXED_SETS + setOf[gi][fi - VTMGPU_ALF_FIXED_SETS]);
+    }
+    for (int k = 0; k < 2 && chroma; k++)
+    {
+      const bool on = p->ctu_enable[1 + k] && p->ctu_enable[1 + k][a];
+      (k ? r.enCr : r.enCb) = on;
+      if (on && (r.flags & 1))
       {
-        if (!p->ctu_filter_idx || p->ctu_filter_idx[a] < 0 || p->ctu_filter_idx[a] >= A.numSets) return c->fail("set_alf: CTU %d: bad filter set index", a);
-        r.setIdx = (uint8_t)p->ctu_filter_idx[a];
+        const int alt = p->ctu_alt[k] ? p->ctu_alt[k][a] : 0;
+        if (alt >= numAlts[gi]) return c->fail("%s: CTU %d: chroma alternative %d not in the APS", who, a, alt);
+        (k ? r.altCr : r.altCb) = (uint8_t)alt;
       }
-      for (int k = 0; k < 2 && chroma; k++)
+      if (A.ccEnabled[k])
       {
-        const bool on = p->ctu_enable[1 + k] && p->ctu_enable[1 + k][a];
-        (k ? r.enCr : r.enCb) = on;
-        if (on)
-        {
-          const int alt = p->ctu_alt[k] ? p->ctu_alt[k][a] : 0;
-          if (alt >= numAlts) return c->fail("set_alf: CTU %d: chroma alternative %d not in the APS", a, alt);
-          (k ? r.altCr : r.altCb) = (uint8_t)alt;
-        }
-        if (A.ccEnabled[k])
-        {
-          const int idc = p->ccalf_idc[k] ? p->ccalf_idc[k][a] : 0;
-          if (idc > VTMGPU_CCALF_MAX_FILTERS) return c->fail("set_alf: CTU %d: bad CC-ALF idc", a);
-          (k ? r.ccCr : r.ccCb) = (uint8_t)idc;
-        }
+        const int idc = p->ccalf_idc[k] ? p->ccalf_idc[k][a] : 0;
+        if (idc > VTMGPU_CCALF_MAX_FILTERS) return c->fail("%s: CTU %d: bad CC-ALF idc", who, a);
+        (k ? r.ccCr : r.ccCb) = (uint8_t)idc;
       }
     }
-    sd.alfOn = (A.enabled[0] | A.enabled[1] | A.enabled[2]) != 0;    // ALFProcess skips the picture otherwise (AdaptiveLoopFilter.cpp:429)
-    sd.alfWide = wide;
-    if (p->num_luma_aps) c->markSide(slot, c->lay.alfTab + sizeof(AlfLumaEntry) * VTMGPU_ALF_FIXED_SETS * 100, sizeof(AlfLumaEntry) * 100 * p->num_luma_aps);
-    c->markSide(slot, c->lay.ctuCtl, c->lay.sao - c->lay.ctuCtl);
   }
-  else
-  {
-    // ALF off for this picture: k_alf reads nothing but the control records, so their flags are cleared
-    memset(c->pinnedSide(slot) + c->lay.ctuCtl, 0, (size_t)c->nCtus * sizeof(CtuCtlDev));
-    c->markSide(slot, c->lay.ctuCtl, (size_t)c->nCtus * sizeof(CtuCtlDev));
-  }
+  sd.alfOn = anyOn;                      // ALFProcess filters nothing otherwise (AdaptiveLoopFilter.cpp:429)
+  sd.alfWide = wide;
+  if (!sets.empty()) c->markSide(slot, c->lay.alfTab + sizeof(AlfLumaEntry) * VTMGPU_ALF_FIXED_SETS * 100, sizeof(AlfLumaEntry) * 100 * sets.size());
+  c->markSide(slot, c->lay.ctuCtl, (c->lay.alf - c->lay.ctuCtl) + sizeof(AlfDev) * ng);
   return c->pushSlot(slot);
+}
+}   // namespace
+
+extern "C" int vtmgpu_set_alf(vtmgpu_ctx* c, int slot, const vtmgpu_alf_params* p)
+{
+  if (!c) return -1;
+  return setAlf(c, slot, 1, p, nullptr, "set_alf");
+}
+
+extern "C" int vtmgpu_set_alf_slices(vtmgpu_ctx* c, int slot, int num_slices, const vtmgpu_alf_params* slices, const uint8_t* ctu_slice)
+{
+  if (!c) return -1;
+  if (num_slices < 1 || num_slices > 255 || !slices) return c->fail("set_alf_slices: bad argument");
+  return setAlf(c, slot, num_slices, slices, ctu_slice, "set_alf_slices");
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -39,9 +39,11 @@ struct AlfChromaEntry
   int32_t  pad;
 };
 
-// ALF data of one picture.  The chroma / CC-ALF operand tables come first: k_alf copies these ALF_SMALL_BYTES into shared
-// memory with one bulk copy per tile.
+// ALF data of one picture -- of one slice parameter set when the slices of a picture differ (a slot holds ALF_MAX_GROUPS of
+// these; the luma sets of ALL groups live in the first one, the per-CTU set index is picture-global).  The chroma / CC-ALF
+// operand tables come first: k_alf copies these ALF_SMALL_BYTES into shared memory with one bulk copy per tile.
 #define ALF_SMALL_BYTES 768
+#define ALF_MAX_GROUPS 8
 struct AlfDev
 {
   AlfChromaEntry chromaTab[8];                       // chroma alternatives expanded into the operands of the packed 5x5 kernel
@@ -77,8 +79,9 @@ struct alignas(16) CtuCtlDev
   uint8_t ccCb, ccCr;            // CC-ALF filter idc (0 = off)
   uint8_t setIdx;                // luma filter set: < 16 fixed, else APS
   uint8_t clip;                  // VTMGPU_ALF_CLIP_* / PAD_*: partition boundaries the filter must not read across
-  uint8_t flags;                 // bit 0: the picture runs ALF (SlotDev::alfOn), bit 1: SlotDev::alfWide -- so that k_alf needs nothing but this record
-  uint8_t pad[6];
+  uint8_t flags;                 // bit 0: the CTU's slice runs ALF, bit 1: SlotDev::alfWide -- so that k_alf needs nothing but this record
+  uint8_t grp;                   // which AlfDev of the slot holds the chroma / CC-ALF data of the CTU's slice (vtmgpu_set_alf_slices; else 0)
+  uint8_t pad[5];
 };
 
 struct LadfDev                   // vtmgpu_ladf; n = 0: off (the luma records carry tc / beta)
@@ -97,7 +100,7 @@ struct SlotDev
   const uint32_t* dbfL[2];
   const uint64_t* dbfC[2];
   const SaoDev*   sao;           // [ctus][3]                     (NULL: stage off)
-  const AlfDev*   alf;           //                               (NULL: stage off)
+  const AlfDev*   alf;           // [ALF_MAX_GROUPS]              (NULL: stage off)
   const CtuCtlDev* ctuCtl;       // [ctus]
   const AlfLumaEntry* lumaTab;   // [sets][25 classes][4 transposes]
   int32_t dbfOn, saoOn, alfOn;   // alfOn: parameters set AND the slice enables ALF for at least one component

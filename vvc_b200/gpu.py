@@ -54,6 +54,7 @@ def load_library(path=None):
         "vtmgpu_set_deblock_async": (C.c_int, [ctx, C.c_int, C.POINTER(abi.DeblockParams)]),
         "vtmgpu_set_sao": (C.c_int, [ctx, C.c_int, C.POINTER(abi.SaoParams)]),
         "vtmgpu_set_alf": (C.c_int, [ctx, C.c_int, C.POINTER(abi.AlfParams)]),
+        "vtmgpu_set_alf_slices": (C.c_int, [ctx, C.c_int, C.c_int, C.POINTER(abi.AlfParams), C.POINTER(C.c_uint8)]),
         "vtmgpu_sao_reconstruct": (C.c_int, [C.POINTER(abi.SaoCtu), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
         "vtmgpu_deblock": (C.c_int, [ctx, C.c_int, C.c_int]), "vtmgpu_sao": (C.c_int, [ctx, C.c_int, C.c_int]),
         "vtmgpu_alf": (C.c_int, [ctx, C.c_int, C.c_int]), "vtmgpu_sao_alf": (C.c_int, [ctx, C.c_int, C.c_int]),
@@ -350,6 +351,14 @@ class Context:
 
     def set_alf(self, slot, params):
         self._ck(self.lib.vtmgpu_set_alf(self.h, slot, C.byref(params) if params is not None else None), "set_alf")
+
+    def set_alf_slices(self, slot, slices, ctu_slice):
+        """slices: list of abi.AlfParams, one per slice of the picture (per-picture arrays are read from slices[0]);
+        ctu_slice: uint8 numpy array, slice index per CTU (ALFProcess reloads the APS data at every slice change)."""
+        arr = (abi.AlfParams * len(slices))()
+        for i, q in enumerate(slices):
+            C.memmove(C.byref(arr[i]), C.byref(q), C.sizeof(abi.AlfParams))
+        self._ck(self.lib.vtmgpu_set_alf_slices(self.h, slot, len(slices), arr, ctu_slice.ctypes.data_as(C.POINTER(C.c_uint8))), "set_alf_slices")
 
     def set_capture(self, slot, cap, upload=True, sync=True):
         """Loads one captured picture (planes + all side information) into a slot."""

@@ -61,6 +61,7 @@ struct GpuApi
   decltype(&vtmgpu_set_deblock_sparse) set_deblock_sparse = nullptr;
   decltype(&vtmgpu_set_sao) set_sao = nullptr;
   decltype(&vtmgpu_set_alf) set_alf = nullptr;
+  decltype(&vtmgpu_set_alf_slices) set_alf_slices = nullptr;
   decltype(&vtmgpu_sao_reconstruct) sao_reconstruct = nullptr;
   decltype(&vtmgpu_deblock) deblock = nullptr;
   decltype(&vtmgpu_sao) sao = nullptr;
@@ -77,7 +78,7 @@ struct GpuApi
     if (!so) THROW("vtmgpu shim: cannot load libvtmgpu.so (" << dlerror() << ") -- no CPU fallback");
 #define SYM(n) n = reinterpret_cast<decltype(n)>(dlsym(so, "vtmgpu_" #n)); if (!n) THROW("vtmgpu shim: missing symbol vtmgpu_" #n)
     SYM(abi_version); SYM(last_error); SYM(create); SYM(destroy); SYM(upload); SYM(download); SYM(set_deblock); SYM(set_deblock_sparse); SYM(set_sao);
-    SYM(set_alf); SYM(sao_reconstruct); SYM(deblock); SYM(sao); SYM(alf); SYM(sao_alf); SYM(deblock_sao); SYM(filter);
+    SYM(set_alf); SYM(set_alf_slices); SYM(sao_reconstruct); SYM(deblock); SYM(sao); SYM(alf); SYM(sao_alf); SYM(deblock_sao); SYM(filter);
 #undef SYM
     if (abi_version() != VTMGPU_ABI_VERSION) THROW("vtmgpu shim: ABI version mismatch");
   }
@@ -417,6 +418,8 @@ void AdaptiveLoopFilter::ALFProcess(CodingStructure& cs)
   Shim& s = shim();
   flattenAlf(cs, m_ccAlfFilterParam, m_ccAlfFilterControl, s.alf);
   const vtmgpu_alf_params* p = s.alf.view();
+  const bool perSlice = !s.alf.more.empty();       // slices with different ALF data: not a case the capture format or the reference-encoded streams hold
+  CHECK(perSlice && !s.captureDir.empty(), "vtmgpu shim: the capture format does not cover pictures whose slices carry different ALF parameters");
   if (!s.captureDir.empty())
   {
     const int32_t hdr[8] = { p->enabled[0], p->enabled[1], p->enabled[2], p->num_luma_aps, s.alf.hasChromaAps, p->ccalf_enabled[0], p->ccalf_enabled[1], p->num_ctus };
@@ -437,7 +440,8 @@ void AdaptiveLoopFilter::ALFProcess(CodingStructure& cs)
   }
   else
   {
-    s.check(s.api.set_alf(s.ctx, 0, p), "set_alf");
+    if (perSlice) s.check(s.api.set_alf_slices(s.ctx, 0, 1 + (int)s.alf.more.size(), s.alf.slicesView(), s.alf.ctuSlice.data()), "set_alf_slices");
+    else          s.check(s.api.set_alf(s.ctx, 0, p), "set_alf");
     if (s.dbfPending)      s.check(s.api.filter(s.ctx, 0, 1), "filter");        // whole chain: two kernels, one synchronisation
     else if (s.saoPending) s.check(s.api.sao_alf(s.ctx, 0, 1), "sao_alf");
     else                   s.check(s.api.alf(s.ctx, 0, 1), "alf");

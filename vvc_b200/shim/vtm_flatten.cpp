@@ -97,6 +97,19 @@ const vtmgpu_alf_params* FlatAlf::view()
   return &p;
 }
 
+const vtmgpu_alf_params* FlatAlf::slicesView()
+{
+  sliceViews.assign(1, *view());
+  for (SliceSet& s : more)
+  {
+    s.p.luma_aps   = s.lumaAps.empty() ? nullptr : s.lumaAps.data();
+    s.p.chroma_aps = s.hasChromaAps ? &s.chromaAps : nullptr;
+    s.p.num_ctus   = p.num_ctus;
+    sliceViews.push_back(s.p);
+  }
+  return sliceViews.data();
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // deblocking derivation
 // ---------------------------------------------------------------------------------------------------------
@@ -728,34 +741,108 @@ void writeBackSao(const FlatSao& in, SAOBlkParam* blk)
 // ---------------------------------------------------------------------------------------------------------
 // ALF
 // ---------------------------------------------------------------------------------------------------------
+namespace
+{
+// what one slice signals for ALF: enable flags, the luma APS list, the chroma APS, the CC-ALF enable flags (reconstructCoeffAPSs :620-649)
+void sliceAlf(Slice* sl, vtmgpu_alf_params& p, std::vector<vtmgpu_alf_luma_aps>& lumaAps, vtmgpu_alf_chroma_aps& chromaAps, bool& hasChromaAps)
+{
+  for (int c = 0; c < 3; c++) p.enabled[c] = sl->getTileGroupAlfEnabledFlag(ComponentID(c));
+  for (int c = 0; c < 2; c++) p.ccalf_enabled[c] = sl->m_ccAlfFilterParam.ccAlfFilterEnabled[c];
+  APS** apss = sl->getAlfAPSs();
+  lumaAps.clear();
+  hasChromaAps = false;
+  p.num_luma_aps = 0;
+  if (!(p.enabled[0] || p.enabled[1] || p.enabled[2])) return;
+  const std::vector<int> ids = sl->getTileGroupApsIdLuma();
+  p.num_luma_aps = sl->getTileGroupNumAps();
+  for (int i = 0; i < p.num_luma_aps; i++)
+  {
+    APS* aps = apss[ids[i]];
+    CHECK(aps == nullptr, "invalid APS");
+    const AlfParam& ap = aps->getAlfAPSParam();
+    vtmgpu_alf_luma_aps f{};
+    f.num_filters = ap.numLumaFilters;
+    f.nonlinear = ap.nonLinearFlag[CHANNEL_TYPE_LUMA];
+    for (int k = 0; k < VTMGPU_ALF_CLASSES; k++)
+    {
+      f.delta_idx[k] = ap.filterCoeffDeltaIdx[k];
+      for (int j = 0; j < VTMGPU_ALF_LUMA_COEFF; j++)
+      {
+        f.coeff[k][j]    = ap.lumaCoeff[k * MAX_NUM_ALF_LUMA_COEFF + j];
+        f.clip_idx[k][j] = ap.lumaClipp[k * MAX_NUM_ALF_LUMA_COEFF + j];
+      }
+    }
+    lumaAps.push_back(f);
+  }
+  if (p.enabled[1] || p.enabled[2])
+  {
+    APS* aps = apss[sl->getTileGroupApsIdChroma()];
+    CHECK(aps == nullptr, "invalid chroma APS");
+    const AlfParam& ap = aps->getAlfAPSParam();
+    hasChromaAps = true;
+    chromaAps = vtmgpu_alf_chroma_aps();
+    chromaAps.num_alts = ap.numAlternativesChroma;
+    chromaAps.nonlinear = ap.nonLinearFlag[CHANNEL_TYPE_CHROMA];
+    for (int k = 0; k < VTMGPU_ALF_MAX_ALTS; k++)
+      for (int j = 0; j < VTMGPU_ALF_CHROMA_COEFF; j++)
+      {
+        chromaAps.coeff[k][j]    = ap.chromaCoeff[k][j];
+        chromaAps.clip_idx[k][j] = ap.chromaClipp[k][j];
+      }
+  }
+}
+
+bool sameSliceAlf(const vtmgpu_alf_params& a, const std::vector<vtmgpu_alf_luma_aps>& la, const vtmgpu_alf_chroma_aps& ca, bool hca,
+                  const vtmgpu_alf_params& b, const std::vector<vtmgpu_alf_luma_aps>& lb, const vtmgpu_alf_chroma_aps& cb, bool hcb)
+{
+  if (memcmp(a.enabled, b.enabled, sizeof(a.enabled)) || memcmp(a.ccalf_enabled, b.ccalf_enabled, sizeof(a.ccalf_enabled))) return false;
+  if (la.size() != lb.size() || hca != hcb) return false;
+  if (!la.empty() && memcmp(la.data(), lb.data(), la.size() * sizeof(la[0]))) return false;
+  return !hca || memcmp(&ca, &cb, sizeof(ca)) == 0;
+}
+}   // namespace
+
 void flattenAlf(CodingStructure& cs, const CcAlfFilterParam& cc, uint8_t* const ccControl[2], FlatAlf& out)
 {
   const PreCalcValues& pcv = *cs.pcv;
   const int n = pcv.sizeInCtus;
   out = FlatAlf();
   out.p.num_ctus = n;
-  // single parameter set per picture: every CTU's slice must agree with the first one (ALFProcess reloads the APSs at
-  // every slice change, AdaptiveLoopFilter.cpp:436-441 -- multi-slice pictures with differing ALF data are rejected)
+  // The first slice's parameters go down as the picture's set; every further slice whose ALF data differ (ALFProcess reloads the
+  // APSs at each slice change and tests the CTU's own slice, AdaptiveLoopFilter.cpp:429-441, :451, :532) becomes a further set with
+  // a per-CTU slice index.  The CC-ALF COEFFICIENTS stay per picture: the reference's ALF object holds one copy (DecLib.cpp:589).
   Slice* first = cs.getCU(Position(0, 0), CH_L)->slice;
-  for (int a = 0; a < n; a++)
+  sliceAlf(first, out.p, out.lumaAps, out.chromaAps, out.hasChromaAps);
   {
-    const Position pos((a % pcv.widthInCtus) * pcv.maxCUWidth, (a / pcv.widthInCtus) * pcv.maxCUHeight);
-    Slice* s = cs.getCU(pos, CH_L)->slice;
-    if (s == first) continue;
-    bool same = s->getTileGroupNumAps() == first->getTileGroupNumAps() && s->getTileGroupApsIdLuma() == first->getTileGroupApsIdLuma() &&
-                s->getTileGroupApsIdChroma() == first->getTileGroupApsIdChroma();
-    for (int c = 0; c < 3; c++) same = same && s->getTileGroupAlfEnabledFlag(ComponentID(c)) == first->getTileGroupAlfEnabledFlag(ComponentID(c));
-    // CC-ALF is tested per CTU against the CTU's own slice (AdaptiveLoopFilter.cpp:451,532): its enable flags, APS ids and the
-    // coefficients the slice header resolved must agree too, or the picture would be filtered with another slice's CC-ALF data
-    for (int c = 0; c < 2; c++)
+    std::vector<Slice*> seen(1, first);
+    std::vector<int> setOf(1, 0);                      // slice object -> parameter set (0 = the first slice's)
+    out.ctuSlice.assign(n, 0);
+    for (int a = 0; a < n; a++)
     {
-      same = same && s->m_ccAlfFilterParam.ccAlfFilterEnabled[c] == first->m_ccAlfFilterParam.ccAlfFilterEnabled[c];
-      if (s->m_ccAlfFilterParam.ccAlfFilterEnabled[c])
-        same = same && memcmp(s->m_ccAlfFilterParam.ccAlfCoeff[c], first->m_ccAlfFilterParam.ccAlfCoeff[c], sizeof(first->m_ccAlfFilterParam.ccAlfCoeff[c])) == 0 &&
-               memcmp(s->m_ccAlfFilterParam.ccAlfFilterIdxEnabled[c], first->m_ccAlfFilterParam.ccAlfFilterIdxEnabled[c], sizeof(first->m_ccAlfFilterParam.ccAlfFilterIdxEnabled[c])) == 0;
+      const Position pos((a % pcv.widthInCtus) * pcv.maxCUWidth, (a / pcv.widthInCtus) * pcv.maxCUHeight);
+      Slice* s = cs.getCU(pos, CH_L)->slice;
+      size_t k = 0;
+      while (k < seen.size() && seen[k] != s) k++;
+      if (k == seen.size())
+      {
+        FlatAlf::SliceSet t;
+        sliceAlf(s, t.p, t.lumaAps, t.chromaAps, t.hasChromaAps);
+        int idx = -1;
+        if (sameSliceAlf(out.p, out.lumaAps, out.chromaAps, out.hasChromaAps, t.p, t.lumaAps, t.chromaAps, t.hasChromaAps)) idx = 0;
+        for (size_t m = 0; m < out.more.size() && idx < 0; m++)
+          if (sameSliceAlf(out.more[m].p, out.more[m].lumaAps, out.more[m].chromaAps, out.more[m].hasChromaAps, t.p, t.lumaAps, t.chromaAps, t.hasChromaAps)) idx = (int)m + 1;
+        if (idx < 0)
+        {
+          CHECK(out.more.size() >= 254, "vtmgpu shim: too many slices with different ALF parameters in one picture");
+          out.more.push_back(t);
+          idx = (int)out.more.size();
+        }
+        seen.push_back(s);
+        setOf.push_back(idx);
+      }
+      out.ctuSlice[a] = (uint8_t)setOf[k];
     }
-    same = same && s->getTileGroupCcAlfCbApsId() == first->getTileGroupCcAlfCbApsId() && s->getTileGroupCcAlfCrApsId() == first->getTileGroupCcAlfCrApsId();
-    CHECK(!same, "vtmgpu shim: slices with different ALF parameters in one picture are not supported");
+    if (out.more.empty()) out.ctuSlice.clear();
   }
   cs.slice = cs.getCU(Position(((n - 1) % pcv.widthInCtus) * pcv.maxCUWidth, ((n - 1) / pcv.widthInCtus) * pcv.maxCUHeight), CH_L)->slice;
   // the clip / pad path of ALFProcess (:452-555) is entered when a CTU touches a slice or tile boundary that must not be
@@ -792,55 +879,15 @@ void flattenAlf(CodingStructure& cs, const CcAlfFilterParam& cc, uint8_t* const 
     if (!any) out.ctuClip.clear();
   }
 
-  for (int c = 0; c < 3; c++) out.p.enabled[c] = first->getTileGroupAlfEnabledFlag(ComponentID(c));
-  APS** apss = first->getAlfAPSs();
-  if (out.p.enabled[0] || out.p.enabled[1] || out.p.enabled[2])
-  {
-    const std::vector<int> ids = first->getTileGroupApsIdLuma();
-    out.p.num_luma_aps = first->getTileGroupNumAps();
-    for (int i = 0; i < out.p.num_luma_aps; i++)
-    {
-      APS* aps = apss[ids[i]];
-      CHECK(aps == nullptr, "invalid APS");
-      const AlfParam& ap = aps->getAlfAPSParam();
-      vtmgpu_alf_luma_aps f{};
-      f.num_filters = ap.numLumaFilters;
-      f.nonlinear = ap.nonLinearFlag[CHANNEL_TYPE_LUMA];
-      for (int k = 0; k < VTMGPU_ALF_CLASSES; k++)
-      {
-        f.delta_idx[k] = ap.filterCoeffDeltaIdx[k];
-        for (int j = 0; j < VTMGPU_ALF_LUMA_COEFF; j++)
-        {
-          f.coeff[k][j]    = ap.lumaCoeff[k * MAX_NUM_ALF_LUMA_COEFF + j];
-          f.clip_idx[k][j] = ap.lumaClipp[k * MAX_NUM_ALF_LUMA_COEFF + j];
-        }
-      }
-      out.lumaAps.push_back(f);
-    }
-    if (out.p.enabled[1] || out.p.enabled[2])
-    {
-      APS* aps = apss[first->getTileGroupApsIdChroma()];
-      CHECK(aps == nullptr, "invalid chroma APS");
-      const AlfParam& ap = aps->getAlfAPSParam();
-      out.hasChromaAps = true;
-      out.chromaAps.num_alts = ap.numAlternativesChroma;
-      out.chromaAps.nonlinear = ap.nonLinearFlag[CHANNEL_TYPE_CHROMA];
-      for (int k = 0; k < VTMGPU_ALF_MAX_ALTS; k++)
-        for (int j = 0; j < VTMGPU_ALF_CHROMA_COEFF; j++)
-        {
-          out.chromaAps.coeff[k][j]    = ap.chromaCoeff[k][j];
-          out.chromaAps.clip_idx[k][j] = ap.chromaClipp[k][j];
-        }
-    }
-  }
   for (int c = 0; c < 3; c++) out.ctuEnable[c].assign(cs.picture->getAlfCtuEnableFlag(c), cs.picture->getAlfCtuEnableFlag(c) + n);
   out.filterIdx.assign(cs.picture->getAlfCtbFilterIndex(), cs.picture->getAlfCtbFilterIndex() + n);
   for (int c = 0; c < 2; c++)
   {
     out.ctuAlt[c].assign(cs.picture->getAlfCtuAlternativeData(c + 1), cs.picture->getAlfCtuAlternativeData(c + 1) + n);
-    out.p.ccalf_enabled[c] = first->m_ccAlfFilterParam.ccAlfFilterEnabled[c];
+    bool anyCc = out.p.ccalf_enabled[c] != 0;
+    for (const FlatAlf::SliceSet& t : out.more) anyCc |= t.p.ccalf_enabled[c] != 0;
     out.ccIdc[c].assign(n, 0);
-    if (out.p.ccalf_enabled[c] && ccControl[c]) out.ccIdc[c].assign(ccControl[c], ccControl[c] + n);
+    if (anyCc && ccControl[c]) out.ccIdc[c].assign(ccControl[c], ccControl[c] + n);
     for (int f = 0; f < VTMGPU_CCALF_MAX_FILTERS; f++)
       for (int j = 0; j < VTMGPU_CCALF_COEFF; j++) out.p.ccalf_coeff[c][f][j] = cc.ccAlfCoeff[c][f][j];
   }

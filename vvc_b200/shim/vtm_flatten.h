@@ -60,6 +60,20 @@ struct FlatAlf
   std::vector<uint8_t> ctuClip;      // VTMGPU_ALF_CLIP_* / PAD_* per CTU; empty = no partition boundary restricts the filter
   std::vector<int16_t> filterIdx;
   const vtmgpu_alf_params* view();
+  // slices of the picture whose ALF data differ from the first slice's (ALFProcess reloads the APSs whenever the CTU's slice changes,
+  // AdaptiveLoopFilter.cpp:429-441): `p` describes the first slice, more[k - 1] the k-th further one, ctuSlice the index per CTU.
+  // Empty for pictures whose slices agree (every stream the reference encoder writes) -> the single-set entry point.
+  struct SliceSet
+  {
+    vtmgpu_alf_params p{};
+    std::vector<vtmgpu_alf_luma_aps> lumaAps;
+    vtmgpu_alf_chroma_aps chromaAps{};
+    bool hasChromaAps = false;
+  };
+  std::vector<SliceSet> more;
+  std::vector<uint8_t> ctuSlice;
+  std::vector<vtmgpu_alf_params> sliceViews;       // view() of p followed by the further sets, as vtmgpu_set_alf_slices reads them
+  const vtmgpu_alf_params* slicesView();
 };
 
 // LoopFilter::xDeblockCU (LoopFilter.cpp:261-408) and everything it calls except the sample filters,

@@ -248,3 +248,63 @@ def make_picture(width, height, chroma_format=1, bit_depth=10, ctu_size=128, see
                 clip[a] = f
             sec["alf_clip"] = clip.tobytes()
     return Capture(sec)
+
+
+def make_alf_slices(cap, nslices=3, seed=0, off_slice=None):
+    """A multi-slice ALF description for the picture of `cap` (vtmgpu_set_alf_slices): slice 0 carries the capture's own
+    parameters, slices 1.. freshly drawn ones (other APSs, chroma alternatives, enable flags); off_slice = index of a slice that
+    switches ALF off altogether.  The slices are horizontal runs of CTUs in raster order (cut at random CTUs), the per-CTU arrays of
+    every CTU are drawn for its own slice.  Returns ([abi.AlfParams per slice], ctu_slice uint8[ctus]); the per-picture arrays live
+    in the first element, as the entry point reads them."""
+    import ctypes as C
+    rng = np.random.default_rng(1000 + seed)
+    n = cap.num_ctus
+    cuts = sorted(rng.choice(np.arange(1, n), size=nslices - 1, replace=False).tolist()) if nslices > 1 else []
+    ctu_slice = np.zeros(n, dtype=np.uint8)
+    for k, c0 in enumerate(cuts):
+        ctu_slice[c0:] = k + 1
+    chroma = cap.ncomp == 3
+    secs = [None] + [_alf_sections(rng, n, 0.9, chroma) for _ in range(nslices - 1)]
+    slices, keep = [], []
+    base = cap.alf
+    comb = dict(ctu_enable=[a.copy() for a in base["ctu_enable"]], filter_idx=base["filter_idx"].copy(), ctu_alt=[a.copy() for a in base["ctu_alt"]],
+                cc_idc=[a.copy() for a in base["cc_idc"]])
+    for k in range(nslices):
+        if k == 0:
+            p = cap.alf_params()
+        else:
+            sec = secs[k]
+            hdr = np.frombuffer(sec["alf_hdr"], dtype=np.int32)
+            p = abi.AlfParams()
+            for c in range(3):
+                p.enabled[c] = int(hdr[c])
+            p.num_luma_aps = min(int(hdr[3]), 2 if nslices <= 3 else 1)           # a picture holds at most 8 distinct luma APSs
+            la = (abi.AlfLumaAps * int(hdr[3])).from_buffer_copy(sec["alf_luma_aps"])
+            ca = abi.AlfChromaAps.from_buffer_copy(sec["alf_chroma_aps"])
+            keep += [la, ca]
+            p.luma_aps = C.cast(la, C.POINTER(abi.AlfLumaAps))
+            if chroma:
+                p.chroma_aps = C.pointer(ca)
+            for c in range(2):
+                p.ccalf_enabled[c] = int(hdr[5 + c])
+            p.num_ctus = n
+            m = ctu_slice == k
+            for c in range(3):
+                comb["ctu_enable"][c][m] = np.frombuffer(sec["alf_en%d" % c], dtype=np.uint8)[m]
+            comb["filter_idx"][m] = np.frombuffer(sec["alf_fidx"], dtype=np.int16)[m] % (16 + p.num_luma_aps)
+            for c in range(2):
+                comb["ctu_alt"][c][m] = np.frombuffer(sec["alf_alt%d" % c], dtype=np.uint8)[m]
+                comb["cc_idc"][c][m] = np.frombuffer(sec["alf_ccidc%d" % c], dtype=np.uint8)[m]
+        if off_slice is not None and k == off_slice:
+            for c in range(3):
+                p.enabled[c] = 0
+        slices.append(p)
+    p0 = slices[0]
+    for c in range(3):
+        p0.ctu_enable[c] = comb["ctu_enable"][c].ctypes.data_as(C.POINTER(C.c_uint8))
+    p0.ctu_filter_idx = comb["filter_idx"].ctypes.data_as(C.POINTER(C.c_int16))
+    for c in range(2):
+        p0.ctu_alt[c] = comb["ctu_alt"][c].ctypes.data_as(C.POINTER(C.c_uint8))
+        p0.ccalf_idc[c] = comb["cc_idc"][c].ctypes.data_as(C.POINTER(C.c_uint8))
+    p0._keep2 = (comb, keep)
+    return slices, ctu_slice
