@@ -269,6 +269,10 @@ int vtmgpu_download(vtmgpu_ctx* ctx, int slot, int16_t* const plane[3], const pt
  * asynchronous only from/to page-locked host memory) */
 int vtmgpu_upload_async  (vtmgpu_ctx* ctx, int slot, const int16_t* const plane[3], const ptrdiff_t stride[3]);
 int vtmgpu_download_async(vtmgpu_ctx* ctx, int slot, int16_t* const plane[3], const ptrdiff_t stride[3]);
+/* download + reference-picture border extension (Picture::extendPicBorder, CommonLib/Picture.cpp:737-772, no wrap-around): plane[k]
+ * points at sample (0,0) of a host buffer with at least margin_luma >> (chroma shift) samples of room on every side of the picture;
+ * the picture and its margins (every outside sample = the nearest picture sample) arrive with one copy per plane.  Synchronous. */
+int vtmgpu_download_extended(vtmgpu_ctx* ctx, int slot, int16_t* const plane[3], const ptrdiff_t stride[3], int margin_luma);
 
 /* per-picture side information (host pointers; copied before return, never retained) */
 int vtmgpu_set_deblock(vtmgpu_ctx* ctx, int slot, const vtmgpu_deblock_params* p);   /* NULL = stage off */
@@ -279,6 +283,12 @@ int vtmgpu_set_deblock_async(vtmgpu_ctx* ctx, int slot, const vtmgpu_deblock_par
  * the ctx stream and scattered into the record arrays on the device; page-locked lists must stay valid until vtmgpu_sync,
  * pageable ones may be reused on return */
 int vtmgpu_set_deblock_sparse(vtmgpu_ctx* ctx, int slot, const vtmgpu_deblock_sparse* p);
+/* LMCS inverse luma mapping of the reconstruction (AreaBuf<Pel>::rspSignal with Reshape::getInvLUT(), CommonLib/Buffer.cpp:380-393,
+ * called by DecLib::executeLoopFilters right before loopFilterPic, DecoderLib/DecLib.cpp:570-577): with a table set, the luma plane
+ * uploaded to the slot is the RESHAPED-domain reconstruction and the first stage that reads it (deblocking and / or SAO) maps every
+ * luma sample through inv_lut while it loads its tile -- no separate pass over the picture.  entries = 1 << bit_depth_luma.
+ * NULL = off (the default).  The table stays with the slot until it is replaced or switched off. */
+int vtmgpu_set_lmcs   (vtmgpu_ctx* ctx, int slot, const int16_t* inv_lut, int entries);
 int vtmgpu_set_sao    (vtmgpu_ctx* ctx, int slot, const vtmgpu_sao_params* p);       /* NULL = stage off */
 int vtmgpu_set_alf    (vtmgpu_ctx* ctx, int slot, const vtmgpu_alf_params* p);       /* NULL = stage off */
 /* Pictures whose slices carry DIFFERENT ALF parameters: ALFProcess reloads the APS data whenever the CTU's slice changes

@@ -80,6 +80,10 @@ STREAMS = {
     "ldp_416x240": (416, 240, 420, 4, 67, 14, 32, ["encoder_lowdelay_P_vtm.cfg"], K, 0),
     # full CTC tool set at a size with 128-wide CUs (affine / ATMVP sub-block edges inside large CUs, long filters clamped next to affine)
     "ra_full_832x480": (832, 480, 420, 6, 36, 12, 30, [RA], [], 0),
+    # LMCS with the slice reshaper ON (the SDR analysis of the encoder leaves it off on the synthetic content above; the PQ signal type always
+    # reshapes): executeLoopFilters maps the luma reconstruction through the inverse table before the deblocking (DecLib.cpp:570-577)
+    "lmcs_416x240": (416, 240, 420, 6, 68, 14, 32, [RA], K + ["--LMCSSignalType=1"], 0),
+    "lmcs_full_832x480": (832, 480, 420, 4, 69, 12, 30, [RA], ["--LMCSSignalType=1"], 0),
     # short 4K clip for fast turnaround (first 8 pictures of the config-3 source)
     "ra_2160p_8":   (3840, 2160, 420, 8, 9160, 14, 32, [RA], K, 0),
 }

@@ -87,6 +87,31 @@ def alf(seq, planes, alf_params):
         raise RuntimeError("vvco_alf rc=%d" % rc)
 
 
+def lmcs_inverse(planes, inv_lut):
+    """LMCS inverse mapping of the luma plane, in place: dst[x] = pLUT[src[x]] over the whole plane (AreaBuf<Pel>::rspSignal,
+    CommonLib/Buffer.cpp:380-393, as DecLib::executeLoopFilters calls it before the deblocking, DecLib.cpp:570-577)."""
+    lut = np.asarray(inv_lut, dtype=np.int16)
+    planes[0][...] = lut[planes[0].astype(np.int64)]
+
+
+def extend_border(seq, planes, margin_luma):
+    """Picture::extendPicBorder (CommonLib/Picture.cpp:737-772, no wrap-around): left / right margins replicate the first / last sample
+    of each row, then the first / last padded row is copied upwards / downwards.  Returns the padded planes."""
+    sx, sy = abi.chroma_shifts(seq["chroma_format"])
+    out = []
+    for c, p in enumerate(planes):
+        xm, ym = (margin_luma >> sx, margin_luma >> sy) if c else (margin_luma, margin_luma)
+        h, w = p.shape
+        q = np.empty((h + 2 * ym, w + 2 * xm), dtype=np.int16)
+        q[ym:ym + h, xm:xm + w] = p
+        q[ym:ym + h, :xm] = p[:, :1]
+        q[ym:ym + h, xm + w:] = p[:, -1:]
+        q[:ym, :] = q[ym:ym + 1, :]
+        q[ym + h:, :] = q[ym + h - 1:ym + h, :]
+        out.append(q)
+    return out
+
+
 def alf_slices(seq, planes, slices, ctu_slice):
     """ALF of a picture whose slices carry different parameters, in place.  ALFProcess reloads the APS data whenever the CTU's
     slice changes and reads the slice's own enable flags (AdaptiveLoopFilter.cpp:429-441, :451, :532); the filters read only the

@@ -286,6 +286,7 @@ STREAMS = [("ra_416x240.bin", 8), ("ld444_1080p.bin", 16), ("ra_1080p.bin", 32),
            ("ld422_416x240.bin", 4),      # 4:2:2, full CTC tool set
            ("ctu64_416x240.bin", 4), ("ctu32_416x240.bin", 4), ("bd12_416x240.bin", 3), ("dbfoffs_416x240.bin", 4),   # CTU 64, 12-bit, beta / tc offsets
            ("scc444_416x240.bin", 3), ("ldp_416x240.bin", 4),
+           ("lmcs_416x240.bin", 6),       # LMCS with the slice reshaper on: inverse luma mapping folded into the deblocking kernel's tile load
            ("ra_full_832x480.bin", 6)]    # full CTC tool set at a size with 128-wide CUs   # palette / IBC / BDPCM on screen content (4:4:4); P slices
 
 
@@ -321,7 +322,7 @@ def test_decoder_drop_in_md5(stream, pictures):
     assert r.stdout.count("(OK)") == pictures and "ERROR" not in r.stdout, r.stdout[-2000:]
 
 
-YUV_STREAMS = ["ra_416x240.bin", "ra_1080p.bin", "ld444_1080p.bin", "ra_2160p_8.bin"]      # BASELINE configs 1, 2, 5, 3
+YUV_STREAMS = ["ra_416x240.bin", "ra_1080p.bin", "ld444_1080p.bin", "ra_2160p_8.bin", "lmcs_416x240.bin"]      # BASELINE configs 1, 2, 5, 3
 
 
 @pytest.mark.parametrize("stream", YUV_STREAMS)
@@ -344,3 +345,36 @@ def test_decoder_output_yuv_byte_identical(stream, tmp_path):
     assert r.returncode == 0 and "ERROR" not in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     assert os.path.getsize(ours) > 0 and os.path.getsize(ours) == os.path.getsize(theirs)
     assert filecmp.cmp(ours, theirs, shallow=False), "%s: the GPU decoder's YUV differs from the reference decoder's" % stream
+
+
+@pytest.mark.parametrize("stream,pictures,lmcs", [("lmcs_416x240.bin", 6, True), ("ra_416x240.bin", 8, False), ("ra_1080p.bin", 32, False)])
+def test_decoder_host_passes_on_device(stream, pictures, lmcs):
+    """SURVEY 8f n2 at decoder level.  With the slice reshaper on (lmcs_*: PQ signal type; the encoder's SDR analysis leaves it off on the
+    other synthetic clips) executeLoopFilters maps the luma reconstruction through the inverse table on the host (DecLib.cpp:570-577),
+    and the border of every reference picture is extended on the host (Picture.cpp:737).  In DecoderApp_gpu both happen on the device -- the host mapping is bypassed (k_dbf_sao maps while it loads its
+    tiles) and the margins arrive with the download; the inter-predicted pictures that follow read those margins, so `MD5 (OK)` on
+    every picture covers both.  The shim's counters prove the device paths were the ones that ran; with both switched back to the
+    host the stream decodes to the same MD5s."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dec = os.path.join(root, "vvc_b200", "_bin", "DecoderApp_gpu")
+    if not os.path.exists(dec):
+        pytest.skip("DecoderApp_gpu not built (needs the reference sources at build time)")
+    bits = os.path.join(root, "tests", "golden", "streams", stream)
+
+    def run(**env):
+        r = subprocess.run([dec, "-b", bits, "-d", "0"], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, VTMGPU_SHIM_BACKEND="gpu", VTMGPU_SHIM_TIMING="1", **env))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert r.stdout.count("(OK)") == pictures and "ERROR" not in r.stdout, r.stdout[-2000:]
+        m = re.search(r"lmcs_on_device=(\d+) border_on_device=(\d+)", r.stdout)
+        assert m, r.stdout[-500:]
+        return int(m.group(1)), int(m.group(2)), re.findall(r"\[MD5:[0-9a-f,]+", r.stdout)
+
+    lm, bo, md5 = run()
+    assert lm == (pictures if lmcs else 0), "%s: %d pictures took the device LMCS path" % (stream, lm)
+    assert bo == pictures
+    lm0, bo0, md5_host = run(VTMGPU_SHIM_HOST_LMCS="1", VTMGPU_SHIM_EXTEND="0")
+    assert lm0 == 0 and bo0 == 0 and md5_host == md5

@@ -473,6 +473,24 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
     mbarWait(&bars[stage], (it >> 1) & 1);                   // samples and records of this tile are in shared memory
     pel* sm = reinterpret_cast<pel*>(stageMem);
 
+    if (comp == 0 && srcBuf == 0 && S.lmcsOn)
+    {
+      // LMCS inverse mapping of the reconstruction (AreaBuf<Pel>::rspSignal, Buffer.cpp:380-393, called by executeLoopFilters before
+      // the deblocking, DecLib.cpp:570-577), folded into the tile load: every luma sample of tile + halo goes through the table
+      // (1 << bit depth entries, read through L1).  Samples outside the picture are never used.
+      const uint16_t* __restrict__ lut = reinterpret_cast<const uint16_t*>(S.lmcs);
+      uint4* t = reinterpret_cast<uint4*>(sm);
+      for (int i = tid; i < DBF_SH * (DBF_PITCH / 8); i += DBF_THREADS)
+      {
+        uint4 v = t[i];
+        uint32_t* w = &v.x;
+#pragma unroll
+        for (int k = 0; k < 4; k++) w[k] = (uint32_t)__ldg(&lut[w[k] & 0xffff]) | (uint32_t)__ldg(&lut[w[k] >> 16]) << 16;
+        t[i] = v;
+      }
+      __syncthreads();
+    }
+
     if (doDbf && S.dbfOn)
     {
       const int maxv = (1 << (comp ? g.bdC : g.bdL)) - 1;

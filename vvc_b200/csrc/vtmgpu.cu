@@ -20,6 +20,7 @@
 #include "dbf_kernel.cuh"
 #include "alf_kernel.cuh"
 #include "hash_kernel.cuh"
+#include "border_kernel.cuh"
 #include "vtmgpu.h"
 #include "vvc_alf_fixed_tables.h"
 
@@ -31,7 +32,7 @@ std::string g_createError;
 
 struct SideLayout     // byte offsets inside a slot's side-info block
 {
-  size_t dbfL[2], dbfC[2], dbfEnd, sao, alfTab, ctuCtl, alf, total;
+  size_t dbfL[2], dbfC[2], dbfEnd, sao, lmcs, alfTab, ctuCtl, alf, total;
   size_t nL, nC[2];          // records of the ABI arrays (dense)
   int recW[4], recH[4], recP[4];   // device record arrays lumaV, lumaH, chromaV, chromaH: width, height, row pitch (records; pitch * size is a multiple of 16 B for TMA)
 };
@@ -92,6 +93,8 @@ struct vtmgpu_ctx
   void* bandPeerMem[2][2] = { { nullptr, nullptr }, { nullptr, nullptr } };     // [above / below][planes, flags] as opened (for cudaIpcCloseMemHandle)
   BandDev band{};
   bool bandOn = false, bandCall = false;   // connected ; inside vtmgpu_band_filter_async (only those launches carry the flags)
+  pel* extendBuf = nullptr;              // picture + margins of one slot (vtmgpu_download_extended), allocated by the first call
+  size_t extendElems = 0;
   std::vector<unsigned char*> sparseDev; // per slot, allocated by the first vtmgpu_set_deblock_sparse: landing area of the record lists
   unsigned char* sidePinned = nullptr; // capacity * lay.total
   SlotDev* slotsPinned = nullptr;      // capacity entries (pinned mirror)
@@ -208,6 +211,7 @@ extern "C" void vtmgpu_destroy(vtmgpu_ctx* c)
   if (c->planeAll) cudaFree(c->planeAll);
   if (c->sideAll) cudaFree(c->sideAll);
   for (unsigned char* p : c->sparseDev) if (p) cudaFree(p);
+  if (c->extendBuf) cudaFree(c->extendBuf);
   if (c->sidePinned) cudaFreeHost(c->sidePinned);
   if (c->slotsPinned) cudaFreeHost(c->slotsPinned);
   if (c->slotsDev) cudaFree(c->slotsDev);
@@ -266,8 +270,9 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
   // the per-picture parts (APS filter tables, CTU control, ALF parameters, SAO parameters) are adjacent: one upload per picture
   L.alfTab = off; off = alignUp(off + sizeof(AlfLumaEntry) * VTMGPU_MAX_LUMA_SETS * 25 * 4, 256);
   L.ctuCtl = off; off = alignUp(off + (size_t)c->nCtus * sizeof(CtuCtlDev), 256);
-  L.alf = off;    off = alignUp(off + sizeof(AlfDev) * ALF_MAX_GROUPS, 256);
   L.sao = off;    off = alignUp(off + (size_t)c->nCtus * 3 * sizeof(SaoDev), 256);
+  L.lmcs = off;   off = alignUp(off + sizeof(int16_t) * 4096, 256);            // LMCS inverse table (<= 12 bit)
+  L.alf = off;    off = alignUp(off + sizeof(AlfDev) * ALF_MAX_GROUPS, 256);   // last: a picture uploads only the groups it uses
   L.total = off;
 
 #define CK(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_createError = std::string("vtmgpu_create: ") + what + ": " + cudaGetErrorString(e_); vtmgpu_destroy(c); return -1; } } while (0)
@@ -334,7 +339,8 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
     sd.alf = reinterpret_cast<const AlfDev*>(side + L.alf);
     sd.ctuCtl = reinterpret_cast<const CtuCtlDev*>(side + L.ctuCtl);
     sd.lumaTab = reinterpret_cast<const AlfLumaEntry*>(side + L.alfTab);
-    sd.dbfOn = sd.saoOn = sd.alfOn = 0;
+    sd.lmcs = reinterpret_cast<const int16_t*>(side + L.lmcs);
+    sd.dbfOn = sd.saoOn = sd.alfOn = sd.lmcsOn = 0;
   }
   {
     // TMA descriptors: one per plane buffer; box = the shared-memory tile of k_sao_alf (row pitch incl. padding), zero fill outside
@@ -467,6 +473,67 @@ extern "C" int vtmgpu_upload(vtmgpu_ctx* c, int slot, const int16_t* const plane
 extern "C" int vtmgpu_download(vtmgpu_ctx* c, int slot, int16_t* const plane[3], const ptrdiff_t stride[3])
 {
   return vtmgpu_download_async(c, slot, plane, stride) ? -1 : vtmgpu_sync(c);
+}
+
+extern "C" int vtmgpu_download_extended(vtmgpu_ctx* c, int slot, int16_t* const plane[3], const ptrdiff_t stride[3], int margin_luma)
+{
+  if (!c) return -1;
+  if (!c->slotOk(slot, 1)) return c->fail("download_extended: bad slot %d", slot);
+  if (margin_luma < 16 || margin_luma > 1024 || (margin_luma & 15)) return c->fail("download_extended: margin must be a multiple of 16 in 16..1024");
+  cudaSetDevice(c->seq.device);
+  const Geom& g = c->g;
+  const SlotDev& sd = c->slotsPinned[slot];
+  ExtendArgs a{};
+  a.ncomp = g.ncomp;
+  size_t elems = 0, off[3];
+  int rows = 0, maxGroups = 0;
+  for (int k = 0; k < g.ncomp; k++)
+  {
+    if (!plane[k]) return c->fail("download_extended: plane %d is NULL", k);
+    const PlaneDev& d = sd.buf[c->cur[slot]][k];
+    a.src[k] = d.p; a.w[k] = d.w; a.h[k] = d.h; a.srcPitch[k] = d.pitch;
+    a.xm[k] = margin_luma >> (k ? g.sx : 0); a.ym[k] = margin_luma >> (k ? g.sy : 0);
+    a.dstPitch[k] = (int)alignUp(d.w + 2 * a.xm[k], 8);
+    a.rowStart[k] = rows;
+    rows += d.h + 2 * a.ym[k];
+    maxGroups = std::max(maxGroups, a.dstPitch[k] / 8);
+    off[k] = elems;
+    elems += alignUp((size_t)a.dstPitch[k] * (d.h + 2 * a.ym[k]), 64);
+  }
+  a.rowStart[g.ncomp] = rows;
+  if (elems > c->extendElems)
+  {
+    // picture + margins of one slot, allocated by the first call
+    if (c->extendBuf) { cudaStreamSynchronize(c->stream); cudaFree(c->extendBuf); c->extendBuf = nullptr; c->extendElems = 0; }
+    if (c->cuda(cudaMalloc((void**)&c->extendBuf, elems * sizeof(pel)), "padded picture allocation")) return -1;
+    c->extendElems = elems;
+  }
+  for (int k = 0; k < g.ncomp; k++) a.dst[k] = c->extendBuf + off[k];
+  k_extend_border<<<dim3((maxGroups + 255) / 256, rows), 256, 0, c->stream>>>(a);
+  c->launches++;
+  if (c->cuda(cudaGetLastError(), "k_extend_border launch")) return -1;
+  for (int k = 0; k < g.ncomp; k++)
+    if (c->cuda(cudaMemcpy2DAsync(plane[k] - (ptrdiff_t)a.ym[k] * stride[k] - a.xm[k], (size_t)stride[k] * 2, a.dst[k], (size_t)a.dstPitch[k] * 2,
+                                  (size_t)(a.w[k] + 2 * a.xm[k]) * 2, a.h[k] + 2 * a.ym[k], cudaMemcpyDeviceToHost, c->stream), "download_extended")) return -1;
+  return vtmgpu_sync(c);
+}
+
+extern "C" int vtmgpu_set_lmcs(vtmgpu_ctx* c, int slot, const int16_t* inv_lut, int entries)
+{
+  if (!c) return -1;
+  if (!c->slotOk(slot, 1)) return c->fail("set_lmcs: bad slot %d", slot);
+  cudaSetDevice(c->seq.device);
+  c->mirrorWrite(slot);
+  SlotDev& sd = c->slotsPinned[slot];
+  sd.lmcsOn = 0;
+  if (inv_lut)
+  {
+    if (entries != 1 << c->g.bdL) { c->pushSlot(slot); return c->fail("set_lmcs: expected %d table entries, got %d", 1 << c->g.bdL, entries); }
+    memcpy(c->pinnedSide(slot) + c->lay.lmcs, inv_lut, (size_t)entries * sizeof(int16_t));
+    c->markSide(slot, c->lay.lmcs, (size_t)entries * sizeof(int16_t));
+    sd.lmcsOn = 1;
+  }
+  return c->pushSlot(slot);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1114,7 +1181,8 @@ int setAlf(vtmgpu_ctx* c, int slot, int ns, const vtmgpu_alf_params* slices, con
   sd.alfOn = anyOn;                      // ALFProcess filters nothing otherwise (AdaptiveLoopFilter.cpp:429)
   sd.alfWide = wide;
   if (!sets.empty()) c->markSide(slot, c->lay.alfTab + sizeof(AlfLumaEntry) * VTMGPU_ALF_FIXED_SETS * 100, sizeof(AlfLumaEntry) * 100 * sets.size());
-  c->markSide(slot, c->lay.ctuCtl, (c->lay.alf - c->lay.ctuCtl) + sizeof(AlfDev) * ng);
+  c->markSide(slot, c->lay.ctuCtl, (size_t)c->nCtus * sizeof(CtuCtlDev));
+  c->markSide(slot, c->lay.alf, sizeof(AlfDev) * ng);
   return c->pushSlot(slot);
 }
 }   // namespace
@@ -1219,6 +1287,10 @@ int runStages(vtmgpu_ctx* c, int first, int count, int stages, bool sync, const 
   if (!c->slotOk(first, count)) return c->fail("%s: bad slot range [%d,%d)", what, first, first + count);
   cudaSetDevice(c->seq.device);
   c->stageValid = false;
+  if (!(stages & (ST_DBF | ST_SAO)))
+    for (int sl = first; sl < first + count; sl++)
+      if (c->slotsPinned[sl].lmcsOn && c->cur[sl] == 0)
+        return c->fail("%s: slot %d holds a reshaped-domain picture (vtmgpu_set_lmcs): the inverse mapping is part of the deblocking / SAO pass", what, sl);
   if (c->flush(first, count)) return -1;
   if (c->profiling) cudaEventRecord(c->stageEv[0], c->stream);
   if ((stages & (ST_DBF | ST_SAO)) && launchDbfSao(c, first, count, (stages & ST_DBF) != 0, (stages & ST_SAO) != 0)) return -1;

@@ -103,6 +103,8 @@ struct SlotDev
   const AlfDev*   alf;           // [ALF_MAX_GROUPS]              (NULL: stage off)
   const CtuCtlDev* ctuCtl;       // [ctus]
   const AlfLumaEntry* lumaTab;   // [sets][25 classes][4 transposes]
+  const int16_t* lmcs;           // LMCS inverse table (vtmgpu_set_lmcs)
+  int32_t lmcsOn;                // the luma plane of buffer 0 is in the reshaped domain: the stage that reads it maps it through lmcs
   int32_t dbfOn, saoOn, alfOn;   // alfOn: parameters set AND the slice enables ALF for at least one component
   int32_t alfWide;               // a luma coefficient does not fit the s8 operand of IDP.2A: generic path
   LadfDev ladf;

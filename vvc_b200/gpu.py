@@ -54,6 +54,8 @@ def load_library(path=None):
         "vtmgpu_set_deblock_async": (C.c_int, [ctx, C.c_int, C.POINTER(abi.DeblockParams)]),
         "vtmgpu_set_sao": (C.c_int, [ctx, C.c_int, C.POINTER(abi.SaoParams)]),
         "vtmgpu_set_alf": (C.c_int, [ctx, C.c_int, C.POINTER(abi.AlfParams)]),
+        "vtmgpu_set_lmcs": (C.c_int, [ctx, C.c_int, C.POINTER(C.c_int16), C.c_int]),
+        "vtmgpu_download_extended": (C.c_int, planes_in + [C.c_int]),
         "vtmgpu_set_alf_slices": (C.c_int, [ctx, C.c_int, C.c_int, C.POINTER(abi.AlfParams), C.POINTER(C.c_uint8)]),
         "vtmgpu_sao_reconstruct": (C.c_int, [C.POINTER(abi.SaoCtu), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
         "vtmgpu_deblock": (C.c_int, [ctx, C.c_int, C.c_int]), "vtmgpu_sao": (C.c_int, [ctx, C.c_int, C.c_int]),
@@ -348,6 +350,29 @@ class Context:
             return
         p = abi.SaoParams(C.cast(ctus, C.POINTER(abi.SaoCtu)), len(ctus), C.pointer(vb) if vb is not None else None)
         self._ck(self.lib.vtmgpu_set_sao(self.h, slot, C.byref(p)), "set_sao")
+
+    def set_lmcs(self, slot, inv_lut):
+        """inv_lut: int16 numpy array of 1 << bit_depth_luma entries (Reshape::getInvLUT()), or None = off.  The luma plane uploaded to
+        the slot is then the reshaped-domain reconstruction; the deblocking / SAO pass maps it while it loads its tiles."""
+        if inv_lut is None:
+            self._ck(self.lib.vtmgpu_set_lmcs(self.h, slot, None, 0), "set_lmcs")
+            return
+        lut = np.ascontiguousarray(inv_lut, dtype=np.int16)
+        self._ck(self.lib.vtmgpu_set_lmcs(self.h, slot, lut.ctypes.data_as(C.POINTER(C.c_int16)), len(lut)), "set_lmcs")
+
+    def download_extended(self, slot, margin_luma):
+        """Returns the planes WITH their margins (Picture::extendPicBorder): arrays of (h + 2 ym, w + 2 xm)."""
+        sx, sy = abi.chroma_shifts(self.seq["chroma_format"])
+        out, ptrs, strides = [], abi.PlanePtrs(), abi.Strides()
+        for c in range(self.ncomp):
+            xm, ym = (margin_luma >> sx, margin_luma >> sy) if c else (margin_luma, margin_luma)
+            w, h = (self.seq["width"] >> sx, self.seq["height"] >> sy) if c else (self.seq["width"], self.seq["height"])
+            a = np.full((h + 2 * ym, w + 2 * xm), -1, dtype=np.int16)
+            out.append(a)
+            ptrs[c] = C.cast(a.ctypes.data + 2 * (ym * a.shape[1] + xm), C.POINTER(C.c_int16))
+            strides[c] = a.shape[1]
+        self._ck(self.lib.vtmgpu_download_extended(self.h, slot, ptrs, strides, margin_luma), "download_extended")
+        return out
 
     def set_alf(self, slot, params):
         self._ck(self.lib.vtmgpu_set_alf(self.h, slot, C.byref(params) if params is not None else None), "set_alf")

@@ -62,6 +62,8 @@ struct GpuApi
   decltype(&vtmgpu_set_sao) set_sao = nullptr;
   decltype(&vtmgpu_set_alf) set_alf = nullptr;
   decltype(&vtmgpu_set_alf_slices) set_alf_slices = nullptr;
+  decltype(&vtmgpu_set_lmcs) set_lmcs = nullptr;
+  decltype(&vtmgpu_download_extended) download_extended = nullptr;
   decltype(&vtmgpu_sao_reconstruct) sao_reconstruct = nullptr;
   decltype(&vtmgpu_deblock) deblock = nullptr;
   decltype(&vtmgpu_sao) sao = nullptr;
@@ -78,7 +80,7 @@ struct GpuApi
     if (!so) THROW("vtmgpu shim: cannot load libvtmgpu.so (" << dlerror() << ") -- no CPU fallback");
 #define SYM(n) n = reinterpret_cast<decltype(n)>(dlsym(so, "vtmgpu_" #n)); if (!n) THROW("vtmgpu shim: missing symbol vtmgpu_" #n)
     SYM(abi_version); SYM(last_error); SYM(create); SYM(destroy); SYM(upload); SYM(download); SYM(set_deblock); SYM(set_deblock_sparse); SYM(set_sao);
-    SYM(set_alf); SYM(set_alf_slices); SYM(sao_reconstruct); SYM(deblock); SYM(sao); SYM(alf); SYM(sao_alf); SYM(deblock_sao); SYM(filter);
+    SYM(set_alf); SYM(set_alf_slices); SYM(set_lmcs); SYM(download_extended); SYM(sao_reconstruct); SYM(deblock); SYM(sao); SYM(alf); SYM(sao_alf); SYM(deblock_sao); SYM(filter);
 #undef SYM
     if (abi_version() != VTMGPU_ABI_VERSION) THROW("vtmgpu shim: ABI version mismatch");
   }
@@ -95,6 +97,15 @@ struct Shim
   static constexpr bool useRef = false;
 #endif
   bool staged = false, saoPending = false, dbfPending = false, denseRecords = false;
+  // the two whole-picture host passes either side of the chain move to the device --
+  //   LMCS inverse mapping: the host call is recorded (see AreaBuf<Pel>::rspSignal below) and applied by the deblocking kernel's tile load
+  //   border extension:     the last download of a picture brings the margins along (vtmgpu_download_extended)
+  // Both are off for captures and the reference backend (they see / produce host-side samples), VTMGPU_SHIM_HOST_LMCS=1 / VTMGPU_SHIM_EXTEND=0 switch them off.
+  bool deferLmcs = false, extendOnDevice = false;
+  bool lmcsPending = false, lmcsActive = false;
+  const Pel* lmcsBuf = nullptr;
+  std::vector<Pel> lmcsLut;
+  int lmcsPics = 0, extendedPics = 0, lmcsHostPics = 0;
   bool capturePreOnly = false;   // VTMGPU_CAPTURE_PRE_ONLY=1: captures hold the pre-filter planes and the side information only (a quarter of the size)
   std::string captureDir;
   int picCount = 0;
@@ -119,13 +130,16 @@ struct Shim
     staged = !captureDir.empty() || (getenv("VTMGPU_STAGED") && atoi(getenv("VTMGPU_STAGED")));
     denseRecords = getenv("VTMGPU_DENSE_RECORDS") && atoi(getenv("VTMGPU_DENSE_RECORDS"));
     timing = getenv("VTMGPU_SHIM_TIMING") && atoi(getenv("VTMGPU_SHIM_TIMING"));
+    const bool product = !useRef && captureDir.empty();
+    deferLmcs = product && !(getenv("VTMGPU_SHIM_HOST_LMCS") && atoi(getenv("VTMGPU_SHIM_HOST_LMCS")));
+    extendOnDevice = product && !(getenv("VTMGPU_SHIM_EXTEND") && !atoi(getenv("VTMGPU_SHIM_EXTEND")));
   }
   ~Shim()
   {
     if (timing)
       printf("vtmgpu-shim-timing: pictures=%d luma_pixels=%lld filter_s=%.6f dbf_s=%.6f sao_s=%.6f alf_s=%.6f derive_s=%.6f backend=%s "
-             "record_lists=%d record_bytes=%lld\n", picCount, lumaPixels, stageSec[0] + stageSec[1] + stageSec[2], stageSec[0], stageSec[1], stageSec[2], deriveSec,
-             useRef ? "ref" : "gpu", listPics, recordBytes);
+             "record_lists=%d record_bytes=%lld lmcs_on_device=%d border_on_device=%d lmcs_on_host=%d\n", picCount, lumaPixels, stageSec[0] + stageSec[1] + stageSec[2], stageSec[0], stageSec[1], stageSec[2], deriveSec,
+             useRef ? "ref" : "gpu", listPics, recordBytes, lmcsPics, extendedPics, lmcsHostPics);
     if (ctx) api.destroy(ctx);
   }
 
@@ -160,6 +174,7 @@ struct Shim
     api.load();
     if (ctx) { api.destroy(ctx); ctx = nullptr; }
     if (api.create(&seq, &ctx)) THROW("vtmgpu shim: vtmgpu_create failed: " << api.last_error(nullptr));
+    lmcsActive = false;
   }
 
   static void planes(CodingStructure& cs, int16_t* p[3], ptrdiff_t st[3], int w[3], int h[3])
@@ -174,7 +189,20 @@ struct Shim
     }
   }
   void upload(CodingStructure& cs)   { int16_t* p[3]; ptrdiff_t st[3]; int w[3], h[3]; planes(cs, p, st, w, h); check(api.upload(ctx, 0, p, st), "upload"); }
-  void download(CodingStructure& cs) { int16_t* p[3]; ptrdiff_t st[3]; int w[3], h[3]; planes(cs, p, st, w, h); check(api.download(ctx, 0, p, st), "download"); }
+  // last = the picture is final: its reference-picture margins come along (Picture::extendPicBorder, Picture.cpp:737-772, would otherwise
+  // run on the host when the picture is first used as a reference, Slice.cpp:456); the wrap-around variant stays on the host
+  void download(CodingStructure& cs, bool last)
+  {
+    int16_t* p[3]; ptrdiff_t st[3]; int w[3], h[3];
+    planes(cs, p, st, w, h);
+    if (last && extendOnDevice && !cs.sps->getWrapAroundEnabledFlag() && (cs.picture->margin & 15) == 0 && cs.picture->margin >= 16 && cs.picture->margin <= 1024)
+    {
+      check(api.download_extended(ctx, 0, p, st, (int)cs.picture->margin), "download_extended");
+      cs.picture->setBorderExtension(true);
+      extendedPics++;
+    }
+    else check(api.download(ctx, 0, p, st), "download");
+  }
 
   void capturePlanes(CodingStructure& cs, const char* stage)
   {
@@ -212,6 +240,34 @@ bool lastStage(const CodingStructure& cs, int stage)   // 0 dbf, 1 sao, 2 alf
 }
 
 }   // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// LMCS table mapping of a sample block (declared in Buffer.h, defined in the reference's Buffer.cpp:380-393).  This definition takes
+// the reference's place at link time (the shim objects precede libCommonNoFilters.a, -Wl,--allow-multiple-definition; a maintainer
+// would guard the one call in DecLib.cpp instead).  The decoder calls it per CU with the forward table
+// (DecCu.cpp:698,742,765) -- done here exactly as the reference does -- and ONCE per picture with the inverse table on the whole luma
+// reconstruction right before loopFilterPic (DecLib.cpp:570-577): a block larger than any CU is that call, and the product shim only
+// records it; k_dbf_sao maps the samples while it loads its tiles (vtmgpu_set_lmcs).
+// ---------------------------------------------------------------------------------------------------------
+template<>
+void AreaBuf<Pel>::rspSignal(std::vector<Pel>& pLUT)
+{
+  Shim& s = shim();
+  if (s.deferLmcs && (width > MAX_CU_SIZE || height > MAX_CU_SIZE))
+  {
+    s.lmcsLut = pLUT;
+    s.lmcsBuf = buf;
+    s.lmcsPending = true;
+    return;
+  }
+  if (width > MAX_CU_SIZE || height > MAX_CU_SIZE) s.lmcsHostPics++;
+  const Pel* lut = pLUT.data();
+  for (unsigned y = 0; y < height; y++)
+  {
+    Pel* row = buf + (ptrdiff_t)y * stride;
+    for (unsigned x = 0; x < width; x++) row[x] = lut[row[x]];
+  }
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // SAOOffset / SAOBlkParam (declared in TypeDef.h:938-963, defined in the reference's SampleAdaptiveOffset.cpp)
@@ -259,6 +315,20 @@ void LoopFilter::loopFilterPic(CodingStructure& cs)
   s.ensureCtx(cs);
   s.saoPending = s.dbfPending = false;
   s.lumaPixels += (long long)cs.pcv->lumaWidth * cs.pcv->lumaHeight;
+  if (s.lmcsPending)
+  {
+    // executeLoopFilters asked for the inverse mapping of THIS picture a moment ago (DecLib.cpp:574): the device applies it
+    CHECK(s.lmcsBuf != cs.getRecoBuf().Y().buf, "vtmgpu shim: deferred LMCS mapping belongs to another buffer");
+    s.check(s.api.set_lmcs(s.ctx, 0, s.lmcsLut.data(), (int)s.lmcsLut.size()), "set_lmcs");
+    s.lmcsPending = false;
+    s.lmcsActive = true;
+    s.lmcsPics++;
+  }
+  else if (s.lmcsActive)
+  {
+    s.check(s.api.set_lmcs(s.ctx, 0, nullptr, 0), "set_lmcs");
+    s.lmcsActive = false;
+  }
   // the upload of the reconstruction (a staged copy out of pageable decoder memory) runs beside the host derivation
   std::thread uploader;
   std::exception_ptr uploadError;
@@ -311,7 +381,7 @@ void LoopFilter::loopFilterPic(CodingStructure& cs)
     if (!s.dbfPending)
     {
       s.check(s.api.deblock(s.ctx, 0, 1), "deblock");
-      s.download(cs);
+      s.download(cs, lastStage(cs, 0));
     }
   }
   s.toc(s.stageSec[0]);
@@ -362,7 +432,7 @@ void SampleAdaptiveOffset::SAOProcess(CodingStructure& cs, SAOBlkParam* saoBlkPa
       if (s.dbfPending) s.check(s.api.deblock_sao(s.ctx, 0, 1), "deblock_sao");     // one kernel: deblocking with the SAO epilogue
       else              s.check(s.api.sao(s.ctx, 0, 1), "sao");
       s.dbfPending = false;
-      s.download(cs);
+      s.download(cs, lastStage(cs, 1));
     }
     else
     {
@@ -446,7 +516,7 @@ void AdaptiveLoopFilter::ALFProcess(CodingStructure& cs)
     else if (s.saoPending) s.check(s.api.sao_alf(s.ctx, 0, 1), "sao_alf");
     else                   s.check(s.api.alf(s.ctx, 0, 1), "alf");
     s.saoPending = s.dbfPending = false;
-    s.download(cs);
+    s.download(cs, true);
   }
   s.toc(s.stageSec[2]);
   s.capturePlanes(cs, "alf");
