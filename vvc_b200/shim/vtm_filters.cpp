@@ -130,7 +130,14 @@ struct Shim
     staged = !captureDir.empty() || (getenv("VTMGPU_STAGED") && atoi(getenv("VTMGPU_STAGED")));
     denseRecords = getenv("VTMGPU_DENSE_RECORDS") && atoi(getenv("VTMGPU_DENSE_RECORDS"));
     timing = getenv("VTMGPU_SHIM_TIMING") && atoi(getenv("VTMGPU_SHIM_TIMING"));
+#ifdef VTMGPU_SHIM_ENCODER
+    // encoder-side reuse: only the deblocking of the final reconstruction runs on the device, the encoder's SAO / ALF
+    // parameter searches read the deblocked picture on the host right afterwards (EncGOP.cpp:2794-2830) -> download after the stage
+    staged = true;
+    const bool product = false;
+#else
     const bool product = !useRef && captureDir.empty();
+#endif
     deferLmcs = product && !(getenv("VTMGPU_SHIM_HOST_LMCS") && atoi(getenv("VTMGPU_SHIM_HOST_LMCS")));
     extendOnDevice = product && !(getenv("VTMGPU_SHIM_EXTEND") && !atoi(getenv("VTMGPU_SHIM_EXTEND")));
   }
@@ -249,6 +256,7 @@ bool lastStage(const CodingStructure& cs, int stage)   // 0 dbf, 1 sao, 2 alf
 // reconstruction right before loopFilterPic (DecLib.cpp:570-577): a block larger than any CU is that call, and the product shim only
 // records it; k_dbf_sao maps the samples while it loads its tiles (vtmgpu_set_lmcs).
 // ---------------------------------------------------------------------------------------------------------
+#ifndef VTMGPU_SHIM_ENCODER
 template<>
 void AreaBuf<Pel>::rspSignal(std::vector<Pel>& pLUT)
 {
@@ -297,9 +305,24 @@ const SAOBlkParam& SAOBlkParam::operator=(const SAOBlkParam& src)
   return *this;
 }
 
+#endif   // !VTMGPU_SHIM_ENCODER
+
 // ---------------------------------------------------------------------------------------------------------
 // LoopFilter
 // ---------------------------------------------------------------------------------------------------------
+#ifdef VTMGPU_SHIM_ENCODER
+// Encoder-side reuse (EncGOP.cpp:2794, :3436 call the same LoopFilter::loopFilterPic): the encoder links this object for
+// its LoopFilter and keeps the reference's SampleAdaptiveOffset / AdaptiveLoopFilter objects (its SAO / ALF parameter searches live in
+// classes derived from them).  Besides the five symbols the decoder needs, EncoderLib references three more:
+//   sm_betaTable         read by the encoder's deblocking-parameter heuristics through the inline getBeta() (LoopFilter.h:128)
+//   initEncPicYuvBuffer  per-picture allocation of the buffer of the deblocking-aware RD optimisation (EncGOP.cpp:2761; the buffer is only
+//                        touched with EncDbOpt = 1, off in the CTC configurations): nothing to allocate here
+//   xDeblockCU           called by that optimisation per CU -- it needs filtered samples of a partial picture on the host: refused loudly
+const uint8_t LoopFilter::sm_betaTable[MAX_QP + 1] = { 0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,6,7,8,9,10,11,12,13,14,15,16,17,18,20,22,24,26,28,30,32,34,36,38,40,
+                                                       42,44,46,48,50,52,54,56,58,60,62,64,66,68,70,72,74,76,78,80,82,84,86,88 };
+void LoopFilter::initEncPicYuvBuffer(ChromaFormat, int, int) {}
+void LoopFilter::xDeblockCU(CodingUnit&, const DeblockEdgeDir) { THROW("vtmgpu shim: EncDbOpt (deblocking inside the RD search) is not available with the GPU deblocking filter"); }
+#endif
 LoopFilter::LoopFilter() {}
 LoopFilter::~LoopFilter() {}
 void LoopFilter::create(const unsigned uiMaxCUDepth)
@@ -389,6 +412,7 @@ void LoopFilter::loopFilterPic(CodingStructure& cs)
   if (lastStage(cs, 0)) s.finishPicture(cs, 1);
 }
 
+#ifndef VTMGPU_SHIM_ENCODER
 // ---------------------------------------------------------------------------------------------------------
 // SampleAdaptiveOffset
 // ---------------------------------------------------------------------------------------------------------
@@ -532,3 +556,4 @@ template void AdaptiveLoopFilter::_initAdaptiveLoopFilterX86<SSE41>();
 template void AdaptiveLoopFilter::_initAdaptiveLoopFilterX86<AVX>();
 template void AdaptiveLoopFilter::_initAdaptiveLoopFilterX86<AVX2>();
 #endif
+#endif   // !VTMGPU_SHIM_ENCODER
