@@ -269,6 +269,11 @@ int vtmgpu_download(vtmgpu_ctx* ctx, int slot, int16_t* const plane[3], const pt
  * asynchronous only from/to page-locked host memory) */
 int vtmgpu_upload_async  (vtmgpu_ctx* ctx, int slot, const int16_t* const plane[3], const ptrdiff_t stride[3]);
 int vtmgpu_download_async(vtmgpu_ctx* ctx, int slot, int16_t* const plane[3], const ptrdiff_t stride[3]);
+/* page-locks host memory the caller keeps transferring from / to (the decoder's picture buffers live as long as the sequence): uploads
+ * and downloads then run as plain DMA instead of through the driver's staging buffers.  Thin wrappers over cudaHostRegister /
+ * cudaHostUnregister so that a host program needs no CUDA headers; non-zero = not registered (the transfers still work, staged). */
+int vtmgpu_host_register(void* ptr, size_t bytes);
+int vtmgpu_host_unregister(void* ptr);
 /* download + reference-picture border extension (Picture::extendPicBorder, CommonLib/Picture.cpp:737-772, no wrap-around): plane[k]
  * points at sample (0,0) of a host buffer with at least margin_luma >> (chroma shift) samples of room on every side of the picture;
  * the picture and its margins (every outside sample = the nearest picture sample) arrive with one copy per plane.  Synchronous. */

@@ -475,6 +475,22 @@ extern "C" int vtmgpu_download(vtmgpu_ctx* c, int slot, int16_t* const plane[3],
   return vtmgpu_download_async(c, slot, plane, stride) ? -1 : vtmgpu_sync(c);
 }
 
+extern "C" int vtmgpu_host_register(void* ptr, size_t bytes)
+{
+  if (!ptr || !bytes) return -1;
+  const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess) { cudaGetLastError(); return -1; }
+  return 0;
+}
+
+extern "C" int vtmgpu_host_unregister(void* ptr)
+{
+  if (!ptr) return -1;
+  const cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) { cudaGetLastError(); return -1; }
+  return 0;
+}
+
 extern "C" int vtmgpu_download_extended(vtmgpu_ctx* c, int slot, int16_t* const plane[3], const ptrdiff_t stride[3], int margin_luma)
 {
   if (!c) return -1;

@@ -56,6 +56,8 @@ def load_library(path=None):
         "vtmgpu_set_alf": (C.c_int, [ctx, C.c_int, C.POINTER(abi.AlfParams)]),
         "vtmgpu_set_lmcs": (C.c_int, [ctx, C.c_int, C.POINTER(C.c_int16), C.c_int]),
         "vtmgpu_download_extended": (C.c_int, planes_in + [C.c_int]),
+        "vtmgpu_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+        "vtmgpu_host_unregister": (C.c_int, [C.c_void_p]),
         "vtmgpu_set_alf_slices": (C.c_int, [ctx, C.c_int, C.c_int, C.POINTER(abi.AlfParams), C.POINTER(C.c_uint8)]),
         "vtmgpu_sao_reconstruct": (C.c_int, [C.POINTER(abi.SaoCtu), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
         "vtmgpu_deblock": (C.c_int, [ctx, C.c_int, C.c_int]), "vtmgpu_sao": (C.c_int, [ctx, C.c_int, C.c_int]),

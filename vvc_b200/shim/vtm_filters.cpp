@@ -62,6 +62,8 @@ struct GpuApi
   decltype(&vtmgpu_set_sao) set_sao = nullptr;
   decltype(&vtmgpu_set_alf) set_alf = nullptr;
   decltype(&vtmgpu_set_alf_slices) set_alf_slices = nullptr;
+  decltype(&vtmgpu_host_register) host_register = nullptr;
+  decltype(&vtmgpu_host_unregister) host_unregister = nullptr;
   decltype(&vtmgpu_set_lmcs) set_lmcs = nullptr;
   decltype(&vtmgpu_download_extended) download_extended = nullptr;
   decltype(&vtmgpu_sao_reconstruct) sao_reconstruct = nullptr;
@@ -80,7 +82,7 @@ struct GpuApi
     if (!so) THROW("vtmgpu shim: cannot load libvtmgpu.so (" << dlerror() << ") -- no CPU fallback");
 #define SYM(n) n = reinterpret_cast<decltype(n)>(dlsym(so, "vtmgpu_" #n)); if (!n) THROW("vtmgpu shim: missing symbol vtmgpu_" #n)
     SYM(abi_version); SYM(last_error); SYM(create); SYM(destroy); SYM(upload); SYM(download); SYM(set_deblock); SYM(set_deblock_sparse); SYM(set_sao);
-    SYM(set_alf); SYM(set_alf_slices); SYM(set_lmcs); SYM(download_extended); SYM(sao_reconstruct); SYM(deblock); SYM(sao); SYM(alf); SYM(sao_alf); SYM(deblock_sao); SYM(filter);
+    SYM(set_alf); SYM(set_alf_slices); SYM(set_lmcs); SYM(download_extended); SYM(host_register); SYM(host_unregister); SYM(sao_reconstruct); SYM(deblock); SYM(sao); SYM(alf); SYM(sao_alf); SYM(deblock_sao); SYM(filter);
 #undef SYM
     if (abi_version() != VTMGPU_ABI_VERSION) THROW("vtmgpu shim: ABI version mismatch");
   }
@@ -101,7 +103,7 @@ struct Shim
   //   LMCS inverse mapping: the host call is recorded (see AreaBuf<Pel>::rspSignal below) and applied by the deblocking kernel's tile load
   //   border extension:     the last download of a picture brings the margins along (vtmgpu_download_extended)
   // Both are off for captures and the reference backend (they see / produce host-side samples), VTMGPU_SHIM_HOST_LMCS=1 / VTMGPU_SHIM_EXTEND=0 switch them off.
-  bool deferLmcs = false, extendOnDevice = false;
+  bool deferLmcs = false, extendOnDevice = false, pinOn = true;
   bool lmcsPending = false, lmcsActive = false;
   const Pel* lmcsBuf = nullptr;
   std::vector<Pel> lmcsLut;
@@ -140,14 +142,19 @@ struct Shim
 #endif
     deferLmcs = product && !(getenv("VTMGPU_SHIM_HOST_LMCS") && atoi(getenv("VTMGPU_SHIM_HOST_LMCS")));
     extendOnDevice = product && !(getenv("VTMGPU_SHIM_EXTEND") && !atoi(getenv("VTMGPU_SHIM_EXTEND")));
+    pinOn = !(getenv("VTMGPU_SHIM_PIN") && !atoi(getenv("VTMGPU_SHIM_PIN")));
   }
   ~Shim()
   {
     if (timing)
       printf("vtmgpu-shim-timing: pictures=%d luma_pixels=%lld filter_s=%.6f dbf_s=%.6f sao_s=%.6f alf_s=%.6f derive_s=%.6f backend=%s "
-             "record_lists=%d record_bytes=%lld lmcs_on_device=%d border_on_device=%d lmcs_on_host=%d\n", picCount, lumaPixels, stageSec[0] + stageSec[1] + stageSec[2], stageSec[0], stageSec[1], stageSec[2], deriveSec,
-             useRef ? "ref" : "gpu", listPics, recordBytes, lmcsPics, extendedPics, lmcsHostPics);
-    if (ctx) api.destroy(ctx);
+             "record_lists=%d record_bytes=%lld lmcs_on_device=%d border_on_device=%d lmcs_on_host=%d pinned_planes=%d\n", picCount, lumaPixels, stageSec[0] + stageSec[1] + stageSec[2], stageSec[0], stageSec[1], stageSec[2], deriveSec,
+             useRef ? "ref" : "gpu", listPics, recordBytes, lmcsPics, extendedPics, lmcsHostPics, pinnedPlanes);
+    if (ctx)
+    {
+      for (const auto& e : pinned) if (e.second) api.host_unregister(e.second);
+      api.destroy(ctx);
+    }
   }
 
   // VTMGPU_SHIM_TIMING=1: steady_clock around the backend's stage calls only (for the reference backend that is exactly
@@ -184,7 +191,27 @@ struct Shim
     lmcsActive = false;
   }
 
-  static void planes(CodingStructure& cs, int16_t* p[3], ptrdiff_t st[3], int w[3], int h[3])
+  // The decoder's picture buffers are pageable (PelStorage::create, Buffer.cpp:726) and live as long as the sequence (the DPB recycles
+  // them): each one is page-locked the first time it is transferred (vtmgpu_host_register), so uploads and downloads are plain DMA
+  // instead of two staged copies at a fraction of the PCIe rate.  A buffer that cannot be registered simply stays pageable.
+  // VTMGPU_SHIM_PIN=0 switches this off.
+  std::vector<std::pair<const void*, void*>> pinned;       // (sample (0,0) of a plane, registered base or nullptr)
+  int pinnedPlanes = 0;
+  void pin(const CodingStructure& cs, const Pel* buf, ptrdiff_t stride, int height, int comp)
+  {
+    for (const auto& e : pinned) if (e.first == buf) return;
+    void* base = nullptr;
+    if (pinOn)
+    {
+      const int xm = (int)cs.picture->margin >> getComponentScaleX(ComponentID(comp), cs.pcv->chrFormat), ym = (int)cs.picture->margin >> getComponentScaleY(ComponentID(comp), cs.pcv->chrFormat);
+      // the allocation behind the plane: margins on every side (Picture::create, Picture.cpp:199-206), rows `stride` apart
+      uintptr_t lo = reinterpret_cast<uintptr_t>(buf - (ptrdiff_t)ym * stride - xm), hi = reinterpret_cast<uintptr_t>(buf + (ptrdiff_t)(height + ym - 1) * stride + (stride - xm));
+      lo &= ~uintptr_t(4095); hi = (hi + 4095) & ~uintptr_t(4095);
+      if (api.host_register(reinterpret_cast<void*>(lo), hi - lo) == 0) { base = reinterpret_cast<void*>(lo); pinnedPlanes++; }
+    }
+    pinned.emplace_back(buf, base);
+  }
+  void planes(CodingStructure& cs, int16_t* p[3], ptrdiff_t st[3], int w[3], int h[3])
   {
     PelUnitBuf rec = cs.getRecoBuf();
     for (int c = 0; c < 3; c++)
@@ -193,6 +220,7 @@ struct Shim
       if (c >= (int)getNumberValidComponents(cs.pcv->chrFormat)) continue;
       PelBuf& b = rec.get(ComponentID(c));
       p[c] = b.buf; st[c] = b.stride; w[c] = b.width; h[c] = b.height;
+      if (!useRef && ctx) pin(cs, b.buf, b.stride, b.height, c);
     }
   }
   void upload(CodingStructure& cs)   { int16_t* p[3]; ptrdiff_t st[3]; int w[3], h[3]; planes(cs, p, st, w, h); check(api.upload(ctx, 0, p, st), "upload"); }
