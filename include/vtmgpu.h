@@ -138,6 +138,78 @@ typedef struct vtmgpu_deblock_sparse
   const vtmgpu_ladf* ladf;     /* as in vtmgpu_deblock_params */
 } vtmgpu_deblock_sparse;
 
+/* Third form: the block structure itself, flattened once per picture; the DEVICE then derives the records (edge
+ * maps, filter lengths, boundary strengths, tc / beta of LoopFilter::xDeblockCU .. xGetBoundaryStrengthSingle, LoopFilter.cpp:261-812,
+ * one thread per 4x4 unit and direction; include/vtmgpu_derive.h is the derivation, shared by the kernel and the host-side self check).
+ * All positions in luma samples unless stated.  tu_luma / tu_chroma: for every 4x4 luma unit (raster order, width/4 per row) the index
+ * of the transform unit that CodingStructure::getTU(pos, CHANNEL_TYPE_LUMA / CHROMA) returns for the unit's top-left sample. */
+#define VTMGPU_CU_INTRA     0x0001   /* predMode == MODE_INTRA                                   */
+#define VTMGPU_CU_IBC       0x0002   /* CU::isIBC                                                */
+#define VTMGPU_CU_PLT       0x0004   /* CU::isPLT                                                */
+#define VTMGPU_CU_AFFINE    0x0008
+#define VTMGPU_CU_MVSUB     0x0010   /* affine or SbTMVP merge: sub-block edges every 8 samples  */
+#define VTMGPU_CU_BDPCM     0x0020
+#define VTMGPU_CU_BDPCM_C   0x0040
+#define VTMGPU_CU_CIIP      0x0080
+#define VTMGPU_CU_ISP       0x0100
+#define VTMGPU_CU_HAS_LUMA  0x0400   /* blocks[COMPONENT_Y].valid()                              */
+#define VTMGPU_CU_HAS_CHROMA 0x0800  /* blocks[COMPONENT_Cb].valid()                             */
+#define VTMGPU_CU_EN_LEFT   0x1000   /* xSetLoopfilterParam (LoopFilter.cpp:656-672): left CU edge, top CU edge, internal edges */
+#define VTMGPU_CU_EN_TOP    0x2000
+#define VTMGPU_CU_EN_INT    0x4000
+typedef struct vtmgpu_dbf_cu
+{
+  uint16_t x, y;          /* area of the CU (a chroma-only CU: its chroma block scaled to luma samples) */
+  uint8_t  w4, h4;        /* size in units of 4 luma samples                                          */
+  int8_t   qp;            /* CodingUnit::qp                                                            */
+  uint8_t  slice;         /* index into slices[]                                                       */
+  uint16_t tile;          /* CodingUnit::tileIdx                                                       */
+  uint16_t flags;         /* VTMGPU_CU_*                                                               */
+  uint32_t reserved;
+} vtmgpu_dbf_cu;
+#define VTMGPU_TU_CBF_Y   1
+#define VTMGPU_TU_CBF_CB  2
+#define VTMGPU_TU_CBF_CR  4
+#define VTMGPU_TU_JOINT   8
+typedef struct vtmgpu_dbf_tu
+{
+  uint16_t x, y;          /* luma block; w = 0: the TU has none                                        */
+  uint8_t  w, h;          /* in samples (ISP sub-partitions may be 1 or 2 samples wide)                */
+  uint8_t  cw, ch;        /* chroma block size in chroma samples; cw = 0: the TU has none              */
+  uint16_t cx, cy;        /* chroma block position in chroma samples                                   */
+  uint8_t  cbf;           /* VTMGPU_TU_*                                                               */
+  int8_t   qp_cb, qp_cr;  /* QpParam(tu, comp).Qp(0) - qpBdOffset (LoopFilter.cpp:1213-1217)           */
+  uint8_t  reserved;
+  uint32_t cu;            /* index into cus[]                                                          */
+} vtmgpu_dbf_tu;
+typedef struct vtmgpu_dbf_slice
+{
+  int8_t  tc_offset, beta_offset;      /* getDeblockingFilterTcOffsetDiv2() * 2, ...BetaOffsetDiv2() * 2 */
+  uint8_t inter_b;                     /* isInterB()                                                      */
+  uint8_t reserved;
+  uint16_t independent_idx;            /* getIndependentSliceIdx() (CU::isSameSlice)                      */
+  int16_t ref_pic[2][16];              /* [list][refIdx] -> picture id (any numbering that identifies the Picture object) */
+} vtmgpu_dbf_slice;
+#define VTMGPU_UNITS_ACROSS_SLICES 1   /* PPS loop_filter_across_slices_enabled_flag */
+#define VTMGPU_UNITS_ACROSS_TILES  2
+#define VTMGPU_UNITS_PLT           4   /* SPS getPLTMode() */
+typedef struct vtmgpu_deblock_units
+{
+  int32_t num_cus, num_tus, num_slices, flags;
+  const vtmgpu_dbf_cu*    cus;
+  const vtmgpu_dbf_tu*    tus;
+  const vtmgpu_dbf_slice* slices;
+  const uint32_t* tu_luma;       /* [units] */
+  const uint32_t* tu_chroma;     /* [units]; NULL for 4:0:0 */
+  /* the picture's motion field at 4x4 granularity as the decoder keeps it (MotionInfo, MotionInfo.h:101): base address, bytes per
+   * element, elements per row, and the byte offsets of mv[0].hor (ver follows), mv[1].hor, refIdx[0], refIdx[1] (int16).  NULL for
+   * pictures without inter CUs. */
+  const void* motion;
+  int32_t motion_elem_bytes, motion_pitch, off_mv0, off_mv1, off_ref0, off_ref1;
+  const vtmgpu_ladf* ladf;                    /* as in vtmgpu_deblock_params */
+  const struct vtmgpu_virtual_boundaries* vb; /* edges on a signalled virtual boundary are not filtered (xDeriveEdgefilterParam) */
+} vtmgpu_deblock_units;
+
 /* ---------------------------------------------------------------------------------------------
  * SAO (SAOOffset / SAOBlkParam, TypeDef.h:938-963; enums :706-748)
  * --------------------------------------------------------------------------------------------- */
@@ -288,6 +360,11 @@ int vtmgpu_set_deblock_async(vtmgpu_ctx* ctx, int slot, const vtmgpu_deblock_par
  * the ctx stream and scattered into the record arrays on the device; page-locked lists must stay valid until vtmgpu_sync,
  * pageable ones may be reused on return */
 int vtmgpu_set_deblock_sparse(vtmgpu_ctx* ctx, int slot, const vtmgpu_deblock_sparse* p);
+/* the block structure; the tables and maps are read by asynchronous copies on the ctx stream (page-locked memory must stay valid until
+ * vtmgpu_sync, pageable memory may be reused on return) and k_dbf_derive writes the record arrays on the device */
+int vtmgpu_set_deblock_units(vtmgpu_ctx* ctx, int slot, const vtmgpu_deblock_units* p);
+/* test hook: the record arrays of a slot as the device holds them, laid out like the arrays of vtmgpu_deblock_params; the caller allocates them */
+int vtmgpu_get_deblock_records(vtmgpu_ctx* ctx, int slot, uint32_t* const luma[2], uint64_t* const chroma[2]);
 /* LMCS inverse luma mapping of the reconstruction (AreaBuf<Pel>::rspSignal with Reshape::getInvLUT(), CommonLib/Buffer.cpp:380-393,
  * called by DecLib::executeLoopFilters right before loopFilterPic, DecoderLib/DecLib.cpp:570-577): with a table set, the luma plane
  * uploaded to the slot is the RESHAPED-domain reconstruction and the first stage that reads it (deblocking and / or SAO) maps every

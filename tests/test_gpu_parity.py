@@ -378,3 +378,25 @@ def test_decoder_host_passes_on_device(stream, pictures, lmcs):
     assert bo == pictures
     lm0, bo0, md5_host = run(VTMGPU_SHIM_HOST_LMCS="1", VTMGPU_SHIM_EXTEND="0")
     assert lm0 == 0 and bo0 == 0 and md5_host == md5
+
+
+@pytest.mark.parametrize("stream,pictures", STREAMS)
+def test_decoder_device_derivation(stream, pictures):
+    """with VTMGPU_SHIM_DEVICE_DERIVE=1 the shim sends the flattened block structure (CUs, TUs, unit maps, slices, the motion
+    field) and k_dbf_derive produces the deblocking records on the device.  VTMGPU_SHIM_CHECK_UNITS=1 makes the shim run the CU walk as
+    well and compare, for every picture, (a) the derivation source run on the host and (b) the records the KERNEL wrote
+    (vtmgpu_get_deblock_records) with the walk's arrays -- byte-identical -- and every picture must still decode to `MD5 (OK)`."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dec = os.path.join(root, "vvc_b200", "_bin", "DecoderApp_gpu")
+    if not os.path.exists(dec):
+        pytest.skip("DecoderApp_gpu not built (needs the reference sources at build time)")
+    r = subprocess.run([dec, "-b", os.path.join(root, "tests", "golden", "streams", stream), "-d", "0"], capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, VTMGPU_SHIM_BACKEND="gpu", VTMGPU_SHIM_DEVICE_DERIVE="1", VTMGPU_SHIM_CHECK_UNITS="1", VTMGPU_SHIM_TIMING="1"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("(OK)") == pictures and "ERROR" not in r.stdout, r.stdout[-2000:]
+    m = re.search(r"device_derived=(\d+) walk_derived_instead=(\d+) units_checked=(\d+) kernel_records_checked=(\d+)", r.stdout)
+    assert m, r.stdout[-500:]
+    assert [int(v) for v in m.groups()] == [pictures, 0, pictures, pictures]

@@ -22,6 +22,7 @@
 #include "hash_kernel.cuh"
 #include "border_kernel.cuh"
 #include "vtmgpu.h"
+#include "vtmgpu_derive.h"
 #include "vvc_alf_fixed_tables.h"
 
 using namespace vtmgpu;
@@ -93,6 +94,8 @@ struct vtmgpu_ctx
   void* bandPeerMem[2][2] = { { nullptr, nullptr }, { nullptr, nullptr } };     // [above / below][planes, flags] as opened (for cudaIpcCloseMemHandle)
   BandDev band{};
   bool bandOn = false, bandCall = false;   // connected ; inside vtmgpu_band_filter_async (only those launches carry the flags)
+  std::vector<unsigned char*> unitsDev;  // per slot, allocated by the first vtmgpu_set_deblock_units: landing area of the block structure
+  std::vector<size_t> unitsBytes;
   pel* extendBuf = nullptr;              // picture + margins of one slot (vtmgpu_download_extended), allocated by the first call
   size_t extendElems = 0;
   std::vector<unsigned char*> sparseDev; // per slot, allocated by the first vtmgpu_set_deblock_sparse: landing area of the record lists
@@ -212,6 +215,7 @@ extern "C" void vtmgpu_destroy(vtmgpu_ctx* c)
   if (c->sideAll) cudaFree(c->sideAll);
   for (unsigned char* p : c->sparseDev) if (p) cudaFree(p);
   if (c->extendBuf) cudaFree(c->extendBuf);
+  for (unsigned char* p : c->unitsDev) if (p) cudaFree(p);
   if (c->sidePinned) cudaFreeHost(c->sidePinned);
   if (c->slotsPinned) cudaFreeHost(c->slotsPinned);
   if (c->slotsDev) cudaFree(c->slotsDev);
@@ -795,6 +799,127 @@ __global__ void __launch_bounds__(256) k_dbf_scatter(ScatterArgs A)
     if (a < 2) reinterpret_cast<uint32_t*>(A.dense[a])[o] = (uint32_t)rec;
     else       reinterpret_cast<uint64_t*>(A.dense[a])[o] = rec;
   }
+}
+
+// Device-side derivation of the deblocking records: one thread per 4x4 unit and edge direction evaluates
+// include/vtmgpu_derive.h on the flattened block structure and stores the unit's luma record and, where the unit sits on the chroma
+// edge grid, the chroma record -- every position of the four record arrays is written, no clearing pass.
+struct DeriveArgs
+{
+  vtmgpu_derive::Ctx D;
+  uint32_t* luma[2];
+  uint64_t* chroma[2];
+  int recP[4];
+};
+
+__global__ void __launch_bounds__(256) k_dbf_derive(const DeriveArgs A)
+{
+  vtmgpu_derive::Ctx D = A.D;
+  D.tcTable = kDbfTcTable;
+  D.betaTable = kDbfBetaTable;
+  const int n = D.w4 * D.h4, t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * n) return;
+  const int dir = t >= n, u = t - dir * n, y = u / D.w4, x = u - y * D.w4;
+  uint32_t lr; uint64_t cr; bool slot;
+  vtmgpu_derive::deriveUnit(D, x, y, dir, lr, cr, slot);
+  A.luma[dir][(size_t)y * A.recP[dir] + x] = lr;
+  if (slot)
+  {
+    if (dir == 0) A.chroma[0][(size_t)y * A.recP[2] + ((4 * x) >> (3 + D.sx))] = cr;
+    else          A.chroma[1][(size_t)((4 * y) >> (3 + D.sy)) * A.recP[3] + x] = cr;
+  }
+}
+
+extern "C" int vtmgpu_set_deblock_units(vtmgpu_ctx* c, int slot, const vtmgpu_deblock_units* p)
+{
+  if (!c) return -1;
+  if (!c->slotOk(slot, 1)) return c->fail("set_deblock_units: bad slot %d", slot);
+  if (!p) return setDeblock(c, slot, nullptr, false);
+  const Geom& g = c->g;
+  const size_t units = (size_t)(g.w / 4) * (g.h / 4);
+  if (p->num_cus < 1 || p->num_tus < 1 || p->num_slices < 1 || p->num_slices > 255 || !p->cus || !p->tus || !p->slices || !p->tu_luma) return c->fail("set_deblock_units: missing tables");
+  if (g.ncomp > 1 && !p->tu_chroma) return c->fail("set_deblock_units: tu_chroma is NULL");
+  if (p->motion && (p->motion_elem_bytes < 20 || p->motion_pitch < g.w / 4 || (p->motion_elem_bytes & 3) || ((p->off_mv0 | p->off_mv1) & 3) || ((p->off_ref0 | p->off_ref1) & 1) ||
+                    p->off_mv0 < 0 || p->off_mv1 < 0 || p->off_ref0 < 0 || p->off_ref1 < 0 ||
+                    p->off_mv0 + 8 > p->motion_elem_bytes || p->off_mv1 + 8 > p->motion_elem_bytes || p->off_ref0 + 2 > p->motion_elem_bytes || p->off_ref1 + 2 > p->motion_elem_bytes))
+    return c->fail("set_deblock_units: bad motion field layout");
+  if (p->vb && (p->vb->num_ver < 0 || p->vb->num_ver > 3 || p->vb->num_hor < 0 || p->vb->num_hor > 3)) return c->fail("set_deblock_units: bad virtual boundaries");
+  cudaSetDevice(c->seq.device);
+  c->mirrorWrite(slot);
+  SlotDev& sd = c->slotsPinned[slot];
+  sd.dbfOn = 1;
+  if (setLadf(c, slot, p->ladf)) { sd.dbfOn = 0; c->pushSlot(slot); return -1; }
+  // landing area of the tables on the device (per slot, grown on demand)
+  const size_t szCu = alignUp(sizeof(vtmgpu_dbf_cu) * p->num_cus, 256), szTu = alignUp(sizeof(vtmgpu_dbf_tu) * p->num_tus, 256), szSl = alignUp(sizeof(vtmgpu_dbf_slice) * p->num_slices, 256);
+  const size_t szMap = alignUp(units * 4, 256), szMi = p->motion ? alignUp(units * p->motion_elem_bytes, 256) : 0;
+  const size_t need = szCu + szTu + szSl + szMap * (g.ncomp > 1 ? 2 : 1) + szMi;
+  if (c->unitsDev.empty()) { c->unitsDev.assign(c->seq.capacity, nullptr); c->unitsBytes.assign(c->seq.capacity, 0); }
+  if (need > c->unitsBytes[slot])
+  {
+    if (c->unitsDev[slot]) { cudaStreamSynchronize(c->stream); cudaFree(c->unitsDev[slot]); c->unitsDev[slot] = nullptr; c->unitsBytes[slot] = 0; }
+    const size_t cap = need + need / 4;
+    if (c->cuda(cudaMalloc(&c->unitsDev[slot], cap), "block structure allocation")) { sd.dbfOn = 0; c->pushSlot(slot); return -1; }
+    c->unitsBytes[slot] = cap;
+  }
+  unsigned char* d = c->unitsDev[slot];
+  DeriveArgs A{};
+  vtmgpu_derive::Ctx& D = A.D;
+  size_t o = 0;
+#define UP(dst, src, bytes) do { if (c->cuda(cudaMemcpyAsync(d + o, src, bytes, cudaMemcpyHostToDevice, c->stream), "set_deblock_units")) { sd.dbfOn = 0; c->pushSlot(slot); return -1; } dst = reinterpret_cast<decltype(dst)>(d + o); } while (0)
+  UP(D.cus, p->cus, sizeof(vtmgpu_dbf_cu) * p->num_cus); o += szCu;
+  UP(D.tus, p->tus, sizeof(vtmgpu_dbf_tu) * p->num_tus); o += szTu;
+  UP(D.slices, p->slices, sizeof(vtmgpu_dbf_slice) * p->num_slices); o += szSl;
+  UP(D.tuL, p->tu_luma, units * 4); o += szMap;
+  if (g.ncomp > 1) { UP(D.tuC, p->tu_chroma, units * 4); o += szMap; }
+#undef UP
+  if (p->motion)
+  {
+    // rows of the motion field, without the pitch padding
+    if (c->cuda(cudaMemcpy2DAsync(d + o, (size_t)(g.w / 4) * p->motion_elem_bytes, p->motion, (size_t)p->motion_pitch * p->motion_elem_bytes, (size_t)(g.w / 4) * p->motion_elem_bytes, g.h / 4,
+                                  cudaMemcpyHostToDevice, c->stream), "set_deblock_units")) { sd.dbfOn = 0; c->pushSlot(slot); return -1; }
+    D.motion = d + o;
+    D.miBytes = p->motion_elem_bytes; D.miPitch = g.w / 4;
+    D.offMv0 = p->off_mv0; D.offMv1 = p->off_mv1; D.offRef0 = p->off_ref0; D.offRef1 = p->off_ref1;
+  }
+  D.w4 = g.w / 4; D.h4 = g.h / 4; D.sx = g.sx; D.sy = g.sy; D.chroma = g.ncomp > 1;
+  D.bdL = g.bdL; D.bdC = g.bdC; D.ctuLog2 = g.ctuLog2;
+  D.flags = p->flags;
+  D.ladf = p->ladf != nullptr;
+  if (p->vb)
+  {
+    D.nvb[0] = p->vb->num_ver; D.nvb[1] = p->vb->num_hor;
+    for (int i = 0; i < 3; i++) { D.vb[0][i] = p->vb->pos_x[i]; D.vb[1][i] = p->vb->pos_y[i]; }
+  }
+  const SideLayout& L = c->lay;
+  for (int a = 0; a < 2; a++)
+  {
+    A.luma[a] = reinterpret_cast<uint32_t*>(c->sideDev[slot] + L.dbfL[a]);
+    A.chroma[a] = reinterpret_cast<uint64_t*>(c->sideDev[slot] + L.dbfC[a]);
+  }
+  for (int a = 0; a < 4; a++) A.recP[a] = L.recP[a];
+  const int threads = 2 * (int)units;
+  k_dbf_derive<<<(threads + 255) / 256, 256, 0, c->stream>>>(A);
+  c->launches++;
+  if (c->cuda(cudaGetLastError(), "k_dbf_derive launch")) { sd.dbfOn = 0; c->pushSlot(slot); return -1; }
+  return c->pushSlot(slot);
+}
+
+extern "C" int vtmgpu_get_deblock_records(vtmgpu_ctx* c, int slot, uint32_t* const luma[2], uint64_t* const chroma[2])
+{
+  if (!c) return -1;
+  if (!c->slotOk(slot, 1)) return c->fail("get_deblock_records: bad slot %d", slot);
+  cudaSetDevice(c->seq.device);
+  const SideLayout& L = c->lay;
+  for (int a = 0; a < 4; a++)
+  {
+    if (!L.recW[a]) continue;
+    const int d = a & 1, es = a < 2 ? 4 : 8;
+    void* dst = a < 2 ? (void*)luma[d] : (void*)chroma[d];
+    if (!dst) return c->fail("get_deblock_records: NULL array");
+    const size_t off = a < 2 ? L.dbfL[d] : L.dbfC[d];
+    if (c->cuda(cudaMemcpy2DAsync(dst, (size_t)L.recW[a] * es, c->sideDev[slot] + off, (size_t)L.recP[a] * es, (size_t)L.recW[a] * es, L.recH[a], cudaMemcpyDeviceToHost, c->stream), "get_deblock_records")) return -1;
+  }
+  return vtmgpu_sync(c);
 }
 
 extern "C" int vtmgpu_set_deblock_sparse(vtmgpu_ctx* c, int slot, const vtmgpu_deblock_sparse* p)

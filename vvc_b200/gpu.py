@@ -64,6 +64,8 @@ def load_library(path=None):
         "vtmgpu_alf": (C.c_int, [ctx, C.c_int, C.c_int]), "vtmgpu_sao_alf": (C.c_int, [ctx, C.c_int, C.c_int]),
         "vtmgpu_deblock_sao": (C.c_int, [ctx, C.c_int, C.c_int]),
         "vtmgpu_set_deblock_sparse": (C.c_int, [ctx, C.c_int, C.POINTER(abi.DeblockSparse)]),
+        "vtmgpu_set_deblock_units": (C.c_int, [ctx, C.c_int, C.c_void_p]),
+        "vtmgpu_get_deblock_records": (C.c_int, [ctx, C.c_int, C.POINTER(C.c_void_p * 2), C.POINTER(C.c_void_p * 2)]),
         "vtmgpu_filter": (C.c_int, [ctx, C.c_int, C.c_int]), "vtmgpu_filter_async": (C.c_int, [ctx, C.c_int, C.c_int]),
         "vtmgpu_sync": (C.c_int, [ctx]), "vtmgpu_timer_start": (C.c_int, [ctx]),
         "vtmgpu_timer_stop": (C.c_int, [ctx, C.POINTER(C.c_float)]),

@@ -59,6 +59,9 @@ struct GpuApi
   decltype(&vtmgpu_download) download = nullptr;
   decltype(&vtmgpu_set_deblock) set_deblock = nullptr;
   decltype(&vtmgpu_set_deblock_sparse) set_deblock_sparse = nullptr;
+  decltype(&vtmgpu_set_deblock_units) set_deblock_units = nullptr;
+  decltype(&vtmgpu_get_deblock_records) get_deblock_records = nullptr;
+  decltype(&vtmgpu_sync) sync = nullptr;
   decltype(&vtmgpu_set_sao) set_sao = nullptr;
   decltype(&vtmgpu_set_alf) set_alf = nullptr;
   decltype(&vtmgpu_set_alf_slices) set_alf_slices = nullptr;
@@ -81,7 +84,7 @@ struct GpuApi
     so = dlopen(path ? path : "libvtmgpu.so", RTLD_NOW | RTLD_LOCAL);
     if (!so) THROW("vtmgpu shim: cannot load libvtmgpu.so (" << dlerror() << ") -- no CPU fallback");
 #define SYM(n) n = reinterpret_cast<decltype(n)>(dlsym(so, "vtmgpu_" #n)); if (!n) THROW("vtmgpu shim: missing symbol vtmgpu_" #n)
-    SYM(abi_version); SYM(last_error); SYM(create); SYM(destroy); SYM(upload); SYM(download); SYM(set_deblock); SYM(set_deblock_sparse); SYM(set_sao);
+    SYM(abi_version); SYM(last_error); SYM(create); SYM(destroy); SYM(upload); SYM(download); SYM(set_deblock); SYM(set_deblock_sparse); SYM(set_deblock_units); SYM(get_deblock_records); SYM(sync); SYM(set_sao);
     SYM(set_alf); SYM(set_alf_slices); SYM(set_lmcs); SYM(download_extended); SYM(host_register); SYM(host_unregister); SYM(sao_reconstruct); SYM(deblock); SYM(sao); SYM(alf); SYM(sao_alf); SYM(deblock_sao); SYM(filter);
 #undef SYM
     if (abi_version() != VTMGPU_ABI_VERSION) THROW("vtmgpu shim: ABI version mismatch");
@@ -112,7 +115,14 @@ struct Shim
   std::string captureDir;
   int picCount = 0;
   // per-picture
-  FlatDeblock dbf;
+  FlatDeblock dbf, dbfFromUnits;
+  FlatUnits units;
+  // VTMGPU_SHIM_DEVICE_DERIVE=1 -- the block structure goes down (flattenUnits) and the DEVICE derives the deblocking records;
+  // VTMGPU_SHIM_CHECK_UNITS=1 -- self check: the CU walk and the unit derivation (the kernel's own source run on the host, and with a device
+  // the kernel's output) must produce identical records for every picture
+  bool deviceDerive = false, checkUnits = false;
+  int unitPics = 0, unitFallbackPics = 0, checkedPics = 0, deviceCheckedPics = 0;
+  double flattenSec = 0;
   FlatSao sao;
   FlatAlf alf;
   CaptureWriter cap;
@@ -143,16 +153,18 @@ struct Shim
     deferLmcs = product && !(getenv("VTMGPU_SHIM_HOST_LMCS") && atoi(getenv("VTMGPU_SHIM_HOST_LMCS")));
     extendOnDevice = product && !(getenv("VTMGPU_SHIM_EXTEND") && !atoi(getenv("VTMGPU_SHIM_EXTEND")));
     pinOn = !(getenv("VTMGPU_SHIM_PIN") && !atoi(getenv("VTMGPU_SHIM_PIN")));
+    deviceDerive = !useRef && getenv("VTMGPU_SHIM_DEVICE_DERIVE") && atoi(getenv("VTMGPU_SHIM_DEVICE_DERIVE"));
+    checkUnits = getenv("VTMGPU_SHIM_CHECK_UNITS") && atoi(getenv("VTMGPU_SHIM_CHECK_UNITS"));
   }
   ~Shim()
   {
     if (timing)
       printf("vtmgpu-shim-timing: pictures=%d luma_pixels=%lld filter_s=%.6f dbf_s=%.6f sao_s=%.6f alf_s=%.6f derive_s=%.6f backend=%s "
-             "record_lists=%d record_bytes=%lld lmcs_on_device=%d border_on_device=%d lmcs_on_host=%d pinned_planes=%d\n", picCount, lumaPixels, stageSec[0] + stageSec[1] + stageSec[2], stageSec[0], stageSec[1], stageSec[2], deriveSec,
-             useRef ? "ref" : "gpu", listPics, recordBytes, lmcsPics, extendedPics, lmcsHostPics, pinnedPlanes);
+             "record_lists=%d record_bytes=%lld lmcs_on_device=%d border_on_device=%d lmcs_on_host=%d pinned_planes=%d device_derived=%d walk_derived_instead=%d units_checked=%d kernel_records_checked=%d flatten_s=%.6f\n", picCount, lumaPixels, stageSec[0] + stageSec[1] + stageSec[2], stageSec[0], stageSec[1], stageSec[2], deriveSec,
+             useRef ? "ref" : "gpu", listPics, recordBytes, lmcsPics, extendedPics, lmcsHostPics, pinnedPlanes, unitPics, unitFallbackPics, checkedPics, deviceCheckedPics, flattenSec);
     if (ctx)
     {
-      for (const auto& e : pinned) if (e.second) api.host_unregister(e.second);
+      for (const Range& r : ranges) if (r.live) api.host_unregister(reinterpret_cast<void*>(r.lo));
       api.destroy(ctx);
     }
   }
@@ -195,21 +207,61 @@ struct Shim
   // them): each one is page-locked the first time it is transferred (vtmgpu_host_register), so uploads and downloads are plain DMA
   // instead of two staged copies at a fraction of the PCIe rate.  A buffer that cannot be registered simply stays pageable.
   // VTMGPU_SHIM_PIN=0 switches this off.
-  std::vector<std::pair<const void*, void*>> pinned;       // (sample (0,0) of a plane, registered base or nullptr)
+  struct Range { uintptr_t lo, hi; bool live; };       // page-aligned; live = registered, else given up (stays pageable)
+  std::vector<Range> ranges;
+  std::vector<const void*> seenPlanes;
   int pinnedPlanes = 0;
   void pin(const CodingStructure& cs, const Pel* buf, ptrdiff_t stride, int height, int comp)
   {
-    for (const auto& e : pinned) if (e.first == buf) return;
-    void* base = nullptr;
-    if (pinOn)
+    for (const void* e : seenPlanes) if (e == buf) return;
+    seenPlanes.push_back(buf);
+    if (!pinOn) return;
+    const int xm = (int)cs.picture->margin >> getComponentScaleX(ComponentID(comp), cs.pcv->chrFormat), ym = (int)cs.picture->margin >> getComponentScaleY(ComponentID(comp), cs.pcv->chrFormat);
+    // the allocation behind the plane: margins on every side (Picture::create, Picture.cpp:199-206), rows `stride` apart
+    pinRange(reinterpret_cast<uintptr_t>(buf - (ptrdiff_t)ym * stride - xm), reinterpret_cast<uintptr_t>(buf + (ptrdiff_t)(height + ym - 1) * stride + (stride - xm)));
+  }
+  void pinOnce(const void* p, size_t bytes)           // other long-lived host buffers the shim transfers from (motion fields, the block-structure tables)
+  {
+    for (const void* e : seenPlanes) if (e == p) return;
+    seenPlanes.push_back(p);
+    if (pinOn) pinRange(reinterpret_cast<uintptr_t>(p), reinterpret_cast<uintptr_t>(p) + bytes);
+  }
+  void unpin(const void* p)
+  {
+    for (size_t i = 0; i < seenPlanes.size(); i++) if (seenPlanes[i] == p) { seenPlanes.erase(seenPlanes.begin() + i); break; }
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p) & ~uintptr_t(4095);
+    for (size_t i = 0; i < ranges.size(); i++)
+      if (ranges[i].lo == a) { if (ranges[i].live) api.host_unregister(reinterpret_cast<void*>(a)); ranges.erase(ranges.begin() + i); break; }
+  }
+  void pinRange(uintptr_t lo, uintptr_t hi)
+  {
+    lo &= ~uintptr_t(4095); hi = (hi + 4095) & ~uintptr_t(4095);
+    // Small pictures come from the heap and neighbouring allocations share pages: a page cannot be registered twice, and a transfer whose
+    // host range is only partly page-locked is refused by the driver -- so ranges that touch are merged into one registration, and a
+    // range that cannot be registered is remembered and left alone (its planes stay pageable as a whole).
+    for (;;)
     {
-      const int xm = (int)cs.picture->margin >> getComponentScaleX(ComponentID(comp), cs.pcv->chrFormat), ym = (int)cs.picture->margin >> getComponentScaleY(ComponentID(comp), cs.pcv->chrFormat);
-      // the allocation behind the plane: margins on every side (Picture::create, Picture.cpp:199-206), rows `stride` apart
-      uintptr_t lo = reinterpret_cast<uintptr_t>(buf - (ptrdiff_t)ym * stride - xm), hi = reinterpret_cast<uintptr_t>(buf + (ptrdiff_t)(height + ym - 1) * stride + (stride - xm));
-      lo &= ~uintptr_t(4095); hi = (hi + 4095) & ~uintptr_t(4095);
-      if (api.host_register(reinterpret_cast<void*>(lo), hi - lo) == 0) { base = reinterpret_cast<void*>(lo); pinnedPlanes++; }
+      bool merged = false;
+      for (size_t i = 0; i < ranges.size(); i++)
+      {
+        Range& r = ranges[i];
+        if (r.lo <= lo && hi <= r.hi) { if (r.live) pinnedPlanes++; return; }          // already covered (or given up)
+        if (r.lo < hi && lo < r.hi)
+        {
+          if (r.live) api.host_unregister(reinterpret_cast<void*>(r.lo));
+          lo = std::min(lo, r.lo); hi = std::max(hi, r.hi);
+          const bool wasDead = !r.live;
+          ranges.erase(ranges.begin() + i);
+          if (wasDead) { ranges.push_back(Range{ lo, hi, false }); return; }
+          merged = true;
+          break;
+        }
+      }
+      if (!merged) break;
     }
-    pinned.emplace_back(buf, base);
+    const bool ok = api.host_register(reinterpret_cast<void*>(lo), hi - lo) == 0;
+    ranges.push_back(Range{ lo, hi, ok });
+    if (ok) pinnedPlanes++;
   }
   void planes(CodingStructure& cs, int16_t* p[3], ptrdiff_t st[3], int w[3], int h[3])
   {
@@ -384,13 +436,52 @@ void LoopFilter::loopFilterPic(CodingStructure& cs)
   std::thread uploader;
   std::exception_ptr uploadError;
   if (!s.useRef) uploader = std::thread([&] { try { s.upload(cs); } catch (...) { uploadError = std::current_exception(); } });
-  if (!s.useRef || !s.captureDir.empty() || !s.timing)   // the reference backend derives its own parameters; skip ours when only timing it
+  bool useUnits = false;
+  try
   {
-    s.tic();
-    try { deriveDeblockRecords(cs, s.dbf); }
-    catch (...) { if (uploader.joinable()) uploader.join(); throw; }
-    s.toc(s.deriveSec);
+    if (s.deviceDerive || s.checkUnits)
+    {
+      s.tic();
+      const size_t unitsNow = (size_t)(cs.pcv->lumaWidth / 4) * (cs.pcv->lumaHeight / 4);
+      if (s.units.block && s.units.units != unitsNow && !s.useRef) s.unpin(s.units.block);      // the tables are about to be reallocated
+      flattenUnits(cs, s.units);
+      s.toc(s.flattenSec);
+      if (s.deviceDerive && s.ctx)
+      {
+        if (s.units.blockIsNew) s.pinOnce(s.units.block, s.units.blockBytes);
+        if (s.units.p.motion) s.pinOnce(s.units.p.motion, (size_t)s.units.p.motion_pitch * (cs.pcv->lumaHeight / 4) * s.units.p.motion_elem_bytes);
+      }
+      useUnits = s.deviceDerive && s.units.supported;
+      if (s.deviceDerive) (useUnits ? s.unitPics : s.unitFallbackPics)++;
+    }
+    if ((!useUnits || s.checkUnits) && (!s.useRef || !s.captureDir.empty() || !s.timing || s.checkUnits))   // the reference backend derives its own parameters; skip ours when only timing it
+    {
+      s.tic();
+      deriveDeblockRecords(cs, s.dbf);
+      s.toc(s.deriveSec);
+    }
+    if (s.checkUnits && s.units.supported)
+    {
+      // the unit derivation (the kernel's source, run here on the host) against the CU walk, record by record
+      deriveFromUnits(s.units, cs.pcv->lumaWidth, cs.pcv->lumaHeight, (int)cs.pcv->chrFormat, cs.sps->getBitDepth(CHANNEL_TYPE_LUMA), cs.sps->getBitDepth(CHANNEL_TYPE_CHROMA),
+                      cs.pcv->maxCUWidth, s.dbfFromUnits);
+      for (int d = 0; d < 2; d++)
+      {
+        for (size_t i = 0; i < s.dbf.luma[d].size(); i++)
+          if (s.dbf.luma[d][i] != s.dbfFromUnits.luma[d][i])
+            THROW("vtmgpu shim: unit derivation differs from the CU walk: POC " << cs.slice->getPOC() << " luma dir " << d << " unit (" << (i % (cs.pcv->lumaWidth / 4)) << "," << (i / (cs.pcv->lumaWidth / 4))
+                  << ") walk " << s.dbf.luma[d][i] << " units " << s.dbfFromUnits.luma[d][i] << " | tuQ " << s.units.tus[s.units.tuLuma[i]].x << "," << s.units.tus[s.units.tuLuma[i]].y << " "
+                  << (int)s.units.tus[s.units.tuLuma[i]].w << "x" << (int)s.units.tus[s.units.tuLuma[i]].h << " cu " << s.units.cus[s.units.tus[s.units.tuLuma[i]].cu].x << "," << s.units.cus[s.units.tus[s.units.tuLuma[i]].cu].y
+                  << " " << (int)s.units.cus[s.units.tus[s.units.tuLuma[i]].cu].w4 << "x" << (int)s.units.cus[s.units.tus[s.units.tuLuma[i]].cu].h4 << " flags " << s.units.cus[s.units.tus[s.units.tuLuma[i]].cu].flags);
+        for (size_t i = 0; i < s.dbf.chroma[d].size(); i++)
+          if (s.dbf.chroma[d][i] != s.dbfFromUnits.chroma[d][i])
+            THROW("vtmgpu shim: unit derivation differs from the CU walk: POC " << cs.slice->getPOC() << " chroma dir " << d << " index " << i
+                  << " walk " << s.dbf.chroma[d][i] << " units " << s.dbfFromUnits.chroma[d][i]);
+      }
+      s.checkedPics++;
+    }
   }
+  catch (...) { if (uploader.joinable()) uploader.join(); throw; }
   if (uploader.joinable()) uploader.join();
   if (uploadError) std::rethrow_exception(uploadError);
   if (!s.captureDir.empty())
@@ -413,7 +504,30 @@ void LoopFilter::loopFilterPic(CodingStructure& cs)
   }
   else
   {
-    if (s.dbf.listsValid && !s.denseRecords)
+    if (useUnits)
+    {
+      // the block structure goes down and k_dbf_derive writes the records; the motion field is read before setRefinedMotionField
+      // changes it (DecLib.cpp:579-580): the copies are complete when this call returns
+      s.check(s.api.set_deblock_units(s.ctx, 0, s.units.view()), "set_deblock_units");
+      s.check(s.api.sync(s.ctx), "sync");
+      if (s.checkUnits)
+      {
+        // the kernel's records against the CU walk's
+        FlatDeblock& k = s.dbfFromUnits;
+        uint32_t* l[2] = { k.luma[0].data(), k.luma[1].data() };
+        uint64_t* cch[2] = { k.chroma[0].empty() ? nullptr : k.chroma[0].data(), k.chroma[1].empty() ? nullptr : k.chroma[1].data() };
+        for (int d = 0; d < 2; d++) { std::fill(k.luma[d].begin(), k.luma[d].end(), 0xffffffffu); std::fill(k.chroma[d].begin(), k.chroma[d].end(), ~0ull); }
+        s.check(s.api.get_deblock_records(s.ctx, 0, l, cch), "get_deblock_records");
+        for (int d = 0; d < 2; d++)
+        {
+          // (records on the picture border are never filtered; the CU walk leaves them zero as well)
+          CHECK(k.luma[d] != s.dbf.luma[d], "vtmgpu shim: k_dbf_derive differs from the CU walk (luma records, POC " << cs.slice->getPOC() << ")");
+          CHECK(k.chroma[d] != s.dbf.chroma[d], "vtmgpu shim: k_dbf_derive differs from the CU walk (chroma records, POC " << cs.slice->getPOC() << ")");
+        }
+        s.deviceCheckedPics++;
+      }
+    }
+    else if (s.dbf.listsValid && !s.denseRecords)
     {
       const vtmgpu_deblock_sparse p = s.dbf.sparseView();      // only the active units cross the bus
       s.listPics++;

@@ -15,6 +15,8 @@
 #include <algorithm>
 #include <cstring>
 
+#include "vtmgpu_derive.h"
+
 #include "CodingStructure.h"
 #include "Picture.h"
 #include "Quant.h"
@@ -679,6 +681,289 @@ void deriveDeblockRecords(CodingStructure& cs, FlatDeblock& out)
 {
   Deriver d(cs, out);
   d.run();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// block structure for the device-side derivation
+// ---------------------------------------------------------------------------------------------------------
+FlatUnits::~FlatUnits() { free(block); }
+
+const vtmgpu_deblock_units* FlatUnits::view()
+{
+  p.num_cus = (int)numCus; p.num_tus = (int)numTus; p.num_slices = (int)slices.size();
+  p.cus = cus; p.tus = tus; p.slices = slices.data();
+  p.tu_luma = tuLuma;
+  p.tu_chroma = tuChroma;
+  p.ladf = hasLadf ? &ladf : nullptr;
+  p.vb = (vb.num_ver || vb.num_hor) ? &vb : nullptr;
+  return &p;
+}
+
+namespace
+{
+// the CTUs are handed out to a few host threads (they only read the coding structure; every CTU writes its own CUs / TUs -- reserved with
+// one atomic add per CTU -- and its own part of the unit maps)
+struct UnitFlattener
+{
+  CodingStructure& cs;
+  const PreCalcValues& pcv;
+  FlatUnits& out;
+  int sx, sy, w4, h4;
+  bool chroma, dual;
+  std::vector<const Slice*> sliceOf;
+  std::atomic<size_t> nCus{ 0 }, nTus{ 0 };
+  std::atomic<int> nextCtu{ 0 };
+  std::atomic<bool> unsupported{ false }, anyInter{ false };
+  UnitFlattener(CodingStructure& c, FlatUnits& o)
+    : cs(c), pcv(*c.pcv), out(o), sx((int)getComponentScaleX(COMPONENT_Cb, c.pcv->chrFormat)), sy((int)getComponentScaleY(COMPONENT_Cb, c.pcv->chrFormat)),
+      w4((int)c.pcv->lumaWidth / 4), h4((int)c.pcv->lumaHeight / 4), chroma(c.pcv->chrFormat != CHROMA_400), dual(CS::isDualITree(c)) {}
+
+  void addSlice(const Slice* s, std::vector<const Picture*>& pics)
+  {
+    vtmgpu_dbf_slice d{};
+    d.tc_offset = (int8_t)(s->getDeblockingFilterTcOffsetDiv2() * 2);
+    d.beta_offset = (int8_t)(s->getDeblockingFilterBetaOffsetDiv2() * 2);
+    d.inter_b = s->isInterB();
+    d.independent_idx = (uint16_t)s->getIndependentSliceIdx();
+    for (int l = 0; l < 2; l++)
+      for (int r = 0; r < 16; r++)
+      {
+        d.ref_pic[l][r] = -1;
+        if (s->isIntra() || r >= s->getNumRefIdx(RefPicList(l))) continue;
+        const Picture* pic = s->getRefPic(RefPicList(l), r);
+        size_t k = 0;
+        while (k < pics.size() && pics[k] != pic) k++;
+        if (k == pics.size()) pics.push_back(pic);
+        d.ref_pic[l][r] = (int16_t)k;
+      }
+    sliceOf.push_back(s);
+    out.slices.push_back(d);
+  }
+  int sliceIndex(const Slice* s) const
+  {
+    for (size_t i = 0; i < sliceOf.size(); i++) if (sliceOf[i] == s) return (int)i;
+    THROW("vtmgpu shim: a CU refers to a slice that is not in the picture's slice list");
+  }
+
+  void fill(uint32_t* map, int x, int y, int w, int h, uint32_t id) const      // luma sample rectangle -> 4x4 units
+  {
+    // a unit belongs to the block that contains its top-left sample (what getTU(pos) of that sample returns; ISP sub-partitions can be narrower than a unit)
+    const int x0 = (x + 3) >> 2, y0 = (y + 3) >> 2, x1 = std::min(w4, (x + w + 3) >> 2), y1 = std::min(h4, (y + h + 3) >> 2);
+    for (int yy = y0; yy < y1; yy++) std::fill(map + (size_t)yy * w4 + x0, map + (size_t)yy * w4 + x1, id);
+  }
+
+  void addCU(const CodingUnit& cu, size_t& cuAt, size_t& tuAt)
+  {
+    const bool hasLuma = cu.Y().valid(), hasChroma = chroma && cu.blocks.size() > 1 && cu.blocks[COMPONENT_Cb].valid();
+    const Area area = hasLuma ? Area(cu.Y())
+                              : Area(recalcPosition(cu.chromaFormat, cu.chType, CHANNEL_TYPE_LUMA, cu.blocks[cu.chType].pos()),
+                                     recalcSize(cu.chromaFormat, cu.chType, CHANNEL_TYPE_LUMA, cu.blocks[cu.chType].size()));
+    vtmgpu_dbf_cu c{};
+    c.x = (uint16_t)area.x; c.y = (uint16_t)area.y; c.w4 = (uint8_t)(area.width / 4); c.h4 = (uint8_t)(area.height / 4);
+    c.qp = cu.qp;
+    c.slice = (uint8_t)sliceIndex(cu.slice);
+    c.tile = (uint16_t)cu.tileIdx;
+    unsigned f = 0;
+    if (cu.predMode == MODE_INTRA) f |= VTMGPU_CU_INTRA; else anyInter = true;
+    if (CU::isIBC(cu)) f |= VTMGPU_CU_IBC;
+    if (CU::isPLT(cu)) f |= VTMGPU_CU_PLT;
+    if (cu.affine) f |= VTMGPU_CU_AFFINE;
+    if (cu.bdpcmMode) f |= VTMGPU_CU_BDPCM;
+    if (cu.bdpcmModeChroma) f |= VTMGPU_CU_BDPCM_C;
+    if (cu.firstPU->ciipFlag) f |= VTMGPU_CU_CIIP;
+    if (cu.ispMode) f |= VTMGPU_CU_ISP;
+    if (hasLuma) f |= VTMGPU_CU_HAS_LUMA;
+    if (hasChroma) f |= VTMGPU_CU_HAS_CHROMA;
+    // the unit model describes CUs with one prediction unit that covers the CU (all VVC prediction modes); anything else takes the CU walk
+    const PredictionUnit& pu = *cu.firstPU;
+    if ((pu.mergeFlag && pu.mergeType == MRG_TYPE_SUBPU_ATMVP) || cu.affine) f |= VTMGPU_CU_MVSUB;
+    if (pu.next && pu.next->cu == &cu) unsupported = true;
+    if (pu.blocks[cu.chType].pos() != cu.blocks[cu.chType].pos() || pu.blocks[cu.chType].size() != cu.blocks[cu.chType].size()) unsupported = true;
+    // xSetLoopfilterParam (LoopFilter.cpp:656-672)
+    if (!cu.slice->getDeblockingFilterDisable())
+    {
+      const Position& pos = cu.blocks[cu.chType].pos();
+      const PPS& pps = *cu.cs->pps;
+      f |= VTMGPU_CU_EN_INT;
+      if (pos.x > 0 && usable(cu, *cu.cs->getCU(pos.offset(-1, 0), cu.chType), pps)) f |= VTMGPU_CU_EN_LEFT;
+      if (pos.y > 0 && usable(cu, *cu.cs->getCU(pos.offset(0, -1), cu.chType), pps)) f |= VTMGPU_CU_EN_TOP;
+    }
+    c.flags = (uint16_t)f;
+    const uint32_t cuId = (uint32_t)cuAt;
+    out.cus[cuAt++] = c;
+    for (auto& tu : CU::traverseTUs(cu))
+    {
+      vtmgpu_dbf_tu t{};
+      t.cu = cuId;
+      const uint32_t tuId = (uint32_t)tuAt;
+      if (tu.blocks[COMPONENT_Y].valid())
+      {
+        const CompArea& b = tu.blocks[COMPONENT_Y];
+        t.x = (uint16_t)b.x; t.y = (uint16_t)b.y; t.w = (uint8_t)b.width; t.h = (uint8_t)b.height;
+        fill(out.tuLuma, b.x, b.y, b.width, b.height, tuId);
+      }
+      if (chroma && tu.blocks.size() > 1 && tu.blocks[COMPONENT_Cb].valid())
+      {
+        const CompArea& b = tu.blocks[COMPONENT_Cb];
+        t.cx = (uint16_t)b.x; t.cy = (uint16_t)b.y; t.cw = (uint8_t)b.width; t.ch = (uint8_t)b.height;
+        fill(out.tuChroma, b.x << sx, b.y << sy, b.width << sx, b.height << sy, tuId);
+      }
+      if (TU::getCbf(tu, COMPONENT_Y)) t.cbf |= VTMGPU_TU_CBF_Y;
+      if (chroma)
+      {
+        if (TU::getCbf(tu, COMPONENT_Cb)) t.cbf |= VTMGPU_TU_CBF_CB;
+        if (TU::getCbf(tu, COMPONENT_Cr)) t.cbf |= VTMGPU_TU_CBF_CR;
+        if (tu.jointCbCr) t.cbf |= VTMGPU_TU_JOINT;
+        // chroma QPs as xEdgeFilterChroma takes them (LoopFilter.cpp:1213-1217)
+        const int bdOff = tu.cs->sps->getQpBDOffset(CHANNEL_TYPE_CHROMA);
+        t.qp_cb = (int8_t)(QpParam(tu, COMPONENT_Cb, -MAX_INT, false).Qp(0) - bdOff);
+        t.qp_cr = (int8_t)(QpParam(tu, COMPONENT_Cr, -MAX_INT, false).Qp(0) - bdOff);
+      }
+      out.tus[tuAt++] = t;
+    }
+  }
+
+  void ctu(int a)
+  {
+    const int cx = a % (int)pcv.widthInCtus, cy = a / (int)pcv.widthInCtus;
+    const UnitArea ctuArea(pcv.chrFormat, Area(cx << pcv.maxCUWidthLog2, cy << pcv.maxCUHeightLog2, pcv.maxCUWidth, pcv.maxCUWidth));
+    // count, reserve, fill
+    size_t ncu = 0, ntu = 0;
+    for (int tree = 0; tree < (dual ? 2 : 1); tree++)
+      for (auto& cu : cs.traverseCUs(CS::getArea(cs, ctuArea, tree ? CH_C : CH_L), tree ? CH_C : CH_L))
+      {
+        ncu++;
+        for (auto& tu : CU::traverseTUs(cu)) { (void)tu; ntu++; }
+      }
+    size_t cuAt = nCus.fetch_add(ncu), tuAt = nTus.fetch_add(ntu);
+    if (cuAt + ncu > out.capCus || tuAt + ntu > out.capTus) { unsupported = true; return; }
+    for (int tree = 0; tree < (dual ? 2 : 1); tree++)
+      for (auto& cu : cs.traverseCUs(CS::getArea(cs, ctuArea, tree ? CH_C : CH_L), tree ? CH_C : CH_L)) addCU(cu, cuAt, tuAt);
+  }
+
+  void work()
+  {
+    const int n = (int)pcv.sizeInCtus;
+    for (int a; (a = nextCtu.fetch_add(1, std::memory_order_relaxed)) < n;) ctu(a);
+  }
+};
+}   // namespace
+
+void flattenUnits(CodingStructure& cs, FlatUnits& out)
+{
+  const PreCalcValues& pcv = *cs.pcv;
+  CHECK(pcv.maxCUWidth > 128 || pcv.minCUWidth != 4 || pcv.minCUHeight != 4, "vtmgpu shim: unsupported CTU / min CU size");
+  const bool chroma = pcv.chrFormat != CHROMA_400;
+  const size_t units = (size_t)(pcv.lumaWidth / 4) * (pcv.lumaHeight / 4);
+  out.blockIsNew = false;
+  if (units != out.units || !out.block)
+  {
+    // capacities: a picture rarely has more CUs / TUs than a third of its units; a picture that does takes the CU walk
+    free(out.block);
+    out.units = units;
+    out.capCus = out.capTus = units;
+    const size_t a = (sizeof(vtmgpu_dbf_cu) * out.capCus + 4095) & ~size_t(4095), b = (sizeof(vtmgpu_dbf_tu) * out.capTus + 4095) & ~size_t(4095), m = (units * 4 + 4095) & ~size_t(4095);
+    out.blockBytes = a + b + 2 * m;
+    out.block = nullptr;
+    CHECK(posix_memalign(&out.block, 4096, out.blockBytes) != 0, "vtmgpu shim: out of memory");
+    unsigned char* p = static_cast<unsigned char*>(out.block);
+    out.cus = reinterpret_cast<vtmgpu_dbf_cu*>(p);
+    out.tus = reinterpret_cast<vtmgpu_dbf_tu*>(p + a);
+    out.tuLuma = reinterpret_cast<uint32_t*>(p + a + b);
+    out.tuChroma = reinterpret_cast<uint32_t*>(p + a + b + m);
+    out.blockIsNew = true;
+  }
+  out.slices.clear();
+  out.supported = true;
+  out.vb = flattenVirtualBoundaries(cs);
+  out.hasLadf = cs.sps->getLadfEnabled();
+  if (out.hasLadf)
+  {
+    out.ladf = vtmgpu_ladf{};
+    out.ladf.num_intervals = cs.sps->getLadfNumIntervals();
+    for (int k = 0; k < out.ladf.num_intervals && k < 5; k++)
+    {
+      out.ladf.qp_offset[k] = cs.sps->getLadfQpOffset(k);
+      out.ladf.lower_bound[k] = cs.sps->getLadfIntervalLowerBound(k);
+    }
+  }
+  UnitFlattener F(cs, out);
+  {
+    std::vector<const Picture*> pics;
+    CHECK(cs.picture->slices.size() > 255, "vtmgpu shim: more than 255 slices in a picture");
+    for (const Slice* s : cs.picture->slices) F.addSlice(s, pics);
+  }
+  int nThreads = 1;
+  if (const char* e = getenv("VTMGPU_SHIM_THREADS")) nThreads = atoi(e);
+  else nThreads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+  nThreads = std::max(1, std::min(nThreads, (int)pcv.sizeInCtus));
+  if (nThreads == 1) F.work();
+  else
+  {
+    std::vector<std::thread> pool;
+    std::vector<std::exception_ptr> err(nThreads);
+    for (int t = 0; t < nThreads; t++) pool.emplace_back([&F, &err, t] { try { F.work(); } catch (...) { err[t] = std::current_exception(); } });
+    for (auto& th : pool) th.join();
+    for (auto& e : err) if (e) std::rethrow_exception(e);
+  }
+  out.numCus = std::min(F.nCus.load(), out.capCus);
+  out.numTus = std::min(F.nTus.load(), out.capTus);
+  out.supported = !F.unsupported;
+  vtmgpu_deblock_units& p = out.p;
+  p = vtmgpu_deblock_units{};
+  p.flags = (cs.pps->getLoopFilterAcrossSlicesEnabledFlag() ? VTMGPU_UNITS_ACROSS_SLICES : 0) | (cs.pps->getLoopFilterAcrossTilesEnabledFlag() ? VTMGPU_UNITS_ACROSS_TILES : 0) |
+            (cs.sps->getPLTMode() ? VTMGPU_UNITS_PLT : 0);
+  if (F.anyInter)
+  {
+    // the motion field as the decoder keeps it, before setRefinedMotionField (DecLib.cpp:579-580)
+    const CMotionBuf mb = const_cast<const CodingStructure&>(cs).getMotionBuf();
+    p.motion = mb.buf;
+    p.motion_elem_bytes = (int)sizeof(MotionInfo);
+    p.motion_pitch = (int)mb.stride;
+    p.off_mv0 = (int)offsetof(MotionInfo, mv);
+    p.off_mv1 = (int)(offsetof(MotionInfo, mv) + sizeof(Mv));
+    p.off_ref0 = (int)offsetof(MotionInfo, refIdx);
+    p.off_ref1 = (int)(offsetof(MotionInfo, refIdx) + sizeof(int16_t));
+    static_assert(sizeof(Mv) == 8 && offsetof(Mv, hor) == 0 && offsetof(Mv, ver) == 4, "Mv layout");
+  }
+}
+
+void deriveFromUnits(const FlatUnits& in, int width, int height, int chromaFormat, int bdLuma, int bdChroma, int ctuSize, FlatDeblock& out)
+{
+  vtmgpu_derive::Ctx D{};
+  D.cus = in.cus; D.tus = in.tus; D.slices = in.slices.data();
+  D.tuL = in.tuLuma; D.tuC = in.tuChroma;
+  D.motion = static_cast<const unsigned char*>(in.p.motion);
+  D.miBytes = in.p.motion_elem_bytes; D.miPitch = in.p.motion_pitch;
+  D.offMv0 = in.p.off_mv0; D.offMv1 = in.p.off_mv1; D.offRef0 = in.p.off_ref0; D.offRef1 = in.p.off_ref1;
+  D.w4 = width / 4; D.h4 = height / 4;
+  D.sx = (chromaFormat == 1 || chromaFormat == 2) ? 1 : 0; D.sy = chromaFormat == 1 ? 1 : 0; D.chroma = chromaFormat != 0;
+  D.bdL = bdLuma; D.bdC = bdChroma;
+  D.ctuLog2 = ctuSize == 128 ? 7 : (ctuSize == 64 ? 6 : 5);
+  D.flags = in.p.flags;
+  D.ladf = in.hasLadf;
+  D.nvb[0] = in.vb.num_ver; D.nvb[1] = in.vb.num_hor;
+  for (int i = 0; i < 3; i++) { D.vb[0][i] = in.vb.pos_x[i]; D.vb[1][i] = in.vb.pos_y[i]; }
+  D.tcTable = kTc; D.betaTable = kBeta;
+  const int gx = 8 << D.sx, gy = 8 << D.sy;
+  out.width = width; out.height = height; out.sx = D.sx; out.sy = D.sy;
+  const size_t nL = (size_t)D.w4 * D.h4;
+  for (int d = 0; d < 2; d++) out.luma[d].assign(nL, 0);
+  out.chroma[0].assign(D.chroma ? (size_t)((width + gx - 1) / gx) * D.h4 : 0, 0);
+  out.chroma[1].assign(D.chroma ? (size_t)((height + gy - 1) / gy) * D.w4 : 0, 0);
+  for (int dir = 0; dir < 2; dir++)
+    for (int y = 0; y < D.h4; y++)
+      for (int x = 0; x < D.w4; x++)
+      {
+        uint32_t lr; uint64_t cr; bool slot;
+        vtmgpu_derive::deriveUnit(D, x, y, dir, lr, cr, slot);
+        out.luma[dir][(size_t)y * D.w4 + x] = lr;
+        if (slot)
+        {
+          if (dir == 0) out.chroma[0][(size_t)y * ((width + gx - 1) / gx) + (4 * x) / gx] = cr;
+          else          out.chroma[1][(size_t)((4 * y) / gy) * D.w4 + x] = cr;
+        }
+      }
 }
 
 // ---------------------------------------------------------------------------------------------------------

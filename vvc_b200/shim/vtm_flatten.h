@@ -76,6 +76,32 @@ struct FlatAlf
   const vtmgpu_alf_params* slicesView();
 };
 
+// The block structure of a picture flattened for the DEVICE-side derivation of the deblocking records (SURVEY 8f n1,
+// vtmgpu_deblock_units in include/vtmgpu.h): one entry per CU and TU, per 4x4 unit the transform unit that covers it in the luma and in
+// the chroma channel, the slices' deblocking offsets / reference picture tables; the motion field is handed over as the decoder keeps it.
+struct FlatUnits
+{
+  // one page-aligned block per picture geometry (the shim page-locks it): CU table | TU table | luma-channel map | chroma-channel map
+  void*  block = nullptr;
+  size_t blockBytes = 0;
+  bool   blockIsNew = false;        // set when flattenUnits (re)allocated the block
+  vtmgpu_dbf_cu* cus = nullptr;
+  vtmgpu_dbf_tu* tus = nullptr;
+  uint32_t *tuLuma = nullptr, *tuChroma = nullptr;
+  size_t capCus = 0, capTus = 0, numCus = 0, numTus = 0, units = 0;
+  std::vector<vtmgpu_dbf_slice> slices;
+  ~FlatUnits();
+  bool hasLadf = false;
+  vtmgpu_ladf ladf{};
+  vtmgpu_virtual_boundaries vb{};
+  vtmgpu_deblock_units p{};
+  bool supported = true;            // false: a structure the unit model does not describe (a CU with several PUs): the CU walk derives this picture
+  const vtmgpu_deblock_units* view();
+};
+void flattenUnits(CodingStructure& cs, FlatUnits& out);
+// the derivation of include/vtmgpu_derive.h run on the host over every unit, into dense record arrays (self check against the CU walk)
+void deriveFromUnits(const FlatUnits& in, int width, int height, int chromaFormat, int bdLuma, int bdChroma, int ctuSize, FlatDeblock& out);
+
 // LoopFilter::xDeblockCU (LoopFilter.cpp:261-408) and everything it calls except the sample filters,
 // re-stated to EMIT one record per edge segment instead of filtering (records: include/vtmgpu.h).
 void deriveDeblockRecords(CodingStructure& cs, FlatDeblock& out);
