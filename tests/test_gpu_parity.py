@@ -376,7 +376,7 @@ def test_decoder_host_passes_on_device(stream, pictures, lmcs):
     lm, bo, md5 = run()
     assert lm == (pictures if lmcs else 0), "%s: %d pictures took the device LMCS path" % (stream, lm)
     assert bo == pictures
-    lm0, bo0, md5_host = run(VTMGPU_SHIM_HOST_LMCS="1", VTMGPU_SHIM_EXTEND="0")
+    lm0, bo0, md5_host = run(VTMGPU_SHIM_HOST_LMCS="1", VTMGPU_SHIM_EXTEND="0", VTMGPU_SHIM_DEVICE_DERIVE="0", VTMGPU_SHIM_PIN="0")
     assert lm0 == 0 and bo0 == 0 and md5_host == md5
 
 

@@ -117,7 +117,7 @@ struct Shim
   // per-picture
   FlatDeblock dbf, dbfFromUnits;
   FlatUnits units;
-  // VTMGPU_SHIM_DEVICE_DERIVE=1 -- the block structure goes down (flattenUnits) and the DEVICE derives the deblocking records;
+  // the block structure goes down (flattenUnits) and the DEVICE derives the deblocking records (VTMGPU_SHIM_DEVICE_DERIVE=0: the CU walk);
   // VTMGPU_SHIM_CHECK_UNITS=1 -- self check: the CU walk and the unit derivation (the kernel's own source run on the host, and with a device
   // the kernel's output) must produce identical records for every picture
   bool deviceDerive = false, checkUnits = false;
@@ -153,7 +153,7 @@ struct Shim
     deferLmcs = product && !(getenv("VTMGPU_SHIM_HOST_LMCS") && atoi(getenv("VTMGPU_SHIM_HOST_LMCS")));
     extendOnDevice = product && !(getenv("VTMGPU_SHIM_EXTEND") && !atoi(getenv("VTMGPU_SHIM_EXTEND")));
     pinOn = !(getenv("VTMGPU_SHIM_PIN") && !atoi(getenv("VTMGPU_SHIM_PIN")));
-    deviceDerive = !useRef && getenv("VTMGPU_SHIM_DEVICE_DERIVE") && atoi(getenv("VTMGPU_SHIM_DEVICE_DERIVE"));
+    deviceDerive = product && !(getenv("VTMGPU_SHIM_DEVICE_DERIVE") && !atoi(getenv("VTMGPU_SHIM_DEVICE_DERIVE")));      // default in the product decoder; =0: the CU walk on host threads
     checkUnits = getenv("VTMGPU_SHIM_CHECK_UNITS") && atoi(getenv("VTMGPU_SHIM_CHECK_UNITS"));
   }
   ~Shim()
