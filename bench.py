@@ -458,8 +458,10 @@ def main():
             per_px = ent.get("dram_bytes_per_luma_pixel")
             if per_px is not None:
                 roofline["traffic"] = round(per_px * px_per_pic * B)      # ncu dram__bytes_read+write per luma pixel x pixels of one launch
-                roofline["traffic_source"] = "extrapolated: ncu --set full of one %s-picture launch (%s), bytes per luma pixel x the pixels of this launch" % (
-                    ent.get("pictures_in_launch", "?"), ent.get("report", "profiles/"))
+                same = ent.get("pictures_in_launch") == B
+                roofline["traffic_source"] = "%s: ncu --set full of one %s-picture launch of this loop (profiles/r2_ncu_full_summary.csv, tools/profile_round.sh), dram__bytes_read + write" % (
+                    "measured per launch" if same else "extrapolated (bytes per luma pixel x the pixels of this launch)", ent.get("pictures_in_launch", "?"))
+                roofline["traffic_over_algorithmic"] = round(per_px / (B_ALG_SAOALF if dom else B_ALG_DBF), 3)
         except Exception:
             pass
 
