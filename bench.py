@@ -136,6 +136,23 @@ def activity_summary(caps):
 # ------------------------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the reference's own filter classes on the host cores
 # ------------------------------------------------------------------------------------------------------------------
+def cpu_reference_single(scalar=False):
+    """ONE reference decoder process with the host otherwise idle (the single-core figure beside the all-core one), with the
+    reference's SIMD ALF (AVX2) or with its plain C++ routines (= the stock decoder's --SIMD=SCALAR).  Mpixel/s of the filter stages or None."""
+    dec = os.path.join(ROOT, "oracle", "_ref", "DecoderApp_cap")
+    stream = os.path.join(ROOT, "tests", "golden", "streams", "ra_2160p_8.bin")
+    if not (os.path.exists(dec) and os.path.exists(stream)):
+        return None
+    env = dict(os.environ, VTMGPU_SHIM_BACKEND="ref", VTMGPU_SHIM_TIMING="1")
+    if scalar:
+        env["VTMGPU_REF_SIMD"] = "SCALAR"
+    r = subprocess.run([dec, "-b", stream, "-d", "0"], env=env, capture_output=True, text=True, timeout=600)
+    m = re.search(r"vtmgpu-shim-timing: pictures=(\d+) luma_pixels=(\d+) filter_s=([0-9.eE+-]+)", r.stdout)
+    if r.returncode != 0 or not m or "ERROR" in r.stdout:
+        return None
+    return round(int(m.group(2)) / float(m.group(3)) / 1e6, 2)
+
+
 def cpu_reference_run(max_procs=None, repeats=1):
     """One unmodified-reference decoder process per host core (oracle/_ref/DecoderApp_cap with the reference backend: the
     three filter stages are executed by RefLoopFilter / RefSampleAdaptiveOffset / RefAdaptiveLoopFilter, AVX2 ALF),
@@ -593,6 +610,13 @@ def main():
             line["cpu_baseline"] = {"value": round(res[0], 2), "unit": "Mpixel/s", "cores": res[1], "kind": res[2], "sample": res[3]}
             if getattr(cpu_reference_run, "per_process", None):
                 line["cpu_baseline"]["per_process"] = cpu_reference_run.per_process
+            if res[2] == "reference":
+                # one process alone on the host (SIMD and plain C++ ALF) beside the all-core aggregate
+                one, scalar = cpu_reference_single(False), cpu_reference_single(True)
+                if one is not None:
+                    line["cpu_baseline"]["single_process_alone"] = one
+                if scalar is not None:
+                    line["cpu_baseline"]["single_process_alone_scalar_alf"] = scalar
     if rank == 0:
         print(json.dumps(line))
     ctx.close()

@@ -8,6 +8,9 @@
 #include "LoopFilter.h"
 #include "SampleAdaptiveOffset.h"
 
+#include <cstdlib>
+#include <cstring>
+
 #include "shim_backend.h"
 
 namespace
@@ -38,6 +41,10 @@ extern "C" const VtmgpuShimAltBackend* vtmgpu_shim_alt_backend() { return &g_bac
 #ifdef TARGET_SIMD_X86
 void AdaptiveLoopFilter::initAdaptiveLoopFilterX86()
 {
+  // VTMGPU_REF_SIMD=SCALAR: leave the C++ filter routines installed (what the stock decoder does with --SIMD=SCALAR) -- bench.py's
+  // cpu_baseline reports that figure beside the SIMD one
+  const char* e = getenv("VTMGPU_REF_SIMD");
+  if (e && !strcmp(e, "SCALAR")) return;
   const X86_VEXT v = read_x86_extension_flags();
   if (v >= AVX2)       _initAdaptiveLoopFilterX86<AVX2>();
   else if (v == AVX)   _initAdaptiveLoopFilterX86<AVX>();
