@@ -193,6 +193,7 @@ typedef struct vtmgpu_dbf_slice
 #define VTMGPU_UNITS_ACROSS_SLICES 1   /* PPS loop_filter_across_slices_enabled_flag */
 #define VTMGPU_UNITS_ACROSS_TILES  2
 #define VTMGPU_UNITS_PLT           4   /* SPS getPLTMode() */
+#define VTMGPU_UNITS_MOTION_PRELOADED 8  /* the motion field of this picture is already on the device (vtmgpu_upload_motion); `motion` is ignored */
 typedef struct vtmgpu_deblock_units
 {
   int32_t num_cus, num_tus, num_slices, flags;
@@ -363,6 +364,9 @@ int vtmgpu_set_deblock_sparse(vtmgpu_ctx* ctx, int slot, const vtmgpu_deblock_sp
 /* the block structure; the tables and maps are read by asynchronous copies on the ctx stream (page-locked memory must stay valid until
  * vtmgpu_sync, pageable memory may be reused on return) and k_dbf_derive writes the record arrays on the device */
 int vtmgpu_set_deblock_units(vtmgpu_ctx* ctx, int slot, const vtmgpu_deblock_units* p);
+/* the motion field alone, ahead of the tables (it does not depend on the host's flattening, so a caller can overlap the two): same
+ * parameters as in vtmgpu_deblock_units; enqueued on the ctx stream like an upload */
+int vtmgpu_upload_motion(vtmgpu_ctx* ctx, int slot, const void* motion, int elem_bytes, int pitch, int off_mv0, int off_mv1, int off_ref0, int off_ref1);
 /* test hook: the record arrays of a slot as the device holds them, laid out like the arrays of vtmgpu_deblock_params; the caller allocates them */
 int vtmgpu_get_deblock_records(vtmgpu_ctx* ctx, int slot, uint32_t* const luma[2], uint64_t* const chroma[2]);
 /* LMCS inverse luma mapping of the reconstruction (AreaBuf<Pel>::rspSignal with Reshape::getInvLUT(), CommonLib/Buffer.cpp:380-393,

@@ -26,7 +26,7 @@ opts = [
  ("--LoopFilterAcrossVirtualBoundariesDisabledFlag=1", "--NumVerVirtualBoundaries=2", "--NumHorVirtualBoundaries=0", "--VirtualBoundariesPosX=64,256"),
  ("--PLT=1", "--IBC=1"),
  ("--DMVR=1", "--BIO=1"), ("--SMVD=1", "--BCW=1", "--IMV=1", "--AffineAmvr=1", "--Affine=1"), ("--MRL=1",), ("--TransformSkip=1", "--ChromaTS=1", "--BDPCM=1"),
- ("--LMChroma=0",), ("--WeightedPredP=1", "--WeightedPredB=1"),
+ ("--LMChroma=0",), ("--WeightedPredP=1", "--WeightedPredB=1"), ("--LMCSSignalType=1",), ("--LMCSSignalType=1", "--DualITree=1"),
 ]
 names = []
 for i in range(int(sys.argv[2]) if len(sys.argv) > 2 else 10):

@@ -124,7 +124,7 @@ class HostPicture(C.Structure):
 # every entry point include/vtmgpu.h declares (tests check that the built library exports all of them)
 ENTRY_POINTS = [
     "vtmgpu_abi_version", "vtmgpu_abi_sizeof", "vtmgpu_upload_async", "vtmgpu_download_async", "vtmgpu_last_error", "vtmgpu_create", "vtmgpu_destroy", "vtmgpu_upload", "vtmgpu_download",
-    "vtmgpu_set_deblock", "vtmgpu_set_deblock_async", "vtmgpu_set_deblock_sparse", "vtmgpu_set_deblock_units", "vtmgpu_get_deblock_records", "vtmgpu_set_lmcs", "vtmgpu_download_extended", "vtmgpu_host_register", "vtmgpu_host_unregister", "vtmgpu_set_sao", "vtmgpu_set_alf", "vtmgpu_set_alf_slices", "vtmgpu_sao_reconstruct", "vtmgpu_deblock", "vtmgpu_sao",
+    "vtmgpu_set_deblock", "vtmgpu_set_deblock_async", "vtmgpu_set_deblock_sparse", "vtmgpu_set_deblock_units", "vtmgpu_upload_motion", "vtmgpu_get_deblock_records", "vtmgpu_set_lmcs", "vtmgpu_download_extended", "vtmgpu_host_register", "vtmgpu_host_unregister", "vtmgpu_set_sao", "vtmgpu_set_alf", "vtmgpu_set_alf_slices", "vtmgpu_sao_reconstruct", "vtmgpu_deblock", "vtmgpu_sao",
     "vtmgpu_alf", "vtmgpu_sao_alf", "vtmgpu_deblock_sao", "vtmgpu_filter", "vtmgpu_filter_async", "vtmgpu_sync", "vtmgpu_timer_start",
     "vtmgpu_timer_stop", "vtmgpu_rewind", "vtmgpu_launch_count", "vtmgpu_set_profiling", "vtmgpu_stage_ms",
     "vtmgpu_set_rows", "vtmgpu_set_stream", "vtmgpu_upload_rows", "vtmgpu_download_rows", "vtmgpu_export_rows", "vtmgpu_import_rows", "vtmgpu_export_halo", "vtmgpu_import_halo",

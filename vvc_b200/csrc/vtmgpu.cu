@@ -96,6 +96,8 @@ struct vtmgpu_ctx
   bool bandOn = false, bandCall = false;   // connected ; inside vtmgpu_band_filter_async (only those launches carry the flags)
   std::vector<unsigned char*> unitsDev;  // per slot, allocated by the first vtmgpu_set_deblock_units: landing area of the block structure
   std::vector<size_t> unitsBytes;
+  struct MotionDev { unsigned char* dev = nullptr; size_t bytes = 0; int elemBytes = 0, offMv0 = 0, offMv1 = 0, offRef0 = 0, offRef1 = 0; bool loaded = false; };
+  std::vector<MotionDev> motionDev;      // per slot: the motion field of the picture in the slot (vtmgpu_upload_motion / vtmgpu_set_deblock_units)
   pel* extendBuf = nullptr;              // picture + margins of one slot (vtmgpu_download_extended), allocated by the first call
   size_t extendElems = 0;
   std::vector<unsigned char*> sparseDev; // per slot, allocated by the first vtmgpu_set_deblock_sparse: landing area of the record lists
@@ -216,6 +218,7 @@ extern "C" void vtmgpu_destroy(vtmgpu_ctx* c)
   for (unsigned char* p : c->sparseDev) if (p) cudaFree(p);
   if (c->extendBuf) cudaFree(c->extendBuf);
   for (unsigned char* p : c->unitsDev) if (p) cudaFree(p);
+  for (auto& m : c->motionDev) if (m.dev) cudaFree(m.dev);
   if (c->sidePinned) cudaFreeHost(c->sidePinned);
   if (c->slotsPinned) cudaFreeHost(c->slotsPinned);
   if (c->slotsDev) cudaFree(c->slotsDev);
@@ -830,6 +833,39 @@ __global__ void __launch_bounds__(256) k_dbf_derive(const DeriveArgs A)
   }
 }
 
+namespace
+{
+int uploadMotion(vtmgpu_ctx* c, int slot, const void* motion, int elemBytes, int pitch, int offMv0, int offMv1, int offRef0, int offRef1, const char* who)
+{
+  const Geom& g = c->g;
+  if (!motion || elemBytes < 20 || pitch < g.w / 4 || (elemBytes & 3) || ((offMv0 | offMv1) & 3) || ((offRef0 | offRef1) & 1) || offMv0 < 0 || offMv1 < 0 || offRef0 < 0 || offRef1 < 0 ||
+      offMv0 + 8 > elemBytes || offMv1 + 8 > elemBytes || offRef0 + 2 > elemBytes || offRef1 + 2 > elemBytes)
+    return c->fail("%s: bad motion field layout", who);
+  if (c->motionDev.empty()) c->motionDev.resize(c->seq.capacity);
+  vtmgpu_ctx::MotionDev& m = c->motionDev[slot];
+  const size_t bytes = (size_t)(g.w / 4) * (g.h / 4) * elemBytes;
+  if (bytes > m.bytes)
+  {
+    if (m.dev) { cudaStreamSynchronize(c->stream); cudaFree(m.dev); m.dev = nullptr; m.bytes = 0; }
+    if (c->cuda(cudaMalloc(&m.dev, bytes), "motion field allocation")) return -1;
+    m.bytes = bytes;
+  }
+  // rows of the motion field, without the pitch padding
+  if (c->cuda(cudaMemcpy2DAsync(m.dev, (size_t)(g.w / 4) * elemBytes, motion, (size_t)pitch * elemBytes, (size_t)(g.w / 4) * elemBytes, g.h / 4, cudaMemcpyHostToDevice, c->stream), who)) return -1;
+  m.elemBytes = elemBytes; m.offMv0 = offMv0; m.offMv1 = offMv1; m.offRef0 = offRef0; m.offRef1 = offRef1;
+  m.loaded = true;
+  return 0;
+}
+}   // namespace
+
+extern "C" int vtmgpu_upload_motion(vtmgpu_ctx* c, int slot, const void* motion, int elem_bytes, int pitch, int off_mv0, int off_mv1, int off_ref0, int off_ref1)
+{
+  if (!c) return -1;
+  if (!c->slotOk(slot, 1)) return c->fail("upload_motion: bad slot %d", slot);
+  cudaSetDevice(c->seq.device);
+  return uploadMotion(c, slot, motion, elem_bytes, pitch, off_mv0, off_mv1, off_ref0, off_ref1, "upload_motion");
+}
+
 extern "C" int vtmgpu_set_deblock_units(vtmgpu_ctx* c, int slot, const vtmgpu_deblock_units* p)
 {
   if (!c) return -1;
@@ -839,10 +875,8 @@ extern "C" int vtmgpu_set_deblock_units(vtmgpu_ctx* c, int slot, const vtmgpu_de
   const size_t units = (size_t)(g.w / 4) * (g.h / 4);
   if (p->num_cus < 1 || p->num_tus < 1 || p->num_slices < 1 || p->num_slices > 255 || !p->cus || !p->tus || !p->slices || !p->tu_luma) return c->fail("set_deblock_units: missing tables");
   if (g.ncomp > 1 && !p->tu_chroma) return c->fail("set_deblock_units: tu_chroma is NULL");
-  if (p->motion && (p->motion_elem_bytes < 20 || p->motion_pitch < g.w / 4 || (p->motion_elem_bytes & 3) || ((p->off_mv0 | p->off_mv1) & 3) || ((p->off_ref0 | p->off_ref1) & 1) ||
-                    p->off_mv0 < 0 || p->off_mv1 < 0 || p->off_ref0 < 0 || p->off_ref1 < 0 ||
-                    p->off_mv0 + 8 > p->motion_elem_bytes || p->off_mv1 + 8 > p->motion_elem_bytes || p->off_ref0 + 2 > p->motion_elem_bytes || p->off_ref1 + 2 > p->motion_elem_bytes))
-    return c->fail("set_deblock_units: bad motion field layout");
+  const bool preloaded = (p->flags & VTMGPU_UNITS_MOTION_PRELOADED) != 0;
+  if (preloaded && (c->motionDev.empty() || !c->motionDev[slot].loaded)) return c->fail("set_deblock_units: no motion field was uploaded to slot %d (vtmgpu_upload_motion)", slot);
   if (p->vb && (p->vb->num_ver < 0 || p->vb->num_ver > 3 || p->vb->num_hor < 0 || p->vb->num_hor > 3)) return c->fail("set_deblock_units: bad virtual boundaries");
   cudaSetDevice(c->seq.device);
   c->mirrorWrite(slot);
@@ -851,8 +885,8 @@ extern "C" int vtmgpu_set_deblock_units(vtmgpu_ctx* c, int slot, const vtmgpu_de
   if (setLadf(c, slot, p->ladf)) { sd.dbfOn = 0; c->pushSlot(slot); return -1; }
   // landing area of the tables on the device (per slot, grown on demand)
   const size_t szCu = alignUp(sizeof(vtmgpu_dbf_cu) * p->num_cus, 256), szTu = alignUp(sizeof(vtmgpu_dbf_tu) * p->num_tus, 256), szSl = alignUp(sizeof(vtmgpu_dbf_slice) * p->num_slices, 256);
-  const size_t szMap = alignUp(units * 4, 256), szMi = p->motion ? alignUp(units * p->motion_elem_bytes, 256) : 0;
-  const size_t need = szCu + szTu + szSl + szMap * (g.ncomp > 1 ? 2 : 1) + szMi;
+  const size_t szMap = alignUp(units * 4, 256);
+  const size_t need = szCu + szTu + szSl + szMap * (g.ncomp > 1 ? 2 : 1);
   if (c->unitsDev.empty()) { c->unitsDev.assign(c->seq.capacity, nullptr); c->unitsBytes.assign(c->seq.capacity, 0); }
   if (need > c->unitsBytes[slot])
   {
@@ -872,15 +906,16 @@ extern "C" int vtmgpu_set_deblock_units(vtmgpu_ctx* c, int slot, const vtmgpu_de
   UP(D.tuL, p->tu_luma, units * 4); o += szMap;
   if (g.ncomp > 1) { UP(D.tuC, p->tu_chroma, units * 4); o += szMap; }
 #undef UP
-  if (p->motion)
+  if (!preloaded && p->motion &&
+      uploadMotion(c, slot, p->motion, p->motion_elem_bytes, p->motion_pitch, p->off_mv0, p->off_mv1, p->off_ref0, p->off_ref1, "set_deblock_units")) { sd.dbfOn = 0; c->pushSlot(slot); return -1; }
+  if (preloaded || p->motion)
   {
-    // rows of the motion field, without the pitch padding
-    if (c->cuda(cudaMemcpy2DAsync(d + o, (size_t)(g.w / 4) * p->motion_elem_bytes, p->motion, (size_t)p->motion_pitch * p->motion_elem_bytes, (size_t)(g.w / 4) * p->motion_elem_bytes, g.h / 4,
-                                  cudaMemcpyHostToDevice, c->stream), "set_deblock_units")) { sd.dbfOn = 0; c->pushSlot(slot); return -1; }
-    D.motion = d + o;
-    D.miBytes = p->motion_elem_bytes; D.miPitch = g.w / 4;
-    D.offMv0 = p->off_mv0; D.offMv1 = p->off_mv1; D.offRef0 = p->off_ref0; D.offRef1 = p->off_ref1;
+    const vtmgpu_ctx::MotionDev& m = c->motionDev[slot];
+    D.motion = m.dev;
+    D.miBytes = m.elemBytes; D.miPitch = g.w / 4;
+    D.offMv0 = m.offMv0; D.offMv1 = m.offMv1; D.offRef0 = m.offRef0; D.offRef1 = m.offRef1;
   }
+  if (!c->motionDev.empty()) c->motionDev[slot].loaded = false;       // one picture's field: the next picture uploads its own
   D.w4 = g.w / 4; D.h4 = g.h / 4; D.sx = g.sx; D.sy = g.sy; D.chroma = g.ncomp > 1;
   D.bdL = g.bdL; D.bdC = g.bdC; D.ctuLog2 = g.ctuLog2;
   D.flags = p->flags;

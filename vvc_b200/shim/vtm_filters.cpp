@@ -21,6 +21,7 @@
 
 #include <chrono>
 #include <exception>
+#include <mutex>
 #include <thread>
 
 #include <cstdio>
@@ -61,6 +62,7 @@ struct GpuApi
   decltype(&vtmgpu_set_deblock_sparse) set_deblock_sparse = nullptr;
   decltype(&vtmgpu_set_deblock_units) set_deblock_units = nullptr;
   decltype(&vtmgpu_get_deblock_records) get_deblock_records = nullptr;
+  decltype(&vtmgpu_upload_motion) upload_motion = nullptr;
   decltype(&vtmgpu_sync) sync = nullptr;
   decltype(&vtmgpu_set_sao) set_sao = nullptr;
   decltype(&vtmgpu_set_alf) set_alf = nullptr;
@@ -84,7 +86,7 @@ struct GpuApi
     so = dlopen(path ? path : "libvtmgpu.so", RTLD_NOW | RTLD_LOCAL);
     if (!so) THROW("vtmgpu shim: cannot load libvtmgpu.so (" << dlerror() << ") -- no CPU fallback");
 #define SYM(n) n = reinterpret_cast<decltype(n)>(dlsym(so, "vtmgpu_" #n)); if (!n) THROW("vtmgpu shim: missing symbol vtmgpu_" #n)
-    SYM(abi_version); SYM(last_error); SYM(create); SYM(destroy); SYM(upload); SYM(download); SYM(set_deblock); SYM(set_deblock_sparse); SYM(set_deblock_units); SYM(get_deblock_records); SYM(sync); SYM(set_sao);
+    SYM(abi_version); SYM(last_error); SYM(create); SYM(destroy); SYM(upload); SYM(download); SYM(set_deblock); SYM(set_deblock_sparse); SYM(set_deblock_units); SYM(get_deblock_records); SYM(upload_motion); SYM(sync); SYM(set_sao);
     SYM(set_alf); SYM(set_alf_slices); SYM(set_lmcs); SYM(download_extended); SYM(host_register); SYM(host_unregister); SYM(sao_reconstruct); SYM(deblock); SYM(sao); SYM(alf); SYM(sao_alf); SYM(deblock_sao); SYM(filter);
 #undef SYM
     if (abi_version() != VTMGPU_ABI_VERSION) THROW("vtmgpu shim: ABI version mismatch");
@@ -211,8 +213,10 @@ struct Shim
   std::vector<Range> ranges;
   std::vector<const void*> seenPlanes;
   int pinnedPlanes = 0;
+  std::mutex pinMutex;                 // the upload thread and the decoder thread both transfer (and therefore pin)
   void pin(const CodingStructure& cs, const Pel* buf, ptrdiff_t stride, int height, int comp)
   {
+    std::lock_guard<std::mutex> lock(pinMutex);
     for (const void* e : seenPlanes) if (e == buf) return;
     seenPlanes.push_back(buf);
     if (!pinOn) return;
@@ -222,12 +226,14 @@ struct Shim
   }
   void pinOnce(const void* p, size_t bytes)           // other long-lived host buffers the shim transfers from (motion fields, the block-structure tables)
   {
+    std::lock_guard<std::mutex> lock(pinMutex);
     for (const void* e : seenPlanes) if (e == p) return;
     seenPlanes.push_back(p);
     if (pinOn) pinRange(reinterpret_cast<uintptr_t>(p), reinterpret_cast<uintptr_t>(p) + bytes);
   }
   void unpin(const void* p)
   {
+    std::lock_guard<std::mutex> lock(pinMutex);
     for (size_t i = 0; i < seenPlanes.size(); i++) if (seenPlanes[i] == p) { seenPlanes.erase(seenPlanes.begin() + i); break; }
     const uintptr_t a = reinterpret_cast<uintptr_t>(p) & ~uintptr_t(4095);
     for (size_t i = 0; i < ranges.size(); i++)
@@ -435,7 +441,36 @@ void LoopFilter::loopFilterPic(CodingStructure& cs)
   // the upload of the reconstruction (a staged copy out of pageable decoder memory) runs beside the host derivation
   std::thread uploader;
   std::exception_ptr uploadError;
-  if (!s.useRef) uploader = std::thread([&] { try { s.upload(cs); } catch (...) { uploadError = std::current_exception(); } });
+  // device-side derivation: the motion field (read before setRefinedMotionField changes it, DecLib.cpp:579-580) goes down behind the planes
+  // while this thread flattens the block structure
+  bool motionPreloaded = false;
+  const void* miBuf = nullptr;
+  int miPitch = 0;
+  if (s.deviceDerive)
+  {
+    bool inter = cs.sps->getIBCFlag();
+    for (const Slice* sl : cs.picture->slices) inter |= !sl->isIntra();
+    if (inter)
+    {
+      const CMotionBuf mb = const_cast<const CodingStructure&>(cs).getMotionBuf();
+      miBuf = mb.buf; miPitch = (int)mb.stride;
+      s.pinOnce(miBuf, (size_t)miPitch * (cs.pcv->lumaHeight / 4) * sizeof(MotionInfo));
+      motionPreloaded = true;
+    }
+  }
+  if (!s.useRef) uploader = std::thread([&] {
+    try
+    {
+      s.upload(cs);
+      if (motionPreloaded)
+      {
+        s.check(s.api.upload_motion(s.ctx, 0, miBuf, (int)sizeof(MotionInfo), miPitch, (int)offsetof(MotionInfo, mv), (int)(offsetof(MotionInfo, mv) + sizeof(Mv)),
+                                    (int)offsetof(MotionInfo, refIdx), (int)(offsetof(MotionInfo, refIdx) + sizeof(int16_t))), "upload_motion");
+        s.check(s.api.sync(s.ctx), "sync");
+      }
+    }
+    catch (...) { uploadError = std::current_exception(); }
+  });
   bool useUnits = false;
   try
   {
@@ -508,7 +543,9 @@ void LoopFilter::loopFilterPic(CodingStructure& cs)
     {
       // the block structure goes down and k_dbf_derive writes the records; the motion field is read before setRefinedMotionField
       // changes it (DecLib.cpp:579-580): the copies are complete when this call returns
-      s.check(s.api.set_deblock_units(s.ctx, 0, s.units.view()), "set_deblock_units");
+      vtmgpu_deblock_units up = *s.units.view();
+      if (motionPreloaded) { up.flags |= VTMGPU_UNITS_MOTION_PRELOADED; up.motion = nullptr; }
+      s.check(s.api.set_deblock_units(s.ctx, 0, &up), "set_deblock_units");
       s.check(s.api.sync(s.ctx), "sync");
       if (s.checkUnits)
       {
