@@ -181,6 +181,8 @@ typedef struct vtmgpu_dbf_tu
   int8_t   qp_cb, qp_cr;  /* QpParam(tu, comp).Qp(0) - qpBdOffset (LoopFilter.cpp:1213-1217)           */
   uint8_t  reserved;
   uint32_t cu;            /* index into cus[]                                                          */
+  uint32_t tail;          /* luma blocks narrower (lower) than a unit -- ISP sub-partitions: the TU that holds the LAST column (row) of the
+                             unit this one starts, i.e. what getTU returns for the sample next to the following edge; else the TU itself */
 } vtmgpu_dbf_tu;
 typedef struct vtmgpu_dbf_slice
 {

@@ -72,6 +72,15 @@ VTMGPU_HD bool tuEdgeLuma(const Ctx& D, int x, int y, int dir)
   return (c.flags & (ts == cs ? (dir == VER ? VTMGPU_CU_EN_LEFT : VTMGPU_CU_EN_TOP) : VTMGPU_CU_EN_INT)) != 0;
 }
 
+/* the luma-channel TU on the P side of an edge: the reference looks up the sample next to the edge (posQ - 1), which in a unit made of
+ * ISP sub-partitions 1 or 2 samples wide (high) is another TU than the one that holds the unit's first sample */
+VTMGPU_HD const vtmgpu_dbf_tu& tuLumaP(const Ctx& D, int unit, int dir)
+{
+  const vtmgpu_dbf_tu& t = D.tus[D.tuL[unit]];
+  const int n = dir == VER ? t.w : t.h;
+  return (n && n < 4) ? D.tus[t.tail] : t;
+}
+
 VTMGPU_HD bool usable(const Ctx& D, const vtmgpu_dbf_cu& q, const vtmgpu_dbf_cu& p)
 {
   /* isAvailableLeft / isAvailableAbove (LoopFilter.cpp:85-93) */
@@ -161,7 +170,7 @@ VTMGPU_HD void deriveUnit(const Ctx& D, int x, int y, int dir, uint32_t& lumaRec
   /* ---- luma channel: the CU that holds the luma block here ------------------------------------------------------------------ */
   const vtmgpu_dbf_tu& tq = D.tus[D.tuL[u]];
   const vtmgpu_dbf_cu& cq = D.cus[tq.cu];
-  const vtmgpu_dbf_tu& tp = D.tus[D.tuL[up]];
+  const vtmgpu_dbf_tu& tp = tuLumaP(D, up, dir);
   const vtmgpu_dbf_cu& cp = D.cus[tp.cu];
   const int cuStart = dir == VER ? cq.x : cq.y;
   const bool border = pos == cuStart;

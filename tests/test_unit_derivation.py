@@ -14,7 +14,7 @@ from conftest import GOLDEN
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DEC = os.path.join(ROOT, "oracle", "_ref", "DecoderApp_cap")
-SMALL = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "streams", "*.bin")) if os.path.getsize(p) < 64 * 1024)
+SMALL = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "streams", "*.bin")) if os.path.getsize(p) < 256 * 1024)
 
 
 @pytest.mark.skipif(not os.path.exists(DEC), reason="oracle/_ref/DecoderApp_cap not built (needs the reference sources)")

@@ -796,11 +796,16 @@ struct UnitFlattener
       vtmgpu_dbf_tu t{};
       t.cu = cuId;
       const uint32_t tuId = (uint32_t)tuAt;
+      t.tail = tuId;
       if (tu.blocks[COMPONENT_Y].valid())
       {
         const CompArea& b = tu.blocks[COMPONENT_Y];
         t.x = (uint16_t)b.x; t.y = (uint16_t)b.y; t.w = (uint8_t)b.width; t.h = (uint8_t)b.height;
         fill(out.tuLuma, b.x, b.y, b.width, b.height, tuId);
+        // ISP sub-partitions 1 or 2 samples wide (high): they follow each other in the TU list, the one that holds the unit's last
+        // column (row) is 3 / width (3 / height) entries further
+        if (b.width < 4 && (b.x & 3) == 0)       t.tail = tuId + 3 / b.width;
+        else if (b.height < 4 && (b.y & 3) == 0) t.tail = tuId + 3 / b.height;
       }
       if (chroma && tu.blocks.size() > 1 && tu.blocks[COMPONENT_Cb].valid())
       {
