@@ -200,7 +200,18 @@ struct Shim
     seq = s;
     if (useRef || (ctx && same)) return;
     api.load();
-    if (ctx) { api.destroy(ctx); ctx = nullptr; }
+    if (ctx)
+    {
+      // new sequence geometry: the decoder re-creates its picture buffers -- drop every page lock taken for the old ones
+      {
+        std::lock_guard<std::mutex> lock(pinMutex);
+        for (const Range& r : ranges) if (r.live) api.host_unregister(reinterpret_cast<void*>(r.lo));
+        ranges.clear();
+        seenPlanes.clear();
+        pinnedPlanes = 0;
+      }
+      api.destroy(ctx); ctx = nullptr;
+    }
     if (api.create(&seq, &ctx)) THROW("vtmgpu shim: vtmgpu_create failed: " << api.last_error(nullptr));
     lmcsActive = false;
   }
