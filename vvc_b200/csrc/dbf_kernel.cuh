@@ -22,11 +22,16 @@
 namespace vtmgpu
 {
 
-constexpr int DBF_TW = 128, DBF_TH = 64, DBF_HALO = 8;
+#ifndef DBF_TILE_W
+#define DBF_TILE_W 128          // plane tile width: 128 (256 threads, 3 CTAs per SM) or 64 (128 threads, 5 CTAs per SM)
+#endif
+constexpr int DBF_TW = DBF_TILE_W, DBF_TH = 64, DBF_HALO = 8;
 constexpr int DBF_SW = DBF_TW + 2 * DBF_HALO;           // 144
 constexpr int DBF_SH = DBF_TH + 2 * DBF_HALO;           // 80
 constexpr int DBF_PITCH = DBF_SW + 8;                   // 152 samples = 304 B: rows shift by 12 banks
-constexpr int DBF_THREADS = 256;
+constexpr int DBF_THREADS = DBF_TW * 2;                 // one thread per 8 x 4 strip of the tile
+constexpr int DBF_CTAS_PER_SM = DBF_TW == 128 ? 3 : 5;
+static_assert(DBF_TW == 128 || DBF_TW == 64, "tile width");
 
 // x points at q0 of one line in shared memory; o = step across the edge; P(k) = x[-(k+1)*o], Q(k) = x[k*o]
 // tc / beta tables of the standard (LoopFilter.cpp:66-74), only needed on the device with LADF
@@ -306,12 +311,17 @@ struct DbfLaunch
 // Persistent CTAs walk the plane tiles of a batch of picture slots round robin (per slot: luma tiles, Cb tiles, Cr tiles).
 // While tile i is filtered, tile i+1 arrives: the samples (tile + 8 halo, zero filled outside the picture) by ONE TMA box,
 // the segment records of both passes by cp.async in exactly the order the passes consume them.
-constexpr int DBF_RECA_BYTES = 5888;                    // pass-1 records of a tile: luma 40x20 u32, chroma 18x40 u64 (multiples of 128 B)
-constexpr int DBF_RECB_BYTES = 4992;                    // pass-2 records: luma 40x17 u32, chroma 68x9 u64
+constexpr int DBF_RECL = DBF_TW / 4 + 8;                // columns of the luma record boxes (40 at tile width 128)
+constexpr int DBF_RECC = DBF_TW / 8 + 2;                // columns of the chroma vertical-edge record box (18)
+constexpr int dbfMax(int a, int b) { return a > b ? a : b; }
+constexpr int dbfUp128(int v) { return (v + 127) / 128 * 128; }
+// pass-1 records of a tile: luma RECL x 20 u32, chroma RECC x 40 u64 (4:2:0); pass-2: luma RECL x 17 u32, chroma (TW / 2 + 4) x 9 u64 -- 5888 and 4992 bytes at width 128
+constexpr int DBF_RECA_BYTES = dbfUp128(dbfMax(DBF_RECL * (DBF_SH / 4) * 4, DBF_RECC * (DBF_SH / 2) * 8));
+constexpr int DBF_RECB_BYTES = dbfUp128(dbfMax(DBF_RECL * (DBF_TH / 4 + 1) * 4, (DBF_TW / 2 + 4) * (DBF_TH / 8 + 1) * 8));
 constexpr int DBF_TILE_BYTES = DBF_SH * DBF_PITCH * 2;  // 24320 (multiple of 128: TMA destination)
+static_assert(DBF_TILE_BYTES % 128 == 0, "TMA destination alignment");
 constexpr int DBF_STAGE_BYTES = DBF_TILE_BYTES + DBF_RECA_BYTES + DBF_RECB_BYTES;
-constexpr int DBF_RECL = 40;                            // columns of the luma record boxes
-constexpr int DBF_QUEUE = 832;                          // queue entries per pass (>= record slots of a pass)                          // active-segment queue entries per warp (a warp scans <= 96 slots per pass)
+constexpr int DBF_QUEUE = dbfMax(DBF_RECL * (DBF_SH / 4), DBF_RECC * (DBF_SH / 2)) + 32;     // queue entries per pass (>= record slots of a pass)
 constexpr int DBF_SMEM_BYTES = 2 * DBF_STAGE_BYTES + 32 + 2 * DBF_QUEUE * 2;      // stages, 2 mbarriers + 2 counters, 2 queues
 
 // record boxes of one tile (columns x rows, in records) for the arrays lumaV, lumaH, chromaV, chromaH.  TMA wants the first
@@ -328,7 +338,7 @@ __host__ __device__ inline DbfRecBoxes dbfRecBoxes(int sx, int sy)
   const int nv = 4 >> sy, nh = 4 >> sx;
   B.cols[0] = DBF_RECL; B.rows[0] = DBF_SH / 4;              // vertical edges x0-4 .. x0+TW+4 (columns 3..37 used), segment rows of tile + halo
   B.cols[1] = DBF_RECL; B.rows[1] = DBF_TH / 4 + 1;          // horizontal edges y0 .. y0+TH, segments of columns x0-4 .. x0+TW+3 (columns 3..36 used)
-  B.cols[2] = 18; B.rows[2] = DBF_SH / nv;                   // chroma vertical edges x0 .. x0+TW step 8 (17 used)
+  B.cols[2] = DBF_RECC; B.rows[2] = DBF_SH / nv;                   // chroma vertical edges x0 .. x0+TW step 8 (17 used)
   B.cols[3] = DBF_TW / nh + 4; B.rows[3] = DBF_TH / 8 + 1;   // chroma horizontal edges, one extra segment each side (columns 1 .. TW/nh+2 used)
   return B;
 }
@@ -366,7 +376,7 @@ __device__ __forceinline__ DbfPassGeom dbfPassGeom(int comp, const Geom& g)
   {
     P.nv = 4 >> g.sy; P.nh = 4 >> g.sx;
     P.ne1 = DBF_TW / 8 + 1; P.ns1 = DBF_SH / P.nv; P.ne2 = DBF_TH / 8 + 1; P.ns2 = DBF_TW / P.nh + 2;
-    P.p1 = 18; P.p2 = P.ns2 + 2;
+    P.p1 = DBF_RECC; P.p2 = P.ns2 + 2;
   }
   P.n1 = P.p1 * P.ns1; P.n2 = P.p2 * P.ne2;                   // slots scanned (incl. the padding column of pass 1)
   return P;
@@ -419,7 +429,7 @@ __device__ __forceinline__ void dbfPrefetch(unsigned char* stageMem, uint64_t* b
 }
 
 // maps = TMA descriptors of the plane buffers: [slot][3 buffers][3 planes], box = DBF_PITCH x DBF_SH samples
-__global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __restrict__ slots, const CUtensorMap* __restrict__ tmaps, const CUtensorMap* __restrict__ recMaps,
+__global__ void __launch_bounds__(DBF_THREADS, DBF_CTAS_PER_SM) k_dbf_sao(const SlotDev* __restrict__ slots, const CUtensorMap* __restrict__ tmaps, const CUtensorMap* __restrict__ recMaps,
                                                              int firstSlot, int numSlots, int srcBuf, int dstBuf, Geom g, DbfLaunch L, TileStep step, int doDbf, int doSao,
                                                              const BandDev band)
 {
@@ -543,7 +553,7 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
         const int c = comp - 1;
         const int tcShift = c ? VTMGPU_DBF_C_TCCR_SHIFT : 0, betaShift = c ? VTMGPU_DBF_C_BETACR_SHIFT : VTMGPU_DBF_C_BETACB_SHIFT;
         const int p2 = P.p2, ns2 = P.ns2;
-        dbfCompact(ra, P.n1, queue1, &qcount[0], [tcShift](uint64_t r, int i) { return ((r >> tcShift) & 0x7ff) != 0 && (i % 18) < 17; });
+        dbfCompact(ra, P.n1, queue1, &qcount[0], [tcShift](uint64_t r, int i) { return ((r >> tcShift) & 0x7ff) != 0 && (i % DBF_RECC) < DBF_RECC - 1; });
         dbfCompact(rbv, P.n2, queue2, &qcount[1], [tcShift, p2, ns2](uint64_t r, int i) { return ((r >> tcShift) & 0x7ff) != 0 && (unsigned)(i % p2 - 1) < (unsigned)ns2; });
         __syncthreads();
         // pass 1: vertical edges on the 8-sample chroma grid; one item = the chroma rows of one 4-luma-row unit
@@ -551,7 +561,7 @@ __global__ void __launch_bounds__(DBF_THREADS, 3) k_dbf_sao(const SlotDev* __res
           const int cnt = qcount[0];
           for (int k = tid; k < cnt; k += DBF_THREADS)
           {
-            const int i = queue1[k], sg = i / 18, e = i - sg * 18;
+            const int i = queue1[k], sg = i / DBF_RECC, e = i - sg * DBF_RECC;
             const uint64_t rec = ra[i];
             dbfChromaSegment(&sm[(P.nv * sg) * DBF_PITCH + DBF_HALO + 8 * e], 1, DBF_PITCH, P.nv, (int)(rec >> tcShift) & 0x7ff, (int)(rec >> betaShift) & 0x7ff,
                              (rec & VTMGPU_DBF_C_LARGE) != 0, (rec & VTMGPU_DBF_C_CTB) != 0, !(rec & VTMGPU_DBF_C_PNOFILT), !(rec & VTMGPU_DBF_C_QNOFILT), maxv);

@@ -1416,7 +1416,7 @@ int launchDbfSao(vtmgpu_ctx* c, int first, int count, int doDbf, int doSao)
   return forRuns(c, first, count, [&](int s, int n, int src) {
     const int dst = src == 1 ? 2 : 1;
     // persistent CTAs: three per SM, each walks the plane tiles round robin with double-buffered TMA loads
-    const int items = L.tilesL + 2 * L.tilesC, grid = std::min(items * n, 3 * c->numSms);
+    const int items = L.tilesL + 2 * L.tilesC, grid = std::min(items * n, DBF_CTAS_PER_SM * c->numSms);
     TileStep st;
     st.dSlot = grid / items;
     st.dItem = grid % items;
