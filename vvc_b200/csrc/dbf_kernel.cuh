@@ -238,6 +238,76 @@ __device__ __forceinline__ void dbfLumaSegmentQuad(pel* x0, int o, int s, uint32
   }
 }
 
+// The same in two steps for SIXTEEN segments per warp round.  The decisions of xEdgeFilterLuma only look at the first and the last
+// line of a segment (LoopFilter.cpp:977-1043), so a PAIR of lanes decides a segment -- lane parity = line 0 / line 3, the partner's
+// gradients and strong-filter tests come by one shuffle -- instead of a quad of which two lanes computed for nothing; then the
+// sixteen segments are filtered in two sub-rounds of eight, one line per lane, with the decision fetched from the pair by shuffle.
+//   decision word: bits 0-1 = 0 nothing / 1 long filter / 2 normal strong / 3 normal weak, bit 2 secondP, bit 3 secondQ
+__device__ __forceinline__ uint32_t dbfLumaDecidePair(const pel* x0, int o, int s, uint32_t rec)
+{
+  const int tc = rec & 0x7ff;
+  const int beta = (rec >> VTMGPU_DBF_L_BETA_SHIFT) & 0x7ff;
+  const pel* x = x0 + ((threadIdx.x & 1) ? 3 * s : 0);
+  const int lenP = (rec >> VTMGPU_DBF_L_LENP_SHIFT) & 7, lenQ = (rec >> VTMGPU_DBF_L_LENQ_SHIFT) & 7;
+  const bool largeP = lenP > 3 && !(rec & VTMGPU_DBF_L_CTUROW), largeQ = lenQ > 3;
+  const int sideThr = (beta + (beta >> 1)) >> 3;
+  const int dp = iabs(PK(2) - 2 * PK(1) + PK(0)), dq = iabs(QK(0) - 2 * QK(1) + QK(2));
+  int dpL = dp, dqL = dq;
+  if (largeP) dpL = (dp + iabs(PK(5) - 2 * PK(4) + PK(3)) + 1) >> 1;
+  if (largeQ) dqL = (dq + iabs(QK(3) - 2 * QK(4) + QK(5)) + 1) >> 1;
+  const bool anyLarge = largeP || largeQ;
+  const bool sL = anyLarge && dbfStrongLong(x, o, 2 * (dpL + dqL), beta, tc, largeP, largeQ, lenP, lenQ);
+  const bool sS = lenP > 2 && lenQ > 2 && dbfStrongShort(x, o, 2 * (dp + dq), beta, tc, false);
+  const uint32_t gS = (uint32_t)dp | (uint32_t)dq << 16, gL = (uint32_t)dpL | (uint32_t)dqL << 16, fl = (sL ? 1u : 0u) | (sS ? 2u : 0u);
+  const uint32_t gSo = __shfl_xor_sync(0xffffffffu, gS, 1), gLo = __shfl_xor_sync(0xffffffffu, gL, 1), flo = __shfl_xor_sync(0xffffffffu, fl, 1);
+  if (anyLarge)
+  {
+    const int dL = (int)(gL & 0xffff) + (int)(gL >> 16) + (int)(gLo & 0xffff) + (int)(gLo >> 16);
+    if (dL < beta && (fl & flo & 1)) return 1u;
+  }
+  const int dpS = (int)(gS & 0xffff) + (int)(gSo & 0xffff), dqS = (int)(gS >> 16) + (int)(gSo >> 16);
+  if (dpS + dqS >= beta) return 0u;
+  uint32_t d = (fl & flo & 2) ? 2u : 3u;
+  if (lenP > 1 && lenQ > 1)
+  {
+    if (dpS < sideThr) d |= 4u;
+    if (dqS < sideThr) d |= 8u;
+  }
+  return d;
+}
+
+__device__ __forceinline__ void dbfLumaApplyLine(pel* xl, int o, uint32_t rec, uint32_t d, int maxv, bool valid)
+{
+  const int tc = rec & 0x7ff;
+  const int lenP = (rec >> VTMGPU_DBF_L_LENP_SHIFT) & 7, lenQ = (rec >> VTMGPU_DBF_L_LENQ_SHIFT) & 7;
+  const bool wP = valid && !(rec & VTMGPU_DBF_L_PNOFILT), wQ = valid && !(rec & VTMGPU_DBF_L_QNOFILT);
+  const uint32_t type = d & 3;
+  if (type == 1)
+  {
+    const bool largeP = lenP > 3 && !(rec & VTMGPU_DBF_L_CTUROW), largeQ = lenQ > 3;
+    dbfLongLine(xl, o, largeP ? lenP : 3, largeQ ? lenQ : 3, tc, wP, wQ);
+  }
+  else if (type) dbfLumaLine(xl, o, tc, type == 2, wP, wQ, (d & 4) != 0, (d & 8) != 0, maxv);
+}
+
+// LADF for a lane pair (see dbfLadfRecord): the two lanes hold lines 0 and 3
+__device__ __noinline__ uint32_t dbfLadfRecordPair(uint32_t rec, const pel* x0, int o, int s, int bd, const LadfDev* ladf)
+{
+  const pel* x = x0 + ((threadIdx.x & 1) ? 3 * s : 0);
+  const int own = PK(0) + QK(0);
+  const int level = (own + __shfl_xor_sync(0xffffffffu, own, 1)) >> 2;
+  int shift = ladf->off[0];
+  for (int k = 1; k < ladf->n; k++)
+  {
+    if (level > ladf->lb[k]) shift = ladf->off[k];
+    else break;
+  }
+  const int t = kDbfTcTable[clip3(0, 65, (int)(rec & 0x7ff) - VTMGPU_DBF_LADF_BIAS + shift)];
+  const int tc = bd < 10 ? (t + 2) >> (10 - bd) : t << (bd - 10);
+  const int beta = (int)kDbfBetaTable[clip3(0, 63, (int)((rec >> VTMGPU_DBF_L_BETA_SHIFT) & 0x7ff) - VTMGPU_DBF_LADF_BIAS + shift)] << (bd - 8);
+  return (rec & ~0x3fffffu) | (uint32_t)tc | (uint32_t)beta << VTMGPU_DBF_L_BETA_SHIFT;
+}
+
 __device__ __forceinline__ void dbfChromaLine(pel* x, int o, int tc, bool strong, bool ctb, bool wP, bool wQ, int maxv)
 {
   const int p0 = PK(0), p1 = PK(1), q0 = QK(0), q1 = QK(1);
@@ -519,30 +589,50 @@ __global__ void __launch_bounds__(DBF_THREADS, DBF_CTAS_PER_SM) k_dbf_sao(const 
         // pass 1: vertical edges x0-4 .. x0+TW+4 (step 4), all rows of tile + halo
         {
           const int cnt = qcount[0];
-          for (int k0 = (tid >> 5) * 8; k0 < cnt; k0 += DBF_THREADS / 4)
+          for (int k0 = (tid >> 5) * 16; k0 < cnt; k0 += DBF_THREADS / 2)
           {
-            const int k = k0 + (lane >> 2);
+            // decisions: a lane pair per segment
+            const int k = k0 + (lane >> 1);
             const bool valid = k < cnt;
             const int i = queue1[valid ? k : k0], sg = i / NE, e = i - sg * NE - 3;
-            pel* seg = &sm[(4 * sg) * DBF_PITCH + DBF_HALO - 4 + 4 * e];
+            const int segOff = (4 * sg) * DBF_PITCH + DBF_HALO - 4 + 4 * e;
             uint32_t rec = ra[i];
-            if (ladf) rec = dbfLadfRecord(rec, seg, 1, DBF_PITCH, lane & 3, g.bdL, ladf);
-            dbfLumaSegmentQuad(seg, 1, DBF_PITCH, rec, maxv, lane & 3, valid && (rec & 0x7ff) != 0);
+            if (ladf) rec = dbfLadfRecordPair(rec, &sm[segOff], 1, DBF_PITCH, g.bdL, ladf);
+            uint32_t d = dbfLumaDecidePair(&sm[segOff], 1, DBF_PITCH, rec);
+            if (!valid || !(rec & 0x7ff)) d = 0;
+            // filters: a quad per segment, eight segments per sub-round
+#pragma unroll 1
+            for (int r = 0; r < 2; r++)
+            {
+              const int src = 2 * (r * 8 + (lane >> 2));
+              const uint32_t dj = __shfl_sync(0xffffffffu, d, src), recj = __shfl_sync(0xffffffffu, rec, src);
+              const int offj = __shfl_sync(0xffffffffu, segOff, src);
+              dbfLumaApplyLine(&sm[offj + (lane & 3) * DBF_PITCH], 1, recj, dj, maxv, dj != 0);
+            }
           }
         }
         __syncthreads();
         // pass 2: horizontal edges y0 .. y0+TH (step 4), columns x0-4 .. x0+TW+3
         {
           const int cnt = qcount[1];
-          for (int k0 = (tid >> 5) * 8; k0 < cnt; k0 += DBF_THREADS / 4)
+          for (int k0 = (tid >> 5) * 16; k0 < cnt; k0 += DBF_THREADS / 2)
           {
-            const int k = k0 + (lane >> 2);
+            const int k = k0 + (lane >> 1);
             const bool valid = k < cnt;
             const int i = queue2[valid ? k : k0], e = i / NSH, sg = i - e * NSH - 3;
-            pel* seg = &sm[(DBF_HALO + 4 * e) * DBF_PITCH + DBF_HALO - 4 + 4 * sg];
+            const int segOff = (DBF_HALO + 4 * e) * DBF_PITCH + DBF_HALO - 4 + 4 * sg;
             uint32_t rec = rbv[i];
-            if (ladf) rec = dbfLadfRecord(rec, seg, DBF_PITCH, 1, lane & 3, g.bdL, ladf);
-            dbfLumaSegmentQuad(seg, DBF_PITCH, 1, rec, maxv, lane & 3, valid && (rec & 0x7ff) != 0);
+            if (ladf) rec = dbfLadfRecordPair(rec, &sm[segOff], DBF_PITCH, 1, g.bdL, ladf);
+            uint32_t d = dbfLumaDecidePair(&sm[segOff], DBF_PITCH, 1, rec);
+            if (!valid || !(rec & 0x7ff)) d = 0;
+#pragma unroll 1
+            for (int r = 0; r < 2; r++)
+            {
+              const int src = 2 * (r * 8 + (lane >> 2));
+              const uint32_t dj = __shfl_sync(0xffffffffu, d, src), recj = __shfl_sync(0xffffffffu, rec, src);
+              const int offj = __shfl_sync(0xffffffffu, segOff, src);
+              dbfLumaApplyLine(&sm[offj + (lane & 3)], DBF_PITCH, recj, dj, maxv, dj != 0);
+            }
           }
         }
       }
