@@ -154,7 +154,7 @@ def test_batch_of_slots_and_rewind():
         for s in range(len(caps)):
             _eq(ctx.download(s), want[s], "slot %d rep %d" % (s, rep))
         ctx.rewind(0, len(caps))
-    assert ctx.launch_count() == 4
+    assert ctx.launch_count() == 4 + len(caps)       # two chain kernels per repetition for the whole batch + one queue build per picture when its records were set
     ctx.close()
 
 

@@ -368,6 +368,7 @@ struct DbfLaunch
   int tilesXL, tilesL;      // luma tile grid (of the rows being filtered)
   int tilesXC, tilesC;      // per chroma plane
   int ty0L, ty0C;           // first tile row (band mode: a CTU-row band of the picture; 0 for whole pictures)
+  int tilesLFull, tilesCFull;   // tiles of the WHOLE plane (the queues of a slot are indexed by picture tile: luma, Cb, Cr)
 };
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------
@@ -384,15 +385,18 @@ struct DbfLaunch
 constexpr int DBF_RECL = DBF_TW / 4 + 8;                // columns of the luma record boxes (40 at tile width 128)
 constexpr int DBF_RECC = DBF_TW / 8 + 2;                // columns of the chroma vertical-edge record box (18)
 constexpr int dbfMax(int a, int b) { return a > b ? a : b; }
-constexpr int dbfUp128(int v) { return (v + 127) / 128 * 128; }
-// pass-1 records of a tile: luma RECL x 20 u32, chroma RECC x 40 u64 (4:2:0); pass-2: luma RECL x 17 u32, chroma (TW / 2 + 4) x 9 u64 -- 5888 and 4992 bytes at width 128
-constexpr int DBF_RECA_BYTES = dbfUp128(dbfMax(DBF_RECL * (DBF_SH / 4) * 4, DBF_RECC * (DBF_SH / 2) * 8));
-constexpr int DBF_RECB_BYTES = dbfUp128(dbfMax(DBF_RECL * (DBF_TH / 4 + 1) * 4, (DBF_TW / 2 + 4) * (DBF_TH / 8 + 1) * 8));
+constexpr int dbfUp16(int v) { return (v + 15) / 16 * 16; }
+// Per-tile queues of the ACTIVE segments, built once per picture by k_dbf_queues when the records are set (round 2: the kernel used to
+// load the record boxes of a tile and every CTA compacted them itself -- 31 % of its shared-memory fill, 8 of its 53 instructions per
+// pixel and one CTA barrier per tile).  Entry = 64 bits: the record in the low 48 bits (luma: 32), the slot index inside the tile's record
+// box in the top 16.  Capacities = every slot of a pass active (luma / chroma, whichever is larger), multiples of 16 entries.
+constexpr int DBF_QCAP1 = dbfUp16(dbfMax((DBF_TW / 4 + 3) * (DBF_SH / 4), (DBF_TW / 8 + 1) * (DBF_SH / 2)));        // 704 at width 128
+constexpr int DBF_QCAP2 = dbfUp16(dbfMax((DBF_TH / 4 + 1) * (DBF_TW / 4 + 2), (DBF_TH / 8 + 1) * (DBF_TW / 2 + 2)));    // 608
+constexpr int DBF_QTILE = DBF_QCAP1 + DBF_QCAP2;       // entries per tile in the queue memory of a slot
 constexpr int DBF_TILE_BYTES = DBF_SH * DBF_PITCH * 2;  // 24320 (multiple of 128: TMA destination)
 static_assert(DBF_TILE_BYTES % 128 == 0, "TMA destination alignment");
-constexpr int DBF_STAGE_BYTES = DBF_TILE_BYTES + DBF_RECA_BYTES + DBF_RECB_BYTES;
-constexpr int DBF_QUEUE = dbfMax(DBF_RECL * (DBF_SH / 4), DBF_RECC * (DBF_SH / 2)) + 32;     // queue entries per pass (>= record slots of a pass)
-constexpr int DBF_SMEM_BYTES = 2 * DBF_STAGE_BYTES + 32 + 2 * DBF_QUEUE * 2;      // stages, 2 mbarriers + 2 counters, 2 queues
+constexpr int DBF_STAGE_BYTES = DBF_TILE_BYTES + DBF_QTILE * 8;
+constexpr int DBF_SMEM_BYTES = 2 * DBF_STAGE_BYTES + 32;      // stages, 2 mbarriers + the queue lengths of the two stages (4 x uint16... as 4 ints)
 
 // record boxes of one tile (columns x rows, in records) for the arrays lumaV, lumaH, chromaV, chromaH.  TMA wants the first
 // element of a box row on a 16-byte boundary and the row length a multiple of 16 bytes, so the luma boxes start 4 records
@@ -452,62 +456,99 @@ __device__ __forceinline__ DbfPassGeom dbfPassGeom(int comp, const Geom& g)
   return P;
 }
 
-// CTA-wide compaction: all warps scan the n record slots of a pass (chunks of 32, interleaved over the warps) and append the
-// indices of the active ones (typically < 10 % of the slots) to one queue -- one shared-memory atomic per warp and chunk --
-// so that the filters run on full warps and every warp gets the same share.  *count must be 0 on entry.
-template <class RecT, class Active> __device__ __forceinline__ void dbfCompact(const RecT* rec, int n, uint16_t* q, int* count, Active act)
+// picture tile number of a tile (luma tiles, then Cb, then Cr) = index of its queues
+__device__ __forceinline__ int dbfQueueTile(const DbfTile& T, const DbfLaunch& L)
 {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i0 = warp * 32; i0 < n; i0 += DBF_THREADS)
-  {
-    const int i = i0 + lane;
-    const bool a = i < n && act(rec[i], i);
-    const unsigned m = __ballot_sync(0xffffffffu, a);
-    if (m == 0) continue;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(count, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (a) q[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)i;
-  }
+  const int tx = T.x0 / DBF_TW, ty = T.y0 / DBF_TH;
+  if (T.comp == 0) return ty * L.tilesXL + tx;
+  return L.tilesLFull + (T.comp - 1) * L.tilesCFull + ty * L.tilesXC + tx;
 }
 
-// issues the asynchronous loads of one tile into a stage (one thread): three TMA boxes on one mbarrier -- the samples
-// (tile + 8 halo) and the segment records of the two passes.  Everything outside the picture arrives as zeros = "no edge".
-__device__ __forceinline__ void dbfPrefetch(unsigned char* stageMem, uint64_t* bar, const CUtensorMap* planeMap, const CUtensorMap* recMaps, const DbfTile& T,
-                                            const Geom& g, bool dbfOn)
+// Builds the queues of one slot from its record arrays (after any of the three producers: uploaded arrays, scattered lists, k_dbf_derive):
+// one warp per (tile, pass) scans the record slots the tile evaluates -- the box the kernel used to load: tile + the halo the passes
+// are evaluated on, slot index i = row * box pitch + column as before -- and appends the active ones in ascending order.
+struct DbfQueueArgs
 {
-  if (threadIdx.x != 0) return;
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  const DbfRecBoxes RB = dbfRecBoxes(g.sx, g.sy);
-  const int a = T.comp ? 2 : 0, words = T.comp ? 2 : 1;
-  const uint32_t recBytes = dbfOn ? (uint32_t)(RB.cols[a] * RB.rows[a] + RB.cols[a + 1] * RB.rows[a + 1]) * words * 4 : 0u;
-  mbarExpectTx(bar, DBF_TILE_BYTES + recBytes);
-  tmaLoad2D(stageMem, planeMap, T.x0 - DBF_HALO, T.y0 - DBF_HALO, bar);
-  if (!dbfOn) return;
-  if (T.comp == 0)
+  const uint32_t* lumaRec[2];
+  const uint64_t* chromaRec[2];
+  int recW[4], recH[4], recP[4];
+  uint64_t* q;              // [tiles][DBF_QTILE]
+  uint32_t* cnt;            // [tiles][2]
+  DbfLaunch L;              // whole picture
+  int sx, sy, ncomp;
+};
+
+__global__ void __launch_bounds__(256) k_dbf_queues(const DbfQueueArgs A)
+{
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int tiles = A.L.tilesLFull + (A.ncomp > 1 ? 2 * A.L.tilesCFull : 0);
+  if (warp >= 2 * tiles) return;
+  const int tile = warp >> 1, pass = warp & 1;
+  int comp = 0, t = tile;
+  if (t >= A.L.tilesLFull) { t -= A.L.tilesLFull; comp = 1; if (t >= A.L.tilesCFull) { t -= A.L.tilesCFull; comp = 2; } }
+  const int tilesX = comp ? A.L.tilesXC : A.L.tilesXL, ty = t / tilesX, x0 = (t - ty * tilesX) * DBF_TW, y0 = ty * DBF_TH;
+  // box of the pass in the record array: origin (c0, r0), pitch p, rows n, used columns [u0, u1)
+  int a, c0, r0, p, n, u0, u1;
+  if (comp == 0)
   {
-    tmaLoad2D(stageMem + DBF_TILE_BYTES, recMaps + 0, (T.x0 >> 2) - 4, (T.y0 - DBF_HALO) >> 2, bar);
-    tmaLoad2D(stageMem + DBF_TILE_BYTES + DBF_RECA_BYTES, recMaps + 1, (T.x0 >> 2) - 4, T.y0 >> 2, bar);
+    a = pass; p = DBF_RECL; c0 = (x0 >> 2) - 4;
+    if (pass == 0) { r0 = (y0 - DBF_HALO) >> 2; n = DBF_SH / 4; u0 = 3; u1 = 3 + DBF_TW / 4 + 3; }
+    else           { r0 = y0 >> 2; n = DBF_TH / 4 + 1; u0 = 3; u1 = 3 + DBF_TW / 4 + 2; }
   }
   else
   {
-    // x0,y0 in chroma samples; record arrays are indexed in luma units (include/vtmgpu.h); a record = 2 words
-    const int nvLog = 2 - g.sy, nhLog = 2 - g.sx;
-    tmaLoad2D(stageMem + DBF_TILE_BYTES, recMaps + 2, (T.x0 >> 3) * 2, (T.y0 - DBF_HALO) >> nvLog, bar);
-    tmaLoad2D(stageMem + DBF_TILE_BYTES + DBF_RECA_BYTES, recMaps + 3, ((T.x0 >> nhLog) - 2) * 2, T.y0 >> 3, bar);
+    const int nvLog = 2 - A.sy, nhLog = 2 - A.sx, nh = 4 >> A.sx;
+    a = 2 + pass;
+    if (pass == 0) { p = DBF_RECC; c0 = x0 >> 3; r0 = (y0 - DBF_HALO) >> nvLog; n = DBF_SH >> nvLog; u0 = 0; u1 = DBF_RECC - 1; }
+    else           { const int ns2 = DBF_TW / nh + 2; p = ns2 + 2; c0 = (x0 >> nhLog) - 2; r0 = y0 >> 3; n = DBF_TH / 8 + 1; u0 = 1; u1 = 1 + ns2; }
   }
+  const int tcShift = comp == 2 ? VTMGPU_DBF_C_TCCR_SHIFT : 0;
+  uint64_t* q = A.q + (size_t)tile * DBF_QTILE + (pass ? DBF_QCAP1 : 0);
+  int count = 0;
+  const int slots = n * p;
+  for (int i0 = 0; i0 < slots; i0 += 32)
+  {
+    const int i = i0 + lane, r = i / p, c = i - r * p;
+    uint64_t rec = 0;
+    if (i < slots && c >= u0 && c < u1)
+    {
+      const int row = r0 + r, col = c0 + c;
+      if (row >= 0 && row < A.recH[a] && col >= 0 && col < A.recW[a])
+      {
+        if (comp == 0) rec = A.lumaRec[pass][(size_t)row * A.recP[a] + col];
+        else           rec = A.chromaRec[pass][(size_t)row * A.recP[a] + col];
+      }
+    }
+    const bool act = ((rec >> tcShift) & 0x7ff) != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, act);
+    if (act) q[count + __popc(m & ((1u << lane) - 1))] = (rec & 0xffffffffffffull) | (uint64_t)i << 48;
+    count += __popc(m);
+  }
+  if (lane == 0) A.cnt[tile * 2 + pass] = (uint32_t)count;
+}
+
+// issues the asynchronous loads of one tile into a stage (one thread): the samples (tile + 8 halo, zero filled outside the picture) by
+// one TMA box and the two queues of its active segments by bulk copies (their lengths were read one tile earlier), all on one mbarrier
+__device__ __forceinline__ void dbfPrefetch(unsigned char* stageMem, uint64_t* bar, int* stageCnt, const CUtensorMap* planeMap, const uint64_t* q, int n1, int n2, const DbfTile& T)
+{
+  stageCnt[0] = n1; stageCnt[1] = n2;                       // published by the release of the arrive below
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  const uint32_t b1 = (uint32_t)((n1 + 1) & ~1) * 8, b2 = (uint32_t)((n2 + 1) & ~1) * 8;      // whole 16-byte units
+  mbarExpectTx(bar, DBF_TILE_BYTES + b1 + b2);
+  tmaLoad2D(stageMem, planeMap, T.x0 - DBF_HALO, T.y0 - DBF_HALO, bar);
+  if (b1) bulkLoad(stageMem + DBF_TILE_BYTES, q, b1, bar);
+  if (b2) bulkLoad(stageMem + DBF_TILE_BYTES + DBF_QCAP1 * 8, q + DBF_QCAP1, b2, bar);
 }
 
 // maps = TMA descriptors of the plane buffers: [slot][3 buffers][3 planes], box = DBF_PITCH x DBF_SH samples
-__global__ void __launch_bounds__(DBF_THREADS, DBF_CTAS_PER_SM) k_dbf_sao(const SlotDev* __restrict__ slots, const CUtensorMap* __restrict__ tmaps, const CUtensorMap* __restrict__ recMaps,
+__global__ void __launch_bounds__(DBF_THREADS, DBF_CTAS_PER_SM) k_dbf_sao(const SlotDev* __restrict__ slots, const CUtensorMap* __restrict__ tmaps,
                                                              int firstSlot, int numSlots, int srcBuf, int dstBuf, Geom g, DbfLaunch L, TileStep step, int doDbf, int doSao,
                                                              const BandDev band)
 {
   extern __shared__ __align__(128) unsigned char smraw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + 2 * DBF_STAGE_BYTES);
   const int tid = threadIdx.x, lane = tid & 31;
-  int* qcount = reinterpret_cast<int*>(smraw + 2 * DBF_STAGE_BYTES + 16);          // [2]
-  uint16_t* queue1 = reinterpret_cast<uint16_t*>(smraw + 2 * DBF_STAGE_BYTES + 32), *queue2 = queue1 + DBF_QUEUE;
+  int* stageCnt = reinterpret_cast<int*>(smraw + 2 * DBF_STAGE_BYTES + 16);        // [stage][2]: queue lengths of the tile in the stage
   const int itemsPerSlot = L.tilesL + 2 * L.tilesC;
   int slot = blockIdx.x / itemsPerSlot, item = blockIdx.x - slot * itemsPerSlot;
   if (slot >= numSlots) return;
@@ -516,13 +557,24 @@ __global__ void __launch_bounds__(DBF_THREADS, DBF_CTAS_PER_SM) k_dbf_sao(const 
     mbarInit(&bars[0], 1);
     mbarInit(&bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    qcount[0] = qcount[1] = 0;
   }
   __syncthreads();
   DbfTile T = dbfDecodeTile(item, L), Tn = T;
+  // queue lengths of a tile (thread 0): loaded one tile before the tile's loads are issued, i.e. two tiles ahead of its filtering
+  auto queueLengths = [&](int sl, const DbfTile& t) -> uint2 {
+    const SlotDev& Sq = slots[firstSlot + sl];
+    if (!(doDbf && Sq.dbfOn)) return make_uint2(0u, 0u);
+    return __ldg(reinterpret_cast<const uint2*>(Sq.dbfQCnt) + dbfQueueTile(t, L));
+  };
+  uint2 cntN = make_uint2(0u, 0u);             // lengths for the tile whose loads the NEXT iteration issues
+  if (tid == 0)
   {
     const SlotDev& S = slots[firstSlot + slot];
-    dbfPrefetch(smraw, &bars[0], tmaps + ((size_t)(firstSlot + slot) * 3 + srcBuf) * 3 + T.comp, recMaps + (size_t)(firstSlot + slot) * 4, T, g, doDbf && S.dbfOn);
+    const uint2 c0 = queueLengths(slot, T);
+    dbfPrefetch(smraw, &bars[0], stageCnt, tmaps + ((size_t)(firstSlot + slot) * 3 + srcBuf) * 3 + T.comp, S.dbfQ + (size_t)dbfQueueTile(T, L) * DBF_QTILE, (int)c0.x, (int)c0.y, T);
+    int s1 = slot + step.dSlot, i1 = item + step.dItem;
+    if (i1 >= itemsPerSlot) { i1 -= itemsPerSlot; s1++; }
+    if (s1 < numSlots) cntN = queueLengths(s1, dbfDecodeTile(i1, L));
   }
   for (uint32_t it = 0; slot < numSlots; it++)
   {
@@ -533,10 +585,16 @@ __global__ void __launch_bounds__(DBF_THREADS, DBF_CTAS_PER_SM) k_dbf_sao(const 
     if (nitem >= itemsPerSlot) { nitem -= itemsPerSlot; nslot++; }
     if (nslot < numSlots)
     {
-      const SlotDev& Sn = slots[firstSlot + nslot];
       Tn = dbfDecodeTile(nitem, L);
-      dbfPrefetch(smraw + (stage ^ 1) * DBF_STAGE_BYTES, &bars[stage ^ 1], tmaps + ((size_t)(firstSlot + nslot) * 3 + srcBuf) * 3 + Tn.comp,
-                  recMaps + (size_t)(firstSlot + nslot) * 4, Tn, g, doDbf && Sn.dbfOn);
+      if (tid == 0)
+      {
+        const SlotDev& Sn = slots[firstSlot + nslot];
+        dbfPrefetch(smraw + (stage ^ 1) * DBF_STAGE_BYTES, &bars[stage ^ 1], stageCnt + 2 * (stage ^ 1), tmaps + ((size_t)(firstSlot + nslot) * 3 + srcBuf) * 3 + Tn.comp,
+                    Sn.dbfQ + (size_t)dbfQueueTile(Tn, L) * DBF_QTILE, (int)cntN.x, (int)cntN.y, Tn);
+        int s2 = nslot + step.dSlot, i2 = nitem + step.dItem;
+        if (i2 >= itemsPerSlot) { i2 -= itemsPerSlot; s2++; }
+        cntN = s2 < numSlots ? queueLengths(s2, dbfDecodeTile(i2, L)) : make_uint2(0u, 0u);
+      }
     }
 
     const int comp = T.comp, x0 = T.x0, y0 = T.y0;
@@ -578,25 +636,23 @@ __global__ void __launch_bounds__(DBF_THREADS, DBF_CTAS_PER_SM) k_dbf_sao(const 
       const LadfDev* const ladf = S.ladf.n > 0 ? &S.ladf : nullptr;
       if (comp == 0)
       {
-        const uint32_t* ra = reinterpret_cast<const uint32_t*>(stageMem + DBF_TILE_BYTES);
-        const uint32_t* rbv = reinterpret_cast<const uint32_t*>(stageMem + DBF_TILE_BYTES + DBF_RECA_BYTES);
-        // both passes are compacted up front (the records are resident); then 8 segments per warp round, one line per lane
-        constexpr int NE = DBF_RECL, NEU = DBF_TW / 4 + 3;     // box pitch, edges used (box columns 3 .. 3+NEU-1)
-        constexpr int NSH = DBF_RECL, NSU = DBF_TW / 4 + 2;
-        dbfCompact(ra, P.n1, queue1, &qcount[0], [](uint32_t r, int i) { return (r & 0x7ff) != 0 && (unsigned)(i % NE - 3) < (unsigned)NEU; });
-        dbfCompact(rbv, P.n2, queue2, &qcount[1], [](uint32_t r, int i) { return (r & 0x7ff) != 0 && (unsigned)(i % NSH - 3) < (unsigned)NSU; });
-        __syncthreads();
+        const uint64_t* qa = reinterpret_cast<const uint64_t*>(stageMem + DBF_TILE_BYTES);
+        const uint64_t* qb = qa + DBF_QCAP1;
+        // 16 segments per warp round: decisions by lane pairs, filters by quads
+        constexpr int NE = DBF_RECL;                            // pitch of the slot numbering (record box columns; edge e sits in column e + 3)
+        constexpr int NSH = DBF_RECL;
         // pass 1: vertical edges x0-4 .. x0+TW+4 (step 4), all rows of tile + halo
         {
-          const int cnt = qcount[0];
+          const int cnt = stageCnt[2 * stage];
           for (int k0 = (tid >> 5) * 16; k0 < cnt; k0 += DBF_THREADS / 2)
           {
             // decisions: a lane pair per segment
             const int k = k0 + (lane >> 1);
             const bool valid = k < cnt;
-            const int i = queue1[valid ? k : k0], sg = i / NE, e = i - sg * NE - 3;
+            const uint64_t ent = qa[valid ? k : k0];
+            const int i = (int)(ent >> 48), sg = i / NE, e = i - sg * NE - 3;
             const int segOff = (4 * sg) * DBF_PITCH + DBF_HALO - 4 + 4 * e;
-            uint32_t rec = ra[i];
+            uint32_t rec = (uint32_t)ent;
             if (ladf) rec = dbfLadfRecordPair(rec, &sm[segOff], 1, DBF_PITCH, g.bdL, ladf);
             uint32_t d = dbfLumaDecidePair(&sm[segOff], 1, DBF_PITCH, rec);
             if (!valid || !(rec & 0x7ff)) d = 0;
@@ -614,14 +670,15 @@ __global__ void __launch_bounds__(DBF_THREADS, DBF_CTAS_PER_SM) k_dbf_sao(const 
         __syncthreads();
         // pass 2: horizontal edges y0 .. y0+TH (step 4), columns x0-4 .. x0+TW+3
         {
-          const int cnt = qcount[1];
+          const int cnt = stageCnt[2 * stage + 1];
           for (int k0 = (tid >> 5) * 16; k0 < cnt; k0 += DBF_THREADS / 2)
           {
             const int k = k0 + (lane >> 1);
             const bool valid = k < cnt;
-            const int i = queue2[valid ? k : k0], e = i / NSH, sg = i - e * NSH - 3;
+            const uint64_t ent = qb[valid ? k : k0];
+            const int i = (int)(ent >> 48), e = i / NSH, sg = i - e * NSH - 3;
             const int segOff = (DBF_HALO + 4 * e) * DBF_PITCH + DBF_HALO - 4 + 4 * sg;
-            uint32_t rec = rbv[i];
+            uint32_t rec = (uint32_t)ent;
             if (ladf) rec = dbfLadfRecordPair(rec, &sm[segOff], DBF_PITCH, 1, g.bdL, ladf);
             uint32_t d = dbfLumaDecidePair(&sm[segOff], DBF_PITCH, 1, rec);
             if (!valid || !(rec & 0x7ff)) d = 0;
@@ -638,21 +695,18 @@ __global__ void __launch_bounds__(DBF_THREADS, DBF_CTAS_PER_SM) k_dbf_sao(const 
       }
       else
       {
-        const uint64_t* ra = reinterpret_cast<const uint64_t*>(stageMem + DBF_TILE_BYTES);
-        const uint64_t* rbv = reinterpret_cast<const uint64_t*>(stageMem + DBF_TILE_BYTES + DBF_RECA_BYTES);
+        const uint64_t* qa = reinterpret_cast<const uint64_t*>(stageMem + DBF_TILE_BYTES);
+        const uint64_t* qb = qa + DBF_QCAP1;
         const int c = comp - 1;
         const int tcShift = c ? VTMGPU_DBF_C_TCCR_SHIFT : 0, betaShift = c ? VTMGPU_DBF_C_BETACR_SHIFT : VTMGPU_DBF_C_BETACB_SHIFT;
-        const int p2 = P.p2, ns2 = P.ns2;
-        dbfCompact(ra, P.n1, queue1, &qcount[0], [tcShift](uint64_t r, int i) { return ((r >> tcShift) & 0x7ff) != 0 && (i % DBF_RECC) < DBF_RECC - 1; });
-        dbfCompact(rbv, P.n2, queue2, &qcount[1], [tcShift, p2, ns2](uint64_t r, int i) { return ((r >> tcShift) & 0x7ff) != 0 && (unsigned)(i % p2 - 1) < (unsigned)ns2; });
-        __syncthreads();
+        const int p2 = P.p2;
         // pass 1: vertical edges on the 8-sample chroma grid; one item = the chroma rows of one 4-luma-row unit
         {
-          const int cnt = qcount[0];
+          const int cnt = stageCnt[2 * stage];
           for (int k = tid; k < cnt; k += DBF_THREADS)
           {
-            const int i = queue1[k], sg = i / DBF_RECC, e = i - sg * DBF_RECC;
-            const uint64_t rec = ra[i];
+            const uint64_t rec = qa[k];
+            const int i = (int)(rec >> 48), sg = i / DBF_RECC, e = i - sg * DBF_RECC;
             dbfChromaSegment(&sm[(P.nv * sg) * DBF_PITCH + DBF_HALO + 8 * e], 1, DBF_PITCH, P.nv, (int)(rec >> tcShift) & 0x7ff, (int)(rec >> betaShift) & 0x7ff,
                              (rec & VTMGPU_DBF_C_LARGE) != 0, (rec & VTMGPU_DBF_C_CTB) != 0, !(rec & VTMGPU_DBF_C_PNOFILT), !(rec & VTMGPU_DBF_C_QNOFILT), maxv);
           }
@@ -660,11 +714,11 @@ __global__ void __launch_bounds__(DBF_THREADS, DBF_CTAS_PER_SM) k_dbf_sao(const 
         __syncthreads();
         // pass 2: horizontal edges, one more segment of columns on each side of the tile
         {
-          const int cnt = qcount[1];
+          const int cnt = stageCnt[2 * stage + 1];
           for (int k = tid; k < cnt; k += DBF_THREADS)
           {
-            const int i = queue2[k], e = i / p2, sg = i - e * p2 - 1;
-            const uint64_t rec = rbv[i];
+            const uint64_t rec = qb[k];
+            const int i = (int)(rec >> 48), e = i / p2, sg = i - e * p2 - 1;
             dbfChromaSegment(&sm[(DBF_HALO + 8 * e) * DBF_PITCH + DBF_HALO - P.nh + P.nh * sg], DBF_PITCH, 1, P.nh, (int)(rec >> tcShift) & 0x7ff,
                              (int)(rec >> betaShift) & 0x7ff, (rec & VTMGPU_DBF_C_LARGE) != 0, (rec & VTMGPU_DBF_C_CTB) != 0, !(rec & VTMGPU_DBF_C_PNOFILT),
                              !(rec & VTMGPU_DBF_C_QNOFILT), maxv);
@@ -712,7 +766,6 @@ __global__ void __launch_bounds__(DBF_THREADS, DBF_CTAS_PER_SM) k_dbf_sao(const 
         }
       }
     }
-    if (tid == 0) qcount[0] = qcount[1] = 0;
     __syncthreads();                                         // the stage is free for the load after next
     slot = nslot; item = nitem; T = Tn;
   }

@@ -110,7 +110,9 @@ struct vtmgpu_ctx
   int rowBegin = 0, rowEnd = 0;         // luma rows the stage calls filter (band mode); whole picture by default
   CUtensorMap* tmapsDev = nullptr;     // [capacity][3 buffers][3 planes]: TMA descriptors of the plane buffers, box = smem tile of k_alf
   CUtensorMap* tmapsDbfDev = nullptr;  // the same planes, box = smem tile of k_dbf_sao
-  CUtensorMap* tmapsRecDev = nullptr;  // [capacity][4]: deblocking record arrays lumaV, lumaH, chromaV, chromaH as u32 tensors, box = records of one tile
+  unsigned char* dbfQueueAll = nullptr;  // per slot: [tiles][DBF_QTILE] queue entries + [tiles][2] lengths (k_dbf_queues)
+  size_t dbfQueueStride = 0;
+  DbfLaunch dbfFull{};                 // tile grid of the whole picture
 
   int fail(const char* fmt, ...)
   {
@@ -224,7 +226,7 @@ extern "C" void vtmgpu_destroy(vtmgpu_ctx* c)
   if (c->slotsDev) cudaFree(c->slotsDev);
   if (c->tmapsDev) cudaFree(c->tmapsDev);
   if (c->tmapsDbfDev) cudaFree(c->tmapsDbfDev);
-  if (c->tmapsRecDev) cudaFree(c->tmapsRecDev);
+  if (c->dbfQueueAll) cudaFree(c->dbfQueueAll);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   for (auto& e : c->stageEv) if (e) cudaEventDestroy(e);
   for (auto& e : c->mirrorEv) if (e) cudaEventDestroy(e);
@@ -323,6 +325,18 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
     a.pitchY = pitch[0]; a.pitchC = g.ncomp > 1 ? pitch[1] : 0;
     a.side = c->sideAll; a.sideStride = L.total; a.offTab = L.alfTab; a.offAlf = L.alf; a.offCtl = L.ctuCtl;
   }
+  {
+    // per-tile queues of the active deblocking segments (k_dbf_queues): tile grid of the whole picture
+    DbfLaunch& F = c->dbfFull;
+    F.tilesXL = (g.w + DBF_TW - 1) / DBF_TW; F.ty0L = 0;
+    F.tilesL = F.tilesLFull = F.tilesXL * ((g.h + DBF_TH - 1) / DBF_TH);
+    F.tilesXC = g.ncomp > 1 ? ((g.w >> g.sx) + DBF_TW - 1) / DBF_TW : 0; F.ty0C = 0;
+    F.tilesC = F.tilesCFull = g.ncomp > 1 ? F.tilesXC * (((g.h >> g.sy) + DBF_TH - 1) / DBF_TH) : 0;
+    const size_t tiles = (size_t)F.tilesLFull + 2 * F.tilesCFull;
+    c->dbfQueueStride = alignUp(tiles * DBF_QTILE * 8 + tiles * 2 * 4, 256);
+    CK(cudaMalloc((void**)&c->dbfQueueAll, c->dbfQueueStride * s.capacity), "deblocking queue memory");
+    CK(cudaMemsetAsync(c->dbfQueueAll, 0, c->dbfQueueStride * s.capacity, c->stream), "memset");
+  }
   for (int sl = 0; sl < s.capacity; sl++)
   {
     pel* mem = c->planeAll + (size_t)sl * slotElems * 3;
@@ -347,6 +361,8 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
     sd.ctuCtl = reinterpret_cast<const CtuCtlDev*>(side + L.ctuCtl);
     sd.lumaTab = reinterpret_cast<const AlfLumaEntry*>(side + L.alfTab);
     sd.lmcs = reinterpret_cast<const int16_t*>(side + L.lmcs);
+    sd.dbfQ = reinterpret_cast<const uint64_t*>(c->dbfQueueAll + (size_t)sl * c->dbfQueueStride);
+    sd.dbfQCnt = reinterpret_cast<const uint32_t*>(c->dbfQueueAll + (size_t)sl * c->dbfQueueStride + ((size_t)c->dbfFull.tilesLFull + 2 * c->dbfFull.tilesCFull) * DBF_QTILE * 8);
     sd.dbfOn = sd.saoOn = sd.alfOn = sd.lmcsOn = 0;
   }
   {
@@ -378,26 +394,6 @@ extern "C" int vtmgpu_create(const vtmgpu_seq_params* seq, vtmgpu_ctx** out)
       CUtensorMap** dev = which ? &c->tmapsDbfDev : &c->tmapsDev;
       CK(cudaMalloc((void**)dev, maps.size() * sizeof(CUtensorMap)), "tensor maps");
       CK(cudaMemcpy(*dev, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice), "tensor maps upload");
-    }
-    {
-      // deblocking record arrays as 2-D u32 tensors (a chroma record = 2 words); box = the records one tile consumes
-      std::vector<CUtensorMap> maps((size_t)s.capacity * 4);
-      memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
-      const DbfRecBoxes RB = dbfRecBoxes(g.sx, g.sy);
-      for (int sl = 0; sl < s.capacity; sl++)
-        for (int a = 0; a < (g.ncomp > 1 ? 4 : 2); a++)
-        {
-          const int words = a < 2 ? 1 : 2;
-          void* base = c->sideDev[sl] + (a < 2 ? L.dbfL[a] : L.dbfC[a - 2]);
-          const cuuint64_t dims[2] = { (cuuint64_t)L.recW[a] * words, (cuuint64_t)L.recH[a] }, strides[1] = { (cuuint64_t)L.recP[a] * words * 4 };
-          const cuuint32_t box[2] = { (cuuint32_t)RB.cols[a] * words, (cuuint32_t)RB.rows[a] }, es[2] = { 1, 1 };
-          const CUresult r = reinterpret_cast<EncodeFn>(fn)(&maps[(size_t)sl * 4 + a], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, base, dims, strides, box, es,
-                                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-          if (r != CUDA_SUCCESS) { g_createError = "vtmgpu_create: cuTensorMapEncodeTiled (records) failed (" + std::to_string((int)r) + ")"; vtmgpu_destroy(c); return -1; }
-        }
-      CK(cudaMalloc((void**)&c->tmapsRecDev, maps.size() * sizeof(CUtensorMap)), "tensor maps");
-      CK(cudaMemcpy(c->tmapsRecDev, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice), "tensor maps upload");
     }
   }
   {
@@ -713,6 +709,22 @@ int clearBorderRecords(vtmgpu_ctx* c, int slot)
 
 // device arrays keep the ABI indexing but with a row pitch that is a multiple of 16 bytes (TMA).  direct = copy straight
 // from the caller's arrays (asynchronous when they are page-locked), else through the context's pinned staging block.
+// the per-tile queues of a slot from its record arrays (enqueued behind whatever wrote the arrays)
+int buildDbfQueues(vtmgpu_ctx* c, int slot)
+{
+  const SideLayout& L = c->lay;
+  const SlotDev& sd = c->slotsPinned[slot];
+  DbfQueueArgs A{};
+  for (int d = 0; d < 2; d++) { A.lumaRec[d] = sd.dbfL[d]; A.chromaRec[d] = sd.dbfC[d]; }
+  for (int a = 0; a < 4; a++) { A.recW[a] = L.recW[a]; A.recH[a] = L.recH[a]; A.recP[a] = L.recP[a]; }
+  A.q = const_cast<uint64_t*>(sd.dbfQ); A.cnt = const_cast<uint32_t*>(sd.dbfQCnt);
+  A.L = c->dbfFull; A.sx = c->g.sx; A.sy = c->g.sy; A.ncomp = c->g.ncomp;
+  const int warps = 2 * (A.L.tilesLFull + (A.ncomp > 1 ? 2 * A.L.tilesCFull : 0));
+  k_dbf_queues<<<(warps * 32 + 255) / 256, 256, 0, c->stream>>>(A);
+  c->launches++;
+  return c->cuda(cudaGetLastError(), "k_dbf_queues launch");
+}
+
 int setLadf(vtmgpu_ctx* c, int slot, const vtmgpu_ladf* l)
 {
   LadfDev& d = c->slotsPinned[slot].ladf;
@@ -763,6 +775,7 @@ int setDeblock(vtmgpu_ctx* c, int slot, const vtmgpu_deblock_params* p, bool dir
       }
     }
     if (clearBorderRecords(c, slot)) return -1;
+    if (buildDbfQueues(c, slot)) return -1;
   }
   return c->pushSlot(slot);
 }
@@ -935,7 +948,7 @@ extern "C" int vtmgpu_set_deblock_units(vtmgpu_ctx* c, int slot, const vtmgpu_de
   const int threads = 2 * (int)units;
   k_dbf_derive<<<(threads + 255) / 256, 256, 0, c->stream>>>(A);
   c->launches++;
-  if (c->cuda(cudaGetLastError(), "k_dbf_derive launch")) { sd.dbfOn = 0; c->pushSlot(slot); return -1; }
+  if (c->cuda(cudaGetLastError(), "k_dbf_derive launch") || buildDbfQueues(c, slot)) { sd.dbfOn = 0; c->pushSlot(slot); return -1; }
   return c->pushSlot(slot);
 }
 
@@ -1015,6 +1028,7 @@ extern "C" int vtmgpu_set_deblock_sparse(vtmgpu_ctx* c, int slot, const vtmgpu_d
     if (c->cuda(cudaGetLastError(), "k_dbf_scatter launch")) return -1;
     c->launches++;
   }
+  if (buildDbfQueues(c, slot)) return -1;
   c->slotsPinned[slot].dbfOn = 1;
   if (setLadf(c, slot, p->ladf)) return -1;
   return c->pushSlot(slot);
@@ -1413,6 +1427,7 @@ int launchDbfSao(vtmgpu_ctx* c, int first, int count, int doDbf, int doSao)
   L.tilesXC = g.ncomp > 1 ? ((g.w >> g.sx) + DBF_TW - 1) / DBF_TW : 0;
   L.ty0C = (c->rowBegin >> g.sy) / DBF_TH;
   L.tilesC = g.ncomp > 1 ? L.tilesXC * (((c->rowEnd >> g.sy) + DBF_TH - 1) / DBF_TH - L.ty0C) : 0;
+  L.tilesLFull = c->dbfFull.tilesLFull; L.tilesCFull = c->dbfFull.tilesCFull;
   return forRuns(c, first, count, [&](int s, int n, int src) {
     const int dst = src == 1 ? 2 : 1;
     // persistent CTAs: three per SM, each walks the plane tiles round robin with double-buffered TMA loads
@@ -1420,7 +1435,7 @@ int launchDbfSao(vtmgpu_ctx* c, int first, int count, int doDbf, int doSao)
     TileStep st;
     st.dSlot = grid / items;
     st.dItem = grid % items;
-    k_dbf_sao<<<grid, DBF_THREADS, DBF_SMEM_BYTES, c->stream>>>(c->slotsDev, c->tmapsDbfDev, c->tmapsRecDev, s, n, src, dst, g, L, st, doDbf, doSao, c->bandCall ? c->band : BandDev{});
+    k_dbf_sao<<<grid, DBF_THREADS, DBF_SMEM_BYTES, c->stream>>>(c->slotsDev, c->tmapsDbfDev, s, n, src, dst, g, L, st, doDbf, doSao, c->bandCall ? c->band : BandDev{});
     c->launches++;
     for (int i = s; i < s + n; i++) c->cur[i] = dst;
     return c->cuda(cudaGetLastError(), "k_dbf_sao launch");

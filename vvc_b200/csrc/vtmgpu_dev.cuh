@@ -99,6 +99,8 @@ struct SlotDev
   PlaneDev buf[3][3];            // [buffer][component]; buffer 0 = pristine upload, 1/2 = working
   const uint32_t* dbfL[2];
   const uint64_t* dbfC[2];
+  const uint64_t* dbfQ;          // per picture tile (luma, Cb, Cr) the queues of the active segments of both passes (k_dbf_queues, dbf_kernel.cuh)
+  const uint32_t* dbfQCnt;       // [tiles][2] their lengths
   const SaoDev*   sao;           // [ctus][3]                     (NULL: stage off)
   const AlfDev*   alf;           // [ALF_MAX_GROUPS]              (NULL: stage off)
   const CtuCtlDev* ctuCtl;       // [ctus]
