@@ -644,11 +644,13 @@ __global__ void __launch_bounds__(DBF_THREADS, DBF_CTAS_PER_SM) k_dbf_sao(const 
         // pass 1: vertical edges x0-4 .. x0+TW+4 (step 4), all rows of tile + halo
         {
           const int cnt = stageCnt[2 * stage];
-          for (int k0 = (tid >> 5) * 16; k0 < cnt; k0 += DBF_THREADS / 2)
+          // few segments (the usual case: ~60 per pass and tile): eight per warp round so that all warps take part; many: sixteen
+          const int per = cnt > 8 * (DBF_THREADS / 32) ? 16 : 8;
+          for (int k0 = (tid >> 5) * per; k0 < cnt; k0 += (DBF_THREADS / 32) * per)
           {
             // decisions: a lane pair per segment
             const int k = k0 + (lane >> 1);
-            const bool valid = k < cnt;
+            const bool valid = k < cnt && (lane >> 1) < per;
             const uint64_t ent = qa[valid ? k : k0];
             const int i = (int)(ent >> 48), sg = i / NE, e = i - sg * NE - 3;
             const int segOff = (4 * sg) * DBF_PITCH + DBF_HALO - 4 + 4 * e;
@@ -658,7 +660,7 @@ __global__ void __launch_bounds__(DBF_THREADS, DBF_CTAS_PER_SM) k_dbf_sao(const 
             if (!valid || !(rec & 0x7ff)) d = 0;
             // filters: a quad per segment, eight segments per sub-round
 #pragma unroll 1
-            for (int r = 0; r < 2; r++)
+            for (int r = 0; r < (per >> 3); r++)
             {
               const int src = 2 * (r * 8 + (lane >> 2));
               const uint32_t dj = __shfl_sync(0xffffffffu, d, src), recj = __shfl_sync(0xffffffffu, rec, src);
@@ -671,10 +673,11 @@ __global__ void __launch_bounds__(DBF_THREADS, DBF_CTAS_PER_SM) k_dbf_sao(const 
         // pass 2: horizontal edges y0 .. y0+TH (step 4), columns x0-4 .. x0+TW+3
         {
           const int cnt = stageCnt[2 * stage + 1];
-          for (int k0 = (tid >> 5) * 16; k0 < cnt; k0 += DBF_THREADS / 2)
+          const int per = cnt > 8 * (DBF_THREADS / 32) ? 16 : 8;
+          for (int k0 = (tid >> 5) * per; k0 < cnt; k0 += (DBF_THREADS / 32) * per)
           {
             const int k = k0 + (lane >> 1);
-            const bool valid = k < cnt;
+            const bool valid = k < cnt && (lane >> 1) < per;
             const uint64_t ent = qb[valid ? k : k0];
             const int i = (int)(ent >> 48), e = i / NSH, sg = i - e * NSH - 3;
             const int segOff = (DBF_HALO + 4 * e) * DBF_PITCH + DBF_HALO - 4 + 4 * sg;
@@ -683,7 +686,7 @@ __global__ void __launch_bounds__(DBF_THREADS, DBF_CTAS_PER_SM) k_dbf_sao(const 
             uint32_t d = dbfLumaDecidePair(&sm[segOff], DBF_PITCH, 1, rec);
             if (!valid || !(rec & 0x7ff)) d = 0;
 #pragma unroll 1
-            for (int r = 0; r < 2; r++)
+            for (int r = 0; r < (per >> 3); r++)
             {
               const int src = 2 * (r * 8 + (lane >> 2));
               const uint32_t dj = __shfl_sync(0xffffffffu, d, src), recj = __shfl_sync(0xffffffffu, rec, src);
