@@ -506,23 +506,33 @@ __global__ void __launch_bounds__(256) k_dbf_queues(const DbfQueueArgs A)
   uint64_t* q = A.q + (size_t)tile * DBF_QTILE + (pass ? DBF_QCAP1 : 0);
   int count = 0;
   const int slots = n * p;
-  for (int i0 = 0; i0 < slots; i0 += 32)
+  for (int i0 = 0; i0 < slots; i0 += 128)
   {
-    const int i = i0 + lane, r = i / p, c = i - r * p;
-    uint64_t rec = 0;
-    if (i < slots && c >= u0 && c < u1)
+    // four chunks of 32 slots at a time: the loads are independent of each other (the kernel is all load latency)
+    uint64_t rec[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
     {
-      const int row = r0 + r, col = c0 + c;
-      if (row >= 0 && row < A.recH[a] && col >= 0 && col < A.recW[a])
+      const int i = i0 + 32 * u + lane, r = i / p, c = i - r * p;
+      rec[u] = 0;
+      if (i < slots && c >= u0 && c < u1)
       {
-        if (comp == 0) rec = A.lumaRec[pass][(size_t)row * A.recP[a] + col];
-        else           rec = A.chromaRec[pass][(size_t)row * A.recP[a] + col];
+        const int row = r0 + r, col = c0 + c;
+        if (row >= 0 && row < A.recH[a] && col >= 0 && col < A.recW[a])
+        {
+          if (comp == 0) rec[u] = A.lumaRec[pass][(size_t)row * A.recP[a] + col];
+          else           rec[u] = A.chromaRec[pass][(size_t)row * A.recP[a] + col];
+        }
       }
     }
-    const bool act = ((rec >> tcShift) & 0x7ff) != 0;
-    const unsigned m = __ballot_sync(0xffffffffu, act);
-    if (act) q[count + __popc(m & ((1u << lane) - 1))] = (rec & 0xffffffffffffull) | (uint64_t)i << 48;
-    count += __popc(m);
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+    {
+      const bool act = ((rec[u] >> tcShift) & 0x7ff) != 0;
+      const unsigned m = __ballot_sync(0xffffffffu, act);
+      if (act) q[count + __popc(m & ((1u << lane) - 1))] = (rec[u] & 0xffffffffffffull) | (uint64_t)(i0 + 32 * u + lane) << 48;
+      count += __popc(m);
+    }
   }
   if (lane == 0) A.cnt[tile * 2 + pass] = (uint32_t)count;
 }
