@@ -70,6 +70,15 @@ bool expandLumaSet(const short2 (*set)[12], AlfLumaEntry* out)
 }
 }   // namespace
 
+// arguments of k_dbf_scatter (record lists -> record arrays of a slot)
+struct ScatterArgs
+{
+  const void* list[4];
+  void* dense[4];
+  uint32_t count[4], first[5];          // first[a] = number of entries before array a
+  int recW[4], recH[4], recP[4];
+};
+
 struct vtmgpu_ctx
 {
   vtmgpu_seq_params seq{};
@@ -101,6 +110,12 @@ struct vtmgpu_ctx
   pel* extendBuf = nullptr;              // picture + margins of one slot (vtmgpu_download_extended), allocated by the first call
   size_t extendElems = 0;
   std::vector<unsigned char*> sparseDev; // per slot, allocated by the first vtmgpu_set_deblock_sparse: landing area of the record lists
+  // vtmgpu_set_deblock_sparse only enqueues the copies of the lists; the kernels that turn them into record arrays and tile queues
+  // run with the next stage call, BEHIND the uploads of the small side information (flush).  The copy engine takes the H2D
+  // operations of all streams in issue order: a copy that waits for a kernel of its own stream holds up the plane uploads of the
+  // pictures behind it (measured: 10 of 44 ms per 64-picture batch of vtmgpu_batch_filter).
+  std::vector<ScatterArgs> sparseArgs;
+  std::vector<char> sparsePending;
   unsigned char* sidePinned = nullptr; // capacity * lay.total
   SlotDev* slotsPinned = nullptr;      // capacity entries (pinned mirror)
   SlotDev* slotsDev = nullptr;
@@ -179,6 +194,8 @@ struct vtmgpu_ctx
     return cuda(cudaMemcpyAsync(sideDev[slot] + off, pinnedSide(slot) + off, bytes, cudaMemcpyHostToDevice, stream), "side info upload");
   }
 };
+
+static int runPendingSparse(vtmgpu_ctx* c, int first, int count);
 
 // ------------------------------------------------------------------------------------------------------------
 extern "C" int vtmgpu_abi_version(void) { return VTMGPU_ABI_VERSION; }
@@ -440,7 +457,11 @@ extern "C" int vtmgpu_upload_async(vtmgpu_ctx* c, int slot, const int16_t* const
   {
     if (!plane[k]) return c->fail("upload: plane %d is NULL", k);
     const PlaneDev& d = sd.buf[0][k];
-    if (c->cuda(cudaMemcpy2DAsync(d.p, (size_t)d.pitch * 2, plane[k], (size_t)stride[k] * 2, (size_t)d.w * 2, d.h, cudaMemcpyHostToDevice, c->stream), "upload")) return -1;
+    // rows that are contiguous on both sides (4K / 8K / 1080p: the width is a multiple of the 64-sample pitch unit) go as ONE linear
+    // copy: the copy engine moves a pitched 2D copy row by row, measurably below the PCIe rate of a linear one
+    const bool linear = d.pitch == d.w && stride[k] == (ptrdiff_t)d.w;
+    if (c->cuda(linear ? cudaMemcpyAsync(d.p, plane[k], (size_t)d.w * d.h * 2, cudaMemcpyHostToDevice, c->stream)
+                       : cudaMemcpy2DAsync(d.p, (size_t)d.pitch * 2, plane[k], (size_t)stride[k] * 2, (size_t)d.w * 2, d.h, cudaMemcpyHostToDevice, c->stream), "upload")) return -1;
   }
   c->cur[slot] = 0;
   return 0;
@@ -456,7 +477,9 @@ extern "C" int vtmgpu_download_async(vtmgpu_ctx* c, int slot, int16_t* const pla
   {
     if (!plane[k]) return c->fail("download: plane %d is NULL", k);
     const PlaneDev& d = sd.buf[c->cur[slot]][k];
-    if (c->cuda(cudaMemcpy2DAsync(plane[k], (size_t)stride[k] * 2, d.p, (size_t)d.pitch * 2, (size_t)d.w * 2, d.h, cudaMemcpyDeviceToHost, c->stream), "download")) return -1;
+    const bool linear = d.pitch == d.w && stride[k] == (ptrdiff_t)d.w;
+    if (c->cuda(linear ? cudaMemcpyAsync(plane[k], d.p, (size_t)d.w * d.h * 2, cudaMemcpyDeviceToHost, c->stream)
+                       : cudaMemcpy2DAsync(plane[k], (size_t)stride[k] * 2, d.p, (size_t)d.pitch * 2, (size_t)d.w * 2, d.h, cudaMemcpyDeviceToHost, c->stream), "download")) return -1;
   }
   return 0;
 }
@@ -745,6 +768,7 @@ int setDeblock(vtmgpu_ctx* c, int slot, const vtmgpu_deblock_params* p, bool dir
   SlotDev& sd = c->slotsPinned[slot];
   sd.dbfOn = p != nullptr;
   c->pushSlot(slot);
+  if (!c->sparsePending.empty()) c->sparsePending[slot] = 0;      // record lists given earlier are superseded
   if (setLadf(c, slot, p ? p->ladf : nullptr)) return -1;
   if (p)
   {
@@ -783,13 +807,11 @@ int setDeblock(vtmgpu_ctx* c, int slot, const vtmgpu_deblock_params* p, bool dir
 
 // scatter of the record lists into the (zeroed) record arrays of a slot: one thread per list entry.  Entries on the picture
 // border (column 0 of the vertical-edge arrays, row 0 of the horizontal-edge arrays) are dropped like clearBorderRecords does.
-struct ScatterArgs
+
+__global__ void __launch_bounds__(256) k_clear16(uint4* __restrict__ p, size_t n)
 {
-  const void* list[4];
-  void* dense[4];
-  uint32_t count[4], first[5];          // first[a] = number of entries before array a
-  int recW[4], recH[4], recP[4];
-};
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = make_uint4(0, 0, 0, 0);
+}
 
 __global__ void __launch_bounds__(256) k_dbf_scatter(ScatterArgs A)
 {
@@ -895,6 +917,7 @@ extern "C" int vtmgpu_set_deblock_units(vtmgpu_ctx* c, int slot, const vtmgpu_de
   c->mirrorWrite(slot);
   SlotDev& sd = c->slotsPinned[slot];
   sd.dbfOn = 1;
+  if (!c->sparsePending.empty()) c->sparsePending[slot] = 0;      // record lists given earlier are superseded
   if (setLadf(c, slot, p->ladf)) { sd.dbfOn = 0; c->pushSlot(slot); return -1; }
   // landing area of the tables on the device (per slot, grown on demand)
   const size_t szCu = alignUp(sizeof(vtmgpu_dbf_cu) * p->num_cus, 256), szTu = alignUp(sizeof(vtmgpu_dbf_tu) * p->num_tus, 256), szSl = alignUp(sizeof(vtmgpu_dbf_slice) * p->num_slices, 256);
@@ -957,6 +980,7 @@ extern "C" int vtmgpu_get_deblock_records(vtmgpu_ctx* c, int slot, uint32_t* con
   if (!c) return -1;
   if (!c->slotOk(slot, 1)) return c->fail("get_deblock_records: bad slot %d", slot);
   cudaSetDevice(c->seq.device);
+  if (runPendingSparse(c, slot, 1)) return -1;
   const SideLayout& L = c->lay;
   for (int a = 0; a < 4; a++)
   {
@@ -1020,18 +1044,44 @@ extern "C" int vtmgpu_set_deblock_sparse(vtmgpu_ctx* c, int slot, const vtmgpu_d
   else
     for (int a = 0; a < 4; a++)
       if (A.count[a] && c->cuda(cudaMemcpyAsync(c->sparseDev[slot] + poff[a], src[a], (size_t)A.count[a] * esz[a], cudaMemcpyHostToDevice, c->stream), "set_deblock_sparse")) return -1;
-  if (c->cuda(cudaMemsetAsync(c->sideDev[slot] + L.dbfL[0], 0, L.dbfEnd - L.dbfL[0], c->stream), "record clear")) return -1;
-  if (A.first[4])
-  {
-    const int grid = (int)std::min<uint32_t>((A.first[4] + 255) / 256, 4u * c->numSms);
-    k_dbf_scatter<<<grid, 256, 0, c->stream>>>(A);
-    if (c->cuda(cudaGetLastError(), "k_dbf_scatter launch")) return -1;
-    c->launches++;
-  }
-  if (buildDbfQueues(c, slot)) return -1;
+  if (c->sparseArgs.empty()) { c->sparseArgs.assign(c->seq.capacity, ScatterArgs{}); c->sparsePending.assign(c->seq.capacity, 0); }
+  c->sparseArgs[slot] = A;               // the kernels follow with the next stage call (runPendingSparse)
+  c->sparsePending[slot] = 1;
   c->slotsPinned[slot].dbfOn = 1;
   if (setLadf(c, slot, p->ladf)) return -1;
   return c->pushSlot(slot);
+}
+
+// the device side of vtmgpu_set_deblock_sparse for the slots [first, first + count): clear the record arrays, scatter the lists,
+// build the tile queues
+static int runPendingSparse(vtmgpu_ctx* c, int first, int count)
+{
+  if (c->sparsePending.empty()) return 0;
+  const SideLayout& L = c->lay;
+  for (int slot = first; slot < first + count; slot++)
+  {
+    if (!c->sparsePending[slot]) continue;
+    c->sparsePending[slot] = 0;
+    const ScatterArgs& A = c->sparseArgs[slot];
+    // cleared by a kernel, not by cudaMemsetAsync: the driver hands a memset of this size to a copy engine, where it sits in line
+    // with the plane copies of the other pictures (measured: 5.6 of 42 ms per 64-picture batch of vtmgpu_batch_filter)
+    {
+      uint4* const z = reinterpret_cast<uint4*>(c->sideDev[slot] + L.dbfL[0]);
+      const size_t n16 = (L.dbfEnd - L.dbfL[0]) / 16;
+      k_clear16<<<(int)std::min<size_t>((n16 + 255) / 256, 8u * c->numSms), 256, 0, c->stream>>>(z, n16);
+      if (c->cuda(cudaGetLastError(), "k_clear16 launch")) return -1;
+      c->launches++;
+    }
+    if (A.first[4])
+    {
+      const int grid = (int)std::min<uint32_t>((A.first[4] + 255) / 256, 4u * c->numSms);
+      k_dbf_scatter<<<grid, 256, 0, c->stream>>>(A);
+      if (c->cuda(cudaGetLastError(), "k_dbf_scatter launch")) return -1;
+      c->launches++;
+    }
+    if (buildDbfQueues(c, slot)) return -1;
+  }
+  return 0;
 }
 
 extern "C" int vtmgpu_set_deblock(vtmgpu_ctx* c, int slot, const vtmgpu_deblock_params* p) { return setDeblock(c, slot, p, false); }
@@ -1483,6 +1533,7 @@ int runStages(vtmgpu_ctx* c, int first, int count, int stages, bool sync, const 
       if (c->slotsPinned[sl].lmcsOn && c->cur[sl] == 0)
         return c->fail("%s: slot %d holds a reshaped-domain picture (vtmgpu_set_lmcs): the inverse mapping is part of the deblocking / SAO pass", what, sl);
   if (c->flush(first, count)) return -1;
+  if (runPendingSparse(c, first, count)) return -1;
   if (c->profiling) cudaEventRecord(c->stageEv[0], c->stream);
   if ((stages & (ST_DBF | ST_SAO)) && launchDbfSao(c, first, count, (stages & ST_DBF) != 0, (stages & ST_SAO) != 0)) return -1;
   if (c->profiling) cudaEventRecord(c->stageEv[1], c->stream);
@@ -1644,9 +1695,24 @@ extern "C" int vtmgpu_band_filter_async(vtmgpu_ctx* c, int slot)
 // ------------------------------------------------------------------------------------------------------------
 // host batches
 // ------------------------------------------------------------------------------------------------------------
+// A batch moves pictures through THREE streams -- uploads, kernels, downloads -- with events between them, over `lanes`
+// single-picture contexts that only serve as buffers:
+//   up    planes, record lists, SAO / ALF side information of picture i          (waits for the download of picture i - lanes)
+//   run   k_clear16, k_dbf_scatter, k_dbf_queues, k_dbf_sao, k_alf of picture i  (waits for its upload)
+//   down  the filtered planes                                                    (waits for its kernels)
+// Each copy engine sees ONE queue of back-to-back copies that never wait for a kernel, whatever the number of hardware queues the
+// device maps streams to.  Measured on B200, 64 4K pictures per call (tools/microbench/e2e_variants.py, event time stamps per
+// picture): the uplink is busy without a gap and bounds the call -- 0.655 ms per picture = 40 GB/s while a download (48 GB/s)
+// runs beside it, against 47 + 45 GB/s for the same bytes as two plain copy streams; copies alone 33.9 ms, with the side
+// information 36.7, with the kernels 42.3 (the earlier form, one stream per lane with upload, kernels and download in stream
+// order, measured the same 42.6 for 2, 4, 8 or 16 lanes).
 struct vtmgpu_batch
 {
   std::vector<vtmgpu_ctx*> lane;
+  std::vector<cudaEvent_t> evUp, evRun, evDown;      // per lane: upload / kernels / download of its current picture finished
+  std::vector<char> used;                            // per lane: evDown has been recorded
+  cudaStream_t up = nullptr, run = nullptr, down = nullptr;
+  int device = 0;
   std::string err;
 };
 
@@ -1655,7 +1721,11 @@ extern "C" const char* vtmgpu_batch_last_error(const vtmgpu_batch* b) { return b
 extern "C" void vtmgpu_batch_destroy(vtmgpu_batch* b)
 {
   if (!b) return;
-  for (vtmgpu_ctx* c : b->lane) vtmgpu_destroy(c);
+  cudaSetDevice(b->device);
+  for (cudaStream_t st : { b->up, b->run, b->down }) if (st) { cudaStreamSynchronize(st); }
+  for (vtmgpu_ctx* c : b->lane) { c->stream = c->ownStream; vtmgpu_destroy(c); }
+  for (auto* v : { &b->evUp, &b->evRun, &b->evDown }) for (cudaEvent_t e : *v) if (e) cudaEventDestroy(e);
+  for (cudaStream_t st : { b->up, b->run, b->down }) if (st) cudaStreamDestroy(st);
   delete b;
 }
 
@@ -1666,12 +1736,21 @@ extern "C" int vtmgpu_batch_create(const vtmgpu_seq_params* seq, int lanes, vtmg
   vtmgpu_batch* b = new vtmgpu_batch();
   vtmgpu_seq_params s = *seq;
   s.capacity = 1;
+  b->device = s.device;
   for (int k = 0; k < lanes; k++)
   {
     vtmgpu_ctx* c = nullptr;
     if (vtmgpu_create(&s, &c)) { vtmgpu_batch_destroy(b); return -1; }      // g_createError holds the reason
     b->lane.push_back(c);
   }
+  cudaSetDevice(s.device);
+  bool ok = cudaStreamCreateWithFlags(&b->up, cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&b->run, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&b->down, cudaStreamNonBlocking) == cudaSuccess;
+  b->evUp.assign(lanes, nullptr); b->evRun.assign(lanes, nullptr); b->evDown.assign(lanes, nullptr); b->used.assign(lanes, 0);
+  for (int k = 0; k < lanes && ok; k++)
+    ok = cudaEventCreateWithFlags(&b->evUp[k], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&b->evRun[k], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&b->evDown[k], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) { g_createError = std::string("vtmgpu_batch_create: ") + cudaGetErrorString(cudaGetLastError()); vtmgpu_batch_destroy(b); return -1; }
   *out = b;
   return 0;
 }
@@ -1688,19 +1767,39 @@ extern "C" int vtmgpu_batch_filter(vtmgpu_batch* b, const vtmgpu_host_picture* p
   if (!b) return -1;
   if (count < 0 || (count && !pics)) { b->err = "batch_filter: bad argument"; return -1; }
   auto lastError = [&](vtmgpu_ctx* c, int i) { b->err = "batch_filter: picture " + std::to_string(i) + ": " + c->err; return -1; };
+  cudaSetDevice(b->device);
   int rc = 0;
   for (int i = 0; i < count && !rc; i++)
   {
-    vtmgpu_ctx* c = b->lane[i % b->lane.size()];
+    const int k = i % (int)b->lane.size();
+    vtmgpu_ctx* c = b->lane[k];
     const vtmgpu_host_picture& p = pics[i];
-    // everything below only enqueues on the lane's stream; the lane's previous picture is ordered before it by the stream, and the
-    // vtmgpu_set_* calls wait (mirror events) until the side-information upload of that picture has left the pinned mirror
-    if (vtmgpu_upload_async(c, 0, p.in, p.in_stride) || vtmgpu_set_deblock_sparse(c, 0, p.deblock) || vtmgpu_set_sao(c, 0, p.sao) ||
-        vtmgpu_set_alf(c, 0, p.alf) || vtmgpu_filter_async(c, 0, 1) || vtmgpu_download_async(c, 0, p.out, p.out_stride))
-      rc = lastError(c, i);
+    // everything below only enqueues; the vtmgpu_set_* calls wait (mirror events) until the side-information upload of the lane's
+    // previous picture has left the pinned mirror
+    cudaStream_t const up = b->up;
+    c->stream = up;
+    if (b->used[k] && c->cuda(cudaStreamWaitEvent(up, b->evDown[k], 0), "batch_filter")) { rc = lastError(c, i); break; }   // the lane's buffers are free again
+#ifdef VTMGPU_BATCH_KNOBS
+    const int skip = getenv("VTMGPU_BATCH_SKIP") ? atoi(getenv("VTMGPU_BATCH_SKIP")) : 0;
+#else
+    const int skip = 0;
+#endif
+    if ((!(skip & 32) && vtmgpu_upload_async(c, 0, p.in, p.in_stride)) || (!(skip & 1) && vtmgpu_set_deblock_sparse(c, 0, p.deblock)) || vtmgpu_set_sao(c, 0, p.sao) ||
+        vtmgpu_set_alf(c, 0, p.alf) || c->flush(0, 1) || c->cuda(cudaEventRecord(b->evUp[k], up), "batch_filter"))
+    { rc = lastError(c, i); break; }
+    c->stream = b->run;
+    if (c->cuda(cudaStreamWaitEvent(b->run, b->evUp[k], 0), "batch_filter") || (!(skip & 8) && vtmgpu_filter_async(c, 0, 1)) || c->cuda(cudaEventRecord(b->evRun[k], b->run), "batch_filter"))
+    { rc = lastError(c, i); break; }
+    c->stream = b->down;
+    if (c->cuda(cudaStreamWaitEvent(b->down, b->evRun[k], 0), "batch_filter") || (!(skip & 16) && vtmgpu_download_async(c, 0, p.out, p.out_stride)) ||
+        c->cuda(cudaEventRecord(b->evDown[k], b->down), "batch_filter"))
+    { rc = lastError(c, i); break; }
+    b->used[k] = 1;
   }
-  for (vtmgpu_ctx* c : b->lane)
-    if (vtmgpu_sync(c) && !rc) rc = lastError(c, -1);
+  // every output has landed when the three streams are drained (also on the error path: nothing may still read the caller's buffers)
+  for (cudaStream_t st : { b->up, b->run, b->down })
+    if (st && cudaStreamSynchronize(st) != cudaSuccess && !rc) { b->err = std::string("batch_filter: ") + cudaGetErrorString(cudaGetLastError()); rc = -1; }
+  for (vtmgpu_ctx* c : b->lane) c->stream = c->ownStream;
   return rc;
 }
 
