@@ -360,8 +360,9 @@ int vtmgpu_set_deblock(vtmgpu_ctx* ctx, int slot, const vtmgpu_deblock_params* p
  * (and should be page-locked) until vtmgpu_sync */
 int vtmgpu_set_deblock_async(vtmgpu_ctx* ctx, int slot, const vtmgpu_deblock_params* p);
 /* the records as lists (0.1-0.2 B of upload per luma pixel instead of 0.75): the lists are read by asynchronous copies on
- * the ctx stream and scattered into the record arrays on the device; page-locked lists must stay valid until vtmgpu_sync,
- * pageable ones may be reused on return */
+ * the ctx stream and scattered into the record arrays on the device (the scatter is enqueued by the next stage call of the slot,
+ * behind the upload of the SAO / ALF side information); page-locked lists must stay valid until vtmgpu_sync, pageable ones may
+ * be reused on return */
 int vtmgpu_set_deblock_sparse(vtmgpu_ctx* ctx, int slot, const vtmgpu_deblock_sparse* p);
 /* the block structure; the tables and maps are read by asynchronous copies on the ctx stream (page-locked memory must stay valid until
  * vtmgpu_sync, pageable memory may be reused on return) and k_dbf_derive writes the record arrays on the device */
@@ -471,10 +472,12 @@ int vtmgpu_band_disconnect(vtmgpu_ctx* ctx);      /* every rank: after its last 
 
 /* ---------------------------------------------------------------------------------------------
  * host batches: the whole boundary for a run of independent pictures that live in HOST memory, in ONE call.
- * A batch object owns `lanes` single-picture contexts (each with its own CUDA stream); vtmgpu_batch_filter walks the pictures
- * round robin over the lanes -- upload of the planes, record lists, SAO / ALF parameters, the chain, download -- so that the
- * copies of one picture overlap the kernels of another, all issued by the calling thread (one issuing thread per GPU; a
- * decoder that holds several reconstructed pictures of a GOP calls this once instead of ~10 entry points per picture).
+ * A batch object owns `lanes` single-picture contexts (the buffers of the pictures in flight) and three CUDA streams -- uploads,
+ * kernels, downloads; vtmgpu_batch_filter walks the pictures round robin over the lanes -- upload of the planes, record lists,
+ * SAO / ALF parameters on the first stream, the chain on the second, the download on the third, ordered by events -- so that the
+ * copies of one picture overlap the kernels and the opposite copies of others, all issued by the calling thread (one issuing
+ * thread per GPU; a decoder that holds several reconstructed pictures of a GOP calls this once instead of ~10 entry points per
+ * picture).
  * Page-locked buffers make every copy asynchronous; pageable buffers work but serialise.  Returns when every output has landed.
  * in / out may alias (in-place, like DecLib::executeLoopFilters on the picture's reco buffer).
  * --------------------------------------------------------------------------------------------- */

@@ -108,22 +108,30 @@ __device__ __noinline__ void saReplicateBorder(pel* s, int bx0, int by0, int xlo
   const int xl = bx0 + SA_HX - margin, yt = by0 + SA_HY - margin;
   const int cols = tw + 2 * margin, rows = th + 2 * margin;
   const int nl = max(0, xlo - xl), cr = min(cols, max(0, xhi - xl));    // columns [0,nl) and [cr,cols) of the region are outside
-  for (int rr = threadIdx.x >> 5; rr < rows; rr += SA_THREADS / 32)
+  const int nTop = min(rows, max(0, ylo - yt)), rBot = min(rows, max(nTop, yhi - yt));      // rows [0,nTop) and [rBot,rows) are outside
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // rows outside the window (a handful): the whole row from the clamped row, a warp per row
+  const int nOut = nTop + rows - rBot;
+  for (int q = warp; q < nOut; q += SA_THREADS / 32)
   {
+    const int rr = q < nTop ? q : rBot + q - nTop;
     const int py = yt + rr, sy_ = min(max(py, ylo), yhi - 1);
     const pel* srow = s + (sy_ - by0) * pitch - bx0;
     pel* drow = s + (py - by0) * pitch - bx0;
-    if (py != sy_)
-    {
-      for (int cc = threadIdx.x & 31; cc < cols; cc += 32) { const int px = xl + cc; drow[px] = srow[min(max(px, xlo), xhi - 1)]; }
-    }
-    else
-    {
-      const int lane = threadIdx.x & 31;
-      for (int cc = lane; cc < nl; cc += 32) drow[xl + cc] = srow[xlo];
-      for (int cc = cr + lane; cc < cols; cc += 32) drow[xl + cc] = srow[xhi - 1];
-    }
+    for (int cc = lane; cc < cols; cc += 32) { const int px = xl + cc; drow[px] = srow[min(max(px, xlo), xhi - 1)]; }
   }
+  // rows inside: only the columns outside (none for a tile that touches the top / bottom side alone), a lane per column
+  const int nCol = nl + cols - cr;
+  if (nCol > 0)
+    for (int rr = nTop + warp; rr < rBot; rr += SA_THREADS / 32)
+    {
+      pel* row = s + (yt + rr - by0) * pitch - bx0;
+      for (int k = lane; k < nCol; k += 32)
+      {
+        const bool left = k < nl;
+        row[xl + (left ? k : cr + k - nl)] = row[left ? xlo : xhi - 1];
+      }
+    }
 }
 
 // raster-scan slices (ALFProcess :478-488, padBorderPel): the CTU's top-left (bottom-right) neighbour is in another slice
@@ -1067,20 +1075,19 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
 
     const pel* const c0 = A0 + hOff;
     const int yb = (y0 + 4 * bi) & ctuMask;
-    const int vb = yb == vbL - 4 ? 1 : (yb == vbL ? 2 : 0);        // uniform per warp (two block rows)
+    const int vb = yb == vbL - 4 ? 1 : (yb == vbL ? 2 : 0);        // non-zero for a whole warp (two block rows)
+    const bool vbTile = ((y0 + 56) & ctuMask) == vbL - 4;          // the tile's block rows 14 and 15 lie at the ALF virtual boundary
 
     // ---- phase 1: Laplacian cells + vertical-pair copy (luma ALF only) -------------------------------------------------
     if (alfY)
     {
       alfBlockCellsAndCopy<SA_P, SA_CELLP>(c0, cell, vBlk + 4, bi, bj, vb == 0, gate);
-      if (vb)
+      if (vbTile && tid < 128)
       {
-#pragma unroll 1
-        for (int k = 0; k < 4; k++)
-        {
-          const int li = 2 * bi + 1 + (k >> 1), lj = 2 * bj + 1 + (k & 1);
-          cell[li][lj] = alfCellAny<SA_P>(&A0[(2 * li + SA_HY - 2) * SA_P + 2 * lj + SA_HX - 2], y0 - 2 + 2 * li, ctuMask, vbL);
-        }
+        // the 128 cells of the two block rows at the virtual boundary (rows replaced, alfCellAny), one per thread of the first four
+        // warps: left to the warp that owns those rows (four cells per thread) they made it the straggler of every such tile
+        const int li = 29 + 2 * (tid >> 6) + ((tid >> 1) & 1), lj = 2 * ((tid & 63) >> 2) + 1 + (tid & 1);
+        cell[li][lj] = alfCellAny<SA_P>(&A0[(2 * li + SA_HY - 2) * SA_P + 2 * lj + SA_HX - 2], y0 - 2 + 2 * li, ctuMask, vbL);
       }
       if (cpH >= 0) alfCopyQuad<SA_P>(A0 + cpH, V + cpV);
       if (ringI >= 0) cell[ringI][ringJ] = alfCellAny<SA_P>(&A0[(2 * ringI + SA_HY - 2) * SA_P + 2 * ringJ + SA_HX - 2], y0 - 2 + 2 * ringI, ctuMask, vbL);
