@@ -475,7 +475,8 @@ int vtmgpu_band_disconnect(vtmgpu_ctx* ctx);      /* every rank: after its last 
  * A batch object owns `lanes` single-picture contexts (the buffers of the pictures in flight) and three CUDA streams -- uploads,
  * kernels, downloads; vtmgpu_batch_filter walks the pictures round robin over the lanes -- upload of the planes, record lists,
  * SAO / ALF parameters on the first stream, the chain on the second, the download on the third, ordered by events -- so that the
- * copies of one picture overlap the kernels and the opposite copies of others, all issued by the calling thread (one issuing
+ * copies of one picture overlap the kernels and the opposite copies of others (use at least 3 lanes: the download of a picture is
+ * then aligned with the upload after next, which the PCIe link rewards), all issued by the calling thread (one issuing
  * thread per GPU; a decoder that holds several reconstructed pictures of a GOP calls this once instead of ~10 entry points per
  * picture).
  * Page-locked buffers make every copy asynchronous; pageable buffers work but serialise.  Returns when every output has landed.

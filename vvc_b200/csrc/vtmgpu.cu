@@ -1701,11 +1701,12 @@ extern "C" int vtmgpu_band_filter_async(vtmgpu_ctx* c, int slot)
 //   run   k_clear16, k_dbf_scatter, k_dbf_queues, k_dbf_sao, k_alf of picture i  (waits for its upload)
 //   down  the filtered planes                                                    (waits for its kernels)
 // Each copy engine sees ONE queue of back-to-back copies that never wait for a kernel, whatever the number of hardware queues the
-// device maps streams to.  Measured on B200, 64 4K pictures per call (tools/microbench/e2e_variants.py, event time stamps per
-// picture): the uplink is busy without a gap and bounds the call -- 0.655 ms per picture = 40 GB/s while a download (48 GB/s)
-// runs beside it, against 47 + 45 GB/s for the same bytes as two plain copy streams; copies alone 33.9 ms, with the side
-// information 36.7, with the kernels 42.3 (the earlier form, one stream per lane with upload, kernels and download in stream
-// order, measured the same 42.6 for 2, 4, 8 or 16 lanes).
+// device maps streams to, and the download of a picture is held back until the upload after it has finished so that the two
+// directions start their copies together.  Measured on B200, 64 4K pictures per call (tools/microbench/e2e_variants.py, event time
+// stamps per picture): the uplink is busy without a gap and bounds the call.  Downloads released as soon as their kernels are done
+// begin in the middle of an upload, which then runs at 40 GB/s beside the 48 GB/s download: 42.3 ms (the earlier form, one stream
+// per lane with upload, kernels and download in stream order, measured the same 42.6 for 2, 4, 8 or 16 lanes).  Aligned starts:
+// 37.3 ms, against 35.4 for the same bytes as two plain copy streams (47 + 45 GB/s) and 36.7 for this pipeline without kernels.
 struct vtmgpu_batch
 {
   std::vector<vtmgpu_ctx*> lane;
@@ -1768,34 +1769,50 @@ extern "C" int vtmgpu_batch_filter(vtmgpu_batch* b, const vtmgpu_host_picture* p
   if (count < 0 || (count && !pics)) { b->err = "batch_filter: bad argument"; return -1; }
   auto lastError = [&](vtmgpu_ctx* c, int i) { b->err = "batch_filter: picture " + std::to_string(i) + ": " + c->err; return -1; };
   cudaSetDevice(b->device);
-  int rc = 0;
+  const int lanes = (int)b->lane.size();
+#ifdef VTMGPU_BATCH_KNOBS
+  const int skip = getenv("VTMGPU_BATCH_SKIP") ? atoi(getenv("VTMGPU_BATCH_SKIP")) : 0;     // experiment build (tools/microbench/e2e_variants.py)
+#else
+  const int skip = 0;
+#endif
+  // The download of picture i is enqueued behind the upload of picture i + 1 and waits for it (and for its own kernels): a
+  // download then starts together with the upload after next instead of somewhere inside one.  Measured (e2e_variants.py): a
+  // download that begins in the middle of an upload costs the uplink 15 % of its rate for the rest of that copy (43.0 -> 37.3-39 ms
+  // per 64 pictures).  With one or two lanes the wait would serialise the lanes: the download follows its kernels directly.
+  const bool defer = lanes >= 3;
+  auto download = [&](int j, int next) -> int
+  {
+    const int kj = j % lanes;
+    vtmgpu_ctx* c = b->lane[kj];
+    c->stream = b->down;
+    if ((next >= 0 && c->cuda(cudaStreamWaitEvent(b->down, b->evUp[next % lanes], 0), "batch_filter")) ||
+        c->cuda(cudaStreamWaitEvent(b->down, b->evRun[kj], 0), "batch_filter") || (!(skip & 16) && vtmgpu_download_async(c, 0, pics[j].out, pics[j].out_stride)) ||
+        c->cuda(cudaEventRecord(b->evDown[kj], b->down), "batch_filter"))
+      return lastError(c, j);
+    b->used[kj] = 1;
+    return 0;
+  };
+  int rc = 0, issued = 0;                // issued = pictures whose upload and kernels are enqueued
   for (int i = 0; i < count && !rc; i++)
   {
-    const int k = i % (int)b->lane.size();
+    const int k = i % lanes;
     vtmgpu_ctx* c = b->lane[k];
     const vtmgpu_host_picture& p = pics[i];
     // everything below only enqueues; the vtmgpu_set_* calls wait (mirror events) until the side-information upload of the lane's
     // previous picture has left the pinned mirror
-    cudaStream_t const up = b->up;
-    c->stream = up;
-    if (b->used[k] && c->cuda(cudaStreamWaitEvent(up, b->evDown[k], 0), "batch_filter")) { rc = lastError(c, i); break; }   // the lane's buffers are free again
-#ifdef VTMGPU_BATCH_KNOBS
-    const int skip = getenv("VTMGPU_BATCH_SKIP") ? atoi(getenv("VTMGPU_BATCH_SKIP")) : 0;
-#else
-    const int skip = 0;
-#endif
+    c->stream = b->up;
+    if (b->used[k] && c->cuda(cudaStreamWaitEvent(b->up, b->evDown[k], 0), "batch_filter")) { rc = lastError(c, i); break; }   // the lane's buffers are free again
     if ((!(skip & 32) && vtmgpu_upload_async(c, 0, p.in, p.in_stride)) || (!(skip & 1) && vtmgpu_set_deblock_sparse(c, 0, p.deblock)) || vtmgpu_set_sao(c, 0, p.sao) ||
-        vtmgpu_set_alf(c, 0, p.alf) || c->flush(0, 1) || c->cuda(cudaEventRecord(b->evUp[k], up), "batch_filter"))
+        vtmgpu_set_alf(c, 0, p.alf) || c->flush(0, 1) || c->cuda(cudaEventRecord(b->evUp[k], b->up), "batch_filter"))
     { rc = lastError(c, i); break; }
     c->stream = b->run;
     if (c->cuda(cudaStreamWaitEvent(b->run, b->evUp[k], 0), "batch_filter") || (!(skip & 8) && vtmgpu_filter_async(c, 0, 1)) || c->cuda(cudaEventRecord(b->evRun[k], b->run), "batch_filter"))
     { rc = lastError(c, i); break; }
-    c->stream = b->down;
-    if (c->cuda(cudaStreamWaitEvent(b->down, b->evRun[k], 0), "batch_filter") || (!(skip & 16) && vtmgpu_download_async(c, 0, p.out, p.out_stride)) ||
-        c->cuda(cudaEventRecord(b->evDown[k], b->down), "batch_filter"))
-    { rc = lastError(c, i); break; }
-    b->used[k] = 1;
+    issued = i + 1;
+    if (!defer) rc = download(i, -1);
+    else if (i > 0) rc = download(i - 1, i);
   }
+  if (defer && issued > 0 && !rc) rc = download(issued - 1, -1);
   // every output has landed when the three streams are drained (also on the error path: nothing may still read the caller's buffers)
   for (cudaStream_t st : { b->up, b->run, b->down })
     if (st && cudaStreamSynchronize(st) != cudaSuccess && !rc) { b->err = std::string("batch_filter: ") + cudaGetErrorString(cudaGetLastError()); rc = -1; }
