@@ -556,8 +556,11 @@ void LoopFilter::loopFilterPic(CodingStructure& cs)
       // changes it (DecLib.cpp:579-580): the copies are complete when this call returns
       vtmgpu_deblock_units up = *s.units.view();
       if (motionPreloaded) { up.flags |= VTMGPU_UNITS_MOTION_PRELOADED; up.motion = nullptr; }
+      const bool motionInCall = up.motion != nullptr;      // the decoder changes its motion field right after this call returns
       s.check(s.api.set_deblock_units(s.ctx, 0, &up), "set_deblock_units");
-      s.check(s.api.sync(s.ctx), "sync");
+      // the tables live in the shim's own page-locked block, which is not written again before this picture's last download has
+      // completed: no need to wait here -- the copies and k_dbf_derive run while the host packs the SAO / ALF parameters
+      if (motionInCall || s.checkUnits) s.check(s.api.sync(s.ctx), "sync");
       if (s.checkUnits)
       {
         // the kernel's records against the CU walk's
