@@ -216,12 +216,15 @@ def test_sparse_records_equal_dense(w, h, cf, density):
     ctx.close()
 
 
-def test_host_batch_equals_oracle():
+@pytest.mark.parametrize("lanes", [1, 2, 3, 8])
+def test_host_batch_equals_oracle(lanes):
     """vtmgpu_batch_filter: a run of host pictures through the whole boundary in one C call (round robin over the lanes, more
-    pictures than lanes, pictures with stages switched off, in-place output) -- every output equals the oracle's."""
+    pictures than lanes, pictures with stages switched off, in-place output) -- every output equals the oracle's.  One and two
+    lanes take the direct download, three and more the download that waits for the next picture's upload; eight lanes > pictures."""
     caps = [synth.make_picture(448, 256, chroma_format=1, seed=40 + i, density=0.3 + 0.1 * i) for i in range(7)]
     want = [pyoracle.filter_capture(c)["final"] for c in caps]
-    batch = gpu.Batch(caps[0].seq, lanes=3)
+    pre0 = [[p.copy() for p in c.pre] for c in caps]              # picture 2 is filtered in place below
+    batch = gpu.Batch(caps[0].seq, lanes=lanes)
     pics, outs = [], []
     for i, c in enumerate(caps):
         ctus = c.sao_ctus()
@@ -239,6 +242,19 @@ def test_host_batch_equals_oracle():
     out = [np.zeros_like(p) for p in inp]
     batch.filter([gpu.host_picture(inp, out)])
     _eq(out, c.pre, "host batch, stages off")
+    # the same batch object again (the lanes' events of the previous call are all complete), page-locked buffers this time
+    import torch
+    pin = [[torch.from_numpy(p).pin_memory() for p in pl] for pl in pre0]
+    pout = [[torch.zeros_like(t).pin_memory() for t in pl] for pl in pin]
+    pics = []
+    for i, c in enumerate(caps):
+        ctus = c.sao_ctus()
+        gpu.sao_reconstruct(ctus, c.width_in_ctus, c.ncomp, c.sao_scale[0], c.sao_scale[1])
+        pics.append(gpu.host_picture([t.numpy() for t in pin[i]], [t.numpy() for t in pout[i]], gpu.sparse_records(c.dbf_luma, c.dbf_chroma, pin=True), ctus, c.alf_params()))
+    for _ in range(2):
+        batch.filter(pics)
+    for i in range(len(caps)):
+        _eq([t.numpy() for t in pout[i]], want[i], "host batch (page-locked) picture %d" % i)
     assert batch.launch_count() > 0
     batch.close()
 

@@ -95,7 +95,7 @@ __host__ __device__ inline SaLayout saLayout(int sx, int sy, int ncomp, bool tab
   L.offPar = L.offV + AV_BYTES;
   L.offBar = L.offPar + 2 * 4 * (int)sizeof(CtuCtlDev);      // per stage: the control records of the (up to 2 x 2) CTUs under the tile
   L.offDesc = L.offBar + 32;                                 // per stage: tile descriptor written by the walking thread (k_alf); bars: 2 x tile loads, cells ready, tile done
-  L.total = L.offDesc + 2 * 32;
+  L.total = L.offDesc + 2 * 48;
   return L;
 }
 
@@ -928,7 +928,16 @@ struct alignas(16) AlfTileDesc
 {
   int x0, y0, slotAbs, valid;
   uint4 ctl;                     // CtuCtlDev of the tile's CTU
+  pel* dY;                       // destination buffer of the tile's slot (the 64-bit address arithmetic is done once per tile, not per thread)
+  uint32_t border, pad;          // border: the tile touches the picture border or a clipped CTU side (samples outside must be replicated)
 };
+static_assert(sizeof(AlfTileDesc) == 48, "AlfTileDesc layout (SaLayout reserves 2 x 48 bytes)");
+
+// the tile reads samples outside the picture or across a CTU side the filter must not cross (clip byte of the control record)
+__device__ __forceinline__ uint32_t alfTileBorder(int x0, int y0, const Geom& g, uint4 ctlv)
+{
+  return x0 == 0 || y0 == 0 || x0 + SA_T + 8 > g.w || y0 + SA_TH + 8 > g.h || (ctlv.z & 0xff) != 0;
+}
 
 template <bool k420>
 __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAddr A, const CUtensorMap* __restrict__ tmaps, int firstSlot, int numSlots,
@@ -997,6 +1006,8 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
       const uint4 ctlA = alfLoadCtl(A, g, firstSlot, cur, ty0);
       if (nxt.slot < numSlots) ctlB = alfLoadCtl(A, g, firstSlot, nxt, ty0);
       desc[0].x0 = cur.tx * SA_T; desc[0].y0 = (cur.ty + ty0) * SA_TH; desc[0].slotAbs = firstSlot + cur.slot; desc[0].valid = 1; desc[0].ctl = ctlA;
+      desc[0].dY = A.planes + (size_t)(firstSlot + cur.slot) * A.slotStride + (size_t)dstBuf * A.bufStride;
+      desc[0].border = alfTileBorder(desc[0].x0, desc[0].y0, g, ctlA);
       alfBandWait(band, cur.ty, tilesY);
       alfPrefetch(smraw, L, 0, A, tmaps + ((size_t)(firstSlot + cur.slot) * 3 + srcBuf) * 3, firstSlot + cur.slot, cur, g, ncomp, sx, sy, ty0, ctlA);
     }
@@ -1021,6 +1032,8 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
         const bool more = nxt.slot < numSlots;
         AlfTileDesc& d = desc[stage ^ 1];
         d.x0 = nxt.tx * SA_T; d.y0 = (nxt.ty + ty0) * SA_TH; d.slotAbs = firstSlot + nxt.slot; d.valid = more; d.ctl = ctlB;
+        d.dY = A.planes + (size_t)(firstSlot + nxt.slot) * A.slotStride + (size_t)dstBuf * A.bufStride;
+        d.border = alfTileBorder(d.x0, d.y0, g, ctlB);
         if (more)
         {
           alfBandWait(band, nxt.ty, tilesY);
@@ -1031,11 +1044,13 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
       }
     };
     const int x0 = dsc.x, y0 = dsc.y;
-    pel* const dY = A.planes + (size_t)dsc.z * A.slotStride + (size_t)dstBuf * A.bufStride;
-    const AlfDev* const alfDev0 = reinterpret_cast<const AlfDev*>(A.side + (size_t)dsc.z * A.sideStride + A.offAlf);     // the luma sets of the picture
+    const uint4 dsc2 = *reinterpret_cast<const uint4*>(&desc[stage].dY);
+    pel* const dY = reinterpret_cast<pel*>((uint64_t)dsc2.x | (uint64_t)dsc2.y << 32);
     CtuCtlDev ctl;
     *reinterpret_cast<uint4*>(&ctl) = ctl0;
-    const AlfDev* const alfDev = alfDev0 + ctl.grp;             // chroma / CC-ALF data of the CTU's slice
+    // the picture's AlfDev records in global memory are only read on the rare paths (wide coefficients, CC-ALF filters whose
+    // coefficient sum does not fit a byte, non-4:2:0 CC-ALF): [0] holds the luma sets, [ctl.grp] the chroma / CC-ALF data of the CTU's slice
+    auto alfDevAt = [&](int grp) { return reinterpret_cast<const AlfDev*>(A.side + (size_t)dsc.z * A.sideStride + A.offAlf) + grp; };
     const bool alfOn = (ctl.flags & 1) != 0, wide = (ctl.flags & 2) != 0;
     const bool alfY = alfOn && ctl.enY != 0, alfCb = alfOn && ctl.enCb != 0, alfCr = alfOn && ctl.enCr != 0;
     const int ccCb = alfOn ? ctl.ccCb : 0, ccCr = alfOn ? ctl.ccCr : 0;
@@ -1051,7 +1066,7 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
     // tiles on the picture border: replicate the border samples into the zero-filled outside
     // (= UnitBuf::extendBorderPel of the ALF input, AdaptiveLoopFilter.cpp:411); CTU sides at a slice / tile boundary the
     // filter must not read across: the same replication at the clipped sides (:452-490)
-    if (x0 == 0 || y0 == 0 || x0 + SA_T + 8 > g.w || y0 + SA_TH + 8 > g.h || clip != 0)
+    if (dsc2.z)
     {
       const int cx0 = x0 & ~ctuMask, cy0 = y0 & ~ctuMask, cx1 = min(cx0 + g.ctu, g.w), cy1 = min(cy0 + g.ctu, g.h);
       const int xlo = (clip & VTMGPU_ALF_CLIP_LEFT) ? cx0 : 0, xhi = (clip & VTMGPU_ALF_CLIP_RIGHT) ? cx1 : g.w;
@@ -1141,13 +1156,13 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
             {
               const uint4 ck = *reinterpret_cast<const uint4*>(small->ccK[c][idc - 1]);
               const uint2 d = ck.w ? ccAlfQuadDual(l, l1, l2, l3, ck.x, ck.y, ck.z, maxcP, halfP)
-                                   : ccAlfQuad420(l, l1, l2, l3, alfDev->ccB[c][idc - 1], maxcP, halfP);
+                                   : ccAlfQuad420(l, l1, l2, l3, alfDevAt(ctl.grp)->ccB[c][idc - 1], maxcP, halfP);
               v.x = addClamp0(v.x, d.x, maxcP);
               v.y = addClamp0(v.y, d.y, maxcP);
             }
             else
             {
-              const int16_t* ccg = alfDev->cc[c][idc - 1];
+              const int16_t* ccg = alfDevAt(ctl.grp)->cc[c][idc - 1];
               const int maxc = (1 << g.bdC) - 1, half = (1 << g.bdC) >> 1;
               int res[4] = { (int)(v.x & 0xffff), (int)(v.x >> 16), (int)(v.y & 0xffff), (int)(v.y >> 16) };
               int cc[7];
@@ -1216,7 +1231,7 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
       if (lumaBlk)
       {
         pel* out = dY + (y0 + 4 * bi) * pitchY + x0 + 4 * bj;
-        if (wide)    alfLumaBlockGeneric(cell, c0, out, pitchY, bi, bj, y0 + 4 * bi, &alfDev0->luma[ctl.setIdx][0][0], ctuMask, vbL, g.bdL);
+        if (wide)    alfLumaBlockGeneric(cell, c0, out, pitchY, bi, bj, y0 + 4 * bi, &alfDevAt(0)->luma[ctl.setIdx][0][0], ctuMask, vbL, g.bdL);
         else if (vb) alfLumaBlockFast(c0, out, pitchY, e, maxvP, vb);
         else         alfLumaBlockV<ALF_BAL>(vBlk, out, pitchY, loadLumaCoef(e), maxvP);
       }
