@@ -46,6 +46,9 @@ constexpr int SA_THREADS = (SA_T / 4) * (SA_TH / 4);   // 256: one thread per 4x
 #ifndef SA_CTAS_PER_SM
 #define SA_CTAS_PER_SM 2
 #endif
+#ifndef ALF_WHATIF
+#define ALF_WHATIF 0        // timing experiments only (results are wrong): 1 no chroma, 2 no classification, 4 no phase 1, 8 no luma filter
+#endif
 #ifndef ALF_BAL
 #define ALF_BAL 2               // which adds of the luma tap run on the ALU pipe (alfLumaBlockV): bit 0 the tap sum, bit 1 clip - cur
 #endif
@@ -1094,7 +1097,7 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
     const bool vbTile = ((y0 + 56) & ctuMask) == vbL - 4;          // the tile's block rows 14 and 15 lie at the ALF virtual boundary
 
     // ---- phase 1: Laplacian cells + vertical-pair copy (luma ALF only) -------------------------------------------------
-    if (alfY)
+    if (alfY && !(ALF_WHATIF & 4))
     {
       alfBlockCellsAndCopy<SA_P, SA_CELLP>(c0, cell, vBlk + 4, bi, bj, vb == 0, gate);
       if (vbTile && tid < 128)
@@ -1114,7 +1117,7 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
     // ---- phase 2 ----------------------------------------------------------------------------------------------------
     const bool lumaBlk = alfY && x0 + 4 * bj < g.w && y0 + 4 * bi < g.h;         // the last tile of a row / column may be partial
 
-    if (ncomp > 1)
+    if (ncomp > 1 && !(ALF_WHATIF & 1))
     {
       const int qShift = 4 - sx, quads = k420 ? SA_THREADS : ((SA_T >> sx) >> 2) << (SA_THLOG - sy);
 #pragma unroll 1
@@ -1189,7 +1192,8 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
 
     mbarWait(&bars[2], it & 1);                              // the cells and the copy of this tile are complete
     const AlfLumaEntry* e = nullptr;
-    if (lumaBlk && !wide)
+    if ((ALF_WHATIF & 2) && lumaBlk && !wide) e = reinterpret_cast<const AlfLumaEntry*>(st + L.offSet) + (tid & 63);
+    if (!(ALF_WHATIF & 2) && lumaBlk && !wide)
     {
       // window = cells (2bi .. 2bi+3) x (2bj .. 2bj+3).  Blocks at the virtual boundary use 3 of the 4 cell rows and the
       // scale 96 (deriveClassificationBlk :977-1010).  Packed 16-bit sums: a cell holds at most 4 * (2^bd - 1) per direction, so
@@ -1226,7 +1230,7 @@ __global__ void __launch_bounds__(SA_THREADS, SA_CTAS_PER_SM) k_alf(const AlfAdd
     }
 
 
-    if (alfY)
+    if (alfY && !(ALF_WHATIF & 8))
     {
       if (lumaBlk)
       {
