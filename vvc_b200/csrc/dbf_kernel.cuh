@@ -1,17 +1,24 @@
-// dbf_kernel.cuh -- deblocking filter (LoopFilter::loopFilterPic, LoopFilter.cpp:145) for sm_100a.
+// dbf_kernel.cuh -- deblocking filter + SAO in one pass over the picture (sm_100a): kernel k_dbf_sao, and k_dbf_queues.
 //
-// One CTA filters one TW x TH tile of one plane, BOTH passes fused through shared memory:
-//   load (TW+16) x (TH+16) samples (8-sample aligned, 128-bit coalesced)  ->  all vertical edges of the tile incl.
-//   the 8-row halo (pass 1 of the reference)  ->  __syncthreads  ->  all horizontal edges (pass 2, which reads the
-//   V-filtered samples)  ->  store the TW x TH own region (128-bit coalesced) to the OUTPUT plane.
-// The two edges on the tile border are evaluated by both neighbouring tiles (each keeps only its own side), so no
-// inter-CTA ordering is needed and input/output planes are distinct.  Why the halo of 8 suffices: tile origins are
-// multiples of 64, every block side >= 32 samples starts on a multiple of 16, hence an edge 4 samples outside the
-// tile can modify at most 3 samples on the tile's side of it.
+//   LoopFilter::loopFilterPic (LoopFilter.cpp:145; xEdgeFilterLuma :971-1080, xEdgeFilterChroma :1246-1279, filters :1302-1555)
+//   SampleAdaptiveOffset::SAOProcess (SampleAdaptiveOffset.cpp:618; offsetBlock :293-547) -- sao_device.cuh
 //
-// Work items: one thread per 4-sample edge segment; the per-segment decisions follow xEdgeFilterLuma
-// (LoopFilter.cpp:971-1080) / xEdgeFilterChroma (:1246-1279) and the filters :1302-1555, driven by the packed
-// segment records of include/vtmgpu.h.  HBM traffic per plane: read (1 + halo) + write 1 samples, records 0.25 B/px.
+// Persistent CTAs (3 per SM, 256 threads) walk the 128 x 64 tiles of the planes of a batch of picture slots round robin.  Per tile:
+//   load     the tile + an 8-sample halo arrives by ONE TMA box (zero filled outside the picture) and the tile's two queues of ACTIVE
+//            segments by bulk copies, all on one mbarrier, issued one tile ahead (two stage buffers)
+//   pass 1   all vertical edges of tile + halo, in place in shared memory: the queue entries are handed out to the warps, a lane PAIR
+//            decides a luma segment (lines 0 and 3), a QUAD filters it (one line per lane); chroma: a thread per segment
+//   barrier
+//   pass 2   all horizontal edges on the V-filtered samples, same scheme
+//   barrier
+//   epilogue every thread: SAO of its 8 x 4 strip of the tile's OWN samples from the deblocked tile (a 128-bit copy where SAO is off),
+//            written straight to the OUTPUT plane -- each plane is read once and written once
+// The edges on a tile border are evaluated by both neighbouring tiles (each keeps only its own side), so no inter-CTA ordering is
+// needed and input / output planes are distinct.  Why the halo of 8 suffices: tile origins are multiples of 64, every block side
+// >= 32 samples starts on a multiple of 16, hence an edge 4 samples outside the tile can modify at most 3 samples on the tile's side.
+// The queues are built once per picture by k_dbf_queues (below) from the packed segment records of include/vtmgpu.h, whoever
+// produced them (uploaded arrays, scattered lists, k_dbf_derive).  HBM traffic per plane: read (1 + halo) + write 1 samples,
+// + the queue entries of the active segments.
 #pragma once
 
 #include "async_copy.cuh"
@@ -381,7 +388,7 @@ struct DbfLaunch
 //
 // Persistent CTAs walk the plane tiles of a batch of picture slots round robin (per slot: luma tiles, Cb tiles, Cr tiles).
 // While tile i is filtered, tile i+1 arrives: the samples (tile + 8 halo, zero filled outside the picture) by ONE TMA box,
-// the segment records of both passes by cp.async in exactly the order the passes consume them.
+// the queues of the active segments of both passes by bulk copies (cp.async.bulk).
 constexpr int DBF_RECL = DBF_TW / 4 + 8;                // columns of the luma record boxes (40 at tile width 128)
 constexpr int DBF_RECC = DBF_TW / 8 + 2;                // columns of the chroma vertical-edge record box (18)
 constexpr int dbfMax(int a, int b) { return a > b ? a : b; }
