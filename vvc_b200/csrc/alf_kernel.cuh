@@ -15,7 +15,7 @@
 //   VIADDMNMX.S16x2.RELU  max(min(a+b, c), 0) per lane    (__viaddmin_s16x2_relu): one instruction = subtract + clamp
 //   IDP.2A                s16 x s8 dot product into s32   (__dp2a_lo / __dp2a_hi): the ALF multiply-accumulate
 //   PRMT / SHF            16-bit lane shuffles
-// A filter tap pair costs 4 ALU-pipe + 2 FMA-pipe instructions per two pixels (scalar code: ~14 per two pixels).
+// A filter tap pair costs 3 ALU-pipe + 3 FMA-pipe instructions per two pixels (scalar code: ~14 per two pixels).
 // The 7x7 luma filter handles the rows next to the ALF virtual boundary (CTU height - 4) in the same packed loop (row offsets
 // clamped at run time); their Laplacian cells, wide coefficients and non-4:2:0 CC-ALF use the generic scalar routines in this
 // file, which follow the reference line by line.

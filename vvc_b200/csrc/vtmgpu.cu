@@ -1506,7 +1506,7 @@ int launchAlf(vtmgpu_ctx* c, int first, int count)
     bool vb = g.ctu < SA_T;                                      // tiles filtered in parts (virtual boundaries, several CTUs per tile) need a scratch copy of the tile
     for (int i = s; i < s + n; i++) vb |= (c->slotsPinned[i].vbAlf.nv | c->slotsPinned[i].vbAlf.nh) != 0;
     const int smem = vb ? SL.total + SL.lumaBytes + 2 * SL.chromaBytes : saLayout(g.sx, g.sy, g.ncomp, true).total;
-    // persistent CTAs: four per SM (register limited), each walks the tiles round robin with double-buffered TMA loads
+    // persistent CTAs: two per SM (123 registers, 108 KB of shared memory each), each walks the tiles round robin with double-buffered TMA loads
     const int grid = std::min(tilesX * tilesY * n, SA_CTAS_PER_SM * c->numSms);
     SaStep st;
     st.dx = grid % tilesX;
