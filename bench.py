@@ -563,7 +563,7 @@ def main():
             "clocks": clocks, "roofline": roofline, "gpu_launches": int(launches),
             "e2e": {"value": round(e2e_val, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": int(h2d * B), "d2h_bytes_per_step": int(d2h * B),
                     "steps": args.e2e_steps, "gpu_launches": int(e2e_launches // max(1, args.e2e_steps)),
-                    "api": "vtmgpu_batch_filter: one C call per step, %d lanes (streams), one issuing thread per GPU" % LANES,
+                    "api": "vtmgpu_batch_filter: one C call per step, %d lanes (pictures in flight), three streams (uploads / kernels / downloads), one issuing thread per GPU" % LANES,
                     "numa_node_of_rank0": numa, "deblock_records": "lists of active units", "ms_per_step": round(e2e_s * 1e3, 2),
                     "pcie_ceiling": {"value": round(ceiling, 1), "unit": "Mpixel/s", "ms_per_step": round(copy_s * 1e3, 2),
                                      "h2d_gbs": round(h2d * B / copy_s / 1e9, 1), "d2h_gbs": round(d2h * B / copy_s / 1e9, 1),
