@@ -484,7 +484,8 @@ def main():
 
     # ---- end to end through the C ABI with host buffers -------------------------------------------------------------
     # ONE C call per step (vtmgpu_batch_filter): the library walks the pictures round robin over LANES single-picture contexts
-    # (streams) -- pinned H2D of the planes, record lists, SAO / ALF parameters, the chain, pinned D2H -- issued by this thread
+    # (the pictures in flight) -- pinned H2D of the planes, record lists, SAO / ALF parameters on an upload stream, the chain on a
+    # second stream, pinned D2H on a third, ordered by events -- issued by this thread
     import ctypes as C
     from vvc_b200 import abi
     LANES = int(os.environ.get("VTMGPU_E2E_LANES", "8"))
