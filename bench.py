@@ -382,7 +382,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="pictures per step per GPU (BASELINE config 3: 64 frames)")
     ap.add_argument("--distinct", type=int, default=40, help="distinct pictures (the two committed 4K streams hold 32 + 8) replicated to fill the batch")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stress", action="store_true", help="skip the forced-on synthetic leg (N=1 only)")
     ap.add_argument("--no-decoder", action="store_true", help="skip the in-decoder leg (N=1 only)")
